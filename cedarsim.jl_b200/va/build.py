@@ -1,0 +1,104 @@
+"""Host-side build of generated model code: C prelude + gcc -> shared object (used by the CPU
+oracle and by tests that check the generator against finite differences).  The CUDA prelude
+for the same generated text lives in csrc/va_device.cuh and is compiled by NVRTC in the engine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+from typing import Optional
+
+from .compiler import CompiledModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GEN_DIR = os.path.join(os.path.dirname(_HERE), "_gen")
+HOST_CC = "/usr/bin/gcc"
+
+
+def c_prelude(nterm: int) -> str:
+    return f"""
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#define NT {nterm}
+#define VA_FN static inline
+static inline double va_limexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0) * (1.0 + x - 80.0); }}
+static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0); }}
+#define VA_SETUP_BEGIN(NAME) void NAME##_setup(const double* par_, const uint8_t* given_, double temp_c_, double gmin_, double* cache_) {{
+#define VA_SETUP_END(NAME) }}
+#define PAR(i) par_[i]
+#define GIVEN(i) (given_[i] != 0)
+#define TEMP_K (temp_c_ + 273.15)
+#define GMIN_V gmin_
+#define CACHE_ST(s, v) cache_[s] = (double)(v)
+#define VA_EVAL_BEGIN(NAME) void NAME##_eval(const double* cache_, const double* v_, double* I_, double* Q_, double* G_, double* C_) {{
+#define VA_EVAL_END(NAME) }}
+#define CACHE_LD(s) cache_[s]
+#define VT(k) v_[k]
+#define OUT_I(k, v) I_[k] = (v)
+#define OUT_Q(k, v) Q_[k] = (v)
+#define OUT_J(idx, k, l, g, c) do {{ G_[(k) * NT + (l)] = (g); C_[(k) * NT + (l)] = (c); }} while (0)
+"""
+
+
+class HostModel:
+    """A generated model compiled for the host; exposes setup/eval through ctypes."""
+
+    def __init__(self, cm: CompiledModel, so_path: str):
+        self.cm = cm
+        self.lib = C.CDLL(so_path)
+        self.setup = getattr(self.lib, cm.name + "_setup")
+        self.eval = getattr(self.lib, cm.name + "_eval")
+        self.setup_addr = C.cast(self.setup, C.c_void_p).value
+        self.eval_addr = C.cast(self.eval, C.c_void_p).value
+
+    def shape(self):
+        from ..flat import VAModelShape
+        cm = self.cm
+        return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
+                            self.setup_addr, self.eval_addr)
+
+    # convenience for tests
+    def run_setup(self, params: dict, temp_c=27.0, gmin=1e-12):
+        import numpy as np
+        cm = self.cm
+        lut = {p.lower(): i for i, p in enumerate(cm.params)}
+        par = np.zeros(max(1, len(cm.params)))
+        given = np.zeros(max(1, len(cm.params)), dtype=np.uint8)
+        for k, v in params.items():
+            par[lut[k.lower()]] = v
+            given[lut[k.lower()]] = 1
+        cache = np.zeros(max(1, cm.ncache))
+        self.setup(par.ctypes.data_as(C.POINTER(C.c_double)), given.ctypes.data_as(C.POINTER(C.c_uint8)),
+                   C.c_double(temp_c), C.c_double(gmin), cache.ctypes.data_as(C.POINTER(C.c_double)))
+        return cache
+
+    def run_eval(self, cache, v):
+        import numpy as np
+        nt = len(self.cm.terminals)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        I = np.zeros(nt); Q = np.zeros(nt); G = np.zeros((nt, nt)); Cm = np.zeros((nt, nt))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self.eval(dp(cache), dp(v), dp(I), dp(Q), dp(G), dp(Cm))
+        return I, Q, G, Cm
+
+
+def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O1") -> HostModel:
+    out_dir = out_dir or GEN_DIR
+    os.makedirs(out_dir, exist_ok=True)
+    text = c_prelude(len(cm.terminals)) + cm.source
+    key = hashlib.sha1((text + opt).encode()).hexdigest()[:16]
+    base = os.path.join(out_dir, f"{cm.name}_{key}")
+    so = base + ".so"
+    if not os.path.exists(so):
+        with open(base + ".c", "w") as f:
+            f.write(text)
+        cmd = [HOST_CC, opt, "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-w", "-o", so + ".tmp",
+               base + ".c", "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host compile of generated model failed:\n{r.stderr[:4000]}")
+        os.replace(so + ".tmp", so)
+    return HostModel(cm, so)

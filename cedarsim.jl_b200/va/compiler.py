@@ -1,0 +1,1481 @@
+"""Verilog-A -> C / CUDA C generator with staging and forward-mode AD.
+
+Semantics follow the reference's VA lowering (src/vasim.jl:128-180 contributions, :337-454
+probes / ddx / $param_given / noise / user functions, :459-492 assignment + vaconvert,
+:503-569 analog functions, :603-626 case; src/va_env.jl:35-123 math + $temperature) but the
+architecture is different: instead of tracing Dual numbers through a DAE compiler, one
+flow-sensitive abstract interpretation of the analog block emits two straight C functions
+
+  <model>_setup : everything that depends only on parameters / temperature ("static" stage).
+                  Runs once per (instance, device); values the bias-dependent code needs are
+                  written to numbered cache slots.
+  <model>_eval  : everything downstream of a V() probe ("dynamic" stage), with explicit
+                  partial derivatives carried only for the terminal voltages a value can
+                  actually depend on.  Produces per-terminal currents I, charges Q and the
+                  structurally non-zero entries of dI/dV (G) and dQ/dV (C).
+
+The same text compiles as C (CPU oracle, via va/build.py) and CUDA C (engine, via NVRTC)
+through the small macro vocabulary PAR / GIVEN / TEMP_K / GMIN_V / CACHE_ST / CACHE_LD / VT
+/ OUT_I / OUT_Q / OUT_J.
+
+MNA formulation: `I(a,b) <+ e` adds e to KCL(a) and -e to KCL(b); `ddt(q)` terms go to the
+charge vector.  Branch currents of VA devices are observables, not unknowns.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from dataclasses import dataclass, field
+from typing import Dict, FrozenSet, List, Optional, Sequence, Set, Tuple
+
+from .parser import Function, Module, parse
+from .preproc import Preprocessor
+
+
+class VACompileError(Exception):
+    pass
+
+
+NOISE_FUNCS = {"white_noise", "flicker_noise", "noise_table"}
+MATH1 = {"exp", "ln", "log", "sqrt", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh",
+         "asinh", "acosh", "atanh", "abs", "floor", "ceil", "limexp"}
+MATH2 = {"pow", "min", "max", "atan2", "hypot"}
+
+P_K, P_Q = 1.3806503e-23, 1.602176462e-19
+
+
+def _lit(x) -> str:
+    if isinstance(x, bool):
+        return "1" if x else "0"
+    if isinstance(x, int):
+        return str(x)
+    if math.isinf(x):
+        return "INFINITY" if x > 0 else "(-INFINITY)"
+    if math.isnan(x):
+        return "NAN"
+    r = repr(float(x))
+    return f"({r})" if x < 0 else r
+
+
+# ---------------------------------------------------------------------------------------
+# liveness: drop assignments whose value can never reach a contribution
+# ---------------------------------------------------------------------------------------
+
+def _expr_vars(e, out: Set[str], funcs):
+    k = e[0]
+    if k == "var":
+        out.add(e[1])
+    elif k == "bin":
+        _expr_vars(e[2], out, funcs)
+        _expr_vars(e[3], out, funcs)
+    elif k == "un":
+        _expr_vars(e[2], out, funcs)
+    elif k == "cond":
+        for s in e[1:]:
+            _expr_vars(s, out, funcs)
+    elif k == "call":
+        if e[1] in NOISE_FUNCS:
+            return
+        for a in e[2]:
+            _expr_vars(a, out, funcs)
+
+
+def _call_outs(e, funcs, out: Set[str]):
+    """variables written through output/inout arguments of user functions inside e"""
+    k = e[0]
+    if k == "call":
+        fn = funcs.get(e[1])
+        if fn is not None:
+            for (an, kind), a in zip(fn.args, e[2]):
+                if kind != "input" and a[0] == "var":
+                    out.add(a[1])
+        for a in e[2]:
+            _call_outs(a, funcs, out)
+    elif k == "bin":
+        _call_outs(e[2], funcs, out)
+        _call_outs(e[3], funcs, out)
+    elif k == "un":
+        _call_outs(e[2], funcs, out)
+    elif k == "cond":
+        for s in e[1:]:
+            _call_outs(s, funcs, out)
+
+
+def _assigned(st, out: Set[str], funcs):
+    k = st[0]
+    if k == "assign":
+        out.add(st[1])
+        _call_outs(st[2], funcs, out)
+    elif k == "contrib":
+        _call_outs(st[3], funcs, out)
+    elif k == "block":
+        for s in st[2]:
+            _assigned(s, out, funcs)
+    elif k == "if":
+        _assigned(st[2], out, funcs)
+        if st[3]:
+            _assigned(st[3], out, funcs)
+    elif k == "case":
+        for _, s in st[2]:
+            _assigned(s, out, funcs)
+        if st[3]:
+            _assigned(st[3], out, funcs)
+    elif k == "for":
+        _assigned(st[1], out, funcs)
+        _assigned(st[3], out, funcs)
+        _assigned(st[4], out, funcs)
+    elif k in ("while", "repeat"):
+        _assigned(st[2], out, funcs)
+
+
+def prune_dead(st, live: Set[str], funcs) -> Tuple[Optional[tuple], Set[str]]:
+    """Backward liveness over structured code. Returns (pruned statement or None, live-before)."""
+    k = st[0]
+    if k == "assign":
+        outs: Set[str] = set()
+        _call_outs(st[2], funcs, outs)
+        if st[1] not in live and not (outs & live):
+            return None, live
+        nl = set(live)
+        nl.discard(st[1])
+        _expr_vars(st[2], nl, funcs)
+        return st, nl
+    if k == "contrib":
+        nl = set(live)
+        _expr_vars(st[3], nl, funcs)
+        return st, nl
+    if k in ("task", "nop"):
+        return None, live
+    if k == "block":
+        kept = []
+        cur = live
+        for s in reversed(st[2]):
+            ns, cur = prune_dead(s, cur, funcs)
+            if ns is not None:
+                kept.append(ns)
+        if not kept:
+            return None, cur
+        return ("block", st[1], kept[::-1], st[3]), cur
+    if k == "if":
+        a, la = prune_dead(st[2], live, funcs)
+        b, lb = prune_dead(st[3], live, funcs) if st[3] else (None, live)
+        if a is None and b is None:
+            return None, live
+        nl = set(la) | set(lb)
+        _expr_vars(st[1], nl, funcs)
+        return ("if", st[1], a if a is not None else ("nop",), b), nl
+    if k == "case":
+        items, nl, any_kept = [], set(), False
+        for vals, s in st[2]:
+            ns, ls = prune_dead(s, live, funcs)
+            any_kept |= ns is not None
+            items.append((vals, ns if ns is not None else ("nop",)))
+            nl |= ls
+            for v in vals:
+                _expr_vars(v, nl, funcs)
+        d, ld = prune_dead(st[3], live, funcs) if st[3] else (None, live)
+        any_kept |= d is not None
+        nl |= ld
+        if not any_kept:
+            return None, live
+        _expr_vars(st[1], nl, funcs)
+        return ("case", st[1], items, d), nl
+    # loops: keep everything, everything read or written inside stays live
+    nl = set(live)
+    asg: Set[str] = set()
+    _assigned(st, asg, funcs)
+
+    def all_vars(s):
+        kk = s[0]
+        if kk == "assign":
+            _expr_vars(s[2], nl, funcs)
+        elif kk == "contrib":
+            _expr_vars(s[3], nl, funcs)
+        elif kk == "block":
+            for x in s[2]:
+                all_vars(x)
+        elif kk == "if":
+            _expr_vars(s[1], nl, funcs)
+            all_vars(s[2])
+            if s[3]:
+                all_vars(s[3])
+        elif kk == "case":
+            _expr_vars(s[1], nl, funcs)
+            for vals, x in s[2]:
+                for v in vals:
+                    _expr_vars(v, nl, funcs)
+                all_vars(x)
+            if s[3]:
+                all_vars(s[3])
+        elif kk == "for":
+            all_vars(s[1]); _expr_vars(s[2], nl, funcs); all_vars(s[3]); all_vars(s[4])
+        elif kk in ("while", "repeat"):
+            _expr_vars(s[1], nl, funcs); all_vars(s[2])
+
+    all_vars(st)
+    return st, nl | asg
+
+
+# ---------------------------------------------------------------------------------------
+# values
+# ---------------------------------------------------------------------------------------
+
+@dataclass
+class Val:
+    """A generated value in the eval (dynamic) stream: an atom plus derivative atoms."""
+    typ: str                      # 'r' | 'i'
+    c: str                        # C atom (identifier or literal)
+    d: Dict[int, object] = field(default_factory=dict)  # seed -> atom (str) or python float
+    const: Optional[float] = None
+
+
+@dataclass
+class Lazy:
+    """A not-yet-emitted static expression (depends on parameters / temperature only)."""
+    e: tuple
+    typ: str
+    const: Optional[float] = None
+
+
+@dataclass
+class VS:
+    dyn: bool = False
+    deps: FrozenSet[int] = frozenset()
+    slot: Optional[int] = None
+    const: Optional[float] = 0.0   # compile-time constant value of a static variable
+
+
+@dataclass
+class CompiledModel:
+    name: str
+    module: str
+    terminals: List[str]
+    nports: int
+    params: List[str]
+    param_types: List[str]
+    ncache: int
+    jrow: List[int]
+    jcol: List[int]
+    source: str          # target-neutral body (macros), see c_prelude()/cuda wrappers in engine
+    n_eval_lines: int = 0
+    n_setup_lines: int = 0
+    census: Dict[str, int] = field(default_factory=dict)  # static op counts of the eval function
+
+    @property
+    def key(self) -> str:
+        return hashlib.sha1(self.source.encode()).hexdigest()[:16]
+
+
+class _Compiler:
+    def __init__(self, mod: Module, name: str):
+        self.mod = mod
+        self.name = name
+        self.terms = list(mod.nets)
+        self.tindex = {n: i for i, n in enumerate(self.terms)}
+        self.S: List[str] = []      # setup stream
+        self.E: List[str] = []      # eval stream
+        self.state: Dict[str, VS] = {}
+        self.scopes: List[Dict[str, str]] = [{}]
+        self.types: Dict[str, str] = {}           # cname -> 'r' | 'i'
+        self.decl_deps: Dict[str, Set[int]] = {}  # cname -> all seeds ever carried
+        self.dyn_vars: Set[str] = set()
+        self.static_vars: Set[str] = set()
+        self.ntemp = 0
+        self.nslot = 0
+        self.ninl = 0
+        self.census: Dict[str, int] = {}
+        self.forced_all: Set[str] = set()         # variables forced to carry all seeds (loops)
+        self.dead_locals: Set[str] = set()        # locals of inlined functions / blocks out of scope
+        self.params = {p.name: p for p in mod.params}
+        for p in mod.params:
+            cn = "p_" + p.name
+            self.types[cn] = "i" if p.type == "integer" else "r"
+        for v, t in mod.var_types.items():
+            self.types["v_" + v] = "i" if t == "integer" else "r"
+
+    # ---- naming ---------------------------------------------------------------------
+    def resolve(self, name: str) -> str:
+        for sc in reversed(self.scopes):
+            if name in sc:
+                return sc[name]
+        if name in self.params:
+            return "p_" + name
+        if name in self.mod.var_types:
+            return "v_" + name
+        raise VACompileError(f"undeclared identifier {name!r} in module {self.mod.name}")
+
+    def tmp(self) -> str:
+        self.ntemp += 1
+        return f"t{self.ntemp}"
+
+    def count(self, op: str, n: int = 1):
+        self.census[op] = self.census.get(op, 0) + n
+
+    def vs(self, cname: str) -> VS:
+        s = self.state.get(cname)
+        if s is None:
+            s = VS(const=None) if cname.startswith("p_") else VS()
+            self.state[cname] = s
+        return s
+
+    # ---- static (setup) expression generation: plain nested C --------------------------
+    def gs(self, e) -> Tuple[str, str, Optional[float]]:
+        """Returns (c expression, type, compile-time constant or None); may emit to self.S."""
+        k = e[0]
+        if k == "num":
+            return _lit(e[1]), ("i" if e[2] else "r"), e[1]
+        if k == "str":
+            raise VACompileError("string expression in numeric context")
+        if k == "var":
+            cn = self.resolve(e[1])
+            s = self.vs(cn)
+            if s.dyn:
+                raise VACompileError(f"internal: static read of dynamic variable {e[1]}")
+            typ = self.types[cn]
+            if s.const is not None:
+                cv = int(s.const) if typ == "i" else float(s.const)
+                return _lit(cv), typ, cv
+            self.static_vars.add(cn)
+            return cn, typ, None
+        if k == "un":
+            a, ta, ca = self.gs(e[2])
+            op = e[1]
+            if op == "-":
+                return f"(-{a})", ta, (None if ca is None else -ca)
+            if op == "!":
+                return f"(!{a})", "i", (None if ca is None else int(not ca))
+            if op == "~":
+                return f"(~{self._as_int(a, ta)})", "i", None
+        if k == "bin":
+            op = e[1]
+            a, ta, ca = self.gs(e[2])
+            b, tb, cb = self.gs(e[3])
+            return self._bin_static(op, a, ta, ca, b, tb, cb)
+        if k == "cond":
+            c, tc, cc = self.gs(e[1])
+            if cc is not None:
+                return self.gs(e[2] if cc else e[3])
+            a, ta, _ = self.gs(e[2])
+            b, tb, _ = self.gs(e[3])
+            typ = "i" if ta == "i" and tb == "i" else "r"
+            return f"({c} ? {self._cast(a, ta, typ)} : {self._cast(b, tb, typ)})", typ, None
+        if k == "call":
+            return self._call_static(e)
+        if k == "probe":
+            raise VACompileError("internal: probe in static expression")
+        raise VACompileError(f"unsupported expression node {k}")
+
+    @staticmethod
+    def _cast(c: str, frm: str, to: str) -> str:
+        if frm == to:
+            return c
+        if to == "r":
+            return f"((double){c})"
+        return f"((int)round({c}))"   # vaconvert: ties away from zero (src/va_env.jl:107)
+
+    def _as_int(self, c, t):
+        return c if t == "i" else f"((int)round({c}))"
+
+    def _bin_static(self, op, a, ta, ca, b, tb, cb):
+        both_int = ta == "i" and tb == "i"
+        const = None
+        if ca is not None and cb is not None:
+            try:
+                const = self._fold(op, ca, cb, both_int)
+            except (ZeroDivisionError, OverflowError, ValueError):
+                const = None
+        if op in ("+", "-", "*"):
+            typ = "i" if both_int else "r"
+            if const is not None:
+                return _lit(const), typ, const
+            return f"({a} {op} {b})", typ, None
+        if op == "/":
+            typ = "i" if both_int else "r"
+            if const is not None:
+                return _lit(const), typ, const
+            if both_int:
+                return f"({a} / {b})", "i", None
+            return f"({self._cast(a, ta, 'r')} / {self._cast(b, tb, 'r')})", "r", None
+        if op == "%":
+            if both_int:
+                return f"({a} % {b})", "i", const
+            return f"fmod({a}, {b})", "r", const
+        if op == "**":
+            return f"pow({self._cast(a, ta, 'r')}, {self._cast(b, tb, 'r')})", "r", const
+        if op in ("==", "!=", "<", "<=", ">", ">="):
+            if const is not None:
+                return _lit(int(const)), "i", int(const)
+            return f"({a} {op} {b})", "i", None
+        if op in ("&&", "||"):
+            # the reference lowers these to non-short-circuit ops (src/vasim.jl:225-228); same value
+            if const is not None:
+                return _lit(int(const)), "i", int(const)
+            if op == "&&" and ((ca is not None and not ca) or (cb is not None and not cb)):
+                return "0", "i", 0
+            if op == "||" and ((ca is not None and ca) or (cb is not None and cb)):
+                return "1", "i", 1
+            return f"(({a} != 0) {op} ({b} != 0))", "i", None
+        if op in ("&", "|", "^", "<<", ">>"):
+            return f"({self._as_int(a, ta)} {op} {self._as_int(b, tb)})", "i", None
+        if op in ("~^", "^~"):
+            return f"(~({self._as_int(a, ta)} ^ {self._as_int(b, tb)}))", "i", None
+        raise VACompileError(f"unsupported operator {op}")
+
+    @staticmethod
+    def _fold(op, a, b, both_int):
+        if op == "+": return a + b
+        if op == "-": return a - b
+        if op == "*": return a * b
+        if op == "/":
+            if both_int:
+                q = abs(a) // abs(b)
+                return q if (a >= 0) == (b >= 0) else -q
+            return a / b
+        if op == "%": return math.fmod(a, b) if not both_int else int(math.fmod(a, b))
+        if op == "**": return float(a) ** float(b)
+        if op == "==": return int(a == b)
+        if op == "!=": return int(a != b)
+        if op == "<": return int(a < b)
+        if op == "<=": return int(a <= b)
+        if op == ">": return int(a > b)
+        if op == ">=": return int(a >= b)
+        if op == "&&": return int(bool(a) and bool(b))
+        if op == "||": return int(bool(a) or bool(b))
+        raise ValueError(op)
+
+    def _call_static(self, e):
+        fn, args = e[1], e[2]
+        if fn == "$temperature":
+            return "TEMP_K", "r", None
+        if fn == "$vt":
+            if args:
+                a, ta, _ = self.gs(args[0])
+                return f"({_lit(P_K / P_Q)} * {a})", "r", None
+            return f"({_lit(P_K / P_Q)} * TEMP_K)", "r", None
+        if fn == "$param_given":
+            p = self.params.get(args[0][1]) if args and args[0][0] == "var" else None
+            if p is None:
+                raise VACompileError("$param_given needs a parameter name")
+            return f"GIVEN({p.index})", "i", None
+        if fn == "$simparam":
+            key = args[0][1] if args and args[0][0] == "str" else None
+            if key == "gmin":
+                return "GMIN_V", "r", None
+            if len(args) > 1:
+                return self.gs(args[1])
+            raise VACompileError(f"$simparam({key!r}) without default")
+        if fn in ("$mfactor",):
+            return "1.0", "r", 1.0
+        if fn in ("$abstime", "$realtime"):
+            return "0.0", "r", 0.0
+        if fn in NOISE_FUNCS:
+            return "0.0", "r", 0.0
+        if fn in ("ddt", "idt", "ddx"):
+            return "0.0", "r", 0.0   # derivative of a bias-independent quantity
+        if fn in self.mod.functions:
+            f = self.mod.functions[fn]
+            if len(args) != len(f.args):
+                raise VACompileError(f"wrong number of arguments to function {fn}")
+            cargs = []
+            for (an, kind), a in zip(f.args, args):
+                if kind == "input":
+                    c, t, _ = self.gs(a)
+                    cargs.append(self._cast(c, t, "i" if f.var_types.get(an) == "integer" else "r"))
+                else:
+                    if a[0] != "var":
+                        raise VACompileError(f"output argument {an} of {fn} must be a variable")
+                    cn = self.resolve(a[1])
+                    s = self.vs(cn)
+                    s.const, s.slot = None, None
+                    self.static_vars.add(cn)
+                    cargs.append("&" + cn)
+            self.used_funcs.add(fn)
+            return f"f_{fn}({', '.join(cargs)})", ("i" if f.type == "integer" else "r"), None
+        if fn in MATH1 or fn in MATH2:
+            cs = [self.gs(a) for a in args]
+            cstr = [self._cast(c, t, "r") for c, t, _ in cs]
+            consts = [c[2] for c in cs]
+            cname = {"ln": "log", "log": "log10", "abs": "fabs", "min": "fmin", "max": "fmax",
+                     "limexp": "va_limexp"}.get(fn, fn)
+            typ = "r"
+            if fn in ("abs", "min", "max") and all(t == "i" for _, t, _ in cs):
+                typ = "i"
+                cstr = [c for c, _, _ in cs]
+                if fn == "abs":
+                    return f"abs({cstr[0]})", "i", (None if consts[0] is None else abs(consts[0]))
+                o = "<" if fn == "min" else ">"
+                return f"(({cstr[0]}) {o} ({cstr[1]}) ? ({cstr[0]}) : ({cstr[1]}))", "i", None
+            const = None
+            if all(c is not None for c in consts):
+                try:
+                    pyf = {"ln": math.log, "log": math.log10, "abs": abs, "min": min, "max": max,
+                           "exp": math.exp, "sqrt": math.sqrt, "pow": math.pow}.get(fn)
+                    if pyf is not None:
+                        const = float(pyf(*[float(c) for c in consts]))
+                except (ValueError, OverflowError, ZeroDivisionError):
+                    const = None
+            if const is not None and math.isfinite(const):
+                return _lit(const), "r", const
+            return f"{cname}({', '.join(cstr)})", typ, None
+        raise VACompileError(f"unsupported function {fn}")
+
+    # ---- staging helpers -----------------------------------------------------------------
+    def is_static_expr(self, e) -> bool:
+        k = e[0]
+        if k in ("num", "str"):
+            return True
+        if k == "var":
+            return not self.vs(self.resolve(e[1])).dyn
+        if k == "probe":
+            return False
+        if k == "un":
+            return self.is_static_expr(e[2])
+        if k == "bin":
+            return self.is_static_expr(e[2]) and self.is_static_expr(e[3])
+        if k == "cond":
+            return all(self.is_static_expr(s) for s in e[1:])
+        if k == "call":
+            if e[1] in NOISE_FUNCS or e[1].startswith("$"):
+                return True
+            fn = self.mod.functions.get(e[1])
+            if fn is not None:
+                for (an, kind), a in zip(fn.args, e[2]):
+                    if kind == "input" and not self.is_static_expr(a):
+                        return False
+                    if kind != "input" and self.dynctl:
+                        return False
+                return True
+            if e[1] in ("ddt", "ddx", "idt"):
+                return all(self.is_static_expr(a) for a in e[2][:1])
+            return all(self.is_static_expr(a) for a in e[2])
+        return False
+
+    def new_slot(self, cexpr: str) -> int:
+        slot = self.nslot
+        self.nslot += 1
+        self.S.append(f"CACHE_ST({slot}, {cexpr});")
+        return slot
+
+    def static_read(self, cname: str) -> Val:
+        """Read a static variable from the eval stream (through its cache slot)."""
+        s = self.vs(cname)
+        typ = self.types[cname]
+        if s.const is not None:
+            cv = int(s.const) if typ == "i" else float(s.const)
+            return Val(typ, _lit(cv), {}, cv)
+        if s.slot is None:
+            self.static_vars.add(cname)
+            s.slot = self.new_slot(cname)
+        ld = f"CACHE_LD({s.slot})"
+        return Val(typ, f"((int){ld})" if typ == "i" else ld, {})
+
+    def hoist(self, e) -> Val:
+        """Evaluate a static expression in setup and read it back in eval."""
+        c, t, const = self.gs(e)
+        if const is not None:
+            return Val(t, _lit(const), {}, const)
+        if e[0] == "var":
+            return self.static_read(self.resolve(e[1]))
+        slot = self.new_slot(c)
+        ld = f"CACHE_LD({slot})"
+        return Val(t, f"((int){ld})" if t == "i" else ld, {})
+
+    # ---- dynamic (eval) expression generation with derivatives --------------------------
+    def emit_val(self, typ: str, cexpr: str, derivs: Dict[int, str]) -> Val:
+        t = self.tmp()
+        self.E.append(f"const {'int' if typ == 'i' else 'double'} {t} = {cexpr};")
+        d = {}
+        for k, de in derivs.items():
+            if isinstance(de, (int, float)):
+                if de != 0:
+                    d[k] = float(de)
+                continue
+            nm = f"{t}_d{k}"
+            self.E.append(f"const double {nm} = {de};")
+            d[k] = nm
+        return Val(typ, t, d)
+
+    @staticmethod
+    def _datom(x) -> str:
+        return _lit(float(x)) if isinstance(x, (int, float)) else x
+
+    def _dmul(self, coef: str, x) -> object:
+        """coef * x for a derivative atom x (python float or C atom)"""
+        if isinstance(x, (int, float)):
+            if x == 0:
+                return 0.0
+            if x == 1:
+                return coef
+            if x == -1:
+                return f"(-{coef})"
+            return f"({coef} * {_lit(float(x))})"
+        return f"({coef} * {x})"
+
+    def gd(self, e):
+        """Generate e in the dynamic stream; returns Val or Lazy (maximal static subtree)."""
+        k = e[0]
+        if k == "num":
+            return Lazy(e, "i" if e[2] else "r", e[1])
+        if k == "str":
+            return Lazy(e, "s")
+        if self.is_static_expr(e):
+            if k == "var":
+                cn = self.resolve(e[1])
+                s = self.vs(cn)
+                return Lazy(e, self.types[cn], s.const)
+            return Lazy(e, "?")
+        if k == "var":
+            cn = self.resolve(e[1])
+            s = self.vs(cn)
+            typ = self.types[cn]
+            self.dyn_vars.add(cn)
+            return Val(typ, cn, {kk: f"{cn}__d{kk}" for kk in sorted(s.deps)} if typ == "r" else {})
+        if k == "probe":
+            return self._probe(e)
+        if k == "un":
+            a = self.force(self.gd(e[2]))
+            op = e[1]
+            if op == "-":
+                if a.typ == "i":
+                    return self.emit_val("i", f"-{a.c}", {})
+                self.count("add", 1 + len(a.d))
+                d = {kk: (-v if isinstance(v, (int, float)) else f"-{v}") for kk, v in a.d.items()}
+                return self.emit_val("r", f"-{a.c}", d)
+            if op == "!":
+                return self.emit_val("i", f"!{a.c}", {})
+            if op == "~":
+                return self.emit_val("i", f"~{self._as_int(a.c, a.typ)}", {})
+        if k == "bin":
+            return self._bin_dyn(e)
+        if k == "cond":
+            c = self.force(self.gd(e[1]))
+            a = self.force(self.gd(e[2]))
+            b = self.force(self.gd(e[3]))
+            typ = "i" if a.typ == "i" and b.typ == "i" else "r"
+            ac, bc = self._cast(a.c, a.typ, typ), self._cast(b.c, b.typ, typ)
+            d = {}
+            for kk in sorted(set(a.d) | set(b.d)):
+                d[kk] = f"({c.c} ? {self._datom(a.d.get(kk, 0.0))} : {self._datom(b.d.get(kk, 0.0))})"
+            return self.emit_val(typ, f"({c.c} ? {ac} : {bc})", d)
+        if k == "call":
+            return self._call_dyn(e)
+        raise VACompileError(f"unsupported expression node {k}")
+
+    def force(self, x) -> Val:
+        if isinstance(x, Val):
+            return x
+        if x.const is not None and x.typ in ("r", "i"):
+            cv = int(x.const) if x.typ == "i" else float(x.const)
+            return Val(x.typ, _lit(cv), {}, cv)
+        return self.hoist(x.e)
+
+    def _probe(self, e) -> Val:
+        acc, nodes = e[1], e[2]
+        if acc not in ("V", "potential"):
+            raise VACompileError(f"probe {acc}({', '.join(nodes)}) is not supported (branch currents are not MNA unknowns)")
+        if len(nodes) == 1 and nodes[0] in self.mod.branches:
+            nodes = list(self.mod.branches[nodes[0]])
+        idx = []
+        for n in nodes:
+            if n in ("0", "gnd") or n not in self.tindex:
+                if n in ("0", "gnd"):
+                    continue
+                raise VACompileError(f"unknown net {n}")
+            idx.append(self.tindex[n])
+        if len(nodes) == 2 and len(idx) == 2:
+            a, b = idx
+            if a == b:
+                return Val("r", "0.0", {}, 0.0)
+            self.count("add")
+            return self.emit_val("r", f"VT({a}) - VT({b})", {a: 1.0, b: -1.0})
+        if len(idx) == 1:
+            sign = 1.0 if (len(nodes) == 1 or nodes[0] not in ("0", "gnd")) else -1.0
+            a = idx[0]
+            return self.emit_val("r", f"VT({a})" if sign > 0 else f"-VT({a})", {a: sign})
+        return Val("r", "0.0", {}, 0.0)
+
+    def _bin_dyn(self, e) -> Val:
+        op = e[1]
+        a = self.force(self.gd(e[2]))
+        b = self.force(self.gd(e[3]))
+        both_int = a.typ == "i" and b.typ == "i"
+        if op in ("==", "!=", "<", "<=", ">", ">="):
+            return self.emit_val("i", f"{a.c} {op} {b.c}", {})
+        if op in ("&&", "||"):
+            return self.emit_val("i", f"({a.c} != 0) {op} ({b.c} != 0)", {})
+        if op in ("&", "|", "^", "<<", ">>"):
+            return self.emit_val("i", f"{self._as_int(a.c, a.typ)} {op} {self._as_int(b.c, b.typ)}", {})
+        if op in ("~^", "^~"):
+            return self.emit_val("i", f"~({self._as_int(a.c, a.typ)} ^ {self._as_int(b.c, b.typ)})", {})
+        if both_int:
+            if op in ("+", "-", "*", "/", "%"):
+                return self.emit_val("i", f"{a.c} {op} {b.c}", {})
+        ac, bc = self._cast(a.c, a.typ, "r"), self._cast(b.c, b.typ, "r")
+        keys = sorted(set(a.d) | set(b.d))
+        if op in ("+", "-"):
+            self.count("add", 1 + len(keys))
+            d = {}
+            for kk in keys:
+                da, db = a.d.get(kk), b.d.get(kk)
+                if db is None:
+                    d[kk] = da
+                elif da is None:
+                    d[kk] = db if op == "+" else (-db if isinstance(db, (int, float)) else f"-{db}")
+                elif isinstance(da, (int, float)) and isinstance(db, (int, float)):
+                    d[kk] = da + db if op == "+" else da - db
+                else:
+                    d[kk] = f"{self._datom(da)} {op} {self._datom(db)}"
+            return self.emit_val("r", f"{ac} {op} {bc}", d)
+        if op == "*":
+            d = {}
+            for kk in keys:
+                da, db = a.d.get(kk), b.d.get(kk)
+                terms = []
+                if da is not None:
+                    terms.append(self._dmul(bc, da))
+                if db is not None:
+                    terms.append(self._dmul(ac, db))
+                terms = [t for t in terms if not (isinstance(t, float) and t == 0.0)]
+                d[kk] = " + ".join(self._datom(t) for t in terms) if terms else 0.0
+                self.count("mul", len(terms)); self.count("add", max(0, len(terms) - 1))
+            self.count("mul")
+            return self.emit_val("r", f"{ac} * {bc}", d)
+        if op == "/":
+            self.count("div")
+            if not b.d:
+                if not a.d:
+                    return self.emit_val("r", f"{ac} / {bc}", {})
+                inv = self.emit_val("r", f"1.0 / {bc}", {})
+                d = {kk: self._dmul(inv.c, v) for kk, v in a.d.items()}
+                self.count("mul", 1 + len(d))
+                return self.emit_val("r", f"{ac} * {inv.c}", d)
+            inv = self.emit_val("r", f"1.0 / {bc}", {})
+            q = self.emit_val("r", f"{ac} * {inv.c}", {})
+            d = {}
+            for kk in keys:
+                da, db = a.d.get(kk), b.d.get(kk)
+                if db is None:
+                    d[kk] = self._dmul(inv.c, da)
+                    self.count("mul")
+                elif da is None:
+                    d[kk] = f"-({q.c} * {self._datom(db)}) * {inv.c}"
+                    self.count("mul", 2)
+                else:
+                    d[kk] = f"({self._datom(da)} - {q.c} * {self._datom(db)}) * {inv.c}"
+                    self.count("mul", 2); self.count("add")
+            return self.emit_val("r", q.c, d)
+        if op == "%":
+            return self.emit_val("r", f"fmod({ac}, {bc})", dict(a.d))
+        if op == "**":
+            return self._pow(a, b)
+        raise VACompileError(f"unsupported operator {op}")
+
+    def _pow(self, a: Val, b: Val) -> Val:
+        ac, bc = self._cast(a.c, a.typ, "r"), self._cast(b.c, b.typ, "r")
+        self.count("pow")
+        p = self.emit_val("r", f"pow({ac}, {bc})", {})
+        keys = sorted(set(a.d) | set(b.d))
+        if not keys:
+            return p
+        d = {}
+        dpa = None
+        if a.d:
+            # d/da a^b = b a^(b-1)  (ForwardDiff's rule; finite at a == 0 for b >= 1)
+            dpa = self.emit_val("r", f"({ac} == 0.0 ? {bc} * pow({ac}, {bc} - 1.0) : {bc} * {p.c} / {ac})", {})
+            self.count("div"); self.count("mul")
+        dpb = None
+        if b.d:
+            dpb = self.emit_val("r", f"({p.c} == 0.0 ? 0.0 : {p.c} * log({ac}))", {})
+            self.count("log"); self.count("mul")
+        for kk in keys:
+            terms = []
+            if kk in a.d:
+                terms.append(self._dmul(dpa.c, a.d[kk]))
+            if kk in b.d:
+                terms.append(self._dmul(dpb.c, b.d[kk]))
+            self.count("mul", len(terms))
+            d[kk] = " + ".join(self._datom(t) for t in terms)
+        return self.emit_val("r", p.c, d)
+
+    def _unary_math(self, fn: str, a: Val) -> Val:
+        ac = self._cast(a.c, a.typ, "r")
+        has_d = bool(a.d)
+
+        def chain(v: Val, dcoef: Optional[str]) -> Val:
+            if not has_d or dcoef is None:
+                return v
+            g = self.emit_val("r", dcoef, {})
+            self.count("mul", len(a.d))
+            return self.emit_val("r", v.c, {kk: self._dmul(g.c, x) for kk, x in a.d.items()})
+
+        if fn == "exp":
+            self.count("exp")
+            v = self.emit_val("r", f"exp({ac})", {})
+            if not has_d:
+                return v
+            self.count("mul", len(a.d))
+            return self.emit_val("r", v.c, {kk: self._dmul(v.c, x) for kk, x in a.d.items()})
+        if fn == "limexp":
+            self.count("exp")
+            v = self.emit_val("r", f"va_limexp({ac})", {})
+            return chain(v, f"va_dlimexp({ac})")
+        if fn == "ln":
+            self.count("log"); self.count("div", 1 if has_d else 0)
+            return chain(self.emit_val("r", f"log({ac})", {}), f"1.0 / {ac}")
+        if fn == "log":
+            self.count("log"); self.count("div", 1 if has_d else 0)
+            return chain(self.emit_val("r", f"log10({ac})", {}), f"{_lit(1.0 / math.log(10.0))} / {ac}")
+        if fn == "sqrt":
+            self.count("sqrt"); self.count("div", 1 if has_d else 0)
+            v = self.emit_val("r", f"sqrt({ac})", {})
+            return chain(v, f"0.5 / {v.c}")
+        if fn == "sin":
+            self.count("trig", 2 if has_d else 1)
+            return chain(self.emit_val("r", f"sin({ac})", {}), f"cos({ac})")
+        if fn == "cos":
+            self.count("trig", 2 if has_d else 1)
+            return chain(self.emit_val("r", f"cos({ac})", {}), f"-sin({ac})")
+        if fn == "tan":
+            self.count("trig")
+            v = self.emit_val("r", f"tan({ac})", {})
+            return chain(v, f"1.0 + {v.c} * {v.c}")
+        if fn == "asin":
+            self.count("trig")
+            return chain(self.emit_val("r", f"asin({ac})", {}), f"1.0 / sqrt(1.0 - {ac} * {ac})")
+        if fn == "acos":
+            self.count("trig")
+            return chain(self.emit_val("r", f"acos({ac})", {}), f"-1.0 / sqrt(1.0 - {ac} * {ac})")
+        if fn == "atan":
+            self.count("trig"); self.count("div", 1 if has_d else 0)
+            return chain(self.emit_val("r", f"atan({ac})", {}), f"1.0 / (1.0 + {ac} * {ac})")
+        if fn == "sinh":
+            self.count("exp", 2)
+            return chain(self.emit_val("r", f"sinh({ac})", {}), f"cosh({ac})")
+        if fn == "cosh":
+            self.count("exp", 2)
+            return chain(self.emit_val("r", f"cosh({ac})", {}), f"sinh({ac})")
+        if fn == "tanh":
+            self.count("exp"); self.count("div")
+            v = self.emit_val("r", f"tanh({ac})", {})
+            return chain(v, f"1.0 - {v.c} * {v.c}")
+        if fn == "asinh":
+            self.count("log")
+            return chain(self.emit_val("r", f"asinh({ac})", {}), f"1.0 / sqrt({ac} * {ac} + 1.0)")
+        if fn == "acosh":
+            self.count("log")
+            return chain(self.emit_val("r", f"acosh({ac})", {}), f"1.0 / sqrt({ac} * {ac} - 1.0)")
+        if fn == "atanh":
+            self.count("log")
+            return chain(self.emit_val("r", f"atanh({ac})", {}), f"1.0 / (1.0 - {ac} * {ac})")
+        if fn == "abs":
+            if a.typ == "i":
+                return self.emit_val("i", f"abs({a.c})", {})
+            v = self.emit_val("r", f"fabs({ac})", {})
+            if not has_d:
+                return v
+            s = self.emit_val("r", f"({ac} < 0.0 ? -1.0 : 1.0)", {})
+            return self.emit_val("r", v.c, {kk: self._dmul(s.c, x) for kk, x in a.d.items()})
+        if fn in ("floor", "ceil"):
+            return self.emit_val("r", f"{fn}({ac})", {})
+        raise VACompileError(f"unsupported function {fn}")
+
+    def _call_dyn(self, e):
+        fn, args = e[1], e[2]
+        if fn in NOISE_FUNCS:
+            return Val("r", "0.0", {}, 0.0)
+        if fn == "ddx":
+            v = self.force(self.gd(args[0]))
+            pr = args[1]
+            if pr[0] != "probe" or pr[1] not in ("V", "potential"):
+                raise VACompileError("ddx: second argument must be a V() probe")
+            idx = [self.tindex[n] for n in pr[2] if n in self.tindex]
+            if len(pr[2]) == 1:
+                d = v.d.get(idx[0], 0.0) if idx else 0.0
+                return self.emit_val("r", self._datom(d), {})
+            # two-node probe: (dx1 - dx2)/2 as the reference does (src/vasim.jl:398-411)
+            d1 = self._datom(v.d.get(self.tindex.get(pr[2][0], -1), 0.0))
+            d2 = self._datom(v.d.get(self.tindex.get(pr[2][1], -1), 0.0))
+            return self.emit_val("r", f"({d1} - {d2}) * 0.5", {})
+        if fn == "ddt":
+            raise VACompileError("ddt() is only supported as a linear term of a contribution")
+        if fn in self.mod.functions:
+            return self._inline(self.mod.functions[fn], args)
+        if fn in MATH1:
+            return self._unary_math(fn, self.force(self.gd(args[0])))
+        if fn == "pow":
+            return self._pow(self.force(self.gd(args[0])), self.force(self.gd(args[1])))
+        if fn in ("min", "max"):
+            a = self.force(self.gd(args[0]))
+            b = self.force(self.gd(args[1]))
+            typ = "i" if a.typ == "i" and b.typ == "i" else "r"
+            ac, bc = self._cast(a.c, a.typ, typ), self._cast(b.c, b.typ, typ)
+            o = "<" if fn == "min" else ">"
+            sel = self.emit_val("i", f"{ac} {o} {bc}", {})
+            d = {}
+            for kk in sorted(set(a.d) | set(b.d)):
+                d[kk] = f"({sel.c} ? {self._datom(a.d.get(kk, 0.0))} : {self._datom(b.d.get(kk, 0.0))})"
+            return self.emit_val(typ, f"({sel.c} ? {ac} : {bc})", d)
+        if fn == "atan2":
+            y = self.force(self.gd(args[0]))
+            x = self.force(self.gd(args[1]))
+            v = self.emit_val("r", f"atan2({y.c}, {x.c})", {})
+            if not (y.d or x.d):
+                return v
+            den = self.emit_val("r", f"1.0 / ({x.c} * {x.c} + {y.c} * {y.c})", {})
+            d = {}
+            for kk in sorted(set(y.d) | set(x.d)):
+                d[kk] = (f"({x.c} * {self._datom(y.d.get(kk, 0.0))} - {y.c} * {self._datom(x.d.get(kk, 0.0))})"
+                         f" * {den.c}")
+            return self.emit_val("r", v.c, d)
+        if fn == "hypot":
+            a = self.force(self.gd(args[0]))
+            b = self.force(self.gd(args[1]))
+            v = self.emit_val("r", f"hypot({a.c}, {b.c})", {})
+            d = {}
+            for kk in sorted(set(a.d) | set(b.d)):
+                d[kk] = (f"({a.c} * {self._datom(a.d.get(kk, 0.0))} + {b.c} * {self._datom(b.d.get(kk, 0.0))})"
+                         f" / {v.c}")
+            return self.emit_val("r", v.c, d)
+        raise VACompileError(f"unsupported function {fn} in bias-dependent code")
+
+    def _inline(self, f: Function, args) -> Val:
+        """Inline a user analog function into the dynamic stream (AD goes through its body)."""
+        if len(args) != len(f.args):
+            raise VACompileError(f"wrong number of arguments to function {f.name}")
+        self.ninl += 1
+        pre = f"f{self.ninl}_"
+        scope = {}
+        for vn, vt in f.var_types.items():
+            cn = pre + vn
+            scope[vn] = cn
+            self.types[cn] = "i" if vt == "integer" else "r"
+        ins = []
+        for (an, kind), a in zip(f.args, args):
+            if kind in ("input", "inout"):
+                ins.append((an, self.gd(a)))
+        outs = [(an, a) for (an, kind), a in zip(f.args, args) if kind in ("output", "inout")]
+        for an, a in outs:
+            if a[0] != "var":
+                raise VACompileError(f"output argument {an} of {f.name} must be a variable")
+        self.scopes.append(scope)
+        for vn in f.var_types:
+            self.state[scope[vn]] = VS()
+        for an, v in ins:
+            self._store(scope[an], v)
+        self.stmt(f.body)
+        self.scopes.pop()
+        self.dead_locals.update(scope.values())
+        for an, a in outs:
+            self._store(self.resolve(a[1]), self._load(scope[an]))
+        return self._load(scope[f.name])
+
+    def _load(self, cn: str):
+        s = self.vs(cn)
+        typ = self.types[cn]
+        if not s.dyn:
+            if s.const is not None:
+                return Lazy(("num", s.const, typ == "i"), typ, s.const)
+            return self.static_read(cn)
+        self.dyn_vars.add(cn)
+        return Val(typ, cn, {kk: f"{cn}__d{kk}" for kk in sorted(s.deps)} if typ == "r" else {})
+
+    def _store(self, cn: str, v):
+        """Assign a generated value (Val or Lazy) to variable cn, in the right stream."""
+        typ = self.types[cn]
+        if isinstance(v, Lazy) and not self.dynctl:
+            c, t, const = self.gs(v.e)
+            s = VS(False, frozenset(), None, None)
+            if const is not None:
+                if typ == "i":   # vaconvert: round half away from zero (src/va_env.jl:107)
+                    s.const = int(math.floor(abs(const) + 0.5)) * (1 if const >= 0 else -1) if t == "r" else int(const)
+                else:
+                    s.const = float(const)
+            self.S.append(f"{cn} = {self._cast(c, t, typ)};")
+            self.static_vars.add(cn)
+            self.state[cn] = s
+            return
+        v = self.force(v)
+        self.dyn_vars.add(cn)
+        self.E.append(f"{cn} = {self._cast(v.c, v.typ, typ)};")
+        deps = set()
+        if typ == "r":
+            for kk, x in v.d.items():
+                self.E.append(f"{cn}__d{kk} = {self._datom(x)};")
+                deps.add(kk)
+            if cn in self.forced_all:
+                for kk in range(len(self.terms)):
+                    if kk not in deps:
+                        self.E.append(f"{cn}__d{kk} = 0.0;")
+                deps = set(range(len(self.terms)))
+            self.decl_deps.setdefault(cn, set()).update(deps)
+        self.state[cn] = VS(True, frozenset(deps), None, None)
+
+    # ---- statements -----------------------------------------------------------------------
+    dynctl = False
+
+    def stmt(self, st):
+        k = st[0]
+        if k in ("nop", "task"):
+            return
+        if k == "block":
+            scope = {}
+            for vn, vt in st[3].items():
+                self.ninl += 1
+                cn = f"b{self.ninl}_{vn}"
+                scope[vn] = cn
+                self.types[cn] = "i" if vt == "integer" else "r"
+                self.state[cn] = VS()
+            self.scopes.append(scope)
+            for s in st[2]:
+                self.stmt(s)
+            self.scopes.pop()
+            self.dead_locals.update(scope.values())
+            return
+        if k == "assign":
+            cn = self.resolve(st[1])
+            if cn.startswith("p_"):
+                raise VACompileError(f"assignment to parameter {st[1]}")
+            self._store(cn, self.gd(st[2]))
+            return
+        if k == "contrib":
+            return self.contrib(st)
+        if k == "if":
+            return self.if_stmt(st[1], st[2], st[3])
+        if k == "case":
+            chain = st[3]
+            for vals, body in reversed(st[2]):
+                cond = None
+                for v in vals:
+                    c = ("bin", "==", st[1], v)
+                    cond = c if cond is None else ("bin", "||", cond, c)
+                chain = ("if", cond, body, chain)
+            if chain is not None:
+                self.stmt(chain)
+            return
+        if k == "for":
+            self.stmt(st[1])
+            return self.loop(st[2], ("block", None, [st[4], st[3]], {}))
+        if k == "while":
+            return self.loop(st[1], st[2])
+        if k == "repeat":
+            self.ninl += 1
+            cn = f"rep{self.ninl}"
+            self.types[cn] = "i"
+            self.scopes.append({cn: cn})
+            self.stmt(("assign", cn, st[1]))
+            body = ("block", None, [st[2], ("assign", cn, ("bin", "-", ("var", cn), ("num", 1, True)))], {})
+            self.loop(("bin", ">", ("var", cn), ("num", 0, True)), body)
+            self.scopes.pop()
+            return
+        raise VACompileError(f"unsupported statement {k}")
+
+    # -- contributions (src/vasim.jl:128-180) --
+    def _split_ddt(self, e):
+        """e = resistive + sum coef_i * ddt(q_i).  Returns (resistive or None, [(coef, q)])."""
+        k = e[0]
+        if k == "call" and e[1] == "ddt":
+            return None, [(("num", 1.0, False), e[2][0])]
+        if not self._has_ddt(e):
+            return e, []
+        if k == "bin" and e[1] in ("+", "-"):
+            ra, qa = self._split_ddt(e[2])
+            rb, qb = self._split_ddt(e[3])
+            if e[1] == "-":
+                rb = None if rb is None else ("un", "-", rb)
+                qb = [(("un", "-", c), q) for c, q in qb]
+            r = ra if rb is None else (rb if ra is None else ("bin", "+", ra, rb))
+            return r, qa + qb
+        if k == "bin" and e[1] == "*":
+            if self._has_ddt(e[2]) and not self._has_ddt(e[3]):
+                r, q = self._split_ddt(e[2])
+                other = e[3]
+            elif self._has_ddt(e[3]) and not self._has_ddt(e[2]):
+                r, q = self._split_ddt(e[3])
+                other = e[2]
+            else:
+                raise VACompileError("product of two ddt() terms")
+            r = None if r is None else ("bin", "*", other, r)
+            return r, [(("bin", "*", other, c), qq) for c, qq in q]
+        if k == "bin" and e[1] == "/" and not self._has_ddt(e[3]):
+            r, q = self._split_ddt(e[2])
+            r = None if r is None else ("bin", "/", r, e[3])
+            return r, [(("bin", "/", c, e[3]), qq) for c, qq in q]
+        if k == "un" and e[1] == "-":
+            r, q = self._split_ddt(e[2])
+            return (None if r is None else ("un", "-", r)), [(("un", "-", c), qq) for c, qq in q]
+        raise VACompileError("ddt() must appear linearly in a contribution")
+
+    def _has_ddt(self, e) -> bool:
+        k = e[0]
+        if k == "call":
+            return e[1] == "ddt" or any(self._has_ddt(a) for a in e[2])
+        if k == "bin":
+            return self._has_ddt(e[2]) or self._has_ddt(e[3])
+        if k == "un":
+            return self._has_ddt(e[2])
+        if k == "cond":
+            return any(self._has_ddt(s) for s in e[1:])
+        return False
+
+    def contrib(self, st):
+        acc, nodes, e = st[1], st[2], st[3]
+        if len(nodes) == 1 and nodes[0] in self.mod.branches:
+            nodes = list(self.mod.branches[nodes[0]])
+        if acc not in ("I", "flow"):
+            raise VACompileError(f"{acc}() contributions are not supported yet (voltage branches need extra MNA unknowns)")
+        res, qs = self._split_ddt(e)
+        pos = self.tindex.get(nodes[0]) if nodes[0] not in ("0", "gnd") else None
+        neg = None
+        if len(nodes) > 1 and nodes[1] not in ("0", "gnd"):
+            neg = self.tindex.get(nodes[1])
+        if pos is not None and pos == neg:
+            return
+        saved = self.dynctl
+        for c, _q in qs:
+            if not self.is_static_expr(c):
+                raise VACompileError("bias-dependent coefficient on ddt() is not charge-conserving; unsupported")
+        for kind, expr in ([("I", res)] if res is not None else []) + [("Q", ("bin", "*", c, q)) for c, q in qs]:
+            v = self.gd(expr)
+            if isinstance(v, Lazy) and v.const is not None and v.const == 0:
+                continue
+            v = self.force(v)
+            if v.typ == "i":
+                v = Val("r", self._cast(v.c, "i", "r"), {})
+            for node, sign in ((pos, 1.0), (neg, -1.0)):
+                if node is None:
+                    continue
+                an = f"acc{kind}_{node}"
+                self.types[an] = "r"
+                s = self.vs(an)
+                op = "+=" if sign > 0 else "-="
+                self.E.append(f"{an} {op} {v.c};")
+                deps = set(s.deps) if s.dyn else set()
+                for kk, x in v.d.items():
+                    self.E.append(f"{an}__d{kk} {op} {self._datom(x)};")
+                    deps.add(kk)
+                self.count("add", 1 + len(v.d))
+                self.dyn_vars.add(an)
+                self.decl_deps.setdefault(an, set()).update(deps)
+                self.state[an] = VS(True, frozenset(deps), None, None)
+        self.dynctl = saved
+
+    # -- control flow --
+    def _snapshot_state(self) -> Dict[str, VS]:
+        return {k: VS(v.dyn, v.deps, v.slot, v.const) for k, v in self.state.items()}
+
+    def if_stmt(self, cond, then, other):
+        cv = self.gd(cond)
+        if isinstance(cv, Lazy):
+            c, t, const = self.gs(cv.e)
+            if const is not None:   # compile-time branch
+                taken = then if const else other
+                if taken is not None:
+                    self.stmt(taken)
+                return
+            if not self.dynctl:
+                return self._if_static(c, then, other)
+            cv = self.force(cv)
+        return self._if_dynamic(cv, then, other)
+
+    def _run_branch(self, st, start_state, dyn):
+        save_S, save_E, save_state, save_dyn = self.S, self.E, self.state, self.dynctl
+        self.S = save_S if dyn else []
+        self.E = []
+        self.state = start_state
+        self.dynctl = dyn or save_dyn
+        if st is not None:
+            self.stmt(st)
+        out = (self.S, self.E, self.state)
+        self.S, self.E, self.state, self.dynctl = save_S, save_E, save_state, save_dyn
+        return out
+
+    def _merge(self, s0, sa, sb, Ea, Eb, Sa, Sb, shared_setup: bool):
+        """Merge branch states; appends fix-ups to the branch code lists."""
+        merged: Dict[str, VS] = {}
+        for name in set(sa) | set(sb):
+            a = sa.get(name) or VS()
+            b = sb.get(name) or VS()
+            if name not in self.types or name in self.dead_locals:
+                continue
+            if not a.dyn and not b.dyn:
+                base = s0.get(name)
+                if shared_setup:
+                    # setup has no branch here: a snapshot taken in either arm ran unconditionally
+                    slot = a.slot if a.slot is not None else b.slot
+                else:
+                    # only a snapshot that predates the `if` and survived both arms is still valid
+                    slot = a.slot if (base is not None and a.slot == b.slot == base.slot) else None
+                const = a.const if (a.const is not None and a.const == b.const) else None
+                merged[name] = VS(False, frozenset(), slot, const)
+                continue
+            deps = frozenset((a.deps if a.dyn else frozenset()) | (b.deps if b.dyn else frozenset()))
+            if name in self.forced_all:
+                deps = frozenset(range(len(self.terms)))
+            for br, E_, S_ in ((a, Ea, Sa), (b, Eb, Sb)):
+                if br.dyn:
+                    for kk in sorted(deps - br.deps):
+                        E_.append(f"{name}__d{kk} = 0.0;")
+                else:
+                    # materialise the static value in this branch
+                    save_S, save_E, save_state = self.S, self.E, self.state
+                    self.S, self.E = S_, E_
+                    self.state = {name: VS(False, frozenset(), br.slot, br.const)}
+                    v = self.static_read(name)
+                    self.S, self.E, self.state = save_S, save_E, save_state
+                    E_.append(f"{name} = {v.c};")
+                    if self.types[name] == "r":
+                        for kk in sorted(deps):
+                            E_.append(f"{name}__d{kk} = 0.0;")
+            self.dyn_vars.add(name)
+            if self.types[name] == "r":
+                self.decl_deps.setdefault(name, set()).update(deps)
+            merged[name] = VS(True, deps if self.types[name] == "r" else frozenset(), None, None)
+        return merged
+
+    def _if_static(self, c: str, then, other):
+        s0 = self.state
+        self.ntemp += 1
+        cvar = f"c{self.ntemp}"
+        self.S.append(f"const int {cvar} = ({c}) != 0;")
+        marker = len(self.S)
+        Sa, Ea, sa = self._run_branch(then, self._snapshot_state(), False)
+        Sb, Eb, sb = self._run_branch(other, self._snapshot_state(), False)
+        self.state = self._merge(s0, sa, sb, Ea, Eb, Sa, Sb, shared_setup=False)
+        if Sa or Sb:
+            self.S.append(f"if ({cvar}) {{")
+            self.S.extend("    " + l for l in Sa)
+            if Sb:
+                self.S.append("} else {")
+                self.S.extend("    " + l for l in Sb)
+            self.S.append("}")
+        if Ea or Eb:
+            slot = self.nslot
+            self.nslot += 1
+            self.S.insert(marker, f"CACHE_ST({slot}, {cvar});")
+            if Ea:
+                self.E.append(f"if (CACHE_LD({slot}) != 0.0) {{")
+                self.E.extend("    " + l for l in Ea)
+                if Eb:
+                    self.E.append("} else {")
+                    self.E.extend("    " + l for l in Eb)
+            else:
+                self.E.append(f"if (CACHE_LD({slot}) == 0.0) {{")
+                self.E.extend("    " + l for l in Eb)
+            self.E.append("}")
+
+    def _if_dynamic(self, cv: Val, then, other):
+        s0 = self.state
+        _, Ea, sa = self._run_branch(then, self._snapshot_state(), True)
+        # slots created while generating `then` stay valid (setup has no branch here)
+        start_b = self._snapshot_state()
+        for name, a in sa.items():
+            b = start_b.get(name)
+            if b is not None and not a.dyn and not b.dyn and b.slot is None and a.slot is not None:
+                b.slot = a.slot
+        _, Eb, sb = self._run_branch(other, start_b, True)
+        self.state = self._merge(s0, sa, sb, Ea, Eb, self.S, self.S, shared_setup=True)
+        if Ea or Eb:
+            if Ea:
+                self.E.append(f"if ({cv.c}) {{")
+                self.E.extend("    " + l for l in Ea)
+                if Eb:
+                    self.E.append("} else {")
+                    self.E.extend("    " + l for l in Eb)
+            else:
+                self.E.append(f"if (!({cv.c})) {{")
+                self.E.extend("    " + l for l in Eb)
+            self.E.append("}")
+
+    def loop(self, cond, body):
+        asg: Set[str] = set()
+        _assigned(body, asg, self.mod.functions)
+        names = [self.resolve(n) for n in asg]
+        # trial run on a scratch copy to classify the loop
+        saved = (self.S, self.E, self.state, self.ntemp, self.nslot, self.ninl, dict(self.census),
+                 {k: set(v) for k, v in self.decl_deps.items()}, set(self.dyn_vars), set(self.static_vars))
+        self.S, self.E, self.state = [], [], self._snapshot_state()
+        for cn in names:
+            s = self.vs(cn)
+            s.const, s.slot = None, None
+        static_ok = not self.dynctl and self.is_static_expr(cond)
+        if static_ok:
+            self.stmt(body)
+            static_ok = not self.E and self.is_static_expr(cond)
+        (self.S, self.E, self.state, self.ntemp, self.nslot, self.ninl, self.census, self.decl_deps,
+         self.dyn_vars, self.static_vars) = saved
+        if static_ok:
+            for cn in names:
+                s = self.vs(cn)
+                s.const, s.slot = None, None
+                self.static_vars.add(cn)
+            c, _, _ = self.gs(cond)
+            outer = self.S
+            self.S = []
+            self.stmt(body)
+            inner = self.S
+            self.S = outer
+            self.S.append(f"while ({c}) {{")
+            self.S.extend("    " + l for l in inner)
+            self.S.append("}")
+            for cn in names:
+                s = self.vs(cn)
+                s.const, s.slot = None, None
+            return
+        # dynamic loop: every variable assigned inside carries all seeds
+        allseeds = frozenset(range(len(self.terms)))
+        for cn in names:
+            v = self._load(cn)
+            self.forced_all.add(cn)
+            save = self.dynctl
+            self.dynctl = True
+            self._store(cn, v)
+            self.dynctl = save
+        save_dyn, outer = self.dynctl, self.E
+        self.dynctl = True
+        self.E = []
+        cv = self.force(self.gd(cond))
+        self.E.append(f"if (!({cv.c})) break;")
+        self.stmt(body)
+        inner = self.E
+        self.E = outer
+        self.dynctl = save_dyn
+        self.E.append("for (;;) {")
+        self.E.extend("    " + l for l in inner)
+        self.E.append("}")
+        for cn in names:
+            if self.types[cn] == "r":
+                self.state[cn] = VS(True, allseeds, None, None)
+
+    # ---- driver ---------------------------------------------------------------------------------
+    def compile(self) -> CompiledModel:
+        mod = self.mod
+        self.used_funcs: Set[str] = set()
+        # parameters: value if given, else default expression (may reference earlier parameters)
+        for p in mod.params:
+            cn = "p_" + p.name
+            if p.type == "string":
+                continue
+            self.state[cn] = VS(False, frozenset(), None, None)
+            dflt, t, _ = self.gs(p.default)
+            ctyp = "i" if p.type == "integer" else "r"
+            raw = f"PAR({p.index})"
+            self.S.append(f"{cn} = GIVEN({p.index}) ? {self._cast(raw, 'r', ctyp)} : {self._cast(dflt, t, ctyp)};")
+            self.static_vars.add(cn)
+        body = ("block", None, list(mod.analog), {})
+        pruned, _ = prune_dead(body, set(), mod.functions)
+        if pruned is not None:
+            self.stmt(pruned)
+        nt = len(self.terms)
+        # outputs
+        jrow, jcol = [], []
+        out_lines = []
+        for kk in range(nt):
+            si, sq = self.state.get(f"accI_{kk}"), self.state.get(f"accQ_{kk}")
+            out_lines.append(f"OUT_I({kk}, {'accI_%d' % kk if si else '0.0'});")
+            out_lines.append(f"OUT_Q({kk}, {'accQ_%d' % kk if sq else '0.0'});")
+            di = si.deps if si else frozenset()
+            dq = sq.deps if sq else frozenset()
+            for ll in sorted(di | dq):
+                g = f"accI_{kk}__d{ll}" if ll in di else "0.0"
+                cq = f"accQ_{kk}__d{ll}" if ll in dq else "0.0"
+                out_lines.append(f"OUT_J({len(jrow)}, {kk}, {ll}, {g}, {cq});")
+                jrow.append(kk)
+                jcol.append(ll)
+        src = self._render(out_lines)
+        ptypes = [p.type for p in mod.params]
+        return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
+                             ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census))
+
+    def _c_function(self, f: Function) -> str:
+        """value-only C translation of an analog function (used by the setup stream)"""
+        sub = _Compiler.__new__(_Compiler)
+        sub.__dict__.update(self.__dict__)
+        sub.S, sub.E, sub.state, sub.scopes = [], [], {}, [dict((v, "l_" + v) for v in f.var_types)]
+        sub.types = dict(self.types)
+        sub.dynctl = False
+        sub.static_vars = set()
+        for v, t in f.var_types.items():
+            sub.types["l_" + v] = "i" if t == "integer" else "r"
+            sub.state["l_" + v] = VS(False, frozenset(), None, None)
+        outs = {a for a, kind in f.args if kind != "input"}
+        sig = []
+        for a, kind in f.args:
+            ct = "int" if f.var_types.get(a) == "integer" else "double"
+            sig.append(f"{ct}{'*' if kind != 'input' else ''} {'o_' if kind != 'input' else 'l_'}{a}")
+        lines = []
+        rt = "int" if f.type == "integer" else "double"
+        lines.append(f"VA_FN {rt} f_{f.name}({', '.join(sig)}) {{")
+        for v, t in f.var_types.items():
+            if v in [a for a, k in f.args if k == "input"]:
+                continue
+            init = f"*o_{v}" if v in outs and dict(f.args)[v] == "inout" else "0"
+            lines.append(f"    {'int' if t == 'integer' else 'double'} l_{v} = {init};")
+        sub.stmt(f.body)
+        if sub.E:
+            raise VACompileError(f"function {f.name} touches bias-dependent state")
+        lines.extend("    " + l for l in sub.S)
+        for v in outs:
+            lines.append(f"    *o_{v} = l_{v};")
+        lines.append(f"    return l_{f.name};")
+        lines.append("}")
+        self.used_funcs |= sub.used_funcs
+        return "\n".join(lines)
+
+    def _render(self, out_lines: List[str]) -> str:
+        nt = len(self.terms)
+        L: List[str] = []
+        L.append(f"// generated by cedarsim.jl_b200.va.compiler from Verilog-A module '{self.mod.name}'")
+        L.append(f"// terminals: {', '.join(self.terms)}   cache slots: {self.nslot}")
+        # helper functions used by setup (emit in dependency-safe order: iterate to closure)
+        done: Dict[str, str] = {}
+        pending = set(self.used_funcs)
+        while pending:
+            fn = pending.pop()
+            if fn in done:
+                continue
+            before = set(self.used_funcs)
+            done[fn] = self._c_function(self.mod.functions[fn])
+            pending |= (self.used_funcs - before) - set(done)
+        order = [fn for fn in self.mod.functions if fn in done]  # declaration order
+        for fn in order:
+            L.append(done[fn])
+        L.append(f"VA_SETUP_BEGIN({self.name})")
+        for cn in sorted(self.static_vars):
+            ct = "int" if self.types.get(cn) == "i" else "double"
+            L.append(f"    {ct} {cn} = 0;")
+        L.extend("    " + l for l in self.S)
+        L.append(f"VA_SETUP_END({self.name})")
+        L.append(f"VA_EVAL_BEGIN({self.name})")
+        for cn in sorted(self.dyn_vars):
+            if self.types.get(cn) == "i":
+                L.append(f"    int {cn} = 0;")
+            else:
+                L.append(f"    double {cn} = 0.0;")
+                for kk in sorted(self.decl_deps.get(cn, ())):
+                    L.append(f"    double {cn}__d{kk} = 0.0;")
+        L.extend("    " + l for l in self.E)
+        L.extend("    " + l for l in out_lines)
+        L.append(f"VA_EVAL_END({self.name})")
+        return "\n".join(L) + "\n"
+
+
+def compile_module(mod: Module, name: Optional[str] = None) -> CompiledModel:
+    return _Compiler(mod, name or mod.name).compile()
+
+
+def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,
+                    include_paths: Sequence[str] = (), defines=None, suppress_defines=()) -> CompiledModel:
+    pp = Preprocessor(include_paths, defines, suppress_defines)
+    text = pp.process_file(path)
+    return compile_va_text(text, module, name, preprocessed=True)
+
+
+def compile_va_text(text: str, module: Optional[str] = None, name: Optional[str] = None,
+                    preprocessed: bool = False, defines=None) -> CompiledModel:
+    if not preprocessed:
+        text = Preprocessor((), defines).process_text(text)
+    mods = parse(text)
+    if not mods:
+        raise VACompileError("no module found")
+    mod = mods[-1] if module is None else next(m for m in mods if m.name == module)
+    return compile_module(mod, name)

@@ -1,0 +1,606 @@
+// oracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A plain scalar-FP64 restatement of the CedarSim sweep hot path, used solely as the
+// checker for the CUDA engine (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline
+// and --impl reference legs).  Nothing in the product path links, imports or executes
+// this file; the product fails loudly without its CUDA extension.
+//
+// What is restated, and from where (paths relative to /root/reference):
+//   * equation formulation and sign conventions: src/simulate_ir.jl:28-75,112-140
+//       (per net one voltage + one KCL; per branch one current with -I into net+, +I
+//        into net-, i.e. positive current flows + -> - through the device)
+//   * primitive devices: src/simpledevices.jl:49-77 (R), 99-109 (C), 122-132 (L),
+//       274-300 (V, dc/tran selection by sim_mode), 315-339 (I), 341-373 (E/G)
+//   * source waveforms: src/spectre_env.jl:15-21 (find_t_in_ts), 43-69 (pwl_at_time),
+//       153-166 (pulse), 169-176 (spsin), 190-196 ($time() == 0 in :dcop)
+//   * DC operating point definition: src/dcop.jl:96-155 (root of F(x, xdot=0, t=0) in
+//       :dcop mode, abstol 1e-10 on the residual, maxiters 200)
+//   * Verilog-A device semantics: src/vasim.jl:663-875 through the generated C model
+//       functions (host_setup / host_eval in cb_va_model)
+//
+// The arithmetic that CedarSim delegates to un-vendored packages (Newton, LU, BDF/trap
+// stepping, LTE control: DAECompiler 1.21.0, OrdinaryDiffEq 6.87.0, Sundials 5.2.3,
+// NonlinearSolve 3.13.1 -- Manifest.toml) is restated here as the textbook algorithms
+// (dense LU with partial pivoting, damped Newton, BE start-up + trapezoidal/BDF2 with
+// predictor-corrector LTE control).  Parity pins: see tests/test_oracle_golden.py, which
+// checks this oracle against the reference's own known answers (test/basic.jl,
+// test/sweep.jl, test/transients.jl).  Transistor-level waveforms: parity unpinned in
+// the reference itself.
+//
+// "No cleverness": dense matrices, partial pivoting, one instance at a time.
+
+#include "../include/cedarb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+typedef void (*va_setup_fn)(const double* par, const uint8_t* given, double temp_c, double gmin,
+                            double* cache);
+typedef void (*va_eval_fn)(const double* cache, const double* v, double* I, double* Q, double* G,
+                           double* C);
+
+struct Inst {  // one sweep point
+    const cb_flat_circuit* fc;
+    const double* params;  // [P][B]
+    int64_t B, b;
+    double pv(const cb_pref& p) const { return p.col < 0 ? p.value : params[(int64_t)p.col * B + b]; }
+};
+
+// ---------------------------------------------------------------- waveforms
+// src/spectre_env.jl:15-21
+int find_t_in_ts(const double* ts, int n, double t) {
+    int idx = (int)(std::lower_bound(ts, ts + n, t) - ts) + 1;  // 1-based searchsortedfirst
+    if (idx <= n && ts[idx - 1] == t) return idx + 1;
+    return idx;
+}
+
+// src/spectre_env.jl:43-69 (1-based i)
+double pwl_at_time(const double* ts, const double* ys, int n, double t) {
+    int i = find_t_in_ts(ts, n, t);
+    if (i <= 1) return ys[0];
+    if (i > n) return ys[n - 1];
+    if (ys[i - 2] == ys[i - 1]) return ys[i - 1];
+    if (ts[i - 1] == ts[i - 2]) return 0.5 * (ys[i - 2] + ys[i - 1]);
+    double slope = (ys[i - 1] - ys[i - 2]) / (ts[i - 1] - ts[i - 2]);
+    return ys[i - 2] + (t - ts[i - 2]) * slope;
+}
+
+double sind(double deg) { return std::sin(deg * (M_PI / 180.0)); }
+
+double wave_tran(const Inst& in, const cb_wave& w, double t) {
+    switch (w.kind) {
+        case CB_W_DC:
+            return in.pv(w.dc);
+        case CB_W_PWL: {
+            std::vector<double> ys(w.npts);
+            for (int k = 0; k < w.npts; k++) ys[k] = in.pv(w.y[k]);
+            return pwl_at_time(w.t, ys.data(), w.npts, t);
+        }
+        case CB_W_PULSE: {  // src/spectre_env.jl:153-166
+            double v1 = in.pv(w.v[0]), v2 = in.pv(w.v[1]), td = in.pv(w.v[2]), tr = in.pv(w.v[3]),
+                   tf = in.pv(w.v[4]), pw = in.pv(w.v[5]), per = in.pv(w.v[6]);
+            double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
+            double ys[4] = {v1, v2, v2, v1};
+            double tt = std::isinf(per) ? t : std::fmod(t, per);
+            return pwl_at_time(ts, ys, 4, tt);
+        }
+        case CB_W_SIN: {  // src/spectre_env.jl:169-176
+            double vo = in.pv(w.v[0]), va = in.pv(w.v[1]), freq = in.pv(w.v[2]), td = in.pv(w.v[3]),
+                   theta = in.pv(w.v[4]), phase = in.pv(w.v[5]), ncyc = in.pv(w.v[6]);
+            if (td < t && t < ncyc / freq)
+                return vo + va * std::exp(-(t - td) * theta) * sind(360.0 * freq * (t - td) + phase);
+            return vo + va * sind(phase);
+        }
+    }
+    return 0.0;
+}
+
+// src/simpledevices.jl:279-297: dc = something(dc, tran, 0); in :dcop $time() is 0.
+double wave_value(const Inst& in, const cb_wave& w, double t, bool dcop) {
+    if (dcop) return w.has_dc ? in.pv(w.dc) : wave_tran(in, w, 0.0);
+    return wave_tran(in, w, t);
+}
+
+void collect_breakpoints(const cb_flat_circuit* fc, double t0, double t1, std::vector<double>& bp) {
+    bp.clear();
+    for (int i = 0; i < fc->n_waves; i++) {
+        const cb_wave& w = fc->waves[i];
+        if (w.kind == CB_W_PWL) {
+            for (int k = 0; k < w.npts; k++) bp.push_back(w.t[k]);
+        } else if (w.kind == CB_W_PULSE) {
+            double td = w.v[2].value, tr = w.v[3].value, tf = w.v[4].value, pw = w.v[5].value,
+                   per = w.v[6].value;
+            double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
+            for (int k = 0; k < 4; k++) {
+                if (!std::isfinite(ts[k])) continue;
+                if (std::isinf(per)) {
+                    bp.push_back(ts[k]);
+                } else {
+                    for (double base = 0.0; base + ts[k] <= t1; base += per) bp.push_back(base + ts[k]);
+                }
+            }
+        } else if (w.kind == CB_W_SIN) {
+            bp.push_back(w.v[3].value);
+        }
+    }
+    bp.push_back(t1);
+    std::sort(bp.begin(), bp.end());
+    std::vector<double> out;
+    double tiny = 1e-12 * std::max(std::fabs(t1), std::fabs(t1 - t0));
+    for (double b : bp) {
+        if (b <= t0 + tiny || b > t1 + tiny) continue;
+        if (!out.empty() && b - out.back() <= tiny) continue;
+        out.push_back(b);
+    }
+    bp.swap(out);
+}
+
+// ---------------------------------------------------------------- system evaluation
+struct Sys {
+    int N;
+    std::vector<double> f, q, G, C;  // G, C dense row-major N x N
+    void resize(int n) {
+        N = n;
+        f.assign(n, 0);
+        q.assign(n, 0);
+        G.assign((size_t)n * n, 0);
+        C.assign((size_t)n * n, 0);
+    }
+    void zero() {
+        std::fill(f.begin(), f.end(), 0.0);
+        std::fill(q.begin(), q.end(), 0.0);
+        std::fill(G.begin(), G.end(), 0.0);
+        std::fill(C.begin(), C.end(), 0.0);
+    }
+};
+
+inline double xv(const double* x, int i) { return i < 0 ? 0.0 : x[i]; }
+
+struct VaCache {  // per instance: bias-independent values of every VA device
+    std::vector<std::vector<double>> cache;
+};
+
+void va_setup_all(const Inst& in, double temp_c, double gmin, VaCache& vc) {
+    const cb_flat_circuit* fc = in.fc;
+    vc.cache.resize(fc->n_va_insts);
+    for (int d = 0; d < fc->n_va_insts; d++) {
+        const cb_va_inst& vi = fc->va_insts[d];
+        const cb_va_model& m = fc->va_models[vi.model];
+        std::vector<double> par(m.nparam);
+        for (int k = 0; k < m.nparam; k++) par[k] = vi.given[k] ? in.pv(vi.par[k]) : 0.0;
+        vc.cache[d].assign(std::max(1, m.ncache), 0.0);
+        ((va_setup_fn)m.host_setup)(par.data(), vi.given, temp_c, gmin, vc.cache[d].data());
+    }
+}
+
+void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, bool dcop, Sys& s) {
+    const cb_flat_circuit* fc = in.fc;
+    const int N = s.N;
+    s.zero();
+    auto addf = [&](int r, double v) { if (r >= 0) s.f[r] += v; };
+    auto addq = [&](int r, double v) { if (r >= 0) s.q[r] += v; };
+    auto addG = [&](int r, int c, double v) { if (r >= 0 && c >= 0) s.G[(size_t)r * N + c] += v; };
+    auto addC = [&](int r, int c, double v) { if (r >= 0 && c >= 0) s.C[(size_t)r * N + c] += v; };
+    for (int d = 0; d < fc->n_devices; d++) {
+        const cb_device& dv = fc->devices[d];
+        const int p = dv.n[0], n = dv.n[1], cp = dv.n[2], cn = dv.n[3], b = dv.branch;
+        const double m = dv.mult;
+        const double vpn = xv(x, p) - xv(x, n);
+        switch (dv.kind) {
+            case CB_DEV_R: {  // I - V/R = 0
+                double g = m / in.pv(dv.value);
+                addf(p, g * vpn); addf(n, -g * vpn);
+                addG(p, p, g); addG(p, n, -g); addG(n, p, -g); addG(n, n, g);
+            } break;
+            case CB_DEV_C: {  // I - C dV/dt = 0
+                double c = m * in.pv(dv.value);
+                addq(p, c * vpn); addq(n, -c * vpn);
+                addC(p, p, c); addC(p, n, -c); addC(n, p, -c); addC(n, n, c);
+            } break;
+            case CB_DEV_L: {  // V - L dI/dt = 0
+                double ib = x[b];
+                addf(p, m * ib); addf(n, -m * ib);
+                addG(p, b, m); addG(n, b, -m);
+                s.f[b] += vpn; addG(b, p, 1.0); addG(b, n, -1.0);
+                s.q[b] += -in.pv(dv.value) * ib; addC(b, b, -in.pv(dv.value));
+            } break;
+            case CB_DEV_VSRC: {  // V - Vsrc = 0
+                double ib = x[b];
+                addf(p, m * ib); addf(n, -m * ib);
+                addG(p, b, m); addG(n, b, -m);
+                s.f[b] += vpn - wave_value(in, fc->waves[dv.wave], t, dcop);
+                addG(b, p, 1.0); addG(b, n, -1.0);
+            } break;
+            case CB_DEV_ISRC: {  // I - Isrc = 0, I flows p -> n through the source
+                double i = m * wave_value(in, fc->waves[dv.wave], t, dcop);
+                addf(p, i); addf(n, -i);
+            } break;
+            case CB_DEV_VCVS: {
+                double ib = x[b], g = in.pv(dv.value);
+                addf(p, m * ib); addf(n, -m * ib);
+                addG(p, b, m); addG(n, b, -m);
+                s.f[b] += vpn - g * (xv(x, cp) - xv(x, cn));
+                addG(b, p, 1.0); addG(b, n, -1.0); addG(b, cp, -g); addG(b, cn, g);
+            } break;
+            case CB_DEV_VCCS: {
+                double g = m * in.pv(dv.value);
+                double i = g * (xv(x, cp) - xv(x, cn));
+                addf(p, i); addf(n, -i);
+                addG(p, cp, g); addG(p, cn, -g); addG(n, cp, -g); addG(n, cn, g);
+            } break;
+        }
+    }
+    // Verilog-A devices: I(a,b) <+ e  puts +e on KCL(a), -e on KCL(b) (src/vasim.jl:819-839)
+    std::vector<double> v, I, Q, Gl, Cl;
+    for (int d = 0; d < fc->n_va_insts; d++) {
+        const cb_va_inst& vi = fc->va_insts[d];
+        const cb_va_model& m = fc->va_models[vi.model];
+        const int nt = m.nterm;
+        v.assign(nt, 0); I.assign(nt, 0); Q.assign(nt, 0);
+        Gl.assign((size_t)nt * nt, 0); Cl.assign((size_t)nt * nt, 0);
+        for (int k = 0; k < nt; k++) v[k] = xv(x, vi.term[k]);
+        ((va_eval_fn)m.host_eval)(vc.cache[d].data(), v.data(), I.data(), Q.data(), Gl.data(), Cl.data());
+        for (int k = 0; k < nt; k++) {
+            addf(vi.term[k], vi.mult * I[k]);
+            addq(vi.term[k], vi.mult * Q[k]);
+            for (int l = 0; l < nt; l++) {
+                addG(vi.term[k], vi.term[l], vi.mult * Gl[(size_t)k * nt + l]);
+                addC(vi.term[k], vi.term[l], vi.mult * Cl[(size_t)k * nt + l]);
+            }
+        }
+    }
+}
+
+// dense LU, partial pivoting; returns false when singular
+bool lu_solve(std::vector<double>& A, std::vector<double>& b, int N) {
+    std::vector<int> piv(N);
+    for (int k = 0; k < N; k++) {
+        int p = k;
+        double best = std::fabs(A[(size_t)k * N + k]);
+        for (int i = k + 1; i < N; i++) {
+            double a = std::fabs(A[(size_t)i * N + k]);
+            if (a > best) { best = a; p = i; }
+        }
+        if (!(best > 0.0) || !std::isfinite(best)) return false;
+        if (p != k) {
+            for (int j = 0; j < N; j++) std::swap(A[(size_t)k * N + j], A[(size_t)p * N + j]);
+            std::swap(b[k], b[p]);
+        }
+        double inv = 1.0 / A[(size_t)k * N + k];
+        for (int i = k + 1; i < N; i++) {
+            double l = A[(size_t)i * N + k] * inv;
+            if (l == 0.0) continue;
+            A[(size_t)i * N + k] = l;
+            for (int j = k + 1; j < N; j++) A[(size_t)i * N + j] -= l * A[(size_t)k * N + j];
+            b[i] -= l * b[k];
+        }
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        double s = b[i];
+        for (int j = i + 1; j < N; j++) s -= A[(size_t)i * N + j] * b[j];
+        b[i] = s / A[(size_t)i * N + i];
+    }
+    return true;
+}
+
+struct Counters {
+    int64_t newton = 0, factors = 0, accepted = 0, rejected = 0;
+};
+
+struct Solver {
+    Inst in;
+    const cb_options* opt;
+    int N, NV;
+    VaCache vc;
+    Sys s;
+    std::vector<double> J, rhs;
+    std::vector<uint8_t> lte_mask;
+    Counters cnt;
+
+    void init(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t b, const cb_options* o) {
+        in.fc = fc; in.params = params; in.B = B; in.b = b;
+        opt = o; N = fc->n_unknowns; NV = fc->n_nodes;
+        s.resize(N);
+        J.resize((size_t)N * N); rhs.resize(N);
+        va_setup_all(in, in.pv(o->temp), in.pv(o->gmin), vc);
+        lte_mask.assign(N, 0);
+        for (int i = 0; i < NV; i++) lte_mask[i] = 1;
+        for (int d = 0; d < fc->n_devices; d++)
+            if (fc->devices[d].kind == CB_DEV_L) lte_mask[fc->devices[d].branch] = 1;
+    }
+    double atol_nr(int i) const { return i < NV ? opt->nr_vabstol : opt->nr_iabstol; }
+    double atol_lte(int i) const { return i < NV ? opt->vabstol : opt->iabstol; }
+
+    // One Newton solve of  f(x,t) + alpha*q(x) + beta + gshunt*x_nodes = 0  starting at x.
+    // On success x holds the converged iterate and qk the charges of the last evaluation.
+    // Returns 0 ok, 1 max iterations, 4 singular / non-finite.
+    int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
+               double gshunt, int maxit, double restol, std::vector<double>& qk) {
+        for (int it = 0; it < maxit; it++) {
+            eval_system(in, vc, x.data(), t, dcop, s);
+            cnt.newton++;
+            double rmax = 0.0;
+            for (int i = 0; i < N; i++) {
+                double r = s.f[i] + alpha * s.q[i] + (beta ? beta[i] : 0.0);
+                if (i < NV) r += gshunt * x[i];
+                rhs[i] = -r;
+                rmax = std::max(rmax, std::fabs(r));
+            }
+            for (size_t k = 0; k < (size_t)N * N; k++) J[k] = s.G[k] + alpha * s.C[k];
+            for (int i = 0; i < NV; i++) J[(size_t)i * N + i] += gshunt;
+            cnt.factors++;
+            if (!lu_solve(J, rhs, N)) return 4;
+            double dvmax = 0.0;
+            bool finite = true;
+            for (int i = 0; i < N; i++) {
+                if (!std::isfinite(rhs[i])) finite = false;
+                if (i < NV) dvmax = std::max(dvmax, std::fabs(rhs[i]));
+            }
+            if (!finite) return 4;
+            double sc = dvmax > opt->dv_max ? opt->dv_max / dvmax : 1.0;
+            bool conv = (sc == 1.0) && (rmax <= restol);
+            for (int i = 0; i < N; i++) {
+                double dx = sc * rhs[i];
+                double xn = x[i] + dx;
+                if (std::fabs(dx) > opt->nr_reltol * std::max(std::fabs(xn), std::fabs(x[i])) + atol_nr(i))
+                    conv = false;
+                x[i] = xn;
+            }
+            if (conv) { qk = s.q; return 0; }
+        }
+        return 1;
+    }
+
+    // DC operating point (src/dcop.jl:96-155) with gmin-stepping fallback.
+    int dc(std::vector<double>& x) {
+        std::vector<double> qk;
+        x.assign(N, 0.0);
+        int rc = newton(x, 0.0, true, 0.0, nullptr, 0.0, opt->max_newton_dc, opt->dc_abstol, qk);
+        if (rc == 0) return CB_ST_SUCCESS;
+        x.assign(N, 0.0);
+        double g = 1e-2;
+        for (int st = 0; st < opt->gmin_steps; st++, g *= 0.1) {
+            std::vector<double> xs = x;
+            rc = newton(xs, 0.0, true, 0.0, nullptr, g, opt->max_newton_dc, opt->dc_abstol, qk);
+            if (rc == 0) x = xs;  // keep the last good point if a stage fails
+        }
+        rc = newton(x, 0.0, true, 0.0, nullptr, 0.0, opt->max_newton_dc, opt->dc_abstol, qk);
+        return rc == 0 ? CB_ST_SUCCESS : CB_ST_INITIAL_FAILURE;
+    }
+};
+
+// polynomial through the last accepted points, evaluated at tt (nh = how many older points valid)
+void predict(int N, int nh, double tt, double tn, const double* xn, double h1, const double* x1,
+             double h2, const double* x2, double* out) {
+    if (nh <= 0) { std::memcpy(out, xn, sizeof(double) * N); return; }
+    double a = tt - tn;
+    if (nh == 1) {
+        for (int i = 0; i < N; i++) out[i] = xn[i] + a * (xn[i] - x1[i]) / h1;
+        return;
+    }
+    for (int i = 0; i < N; i++) {  // Newton divided differences on t_n, t_n-h1, t_n-h1-h2
+        double d1 = (xn[i] - x1[i]) / h1;
+        double d2 = (x1[i] - x2[i]) / h2;
+        double dd = (d1 - d2) / (h1 + h2);
+        out[i] = xn[i] + a * d1 + a * (a + h1) * dd;
+    }
+}
+
+int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsave, double* y_out,
+             int64_t B, int64_t b) {
+    const cb_options* opt = S.opt;
+    const cb_flat_circuit* fc = S.in.fc;
+    const int N = S.N, O = fc->n_outputs;
+    std::vector<double> xn(N, 0.0), x1(N), x2(N), x(N), xp(N), qn(N), q1(N), qd(N, 0.0), beta(N), qk;
+    auto emit = [&](int64_t s, const double* xx) {
+        for (int o = 0; o < O; o++) y_out[((int64_t)o * nsave + s) * B + b] = xx[fc->outputs[o]];
+    };
+    int st = CB_ST_SUCCESS;
+    if (!opt->skip_dc) st = S.dc(xn);
+    // charges at the operating point; qdot(t0) = 0 (steady state)
+    eval_system(S.in, S.vc, xn.data(), 0.0, true, S.s);
+    qn = S.s.q;
+    const double span = t1 - t0;
+    const double teps = 1e-12 * std::max(std::fabs(t1), span);
+    int64_t sidx = 0;
+    while (sidx < nsave && saveat[sidx] <= t0 + teps) emit(sidx++, xn.data());
+    if (st != CB_ST_SUCCESS) {
+        for (; sidx < nsave; sidx++) emit(sidx, xn.data());
+        return st;
+    }
+    std::vector<double> bp;
+    collect_breakpoints(fc, t0, t1, bp);
+    size_t bpi = 0;
+    const bool fixed = opt->fixed_step != 0;
+    const double dtmax = opt->dt_max > 0 ? opt->dt_max : span / 50.0;
+    double hprop = opt->dt > 0 ? opt->dt : span * 1e-5;
+    double t = t0, h1 = 0, h2 = 0;
+    int nh = 0;  // valid older history points (x1, x2)
+    int64_t kstep = 0;
+    const int64_t nfixed = fixed ? (int64_t)std::llround(span / opt->dt) : 0;
+    std::vector<double> tmp(N);
+    while (fixed ? kstep < nfixed : t < t1 - teps) {
+        double h, tnew;
+        bool hit_bp = false;
+        if (fixed) {
+            tnew = t0 + (double)(kstep + 1) * opt->dt;
+            h = tnew - t;
+        } else {
+            while (bpi < bp.size() && bp[bpi] <= t + teps) bpi++;
+            double tb = bpi < bp.size() ? bp[bpi] : t1;
+            h = std::min(hprop, dtmax);
+            if (t + h >= tb - 1e-3 * h) { h = tb - t; tnew = tb; hit_bp = true; }
+            else if (t + 2.0 * h > tb) { h = 0.5 * (tb - t); tnew = t + h; }
+            else tnew = t + h;
+        }
+        const int method = nh == 0 ? CB_METHOD_BE : opt->method;
+        double alpha;
+        if (method == CB_METHOD_BE) {
+            alpha = 1.0 / h;
+            for (int i = 0; i < N; i++) beta[i] = -alpha * qn[i];
+        } else if (method == CB_METHOD_TRAP) {
+            alpha = 2.0 / h;
+            for (int i = 0; i < N; i++) beta[i] = -alpha * qn[i] - qd[i];
+        } else {  // variable-step BDF2
+            double rho = h / h1;
+            alpha = (1.0 + 2.0 * rho) / (h * (1.0 + rho));
+            double a1 = -(1.0 + rho) / h, a2 = rho * rho / (h * (1.0 + rho));
+            for (int i = 0; i < N; i++) beta[i] = a1 * qn[i] + a2 * q1[i];
+        }
+        const int np = (method == CB_METHOD_BE) ? std::min(nh, 1) : nh;  // predictor order
+        predict(N, np, tnew, t, xn.data(), h1, x1.data(), h2, x2.data(), xp.data());
+        x = xp;
+        int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);
+        if (rc != 0) {
+            S.cnt.rejected++;
+            if (fixed) { st = rc == 1 ? CB_ST_MAXITERS : CB_ST_UNSTABLE; break; }
+            hprop = h / 8.0;
+            if (hprop < opt->dt_min) { st = CB_ST_DT_LESS_THAN_MIN; break; }
+            continue;
+        }
+        double fac = 2.0;
+        if (!fixed && np >= 1) {
+            // local truncation error from the predictor-corrector difference
+            double ratio;
+            if (method == CB_METHOD_BE) ratio = h / (2.0 * h + h1);
+            else {
+                double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
+                double lc = method == CB_METHOD_TRAP ? h * h * h / 12.0
+                                                     : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
+                ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
+            }
+            double err = 0.0;
+            for (int i = 0; i < N; i++) {
+                if (!S.lte_mask[i]) continue;
+                double tol = opt->reltol * std::max(std::fabs(x[i]), std::fabs(xn[i])) + S.atol_lte(i);
+                err = std::max(err, ratio * std::fabs(x[i] - xp[i]) / tol);
+            }
+            const int p = (method == CB_METHOD_BE || np < 2) ? 1 : 2;
+            fac = err > 0 ? 0.9 * std::pow(err, -1.0 / (p + 1)) : 2.0;
+            fac = std::min(2.0, std::max(0.2, fac));
+            if (err > 1.0) {
+                S.cnt.rejected++;
+                hprop = h * fac;
+                if (hprop < opt->dt_min) { st = CB_ST_DT_LESS_THAN_MIN; break; }
+                continue;
+            }
+        }
+        // accept
+        S.cnt.accepted++;
+        for (int i = 0; i < N; i++) qd[i] = alpha * qk[i] + beta[i];
+        x2.swap(x1); x1.swap(xn); xn.swap(x);
+        q1.swap(qn); qn = qk;
+        h2 = h1; h1 = h;
+        nh = std::min(nh + 1, 2);
+        t = tnew;
+        kstep++;
+        // outputs by interpolation on the accepted polynomial
+        while (sidx < nsave && saveat[sidx] <= t + teps) {
+            double ts = saveat[sidx];
+            if (std::fabs(ts - t) <= teps) emit(sidx, xn.data());
+            else {
+                int ni = (opt->method == CB_METHOD_BE) ? 1 : std::min(nh, 2);
+                predict(N, ni, ts, t, xn.data(), h1, x1.data(), h2, x2.data(), tmp.data());
+                emit(sidx, tmp.data());
+            }
+            sidx++;
+        }
+        if (!fixed) {
+            hprop = h * fac;
+            if (hit_bp) {  // restart after a source corner: BE, short step
+                nh = 0;
+                double nb = (bpi + 1 < bp.size()) ? bp[bpi + 1] - t : t1 - t;
+                hprop = std::min(hprop, 0.1 * std::min(h, nb > 0 ? nb : h));
+                hprop = std::max(hprop, span * 1e-9);
+            }
+        }
+    }
+    for (; sidx < nsave; sidx++) emit(sidx, xn.data());
+    return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_options_default(cb_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->temp.value = 27.0; o->temp.col = -1;
+    o->gmin.value = 1e-12; o->gmin.col = -1;
+    o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
+    o->nr_reltol = 1e-6; o->nr_vabstol = 1e-9; o->nr_iabstol = 1e-12;
+    o->dc_abstol = 1e-10; o->dv_max = 0.5;
+    o->max_newton_dc = 200; o->max_newton_tran = 20;
+    o->method = CB_METHOD_TRAP; o->fixed_step = 0;
+    o->dt = 0; o->dt_min = 1e-18; o->dt_max = 0;
+    o->gmin_steps = 10; o->skip_dc = 0;
+}
+
+// DC sweep: x_out [O][B], x_full [N][B] (optional), status [B].  Serial over points like
+// the reference's broadcast (src/sweeps.jl:473); nthreads > 1 uses OpenMP for the timing baseline.
+int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_options* opt,
+           double* x_out, double* x_full, int32_t* status, cb_stats* stats, int nthreads) {
+    int64_t newton = 0, factors = 0;
+    const int N = fc->n_unknowns;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors)
+    for (int64_t b = 0; b < B; b++) {
+        Solver S;
+        S.init(fc, params, B, b, opt);
+        std::vector<double> x;
+        status[b] = S.dc(x);
+        for (int o = 0; o < fc->n_outputs; o++) x_out[(int64_t)o * B + b] = x[fc->outputs[o]];
+        if (x_full)
+            for (int i = 0; i < N; i++) x_full[(int64_t)i * B + b] = x[i];
+        newton += S.cnt.newton; factors += S.cnt.factors;
+    }
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->newton_iters = newton; stats->lu_factors = factors; }
+    return 0;
+}
+
+int orc_tran(const cb_flat_circuit* fc, const double* params, int64_t B, double t0, double t1,
+             const double* saveat, int64_t nsave, const cb_options* opt, double* y_out,
+             int32_t* status, cb_stats* stats, int nthreads) {
+    int64_t newton = 0, factors = 0, acc = 0, rej = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors, acc, rej)
+    for (int64_t b = 0; b < B; b++) {
+        Solver S;
+        S.init(fc, params, B, b, opt);
+        status[b] = tran_one(S, t0, t1, saveat, nsave, y_out, B, b);
+        newton += S.cnt.newton; factors += S.cnt.factors; acc += S.cnt.accepted; rej += S.cnt.rejected;
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->newton_iters = newton; stats->lu_factors = factors;
+        stats->steps_accepted = acc; stats->steps_rejected = rej;
+    }
+    return 0;
+}
+
+// One evaluation of the assembled system at x (for Jacobian / stamp tests):
+// f[N], q[N], G[N*N], C[N*N] row-major.
+int orc_eval(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t b,
+             const cb_options* opt, const double* x, double t, int dcop, double* f, double* q,
+             double* G, double* C) {
+    Solver S;
+    S.init(fc, params, B, b, opt);
+    eval_system(S.in, S.vc, x, t, dcop != 0, S.s);
+    const int N = S.N;
+    std::memcpy(f, S.s.f.data(), sizeof(double) * N);
+    std::memcpy(q, S.s.q.data(), sizeof(double) * N);
+    std::memcpy(G, S.s.G.data(), sizeof(double) * N * N);
+    std::memcpy(C, S.s.C.data(), sizeof(double) * N * N);
+    return 0;
+}
+
+double orc_wave_value(const cb_flat_circuit* fc, int wave, const double* params, int64_t B, int64_t b,
+                      double t, int dcop) {
+    Inst in; in.fc = fc; in.params = params; in.B = B; in.b = b;
+    return wave_value(in, fc->waves[wave], t, dcop != 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""ctypes wrapper of the CPU oracle (oracle/oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _here, "-s"], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_here, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        _lib.orc_wave_value.restype = C.c_double
+    return _lib
+
+
+def _flat():
+    import cedarsim.jl_b200.flat as flat
+    return flat
+
+
+def default_options(**kw):
+    flat = _flat()
+    o = flat.cb_options()
+    lib().orc_options_default(C.byref(o))
+    for k, v in kw.items():
+        if k in ("temp", "gmin"):
+            setattr(o, k, flat._pref(v))
+        else:
+            if not hasattr(o, k):
+                raise KeyError(k)
+            setattr(o, k, v)
+    return o
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def dc(fc, params=None, B=1, opts=None, nthreads=1):
+    """fc: FlatCircuit. Returns (x_out [O,B], x_full [N,B], status [B], stats dict)."""
+    flat = _flat()
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), B)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    if params.size:
+        B = params.shape[1]
+    opts = opts or default_options()
+    O, N = len(fc.outputs), fc.n_unknowns
+    x_out = np.zeros((O, B)); x_full = np.zeros((N, B)); status = np.zeros(B, dtype=np.int32)
+    st = flat.cb_stats()
+    rc = lib().orc_dc(pk.ref(), _dp(params), C.c_int64(B), C.byref(opts), _dp(x_out), _dp(x_full),
+                      status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st), C.c_int(nthreads))
+    assert rc == 0
+    return x_out, x_full, status, st.as_dict()
+
+
+def tran(fc, t0, t1, saveat, params=None, B=1, opts=None, nthreads=1):
+    """Returns (y [O,S,B], status [B], stats dict)."""
+    flat = _flat()
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), B)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    if params.size:
+        B = params.shape[1]
+    opts = opts or default_options()
+    saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+    O, S = len(fc.outputs), len(saveat)
+    y = np.zeros((O, S, B)); status = np.zeros(B, dtype=np.int32)
+    st = flat.cb_stats()
+    rc = lib().orc_tran(pk.ref(), _dp(params), C.c_int64(B), C.c_double(t0), C.c_double(t1), _dp(saveat),
+                        C.c_int64(S), C.byref(opts), _dp(y), status.ctypes.data_as(C.POINTER(C.c_int32)),
+                        C.byref(st), C.c_int(nthreads))
+    assert rc == 0
+    return y, status, st.as_dict()
+
+
+def eval_system(fc, x, t=0.0, dcop=False, params=None, b=0, opts=None):
+    """One assembled evaluation: returns f[N], q[N], G[N,N], C[N,N]."""
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), 1)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    B = params.shape[1]
+    opts = opts or default_options()
+    N = fc.n_unknowns
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    f = np.zeros(N); q = np.zeros(N); G = np.zeros((N, N)); Cm = np.zeros((N, N))
+    lib().orc_eval(pk.ref(), _dp(params), C.c_int64(B), C.c_int64(b), C.byref(opts), _dp(x), C.c_double(t),
+                   C.c_int(1 if dcop else 0), _dp(f), _dp(q), _dp(G), _dp(Cm))
+    return f, q, G, Cm
+
+
+def wave_value(fc, wave, t, dcop=False, params=None, b=0):
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), 1)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    return lib().orc_wave_value(pk.ref(), C.c_int(wave), _dp(params), C.c_int64(params.shape[1]), C.c_int64(b),
+                                C.c_double(t), C.c_int(1 if dcop else 0))
