@@ -1,0 +1,138 @@
+"""Programmatic builders of the benchmark / parity workloads.
+
+BSIM4 and the GF180 / sky130 cards are not in the reference tree, so the
+transistor-level workloads use BSIM-CMG 107 with the ASAP7 cards, same topologies:
+  * fet_iv        : config 4, single nFET DC I-V sweep over (vg, vd)
+  * inverter      : configs 1/2, CMOS inverter driven by a PWL source, sweep vdd x nfin x l
+  * dff           : config 3, the 30-FET D flip-flop of test/DFF/*.ngspice (topology restated
+                    here with ASAP7 devices, 0.7 V supply and time axis scaled to FinFET speeds)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import models
+from .flat import FlatCircuit, VAModelShape, Wave, W_PWL, W_DC
+
+
+def _shape(cm, host_model=None) -> VAModelShape:
+    if host_model is not None:
+        return host_model.shape()
+    return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol))
+
+
+def fet_iv(host_model=None, card: str = "nmos_lvt", nfin: float = 3.0, l: float = 20e-9):
+    cm, cards = models.bsimcmg107(), models.asap7_cards()
+    fc = FlatCircuit()
+    m = fc.va_model(_shape(cm, host_model))
+    fc.vsource("Vg", "g", "0", fc.param("vg.dc"))
+    fc.vsource("Vd", "d", "0", fc.param("vd.dc"))
+    fc.va_instance("m1", m, ["d", "g", "0", "0"], dict(cards[card].params, L=l, NFIN=nfin))
+    fc.set_outputs(["vd.i", "m1.di", "m1.si"])
+    return fc, [cm]
+
+
+def inverter(host_model=None, vdd=0.7, sweep: bool = True, cload: float = 1e-15, tscale: float = 1.0):
+    """CMOS inverter, topology of benchmarks/benchmark_common.jl:82-106 (Xneg/Xpos, VVDD, VD PWL,
+    CQ on the output).  Swept columns: vvdd.dc, xneg.nfin, xneg.l (FinFET analogue of W, L)."""
+    cm, cards = models.bsimcmg107(), models.asap7_cards()
+    fc = FlatCircuit()
+    m = fc.va_model(_shape(cm, host_model))
+    vd = fc.param("vvdd.dc") if sweep else vdd
+    nfin = fc.param("xneg.nfin") if sweep else 3.0
+    ln = fc.param("xneg.l") if sweep else 21e-9
+    fc.vsource("VVDD", "vdd", "0", vd)
+    fc.vsource("VVSS", "vss", "0", 0.0)
+    # 8-point PWL on D with 10 ns edges (scaled), amplitude follows the nominal supply
+    t = np.array([0, 50, 60, 150, 160, 250, 260, 400]) * 1e-9 * tscale
+    y = [0.0, 0.0, vdd, vdd, 0.0, 0.0, vdd, vdd]
+    fc.vsource("VD", "d", "0", Wave(W_PWL, t=list(t), y=y))
+    fc.va_instance("xneg", m, ["q", "d", "vss", "vss"], dict(cards["nmos_lvt"].params, L=ln, NFIN=nfin))
+    fc.va_instance("xpos", m, ["q", "d", "vdd", "vdd"], dict(cards["pmos_lvt"].params, L=21e-9, NFIN=3.0))
+    fc.capacitor("CQ", "q", "0", cload)
+    fc.set_outputs(["q", "d"])
+    return fc, [cm]
+
+
+# (name, drain, gate, source, bulk, kind, nfin): topology of
+# test/DFF/gf180mcu_fd_sc_mcu7t5v0__dffnq_4.ngspice:4-58, widths mapped to fin counts
+_DFF_FETS: List[Tuple[str, str, str, str, str, str, int]] = [
+    ("x_tn10", "vss", "d", "d_neg", "vpw", "n", 2), ("x_tp10", "vdd", "d", "d_neg", "vnw", "p", 3),
+    ("x_tn11", "d_neg", "cki", "d_neg_clked", "vpw", "n", 2), ("x_tp11", "d_neg_clked", "ncki", "d_neg", "vnw", "p", 3),
+    ("x_tn15", "q_internal", "d_neg_clked", "vss", "vpw", "n", 2), ("x_tp15", "q_internal", "d_neg_clked", "vdd", "vnw", "p", 3),
+    ("x_tn0", "d_neg_clked", "ncki", "net11", "vpw", "n", 2), ("x_tp0", "net4", "cki", "d_neg_clked", "vnw", "p", 3),
+    ("x_tn1", "vss", "q_internal", "net11", "vpw", "n", 2), ("x_tp1", "vdd", "q_internal", "net4", "vnw", "p", 3),
+    ("x_tn2", "net0", "ncki", "q_internal", "vpw", "n", 2), ("x_tp7", "net0", "cki", "q_internal", "vnw", "p", 3),
+    ("x_tn3", "net7", "cki", "net0", "vpw", "n", 2), ("x_tp6", "net7", "ncki", "net0", "vnw", "p", 3),
+    ("x_tn5", "q_neg", "net0", "vss", "vpw", "n", 5), ("x_tp3", "q_neg", "net0", "vdd", "vnw", "p", 6),
+    ("x_tn4", "vss", "q_neg", "net7", "vpw", "n", 5), ("x_tp2", "vdd", "q_neg", "net7", "vnw", "p", 6),
+    ("x_tn6_7", "q", "q_neg", "vss", "vpw", "n", 4), ("x_tn6", "q", "q_neg", "vss", "vpw", "n", 4),
+    ("x_tn6_7_61", "q", "q_neg", "vss", "vpw", "n", 4), ("x_tn6_49", "q", "q_neg", "vss", "vpw", "n", 4),
+    ("x_tp4_13", "q", "q_neg", "vdd", "vnw", "p", 6), ("x_tp4", "q", "q_neg", "vdd", "vnw", "p", 6),
+    ("x_tp4_13_64", "q", "q_neg", "vdd", "vnw", "p", 6), ("x_tp4_55", "q", "q_neg", "vdd", "vnw", "p", 6),
+    ("x_tn9", "ncki", "clkn", "vss", "vpw", "n", 3), ("x_tp9", "ncki", "clkn", "vdd", "vnw", "p", 5),
+    ("x_tn16", "cki", "ncki", "vss", "vpw", "n", 3), ("x_tp16", "cki", "ncki", "vdd", "vnw", "p", 5),
+]
+DFF_FET_NAMES = [f[0] for f in _DFF_FETS]
+
+
+def dff(host_model=None, vdd: float = 0.7, sweep: bool = True, tscale: float = 1.0, cq: float = 2e-15):
+    """30-FET DFF + 7 V sources + load cap, deck shape of test/DFF/DFF_cap_all.cir.  With `sweep`
+    every FET gets two swept columns `<inst>.l` and `<inst>.nfin` (P = 60, Monte-Carlo draws are
+    supplied by the caller as a TandemSweep of pre-drawn values)."""
+    cm, cards = models.bsimcmg107(), models.asap7_cards()
+    fc = FlatCircuit()
+    m = fc.va_model(_shape(cm, host_model))
+    fc.vsource("VVDD", "vdd", "0", vdd)
+    fc.vsource("VVSS", "vss", "0", 0.0)
+    for name, d, g, s, b, kind, nfin in _DFF_FETS:
+        card = cards["nmos_lvt" if kind == "n" else "pmos_lvt"].params
+        ln = fc.param(f"{name}.l") if sweep else 21e-9
+        nf = fc.param(f"{name}.nfin") if sweep else float(nfin)
+        fc.va_instance(name, m, [d, g, s, b], dict(card, L=ln, NFIN=nf))
+    fc.capacitor("CQ", "q_tmp", "0", cq)
+    fc.vsource("VQ", "q", "q_tmp", 0.0)
+    fc.vsource("VNW", "vnw", "vdd", 0.0)
+    fc.vsource("VPW", "vpw", "vss", 0.0)
+    ps = 1e-12 * tscale
+    tc = np.array([0, 50000, 51020, 100000, 101020, 400000, 401020, 500000, 501020, 600000, 601020, 700000]) * ps
+    yc = [vdd, vdd, 0, 0, vdd, vdd, 0, 0, vdd, vdd, 0, 0]
+    td = np.array([0, 200000, 201020, 300000, 301020, 380000, 381020, 600000]) * ps  # 3rd edge 20 ns early: no D/CLKN race
+    yd = [0, 0, vdd, vdd, 0, 0, vdd, vdd]
+    fc.vsource("VCLKN", "clkn", "0", Wave(W_PWL, t=list(tc), y=yc))
+    fc.vsource("VD", "d", "0", Wave(W_PWL, t=list(td), y=yd))
+    fc.set_outputs(["q", "d"])
+    return fc, [cm]
+
+
+def dff_nominal_params() -> Dict[str, float]:
+    out = {}
+    for name, *_rest, nfin in _DFF_FETS:
+        out[f"{name}.l"] = 21e-9
+        out[f"{name}.nfin"] = float(nfin)
+    return out
+
+
+def dff_mc_params(fc: FlatCircuit, B: int, seed: int = 20240607, sigma: float = 0.02) -> np.ndarray:
+    """Pre-drawn Monte-Carlo values, draw order [instance][device][l, nfin], z ~ N(0,1) truncated
+    at +-3."""
+    rng = np.random.default_rng(seed)
+    z = np.clip(rng.standard_normal((B, len(_DFF_FETS), 2)), -3.0, 3.0)
+    nom = dff_nominal_params()
+    P = np.zeros((len(fc.param_names), B))
+    for k, (name, *_rest) in enumerate(_DFF_FETS):
+        P[fc.param_names.index(f"{name}.l")] = nom[f"{name}.l"] * (1.0 + sigma * z[:, k, 0])
+        P[fc.param_names.index(f"{name}.nfin")] = nom[f"{name}.nfin"] * (1.0 + sigma * z[:, k, 1])
+    return P
+
+
+def two_resistor():
+    """test/sweep.jl:326-340: V = 1 V across R1 + R2, sweep R1 x R2, I(V) = -1/(R1+R2)."""
+    fc = FlatCircuit()
+    fc.vsource("V", "vcc", "0", 1.0)
+    fc.resistor("R1", "vcc", "out", fc.param("R1"))
+    fc.resistor("R2", "out", "0", fc.param("R2"))
+    fc.set_outputs(["v.i", "out"])
+    return fc

@@ -1,0 +1,930 @@
+// cedarb200.cu -- C-ABI shared library of the B200 batched circuit-sweep engine
+// (include/cedarb200.h).  Host side: deep copy of the flat circuit, symbolic analysis,
+// NVRTC compilation of the host-generated device models for sm_100a (+ cubin cache), plan
+// (device memory) management and the lock-step round driver.  Device side: kernels.cuh.
+//
+// There is NO CPU fallback anywhere in this file: without a CUDA device cb_plan_create fails
+// with CB_ERR_NO_DEVICE.
+#include "../../include/cedarb200.h"
+
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "symbolic.hpp"
+#include "va_prelude.h"
+
+using namespace cbk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(CB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+struct WaveH {
+    int kind, has_dc;
+    cb_pref dc;
+    std::vector<double> t;
+    std::vector<cb_pref> y;
+    cb_pref v[7];
+};
+struct ModelH {
+    std::string name;
+    int nterm, nparam, ncache, nj;
+    std::vector<int> jrow, jcol;
+    int nout() const { return 2 * nterm + nj; }
+};
+struct VaInstH {
+    int model;
+    std::vector<int> term;
+    std::vector<cb_pref> par;
+    std::vector<uint8_t> given;
+    double mult;
+};
+
+struct cb_circuit {
+    int N = 0, NV = 0, P = 0;
+    std::vector<cb_device> devs;
+    std::vector<WaveH> waves;
+    std::vector<ModelH> models;
+    std::vector<VaInstH> insts;
+    std::vector<int> outputs;
+    std::string cuda_source;
+    std::vector<char> cubin;
+    bool compiled = false;
+    cb::Symbolic sym;
+    // assembly tables (host copies)
+    std::vector<int> a_ptr, a_src, a_lin;
+    std::vector<double> a_mult;
+    std::vector<uint8_t> a_diag;
+    std::vector<int> ri_ptr, ri_src, rq_ptr, rq_src, rl_ptr, rl_col, rl_lin, rs_ptr, rs_wave;
+    std::vector<double> ri_mult, rq_mult, rs_coef;
+    std::vector<LinContrib> lin_contrib;
+    int nlin = 0;
+    bool lin_swept = false;
+    std::vector<uint8_t> lte_mask;
+    // per-model device instance lists and slot offsets
+    std::vector<std::vector<int>> model_insts;  // model -> global inst ids
+    std::vector<long long> out_off, cache_off;  // per model, in slots
+    long long total_out = 0, total_cache = 0;
+    std::vector<long long> inst_out_base;       // per inst: first slot
+};
+
+extern "C" int cb_version(void) { return CB_ABI_VERSION; }
+extern "C" const char* cb_last_error(void) { return g_err.c_str(); }
+
+extern "C" void cb_options_default(cb_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->temp.value = 27.0; o->temp.col = -1;
+    o->gmin.value = 1e-12; o->gmin.col = -1;
+    o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
+    o->nr_reltol = 1e-6; o->nr_vabstol = 1e-9; o->nr_iabstol = 1e-12;
+    o->dc_abstol = 1e-10; o->dv_max = 0.5;
+    o->max_newton_dc = 200; o->max_newton_tran = 20;
+    o->method = CB_METHOD_TRAP; o->fixed_step = 0;
+    o->dt = 0; o->dt_min = 1e-18; o->dt_max = 0;
+    o->gmin_steps = 10; o->skip_dc = 0;
+}
+
+extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
+    if (!f || !out) return fail(CB_ERR_INVALID, "null argument");
+    if (f->n_unknowns <= 0 || f->n_nodes > f->n_unknowns) return fail(CB_ERR_INVALID, "bad unknown counts");
+    auto c = std::make_unique<cb_circuit>();
+    c->N = f->n_unknowns; c->NV = f->n_nodes; c->P = f->n_params;
+    auto chk = [&](int idx) { return idx >= -1 && idx < c->N; };
+    auto chkp = [&](const cb_pref& p) { return p.col < f->n_params; };
+    for (int i = 0; i < f->n_devices; i++) {
+        const cb_device& d = f->devices[i];
+        for (int k = 0; k < 4; k++) if (!chk(d.n[k])) return fail(CB_ERR_INVALID, "device node index out of range");
+        if (!chk(d.branch) || !chkp(d.value)) return fail(CB_ERR_INVALID, "device branch/param index out of range");
+        if ((d.kind == CB_DEV_VSRC || d.kind == CB_DEV_ISRC) && (d.wave < 0 || d.wave >= f->n_waves))
+            return fail(CB_ERR_INVALID, "source without waveform");
+        if ((d.kind == CB_DEV_L || d.kind == CB_DEV_VSRC || d.kind == CB_DEV_VCVS) && d.branch < 0)
+            return fail(CB_ERR_INVALID, "voltage-defined device without branch unknown");
+        c->devs.push_back(d);
+    }
+    for (int i = 0; i < f->n_waves; i++) {
+        const cb_wave& w = f->waves[i];
+        WaveH h;
+        h.kind = w.kind; h.has_dc = w.has_dc; h.dc = w.dc;
+        if (w.kind == CB_W_PWL) {
+            if (w.npts <= 0) return fail(CB_ERR_INVALID, "empty PWL");
+            h.t.assign(w.t, w.t + w.npts);
+            h.y.assign(w.y, w.y + w.npts);
+        }
+        for (int k = 0; k < 7; k++) h.v[k] = w.v[k];
+        if (w.kind == CB_W_PULSE)
+            for (int k = 2; k < 7; k++)
+                if (w.v[k].col >= 0) return fail(CB_ERR_INVALID, "PULSE timing parameters cannot be swept");
+        c->waves.push_back(std::move(h));
+    }
+    for (int i = 0; i < f->n_va_models; i++) {
+        const cb_va_model& m = f->va_models[i];
+        ModelH h;
+        h.name = m.name ? m.name : "";
+        h.nterm = m.nterm; h.nparam = m.nparam; h.ncache = m.ncache; h.nj = m.nj;
+        h.jrow.assign(m.jrow, m.jrow + m.nj);
+        h.jcol.assign(m.jcol, m.jcol + m.nj);
+        c->models.push_back(std::move(h));
+    }
+    for (int i = 0; i < f->n_va_insts; i++) {
+        const cb_va_inst& v = f->va_insts[i];
+        if (v.model < 0 || v.model >= f->n_va_models) return fail(CB_ERR_INVALID, "VA instance model index");
+        const ModelH& m = c->models[v.model];
+        VaInstH h;
+        h.model = v.model; h.mult = v.mult;
+        h.term.assign(v.term, v.term + m.nterm);
+        for (int t : h.term) if (!chk(t)) return fail(CB_ERR_INVALID, "VA terminal index out of range");
+        h.par.assign(v.par, v.par + m.nparam);
+        h.given.assign(v.given, v.given + m.nparam);
+        c->insts.push_back(std::move(h));
+    }
+    c->outputs.assign(f->outputs, f->outputs + f->n_outputs);
+    for (int o : c->outputs) if (o < 0 || o >= c->N) return fail(CB_ERR_INVALID, "output index out of range");
+    *out = c.release();
+    return CB_OK;
+}
+
+extern "C" int cb_circuit_set_cuda_source(cb_circuit* c, const char* src, size_t len) {
+    if (!c || !src) return fail(CB_ERR_INVALID, "null argument");
+    c->cuda_source.assign(src, len);
+    c->compiled = false;
+    return CB_OK;
+}
+
+static uint64_t fnv1a(const std::string& s) {
+    uint64_t h = 1469598103934665603ULL;
+    for (unsigned char ch : s) { h ^= ch; h *= 1099511628211ULL; }
+    return h;
+}
+
+static int build_tables(cb_circuit* c) {
+    const int N = c->N;
+    std::vector<cb::PatternEntry> pat;
+    for (int i = 0; i < c->NV; i++) pat.push_back({i, i, 0});  // gshunt slot, not a pivot by itself
+    // ---- linear devices: pattern + contributions per (row, col)
+    std::map<std::pair<int, int>, int> lin_index;
+    auto lin_of = [&](int r, int col) {
+        auto key = std::make_pair(r, col);
+        auto it = lin_index.find(key);
+        if (it != lin_index.end()) return it->second;
+        int idx = (int)lin_index.size();
+        lin_index[key] = idx;
+        return idx;
+    };
+    auto add = [&](int r, int col, int cls, cb_pref p, double coef, bool recip, bool is_c) {
+        if (r < 0 || col < 0) return;
+        pat.push_back({r, col, cls});
+        LinContrib k;
+        k.p.value = p.value; k.p.col = p.col; k.p.pad = 0;
+        k.coef = coef; k.entry = lin_of(r, col); k.recip = recip; k.is_c = is_c; k.pad = 0;
+        if (p.col >= 0) c->lin_swept = true;
+        c->lin_contrib.push_back(k);
+    };
+    const cb_pref one = {1.0, -1, 0};
+    std::vector<std::vector<std::pair<int, double>>> src_rows(N);
+    c->lte_mask.assign(N, 0);
+    for (int i = 0; i < c->NV; i++) c->lte_mask[i] = 1;
+    for (const cb_device& d : c->devs) {
+        const int p = d.n[0], n = d.n[1], cp = d.n[2], cn = d.n[3], b = d.branch;
+        const double m = d.mult;
+        switch (d.kind) {
+            case CB_DEV_R:
+                add(p, p, 2, d.value, m, true, false); add(p, n, 1, d.value, -m, true, false);
+                add(n, p, 1, d.value, -m, true, false); add(n, n, 2, d.value, m, true, false);
+                break;
+            case CB_DEV_C:
+                add(p, p, 1, d.value, m, false, true); add(p, n, 1, d.value, -m, false, true);
+                add(n, p, 1, d.value, -m, false, true); add(n, n, 1, d.value, m, false, true);
+                break;
+            case CB_DEV_L:
+                add(p, b, 3, one, m, false, false); add(n, b, 3, one, -m, false, false);
+                add(b, p, 3, one, 1.0, false, false); add(b, n, 3, one, -1.0, false, false);
+                add(b, b, 0, d.value, -1.0, false, true);
+                c->lte_mask[b] = 1;
+                break;
+            case CB_DEV_VSRC:
+                add(p, b, 3, one, m, false, false); add(n, b, 3, one, -m, false, false);
+                add(b, p, 3, one, 1.0, false, false); add(b, n, 3, one, -1.0, false, false);
+                src_rows[b].push_back({d.wave, -1.0});
+                break;
+            case CB_DEV_ISRC:
+                if (p >= 0) src_rows[p].push_back({d.wave, m});
+                if (n >= 0) src_rows[n].push_back({d.wave, -m});
+                break;
+            case CB_DEV_VCVS:
+                add(p, b, 3, one, m, false, false); add(n, b, 3, one, -m, false, false);
+                add(b, p, 3, one, 1.0, false, false); add(b, n, 3, one, -1.0, false, false);
+                add(b, cp, 1, d.value, -1.0, false, false); add(b, cn, 1, d.value, 1.0, false, false);
+                break;
+            case CB_DEV_VCCS:
+                add(p, cp, 1, d.value, m, false, false); add(p, cn, 1, d.value, -m, false, false);
+                add(n, cp, 1, d.value, -m, false, false); add(n, cn, 1, d.value, m, false, false);
+                break;
+            default:
+                return fail(CB_ERR_INVALID, "unknown device kind");
+        }
+    }
+    c->nlin = (int)lin_index.size();
+    // ---- VA devices: slot numbering [model][device][slot]
+    const int nm = (int)c->models.size();
+    c->model_insts.assign(nm, {});
+    for (int i = 0; i < (int)c->insts.size(); i++) c->model_insts[c->insts[i].model].push_back(i);
+    c->out_off.assign(nm, 0); c->cache_off.assign(nm, 0);
+    c->total_out = 0; c->total_cache = 0;
+    c->inst_out_base.assign(c->insts.size(), 0);
+    for (int m = 0; m < nm; m++) {
+        c->out_off[m] = c->total_out;
+        c->cache_off[m] = c->total_cache;
+        for (size_t k = 0; k < c->model_insts[m].size(); k++)
+            c->inst_out_base[c->model_insts[m][k]] = c->total_out + (long long)k * c->models[m].nout();
+        c->total_out += (long long)c->model_insts[m].size() * c->models[m].nout();
+        c->total_cache += (long long)c->model_insts[m].size() * std::max(1, c->models[m].ncache);
+    }
+    for (size_t i = 0; i < c->insts.size(); i++) {
+        const VaInstH& v = c->insts[i];
+        const ModelH& m = c->models[v.model];
+        for (int j = 0; j < m.nj; j++) {
+            const int r = v.term[m.jrow[j]], col = v.term[m.jcol[j]];
+            if (r >= 0 && col >= 0) pat.push_back({r, col, m.jrow[j] == m.jcol[j] ? 2 : 1});
+        }
+    }
+    if (!cb::analyze(N, pat, c->sym)) return fail(CB_ERR_SINGULAR, c->sym.error);
+    const cb::Symbolic& S = c->sym;
+    // ---- J assembly lists per LU entry
+    std::vector<std::vector<std::pair<int, double>>> ent_src(S.nnz_lu);
+    c->a_lin.assign(S.nnz_lu, -1);
+    c->a_diag.assign(S.nnz_lu, 0);
+    for (const auto& kv : lin_index) c->a_lin[S.pos_of_orig.at(kv.first)] = kv.second;
+    for (int i = 0; i < c->NV; i++) c->a_diag[S.pos_of_orig.at({i, i})] = 1;
+    std::vector<std::vector<std::pair<int, double>>> rowI(N), rowQ(N);
+    for (size_t i = 0; i < c->insts.size(); i++) {
+        const VaInstH& v = c->insts[i];
+        const ModelH& m = c->models[v.model];
+        const long long base = c->inst_out_base[i];
+        for (int k = 0; k < m.nterm; k++) {
+            if (v.term[k] < 0) continue;
+            rowI[v.term[k]].push_back({(int)(base + k), v.mult});
+            rowQ[v.term[k]].push_back({(int)(base + m.nterm + k), v.mult});
+        }
+        for (int j = 0; j < m.nj; j++) {
+            const int r = v.term[m.jrow[j]], col = v.term[m.jcol[j]];
+            if (r < 0 || col < 0) continue;
+            ent_src[S.pos_of_orig.at({r, col})].push_back({(int)(base + 2 * m.nterm + j), v.mult});
+        }
+    }
+    auto flatten = [](const std::vector<std::vector<std::pair<int, double>>>& src, std::vector<int>& ptr,
+                      std::vector<int>& idx, std::vector<double>& mult) {
+        ptr.assign(1, 0); idx.clear(); mult.clear();
+        for (const auto& l : src) {
+            for (const auto& p : l) { idx.push_back(p.first); mult.push_back(p.second); }
+            ptr.push_back((int)idx.size());
+        }
+    };
+    flatten(ent_src, c->a_ptr, c->a_src, c->a_mult);
+    flatten(rowI, c->ri_ptr, c->ri_src, c->ri_mult);
+    flatten(rowQ, c->rq_ptr, c->rq_src, c->rq_mult);
+    flatten(src_rows, c->rs_ptr, c->rs_wave, c->rs_coef);
+    c->rl_ptr.assign(1, 0); c->rl_col.clear(); c->rl_lin.clear();
+    {
+        std::vector<std::vector<std::pair<int, int>>> rows(N);
+        for (const auto& kv : lin_index) rows[kv.first.first].push_back({kv.first.second, kv.second});
+        for (int i = 0; i < N; i++) {
+            for (auto& p : rows[i]) { c->rl_col.push_back(p.first); c->rl_lin.push_back(p.second); }
+            c->rl_ptr.push_back((int)c->rl_col.size());
+        }
+    }
+    return CB_OK;
+}
+
+static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
+    std::string full = std::string(CB_VA_PRELUDE) + "\n" + c->cuda_source;
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+    std::string key;
+    {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(full + "|sm_100a|v1"));
+        key = buf;
+    }
+    std::string path;
+    if (cache_dir && *cache_dir) {
+        path = std::string(cache_dir) + "/cb_" + key + ".cubin";
+        std::ifstream in(path, std::ios::binary);
+        if (in) {
+            c->cubin.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+            if (!c->cubin.empty()) return CB_OK;
+        }
+    }
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, full.c_str(), "cb_models.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(CB_ERR_NVRTC, "nvrtcCreateProgram failed");
+    nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, 0);
+        nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        if (log.size() > 6000) log.resize(6000);
+        return fail(CB_ERR_NVRTC, "NVRTC: " + log);
+    }
+    size_t sz = 0;
+    nvrtcGetCUBINSize(prog, &sz);
+    c->cubin.resize(sz);
+    nvrtcGetCUBIN(prog, c->cubin.data());
+    nvrtcDestroyProgram(&prog);
+    if (!path.empty()) {
+        std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+        std::ofstream outf(tmp, std::ios::binary);
+        outf.write(c->cubin.data(), (std::streamsize)c->cubin.size());
+        outf.close();
+        std::rename(tmp.c_str(), path.c_str());
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_circuit_compile(cb_circuit* c, const char* cache_dir, double* compile_seconds) {
+    if (!c) return fail(CB_ERR_INVALID, "null circuit");
+    auto t0 = std::chrono::steady_clock::now();
+    c->lin_contrib.clear();
+    c->lin_swept = false;
+    int rc = build_tables(c);
+    if (rc != CB_OK) return rc;
+    if (!c->models.empty()) {
+        if (c->cuda_source.empty()) return fail(CB_ERR_STATE, "circuit has Verilog-A devices but no CUDA source was set");
+        rc = nvrtc_compile(c, cache_dir);
+        if (rc != CB_OK) return rc;
+    }
+    c->compiled = true;
+    if (compile_seconds)
+        *compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return CB_OK;
+}
+
+extern "C" int cb_circuit_lu_info(const cb_circuit* c, int32_t* nnz_a, int32_t* nnz_lu, int64_t* lu_flops) {
+    if (!c || !c->compiled) return fail(CB_ERR_STATE, "circuit not compiled");
+    if (nnz_a) *nnz_a = c->sym.nnz_a;
+    if (nnz_lu) *nnz_lu = c->sym.nnz_lu;
+    if (lu_flops) *lu_flops = c->sym.flops;
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct cb_plan {
+    cb_circuit* c = nullptr;
+    long long B = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaLibrary_t lib = nullptr;
+    std::vector<cudaKernel_t> k_setup, k_eval;
+    std::vector<void*> allocs;
+    NArgs na{};
+    int G = 8, gpc = 1;
+    size_t smem_bytes = 0;
+    // device arrays
+    double* d_params = nullptr;
+    double* d_cache = nullptr;
+    double* d_dev_out = nullptr;
+    double* d_y = nullptr;
+    size_t y_capacity = 0;
+    double* d_saveat = nullptr;
+    size_t saveat_capacity = 0;
+    double* d_bp = nullptr;
+    size_t bp_capacity = 0;
+    double* d_xout = nullptr;
+    int* d_done = nullptr;
+    int* h_done = nullptr;  // pinned
+    // per-model device tables
+    std::vector<int*> d_term;
+    std::vector<double*> d_par_val;
+    std::vector<int*> d_par_col;
+    std::vector<uint8_t*> d_given;
+    LinContrib* d_lin_contrib = nullptr;
+    double *d_lin_g = nullptr, *d_lin_c = nullptr;
+    int* d_outputs = nullptr;
+    bool params_set = false;
+    bool setup_valid = false;
+    double* d_x0 = nullptr;
+    long long x0_stride = 0;
+    bool have_x0 = false;
+    cb_pref last_temp{}, last_gmin{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    template <class T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+        if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        allocs.push_back(p);
+        *out = (T*)p;
+        return CB_OK;
+    }
+    template <class T>
+    int upload(T** out, const std::vector<T>& v) {
+        int rc = alloc(out, v.size());
+        if (rc != CB_OK) return rc;
+        if (!v.empty()) CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return CB_OK;
+    }
+};
+
+static int pick_group(const cb_circuit* c) {
+    const char* env = std::getenv("CB_GROUP");
+    if (env) { int g = std::atoi(env); if (g == 4 || g == 8 || g == 16 || g == 32) return g; }
+    if (c->sym.nnz_lu <= 64) return 4;
+    if (c->sym.nnz_lu <= 2048) return 8;
+    return 16;
+}
+
+extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** out) {
+    if (!c || !out || n_inst <= 0) return fail(CB_ERR_INVALID, "bad argument");
+    if (!c->compiled) return fail(CB_ERR_STATE, "circuit not compiled");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CB_ERR_NO_DEVICE, "no CUDA device available; this engine has no CPU fallback");
+    if (device_id < 0 || device_id >= ndev) return fail(CB_ERR_INVALID, "device id out of range");
+    CUDA_TRY(cudaSetDevice(device_id));
+    auto p = std::make_unique<cb_plan>();
+    p->c = c; p->B = n_inst; p->device = device_id;
+    const long long B = n_inst;
+    const int N = c->N;
+    const cb::Symbolic& S = c->sym;
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&p->ev0));
+    CUDA_TRY(cudaEventCreate(&p->ev1));
+    int rc;
+#define TRY(x) do { rc = (x); if (rc != CB_OK) return rc; } while (0)
+    if (!c->models.empty()) {
+        CUDA_TRY(cudaLibraryLoadData(&p->lib, c->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        for (const ModelH& m : c->models) {
+            cudaKernel_t ks, ke;
+            CUDA_TRY(cudaLibraryGetKernel(&ks, p->lib, ("k_setup_" + m.name).c_str()));
+            CUDA_TRY(cudaLibraryGetKernel(&ke, p->lib, ("k_eval_" + m.name).c_str()));
+            p->k_setup.push_back(ks);
+            p->k_eval.push_back(ke);
+        }
+    }
+    NArgs& a = p->na;
+    a.B = B; a.N = N; a.NV = c->NV; a.nnz_lu = S.nnz_lu; a.O = (int)c->outputs.size();
+    a.nwaves = (int)c->waves.size();
+    // symbolic + assembly tables
+    int* tmp;
+#define UP(field, vec) do { TRY(p->upload(&tmp, vec)); a.field = tmp; } while (0)
+    UP(diag_pos, S.diag_pos); UP(l_ptr, S.l_ptr); UP(l_pos, S.l_pos); UP(l_row, S.l_row);
+    UP(u_ptr, S.u_ptr); UP(u_pos, S.u_pos); UP(pair_ptr, S.pair_ptr); UP(pair_dst, S.pair_dst);
+    UP(uc_ptr, S.uc_ptr); UP(uc_pos, S.uc_pos); UP(uc_row, S.uc_row);
+    UP(row_to_step, S.row_to_step); UP(col_to_step, S.col_to_step);
+    UP(a_ptr, c->a_ptr); UP(a_src, c->a_src); UP(a_lin, c->a_lin);
+    UP(ri_ptr, c->ri_ptr); UP(ri_src, c->ri_src); UP(rq_ptr, c->rq_ptr); UP(rq_src, c->rq_src);
+    UP(rl_ptr, c->rl_ptr); UP(rl_col, c->rl_col); UP(rl_lin, c->rl_lin);
+    UP(rs_ptr, c->rs_ptr); UP(rs_wave, c->rs_wave);
+#undef UP
+    double* dtmp;
+    TRY(p->upload(&dtmp, c->a_mult)); a.a_mult = dtmp;
+    TRY(p->upload(&dtmp, c->ri_mult)); a.ri_mult = dtmp;
+    TRY(p->upload(&dtmp, c->rq_mult)); a.rq_mult = dtmp;
+    TRY(p->upload(&dtmp, c->rs_coef)); a.rs_coef = dtmp;
+    uint8_t* btmp;
+    TRY(p->upload(&btmp, c->a_diag)); a.a_diag = btmp;
+    TRY(p->upload(&btmp, c->lte_mask)); a.lte_mask = btmp;
+    TRY(p->upload(&p->d_outputs, c->outputs)); a.outputs = p->d_outputs;
+    // waves
+    {
+        std::vector<WaveDev> wd(c->waves.size());
+        for (size_t i = 0; i < c->waves.size(); i++) {
+            const WaveH& w = c->waves[i];
+            WaveDev d{};
+            d.kind = w.kind; d.has_dc = w.has_dc;
+            d.dc = {w.dc.value, w.dc.col, 0};
+            d.npts = (int)w.t.size();
+            if (!w.t.empty()) {
+                double* dt_; Pref* dy_;
+                TRY(p->upload(&dt_, w.t));
+                std::vector<Pref> ys(w.y.size());
+                for (size_t k = 0; k < ys.size(); k++) ys[k] = {w.y[k].value, w.y[k].col, 0};
+                TRY(p->upload(&dy_, ys));
+                d.t = dt_; d.y = dy_;
+            }
+            for (int k = 0; k < 7; k++) d.v[k] = {w.v[k].value, w.v[k].col, 0};
+            wd[i] = d;
+        }
+        WaveDev* dw;
+        TRY(p->upload(&dw, wd));
+        a.waves = dw;
+    }
+    // linear stamp values
+    TRY(p->upload(&p->d_lin_contrib, c->lin_contrib));
+    {
+        const long long Bl = c->lin_swept ? B : 1;
+        TRY(p->alloc(&p->d_lin_g, (size_t)std::max(1, c->nlin) * Bl));
+        TRY(p->alloc(&p->d_lin_c, (size_t)std::max(1, c->nlin) * Bl));
+        a.lin_g = p->d_lin_g; a.lin_c = p->d_lin_c;
+        a.lin_inst_stride = c->lin_swept ? 1 : 0;
+        a.lin_ent_stride = Bl;
+    }
+    // state
+    TRY(p->alloc(&p->d_params, (size_t)std::max(1, c->P) * B));
+    a.params = p->d_params;
+    double** vecs[] = {&a.X, &a.XN, &a.X1, &a.X2, &a.XP, &a.QN, &a.Q1, &a.QD, &a.BETA};
+    for (double** v : vecs) TRY(p->alloc(v, (size_t)N * B));
+    TRY(p->alloc(&a.alpha, (size_t)B));
+    TRY(p->alloc(&a.dst, (size_t)DS_COUNT * B));
+    TRY(p->alloc(&a.ist, (size_t)IS_COUNT * B));
+    TRY(p->alloc(&a.active, (size_t)B));
+    TRY(p->alloc(&p->d_cache, (size_t)std::max<long long>(1, c->total_cache) * B));
+    TRY(p->alloc(&p->d_dev_out, (size_t)std::max<long long>(1, c->total_out) * B));
+    a.dev_out = p->d_dev_out;
+    TRY(p->alloc(&p->d_xout, (size_t)std::max<size_t>(1, c->outputs.size()) * B));
+    TRY(p->alloc(&p->d_done, 1));
+    a.done_count = p->d_done;
+    CUDA_TRY(cudaMallocHost((void**)&p->h_done, sizeof(int)));
+    // per-model tables
+    for (size_t m = 0; m < c->models.size(); m++) {
+        const ModelH& M = c->models[m];
+        std::vector<int> term, pcol;
+        std::vector<double> pval;
+        std::vector<uint8_t> giv;
+        for (int gi : c->model_insts[m]) {
+            const VaInstH& v = c->insts[gi];
+            term.insert(term.end(), v.term.begin(), v.term.end());
+            for (int k = 0; k < M.nparam; k++) {
+                pval.push_back(v.par[k].value);
+                pcol.push_back(v.given[k] ? v.par[k].col : -1);
+                giv.push_back(v.given[k]);
+            }
+        }
+        int* dt_; int* dc_; double* dv_; uint8_t* dg_;
+        TRY(p->upload(&dt_, term)); TRY(p->upload(&dc_, pcol)); TRY(p->upload(&dv_, pval)); TRY(p->upload(&dg_, giv));
+        p->d_term.push_back(dt_); p->d_par_col.push_back(dc_); p->d_par_val.push_back(dv_); p->d_given.push_back(dg_);
+    }
+    // launch geometry of k_newton: G lanes per point, as many points per CTA as shared memory allows
+    p->G = pick_group(c);
+    int per = S.nnz_lu + 3 * N + a.nwaves;
+    {
+        const int want = p->G / 2;  // stagger groups of one warp across shared-memory banks
+        while (p->G < 32 && (per % 16) != want) per++;
+    }
+    a.sm_stride = per;
+    const size_t per_bytes = (size_t)per * sizeof(double);
+    int max_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
+    if (per_bytes > (size_t)max_smem)
+        return fail(CB_ERR_INVALID, "circuit too large for the shared-memory LU (nnz(L+U) = " + std::to_string(S.nnz_lu) + ")");
+    int gpc = (int)std::min<size_t>(256 / p->G, (size_t)max_smem / per_bytes);
+    // keep at least 2 CTAs per SM resident when the circuit is small
+    while (gpc > 4 && (size_t)gpc * per_bytes > (size_t)max_smem / 2) gpc--;
+    const int warp_groups = 32 / p->G;
+    if (gpc >= warp_groups) gpc -= gpc % warp_groups;
+    p->gpc = std::max(1, gpc);
+    p->smem_bytes = (size_t)p->gpc * per_bytes;
+#define SET_SMEM(GG)                                                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(k_newton<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes))
+    if (p->G == 4) SET_SMEM(4); else if (p->G == 8) SET_SMEM(8); else if (p->G == 16) SET_SMEM(16); else SET_SMEM(32);
+#undef SET_SMEM
+#undef TRY
+    *out = p.release();
+    return CB_OK;
+}
+
+extern "C" int cb_plan_set_params(cb_plan* p, const double* params) {
+    if (!p) return fail(CB_ERR_INVALID, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (p->c->P > 0) {
+        if (!params) return fail(CB_ERR_INVALID, "params is null but the circuit has swept parameters");
+        CUDA_TRY(cudaMemcpyAsync(p->d_params, params, (size_t)p->c->P * p->B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    p->params_set = true;
+    p->setup_valid = false;
+    return CB_OK;
+}
+
+extern "C" int cb_plan_set_x0(cb_plan* p, const double* x0, int per_point) {
+    if (!p) return fail(CB_ERR_INVALID, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!x0) { p->have_x0 = false; return CB_OK; }
+    const size_t n = (size_t)p->c->N * (per_point ? (size_t)p->B : 1);
+    if (!p->d_x0) {
+        int rc = p->alloc(&p->d_x0, (size_t)p->c->N * p->B);
+        if (rc != CB_OK) return rc;
+    }
+    CUDA_TRY(cudaMemcpy(p->d_x0, x0, n * sizeof(double), cudaMemcpyHostToDevice));
+    p->x0_stride = per_point ? p->B : 0;
+    p->have_x0 = true;
+    return CB_OK;
+}
+
+extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
+    if (!p || !d_params) return fail(CB_ERR_INVALID, "null argument");
+    *d_params = p->d_params;
+    p->params_set = true;   // caller writes the device buffer directly
+    p->setup_valid = false;
+    return CB_OK;
+}
+
+static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args) {
+    // layout must match struct VaArgs in va_prelude.h
+    struct VaArgsH {
+        long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out;
+        const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
+        double temp_val; double gmin_val; int temp_col; int gmin_col;
+    };
+    VaArgsH* a = (VaArgsH*)out_args;
+    const cb_circuit* c = p->c;
+    a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha; a->active = p->na.active;
+    a->cache = p->d_cache + (size_t)c->cache_off[m] * p->B;
+    a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
+    a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
+    a->given = p->d_given[m];
+    a->temp_val = opt->temp.value; a->gmin_val = opt->gmin.value;
+    a->temp_col = opt->temp.col; a->gmin_col = opt->gmin.col;
+}
+
+static int run_setup(cb_plan* p, const cb_options* opt) {
+    const cb_circuit* c = p->c;
+    if (p->setup_valid && std::memcmp(&p->last_temp, &opt->temp, sizeof(cb_pref)) == 0 &&
+        std::memcmp(&p->last_gmin, &opt->gmin, sizeof(cb_pref)) == 0)
+        return CB_OK;
+    const long long B = p->B;
+    // linear stamp values
+    {
+        const long long Bl = c->lin_swept ? B : 1;
+        const int threads = 128;
+        k_lin_setup<<<(unsigned)((Bl + threads - 1) / threads), threads, 0, p->stream>>>(
+            Bl, B, c->nlin, (int)c->lin_contrib.size(), p->d_lin_contrib, p->d_params, p->d_lin_g, p->d_lin_c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (size_t m = 0; m < c->models.size(); m++) {
+        if (c->model_insts[m].empty()) continue;
+        char args[256];
+        fill_va_args(p, m, opt, args);
+        void* kargs[] = {args};
+        dim3 grid((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());
+        CUDA_TRY(cudaLaunchKernel((const void*)p->k_setup[m], grid, dim3(128), kargs, 0, p->stream));
+    }
+    p->setup_valid = true;
+    p->last_temp = opt->temp; p->last_gmin = opt->gmin;
+    return CB_OK;
+}
+
+static void collect_breakpoints(const cb_circuit* c, double t0, double t1, std::vector<double>& out) {
+    std::vector<double> bp;
+    for (const WaveH& w : c->waves) {
+        if (w.kind == CB_W_PWL) for (double t : w.t) bp.push_back(t);
+        else if (w.kind == CB_W_PULSE) {
+            const double td = w.v[2].value, tr = w.v[3].value, tf = w.v[4].value, pw = w.v[5].value, per = w.v[6].value;
+            const double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
+            for (int k = 0; k < 4; k++) {
+                if (!std::isfinite(ts[k])) continue;
+                if (std::isinf(per)) bp.push_back(ts[k]);
+                else for (double base = 0.0; base + ts[k] <= t1; base += per) bp.push_back(base + ts[k]);
+            }
+        } else if (w.kind == CB_W_SIN) bp.push_back(w.v[3].value);
+    }
+    bp.push_back(t1);
+    std::sort(bp.begin(), bp.end());
+    out.clear();
+    const double tiny = 1e-12 * std::max(std::fabs(t1), std::fabs(t1 - t0));
+    for (double b : bp) {
+        if (b <= t0 + tiny || b > t1 + tiny) continue;
+        if (!out.empty() && b - out.back() <= tiny) continue;
+        out.push_back(b);
+    }
+}
+
+static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, double t1, const double* saveat,
+                 int64_t nsave, cb_stats* stats) {
+    cb_circuit* c = p->c;
+    if (!p->params_set && c->P > 0) return fail(CB_ERR_STATE, "cb_plan_set_params was not called");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const long long B = p->B;
+    NArgs& a = p->na;
+    for (int k = 0; k < 2; k++) {
+        const cb_pref& pr = k == 0 ? opt->temp : opt->gmin;
+        if (pr.col >= c->P) return fail(CB_ERR_INVALID, "temp/gmin column out of range");
+    }
+    Opts& o = a.o;
+    o.reltol = opt->reltol; o.vabstol = opt->vabstol; o.iabstol = opt->iabstol;
+    o.nr_reltol = opt->nr_reltol; o.nr_vabstol = opt->nr_vabstol; o.nr_iabstol = opt->nr_iabstol;
+    o.dc_abstol = opt->dc_abstol; o.dv_max = opt->dv_max;
+    o.dt = opt->dt; o.dt_min = opt->dt_min; o.t0 = t0; o.t1 = t1;
+    o.span = t1 - t0;
+    o.teps = 1e-12 * std::max(std::fabs(t1), o.span);
+    o.dt_max = opt->dt_max > 0 ? opt->dt_max : o.span / 50.0;
+    o.max_newton_dc = opt->max_newton_dc; o.max_newton_tran = opt->max_newton_tran;
+    o.method = opt->method; o.fixed_step = opt->fixed_step; o.gmin_steps = opt->gmin_steps;
+    o.skip_dc = opt->skip_dc; o.dc_only = dc_only ? 1 : 0;
+    o.nsave = dc_only ? 0 : nsave;
+    o.nfixed = 0;
+    if (!dc_only) {
+        if (!(t1 > t0)) return fail(CB_ERR_INVALID, "tran needs t1 > t0");
+        if (opt->fixed_step) {
+            if (!(opt->dt > 0)) return fail(CB_ERR_INVALID, "fixed-step mode needs dt > 0");
+            o.nfixed = (long long)std::llround(o.span / opt->dt);
+        }
+        // outputs, saveat, breakpoints
+        const size_t ycount = (size_t)a.O * (size_t)nsave * (size_t)B;
+        if (ycount > p->y_capacity) {
+            if (p->d_y) cudaFree(p->d_y);
+            p->d_y = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&p->d_y, std::max<size_t>(1, ycount) * sizeof(double)));
+            p->y_capacity = ycount;
+        }
+        if ((size_t)nsave > p->saveat_capacity) {
+            if (p->d_saveat) cudaFree(p->d_saveat);
+            CUDA_TRY(cudaMalloc((void**)&p->d_saveat, std::max<size_t>(1, nsave) * sizeof(double)));
+            p->saveat_capacity = nsave;
+        }
+        if (nsave > 0)
+            CUDA_TRY(cudaMemcpyAsync(p->d_saveat, saveat, nsave * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        std::vector<double> bp;
+        collect_breakpoints(c, t0, t1, bp);
+        if (bp.size() > p->bp_capacity) {
+            if (p->d_bp) cudaFree(p->d_bp);
+            CUDA_TRY(cudaMalloc((void**)&p->d_bp, std::max<size_t>(1, bp.size()) * sizeof(double)));
+            p->bp_capacity = bp.size();
+        }
+        if (!bp.empty())
+            CUDA_TRY(cudaMemcpy(p->d_bp, bp.data(), bp.size() * sizeof(double), cudaMemcpyHostToDevice));
+        a.bp = p->d_bp; a.nbp = (int)bp.size();
+        a.saveat = p->d_saveat;
+        a.y_out = p->d_y;
+    } else {
+        a.y_out = p->d_xout;
+        a.bp = nullptr; a.nbp = 0; a.saveat = nullptr;
+    }
+    CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
+    int rc = run_setup(p, opt);
+    if (rc != CB_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(p->d_done, 0, sizeof(int), p->stream));
+    k_init_state<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.N, a.ist, a.dst, a.alpha, a.active, a.X, a.XN, a.BETA,
+                                                                          p->have_x0 ? p->d_x0 : nullptr, p->x0_stride, o);
+    CUDA_TRY(cudaGetLastError());
+
+    const unsigned ngrid = (unsigned)((B + p->gpc - 1) / p->gpc);
+    const unsigned nthreads = (unsigned)(p->gpc * p->G);
+    const int poll = std::getenv("CB_POLL") ? std::max(1, std::atoi(std::getenv("CB_POLL"))) : 16;
+    const bool timing = std::getenv("CB_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    double t_eval = 0, t_newton = 0;
+    int64_t rounds = 0, launches = 0;
+    const int64_t max_rounds = std::getenv("CB_MAX_ROUNDS") ? std::atoll(std::getenv("CB_MAX_ROUNDS")) : (int64_t)1 << 40;
+    char vargs[8][256];
+    if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
+    for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs[m]);
+    bool done = false;
+    while (!done && rounds < max_rounds) {
+        for (int r = 0; r < poll; r++) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+            if (timing) {
+                cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+                cudaEventRecord(e0, p->stream);
+            }
+            for (size_t m = 0; m < c->models.size(); m++) {
+                if (c->model_insts[m].empty()) continue;
+                void* kargs[] = {vargs[m]};
+                dim3 grid((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());
+                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(128), kargs, 0, p->stream));
+                launches++;
+            }
+            if (timing) cudaEventRecord(e1, p->stream);
+            switch (p->G) {
+                case 4: k_newton<4><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                case 8: k_newton<8><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                case 16: k_newton<16><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                default: k_newton<32><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+            }
+            launches++;
+            if (timing) { cudaEventRecord(e2, p->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
+            rounds++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(p->h_done, p->d_done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        done = *p->h_done >= B;
+        if (timing) {
+            for (size_t k = 0; k + 2 < evs.size(); k += 3) {
+                float ms1 = 0, ms2 = 0;
+                cudaEventElapsedTime(&ms1, evs[k], evs[k + 1]);
+                cudaEventElapsedTime(&ms2, evs[k + 1], evs[k + 2]);
+                t_eval += ms1 * 1e-3; t_newton += ms2 * 1e-3;
+                cudaEventDestroy(evs[k]); cudaEventDestroy(evs[k + 1]); cudaEventDestroy(evs[k + 2]);
+            }
+            evs.clear();
+        }
+    }
+    CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    if (!done) return fail(CB_ERR_STATE, "round limit reached before all points finished");
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p->ev0, p->ev1);
+        stats->solve_seconds = ms * 1e-3;
+        stats->rounds = rounds; stats->kernel_launches = launches + 2 + (int64_t)c->models.size();
+        stats->eval_seconds = t_eval; stats->newton_seconds = t_newton;
+        std::vector<int> cnt((size_t)3 * B);
+        CUDA_TRY(cudaMemcpy(cnt.data(), a.ist + (size_t)IS_NNEWTON * B, (size_t)3 * B * sizeof(int), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < B; i++) {
+            stats->newton_iters += cnt[i];
+            stats->steps_accepted += cnt[(size_t)B + i];
+            stats->steps_rejected += cnt[(size_t)2 * B + i];
+        }
+        stats->lu_factors = stats->newton_iters;
+    }
+    return CB_OK;
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int cb_dc_device(cb_plan* p, const cb_options* opt, double** d_x_out, int32_t** d_status, cb_stats* stats) {
+    if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    int rc = solve(p, opt, true, 0.0, 1.0, nullptr, 0, stats);
+    if (rc != CB_OK) return rc;
+    if (d_x_out) *d_x_out = p->d_xout;
+    if (d_status) *d_status = p->na.ist + (size_t)IS_STATUS * p->B;
+    return CB_OK;
+}
+
+extern "C" int cb_dc(cb_plan* p, const cb_options* opt, double* x_out, double* x_full, int32_t* status, cb_stats* stats) {
+    if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    int rc = solve(p, opt, true, 0.0, 1.0, nullptr, 0, stats);
+    if (rc != CB_OK) return rc;
+    const double t = now_s();
+    const long long B = p->B;
+    if (x_out && p->na.O > 0) CUDA_TRY(cudaMemcpy(x_out, p->d_xout, (size_t)p->na.O * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (x_full) CUDA_TRY(cudaMemcpy(x_full, p->na.X, (size_t)p->na.N * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) CUDA_TRY(cudaMemcpy(status, p->na.ist + (size_t)IS_STATUS * B, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (stats) stats->d2h_seconds = now_s() - t;
+    return CB_OK;
+}
+
+extern "C" int cb_tran_device(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save,
+                              const cb_options* opt, double** d_y_out, int32_t** d_status, cb_stats* stats) {
+    if (!p || !opt || (n_save > 0 && !saveat)) return fail(CB_ERR_INVALID, "null argument");
+    for (int64_t k = 1; k < n_save; k++)
+        if (!(saveat[k] >= saveat[k - 1])) return fail(CB_ERR_INVALID, "saveat must be ascending");
+    int rc = solve(p, opt, false, t0, t1, saveat, n_save, stats);
+    if (rc != CB_OK) return rc;
+    if (d_y_out) *d_y_out = p->d_y;
+    if (d_status) *d_status = p->na.ist + (size_t)IS_STATUS * p->B;
+    return CB_OK;
+}
+
+extern "C" int cb_tran(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save, const cb_options* opt,
+                       double* y_out, int32_t* status, cb_stats* stats) {
+    int rc = cb_tran_device(p, t0, t1, saveat, n_save, opt, nullptr, nullptr, stats);
+    if (rc != CB_OK) return rc;
+    const double t = now_s();
+    const long long B = p->B;
+    if (y_out && n_save > 0 && p->na.O > 0)
+        CUDA_TRY(cudaMemcpy(y_out, p->d_y, (size_t)p->na.O * n_save * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) CUDA_TRY(cudaMemcpy(status, p->na.ist + (size_t)IS_STATUS * B, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (stats) stats->d2h_seconds = now_s() - t;
+    return CB_OK;
+}
+
+extern "C" void cb_plan_destroy(cb_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (void* q : p->allocs) cudaFree(q);
+    if (p->d_y) cudaFree(p->d_y);
+    if (p->d_saveat) cudaFree(p->d_saveat);
+    if (p->d_bp) cudaFree(p->d_bp);
+    if (p->h_done) cudaFreeHost(p->h_done);
+    if (p->lib) cudaLibraryUnload(p->lib);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" void cb_circuit_destroy(cb_circuit* c) { delete c; }

@@ -1,0 +1,544 @@
+// kernels.cuh -- hand-written sm_100a kernels of the batched Newton / transient engine.
+//
+// k_newton<G>: one group of G lanes per sweep point, several points per CTA.  Per round and
+// point it (1) gathers the Jacobian J = G + alpha*C and the residual from the batch-
+// interleaved device outputs into shared memory, (2) refactors J with the shared static-
+// pivot sparse LU schedule and solves, (3) applies the damped Newton update with
+// warp-shuffle norms, and (4) advances that point's own DC / transient state machine
+// (LTE step control, breakpoints, output sampling).  All points execute the same schedule,
+// so there is no divergence in the numeric phases; the per-point control code is scalar and
+// replicated across the group's lanes.  There is no host round trip per step.
+//
+// Layout: every per-point array is [k][B] (batch-interleaved, B fastest): a warp that holds
+// 32/G points touches one 32-byte sector per k when G = 8.
+//
+// The step-control algorithm is the engine's own (the reference delegates it to Sundials
+// IDA / OrdinaryDiffEq); the CPU oracle restates the same algorithm for
+// parity checks.
+#pragma once
+#include <cstdint>
+
+namespace cbk {
+
+enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3 };
+// integer per-point state rows
+enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HITBP, IS_METHOD, IS_NP,
+       IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_COUNT };
+// double per-point state rows
+enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_COUNT };
+
+struct Pref { double value; int col; int pad; };
+
+struct WaveDev {
+    int kind, has_dc;
+    Pref dc;
+    int npts, pad;
+    const double* t;
+    const Pref* y;
+    Pref v[7];
+};
+
+struct Opts {
+    double reltol, vabstol, iabstol, nr_reltol, nr_vabstol, nr_iabstol, dc_abstol, dv_max;
+    double dt, dt_min, dt_max, t0, t1, teps, span;
+    int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only;
+    long long nfixed, nsave;
+};
+
+struct NArgs {
+    long long B;
+    int N, NV, nnz_lu, O, nwaves, nbp, sm_stride, pad0;
+    // symbolic schedule
+    const int *diag_pos, *l_ptr, *l_pos, *l_row, *u_ptr, *u_pos, *pair_ptr, *pair_dst;
+    const int *uc_ptr, *uc_pos, *uc_row, *row_to_step, *col_to_step;
+    // assembly of J (per LU entry) and of the residual (per original row)
+    const int *a_ptr, *a_src, *a_lin;
+    const double* a_mult;
+    const unsigned char* a_diag;
+    const int *ri_ptr, *ri_src, *rq_ptr, *rq_src, *rl_ptr, *rl_col, *rl_lin, *rs_ptr, *rs_wave;
+    const double *ri_mult, *rq_mult, *rs_coef;
+    const double *lin_g, *lin_c;
+    long long lin_inst_stride;  // 0 when no linear device value is swept
+    long long lin_ent_stride;   // B or 1
+    const WaveDev* waves;
+    const double* bp;
+    const unsigned char* lte_mask;
+    const int* outputs;
+    const double* saveat;
+    const double* params;
+    // per-point state, all [k][B]
+    double *X, *XN, *X1, *X2, *XP, *QN, *Q1, *QD, *BETA, *alpha, *dst;
+    int *ist, *active;
+    const double* dev_out;
+    double* y_out;  // tran: [O][S][B]; dc: [O][B]
+    int* done_count;
+    Opts o;
+};
+
+__device__ __forceinline__ double pv(const Pref& p, const double* params, long long B, long long inst) {
+    return p.col < 0 ? p.value : params[(size_t)p.col * B + inst];
+}
+
+// reference src/spectre_env.jl:15-21 and 43-69, 1-based index i as there
+__device__ inline double pwl_eval(const double* ts, const Pref* ys, int n, double t, const double* params,
+                                  long long B, long long inst) {
+    int lo = 0, hi = n;  // first index with ts[idx] >= t
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ts[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    int i = lo + 1;
+    if (i <= n && ts[i - 1] == t) i += 1;
+    if (i <= 1) return pv(ys[0], params, B, inst);
+    if (i > n) return pv(ys[n - 1], params, B, inst);
+    const double y0 = pv(ys[i - 2], params, B, inst), y1 = pv(ys[i - 1], params, B, inst);
+    if (y0 == y1) return y1;
+    if (ts[i - 1] == ts[i - 2]) return 0.5 * (y0 + y1);
+    const double slope = (y1 - y0) / (ts[i - 1] - ts[i - 2]);
+    return y0 + (t - ts[i - 2]) * slope;
+}
+
+__device__ inline double pwl4(const double* ts, const double* ys, double t) {
+    int i = 1;
+    while (i <= 4 && ts[i - 1] < t) i++;
+    if (i <= 4 && ts[i - 1] == t) i += 1;
+    if (i <= 1) return ys[0];
+    if (i > 4) return ys[3];
+    if (ys[i - 2] == ys[i - 1]) return ys[i - 1];
+    if (ts[i - 1] == ts[i - 2]) return 0.5 * (ys[i - 2] + ys[i - 1]);
+    const double slope = (ys[i - 1] - ys[i - 2]) / (ts[i - 1] - ts[i - 2]);
+    return ys[i - 2] + (t - ts[i - 2]) * slope;
+}
+
+__device__ inline double wave_tran(const WaveDev& w, double t, const double* params, long long B, long long inst) {
+    switch (w.kind) {
+        case 0: return pv(w.dc, params, B, inst);
+        case 1: return pwl_eval(w.t, w.y, w.npts, t, params, B, inst);
+        case 2: {  // src/spectre_env.jl:153-166
+            const double v1 = pv(w.v[0], params, B, inst), v2 = pv(w.v[1], params, B, inst);
+            const double td = w.v[2].value, tr = w.v[3].value, tf = w.v[4].value, pw = w.v[5].value,
+                         per = w.v[6].value;
+            const double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
+            const double ys[4] = {v1, v2, v2, v1};
+            const double tt = isinf(per) ? t : fmod(t, per);
+            return pwl4(ts, ys, tt);
+        }
+        case 3: {  // src/spectre_env.jl:169-176
+            const double vo = pv(w.v[0], params, B, inst), va = pv(w.v[1], params, B, inst),
+                         freq = pv(w.v[2], params, B, inst), td = pv(w.v[3], params, B, inst),
+                         theta = pv(w.v[4], params, B, inst), phase = pv(w.v[5], params, B, inst),
+                         ncyc = pv(w.v[6], params, B, inst);
+            const double d2r = 3.14159265358979323846 / 180.0;
+            if (td < t && t < ncyc / freq)
+                return vo + va * exp(-(t - td) * theta) * sin((360.0 * freq * (t - td) + phase) * d2r);
+            return vo + va * sin(phase * d2r);
+        }
+    }
+    return 0.0;
+}
+
+__device__ inline double wave_value(const WaveDev& w, double t, bool dcop, const double* params, long long B,
+                                    long long inst) {
+    if (dcop) return w.has_dc ? pv(w.dc, params, B, inst) : wave_tran(w, 0.0, params, B, inst);
+    return wave_tran(w, t, params, B, inst);
+}
+
+template <int G>
+__device__ __forceinline__ double gmax(double v, unsigned mask) {
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, s, G));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int gand(int v, unsigned mask) {
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) v &= __shfl_xor_sync(mask, v, s, G);
+    return v;
+}
+
+// value of the accepted interpolation polynomial at tt for unknown i (mirrors oracle predict())
+__device__ __forceinline__ double poly_at(int nh, double tt, double tn, double xn, double h1, double x1, double h2,
+                                          double x2) {
+    if (nh <= 0) return xn;
+    const double a = tt - tn;
+    if (nh == 1) return xn + a * (xn - x1) / h1;
+    const double d1 = (xn - x1) / h1, d2 = (x1 - x2) / h2, dd = (d1 - d2) / (h1 + h2);
+    return xn + a * d1 + a * (a + h1) * dd;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_newton(const NArgs a) {
+    extern __shared__ double smem[];
+    const int gpc = blockDim.x / G;
+    const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+    const long long B = a.B;
+    const long long inst = (long long)blockIdx.x * gpc + grp;
+    if (inst >= B) return;
+    int phase = a.ist[(size_t)IS_PHASE * B + inst];
+    if (phase == PH_DONE) return;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+    const int N = a.N, NV = a.NV;
+    const Opts& o = a.o;
+    double* A = smem + (size_t)grp * a.sm_stride;
+    double* rhs = A + a.nnz_lu;
+    double* xs = rhs + N;
+    double* qk = xs + N;
+    double* wv = qk + N;
+
+#define IST(k) a.ist[(size_t)(k) * B + inst]
+#define DST(k) a.dst[(size_t)(k) * B + inst]
+#define AT(arr, i) arr[(size_t)(i) * B + inst]
+    int it = IST(IS_IT), stage = IST(IS_STAGE), nh = IST(IS_NH), bpi = IST(IS_BPI), kstep = IST(IS_KSTEP);
+    int status = IST(IS_STATUS), hit_bp = IST(IS_HITBP), method = IST(IS_METHOD), np = IST(IS_NP);
+    int sidx = IST(IS_SIDX), nnewton = IST(IS_NNEWTON), nacc = IST(IS_NACC), nrej = IST(IS_NREJ);
+    int retry = IST(IS_RETRY);
+    double t = DST(DS_T), tnew = DST(DS_TNEW), h = DST(DS_H), h1 = DST(DS_H1), h2 = DST(DS_H2);
+    double hprop = DST(DS_HPROP), gshunt = DST(DS_GSHUNT);
+    double alpha = a.alpha[inst];
+
+    // ---- 1. current iterate and source values -------------------------------------------
+    for (int i = lane; i < N; i += G) xs[i] = AT(a.X, i);
+    {
+        const bool dcop = phase != PH_TRAN;
+        for (int w = lane; w < a.nwaves; w += G) wv[w] = wave_value(a.waves[w], tnew, dcop, a.params, B, inst);
+    }
+    __syncwarp(gmask);
+
+    // ---- 2. assemble J (LU storage, fill = 0) and residual ---------------------------------
+    for (int e = lane; e < a.nnz_lu; e += G) {
+        double v = 0.0;
+        const int lin = a.a_lin[e];
+        if (lin >= 0) {
+            const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            v = a.lin_g[li] + alpha * a.lin_c[li];
+        }
+        if (a.a_diag[e]) v += gshunt;
+        for (int s = a.a_ptr[e]; s < a.a_ptr[e + 1]; s++) v += a.a_mult[s] * a.dev_out[(size_t)a.a_src[s] * B + inst];
+        A[e] = v;
+    }
+    double rmax = 0.0;
+    for (int i = lane; i < N; i += G) {
+        double f = 0.0, q = 0.0;
+        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
+            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            const double xc = xs[a.rl_col[p]];
+            f += a.lin_g[li] * xc;
+            q += a.lin_c[li] * xc;
+        }
+        for (int p = a.ri_ptr[i]; p < a.ri_ptr[i + 1]; p++) f += a.ri_mult[p] * a.dev_out[(size_t)a.ri_src[p] * B + inst];
+        for (int p = a.rq_ptr[i]; p < a.rq_ptr[i + 1]; p++) q += a.rq_mult[p] * a.dev_out[(size_t)a.rq_src[p] * B + inst];
+        for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * wv[a.rs_wave[p]];
+        if (i < NV) f += gshunt * xs[i];
+        const double r = f + alpha * q + AT(a.BETA, i);
+        qk[i] = q;
+        rhs[a.row_to_step[i]] = -r;
+        rmax = fmax(rmax, fabs(r));
+    }
+    rmax = gmax<G>(rmax, gmask);
+    __syncwarp(gmask);
+
+    bool finish = false;      // emit remaining outputs and retire the point
+    bool begin = false;       // set up the next transient step attempt
+    bool newton_ok = false, newton_fail = false;
+
+    if (phase == PH_TRAN_INIT) {
+        // charges at the operating point; qdot(t0) = 0
+        for (int i = lane; i < N; i += G) { AT(a.QN, i) = qk[i]; AT(a.QD, i) = 0.0; }
+        while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
+            for (int k = lane; k < a.O; k += G) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = AT(a.XN, a.outputs[k]);
+            sidx++;
+        }
+        if (status != 0) finish = true;
+        else { begin = true; phase = PH_TRAN; }
+    } else {
+        // ---- 3. static-pivot sparse LU (right-looking) fused with the forward substitution ----
+        bool singular = false;
+        for (int k = 0; k < N; k++) {
+            const double d = A[a.diag_pos[k]];
+            if (!(fabs(d) > 0.0) || !isfinite(d)) singular = true;
+            const double inv = 1.0 / d;
+            const int lp = a.l_ptr[k], nL = a.l_ptr[k + 1] - lp;
+            const int up = a.u_ptr[k], nU = a.u_ptr[k + 1] - up;
+            const int pp = a.pair_ptr[k];
+            const double bk = rhs[k];
+            for (int li = lane; li < nL; li += G) {
+                const int lpos = a.l_pos[lp + li];
+                const double l = A[lpos] * inv;
+                A[lpos] = l;
+                const int* dst = a.pair_dst + pp + li * nU;
+                for (int uj = 0; uj < nU; uj++) A[dst[uj]] -= l * A[a.u_pos[up + uj]];
+                rhs[a.l_row[lp + li]] -= l * bk;
+            }
+            __syncwarp(gmask);
+        }
+        // ---- backward substitution, column oriented ----
+        for (int k = N - 1; k >= 0; k--) {
+            const double xk = rhs[k] / A[a.diag_pos[k]];
+            __syncwarp(gmask);
+            if (lane == 0) rhs[k] = xk;
+            const int cp = a.uc_ptr[k], nC = a.uc_ptr[k + 1] - cp;
+            for (int p = lane; p < nC; p += G) rhs[a.uc_row[cp + p]] -= A[a.uc_pos[cp + p]] * xk;
+            __syncwarp(gmask);
+        }
+        nnewton++;
+        // ---- 4. damped update and convergence norms ----
+        double dvmax = 0.0;
+        int finite = 1;
+        for (int i = lane; i < N; i += G) {
+            const double dx = rhs[a.col_to_step[i]];
+            if (!isfinite(dx)) finite = 0;
+            if (i < NV) dvmax = fmax(dvmax, fabs(dx));
+        }
+        dvmax = gmax<G>(dvmax, gmask);
+        finite = gand<G>(finite, gmask);
+        if (singular || !finite) {
+            newton_fail = true;
+            status = 4;
+        } else {
+            const double sc = dvmax > o.dv_max ? o.dv_max / dvmax : 1.0;
+            const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
+            int conv = (sc == 1.0) && (rmax <= restol);
+            for (int i = lane; i < N; i += G) {
+                const double dx = sc * rhs[a.col_to_step[i]];
+                const double xo = xs[i], xn = xo + dx;
+                const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
+                if (fabs(dx) > o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol) conv = 0;
+                AT(a.X, i) = xn;
+            }
+            conv = gand<G>(conv, gmask);
+            it++;
+            if (conv) newton_ok = true;
+            else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
+        }
+
+        // ---- 5. per-point control --------------------------------------------------------
+        if (phase == PH_DC && (newton_ok || newton_fail)) {
+            bool dc_done = false;
+            it = 0;
+            if (stage < 0) {
+                if (newton_ok) { dc_done = true; status = 0; }
+                else {
+                    for (int i = lane; i < N; i += G) { AT(a.X, i) = 0.0; AT(a.XN, i) = 0.0; }
+                    stage = 0; gshunt = 1e-2; status = 0;
+                    if (o.gmin_steps == 0) gshunt = 0.0;
+                }
+            } else if (stage < o.gmin_steps) {
+                if (newton_ok) { for (int i = lane; i < N; i += G) AT(a.XN, i) = AT(a.X, i); }
+                else { for (int i = lane; i < N; i += G) AT(a.X, i) = AT(a.XN, i); }
+                stage++; gshunt *= 0.1; status = 0;
+                if (stage == o.gmin_steps) gshunt = 0.0;
+            } else {
+                dc_done = true;
+                status = newton_ok ? 0 : 2;
+            }
+            if (dc_done) {
+                gshunt = 0.0;
+                if (o.dc_only) {
+                    for (int k = lane; k < a.O; k += G) a.y_out[(size_t)k * B + inst] = AT(a.X, a.outputs[k]);
+                    phase = PH_DONE;
+                    if (lane == 0) atomicAdd(a.done_count, 1);
+                } else {
+                    for (int i = lane; i < N; i += G) AT(a.XN, i) = AT(a.X, i);
+                    phase = PH_TRAN_INIT;
+                }
+            }
+        } else if (phase == PH_TRAN && newton_fail && o.fixed_step && !retry) {
+            // fixed step cannot shrink: retry once from the flat guess x_n
+            for (int i = lane; i < N; i += G) AT(a.X, i) = AT(a.XN, i);
+            retry = 1; it = 0; status = 0;
+        } else if (phase == PH_TRAN && newton_fail) {
+            nrej++;
+            if (o.fixed_step) finish = true;  // status already holds MAXITERS / UNSTABLE
+            else {
+                hprop = h / 8.0;
+                if (hprop < o.dt_min) { status = 3; finish = true; }
+                else { status = 0; begin = true; }
+            }
+        } else if (phase == PH_TRAN && newton_ok) {
+            double fac = 2.0;
+            bool reject = false;
+            if (!o.fixed_step && np >= 1) {
+                double ratio;
+                if (method == 0) ratio = h / (2.0 * h + h1);
+                else {
+                    const double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
+                    const double lc = method == 1 ? h * h * h / 12.0 : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
+                    ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
+                }
+                double err = 0.0;
+                for (int i = lane; i < N; i += G) {
+                    if (!a.lte_mask[i]) continue;
+                    const double xv = AT(a.X, i), xnv = AT(a.XN, i);
+                    const double tol = o.reltol * fmax(fabs(xv), fabs(xnv)) + (i < NV ? o.vabstol : o.iabstol);
+                    err = fmax(err, ratio * fabs(xv - AT(a.XP, i)) / tol);
+                }
+                err = gmax<G>(err, gmask);
+                const int p = (method == 0 || np < 2) ? 1 : 2;
+                fac = err > 0.0 ? 0.9 * pow(err, -1.0 / (p + 1)) : 2.0;
+                fac = fmin(2.0, fmax(0.2, fac));
+                if (err > 1.0) {
+                    reject = true;
+                    nrej++;
+                    hprop = h * fac;
+                    if (hprop < o.dt_min) { status = 3; finish = true; }
+                    else begin = true;
+                }
+            }
+            if (!reject) {
+                nacc++;
+                for (int i = lane; i < N; i += G) {
+                    AT(a.QD, i) = alpha * qk[i] + AT(a.BETA, i);
+                    AT(a.X2, i) = AT(a.X1, i);
+                    AT(a.X1, i) = AT(a.XN, i);
+                    AT(a.XN, i) = AT(a.X, i);
+                    AT(a.Q1, i) = AT(a.QN, i);
+                    AT(a.QN, i) = qk[i];
+                }
+                h2 = h1; h1 = h;
+                nh = nh + 1 < 2 ? nh + 1 : 2;
+                t = tnew;
+                kstep++;
+                while (sidx < o.nsave && a.saveat[sidx] <= t + o.teps) {
+                    const double ts = a.saveat[sidx];
+                    const bool exact = fabs(ts - t) <= o.teps;
+                    const int ni = o.method == 0 ? 1 : (nh < 2 ? nh : 2);
+                    for (int k = lane; k < a.O; k += G) {
+                        const int u = a.outputs[k];
+                        const double xn = AT(a.XN, u);
+                        a.y_out[((size_t)k * o.nsave + sidx) * B + inst] =
+                            exact ? xn : poly_at(ni, ts, t, xn, h1, AT(a.X1, u), h2, AT(a.X2, u));
+                    }
+                    sidx++;
+                }
+                if (!o.fixed_step) {
+                    hprop = h * fac;
+                    if (hit_bp) {
+                        nh = 0;
+                        const double nb = (bpi + 1 < a.nbp) ? a.bp[bpi + 1] - t : o.t1 - t;
+                        hprop = fmin(hprop, 0.1 * fmin(h, nb > 0.0 ? nb : h));
+                        hprop = fmax(hprop, o.span * 1e-9);
+                    }
+                }
+                begin = true;
+            }
+        }
+    }
+
+    // ---- 6. set up the next step attempt (mirrors the top of the oracle's step loop) --------
+    if (begin) {
+        bool more;
+        if (o.fixed_step) {
+            more = kstep < o.nfixed;
+            if (more) { tnew = o.t0 + (double)(kstep + 1) * o.dt; h = tnew - t; hit_bp = 0; }
+        } else {
+            more = t < o.t1 - o.teps;
+            if (more) {
+                while (bpi < a.nbp && a.bp[bpi] <= t + o.teps) bpi++;
+                const double tb = bpi < a.nbp ? a.bp[bpi] : o.t1;
+                h = fmin(hprop, o.dt_max);
+                hit_bp = 0;
+                if (t + h >= tb - 1e-3 * h) { h = tb - t; tnew = tb; hit_bp = 1; }
+                else if (t + 2.0 * h > tb) { h = 0.5 * (tb - t); tnew = t + h; }
+                else tnew = t + h;
+            }
+        }
+        if (!more) finish = true;
+        else {
+            method = nh == 0 ? 0 : o.method;
+            double a1 = 0.0, a2 = 0.0;
+            if (method == 0) { alpha = 1.0 / h; a1 = -alpha; }
+            else if (method == 1) { alpha = 2.0 / h; a1 = -alpha; }
+            else {
+                const double rho = h / h1;
+                alpha = (1.0 + 2.0 * rho) / (h * (1.0 + rho));
+                a1 = -(1.0 + rho) / h;
+                a2 = rho * rho / (h * (1.0 + rho));
+            }
+            np = method == 0 ? (nh < 1 ? nh : 1) : nh;
+            for (int i = lane; i < N; i += G) {
+                const double qn = AT(a.QN, i);
+                double beta = a1 * qn;
+                if (method == 1) beta -= AT(a.QD, i);
+                else if (method == 2) beta += a2 * AT(a.Q1, i);
+                AT(a.BETA, i) = beta;
+                const double xn = AT(a.XN, i), x1 = AT(a.X1, i);
+                const double xp = poly_at(np, tnew, t, xn, h1, x1, h2, AT(a.X2, i));
+                AT(a.XP, i) = xp;
+                // clamped Newton start (see the oracle): at most the linear trend of the last step
+                double lim = np >= 1 ? fabs(xn - x1) * (h / h1) : 0.0;
+                if (i < NV) lim = fmin(lim, o.dv_max);
+                AT(a.X, i) = xn + fmax(-lim, fmin(lim, xp - xn));
+            }
+            it = 0;
+            retry = 0;
+        }
+    }
+    if (finish) {
+        for (; sidx < o.nsave; sidx++)
+            for (int k = lane; k < a.O; k += G)
+                a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = AT(a.XN, a.outputs[k]);
+        phase = PH_DONE;
+        if (lane == 0) atomicAdd(a.done_count, 1);
+    }
+
+    if (lane == 0) {
+        IST(IS_PHASE) = phase; IST(IS_IT) = it; IST(IS_STAGE) = stage; IST(IS_NH) = nh; IST(IS_BPI) = bpi;
+        IST(IS_KSTEP) = kstep; IST(IS_STATUS) = status; IST(IS_HITBP) = hit_bp; IST(IS_METHOD) = method;
+        IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
+        IST(IS_RETRY) = retry;
+        DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
+        DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt;
+        a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
+        a.active[inst] = phase != PH_DONE;
+    }
+#undef IST
+#undef DST
+#undef AT
+}
+
+// ---- small helper kernels ---------------------------------------------------------------------
+__global__ void k_init_state(long long B, int N, int* ist, double* dst, double* alpha, int* active, double* X,
+                             double* XN, double* BETA, const double* x0, long long x0_stride, Opts o) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    for (int k = 0; k < IS_COUNT; k++) ist[(size_t)k * B + inst] = 0;
+    for (int k = 0; k < DS_COUNT; k++) dst[(size_t)k * B + inst] = 0.0;
+    ist[(size_t)IS_PHASE * B + inst] = o.skip_dc && !o.dc_only ? PH_TRAN_INIT : PH_DC;
+    ist[(size_t)IS_STAGE * B + inst] = -1;
+    dst[(size_t)DS_T * B + inst] = o.t0;
+    dst[(size_t)DS_HPROP * B + inst] = o.dt > 0.0 ? o.dt : o.span * 1e-5;
+    alpha[inst] = 0.0;
+    active[inst] = 1;
+    for (int i = 0; i < N; i++) {
+        const double v = x0 ? (x0_stride ? x0[(size_t)i * x0_stride + inst] : x0[i]) : 0.0;
+        X[(size_t)i * B + inst] = v;
+        XN[(size_t)i * B + inst] = v;
+        BETA[(size_t)i * B + inst] = 0.0;
+    }
+}
+
+struct LinContrib { Pref p; double coef; int entry, recip, is_c, pad; };
+
+// per-point values of the linear (R, C, L, E, G, incidence) stamps: lin_g / lin_c [nlin][Bl]
+__global__ void k_lin_setup(long long Bl, long long B, int nlin, int ncontrib, const LinContrib* lc, const double* params,
+                            double* lin_g, double* lin_c) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= Bl) return;
+    for (int e = 0; e < nlin; e++) { lin_g[(size_t)e * Bl + inst] = 0.0; lin_c[(size_t)e * Bl + inst] = 0.0; }
+    for (int c = 0; c < ncontrib; c++) {
+        const LinContrib& k = lc[c];
+        double v = pv(k.p, params, B, inst);
+        if (k.recip) v = 1.0 / v;
+        v *= k.coef;
+        if (k.is_c) lin_c[(size_t)k.entry * Bl + inst] += v;
+        else lin_g[(size_t)k.entry * Bl + inst] += v;
+    }
+}
+
+__global__ void k_gather_rows(long long B, int n, const int* idx, const double* src, double* dst) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    for (int k = 0; k < n; k++) dst[(size_t)k * B + inst] = src[(size_t)idx[k] * B + inst];
+}
+
+}  // namespace cbk

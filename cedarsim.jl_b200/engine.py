@@ -1,0 +1,205 @@
+"""ctypes binding of the C-ABI engine (include/cedarb200.h, csrc/libcedarb200.so).
+
+This is the thin host layer the north star describes: the host flattens the netlist and
+generates CUDA C for the device models; everything numeric happens behind the `cb_*` calls.
+There is no CPU fallback: `load()` raises when the CUDA library has not been built and the
+library itself fails with CB_ERR_NO_DEVICE when no GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import flat as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcedarb200.so")
+CUBIN_CACHE = os.path.join(_HERE, "_gen", "cubin")
+_lib = None
+
+SYMBOLS = [
+    "cb_version", "cb_last_error", "cb_options_default", "cb_circuit_create", "cb_circuit_set_cuda_source",
+    "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_set_params", "cb_dc", "cb_tran",
+    "cb_plan_device_params", "cb_plan_set_x0", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
+]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cedarb200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(-100, f"{LIB_PATH} is missing: build the CUDA engine first "
+                              "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.cb_last_error.restype = C.c_char_p
+        lib.cb_plan_destroy.restype = None
+        lib.cb_circuit_destroy.restype = None
+        lib.cb_options_default.restype = None
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EngineError(rc, load().cb_last_error().decode(errors="replace"))
+
+
+def default_options(**kw) -> F.cb_options:
+    o = F.cb_options()
+    load().cb_options_default(C.byref(o))
+    for k, v in kw.items():
+        if k in ("temp", "gmin"):
+            setattr(o, k, F._pref(v))
+        else:
+            if not hasattr(o, k):
+                raise KeyError(f"unknown option {k!r}")
+            setattr(o, k, v)
+    return o
+
+
+def cuda_source(models: Sequence) -> str:
+    """Concatenate generated model sources with their shape macros (see csrc/va_prelude.h)."""
+    parts = []
+    for cm in models:
+        parts.append(f"#undef NT\n#undef NPARAM\n#undef NCACHE\n#undef NOUT\n"
+                     f"#define NT {len(cm.terminals)}\n#define NPARAM {max(1, len(cm.params))}\n"
+                     f"#define NCACHE {max(1, cm.ncache)}\n#define NOUT {2 * len(cm.terminals) + len(cm.jrow)}\n")
+        parts.append(cm.source)
+    return "\n".join(parts)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Circuit:
+    """A compiled circuit: flat description + generated device code + symbolic LU."""
+
+    def __init__(self, fc: F.FlatCircuit, models: Sequence = (), cache_dir: Optional[str] = CUBIN_CACHE):
+        self.lib = load()
+        self.fc = fc
+        self.packed = fc.pack()
+        self.handle = C.c_void_p()
+        _check(self.lib.cb_circuit_create(self.packed.ref(), C.byref(self.handle)))
+        if fc.va_models:
+            by_name = {cm.name: cm for cm in models}
+            src = cuda_source([by_name[m.name] for m in fc.va_models]).encode()
+            _check(self.lib.cb_circuit_set_cuda_source(self.handle, src, C.c_size_t(len(src))))
+        secs = C.c_double(0.0)
+        if cache_dir:
+            os.makedirs(cache_dir, exist_ok=True)
+        _check(self.lib.cb_circuit_compile(self.handle, cache_dir.encode() if cache_dir else None, C.byref(secs)))
+        self.compile_seconds = secs.value
+
+    def lu_info(self):
+        a, l, f = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(self.lib.cb_circuit_lu_info(self.handle, C.byref(a), C.byref(l), C.byref(f)))
+        return {"nnz_a": a.value, "nnz_lu": l.value, "lu_flops": f.value}
+
+    def plan(self, n_inst: int, device: int = 0) -> "Plan":
+        return Plan(self, n_inst, device)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.cb_circuit_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Plan:
+    def __init__(self, circuit: Circuit, n_inst: int, device: int = 0):
+        self.circuit = circuit
+        self.lib = circuit.lib
+        self.B = int(n_inst)
+        self.device = device
+        self.handle = C.c_void_p()
+        _check(self.lib.cb_plan_create(circuit.handle, C.c_int64(self.B), C.c_int(device), C.byref(self.handle)))
+
+    def set_params(self, params: Optional[np.ndarray]):
+        P = len(self.circuit.fc.param_names)
+        if P == 0:
+            _check(self.lib.cb_plan_set_params(self.handle, None))
+            return
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.shape != (P, self.B):
+            raise ValueError(f"params must have shape ({P}, {self.B}), got {params.shape}")
+        self._params = params
+        _check(self.lib.cb_plan_set_params(self.handle, _dp(params)))
+
+    def set_x0(self, x0: Optional[np.ndarray]):
+        """DC initial guess: None, x0[N] shared by all points, or x0[N, B]."""
+        if x0 is None:
+            _check(self.lib.cb_plan_set_x0(self.handle, None, C.c_int(0)))
+            return
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        N = self.circuit.fc.n_unknowns
+        if x0.shape not in ((N,), (N, self.B)):
+            raise ValueError(f"x0 must have shape ({N},) or ({N}, {self.B})")
+        _check(self.lib.cb_plan_set_x0(self.handle, _dp(x0), C.c_int(1 if x0.ndim == 2 else 0)))
+
+    def dc(self, opts: Optional[F.cb_options] = None, want_full: bool = True):
+        opts = opts or default_options()
+        fc = self.circuit.fc
+        O, N = len(fc.outputs), fc.n_unknowns
+        x_out = np.zeros((O, self.B))
+        x_full = np.zeros((N, self.B)) if want_full else None
+        status = np.zeros(self.B, dtype=np.int32)
+        st = F.cb_stats()
+        _check(self.lib.cb_dc(self.handle, C.byref(opts), _dp(x_out), _dp(x_full) if want_full else None,
+                              status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return x_out, x_full, status, st.as_dict()
+
+    def tran(self, t0: float, t1: float, saveat, opts: Optional[F.cb_options] = None, out: Optional[np.ndarray] = None):
+        opts = opts or default_options()
+        saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+        O, S = len(self.circuit.fc.outputs), len(saveat)
+        y = out if out is not None else np.zeros((O, S, self.B))
+        status = np.zeros(self.B, dtype=np.int32)
+        st = F.cb_stats()
+        _check(self.lib.cb_tran(self.handle, C.c_double(t0), C.c_double(t1), _dp(saveat), C.c_int64(S), C.byref(opts),
+                                _dp(y), status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return y, status, st.as_dict()
+
+    def tran_device(self, t0: float, t1: float, saveat, opts: Optional[F.cb_options] = None):
+        """Results stay in HBM; returns (device pointer of y, device pointer of status, stats)."""
+        opts = opts or default_options()
+        saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+        dy, ds = C.c_void_p(), C.c_void_p()
+        st = F.cb_stats()
+        _check(self.lib.cb_tran_device(self.handle, C.c_double(t0), C.c_double(t1), _dp(saveat), C.c_int64(len(saveat)),
+                                       C.byref(opts), C.byref(dy), C.byref(ds), C.byref(st)))
+        return dy.value, ds.value, st.as_dict()
+
+    def dc_device(self, opts: Optional[F.cb_options] = None):
+        opts = opts or default_options()
+        dx, ds = C.c_void_p(), C.c_void_p()
+        st = F.cb_stats()
+        _check(self.lib.cb_dc_device(self.handle, C.byref(opts), C.byref(dx), C.byref(ds), C.byref(st)))
+        return dx.value, ds.value, st.as_dict()
+
+    def device_params_ptr(self) -> int:
+        dp = C.c_void_p()
+        _check(self.lib.cb_plan_device_params(self.handle, C.byref(dp)))
+        return dp.value
+
+    def close(self):
+        if self.handle:
+            self.lib.cb_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,78 @@
+"""Registry of compiled device models and model cards.
+
+The Verilog-A sources and foundry cards are *inputs* that live outside this repository (the
+reference vendors BSIM-CMG 107 under VerilogAParser.jl/cmc_models/bsimcmg107 and the ASAP7 cards
+under SpectreNetlistParser.jl/test/examples/7nm_TT.scs).  They are compiled where they lie; the
+generated artefacts are cached under `cedarsim.jl_b200/_gen/` (git-ignored, travels to the GPU
+box with the built .so files), so no GPU-side code ever reads /root/reference.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+from typing import Dict, Optional
+
+from .modelcard import ModelCard, load_model_cards
+from .va.compiler import CompiledModel, compile_va_file
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GEN_DIR = os.path.join(_HERE, "_gen")
+REFERENCE_ROOT = os.environ.get("CEDAR_REFERENCE_ROOT", "/root/reference")
+BSIMCMG_VA = os.path.join(REFERENCE_ROOT, "VerilogAParser.jl/cmc_models/bsimcmg107/bsimcmg.va")
+ASAP7_CARDS = os.path.join(REFERENCE_ROOT, "SpectreNetlistParser.jl/test/examples/7nm_TT.scs")
+
+_cache: Dict[str, CompiledModel] = {}
+
+
+def save_model(cm: CompiledModel, path: str):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path + ".tmp", "w") as f:
+        json.dump(dataclasses.asdict(cm), f)
+    os.replace(path + ".tmp", path)
+
+
+def load_model(path: str) -> CompiledModel:
+    with open(path) as f:
+        return CompiledModel(**json.load(f))
+
+
+def compiled_model(name: str, va_path: Optional[str] = None, rebuild: bool = False, **kw) -> CompiledModel:
+    """Compiled model by name, from the _gen cache or by compiling `va_path`."""
+    if name in _cache and not rebuild:
+        return _cache[name]
+    path = os.path.join(GEN_DIR, f"{name}.model.json")
+    if os.path.exists(path) and not rebuild:
+        cm = load_model(path)
+    else:
+        if va_path is None or not os.path.exists(va_path):
+            raise FileNotFoundError(f"no cached model {path} and no Verilog-A source {va_path!r}; run build() where the source exists")
+        cm = compile_va_file(va_path, name=name, **kw)
+        save_model(cm, path)
+    _cache[name] = cm
+    return cm
+
+
+def bsimcmg107(rebuild: bool = False) -> CompiledModel:
+    # __OPINFO__ only computes operating-point report variables; suppressing it does not change
+    # any contribution (bsimcmg_main.va:62).
+    return compiled_model("bsimcmg107", BSIMCMG_VA, rebuild, suppress_defines=["__OPINFO__"])
+
+
+def asap7_cards(rebuild: bool = False) -> Dict[str, ModelCard]:
+    path = os.path.join(GEN_DIR, "asap7_cards.json")
+    if os.path.exists(path) and not rebuild:
+        with open(path) as f:
+            return {k: ModelCard(**v) for k, v in json.load(f).items()}
+    if not os.path.exists(ASAP7_CARDS):
+        raise FileNotFoundError(f"no cached cards {path} and no card file {ASAP7_CARDS}")
+    cards = load_model_cards(ASAP7_CARDS)
+    os.makedirs(GEN_DIR, exist_ok=True)
+    with open(path, "w") as f:
+        json.dump({k: dataclasses.asdict(v) for k, v in cards.items()}, f)
+    return cards
+
+
+def available() -> bool:
+    return (os.path.exists(os.path.join(GEN_DIR, "bsimcmg107.model.json")) or os.path.exists(BSIMCMG_VA)) and \
+           (os.path.exists(os.path.join(GEN_DIR, "asap7_cards.json")) or os.path.exists(ASAP7_CARDS))

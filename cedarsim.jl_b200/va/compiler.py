@@ -781,7 +781,8 @@ class _Compiler:
         dpa = None
         if a.d:
             # d/da a^b = b a^(b-1)  (ForwardDiff's rule; finite at a == 0 for b >= 1)
-            dpa = self.emit_val("r", f"({ac} == 0.0 ? {bc} * pow({ac}, {bc} - 1.0) : {bc} * {p.c} / {ac})", {})
+            # (b == 0 -> 0 avoids 0*inf = NaN at a == 0, e.g. DVTP0*pow(vdsx, DVTP1) with DVTP1 = 0)
+            dpa = self.emit_val("r", f"({bc} == 0.0 ? 0.0 : ({ac} == 0.0 ? {bc} * pow({ac}, {bc} - 1.0) : {bc} * {p.c} / {ac}))", {})
             self.count("div"); self.count("mul")
         dpb = None
         if b.d:

@@ -35,6 +35,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -301,6 +302,7 @@ struct Solver {
     std::vector<double> J, rhs;
     std::vector<uint8_t> lte_mask;
     Counters cnt;
+    bool debug = std::getenv("ORC_DEBUG") != nullptr;
 
     void init(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t b, const cb_options* o) {
         in.fc = fc; in.params = params; in.B = B; in.b = b;
@@ -351,15 +353,24 @@ struct Solver {
                     conv = false;
                 x[i] = xn;
             }
+            if (debug) {
+                int im = 0; double dm = 0;
+                for (int i = 0; i < N; i++) if (std::fabs(sc * rhs[i]) > dm) { dm = std::fabs(sc * rhs[i]); im = i; }
+                std::fprintf(stderr, "  t=%.6e it=%d rmax=%.3e dxmax=%.3e at %d (x=%.6e) sc=%.3g conv=%d\n", t, it, rmax, dm, im, x[im], sc, (int)conv);
+            }
             if (conv) { qk = s.q; return 0; }
         }
         return 1;
     }
 
-    // DC operating point (src/dcop.jl:96-155) with gmin-stepping fallback.
+    // DC operating point (src/dcop.jl:96-155) with gmin-stepping fallback.  x0 (optional) is the
+    // caller's initial guess, the counterpart of remake(prob, u0=...) at src/sweeps.jl:474-477.
+    const double* x0 = nullptr;
+    int64_t x0_stride = 0;
     int dc(std::vector<double>& x) {
         std::vector<double> qk;
         x.assign(N, 0.0);
+        if (x0) for (int i = 0; i < N; i++) x[i] = x0_stride ? x0[(int64_t)i * x0_stride + in.b] : x0[i];
         int rc = newton(x, 0.0, true, 0.0, nullptr, 0.0, opt->max_newton_dc, opt->dc_abstol, qk);
         if (rc == 0) return CB_ST_SUCCESS;
         x.assign(N, 0.0);
@@ -454,8 +465,20 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
         }
         const int np = (method == CB_METHOD_BE) ? std::min(nh, 1) : nh;  // predictor order
         predict(N, np, tnew, t, xn.data(), h1, x1.data(), h2, x2.data(), xp.data());
-        x = xp;
+        // Newton starts from the predictor, but never further from x_n than the linear trend of the
+        // last step (nor than dv_max): a quadratic extrapolation through a switching edge overshoots
+        // the rails and strands Newton.  The LTE estimate below uses the unclamped predictor.
+        for (int i = 0; i < N; i++) {
+            double d = xp[i] - xn[i];
+            double lim = np >= 1 ? std::fabs(xn[i] - x1[i]) * (h / h1) : 0.0;
+            if (i < S.NV) lim = std::min(lim, opt->dv_max);
+            x[i] = xn[i] + std::max(-lim, std::min(lim, d));
+        }
         int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);
+        if (rc != 0 && fixed) {  // fixed step cannot shrink: retry once from the flat guess x_n
+            x = xn;
+            rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);
+        }
         if (rc != 0) {
             S.cnt.rejected++;
             if (fixed) { st = rc == 1 ? CB_ST_MAXITERS : CB_ST_UNSTABLE; break; }
@@ -543,6 +566,11 @@ void orc_options_default(cb_options* o) {
 
 // DC sweep: x_out [O][B], x_full [N][B] (optional), status [B].  Serial over points like
 // the reference's broadcast (src/sweeps.jl:473); nthreads > 1 uses OpenMP for the timing baseline.
+static const double* g_x0 = nullptr;
+static int64_t g_x0_stride = 0;
+// initial guess for the DC Newton: x0[N] shared by all points (stride 0) or x0[N][B] (stride B)
+void orc_set_x0(const double* x0, int64_t stride) { g_x0 = x0; g_x0_stride = stride; }
+
 int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_options* opt,
            double* x_out, double* x_full, int32_t* status, cb_stats* stats, int nthreads) {
     int64_t newton = 0, factors = 0;
@@ -551,6 +579,7 @@ int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_
     for (int64_t b = 0; b < B; b++) {
         Solver S;
         S.init(fc, params, B, b, opt);
+        S.x0 = g_x0; S.x0_stride = g_x0_stride;
         std::vector<double> x;
         status[b] = S.dc(x);
         for (int o = 0; o < fc->n_outputs; o++) x_out[(int64_t)o * B + b] = x[fc->outputs[o]];
@@ -570,6 +599,7 @@ int orc_tran(const cb_flat_circuit* fc, const double* params, int64_t B, double 
     for (int64_t b = 0; b < B; b++) {
         Solver S;
         S.init(fc, params, B, b, opt);
+        S.x0 = g_x0; S.x0_stride = g_x0_stride;
         status[b] = tran_one(S, t0, t1, saveat, nsave, y_out, B, b);
         newton += S.cnt.newton; factors += S.cnt.factors; acc += S.cnt.accepted; rej += S.cnt.rejected;
     }

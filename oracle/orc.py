@@ -51,6 +51,21 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+_x0_keep = None
+
+
+def set_x0(x0=None):
+    """Initial guess of the DC Newton: None, x0[N] (shared) or x0[N, B] (per point)."""
+    global _x0_keep
+    if x0 is None:
+        _x0_keep = None
+        lib().orc_set_x0(None, C.c_int64(0))
+        return
+    _x0_keep = np.ascontiguousarray(x0, dtype=np.float64)
+    stride = 0 if _x0_keep.ndim == 1 else _x0_keep.shape[1]
+    lib().orc_set_x0(_dp(_x0_keep), C.c_int64(stride))
+
+
 def dc(fc, params=None, B=1, opts=None, nthreads=1):
     """fc: FlatCircuit. Returns (x_out [O,B], x_full [N,B], status [B], stats dict)."""
     flat = _flat()
