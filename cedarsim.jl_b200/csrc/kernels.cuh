@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
                 AT(a.X, i) = xn;
             }
             conv = gand<G>(conv, gmask);
+            __syncwarp(gmask);  // X written by its owning lanes is read across lanes below (outputs)
             it++;
             if (conv) newton_ok = true;
             else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
                     AT(a.Q1, i) = AT(a.QN, i);
                     AT(a.QN, i) = qk[i];
                 }
+                __syncwarp(gmask);  // history rows are read across lanes by the output sampling
                 h2 = h1; h1 = h;
                 nh = nh + 1 < 2 ? nh + 1 : 2;
                 t = tnew;

@@ -556,7 +556,7 @@ void orc_options_default(cb_options* o) {
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
-    o->nr_reltol = 1e-6; o->nr_vabstol = 1e-9; o->nr_iabstol = 1e-12;
+    o->nr_reltol = 1e-7; o->nr_vabstol = 1e-10; o->nr_iabstol = 1e-13;
     o->dc_abstol = 1e-10; o->dv_max = 0.5;
     o->max_newton_dc = 200; o->max_newton_tran = 20;
     o->method = CB_METHOD_TRAP; o->fixed_step = 0;

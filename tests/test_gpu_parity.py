@@ -1,0 +1,135 @@
+"""GPU parity tests: CUDA engine (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): DC node voltages within 1e-9 V; transient within 1e-6
+relative / 1e-9 V absolute at shared output times in fixed-step comparison mode.  Adaptive-step
+runs choose their own step sequences from LTE estimates, so they are compared at the LTE tolerance.
+"""
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import circuits, models
+from cedarsim.jl_b200.flat import FlatCircuit, Wave, W_PULSE, W_PWL, W_SIN, params_matrix
+
+from helpers import run_dc_both, run_tran_both, x0_from
+
+pytestmark = pytest.mark.gpu
+
+DC_VTOL = 1e-9
+
+
+def assert_tran_close(yg, yo, rtol=1e-6, atol=1e-9):
+    err = np.abs(yg - yo)
+    tol = rtol * np.abs(yo) + atol
+    assert np.all(err <= tol), f"max err {err.max():.3e}, worst excess {(err - tol).max():.3e}"
+
+
+def test_two_resistor_dc_sweep():
+    # reference test/sweep.jl:326-340: I(V) = -1/(R1+R2) to 1e-7 on a 20x20 ProductSweep
+    fc = circuits.two_resistor()
+    r1, r2 = np.meshgrid(np.arange(100, 2001, 100.0), np.arange(100, 2001, 100.0), indexing="ij")
+    P = params_matrix([r1.ravel(order="F"), r2.ravel(order="F")])
+    (xg, xfg, sg, _), (xo, xfo, so, _) = run_dc_both(fc, [], P)
+    assert sg.max() == 0 and so.max() == 0
+    assert np.abs(xg[0] - (-1.0 / (P[0] + P[1]))).max() < 1e-12
+    assert np.abs(xfg - xfo).max() < DC_VTOL
+
+
+def test_rc_pulse_fixed_step():
+    fc = FlatCircuit()
+    fc.vsource("V", "in", "0", Wave(W_PULSE, v=[0, 1, 1e-8, 1e-9, 1e-9, 2e-6, 4e-6]))
+    fc.resistor("R", "in", "out", fc.param("r"))
+    fc.capacitor("C", "out", "0", 1e-9)
+    fc.set_outputs(["out", "v.i"])
+    P = params_matrix([np.linspace(500.0, 2000.0, 37)])
+    ts = np.linspace(0, 5e-6, 101)
+    for method in (0, 1, 2):
+        (yg, sg, _), (yo, so, _) = run_tran_both(fc, [], P, 0.0, 5e-6, ts, fixed_step=1, dt=1e-8, method=method)
+        assert sg.max() == 0 and so.max() == 0
+        assert_tran_close(yg, yo)
+
+
+def test_rlc_sin_adaptive():
+    fc = FlatCircuit()
+    fc.vsource("V", "in", "0", Wave(W_SIN, v=[0.0, 1.0, 1e6]))
+    fc.resistor("R", "in", "a", 50.0)
+    fc.inductor("L", "a", "out", fc.param("l"))
+    fc.capacitor("C", "out", "0", 1e-9)
+    fc.resistor("RL", "out", "0", 1e3)
+    fc.set_outputs(["out", "l.i"])
+    P = params_matrix([np.linspace(1e-6, 2e-5, 16)])
+    ts = np.linspace(0, 5e-6, 201)
+    (yg, sg, stg), (yo, so, sto) = run_tran_both(fc, [], P, 0.0, 5e-6, ts, reltol=1e-4)
+    assert sg.max() == 0 and so.max() == 0
+    assert np.abs(yg - yo).max() < 5e-3  # both within the LTE tolerance of the same algorithm
+    assert abs(stg["steps_accepted"] - sto["steps_accepted"]) <= 0.05 * sto["steps_accepted"] + 5
+
+
+def test_pwl_current_source_fixed():
+    # shape of reference test/transients.jl:17-63 (PWL current into R, analytic at every time point)
+    fc = FlatCircuit()
+    fc.isource("I", "0", "out", Wave(W_PWL, t=[0, 1e-3, 2e-3, 3e-3], y=[0.0, 1e-3, 1e-3, 0.0]))
+    fc.resistor("R", "out", "0", fc.param("r"))
+    fc.set_outputs(["out"])
+    P = params_matrix([np.array([10.0, 100.0, 1e3, 1e4])])
+    ts = np.linspace(0, 3e-3, 61)
+    (yg, sg, _), (yo, so, _) = run_tran_both(fc, [], P, 0.0, 3e-3, ts, fixed_step=1, dt=5e-5)
+    assert sg.max() == 0
+    exact = np.interp(ts, [0, 1e-3, 2e-3, 3e-3], [0, 1e-3, 1e-3, 0])[None, :] * P[0][:, None]
+    assert np.abs(yg[0].T - exact).max() < 1e-9
+    assert_tran_close(yg, yo)
+
+
+def test_bsimcmg_fet_iv_dc(host_bsimcmg):
+    # BASELINE config 4 at reduced size: ASAP7 nmos_lvt I-V grid
+    fc, ms = circuits.fet_iv(host_bsimcmg)
+    vg, vd = np.meshgrid(np.linspace(0, 0.9, 24), np.linspace(0, 0.9, 24), indexing="ij")
+    P = params_matrix([vg.ravel(order="F"), vd.ravel(order="F")])
+    (xg, xfg, sg, _), (xo, xfo, so, _) = run_dc_both(fc, ms, P)
+    assert sg.max() == 0 and so.max() == 0
+    nv = fc.n_nodes
+    assert np.abs(xfg[:nv] - xfo[:nv]).max() < DC_VTOL
+    assert np.abs(xfg[nv:] - xfo[nv:]).max() < 1e-12 + 1e-9 * np.abs(xfo[nv:]).max()
+
+
+def test_bsimcmg_inverter_tran_fixed(host_bsimcmg):
+    # BASELINE config 2 at reduced size: vdd x nfin x l sweep, fixed-step trapezoidal
+    fc, ms = circuits.inverter(host_bsimcmg, tscale=0.01)
+    vdd, nfin, ln = np.meshgrid(np.linspace(0.56, 0.84, 3), np.linspace(2, 6, 3), np.linspace(21e-9, 40e-9, 3), indexing="ij")
+    P = np.zeros((3, 27))
+    P[fc.param_names.index("vvdd.dc")] = vdd.ravel(order="F")
+    P[fc.param_names.index("xneg.nfin")] = nfin.ravel(order="F")
+    P[fc.param_names.index("xneg.l")] = ln.ravel(order="F")
+    ts = np.linspace(0, 4e-9, 81)
+    (yg, sg, _), (yo, so, _) = run_tran_both(fc, ms, P, 0.0, 4e-9, ts, fixed_step=1, dt=2e-12)
+    assert sg.max() == 0 and so.max() == 0
+    assert_tran_close(yg, yo)
+
+
+DFF_NODESET = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki=0.0, cki=0.7)
+
+
+def test_bsimcmg_dff_mc_fixed(host_bsimcmg):
+    # BASELINE config 3 at reduced size and span: 30-FET DFF, Monte-Carlo L/NFIN, fixed step
+    fc, ms = circuits.dff(host_bsimcmg)
+    P = circuits.dff_mc_params(fc, 16)
+    x0 = x0_from(fc, DFF_NODESET)
+    ts = np.linspace(0, 5.2e-8, 53)
+    (yg, sg, stg), (yo, so, sto) = run_tran_both(fc, ms, P, 0.0, 5.2e-8, ts, x0=x0, fixed_step=1, dt=25e-12)
+    assert sg.max() == 0 and so.max() == 0
+    assert_tran_close(yg, yo)
+    # borderline convergence decisions may differ by an iteration between FMA and non-FMA arithmetic
+    assert abs(stg["newton_iters"] - sto["newton_iters"]) <= 1e-3 * sto["newton_iters"]
+
+
+def test_bsimcmg_dff_adaptive_known_answers(host_bsimcmg):
+    # full span, adaptive: Q follows the reference's known pattern 0,0,VDD,VDD,VDD
+    # (test/gf180_dff.jl:29-33 asserts 0,0,5,5,5 V on the GF180 deck; same topology at 0.7 V here)
+    fc, ms = circuits.dff(host_bsimcmg)
+    P = circuits.dff_mc_params(fc, 64)
+    x0 = x0_from(fc, DFF_NODESET)
+    ts = np.array([1.5e-7, 2.5e-7, 4.5e-7, 5.5e-7, 6.0e-7])
+    (yg, sg, stg), (yo, so, sto) = run_tran_both(fc, ms, P, 0.0, 6e-7, ts, x0=x0, reltol=1e-3)
+    assert sg.max() == 0 and so.max() == 0
+    want = np.array([0, 0, 0.7, 0.7, 0.7])[:, None]
+    assert np.abs(yg[0] - want).max() < 1e-3
+    assert np.abs(yg - yo).max() < 1e-3
