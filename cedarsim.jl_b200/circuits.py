@@ -9,7 +9,7 @@ transistor-level workloads use BSIM-CMG 107 with the ASAP7 cards, same topologie
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 
@@ -17,29 +17,36 @@ from . import models
 from .flat import FlatCircuit, VAModelShape, Wave, W_PWL, W_DC
 
 
-def _shape(cm, host_model=None) -> VAModelShape:
-    if host_model is not None:
-        return host_model.shape()
-    return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol))
+def _model(fc: FlatCircuit, card: str, host: bool, used: list) -> int:
+    """Register BSIM-CMG specialised on `card`; with host=True the shape also carries the addresses
+    of the host-compiled setup/eval functions (needed only by the CPU oracle in tests)."""
+    cm = models.bsimcmg107_card(card)
+    if cm not in used:
+        used.append(cm)
+    if host:
+        from .va.build import build_host
+        shape = build_host(cm).shape()
+    else:
+        shape = VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol))
+    return fc.va_model(shape)
 
 
-def fet_iv(host_model=None, card: str = "nmos_lvt", nfin: float = 3.0, l: float = 20e-9):
-    cm, cards = models.bsimcmg107(), models.asap7_cards()
-    fc = FlatCircuit()
-    m = fc.va_model(_shape(cm, host_model))
+def fet_iv(host: bool = False, card: str = "nmos_lvt", nfin: float = 3.0, l: float = 20e-9):
+    fc, used = FlatCircuit(), []
+    m = _model(fc, card, host, used)
     fc.vsource("Vg", "g", "0", fc.param("vg.dc"))
     fc.vsource("Vd", "d", "0", fc.param("vd.dc"))
-    fc.va_instance("m1", m, ["d", "g", "0", "0"], dict(cards[card].params, L=l, NFIN=nfin))
+    fc.va_instance("m1", m, ["d", "g", "0", "0"], dict(L=l, NFIN=nfin))
     fc.set_outputs(["vd.i", "m1.di", "m1.si"])
-    return fc, [cm]
+    return fc, used
 
 
-def inverter(host_model=None, vdd=0.7, sweep: bool = True, cload: float = 1e-15, tscale: float = 1.0):
+def inverter(host: bool = False, vdd=0.7, sweep: bool = True, cload: float = 1e-15, tscale: float = 1.0):
     """CMOS inverter, topology of benchmarks/benchmark_common.jl:82-106 (Xneg/Xpos, VVDD, VD PWL,
     CQ on the output).  Swept columns: vvdd.dc, xneg.nfin, xneg.l (FinFET analogue of W, L)."""
-    cm, cards = models.bsimcmg107(), models.asap7_cards()
-    fc = FlatCircuit()
-    m = fc.va_model(_shape(cm, host_model))
+    fc, used = FlatCircuit(), []
+    mn = _model(fc, "nmos_lvt", host, used)
+    mp = _model(fc, "pmos_lvt", host, used)
     vd = fc.param("vvdd.dc") if sweep else vdd
     nfin = fc.param("xneg.nfin") if sweep else 3.0
     ln = fc.param("xneg.l") if sweep else 21e-9
@@ -49,11 +56,11 @@ def inverter(host_model=None, vdd=0.7, sweep: bool = True, cload: float = 1e-15,
     t = np.array([0, 50, 60, 150, 160, 250, 260, 400]) * 1e-9 * tscale
     y = [0.0, 0.0, vdd, vdd, 0.0, 0.0, vdd, vdd]
     fc.vsource("VD", "d", "0", Wave(W_PWL, t=list(t), y=y))
-    fc.va_instance("xneg", m, ["q", "d", "vss", "vss"], dict(cards["nmos_lvt"].params, L=ln, NFIN=nfin))
-    fc.va_instance("xpos", m, ["q", "d", "vdd", "vdd"], dict(cards["pmos_lvt"].params, L=21e-9, NFIN=3.0))
+    fc.va_instance("xneg", mn, ["q", "d", "vss", "vss"], dict(L=ln, NFIN=nfin))
+    fc.va_instance("xpos", mp, ["q", "d", "vdd", "vdd"], dict(L=21e-9, NFIN=3.0))
     fc.capacitor("CQ", "q", "0", cload)
     fc.set_outputs(["q", "d"])
-    return fc, [cm]
+    return fc, used
 
 
 # (name, drain, gate, source, bulk, kind, nfin): topology of
@@ -78,20 +85,19 @@ _DFF_FETS: List[Tuple[str, str, str, str, str, str, int]] = [
 DFF_FET_NAMES = [f[0] for f in _DFF_FETS]
 
 
-def dff(host_model=None, vdd: float = 0.7, sweep: bool = True, tscale: float = 1.0, cq: float = 2e-15):
+def dff(host: bool = False, vdd: float = 0.7, sweep: bool = True, tscale: float = 1.0, cq: float = 2e-15):
     """30-FET DFF + 7 V sources + load cap, deck shape of test/DFF/DFF_cap_all.cir.  With `sweep`
     every FET gets two swept columns `<inst>.l` and `<inst>.nfin` (P = 60, Monte-Carlo draws are
     supplied by the caller as a TandemSweep of pre-drawn values)."""
-    cm, cards = models.bsimcmg107(), models.asap7_cards()
-    fc = FlatCircuit()
-    m = fc.va_model(_shape(cm, host_model))
+    fc, used = FlatCircuit(), []
+    mn = _model(fc, "nmos_lvt", host, used)
+    mp = _model(fc, "pmos_lvt", host, used)
     fc.vsource("VVDD", "vdd", "0", vdd)
     fc.vsource("VVSS", "vss", "0", 0.0)
     for name, d, g, s, b, kind, nfin in _DFF_FETS:
-        card = cards["nmos_lvt" if kind == "n" else "pmos_lvt"].params
         ln = fc.param(f"{name}.l") if sweep else 21e-9
         nf = fc.param(f"{name}.nfin") if sweep else float(nfin)
-        fc.va_instance(name, m, [d, g, s, b], dict(card, L=ln, NFIN=nf))
+        fc.va_instance(name, mn if kind == "n" else mp, [d, g, s, b], dict(L=ln, NFIN=nf))
     fc.capacitor("CQ", "q_tmp", "0", cq)
     fc.vsource("VQ", "q", "q_tmp", 0.0)
     fc.vsource("VNW", "vnw", "vdd", 0.0)
@@ -104,7 +110,7 @@ def dff(host_model=None, vdd: float = 0.7, sweep: bool = True, tscale: float = 1
     fc.vsource("VCLKN", "clkn", "0", Wave(W_PWL, t=list(tc), y=yc))
     fc.vsource("VD", "d", "0", Wave(W_PWL, t=list(td), y=yd))
     fc.set_outputs(["q", "d"])
-    return fc, [cm]
+    return fc, used
 
 
 def dff_nominal_params() -> Dict[str, float]:

@@ -320,7 +320,7 @@ static int build_tables(cb_circuit* c) {
 
 static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
     std::string full = std::string(CB_VA_PRELUDE) + "\n" + c->cuda_source;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device", "-w"};
     std::string key;
     {
         char buf[64];
@@ -339,14 +339,14 @@ static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, full.c_str(), "cb_models.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(CB_ERR_NVRTC, "nvrtcCreateProgram failed");
-    nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
+    nvrtcResult r = nvrtcCompileProgram(prog, 5, opts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
         nvrtcGetProgramLogSize(prog, &n);
         std::string log(n, 0);
         nvrtcGetProgramLog(prog, &log[0]);
         nvrtcDestroyProgram(&prog);
-        if (log.size() > 6000) log.resize(6000);
+        if (log.size() > 6000) log = log.substr(0, 3000) + "\n...\n" + log.substr(log.size() - 3000);
         return fail(CB_ERR_NVRTC, "NVRTC: " + log);
     }
     size_t sz = 0;
@@ -458,8 +458,8 @@ static int pick_group(const cb_circuit* c) {
     const char* env = std::getenv("CB_GROUP");
     if (env) { int g = std::atoi(env); if (g == 4 || g == 8 || g == 16 || g == 32) return g; }
     if (c->sym.nnz_lu <= 64) return 4;
-    if (c->sym.nnz_lu <= 2048) return 8;
-    return 16;
+    if (c->sym.nnz_lu <= 256) return 8;
+    return 32;
 }
 
 extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** out) {

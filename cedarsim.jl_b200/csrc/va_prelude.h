@@ -10,6 +10,7 @@ typedef unsigned char uint8_t;
 #define INFINITY __longlong_as_double(0x7ff0000000000000LL)
 #define NAN __longlong_as_double(0x7ff8000000000000LL)
 #define VA_FN static __device__ __forceinline__
+#define VA_OPS(a, m, d, s)
 
 struct VaArgs {
     long long B;                 // sweep points on this device

@@ -59,6 +59,16 @@ def bsimcmg107(rebuild: bool = False) -> CompiledModel:
     return compiled_model("bsimcmg107", BSIMCMG_VA, rebuild, suppress_defines=["__OPINFO__"])
 
 
+def bsimcmg107_card(card: str, runtime=("L", "NFIN"), rebuild: bool = False) -> CompiledModel:
+    """BSIM-CMG 107 specialised on one ASAP7 model card: every card parameter is folded at code
+    generation time (circuit-specialised CUDA C, as the north star asks); only `runtime`
+    instance parameters are read per device / per sweep point."""
+    params = asap7_cards()[card].params
+    name = f"bsimcmg107_{card}"
+    return compiled_model(name, BSIMCMG_VA, rebuild, suppress_defines=["__OPINFO__"], const_params=params,
+                          runtime_params=list(runtime))
+
+
 def asap7_cards(rebuild: bool = False) -> Dict[str, ModelCard]:
     path = os.path.join(GEN_DIR, "asap7_cards.json")
     if os.path.exists(path) and not rebuild:
@@ -74,5 +84,5 @@ def asap7_cards(rebuild: bool = False) -> Dict[str, ModelCard]:
 
 
 def available() -> bool:
-    return (os.path.exists(os.path.join(GEN_DIR, "bsimcmg107.model.json")) or os.path.exists(BSIMCMG_VA)) and \
+    return (os.path.exists(os.path.join(GEN_DIR, "bsimcmg107_nmos_lvt.model.json")) or os.path.exists(BSIMCMG_VA)) and \
            (os.path.exists(os.path.join(GEN_DIR, "asap7_cards.json")) or os.path.exists(ASAP7_CARDS))

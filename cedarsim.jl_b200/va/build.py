@@ -17,8 +17,10 @@ GEN_DIR = os.path.join(os.path.dirname(_HERE), "_gen")
 HOST_CC = "/usr/bin/gcc"
 
 
-def c_prelude(nterm: int) -> str:
-    return f"""
+def c_prelude(nterm: int, count_ops: bool = False) -> str:
+    ops = ("double va_ops_[4];\n#define VA_OPS(a, m, d, s) (va_ops_[0] += (a), va_ops_[1] += (m), va_ops_[2] += (d), va_ops_[3] += (s))\n"
+           if count_ops else "#define VA_OPS(a, m, d, s)\n")
+    return ops + f"""
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -75,6 +77,16 @@ class HostModel:
                    C.c_double(temp_c), C.c_double(gmin), cache.ctypes.data_as(C.POINTER(C.c_double)))
         return cache
 
+    def executed_ops(self, cache, v):
+        """(add, mul, div, special) source-level FP64 operation counts on the path executed for bias v
+        (needs build_host(..., count_ops=True)); special = exp/log/sqrt/pow/trig calls."""
+        import numpy as np
+        arr = (C.c_double * 4).in_dll(self.lib, "va_ops_")
+        for k in range(4):
+            arr[k] = 0.0
+        self.run_eval(cache, v)
+        return tuple(int(arr[k]) for k in range(4))
+
     def run_eval(self, cache, v):
         import numpy as np
         nt = len(self.cm.terminals)
@@ -85,10 +97,10 @@ class HostModel:
         return I, Q, G, Cm
 
 
-def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O1") -> HostModel:
+def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O1", count_ops: bool = False) -> HostModel:
     out_dir = out_dir or GEN_DIR
     os.makedirs(out_dir, exist_ok=True)
-    text = c_prelude(len(cm.terminals)) + cm.source
+    text = c_prelude(len(cm.terminals), count_ops) + cm.source
     key = hashlib.sha1((text + opt).encode()).hexdigest()[:16]
     base = os.path.join(out_dir, f"{cm.name}_{key}")
     so = base + ".so"

@@ -43,6 +43,101 @@ MATH2 = {"pow", "min", "max", "atan2", "hypot"}
 
 P_K, P_Q = 1.3806503e-23, 1.602176462e-19
 
+_PYF = {"ln": math.log, "log": math.log10, "abs": abs, "min": min, "max": max, "exp": math.exp, "sqrt": math.sqrt,
+        "pow": math.pow, "sin": math.sin, "cos": math.cos, "tan": math.tan, "asin": math.asin, "acos": math.acos,
+        "atan": math.atan, "atan2": math.atan2, "sinh": math.sinh, "cosh": math.cosh, "tanh": math.tanh,
+        "asinh": math.asinh, "acosh": math.acosh, "atanh": math.atanh, "hypot": math.hypot, "floor": math.floor,
+        "ceil": math.ceil, "limexp": lambda x: math.exp(x) if x < 80.0 else math.exp(80.0) * (1.0 + x - 80.0)}
+
+
+class _NotConst(Exception):
+    pass
+
+
+def _vaconvert_int(x: float) -> int:
+    """real -> integer conversion, ties away from zero (src/va_env.jl:107)"""
+    return int(math.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
+
+class _ConstEval:
+    """Compile-time evaluation of analog functions whose arguments are all constants: lets the
+    generator fold everything that depends only on a model card (circuit-specialised code)."""
+
+    def __init__(self, functions):
+        self.functions = functions
+
+    def call(self, fname: str, args: List[float]):
+        f = self.functions[fname]
+        if any(kind != "input" for _, kind in f.args):
+            raise _NotConst()
+        env = {v: (0 if t == "integer" else 0.0) for v, t in f.var_types.items()}
+        types = dict(f.var_types)
+        for (an, _), v in zip(f.args, args):
+            env[an] = _vaconvert_int(v) if types.get(an) == "integer" and isinstance(v, float) else v
+        self.stmt(f.body, env, types)
+        return env[fname]
+
+    def stmt(self, st, env, types):
+        k = st[0]
+        if k in ("nop", "task"):
+            return
+        if k == "block":
+            if st[3]:
+                raise _NotConst()
+            for s_ in st[2]:
+                self.stmt(s_, env, types)
+        elif k == "assign":
+            v = self.expr(st[2], env)
+            if st[1] not in env:
+                raise _NotConst()
+            env[st[1]] = _vaconvert_int(v) if types.get(st[1]) == "integer" and isinstance(v, float) else \
+                (float(v) if types.get(st[1]) != "integer" else v)
+        elif k == "if":
+            if self.expr(st[1], env):
+                self.stmt(st[2], env, types)
+            elif st[3] is not None:
+                self.stmt(st[3], env, types)
+        else:
+            raise _NotConst()
+
+    def expr(self, e, env):
+        k = e[0]
+        if k == "num":
+            return e[1]
+        if k == "var":
+            if e[1] not in env:
+                raise _NotConst()
+            return env[e[1]]
+        if k == "un":
+            a = self.expr(e[2], env)
+            if e[1] == "-":
+                return -a
+            if e[1] == "!":
+                return int(not a)
+            raise _NotConst()
+        if k == "bin":
+            a, b = self.expr(e[2], env), self.expr(e[3], env)
+            both_int = isinstance(a, int) and isinstance(b, int)
+            try:
+                return _Compiler._fold(e[1], a, b, both_int)
+            except (ValueError, ZeroDivisionError, OverflowError):
+                raise _NotConst()
+        if k == "cond":
+            return self.expr(e[2], env) if self.expr(e[1], env) else self.expr(e[3], env)
+        if k == "call":
+            args = [self.expr(a, env) for a in e[2]]
+            if e[1] in self.functions:
+                return self.call(e[1], args)
+            fn = _PYF.get(e[1])
+            if fn is None:
+                raise _NotConst()
+            try:
+                r = fn(*[float(a) for a in args])
+            except (ValueError, OverflowError, ZeroDivisionError):
+                raise _NotConst()
+            return float(r)
+        raise _NotConst()
+
 
 def _lit(x) -> str:
     if isinstance(x, bool):
@@ -267,9 +362,14 @@ class CompiledModel:
 
 
 class _Compiler:
-    def __init__(self, mod: Module, name: str):
+    def __init__(self, mod: Module, name: str, const_params: Optional[Dict[str, float]] = None,
+                 runtime_params: Optional[Sequence[str]] = None):
         self.mod = mod
         self.name = name
+        # specialisation: parameters with compile-time values (a model card) are folded; only
+        # `runtime_params` are read through PAR(); every other parameter takes its default
+        self.const_params = None if const_params is None else {k.upper(): v for k, v in const_params.items()}
+        self.runtime_params = None if runtime_params is None else {k.upper() for k in runtime_params}
         self.terms = list(mod.nets)
         self.tindex = {n: i for i, n in enumerate(self.terms)}
         self.S: List[str] = []      # setup stream
@@ -286,6 +386,7 @@ class _Compiler:
         self.census: Dict[str, int] = {}
         self.forced_all: Set[str] = set()         # variables forced to carry all seeds (loops)
         self.dead_locals: Set[str] = set()        # locals of inlined functions / blocks out of scope
+        self.block_ops: Dict[int, List[int]] = {}
         self.params = {p.name: p for p in mod.params}
         for p in mod.params:
             cn = "p_" + p.name
@@ -310,6 +411,16 @@ class _Compiler:
 
     def count(self, op: str, n: int = 1):
         self.census[op] = self.census.get(op, 0) + n
+        # per-basic-block tallies, emitted as VA_OPS(add, mul, div, special) so that an
+        # instrumented host build can report the op count of the *executed* path
+        if n:
+            blk = self.block_ops.setdefault(id(self.E), [0, 0, 0, 0])
+            blk[{"add": 0, "mul": 1, "div": 2}.get(op, 3)] += n
+
+    def flush_ops(self, lst: List[str]):
+        blk = self.block_ops.pop(id(lst), None)
+        if blk and any(blk):
+            lst.append(f"VA_OPS({blk[0]}, {blk[1]}, {blk[2]}, {blk[3]});")
 
     def vs(self, cname: str) -> VS:
         s = self.state.get(cname)
@@ -456,6 +567,9 @@ class _Compiler:
             p = self.params.get(args[0][1]) if args and args[0][0] == "var" else None
             if p is None:
                 raise VACompileError("$param_given needs a parameter name")
+            if p.name in getattr(self, "given_const", {}):
+                g = self.given_const[p.name]
+                return str(g), "i", g
             return f"GIVEN({p.index})", "i", None
         if fn == "$simparam":
             key = args[0][1] if args and args[0][0] == "str" else None
@@ -476,6 +590,15 @@ class _Compiler:
             f = self.mod.functions[fn]
             if len(args) != len(f.args):
                 raise VACompileError(f"wrong number of arguments to function {fn}")
+            if all(kind == "input" for _, kind in f.args):
+                consts = [self.gs(a)[2] for a in args]
+                if all(c is not None for c in consts):
+                    try:
+                        cv = _ConstEval(self.mod.functions).call(fn, list(consts))
+                        if isinstance(cv, int) or math.isfinite(cv):
+                            return _lit(cv), ("i" if f.type == "integer" else "r"), cv
+                    except _NotConst:
+                        pass
             cargs = []
             for (an, kind), a in zip(f.args, args):
                 if kind == "input":
@@ -490,7 +613,7 @@ class _Compiler:
                     self.static_vars.add(cn)
                     cargs.append("&" + cn)
             self.used_funcs.add(fn)
-            return f"f_{fn}({', '.join(cargs)})", ("i" if f.type == "integer" else "r"), None
+            return f"f_{self.name}_{fn}({', '.join(cargs)})", ("i" if f.type == "integer" else "r"), None
         if fn in MATH1 or fn in MATH2:
             cs = [self.gs(a) for a in args]
             cstr = [self._cast(c, t, "r") for c, t, _ in cs]
@@ -508,8 +631,7 @@ class _Compiler:
             const = None
             if all(c is not None for c in consts):
                 try:
-                    pyf = {"ln": math.log, "log": math.log10, "abs": abs, "min": min, "max": max,
-                           "exp": math.exp, "sqrt": math.sqrt, "pow": math.pow}.get(fn)
+                    pyf = _PYF.get(fn)
                     if pyf is not None:
                         const = float(pyf(*[float(c) for c in consts]))
                 except (ValueError, OverflowError, ZeroDivisionError):
@@ -1186,6 +1308,7 @@ class _Compiler:
         self.dynctl = dyn or save_dyn
         if st is not None:
             self.stmt(st)
+        self.flush_ops(self.E)
         out = (self.S, self.E, self.state)
         self.S, self.E, self.state, self.dynctl = save_S, save_E, save_state, save_dyn
         return out
@@ -1292,6 +1415,7 @@ class _Compiler:
         _assigned(body, asg, self.mod.functions)
         names = [self.resolve(n) for n in asg]
         # trial run on a scratch copy to classify the loop
+        saved_ops = {k: list(v) for k, v in self.block_ops.items()}
         saved = (self.S, self.E, self.state, self.ntemp, self.nslot, self.ninl, dict(self.census),
                  {k: set(v) for k, v in self.decl_deps.items()}, set(self.dyn_vars), set(self.static_vars))
         self.S, self.E, self.state = [], [], self._snapshot_state()
@@ -1304,6 +1428,7 @@ class _Compiler:
             static_ok = not self.E and self.is_static_expr(cond)
         (self.S, self.E, self.state, self.ntemp, self.nslot, self.ninl, self.census, self.decl_deps,
          self.dyn_vars, self.static_vars) = saved
+        self.block_ops = saved_ops
         if static_ok:
             for cn in names:
                 s = self.vs(cn)
@@ -1337,6 +1462,7 @@ class _Compiler:
         cv = self.force(self.gd(cond))
         self.E.append(f"if (!({cv.c})) break;")
         self.stmt(body)
+        self.flush_ops(self.E)
         inner = self.E
         self.E = outer
         self.dynctl = save_dyn
@@ -1351,21 +1477,49 @@ class _Compiler:
     def compile(self) -> CompiledModel:
         mod = self.mod
         self.used_funcs: Set[str] = set()
+        self.given_const: Dict[str, int] = {}
         # parameters: value if given, else default expression (may reference earlier parameters)
         for p in mod.params:
             cn = "p_" + p.name
             if p.type == "string":
                 continue
             self.state[cn] = VS(False, frozenset(), None, None)
-            dflt, t, _ = self.gs(p.default)
             ctyp = "i" if p.type == "integer" else "r"
             raw = f"PAR({p.index})"
+            if self.const_params is not None:
+                pu = p.name.upper()
+                if pu in self.runtime_params:
+                    self.given_const[p.name] = 1
+                    self.S.append(f"{cn} = {self._cast(raw, 'r', ctyp)};")
+                    self.static_vars.add(cn)
+                    continue
+                self.given_const[p.name] = 1 if pu in self.const_params else 0
+                if pu in self.const_params:
+                    v = float(self.const_params[pu])
+                    cv = _vaconvert_int(v) if ctyp == "i" else v
+                    self.state[cn] = VS(False, frozenset(), None, cv)
+                    continue
+                dflt, t, dc = self.gs(p.default)
+                if dc is not None:
+                    cv = (_vaconvert_int(dc) if t == "r" else int(dc)) if ctyp == "i" else float(dc)
+                    self.state[cn] = VS(False, frozenset(), None, cv)
+                else:
+                    self.S.append(f"{cn} = {self._cast(dflt, t, ctyp)};")
+                    self.static_vars.add(cn)
+                continue
+            dflt, t, _ = self.gs(p.default)
             self.S.append(f"{cn} = GIVEN({p.index}) ? {self._cast(raw, 'r', ctyp)} : {self._cast(dflt, t, ctyp)};")
             self.static_vars.add(cn)
+        if self.const_params is not None:
+            known = {p.name.upper() for p in mod.params}
+            bad = [k for k in list(self.const_params) + list(self.runtime_params) if k not in known]
+            if bad:
+                raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
         pruned, _ = prune_dead(body, set(), mod.functions)
         if pruned is not None:
             self.stmt(pruned)
+        self.flush_ops(self.E)
         nt = len(self.terms)
         # outputs
         jrow, jcol = [], []
@@ -1405,7 +1559,7 @@ class _Compiler:
             sig.append(f"{ct}{'*' if kind != 'input' else ''} {'o_' if kind != 'input' else 'l_'}{a}")
         lines = []
         rt = "int" if f.type == "integer" else "double"
-        lines.append(f"VA_FN {rt} f_{f.name}({', '.join(sig)}) {{")
+        lines.append(f"VA_FN {rt} f_{self.name}_{f.name}({', '.join(sig)}) {{")
         for v, t in f.var_types.items():
             if v in [a for a, k in f.args if k == "input"]:
                 continue
@@ -1460,23 +1614,25 @@ class _Compiler:
         return "\n".join(L) + "\n"
 
 
-def compile_module(mod: Module, name: Optional[str] = None) -> CompiledModel:
-    return _Compiler(mod, name or mod.name).compile()
+def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None) -> CompiledModel:
+    return _Compiler(mod, name or mod.name, const_params, runtime_params).compile()
 
 
 def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,
-                    include_paths: Sequence[str] = (), defines=None, suppress_defines=()) -> CompiledModel:
+                    include_paths: Sequence[str] = (), defines=None, suppress_defines=(),
+                    const_params=None, runtime_params=None) -> CompiledModel:
     pp = Preprocessor(include_paths, defines, suppress_defines)
     text = pp.process_file(path)
-    return compile_va_text(text, module, name, preprocessed=True)
+    return compile_va_text(text, module, name, preprocessed=True, const_params=const_params,
+                           runtime_params=runtime_params)
 
 
 def compile_va_text(text: str, module: Optional[str] = None, name: Optional[str] = None,
-                    preprocessed: bool = False, defines=None) -> CompiledModel:
+                    preprocessed: bool = False, defines=None, const_params=None, runtime_params=None) -> CompiledModel:
     if not preprocessed:
         text = Preprocessor((), defines).process_text(text)
     mods = parse(text)
     if not mods:
         raise VACompileError("no module found")
     mod = mods[-1] if module is None else next(m for m in mods if m.name == module)
-    return compile_module(mod, name)
+    return compile_module(mod, name, const_params, runtime_params)

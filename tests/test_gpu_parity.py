@@ -81,7 +81,7 @@ def test_pwl_current_source_fixed():
 
 def test_bsimcmg_fet_iv_dc(host_bsimcmg):
     # BASELINE config 4 at reduced size: ASAP7 nmos_lvt I-V grid
-    fc, ms = circuits.fet_iv(host_bsimcmg)
+    fc, ms = circuits.fet_iv(host=host_bsimcmg)
     vg, vd = np.meshgrid(np.linspace(0, 0.9, 24), np.linspace(0, 0.9, 24), indexing="ij")
     P = params_matrix([vg.ravel(order="F"), vd.ravel(order="F")])
     (xg, xfg, sg, _), (xo, xfo, so, _) = run_dc_both(fc, ms, P)
@@ -93,7 +93,7 @@ def test_bsimcmg_fet_iv_dc(host_bsimcmg):
 
 def test_bsimcmg_inverter_tran_fixed(host_bsimcmg):
     # BASELINE config 2 at reduced size: vdd x nfin x l sweep, fixed-step trapezoidal
-    fc, ms = circuits.inverter(host_bsimcmg, tscale=0.01)
+    fc, ms = circuits.inverter(host=host_bsimcmg, tscale=0.01)
     vdd, nfin, ln = np.meshgrid(np.linspace(0.56, 0.84, 3), np.linspace(2, 6, 3), np.linspace(21e-9, 40e-9, 3), indexing="ij")
     P = np.zeros((3, 27))
     P[fc.param_names.index("vvdd.dc")] = vdd.ravel(order="F")
@@ -110,7 +110,7 @@ DFF_NODESET = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki
 
 def test_bsimcmg_dff_mc_fixed(host_bsimcmg):
     # BASELINE config 3 at reduced size and span: 30-FET DFF, Monte-Carlo L/NFIN, fixed step
-    fc, ms = circuits.dff(host_bsimcmg)
+    fc, ms = circuits.dff(host=host_bsimcmg)
     P = circuits.dff_mc_params(fc, 16)
     x0 = x0_from(fc, DFF_NODESET)
     ts = np.linspace(0, 5.2e-8, 53)
@@ -124,7 +124,7 @@ def test_bsimcmg_dff_mc_fixed(host_bsimcmg):
 def test_bsimcmg_dff_adaptive_known_answers(host_bsimcmg):
     # full span, adaptive: Q follows the reference's known pattern 0,0,VDD,VDD,VDD
     # (test/gf180_dff.jl:29-33 asserts 0,0,5,5,5 V on the GF180 deck; same topology at 0.7 V here)
-    fc, ms = circuits.dff(host_bsimcmg)
+    fc, ms = circuits.dff(host=host_bsimcmg)
     P = circuits.dff_mc_params(fc, 64)
     x0 = x0_from(fc, DFF_NODESET)
     ts = np.array([1.5e-7, 2.5e-7, 4.5e-7, 5.5e-7, 6.0e-7])
