@@ -320,11 +320,23 @@ static int build_tables(cb_circuit* c) {
 
 static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
     std::string full = std::string(CB_VA_PRELUDE) + "\n" + c->cuda_source;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device", "-w"};
+    // experiment knobs (they change the cache key): CB_MAXREG=<n>, CB_NVRTC_DEFS="-DX=1 -DY"
+    std::string maxreg = std::getenv("CB_MAXREG") ? std::string("--maxrregcount=") + std::getenv("CB_MAXREG") : "";
+    std::vector<std::string> extra;
+    if (const char* d = std::getenv("CB_NVRTC_DEFS")) {
+        std::istringstream is(d);
+        std::string tok;
+        while (is >> tok) extra.push_back(tok);
+    }
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device", "-w"};
+    if (!maxreg.empty()) opts.push_back(maxreg.c_str());
+    for (const std::string& e : extra) opts.push_back(e.c_str());
     std::string key;
     {
+        std::string tag = full + "|sm_100a|v1|" + maxreg;
+        for (const std::string& e : extra) tag += "|" + e;
         char buf[64];
-        std::snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(full + "|sm_100a|v1"));
+        std::snprintf(buf, sizeof buf, "%016llx", (unsigned long long)fnv1a(tag));
         key = buf;
     }
     std::string path;
@@ -339,7 +351,7 @@ static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, full.c_str(), "cb_models.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(CB_ERR_NVRTC, "nvrtcCreateProgram failed");
-    nvrtcResult r = nvrtcCompileProgram(prog, 5, opts);
+    nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
         nvrtcGetProgramLogSize(prog, &n);
@@ -406,6 +418,7 @@ struct cb_plan {
     std::vector<void*> allocs;
     NArgs na{};
     int G = 8, gpc = 1;
+    bool glob = false;       // thread-per-point k_newton with the matrix in global scratch
     size_t smem_bytes = 0;
     // device arrays
     double* d_params = nullptr;
@@ -433,6 +446,7 @@ struct cb_plan {
     double* d_x0 = nullptr;
     long long x0_stride = 0;
     bool have_x0 = false;
+    bool timing = false;
     cb_pref last_temp{}, last_gmin{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -583,30 +597,44 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
         TRY(p->upload(&dt_, term)); TRY(p->upload(&dc_, pcol)); TRY(p->upload(&dv_, pval)); TRY(p->upload(&dg_, giv));
         p->d_term.push_back(dt_); p->d_par_col.push_back(dc_); p->d_par_val.push_back(dv_); p->d_given.push_back(dg_);
     }
-    // launch geometry of k_newton: G lanes per point, as many points per CTA as shared memory allows
-    p->G = pick_group(c);
-    int per = S.nnz_lu + 3 * N + a.nwaves;
+    // launch geometry of k_newton.  Two variants: (a) one thread per point with the matrix in a
+    // batch-interleaved global scratch (default for batches that fill the GPU), (b) G lanes per point
+    // with the matrix in shared memory (small batches, where per-point parallelism matters).
+    const int per_raw = S.nnz_lu + 3 * N + a.nwaves;
     {
-        const int want = p->G / 2;  // stagger groups of one warp across shared-memory banks
-        while (p->G < 32 && (per % 16) != want) per++;
+        const char* env = std::getenv("CB_NEWTON");
+        p->glob = env ? std::string(env) == "glob" : (B >= 4096);
     }
-    a.sm_stride = per;
-    const size_t per_bytes = (size_t)per * sizeof(double);
-    int max_smem = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
-    if (per_bytes > (size_t)max_smem)
-        return fail(CB_ERR_INVALID, "circuit too large for the shared-memory LU (nnz(L+U) = " + std::to_string(S.nnz_lu) + ")");
-    int gpc = (int)std::min<size_t>(256 / p->G, (size_t)max_smem / per_bytes);
-    // keep at least 2 CTAs per SM resident when the circuit is small
-    while (gpc > 4 && (size_t)gpc * per_bytes > (size_t)max_smem / 2) gpc--;
-    const int warp_groups = 32 / p->G;
-    if (gpc >= warp_groups) gpc -= gpc % warp_groups;
-    p->gpc = std::max(1, gpc);
-    p->smem_bytes = (size_t)p->gpc * per_bytes;
+    if (p->glob) {
+        p->G = 1; p->gpc = 64; p->smem_bytes = 0;
+        a.sm_stride = per_raw;
+        TRY(p->alloc(&a.scratch, (size_t)per_raw * B));
+    } else {
+        p->G = pick_group(c);
+        int per = per_raw;
+        {
+            const int want = p->G / 2;  // stagger groups of one warp across shared-memory banks
+            while (p->G < 32 && (per % 16) != want) per++;
+        }
+        a.sm_stride = per;
+        a.scratch = nullptr;
+        const size_t per_bytes = (size_t)per * sizeof(double);
+        int max_smem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
+        if (per_bytes > (size_t)max_smem)
+            return fail(CB_ERR_INVALID, "circuit too large for the shared-memory LU (nnz(L+U) = " + std::to_string(S.nnz_lu) + ")");
+        int gpc = (int)std::min<size_t>(256 / p->G, (size_t)max_smem / per_bytes);
+        // keep at least 2 CTAs per SM resident when the circuit is small
+        while (gpc > 4 && (size_t)gpc * per_bytes > (size_t)max_smem / 2) gpc--;
+        const int warp_groups = 32 / p->G;
+        if (gpc >= warp_groups) gpc -= gpc % warp_groups;
+        p->gpc = std::max(1, gpc);
+        p->smem_bytes = (size_t)p->gpc * per_bytes;
 #define SET_SMEM(GG)                                                                                     \
-    CUDA_TRY(cudaFuncSetAttribute(k_newton<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes))
-    if (p->G == 4) SET_SMEM(4); else if (p->G == 8) SET_SMEM(8); else if (p->G == 16) SET_SMEM(16); else SET_SMEM(32);
+    CUDA_TRY(cudaFuncSetAttribute(k_newton<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes))
+        if (p->G == 4) SET_SMEM(4); else if (p->G == 8) SET_SMEM(8); else if (p->G == 16) SET_SMEM(16); else SET_SMEM(32);
 #undef SET_SMEM
+    }
 #undef TRY
     *out = p.release();
     return CB_OK;
@@ -789,7 +817,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     const unsigned ngrid = (unsigned)((B + p->gpc - 1) / p->gpc);
     const unsigned nthreads = (unsigned)(p->gpc * p->G);
     const int poll = std::getenv("CB_POLL") ? std::max(1, std::atoi(std::getenv("CB_POLL"))) : 16;
-    const bool timing = std::getenv("CB_TIMING") != nullptr;
+    const bool timing = p->timing || std::getenv("CB_TIMING") != nullptr;
     std::vector<cudaEvent_t> evs;
     double t_eval = 0, t_newton = 0;
     int64_t rounds = 0, launches = 0;
@@ -797,6 +825,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     char vargs[8][256];
     if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
     for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs[m]);
+    const unsigned eval_threads = std::getenv("CB_EVAL_THREADS") ? (unsigned)std::atoi(std::getenv("CB_EVAL_THREADS")) : 128u;
     bool done = false;
     while (!done && rounds < max_rounds) {
         for (int r = 0; r < poll; r++) {
@@ -808,16 +837,17 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
                 void* kargs[] = {vargs[m]};
-                dim3 grid((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());
-                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(128), kargs, 0, p->stream));
+                dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
+                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(eval_threads), kargs, 0, p->stream));
                 launches++;
             }
             if (timing) cudaEventRecord(e1, p->stream);
-            switch (p->G) {
-                case 4: k_newton<4><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                case 8: k_newton<8><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                case 16: k_newton<16><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                default: k_newton<32><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+            if (p->glob) k_newton<1, true><<<ngrid, nthreads, 0, p->stream>>>(a);
+            else switch (p->G) {
+                case 4: k_newton<4, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                case 8: k_newton<8, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                case 16: k_newton<16, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
+                default: k_newton<32, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
             }
             launches++;
             if (timing) { cudaEventRecord(e2, p->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
@@ -908,6 +938,42 @@ extern "C" int cb_tran(cb_plan* p, double t0, double t1, const double* saveat, i
         CUDA_TRY(cudaMemcpy(y_out, p->d_y, (size_t)p->na.O * n_save * B * sizeof(double), cudaMemcpyDeviceToHost));
     if (status) CUDA_TRY(cudaMemcpy(status, p->na.ist + (size_t)IS_STATUS * B, B * sizeof(int), cudaMemcpyDeviceToHost));
     if (stats) stats->d2h_seconds = now_s() - t;
+    return CB_OK;
+}
+
+extern "C" int cb_plan_set_timing(cb_plan* p, int enable) {
+    if (!p) return fail(CB_ERR_INVALID, "null plan");
+    p->timing = enable != 0;
+    return CB_OK;
+}
+
+extern "C" int cb_measure_fp64_peak(int device_id, double* tflops) {
+    if (!tflops) return fail(CB_ERR_INVALID, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(CB_ERR_NO_DEVICE, "no CUDA device");
+    CUDA_TRY(cudaSetDevice(device_id));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id));
+    const int blocks = sms * 8, threads = 256, iters = 8192;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
     return CB_OK;
 }
 

@@ -25,7 +25,7 @@ enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3 };
 enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HITBP, IS_METHOD, IS_NP,
        IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_COUNT };
 // double per-point state rows
-enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_COUNT };
+enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_COUNT };
 
 struct Pref { double value; int col; int pad; };
 
@@ -69,6 +69,7 @@ struct NArgs {
     // per-point state, all [k][B]
     double *X, *XN, *X1, *X2, *XP, *QN, *Q1, *QD, *BETA, *alpha, *dst;
     int *ist, *active;
+    double* scratch;  // GLOB kernels: [nnz_lu + 3N + nwaves][B]
     const double* dev_out;
     double* y_out;  // tran: [O][S][B]; dc: [O][B]
     int* done_count;
@@ -166,7 +167,11 @@ __device__ __forceinline__ double poly_at(int nh, double tt, double tn, double x
     return xn + a * d1 + a * (a + h1) * dd;
 }
 
-template <int G>
+// GLOB = false: G lanes cooperate on one point, its matrix lives in shared memory.
+// GLOB = true (G must be 1): one thread per point, the matrix lives in a batch-interleaved global
+// scratch [entry][B] (L2-resident for the batch sizes of interest) -- every access of a warp is one
+// coalesced 256-byte row, there are no barriers and no redundant lanes.
+template <int G, bool GLOB>
 __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
     extern __shared__ double smem[];
     const int gpc = blockDim.x / G;
@@ -179,11 +184,13 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
     const int N = a.N, NV = a.NV;
     const Opts& o = a.o;
-    double* A = smem + (size_t)grp * a.sm_stride;
-    double* rhs = A + a.nnz_lu;
-    double* xs = rhs + N;
-    double* qk = xs + N;
-    double* wv = qk + N;
+    const size_t ST = GLOB ? (size_t)B : 1;   // element stride of the per-point work arrays
+    double* A = GLOB ? a.scratch + inst : smem + (size_t)grp * a.sm_stride;
+    double* rhs = A + (size_t)a.nnz_lu * ST;
+    double* xs = rhs + (size_t)N * ST;
+    double* qk = xs + (size_t)N * ST;
+    double* wv = qk + (size_t)N * ST;
+#define WA(arr, i) arr[(size_t)(i) * ST]
 
 #define IST(k) a.ist[(size_t)(k) * B + inst]
 #define DST(k) a.dst[(size_t)(k) * B + inst]
@@ -193,14 +200,14 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
     int sidx = IST(IS_SIDX), nnewton = IST(IS_NNEWTON), nacc = IST(IS_NACC), nrej = IST(IS_NREJ);
     int retry = IST(IS_RETRY);
     double t = DST(DS_T), tnew = DST(DS_TNEW), h = DST(DS_H), h1 = DST(DS_H1), h2 = DST(DS_H2);
-    double hprop = DST(DS_HPROP), gshunt = DST(DS_GSHUNT);
+    double hprop = DST(DS_HPROP), gshunt = DST(DS_GSHUNT), lim = DST(DS_LIM);
     double alpha = a.alpha[inst];
 
     // ---- 1. current iterate and source values -------------------------------------------
-    for (int i = lane; i < N; i += G) xs[i] = AT(a.X, i);
+    for (int i = lane; i < N; i += G) WA(xs, i) = AT(a.X, i);
     {
         const bool dcop = phase != PH_TRAN;
-        for (int w = lane; w < a.nwaves; w += G) wv[w] = wave_value(a.waves[w], tnew, dcop, a.params, B, inst);
+        for (int w = lane; w < a.nwaves; w += G) WA(wv, w) = wave_value(a.waves[w], tnew, dcop, a.params, B, inst);
     }
     __syncwarp(gmask);
 
@@ -214,24 +221,24 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
         }
         if (a.a_diag[e]) v += gshunt;
         for (int s = a.a_ptr[e]; s < a.a_ptr[e + 1]; s++) v += a.a_mult[s] * a.dev_out[(size_t)a.a_src[s] * B + inst];
-        A[e] = v;
+        WA(A, e) = v;
     }
     double rmax = 0.0;
     for (int i = lane; i < N; i += G) {
         double f = 0.0, q = 0.0;
         for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
             const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
-            const double xc = xs[a.rl_col[p]];
+            const double xc = WA(xs, a.rl_col[p]);
             f += a.lin_g[li] * xc;
             q += a.lin_c[li] * xc;
         }
         for (int p = a.ri_ptr[i]; p < a.ri_ptr[i + 1]; p++) f += a.ri_mult[p] * a.dev_out[(size_t)a.ri_src[p] * B + inst];
         for (int p = a.rq_ptr[i]; p < a.rq_ptr[i + 1]; p++) q += a.rq_mult[p] * a.dev_out[(size_t)a.rq_src[p] * B + inst];
-        for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * wv[a.rs_wave[p]];
-        if (i < NV) f += gshunt * xs[i];
+        for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * WA(wv, a.rs_wave[p]);
+        if (i < NV) f += gshunt * WA(xs, i);
         const double r = f + alpha * q + AT(a.BETA, i);
-        qk[i] = q;
-        rhs[a.row_to_step[i]] = -r;
+        WA(qk, i) = q;
+        WA(rhs, a.row_to_step[i]) = -r;
         rmax = fmax(rmax, fabs(r));
     }
     rmax = gmax<G>(rmax, gmask);
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
 
     if (phase == PH_TRAN_INIT) {
         // charges at the operating point; qdot(t0) = 0
-        for (int i = lane; i < N; i += G) { AT(a.QN, i) = qk[i]; AT(a.QD, i) = 0.0; }
+        for (int i = lane; i < N; i += G) { AT(a.QN, i) = WA(qk, i); AT(a.QD, i) = 0.0; }
         while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
             for (int k = lane; k < a.O; k += G) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = AT(a.XN, a.outputs[k]);
             sidx++;
@@ -254,30 +261,30 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
         // ---- 3. static-pivot sparse LU (right-looking) fused with the forward substitution ----
         bool singular = false;
         for (int k = 0; k < N; k++) {
-            const double d = A[a.diag_pos[k]];
+            const double d = WA(A, a.diag_pos[k]);
             if (!(fabs(d) > 0.0) || !isfinite(d)) singular = true;
             const double inv = 1.0 / d;
             const int lp = a.l_ptr[k], nL = a.l_ptr[k + 1] - lp;
             const int up = a.u_ptr[k], nU = a.u_ptr[k + 1] - up;
             const int pp = a.pair_ptr[k];
-            const double bk = rhs[k];
+            const double bk = WA(rhs, k);
             for (int li = lane; li < nL; li += G) {
                 const int lpos = a.l_pos[lp + li];
-                const double l = A[lpos] * inv;
-                A[lpos] = l;
+                const double l = WA(A, lpos) * inv;
+                WA(A, lpos) = l;
                 const int* dst = a.pair_dst + pp + li * nU;
-                for (int uj = 0; uj < nU; uj++) A[dst[uj]] -= l * A[a.u_pos[up + uj]];
-                rhs[a.l_row[lp + li]] -= l * bk;
+                for (int uj = 0; uj < nU; uj++) WA(A, dst[uj]) -= l * WA(A, a.u_pos[up + uj]);
+                WA(rhs, a.l_row[lp + li]) -= l * bk;
             }
             __syncwarp(gmask);
         }
         // ---- backward substitution, column oriented ----
         for (int k = N - 1; k >= 0; k--) {
-            const double xk = rhs[k] / A[a.diag_pos[k]];
+            const double xk = WA(rhs, k) / WA(A, a.diag_pos[k]);
             __syncwarp(gmask);
-            if (lane == 0) rhs[k] = xk;
+            if (lane == 0) WA(rhs, k) = xk;
             const int cp = a.uc_ptr[k], nC = a.uc_ptr[k + 1] - cp;
-            for (int p = lane; p < nC; p += G) rhs[a.uc_row[cp + p]] -= A[a.uc_pos[cp + p]] * xk;
+            for (int p = lane; p < nC; p += G) WA(rhs, a.uc_row[cp + p]) -= WA(A, a.uc_pos[cp + p]) * xk;
             __syncwarp(gmask);
         }
         nnewton++;
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
         double dvmax = 0.0;
         int finite = 1;
         for (int i = lane; i < N; i += G) {
-            const double dx = rhs[a.col_to_step[i]];
+            const double dx = WA(rhs, a.col_to_step[i]);
             if (!isfinite(dx)) finite = 0;
             if (i < NV) dvmax = fmax(dvmax, fabs(dx));
         }
@@ -295,12 +302,14 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
             newton_fail = true;
             status = 4;
         } else {
-            const double sc = dvmax > o.dv_max ? o.dv_max / dvmax : 1.0;
+            if (it == 0) lim = o.dv_max;   // limit doubles while it keeps binding (mirrors the oracle)
+            const double sc = dvmax > lim ? lim / dvmax : 1.0;
+            lim = sc < 1.0 ? 2.0 * lim : o.dv_max;
             const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
             int conv = (sc == 1.0) && (rmax <= restol);
             for (int i = lane; i < N; i += G) {
-                const double dx = sc * rhs[a.col_to_step[i]];
-                const double xo = xs[i], xn = xo + dx;
+                const double dx = sc * WA(rhs, a.col_to_step[i]);
+                const double xo = WA(xs, i), xn = xo + dx;
                 const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
                 if (fabs(dx) > o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol) conv = 0;
                 AT(a.X, i) = xn;
@@ -388,12 +397,12 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
             if (!reject) {
                 nacc++;
                 for (int i = lane; i < N; i += G) {
-                    AT(a.QD, i) = alpha * qk[i] + AT(a.BETA, i);
+                    AT(a.QD, i) = alpha * WA(qk, i) + AT(a.BETA, i);
                     AT(a.X2, i) = AT(a.X1, i);
                     AT(a.X1, i) = AT(a.XN, i);
                     AT(a.XN, i) = AT(a.X, i);
                     AT(a.Q1, i) = AT(a.QN, i);
-                    AT(a.QN, i) = qk[i];
+                    AT(a.QN, i) = WA(qk, i);
                 }
                 __syncwarp(gmask);  // history rows are read across lanes by the output sampling
                 h2 = h1; h1 = h;
@@ -489,13 +498,14 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
         IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
         IST(IS_RETRY) = retry;
         DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
-        DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt;
+        DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim;
         a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
         a.active[inst] = phase != PH_DONE;
     }
 #undef IST
 #undef DST
 #undef AT
+#undef WA
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------
@@ -535,6 +545,18 @@ __global__ void k_lin_setup(long long Bl, long long B, int nlin, int ncontrib, c
         if (k.is_c) lin_c[(size_t)k.entry * Bl + inst] += v;
         else lin_g[(size_t)k.entry * Bl + inst] += v;
     }
+}
+
+// FP64 FMA throughput microbenchmark (roofline denominator of the device-evaluation kernels;
+// MEASURED_PEAKS.json carries no FP64 figure): 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double b, double c) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 __global__ void k_gather_rows(long long B, int n, const int* idx, const double* src, double* dst) {

@@ -56,8 +56,21 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
         (void)gmin_; (void)temp_c_; (void)par_val_; (void)par_col_; (void)given_;
 #define VA_SETUP_END(NAME) }
 
+#ifndef VA_EVAL_THREADS
+#define VA_EVAL_THREADS 128
+#endif
+#ifndef VA_EVAL_MINBLOCKS
+#define VA_EVAL_MINBLOCKS 1
+#endif
+#ifdef VA_PREFETCH_L2
+#define VA_PREFETCH_ALL()                                                                        \
+    for (int s_ = 0; s_ < NCACHE; s_++)                                                          \
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cache_ + (size_t)s_ * a.B));
+#else
+#define VA_PREFETCH_ALL()
+#endif
 #define VA_EVAL_BEGIN(NAME)                                                                      \
-    extern "C" __global__ void __launch_bounds__(128) k_eval_##NAME(VaArgs a) {                  \
+    extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, VA_EVAL_MINBLOCKS) k_eval_##NAME(VaArgs a) {      \
         const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;                 \
         if (inst >= a.B) return;                                                                 \
         if (!a.active[inst]) return;                                                             \
@@ -69,6 +82,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
         _Pragma("unroll") for (int k_ = 0; k_ < NT; k_++) {                                      \
             const int n_ = a.term[dev * NT + k_];                                                \
             vt_[k_] = n_ < 0 ? 0.0 : a.x[(size_t)n_ * a.B + inst];                               \
-        }
+        }                                                                                        \
+        VA_PREFETCH_ALL()
 #define VA_EVAL_END(NAME) }
 )CUDA";

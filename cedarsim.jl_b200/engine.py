@@ -23,7 +23,7 @@ _lib = None
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_options_default", "cb_circuit_create", "cb_circuit_set_cuda_source",
     "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_set_params", "cb_dc", "cb_tran",
-    "cb_plan_device_params", "cb_plan_set_x0", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
+    "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
 ]
 
 
@@ -81,6 +81,13 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def measure_fp64_peak(device: int = 0) -> float:
+    """FP64 FMA TFLOP/s of `device` (DFMA microbenchmark in the engine library)."""
+    tf = C.c_double(0.0)
+    _check(load().cb_measure_fp64_peak(C.c_int(device), C.byref(tf)))
+    return tf.value
+
+
 class Circuit:
     """A compiled circuit: flat description + generated device code + symbolic LU."""
 
@@ -136,6 +143,9 @@ class Plan:
             raise ValueError(f"params must have shape ({P}, {self.B}), got {params.shape}")
         self._params = params
         _check(self.lib.cb_plan_set_params(self.handle, _dp(params)))
+
+    def set_timing(self, enable: bool):
+        _check(self.lib.cb_plan_set_timing(self.handle, C.c_int(1 if enable else 0)))
 
     def set_x0(self, x0: Optional[np.ndarray]):
         """DC initial guess: None, x0[N] shared by all points, or x0[N, B]."""

@@ -35,7 +35,8 @@ def parse_number(tok: str) -> float:
         return float(f"{mant}e{exp}") * 25.4e-6
     if rest.startswith("meg"):
         exp += 6
-    elif rest and rest[0] in _SUFFIX_EXP:
+    elif rest and rest[0] in _SUFFIX_EXP and not rest.startswith("am"):
+        # `1Amp` is one ampere, not one atto-"mp" (SPICE lexer.jl:377-395 excludes ('A','M'))
         exp += _SUFFIX_EXP[rest[0]]
     return float(f"{mant}e{exp}")
 

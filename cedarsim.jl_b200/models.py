@@ -37,7 +37,18 @@ def load_model(path: str) -> CompiledModel:
         return CompiledModel(**json.load(f))
 
 
-def compiled_model(name: str, va_path: Optional[str] = None, rebuild: bool = False, **kw) -> CompiledModel:
+def _count_executed_ops(cm: CompiledModel, probe) -> list:
+    """FP64 operation count of one evaluation on the path executed at a representative bias (the
+    algorithmic flops per device evaluation used by bench.py's roofline).  exp/log/sqrt/pow/div
+    count 1 each, so fractions of peak derived from it are conservative."""
+    import numpy as np
+    from .va.build import build_host
+    hm = build_host(cm, count_ops=True)
+    cache = hm.run_setup(probe["params"])
+    return list(hm.executed_ops(cache, np.asarray(probe["v"], dtype=float)))
+
+
+def compiled_model(name: str, va_path: Optional[str] = None, rebuild: bool = False, probe=None, **kw) -> CompiledModel:
     """Compiled model by name, from the _gen cache or by compiling `va_path`."""
     if name in _cache and not rebuild:
         return _cache[name]
@@ -48,6 +59,8 @@ def compiled_model(name: str, va_path: Optional[str] = None, rebuild: bool = Fal
         if va_path is None or not os.path.exists(va_path):
             raise FileNotFoundError(f"no cached model {path} and no Verilog-A source {va_path!r}; run build() where the source exists")
         cm = compile_va_file(va_path, name=name, **kw)
+        if probe is not None:
+            cm.exec_ops = _count_executed_ops(cm, probe)
         save_model(cm, path)
     _cache[name] = cm
     return cm
@@ -65,8 +78,38 @@ def bsimcmg107_card(card: str, runtime=("L", "NFIN"), rebuild: bool = False) -> 
     instance parameters are read per device / per sweep point."""
     params = asap7_cards()[card].params
     name = f"bsimcmg107_{card}"
-    return compiled_model(name, BSIMCMG_VA, rebuild, suppress_defines=["__OPINFO__"], const_params=params,
+    vdd = 0.7 if params.get("DEVTYPE", 1.0) else -0.7
+    probe = {"params": {"L": 21e-9, "NFIN": 3.0}, "v": [0.5 * vdd, 0.5 * vdd, 0.0, 0.0, 0.5 * vdd, 0.0]}
+    return compiled_model(name, BSIMCMG_VA, rebuild, probe=probe, suppress_defines=["__OPINFO__"], const_params=params,
                           runtime_params=list(runtime))
+
+
+def specialized_model(card: ModelCard, runtime=("L", "NFIN"), rebuild: bool = False) -> CompiledModel:
+    """BSIM-CMG 107 specialised on an arbitrary model card (netlist `.model` or included card file)."""
+    import hashlib
+    if not card.master.startswith("bsimcmg"):
+        raise ValueError(f"no Verilog-A source for device family {card.master!r}")
+    runtime = tuple(sorted(k.upper() for k in runtime))
+    const = {k: v for k, v in card.params.items() if k.upper() not in runtime}
+    key = hashlib.sha1(repr((sorted(const.items()), runtime)).encode()).hexdigest()[:10]
+    try:
+        ref = asap7_cards().get(card.name)
+    except FileNotFoundError:
+        ref = None
+    if ref is not None and ref.params == card.params and runtime == ("L", "NFIN"):
+        return bsimcmg107_card(card.name, rebuild=rebuild)
+    vdd = 0.7 if const.get("DEVTYPE", 1.0) else -0.7
+    probe = {"params": {k: (21e-9 if k == "L" else 3.0 if k == "NFIN" else card.params.get(k, 0.0)) for k in runtime},
+             "v": [0.5 * vdd, 0.5 * vdd, 0.0, 0.0, 0.5 * vdd, 0.0]}
+    return compiled_model(f"bsimcmg107_{card.name}_{key}", BSIMCMG_VA, rebuild, probe=probe, suppress_defines=["__OPINFO__"],
+                          const_params=const, runtime_params=list(runtime))
+
+
+def param_default(cm: CompiledModel, name: str) -> float:
+    for k, v in cm.param_defaults.items():
+        if k.upper() == name.upper():
+            return v
+    raise KeyError(f"parameter {name} of {cm.name} has no constant default")
 
 
 def asap7_cards(rebuild: bool = False) -> Dict[str, ModelCard]:

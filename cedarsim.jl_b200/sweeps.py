@@ -1,0 +1,514 @@
+"""Sweep API: mirror of reference src/sweeps.jl, with the batched engine behind `dc_` / `tran_`.
+
+    Sweep / ProductSweep / TandemSweep / SerialSweep / sweepify / split_axes / sweepvars /
+    find_param_ranges                        src/sweeps.jl:52-60, 98-146, 175-354, 507-546
+    CircuitSweep                             src/sweeps.jl:390-435
+    dc_(cs)   == dc!(cs::CircuitSweep)       src/sweeps.jl:437-448, 471-486
+    tran_(cs) == tran!(cs::CircuitSweep, tspan)  src/sweeps.jl:450-463, 488-502 (with the defects
+                                             listed in SURVEY.md 3.2 fixed: tspan is an argument)
+
+Iteration order and shapes are the reference's: a point is a tuple of (name, value) pairs sorted by
+name; a product varies its FIRST axis fastest and `size(cs)` is the tuple of axis lengths (Julia
+column-major), tandem zips, serial concatenates with None ("keep default") for inactive names.
+
+Instead of the reference's serial `broadcast` over points (src/sweeps.jl:473,490) the whole sweep
+is flattened once into per-point parameter columns and solved in one batched call on the GPU(s).
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Set, Tuple, Union
+
+import numpy as np
+
+from . import engine
+from .flat import FlatCircuit, RETCODES
+from .netlist import Flattened, Netlist, flatten
+
+Point = Tuple[Tuple[str, object], ...]
+
+
+def _expand(items) -> Point:
+    """flatten nested point tuples and sort by name (src/sweeps.jl:131-137)"""
+    out: List[Tuple[str, object]] = []
+
+    def rec(x):
+        if isinstance(x, tuple) and len(x) == 2 and isinstance(x[0], str):
+            out.append(x)
+        else:
+            for y in x:
+                rec(y)
+
+    rec(items)
+    return tuple(sorted(out, key=lambda kv: kv[0]))
+
+
+class SweepBase:
+    shape: Tuple[int, ...] = ()
+
+    def __len__(self) -> int:
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    def size(self, d: Optional[int] = None):
+        """size(s) / size(s, d) with Julia's 1-based d; missing dimensions are 1"""
+        if d is None:
+            return self.shape
+        return self.shape[d - 1] if 1 <= d <= len(self.shape) else 1
+
+    def sweepvars(self) -> Set[str]:
+        raise NotImplementedError
+
+    def __iter__(self) -> Iterator[Point]:
+        raise NotImplementedError
+
+    def first(self) -> Point:
+        for p in self:
+            return p
+        return ()
+
+    def columns(self) -> Dict[str, np.ndarray]:
+        """{name: float array over all points in iteration order}; None -> NaN"""
+        names = sorted(self.sweepvars())
+        cols = {n: np.full(len(self), np.nan) for n in names}
+        for i, pt in enumerate(self):
+            for k, v in pt:
+                if v is not None:
+                    cols[k][i] = float(v)
+        return cols
+
+    def children(self) -> Sequence["SweepBase"]:
+        return ()
+
+
+class Sweep(SweepBase):
+    """Sweep("R1", values) / Sweep(R1=values); a scalar becomes a one-point sweep."""
+
+    def __init__(self, selector=None, values=None, **kw):
+        if isinstance(selector, SweepBase):
+            raise TypeError("use sweepify() to pass sweeps through")
+        if selector is None:
+            if len(kw) != 1:
+                raise ValueError("`Sweep` takes a single variable at a time!")
+            (selector, values), = kw.items()
+        elif isinstance(selector, tuple) and values is None:
+            selector, values = selector
+        self.selector = str(selector)
+        if np.isscalar(values):
+            values = [values]
+        self.values = list(values)
+        self.shape = (len(self.values),)
+
+    def __eq__(self, other):
+        return isinstance(other, Sweep) and self.selector == other.selector and self.values == other.values
+
+    def __hash__(self):
+        return hash((self.selector, tuple(self.values)))
+
+    def __iter__(self):
+        for v in self.values:
+            yield ((self.selector, v),)
+
+    def sweepvars(self):
+        return {self.selector}
+
+    def __repr__(self):
+        if len(self.values) > 1:
+            return f"Sweep of {self.selector} with {len(self.values)} values over [{min(self.values)} .. {max(self.values)}]"
+        return f"Sweep of {self.selector} set to {self.values[0]}"
+
+
+def _as_sweeps(args, kwargs) -> List[SweepBase]:
+    out: List[SweepBase] = []
+    for a in args:
+        out.append(a if isinstance(a, SweepBase) else Sweep(a) if not isinstance(a, dict) else None)
+        if out[-1] is None:
+            out.pop()
+            out.extend(Sweep(k, v) for k, v in a.items())
+    out.extend(Sweep(k, v) for k, v in kwargs.items())
+    return out
+
+
+class _Product(SweepBase):
+    def __init__(self, its: List[SweepBase]):
+        self.iterators = its
+        self.shape = tuple(itertools.chain.from_iterable(it.shape for it in its))
+
+    def __iter__(self):
+        if not self.iterators:
+            yield ()
+            return
+        lists = [list(it) for it in self.iterators]
+        # first iterator varies fastest (Base.Iterators.product)
+        for combo in itertools.product(*reversed(lists)):
+            yield _expand(tuple(reversed(combo)))
+
+    def __len__(self):
+        n = 1
+        for it in self.iterators:
+            n *= len(it)
+        return n
+
+    def sweepvars(self):
+        return set().union(*[it.sweepvars() for it in self.iterators]) if self.iterators else set()
+
+    def children(self):
+        return self.iterators
+
+
+class _Tandem(SweepBase):
+    def __init__(self, its: List[SweepBase]):
+        lens = [len(it) for it in its]
+        if any(n != lens[0] for n in lens):
+            raise ValueError("TandemSweep requires all sweeps be of the same length!")
+        self.iterators = its
+        self.shape = (lens[0],) if lens else ()
+
+    def __iter__(self):
+        for combo in zip(*self.iterators):
+            yield _expand(combo)
+
+    def sweepvars(self):
+        return set().union(*[it.sweepvars() for it in self.iterators])
+
+    def children(self):
+        return self.iterators
+
+
+class _Serial(SweepBase):
+    def __init__(self, its: List[SweepBase]):
+        self.iterators = its
+        self.vars = set().union(*[it.sweepvars() for it in its]) if its else set()
+        self.shape = (sum(len(it) for it in its),)
+
+    def __iter__(self):
+        for it in self.iterators:
+            for pt in it:
+                m = {v: None for v in self.vars}
+                m.update(dict(_expand(pt)))
+                yield tuple(sorted(m.items()))
+
+    def sweepvars(self):
+        return set(self.vars)
+
+    def children(self):
+        return self.iterators
+
+
+def ProductSweep(*args, **kwargs) -> SweepBase:
+    its = _as_sweeps(args, kwargs)
+    if len(its) == 1:
+        return its[0]
+    return _Product(its)
+
+
+def TandemSweep(*args, **kwargs) -> SweepBase:
+    its = _as_sweeps(args, kwargs)
+    if len(its) == 1:
+        return its[0]
+    return _Tandem(its)
+
+
+def SerialSweep(*args, **kwargs) -> SweepBase:
+    its = _as_sweeps(args, kwargs)
+    if len(its) == 1:
+        return its[0]
+    return _Serial(its)
+
+
+def sweepvars(*sweeps) -> Set[str]:
+    out: Set[str] = set()
+    for s in sweeps:
+        out |= s.sweepvars()
+    return out
+
+
+def sweepify(x) -> SweepBase:
+    """lists -> SerialSweep, dicts -> ProductSweep, (name, values) -> Sweep (src/sweeps.jl:349-354)"""
+    if isinstance(x, SweepBase):
+        return x
+    if isinstance(x, dict):
+        return ProductSweep(**x)
+    if isinstance(x, tuple) and len(x) == 2 and isinstance(x[0], str):
+        return Sweep(x[0], x[1])
+    if isinstance(x, (list, tuple)):
+        return SerialSweep(*[sweepify(y) for y in x])
+    raise TypeError(f"cannot turn {x!r} into a sweep")
+
+
+def split_axes(sweep: SweepBase, axes: Iterable[str]):
+    """split a ProductSweep into (outer, inner) products; inner holds `axes` (src/sweeps.jl:98-129)"""
+    if not isinstance(sweep, _Product):
+        raise ValueError("split_axes only works with ProductSweep objects!")
+    axes = list(axes)
+    idx = []
+    for ax in axes:
+        found = [i for i, it in enumerate(sweep.iterators) if isinstance(it, Sweep) and it.selector == ax]
+        if not found:
+            raise ValueError(f"Unable to find product axis matching '{ax}'")
+        idx.append(found[0])
+    inner = _Product([sweep.iterators[i] for i in idx])
+    outer = _Product([it for i, it in enumerate(sweep.iterators) if i not in idx])
+    return outer, inner
+
+
+def find_param_ranges(sweep: SweepBase) -> Dict[str, Tuple[float, float, int]]:
+    """(min, max, number of values) explored along each name (src/sweeps.jl:507-546)"""
+    acc: Dict[str, List[Tuple[float, float, int]]] = {}
+
+    def rec(it):
+        if isinstance(it, Sweep):
+            acc.setdefault(it.selector, []).append((min(it.values), max(it.values), len(it.values)))
+        else:
+            for c in it.children():
+                rec(c)
+
+    rec(sweep)
+    out = {}
+    for name, ranges in acc.items():
+        lo, hi, n = ranges[0]
+        for a, b, m in ranges[1:]:
+            lo, hi, n = min(lo, a), max(hi, b), n + m
+        out[name] = (lo, hi, n)
+    return out
+
+
+# ---------------------------------------------------------------- circuit sweep + solutions
+
+
+class ScopeRef:
+    """cs.sys.node_q / cs.sys.v1.I / cs.sys.x1.r1.I -- names results as the reference does
+    (src/simulate_ir.jl:79-91, src/spectre.jl:736-749, test/sweep.jl:336-339,363-369)."""
+
+    def __init__(self, path: str = ""):
+        object.__setattr__(self, "_path", path)
+
+    def __getattr__(self, name: str):
+        return ScopeRef(f"{self._path}.{name}" if self._path else name)
+
+    def __getitem__(self, name: str):
+        return getattr(self, name)
+
+    def __repr__(self):
+        return f"sys.{self._path}"
+
+
+def _resolve(fc: FlatCircuit, ref: Union[str, ScopeRef]) -> int:
+    key = ref._path if isinstance(ref, ScopeRef) else str(ref)
+    key = key.lower()
+    if key.endswith(".i") or key.endswith(".v"):
+        pass
+    return fc.unknown(key)
+
+
+class PointSolution:
+    """One element of the result array of dc_ / tran_."""
+
+    def __init__(self, parent: "SweepSolution", index: int):
+        self._p, self._i = parent, index
+
+    @property
+    def retcode(self) -> str:
+        return RETCODES[int(self._p.status[self._i])]
+
+    @property
+    def params(self) -> Dict[str, float]:
+        return self._p.point_params(self._i)
+
+    @property
+    def t(self) -> np.ndarray:
+        return self._p.t
+
+    def __getitem__(self, ref):
+        u = _resolve(self._p.fc, ref)
+        o = self._p.out_index[u]
+        if self._p.t is None:
+            return float(self._p.y[o, self._i])
+        return self._p.y[o, :, self._i]
+
+    def __call__(self, t, idxs=None):
+        """sol(t; idxs=sys.node_q): linear interpolation of the saved waveform"""
+        if self._p.t is None:
+            raise TypeError("DC solutions are not functions of time")
+        refs = idxs if isinstance(idxs, (list, tuple)) else [idxs]
+        vals = [np.interp(t, self._p.t, self[r]) for r in refs]
+        return vals if isinstance(idxs, (list, tuple)) else vals[0]
+
+
+class SweepSolution:
+    """Array of per-point solutions with `size(cs)` (column-major like the Julia result)."""
+
+    def __init__(self, cs: "CircuitSweep", y: np.ndarray, status: np.ndarray, stats: dict, t: Optional[np.ndarray]):
+        self.cs, self.fc, self.y, self.status, self.stats, self.t = cs, cs.flat.fc, y, status, stats, t
+        self.shape = cs.shape
+        self.out_index = {u: k for k, u in enumerate(self.fc.outputs)}
+
+    def __len__(self):
+        return len(self.status)
+
+    def point_params(self, i: int) -> Dict[str, float]:
+        return {k: (None if np.isnan(v[i]) else float(v[i])) for k, v in self.cs.columns.items()}
+
+    def _linear(self, idx) -> int:
+        if isinstance(idx, (int, np.integer)):
+            return int(idx)
+        return int(np.ravel_multi_index(tuple(idx), self.shape, order="F"))
+
+    def __getitem__(self, idx) -> PointSolution:
+        return PointSolution(self, self._linear(idx))
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield PointSolution(self, i)
+
+    def array(self, ref) -> np.ndarray:
+        """values of one unknown over the whole sweep, shaped size(cs) (+ time axis last for tran)"""
+        o = self.out_index[_resolve(self.fc, ref)]
+        if self.t is None:
+            return self.y[o].reshape(self.shape, order="F")
+        return np.moveaxis(self.y[o], 0, -1).reshape(self.shape + (len(self.t),), order="F")
+
+    @property
+    def retcodes(self) -> np.ndarray:
+        return self.status.reshape(self.shape, order="F")
+
+
+class CircuitSweep:
+    """CircuitSweep(circuit, sweep): compile once for the set of swept names, then solve all points
+    in one batched call.  `circuit` is a parsed `Netlist` (or SPICE text), or a callable
+    `builder(columns: dict, B: int) -> Flattened`."""
+
+    def __init__(self, circuit, iterator, outputs: Optional[Sequence[str]] = None, devices: Optional[Sequence[int]] = None,
+                 host: bool = False):
+        self.iterator = sweepify(iterator)
+        self.shape = self.iterator.shape
+        self.circuit = circuit
+        self.columns = self.iterator.columns()
+        B = len(self.iterator)
+        if isinstance(circuit, str):
+            from .netlist import parse_netlist
+            circuit = parse_netlist(circuit)
+        if isinstance(circuit, Netlist):
+            self.flat: Flattened = flatten(circuit, self.columns, B=B, outputs=outputs, host=host)
+        elif callable(circuit):
+            self.flat = circuit(self.columns, B)
+        else:
+            raise TypeError("circuit must be a Netlist, SPICE text or a builder callable")
+        self.sys = ScopeRef()
+        self.devices = list(devices) if devices is not None else [0]
+        self._compiled: Optional[engine.Circuit] = None
+        self._plans: List[Tuple[engine.Plan, slice]] = []
+        self.x0: Optional[np.ndarray] = None
+
+    def __len__(self):
+        return len(self.iterator)
+
+    def size(self, d: Optional[int] = None):
+        return self.iterator.size(d)
+
+    def sweepvars(self):
+        return self.iterator.sweepvars()
+
+    def __iter__(self):
+        """yields the parameter assignment of each point (the reference yields ParamSim objects)"""
+        return iter(self.iterator)
+
+    def nodeset(self, **node_voltages):
+        """initial guess for the DC Newton (warm start, cf. remake(prob, u0=...) src/sweeps.jl:474-477)"""
+        fc = self.flat.fc
+        x0 = np.zeros(fc.n_unknowns)
+        for k, v in node_voltages.items():
+            x0[fc.unknown(k)] = v
+        self.x0 = x0
+        return self
+
+    # ---- engine plumbing: contiguous block of points per GPU, one host thread per device
+    def _ensure_plans(self):
+        if self._plans:
+            return
+        self._compiled = engine.Circuit(self.flat.fc, self.flat.models)
+        B, G = len(self), len(self.devices)
+        per = -(-B // G)
+        for g, dev in enumerate(self.devices):
+            lo, hi = g * per, min(B, (g + 1) * per)
+            if lo >= hi:
+                continue
+            plan = self._compiled.plan(hi - lo, device=dev)
+            P = self.flat.params[:, lo:hi] if self.flat.params.size else None
+            plan.set_params(np.ascontiguousarray(P) if P is not None else None)
+            self._plans.append((plan, slice(lo, hi)))
+
+    def _options(self, kw):
+        opts = dict(kw)
+        for f_ in ("temp", "gmin"):
+            if f_ in self.flat.options and f_ not in opts:
+                opts[f_] = self.flat.options[f_]
+        if "abstol" in opts:      # reference kwargs (test/sweep.jl:333): abstol -> DC residual tolerance
+            opts["dc_abstol"] = min(opts.pop("abstol"), 1e-10)
+        return engine.default_options(**opts)
+
+    def _run(self, fn):
+        self._ensure_plans()
+        results = [None] * len(self._plans)
+        errors = []
+
+        def work(k, plan, sl):
+            try:
+                plan.set_x0(self.x0 if self.x0 is None or self.x0.ndim == 1 else self.x0[:, sl])
+                results[k] = fn(plan)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k, p, sl)) for k, (p, sl) in enumerate(self._plans)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+
+def dc_(cs: CircuitSweep, **kw) -> SweepSolution:
+    """dc!(cs): DC operating point of every sweep point."""
+    opts = cs._options(kw)
+    res = cs._run(lambda plan: plan.dc(opts, want_full=False))
+    y = np.concatenate([r[0] for r in res], axis=1)
+    status = np.concatenate([r[2] for r in res])
+    stats = _merge_stats([r[3] for r in res])
+    return SweepSolution(cs, y, status, stats, None)
+
+
+def tran_(cs: CircuitSweep, tspan: Optional[Tuple[float, float]] = None, saveat=None, **kw) -> SweepSolution:
+    """tran!(cs, tspan): transient of every sweep point from its DC operating point."""
+    if tspan is None:
+        if cs.flat.tran is None:
+            raise ValueError("no tspan given and the netlist has no .tran card")
+        tspan = (0.0, cs.flat.tran[1])
+    t0, t1 = tspan
+    if saveat is None:
+        step = cs.flat.tran[0] if cs.flat.tran else (t1 - t0) / 100.0
+        saveat = t0 + np.arange(int(round((t1 - t0) / step)) + 1) * step
+    elif np.isscalar(saveat):
+        saveat = t0 + np.arange(int(round((t1 - t0) / saveat)) + 1) * saveat
+    saveat = np.asarray(saveat, dtype=float)
+    opts = cs._options(kw)
+    res = cs._run(lambda plan: plan.tran(t0, t1, saveat, opts))
+    y = np.concatenate([r[0] for r in res], axis=2)
+    status = np.concatenate([r[1] for r in res])
+    return SweepSolution(cs, y, status, _merge_stats([r[2] for r in res]), saveat)
+
+
+def _merge_stats(stats: List[dict]) -> dict:
+    out = dict(stats[0])
+    for s in stats[1:]:
+        for k, v in s.items():
+            out[k] = max(out[k], v) if k.endswith("seconds") else out[k] + v
+    return out
+
+
+dc = dc_
+tran = tran_

@@ -97,7 +97,7 @@ class HostModel:
         return I, Q, G, Cm
 
 
-def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O1", count_ops: bool = False) -> HostModel:
+def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2", count_ops: bool = False) -> HostModel:
     out_dir = out_dir or GEN_DIR
     os.makedirs(out_dir, exist_ok=True)
     text = c_prelude(len(cm.terminals), count_ops) + cm.source

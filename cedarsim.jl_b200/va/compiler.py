@@ -355,6 +355,8 @@ class CompiledModel:
     n_eval_lines: int = 0
     n_setup_lines: int = 0
     census: Dict[str, int] = field(default_factory=dict)  # static op counts of the eval function
+    exec_ops: List[int] = field(default_factory=list)     # (add, mul, div, special) on the executed path, see models.py
+    param_defaults: Dict[str, float] = field(default_factory=dict)  # constant defaults of the module's parameters
 
     @property
     def key(self) -> str:
@@ -1335,6 +1337,8 @@ class _Compiler:
             deps = frozenset((a.deps if a.dyn else frozenset()) | (b.deps if b.dyn else frozenset()))
             if name in self.forced_all:
                 deps = frozenset(range(len(self.terms)))
+            if self.types[name] != "r":
+                deps = frozenset()   # integer variables carry no derivatives
             for br, E_, S_ in ((a, Ea, Sa), (b, Eb, Sb)):
                 if br.dyn:
                     for kk in sorted(deps - br.deps):
@@ -1538,8 +1542,19 @@ class _Compiler:
                 jcol.append(ll)
         src = self._render(out_lines)
         ptypes = [p.type for p in mod.params]
+        defaults: Dict[str, float] = {}
+        ce = _ConstEval(mod.functions)
+        for p in mod.params:
+            if p.type == "string":
+                continue
+            try:
+                v = ce.expr(p.default, defaults)
+                defaults[p.name] = float(v)
+            except (_NotConst, TypeError, ValueError):
+                pass
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
-                             ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census))
+                             ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
+                             param_defaults=defaults)
 
     def _c_function(self, f: Function) -> str:
         """value-only C translation of an analog function (used by the setup stream)"""

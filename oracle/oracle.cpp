@@ -323,6 +323,7 @@ struct Solver {
     // Returns 0 ok, 1 max iterations, 4 singular / non-finite.
     int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
                double gshunt, int maxit, double restol, std::vector<double>& qk) {
+        double lim = opt->dv_max;  // voltage-step limit; doubles while it keeps binding (trust-region growth)
         for (int it = 0; it < maxit; it++) {
             eval_system(in, vc, x.data(), t, dcop, s);
             cnt.newton++;
@@ -344,7 +345,8 @@ struct Solver {
                 if (i < NV) dvmax = std::max(dvmax, std::fabs(rhs[i]));
             }
             if (!finite) return 4;
-            double sc = dvmax > opt->dv_max ? opt->dv_max / dvmax : 1.0;
+            double sc = dvmax > lim ? lim / dvmax : 1.0;
+            lim = sc < 1.0 ? 2.0 * lim : opt->dv_max;
             bool conv = (sc == 1.0) && (rmax <= restol);
             for (int i = 0; i < N; i++) {
                 double dx = sc * rhs[i];

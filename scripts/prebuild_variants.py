@@ -1,0 +1,9 @@
+# pre-compile NVRTC variants here (no GPU needed) so the GPU box only loads cubins
+import os, sys, subprocess
+variants = [dict(), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=3"), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=4"),
+            dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=6"), dict(CB_NVRTC_DEFS="-DVA_EVAL_THREADS=64 -DVA_EVAL_MINBLOCKS=6")]
+procs = []
+for v in variants:
+    env = dict(os.environ, **v)
+    procs.append(subprocess.Popen([sys.executable, "-c", "import sys; sys.path.insert(0,'.'); from cedarsim.jl_b200 import circuits, engine; fc, ms = circuits.dff(); engine.Circuit(fc, ms)"], env=env))
+for p in procs: p.wait()

@@ -1,0 +1,84 @@
+"""The reference-facing sweep API on the GPU: these read like the reference's own sweep tests
+(test/sweep.jl:326-371) with `dc_` / `tran_` in place of `dc!` / `tran!`."""
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import netlist
+from cedarsim.jl_b200.sweeps import CircuitSweep, ProductSweep, SerialSweep, Sweep, TandemSweep, dc_, tran_
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+DEFTOL = 1e-7
+
+TWO_R = "* two resistor\n.param R1=100 R2=100\nV vcc 0 1\nRa vcc out 'R1'\nRb out 0 'R2'\n"
+
+
+def test_dc_sweep_two_resistors():   # test/sweep.jl:326-340
+    cs = CircuitSweep(TWO_R, ProductSweep(R1=np.arange(100.0, 2001, 100), R2=np.arange(100.0, 2001, 100)))
+    sols = dc_(cs, abstol=DEFTOL, reltol=DEFTOL)
+    assert sols.shape == (20, 20) and len(sols) == 400
+    for sol, point in zip(sols, cs):
+        p = dict(point)
+        assert sol.retcode == "Success"
+        assert abs(-1 / (p["R1"] + p["R2"]) - sol[cs.sys.v.I]) < DEFTOL
+    # column-major result array like the Julia one: sols[i, j] <-> (R1[i], R2[j])
+    assert abs(sols[3, 7][cs.sys.v.I] + 1 / (400.0 + 800.0)) < DEFTOL
+    assert sols.array(cs.sys.node_out).shape == (20, 20)
+
+
+def test_dc_sweep_on_spice_subckt_param():   # test/sweep.jl:342-371
+    text = """* Parameter scoping test
+.subckt subcircuit1 vss gnd
+.param r_load=1
+r1 vss gnd 'r_load'
+.ends
+.param v_in=1
+x1 vss 0 subcircuit1
+v1 vss 0 'v_in'
+"""
+    cs = CircuitSweep(text, ProductSweep(**{"v_in": np.arange(1.0, 11), "x1.r_load": np.arange(1.0, 11)}))
+    sols = dc_(cs, abstol=DEFTOL, reltol=DEFTOL)
+    for sol in sols:
+        p = sol.params
+        assert abs(p["v_in"] / p["x1.r_load"] + sol[cs.sys.v1.I]) < DEFTOL
+
+
+def test_serial_and_tandem_sweeps_keep_defaults():
+    cs = CircuitSweep(TWO_R, SerialSweep(R1=[100.0, 300.0], R2=[700.0]))
+    sols = dc_(cs)
+    want = [-1 / 200.0, -1 / 400.0, -1 / 800.0]    # None -> the netlist default (100)
+    assert np.allclose([s[cs.sys.v.I] for s in sols], want, atol=1e-12)
+    cs = CircuitSweep(TWO_R, TandemSweep(R1=[100.0, 200.0], R2=[300.0, 400.0]))
+    assert np.allclose([s[cs.sys.v.I] for s in dc_(cs)], [-1 / 400.0, -1 / 600.0], atol=1e-12)
+
+
+def test_tran_sweep_rc_and_interpolation():
+    text = "* rc\n.param r=1k\nV1 in 0 PULSE(0 1 0 1n 1n 1 2)\nR1 in out 'r'\nC1 out 0 1n\n.tran 10n 5u\n"
+    cs = CircuitSweep(text, Sweep(r=[500.0, 1000.0, 2000.0]), outputs=["out"])
+    sols = tran_(cs, reltol=1e-5)
+    assert sols.shape == (3,) and len(sols.t) == 501
+    for sol, r in zip(sols, (500.0, 1000.0, 2000.0)):
+        assert sol.retcode == "Success"
+        tt = 2.0e-6
+        assert abs(sol(tt, idxs=cs.sys.node_out) - (1 - np.exp(-(tt - 0.5e-9) / (r * 1e-9)))) < 2e-3
+
+
+def test_bsimcmg_inverter_deck_tran(host_bsimcmg):   # test/bsimcmg/inverter.jl: retcode == Success
+    text = """** Test circuit
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+mneg Q D VSS VSS nmos_lvt
+mpos Q D VDD VDD pmos_lvt
+VVDD VDD 0 'vdd'
+VVSS VSS 0 0.0
+CQ D 0 1e-15
+VD D 0 AC 1 SIN (0.35 0.3 1e7)
+.param vdd=0.7
+.TRAN 1e-9 4.0e-7
+"""
+    cs = CircuitSweep(text, ProductSweep(**{"vdd": [0.6, 0.7, 0.8], "mneg.nfin": [1.0, 2.0, 3.0]}), outputs=["q", "d"], host=True)
+    sols = tran_(cs, reltol=1e-3)
+    assert sols.shape == (3, 3) and all(s.retcode == "Success" for s in sols)
+    y, st, _ = orc.tran(cs.flat.fc, 0.0, 4e-7, sols.t, params=cs.flat.params, opts=orc.default_options(reltol=1e-3))
+    assert st.max() == 0 and np.abs(sols.y - y).max() < 5e-3
+    q = sols.array(cs.sys.node_q)
+    assert q.shape == (3, 3, len(sols.t)) and q.min() < 0.1 and q.max() > 0.5   # the inverter switches rail to rail

@@ -1,0 +1,103 @@
+"""SPICE-subset reader / flattener semantics (reference src/spectre.jl, see netlist.py)."""
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import netlist
+from cedarsim.jl_b200.expr import evaluate, parse_expr, parse_number
+from cedarsim.jl_b200.flat import Col
+from cedarsim.jl_b200.sweeps import CircuitSweep, ProductSweep
+
+
+def test_numbers_and_magnitudes():   # test/basic.jl:609-638
+    assert parse_number("0.22u") == parse_number("0.22e-6") == 0.22e-6
+    assert parse_number("1MegQux") == 1e6 and parse_number("1Mil") == 25.4e-6 and parse_number("-1mAmp") == -1e-3
+    assert parse_number("1Amp") == 1.0 and parse_number("1.8_V") == 1.8 and parse_number("10k") == 1e4
+
+
+def test_expressions():   # functions int/nint/floor/ceil/pow/ln: test/basic.jl:651-684
+    env = {"a": 2.0}
+    assert evaluate(parse_expr("'a*3+pow(a,3)'"), env) == 14.0
+    assert evaluate(parse_expr("{int(2.7)+nint(2.5)+floor(-0.5)+ceil(0.2)}"), env) == 2 + 2 - 1 + 1
+    assert evaluate(parse_expr("a > 1 ? 10 : 20"), env) == 10
+    assert abs(evaluate(parse_expr("ln(exp(1.5))"), env) - 1.5) < 1e-15
+    v = evaluate(parse_expr("2*x"), {"x": np.array([1.0, 2.0])})
+    assert v.tolist() == [2.0, 4.0]
+
+
+def test_comments_continuations_case():
+    nl = netlist.parse_netlist("""title line is ignored
+* comment
+R1 A 0 1k $ trailing
+V1 a 0
++ DC 2 ; other trailing
+.END
+""")
+    fl = netlist.flatten(nl)
+    assert fl.fc.node_names == ["a"] and [d.name for d in fl.fc.devices] == ["r1", "v1"]
+    assert fl.fc.devices[0].value == 1000.0 and fl.fc.waves[0].dc == 2.0
+
+
+def test_param_scoping_and_sweep_columns():   # test/basic.jl:382-532 flavour; src/circuitodesystem.jl:66-97
+    text = """* scoping
+.param top=2 r_a='top*100'
+.subckt div a b rr=10
+r1 a m 'rr'
+r2 m b 'rr*top'
+.ends
+x1 in 0 div rr='r_a'
+x2 in 0 div
+v1 in 0 'top'
+"""
+    nl = netlist.parse_netlist(text)
+    fl = netlist.flatten(nl)
+    vals = {d.name: d.value for d in fl.fc.devices}
+    assert vals["x1.r1"] == 200.0 and vals["x1.r2"] == 400.0 and vals["x2.r1"] == 10.0 and vals["x2.r2"] == 20.0
+    # sweeping `top` turns exactly the dependent values into per-point columns
+    fl = netlist.flatten(nl, {"top": np.array([1.0, 2.0, 3.0])})
+    vals = {d.name: d.value for d in fl.fc.devices}
+    assert isinstance(vals["x1.r1"], Col) and isinstance(vals["x2.r2"], Col) and vals["x2.r1"] == 10.0
+    assert fl.params.shape[1] == 3
+    assert fl.params[vals["x1.r2"].index].tolist() == [100.0, 400.0, 900.0]
+    with pytest.raises(netlist.NetlistError):
+        netlist.flatten(nl, {"nosuch": np.array([1.0])})
+
+
+def test_sources():
+    nl = netlist.parse_netlist("""* sources
+V1 a 0 PWL(0 0 1n 1 2n 1)
+V2 b 0 DC 0.5 PULSE(0 1 1n 0.1n 0.1n 2n 5n)
+I3 c 0 SIN(0 1m 1meg)
+R1 a 0 1
+R2 b 0 1
+R3 c 0 1
+""")
+    fl = netlist.flatten(nl)
+    w = fl.fc.waves
+    assert w[0].kind == 1 and list(w[0].t) == [0.0, 1e-9, 2e-9] and w[0].dc is None
+    assert w[1].kind == 2 and w[1].dc == 0.5 and list(w[1].v)[:2] == [0.0, 1.0]
+    assert w[2].kind == 3 and list(w[2].v)[:3] == [0.0, 1e-3, 1e6]
+
+
+def test_circuit_sweep_shapes_without_gpu():   # test/sweep.jl:244-319 (construction only)
+    text = "* two r\nv1 vcc 0 1\nr1 vcc out 'r1v'\nr2 out 0 'r2v'\n.param r1v=100 r2v=100\n"
+    cs = CircuitSweep(text, ProductSweep(r1v=np.arange(100.0, 2001, 100), r2v=np.arange(100.0, 2001, 100)))
+    assert len(cs) == 400 and cs.size() == (20, 20) and cs.size(1) == 20 and cs.sweepvars() == {"r1v", "r2v"}
+    assert cs.flat.params.shape == (2, 400)
+    first = next(iter(cs))
+    assert first == (("r1v", 100.0), ("r2v", 100.0))
+
+
+def test_bsimcmg_deck(host_bsimcmg):   # test/bsimcmg/inverter_cmg_cedar.cir shape
+    nl = netlist.parse_netlist("""** Test circuit
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+mneg Q D VSS VSS nmos_lvt
+mpos Q D VDD VDD pmos_lvt nfin=2
+VVDD VDD 0 1.0
+VVSS VSS 0 0.0
+CQ D 0 1e-15
+VD D 0 AC 1 SIN (0.5 0.01 1e7)
+.TRAN 1e-9 4.0e-7
+""")
+    fl = netlist.flatten(nl, {"mneg.nfin": np.array([1.0, 2.0])})
+    assert fl.tran == (1e-9, 4e-7) and len(fl.fc.va_insts) == 2 and fl.fc.n_nodes == 8
+    assert "mneg.nfin" in fl.fc.param_names
