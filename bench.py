@@ -37,10 +37,8 @@ WORKLOAD = "dff30-bsimcmg107-asap7 monte-carlo transient, adaptive trap, reltol 
 
 
 def nodeset(fc):
-    x0 = np.zeros(fc.n_unknowns)
-    for n, v in DFF_NODESET.items():
-        x0[fc.unknown(n)] = v
-    return x0
+    from cedarsim.jl_b200.flat import nodeset_vector
+    return nodeset_vector(fc, DFF_NODESET)
 
 
 class ClockSampler(threading.Thread):

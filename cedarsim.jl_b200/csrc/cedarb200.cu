@@ -318,8 +318,154 @@ static int build_tables(cb_circuit* c) {
     return CB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Circuit-specialised straight-line kernel k_solve: residual + Jacobian assembly from the device
+// outputs, static-pivot sparse LU (right-looking, fused forward substitution) and backward
+// substitution, all on named scalars -- one thread per sweep point, every global access a
+// coalesced [k][B] row, no index loads, no barriers.  Generated from the symbolic analysis; linear
+// stamp values that are not swept are baked in as literals so that e.g. the +-1 incidence entries
+// of voltage sources fold away.
+static std::string dlit(double v) {
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.17g", v);
+    std::string s(buf);
+    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+    if (s.find("inf") != std::string::npos || s.find("nan") != std::string::npos) return "(0.0/0.0)";
+    return v < 0 ? "(" + s + ")" : s;
+}
+
+static void host_lin_values(const cb_circuit* c, std::vector<double>& g, std::vector<double>& cc) {
+    g.assign(std::max(1, c->nlin), 0.0);
+    cc.assign(std::max(1, c->nlin), 0.0);
+    for (const LinContrib& k : c->lin_contrib) {
+        double v = k.p.value;
+        if (k.recip) v = 1.0 / v;
+        v *= k.coef;
+        (k.is_c ? cc : g)[k.entry] += v;
+    }
+}
+
+static std::string gen_solve_source(const cb_circuit* c) {
+    const cb::Symbolic& S = c->sym;
+    const int N = c->N, NV = c->NV;
+    std::vector<double> lg, lc;
+    host_lin_values(c, lg, lc);
+    std::ostringstream o;
+    o << "\n// ---- generated: assembly + static-pivot LU + solve for this circuit (N=" << N << ", nnz(L+U)=" << S.nnz_lu << ")\n";
+    o << "struct SArgs { long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA;\n"
+         "  const double* dev_out; const double* lin_g; const double* lin_c; const double* WV; const int* active;\n"
+         "  double* DX; double* QK; double* RMAX; int* BAD; double* DVMAX; };\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(64, 1) k_solve(SArgs a) {\n";
+    o << "  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
+    o << "  if (inst >= a.B) return;\n  if (!a.active[inst]) return;\n";
+    o << "  const size_t B = (size_t)a.B;\n";
+    o << "  const double al = a.alpha[inst], gs = a.gshunt[inst];\n";
+    o << "  const double* __restrict__ od = a.dev_out + inst;\n";
+    o << "#define OD(s) __ldg(od + (size_t)(s) * B)\n";
+    for (int i = 0; i < N; i++) o << "  const double x" << i << " = a.X[" << i << " * B + inst];\n";
+    for (size_t w = 0; w < c->waves.size(); w++) o << "  const double w" << w << " = a.WV[" << w << " * B + inst];\n";
+    auto LG = [&](int l) { return c->lin_swept ? "lg" + std::to_string(l) : dlit(lg[l]); };
+    auto LC = [&](int l) { return c->lin_swept ? "lc" + std::to_string(l) : dlit(lc[l]); };
+    if (c->lin_swept)
+        for (int l = 0; l < c->nlin; l++)
+            o << "  const double lg" << l << " = a.lin_g[" << l << " * B + inst], lc" << l << " = a.lin_c[" << l << " * B + inst];\n";
+    // Row-by-row (up-looking) elimination: row i is assembled from the device outputs right before
+    // it is eliminated against the finished rows k < i, so only the U parts of finished rows stay
+    // live.  Every entry receives its updates in the same ascending-k order as the right-looking
+    // schedule of k_newton, so both kernels produce identical factors.
+    std::map<std::pair<int, int>, int> pos;   // (row step, col step) -> LU position
+    std::vector<std::vector<int>> row_cols(N);
+    for (int e = 0; e < S.nnz_lu; e++) { pos[{S.lu_i[e], S.lu_j[e]}] = e; row_cols[S.lu_i[e]].push_back(S.lu_j[e]); }
+    for (auto& rc : row_cols) std::sort(rc.begin(), rc.end());
+    auto entry_expr = [&](int e) {
+        std::ostringstream v;
+        bool h = false;
+        const int lin = c->a_lin[e];
+        if (lin >= 0) {
+            const bool g0 = !c->lin_swept && lg[lin] == 0.0, c0 = !c->lin_swept && lc[lin] == 0.0;
+            if (!g0) { v << LG(lin); h = true; }
+            if (!c0) { v << (h ? " + " : "") << "al * " << LC(lin); h = true; }
+        }
+        if (c->a_diag[e]) { v << (h ? " + " : "") << "gs"; h = true; }
+        for (int p = c->a_ptr[e]; p < c->a_ptr[e + 1]; p++) {
+            v << (h ? " + " : "");
+            if (c->a_mult[p] != 1.0) v << dlit(c->a_mult[p]) << " * ";
+            v << "OD(" << c->a_src[p] << ")";
+            h = true;
+        }
+        return h ? v.str() : std::string("0.0");
+    };
+    o << "  double rmax = 0.0;\n  int bad = 0;\n";
+    for (int si = 0; si < N; si++) {
+        const int i = S.prow[si];   // original row eliminated at step si
+        // residual of this row
+        std::ostringstream f, q;
+        bool hf = false, hq = false;
+        for (int p = c->rl_ptr[i]; p < c->rl_ptr[i + 1]; p++) {
+            const int l = c->rl_lin[p], col = c->rl_col[p];
+            if (c->lin_swept || lg[l] != 0.0) { f << (hf ? " + " : "") << LG(l) << " * x" << col; hf = true; }
+            if (c->lin_swept || lc[l] != 0.0) { q << (hq ? " + " : "") << LC(l) << " * x" << col; hq = true; }
+        }
+        for (int p = c->ri_ptr[i]; p < c->ri_ptr[i + 1]; p++) {
+            f << (hf ? " + " : "");
+            if (c->ri_mult[p] != 1.0) f << dlit(c->ri_mult[p]) << " * ";
+            f << "OD(" << c->ri_src[p] << ")";
+            hf = true;
+        }
+        for (int p = c->rq_ptr[i]; p < c->rq_ptr[i + 1]; p++) {
+            q << (hq ? " + " : "");
+            if (c->rq_mult[p] != 1.0) q << dlit(c->rq_mult[p]) << " * ";
+            q << "OD(" << c->rq_src[p] << ")";
+            hq = true;
+        }
+        for (int p = c->rs_ptr[i]; p < c->rs_ptr[i + 1]; p++) {
+            f << (hf ? " + " : "") << dlit(c->rs_coef[p]) << " * w" << c->rs_wave[p];
+            hf = true;
+        }
+        if (i < NV) { f << (hf ? " + " : "") << "gs * x" << i; hf = true; }
+        o << "  const double q" << i << " = " << (hq ? q.str() : "0.0") << ";\n";
+        o << "  a.QK[" << i << " * B + inst] = q" << i << ";\n";
+        o << "  const double r" << i << " = " << (hf ? f.str() : "0.0") << (hq ? " + al * q" + std::to_string(i) : "")
+          << " + a.BETA[" << i << " * B + inst];\n";
+        o << "  rmax = fmax(rmax, fabs(r" << i << "));\n";
+        o << "  double b" << si << " = -r" << i << ";\n";
+        // entries of this row
+        for (int j : row_cols[si]) o << "  double e" << pos[{si, j}] << " = " << entry_expr(pos[{si, j}]) << ";\n";
+        // eliminate against finished rows
+        for (int k : row_cols[si]) {
+            if (k >= si) break;
+            o << "  { const double l = e" << pos[{si, k}] << " * inv" << k << ";";
+            const int up = S.u_ptr[k], nU = S.u_ptr[k + 1] - up;
+            for (int uj = 0; uj < nU; uj++) o << " e" << pos[{si, S.u_col[up + uj]}] << " -= l * e" << S.u_pos[up + uj] << ";";
+            o << " b" << si << " -= l * b" << k << "; }\n";
+        }
+        const int d = S.diag_pos[si];
+        o << "  bad |= !(fabs(e" << d << ") > 0.0);\n";
+        o << "  const double inv" << si << " = 1.0 / e" << d << ";\n";
+    }
+    o << "  a.RMAX[inst] = rmax;\n  double dvm = 0.0;\n";
+    // ---- backward substitution (row oriented)
+    for (int k = N - 1; k >= 0; k--) {
+        o << "  const double s" << k << " = (b" << k;
+        const int up = S.u_ptr[k], nU = S.u_ptr[k + 1] - up;
+        for (int uj = 0; uj < nU; uj++) o << " - e" << S.u_pos[up + uj] << " * s" << S.u_col[up + uj];
+        o << ") * inv" << k << ";\n";
+        o << "  a.DX[" << S.pcol[k] << " * B + inst] = s" << k << ";\n";
+        if (S.pcol[k] < NV) o << "  dvm = fmax(dvm, fabs(s" << k << "));\n";
+        o << "  bad |= !isfinite(s" << k << ");\n";
+    }
+    o << "  a.DVMAX[inst] = dvm;\n";
+    o << "  a.BAD[inst] = bad;\n#undef OD\n}\n";
+    return o.str();
+}
+
 static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
-    std::string full = std::string(CB_VA_PRELUDE) + "\n" + c->cuda_source;
+    std::string full = std::string(CB_VA_PRELUDE) + "\n" + c->cuda_source + gen_solve_source(c);
+    if (const char* dump = std::getenv("CB_DUMP_SRC")) {
+        std::ofstream df(dump);
+        df << full;
+    }
     // experiment knobs (they change the cache key): CB_MAXREG=<n>, CB_NVRTC_DEFS="-DX=1 -DY"
     std::string maxreg = std::getenv("CB_MAXREG") ? std::string("--maxrregcount=") + std::getenv("CB_MAXREG") : "";
     std::vector<std::string> extra;
@@ -383,11 +529,10 @@ extern "C" int cb_circuit_compile(cb_circuit* c, const char* cache_dir, double* 
     c->lin_swept = false;
     int rc = build_tables(c);
     if (rc != CB_OK) return rc;
-    if (!c->models.empty()) {
-        if (c->cuda_source.empty()) return fail(CB_ERR_STATE, "circuit has Verilog-A devices but no CUDA source was set");
-        rc = nvrtc_compile(c, cache_dir);
-        if (rc != CB_OK) return rc;
-    }
+    if (!c->models.empty() && c->cuda_source.empty())
+        return fail(CB_ERR_STATE, "circuit has Verilog-A devices but no CUDA source was set");
+    rc = nvrtc_compile(c, cache_dir);
+    if (rc != CB_OK) return rc;
     c->compiled = true;
     if (compile_seconds)
         *compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -415,6 +560,10 @@ struct cb_plan {
     cudaStream_t stream = nullptr;
     cudaLibrary_t lib = nullptr;
     std::vector<cudaKernel_t> k_setup, k_eval;
+    cudaKernel_t k_solve = nullptr;
+    bool gen = true;         // generated straight-line k_solve + k_control (default)
+    double *d_DX = nullptr, *d_QK = nullptr, *d_RMAX = nullptr, *d_WV = nullptr, *d_DVMAX = nullptr;
+    int* d_BAD = nullptr;
     std::vector<void*> allocs;
     NArgs na{};
     int G = 8, gpc = 1;
@@ -494,8 +643,9 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
     CUDA_TRY(cudaEventCreate(&p->ev1));
     int rc;
 #define TRY(x) do { rc = (x); if (rc != CB_OK) return rc; } while (0)
-    if (!c->models.empty()) {
+    {
         CUDA_TRY(cudaLibraryLoadData(&p->lib, c->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        CUDA_TRY(cudaLibraryGetKernel(&p->k_solve, p->lib, "k_solve"));
         for (const ModelH& m : c->models) {
             cudaKernel_t ks, ke;
             CUDA_TRY(cudaLibraryGetKernel(&ks, p->lib, ("k_setup_" + m.name).c_str()));
@@ -603,9 +753,19 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
     const int per_raw = S.nnz_lu + 3 * N + a.nwaves;
     {
         const char* env = std::getenv("CB_NEWTON");
-        p->glob = env ? std::string(env) == "glob" : (B >= 4096);
+        p->gen = !env || std::string(env) == "gen";
+        p->glob = env && std::string(env) == "glob";
     }
-    if (p->glob) {
+    if (p->gen) {
+        TRY(p->alloc(&p->d_DX, (size_t)N * B));
+        TRY(p->alloc(&p->d_QK, (size_t)N * B));
+        TRY(p->alloc(&p->d_RMAX, (size_t)B));
+        TRY(p->alloc(&p->d_DVMAX, (size_t)B));
+        TRY(p->alloc(&p->d_BAD, (size_t)B));
+        TRY(p->alloc(&p->d_WV, (size_t)std::max(1, a.nwaves) * B));
+        a.scratch = nullptr;
+        a.sm_stride = per_raw;
+    } else if (p->glob) {
         p->G = 1; p->gpc = 64; p->smem_bytes = 0;
         a.sm_stride = per_raw;
         TRY(p->alloc(&a.scratch, (size_t)per_raw * B));
@@ -759,7 +919,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     Opts& o = a.o;
     o.reltol = opt->reltol; o.vabstol = opt->vabstol; o.iabstol = opt->iabstol;
     o.nr_reltol = opt->nr_reltol; o.nr_vabstol = opt->nr_vabstol; o.nr_iabstol = opt->nr_iabstol;
-    o.dc_abstol = opt->dc_abstol; o.dv_max = opt->dv_max;
+    o.dc_abstol = opt->dc_abstol;
+    // the Newton voltage-step limit only exists for nonlinear (Verilog-A) devices
+    o.dv_max = c->insts.empty() ? 1e300 : opt->dv_max;
     o.dt = opt->dt; o.dt_min = opt->dt_min; o.t0 = t0; o.t1 = t1;
     o.span = t1 - t0;
     o.teps = 1e-12 * std::max(std::fabs(t1), o.span);
@@ -825,6 +987,18 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     char vargs[8][256];
     if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
     for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs[m]);
+    struct SArgsH {
+        long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA; const double* dev_out;
+        const double* lin_g; const double* lin_c; const double* WV; const int* active; double* DX; double* QK; double* RMAX; int* BAD;
+        double* DVMAX;
+    } sargs{B, a.X, a.alpha, a.dst + (size_t)DS_GSHUNT * B, a.BETA, a.dev_out, a.lin_g, a.lin_c, p->d_WV, a.active,
+            p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
+    void* sargs_ptr[] = {&sargs};
+    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV};
+    if (p->gen) {
+        k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
+        CUDA_TRY(cudaGetLastError());
+    }
     const unsigned eval_threads = std::getenv("CB_EVAL_THREADS") ? (unsigned)std::atoi(std::getenv("CB_EVAL_THREADS")) : 128u;
     bool done = false;
     while (!done && rounds < max_rounds) {
@@ -842,7 +1016,11 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
                 launches++;
             }
             if (timing) cudaEventRecord(e1, p->stream);
-            if (p->glob) k_newton<1, true><<<ngrid, nthreads, 0, p->stream>>>(a);
+            if (p->gen) {
+                CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
+                k_control<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(cargs);
+                launches++;
+            } else if (p->glob) k_newton<1, true><<<ngrid, nthreads, 0, p->stream>>>(a);
             else switch (p->G) {
                 case 4: k_newton<4, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
                 case 8: k_newton<8, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;

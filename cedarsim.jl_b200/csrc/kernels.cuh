@@ -302,9 +302,8 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
             newton_fail = true;
             status = 4;
         } else {
-            if (it == 0) lim = o.dv_max;   // limit doubles while it keeps binding (mirrors the oracle)
+            lim = o.dv_max;
             const double sc = dvmax > lim ? lim / dvmax : 1.0;
-            lim = sc < 1.0 ? 2.0 * lim : o.dv_max;
             const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
             int conv = (sc == 1.0) && (rmax <= restol);
             for (int i = lane; i < N; i += G) {
@@ -506,6 +505,286 @@ __global__ void __launch_bounds__(256) k_newton(const NArgs a) {
 #undef DST
 #undef AT
 #undef WA
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_control: per-point Newton update + DC / transient state machine, one thread per point.
+// Partner of the circuit-specialised generated kernel k_solve (gen_solve_source() in cedarb200.cu),
+// which assembles J and r from the device outputs, runs the straight-line static-pivot LU and
+// leaves dx = -J^-1 r, the charges q and max|r| in batch-interleaved arrays.  Every access here
+// is [k][B] with consecutive threads on consecutive points (fully coalesced).  The control logic
+// mirrors k_newton above (and the CPU oracle) statement for statement.
+struct CArgs {
+    NArgs n;
+    const double *DX, *QK, *RMAX, *DVMAX;
+    const int* BAD;
+    double* WV;  // [nwaves][B] source values for the next evaluation
+};
+
+__device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long long inst, bool dcop, double t) {
+    for (int w = 0; w < a.nwaves; w++) WV[(size_t)w * a.B + inst] = wave_value(a.waves[w], t, dcop, a.params, a.B, inst);
+}
+
+__global__ void __launch_bounds__(128) k_control(const CArgs c) {
+    const NArgs& a = c.n;
+    const long long B = a.B;
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    int phase = a.ist[(size_t)IS_PHASE * B + inst];
+    if (phase == PH_DONE) return;
+    const int N = a.N, NV = a.NV;
+    const Opts& o = a.o;
+    // restrict-qualified views: lets the compiler batch the loads of the unrolled vector loops
+    double* __restrict__ X = a.X + inst;   double* __restrict__ XN = a.XN + inst; double* __restrict__ X1 = a.X1 + inst;
+    double* __restrict__ X2 = a.X2 + inst; double* __restrict__ XP = a.XP + inst; double* __restrict__ QN = a.QN + inst;
+    double* __restrict__ Q1 = a.Q1 + inst; double* __restrict__ QD = a.QD + inst; double* __restrict__ BETA = a.BETA + inst;
+    const double* __restrict__ DX = c.DX + inst; const double* __restrict__ QK = c.QK + inst;
+    const unsigned char* __restrict__ mask = a.lte_mask;
+#define IST(k) a.ist[(size_t)(k) * B + inst]
+#define DST(k) a.dst[(size_t)(k) * B + inst]
+#define V(arr, i) arr[(size_t)(i) * B]
+    int it = IST(IS_IT), stage = IST(IS_STAGE), nh = IST(IS_NH), bpi = IST(IS_BPI), kstep = IST(IS_KSTEP);
+    int status = IST(IS_STATUS), hit_bp = IST(IS_HITBP), method = IST(IS_METHOD), np = IST(IS_NP);
+    int sidx = IST(IS_SIDX), nnewton = IST(IS_NNEWTON), nacc = IST(IS_NACC), nrej = IST(IS_NREJ);
+    int retry = IST(IS_RETRY);
+    double t = DST(DS_T), tnew = DST(DS_TNEW), h = DST(DS_H), h1 = DST(DS_H1), h2 = DST(DS_H2);
+    double hprop = DST(DS_HPROP), gshunt = DST(DS_GSHUNT), lim = DST(DS_LIM);
+    double alpha = a.alpha[inst];
+    const double rmax = c.RMAX[inst];
+    bool finish = false, begin = false, newton_ok = false, newton_fail = false;
+    // what the fused history pass at the end has to do
+    bool do_accept = false;        // shift history, QD/QN from this iterate
+    int copy_mode = 0;             // 1: X <- 0, XN <- 0   2: XN <- X   3: X <- XN   4: QN <- QK, QD <- 0
+
+    if (phase == PH_TRAN_INIT) {
+        copy_mode = 4;
+        while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
+            for (int k = 0; k < a.O; k++) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
+            sidx++;
+        }
+        if (status != 0) finish = true;
+        else { begin = true; phase = PH_TRAN; }
+    } else {
+        nnewton++;
+        const double dvmax = c.DVMAX[inst];
+        if (c.BAD[inst]) {
+            newton_fail = true;
+            status = 4;
+        } else {
+            lim = o.dv_max;
+            const double sc = dvmax > lim ? lim / dvmax : 1.0;
+            const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
+            int conv = (sc == 1.0) && (rmax <= restol);
+            // update pass; the LTE estimate is accumulated speculatively in the same sweep
+            double ratio = 0.0;
+            const bool want_lte = phase == PH_TRAN && !o.fixed_step && np >= 1;
+            if (want_lte) {
+                if (method == 0) ratio = h / (2.0 * h + h1);
+                else {
+                    const double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
+                    const double lc = method == 1 ? h * h * h / 12.0 : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
+                    ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
+                }
+            }
+            double err = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < N; i++) {
+                const double dx = sc * V(DX, i);
+                const double xo = V(X, i), xn = xo + dx;
+                const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
+                if (fabs(dx) > o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol) conv = 0;
+                V(X, i) = xn;
+                if (want_lte && mask[i]) {
+                    const double tol = o.reltol * fmax(fabs(xn), fabs(V(XN, i))) + (i < NV ? o.vabstol : o.iabstol);
+                    err = fmax(err, ratio * fabs(xn - V(XP, i)) / tol);
+                }
+            }
+            it++;
+            if (conv) newton_ok = true;
+            else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
+
+            if (phase == PH_TRAN && newton_ok) {
+                double fac = 2.0;
+                bool reject = false;
+                if (want_lte) {
+                    const int p = (method == 0 || np < 2) ? 1 : 2;
+                    fac = err > 0.0 ? 0.9 * pow(err, -1.0 / (p + 1)) : 2.0;
+                    fac = fmin(2.0, fmax(0.2, fac));
+                    if (err > 1.0) {
+                        reject = true;
+                        nrej++;
+                        hprop = h * fac;
+                        if (hprop < o.dt_min) { status = 3; finish = true; }
+                        else begin = true;
+                    }
+                }
+                if (!reject) {
+                    nacc++;
+                    do_accept = true;
+                    const double told = t;
+                    const double oh1 = h1, oh2 = h2;
+                    h2 = h1; h1 = h;
+                    nh = nh + 1 < 2 ? nh + 1 : 2;
+                    t = tnew;
+                    kstep++;
+                    // outputs from the NEW history: x_n = X, x_{n-1} = old XN, x_{n-2} = old X1 (not yet shifted)
+                    while (sidx < o.nsave && a.saveat[sidx] <= t + o.teps) {
+                        const double ts = a.saveat[sidx];
+                        const bool exact = fabs(ts - t) <= o.teps;
+                        const int ni = o.method == 0 ? 1 : (nh < 2 ? nh : 2);
+                        for (int k = 0; k < a.O; k++) {
+                            const int u = a.outputs[k];
+                            const double xn = V(X, u);
+                            a.y_out[((size_t)k * o.nsave + sidx) * B + inst] =
+                                exact ? xn : poly_at(ni, ts, t, xn, h1, V(XN, u), h2, V(X1, u));
+                        }
+                        sidx++;
+                    }
+                    (void)told; (void)oh1; (void)oh2;
+                    if (!o.fixed_step) {
+                        hprop = h * fac;
+                        if (hit_bp) {
+                            nh = 0;
+                            const double nb = (bpi + 1 < a.nbp) ? a.bp[bpi + 1] - t : o.t1 - t;
+                            hprop = fmin(hprop, 0.1 * fmin(h, nb > 0.0 ? nb : h));
+                            hprop = fmax(hprop, o.span * 1e-9);
+                        }
+                    }
+                    begin = true;
+                }
+            }
+        }
+        if (phase == PH_DC && (newton_ok || newton_fail)) {
+            bool dc_done = false;
+            it = 0;
+            if (stage < 0) {
+                if (newton_ok) { dc_done = true; status = 0; }
+                else {
+                    copy_mode = 1;
+                    stage = 0; gshunt = 1e-2; status = 0;
+                    if (o.gmin_steps == 0) gshunt = 0.0;
+                }
+            } else if (stage < o.gmin_steps) {
+                copy_mode = newton_ok ? 2 : 3;
+                stage++; gshunt *= 0.1; status = 0;
+                if (stage == o.gmin_steps) gshunt = 0.0;
+            } else {
+                dc_done = true;
+                status = newton_ok ? 0 : 2;
+            }
+            if (dc_done) {
+                gshunt = 0.0;
+                if (o.dc_only) {
+                    for (int k = 0; k < a.O; k++) a.y_out[(size_t)k * B + inst] = V(X, a.outputs[k]);
+                    phase = PH_DONE;
+                    atomicAdd(a.done_count, 1);
+                } else {
+                    copy_mode = 2;
+                    phase = PH_TRAN_INIT;
+                }
+            }
+        } else if (phase == PH_TRAN && newton_fail && o.fixed_step && !retry) {
+            copy_mode = 3;
+            retry = 1; it = 0; status = 0;
+        } else if (phase == PH_TRAN && newton_fail) {
+            nrej++;
+            if (o.fixed_step) finish = true;
+            else {
+                hprop = h / 8.0;
+                if (hprop < o.dt_min) { status = 3; finish = true; }
+                else { status = 0; begin = true; }
+            }
+        }
+    }
+    // ---- next step attempt: scalars first (mirrors the top of the oracle's step loop)
+    double a1 = 0.0, a2 = 0.0;
+    if (begin) {
+        bool more;
+        if (o.fixed_step) {
+            more = kstep < o.nfixed;
+            if (more) { tnew = o.t0 + (double)(kstep + 1) * o.dt; h = tnew - t; hit_bp = 0; }
+        } else {
+            more = t < o.t1 - o.teps;
+            if (more) {
+                while (bpi < a.nbp && a.bp[bpi] <= t + o.teps) bpi++;
+                const double tb = bpi < a.nbp ? a.bp[bpi] : o.t1;
+                h = fmin(hprop, o.dt_max);
+                hit_bp = 0;
+                if (t + h >= tb - 1e-3 * h) { h = tb - t; tnew = tb; hit_bp = 1; }
+                else if (t + 2.0 * h > tb) { h = 0.5 * (tb - t); tnew = t + h; }
+                else tnew = t + h;
+            }
+        }
+        if (!more) { finish = true; begin = false; }
+        else {
+            method = nh == 0 ? 0 : o.method;
+            if (method == 0) { alpha = 1.0 / h; a1 = -alpha; }
+            else if (method == 1) { alpha = 2.0 / h; a1 = -alpha; }
+            else {
+                const double rho = h / h1;
+                alpha = (1.0 + 2.0 * rho) / (h * (1.0 + rho));
+                a1 = -(1.0 + rho) / h;
+                a2 = rho * rho / (h * (1.0 + rho));
+            }
+            np = method == 0 ? (nh < 1 ? nh : 1) : nh;
+            it = 0;
+            retry = 0;
+        }
+    }
+    // ---- one fused pass over the unknowns: history shift (accept), DC copies, beta + predictor (begin)
+    const double alpha_old = a.alpha[inst];
+    if (do_accept || copy_mode || begin) {
+#pragma unroll 4
+        for (int i = 0; i < N; i++) {
+            double x = V(X, i), xn = V(XN, i), x1 = V(X1, i), x2 = V(X2, i), qn = V(QN, i), q1 = V(Q1, i), qd = V(QD, i);
+            if (do_accept) {
+                const double qk = V(QK, i);
+                qd = alpha_old * qk + V(BETA, i);
+                x2 = x1; x1 = xn; xn = x;
+                q1 = qn; qn = qk;
+                V(QD, i) = qd; V(X2, i) = x2; V(X1, i) = x1; V(XN, i) = xn; V(Q1, i) = q1; V(QN, i) = qn;
+            } else if (copy_mode == 1) { x = 0.0; xn = 0.0; V(X, i) = x; V(XN, i) = xn; }
+            else if (copy_mode == 2) { xn = x; V(XN, i) = xn; }
+            else if (copy_mode == 3) { x = xn; V(X, i) = x; }
+            else if (copy_mode == 4) { qn = V(QK, i); qd = 0.0; V(QN, i) = qn; V(QD, i) = qd; }
+            if (begin) {
+                double beta = a1 * qn;
+                if (method == 1) beta -= qd;
+                else if (method == 2) beta += a2 * q1;
+                V(BETA, i) = beta;
+                const double xp = poly_at(np, tnew, t, xn, h1, x1, h2, x2);
+                V(XP, i) = xp;
+                double lm = np >= 1 ? fabs(xn - x1) * (h / h1) : 0.0;
+                if (i < NV) lm = fmin(lm, o.dv_max);
+                V(X, i) = xn + fmax(-lm, fmin(lm, xp - xn));
+            }
+        }
+    }
+    if (finish) {
+        for (; sidx < o.nsave; sidx++)
+            for (int k = 0; k < a.O; k++)
+                a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
+        phase = PH_DONE;
+        atomicAdd(a.done_count, 1);
+    }
+    IST(IS_PHASE) = phase; IST(IS_IT) = it; IST(IS_STAGE) = stage; IST(IS_NH) = nh; IST(IS_BPI) = bpi;
+    IST(IS_KSTEP) = kstep; IST(IS_STATUS) = status; IST(IS_HITBP) = hit_bp; IST(IS_METHOD) = method;
+    IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
+    IST(IS_RETRY) = retry;
+    DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
+    DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim;
+    a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
+    a.active[inst] = phase != PH_DONE;
+    if (phase != PH_DONE) store_waves(a, c.WV, inst, phase != PH_TRAN, tnew);
+#undef IST
+#undef DST
+#undef V
+}
+
+__global__ void k_init_waves(const NArgs a, double* WV) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.B) return;
+    store_waves(a, WV, inst, true, 0.0);
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------

@@ -60,7 +60,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define VA_EVAL_THREADS 128
 #endif
 #ifndef VA_EVAL_MINBLOCKS
-#define VA_EVAL_MINBLOCKS 1
+#define VA_EVAL_MINBLOCKS 8
 #endif
 #ifdef VA_PREFETCH_L2
 #define VA_PREFETCH_ALL()                                                                        \

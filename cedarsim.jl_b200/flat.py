@@ -418,6 +418,21 @@ class PackedCircuit:
         return C.byref(self.struct)
 
 
+def nodeset_vector(fc: "FlatCircuit", nodeset: Dict[str, float]) -> np.ndarray:
+    """Initial guess x0[N] from named node voltages.  Internal nodes of Verilog-A devices that sit
+    behind a series resistance (BSIM `di`/`si` behind `d`/`s`) start at their port's voltage."""
+    x0 = np.zeros(fc.n_unknowns)
+    for n, v in nodeset.items():
+        x0[fc.unknown(n)] = v
+    for vi in fc.va_insts:
+        terms = fc.va_models[vi.model].terminals
+        for k, tname in enumerate(terms):
+            if tname.endswith("i") and tname[:-1] in terms and vi.term[k] >= 0:
+                port = vi.term[terms.index(tname[:-1])]
+                x0[vi.term[k]] = x0[port] if port >= 0 else 0.0
+    return x0
+
+
 def params_matrix(cols: Sequence[np.ndarray]) -> np.ndarray:
     """Stack per-instance parameter columns into the C-ABI layout [P][B]."""
     if len(cols) == 0:

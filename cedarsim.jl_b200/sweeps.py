@@ -418,11 +418,8 @@ class CircuitSweep:
 
     def nodeset(self, **node_voltages):
         """initial guess for the DC Newton (warm start, cf. remake(prob, u0=...) src/sweeps.jl:474-477)"""
-        fc = self.flat.fc
-        x0 = np.zeros(fc.n_unknowns)
-        for k, v in node_voltages.items():
-            x0[fc.unknown(k)] = v
-        self.x0 = x0
+        from .flat import nodeset_vector
+        self.x0 = nodeset_vector(self.flat.fc, node_voltages)
         return self
 
     # ---- engine plumbing: contiguous block of points per GPU, one host thread per device (SURVEY 8(e))

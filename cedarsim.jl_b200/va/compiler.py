@@ -811,7 +811,9 @@ class _Compiler:
             if a == b:
                 return Val("r", "0.0", {}, 0.0)
             self.count("add")
-            return self.emit_val("r", f"VT({a}) - VT({b})", {a: 1.0, b: -1.0})
+            d = {a: 1.0, b: -1.0}
+            d.pop(getattr(self, "drop_seed", None), None)
+            return self.emit_val("r", f"VT({a}) - VT({b})", d)
         if len(idx) == 1:
             sign = 1.0 if (len(nodes) == 1 or nodes[0] not in ("0", "gnd")) else -1.0
             a = idx[0]
@@ -896,6 +898,39 @@ class _Compiler:
 
     def _pow(self, a: Val, b: Val) -> Val:
         ac, bc = self._cast(a.c, a.typ, "r"), self._cast(b.c, b.typ, "r")
+        # strength reduction for compile-time exponents (card-specialised code has many pow(x, 2|3|4))
+        if b.const is not None and not b.d:
+            e = float(b.const)
+            if e == 0.0:
+                return Val("r", "1.0", {}, 1.0)
+            if e == 1.0:
+                return Val("r", ac, dict(a.d)) if a.typ == "r" else self.emit_val("r", ac, {})
+            if e == 0.5:
+                return self._unary_math("sqrt", a)
+            if e == float(int(e)) and 2 <= abs(e) <= 8:
+                n = int(abs(e))
+                base = self.emit_val("r", ac, {})
+                # x^(n-1) by repeated multiplication, then value and derivative n*x^(n-1)
+                pm1 = base.c
+                for _ in range(n - 2):
+                    pm1 = self.emit_val("r", f"{pm1} * {base.c}", {}).c
+                    self.count("mul")
+                val = self.emit_val("r", f"{pm1} * {base.c}", {})
+                self.count("mul")
+                if e > 0:
+                    if not a.d:
+                        return val
+                    g = self.emit_val("r", f"{float(n)!r} * {pm1}", {})
+                    self.count("mul", 1 + len(a.d))
+                    return self.emit_val("r", val.c, {kk: self._dmul(g.c, x) for kk, x in a.d.items()})
+                inv = self.emit_val("r", f"1.0 / {val.c}", {})
+                self.count("div")
+                if not a.d:
+                    return inv
+                # d/dx x^-n = -n x^-n / x
+                g = self.emit_val("r", f"{-float(n)!r} * {inv.c} / {base.c}", {})
+                self.count("div"); self.count("mul", 1 + len(a.d))
+                return self.emit_val("r", inv.c, {kk: self._dmul(g.c, x) for kk, x in a.d.items()})
         self.count("pow")
         p = self.emit_val("r", f"pow({ac}, {bc})", {})
         keys = sorted(set(a.d) | set(b.d))
@@ -1014,12 +1049,19 @@ class _Compiler:
             if pr[0] != "probe" or pr[1] not in ("V", "potential"):
                 raise VACompileError("ddx: second argument must be a V() probe")
             idx = [self.tindex[n] for n in pr[2] if n in self.tindex]
+
+            def dwrt(node):
+                t_ = self.tindex.get(node, -1)
+                if t_ >= 0 and t_ == getattr(self, "drop_seed", None):   # recovered by invariance
+                    terms = [self._datom(x) for x in v.d.values()]
+                    return "(-(" + " + ".join(terms) + "))" if terms else "0.0"
+                return self._datom(v.d.get(t_, 0.0))
+
             if len(pr[2]) == 1:
-                d = v.d.get(idx[0], 0.0) if idx else 0.0
-                return self.emit_val("r", self._datom(d), {})
+                return self.emit_val("r", dwrt(pr[2][0]) if idx else "0.0", {})
             # two-node probe: (dx1 - dx2)/2 as the reference does (src/vasim.jl:398-411)
-            d1 = self._datom(v.d.get(self.tindex.get(pr[2][0], -1), 0.0))
-            d2 = self._datom(v.d.get(self.tindex.get(pr[2][1], -1), 0.0))
+            d1 = dwrt(pr[2][0])
+            d2 = dwrt(pr[2][1])
             return self.emit_val("r", f"({d1} - {d2}) * 0.5", {})
         if fn == "ddt":
             raise VACompileError("ddt() is only supported as a linear term of a contribution")
@@ -1520,6 +1562,7 @@ class _Compiler:
             if bad:
                 raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
+        self.drop_seed = self._pick_drop_seed(body)
         pruned, _ = prune_dead(body, set(), mod.functions)
         if pruned is not None:
             self.stmt(pruned)
@@ -1534,9 +1577,16 @@ class _Compiler:
             out_lines.append(f"OUT_Q({kk}, {'accQ_%d' % kk if sq else '0.0'});")
             di = si.deps if si else frozenset()
             dq = sq.deps if sq else frozenset()
-            for ll in sorted(di | dq):
-                g = f"accI_{kk}__d{ll}" if ll in di else "0.0"
-                cq = f"accQ_{kk}__d{ll}" if ll in dq else "0.0"
+            cols = set(di | dq)
+            if self.drop_seed is not None and cols:
+                cols.add(self.drop_seed)
+            for ll in sorted(cols):
+                if ll == self.drop_seed:
+                    g = "-(" + " + ".join(f"accI_{kk}__d{m}" for m in sorted(di)) + ")" if di else "0.0"
+                    cq = "-(" + " + ".join(f"accQ_{kk}__d{m}" for m in sorted(dq)) + ")" if dq else "0.0"
+                else:
+                    g = f"accI_{kk}__d{ll}" if ll in di else "0.0"
+                    cq = f"accQ_{kk}__d{ll}" if ll in dq else "0.0"
                 out_lines.append(f"OUT_J({len(jrow)}, {kk}, {ll}, {g}, {cq});")
                 jrow.append(kk)
                 jcol.append(ll)
@@ -1555,6 +1605,69 @@ class _Compiler:
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
                              ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
                              param_defaults=defaults)
+
+    def _pick_drop_seed(self, body) -> Optional[int]:
+        """Translational invariance: when every probe is a difference V(a,b) of two terminals, every
+        value v satisfies sum_k dv/dV_k = 0, so the derivative w.r.t. one terminal never has to be
+        propagated -- it is recovered at the end as minus the sum of the others.  Returns the index of
+        the terminal that appears in the most probes (the cheapest one to drop), or None."""
+        counts: Dict[int, int] = {}
+        ok = [True]
+
+        def ex(e):
+            k = e[0]
+            if k == "probe":
+                nodes = list(e[2])
+                if len(nodes) == 1 and nodes[0] in self.mod.branches:
+                    nodes = list(self.mod.branches[nodes[0]])
+                if len(nodes) != 2 or any(n not in self.tindex for n in nodes):
+                    ok[0] = False
+                    return
+                for n in nodes:
+                    counts[self.tindex[n]] = counts.get(self.tindex[n], 0) + 1
+            elif k == "bin":
+                ex(e[2]); ex(e[3])
+            elif k == "un":
+                ex(e[2])
+            elif k == "cond":
+                for s_ in e[1:]:
+                    ex(s_)
+            elif k == "call":
+                for a in e[2]:
+                    ex(a)
+
+        def st(s_):
+            k = s_[0]
+            if k == "assign":
+                ex(s_[2])
+            elif k == "contrib":
+                ex(s_[3])
+            elif k == "block":
+                for x in s_[2]:
+                    st(x)
+            elif k == "if":
+                ex(s_[1]); st(s_[2])
+                if s_[3]:
+                    st(s_[3])
+            elif k == "case":
+                ex(s_[1])
+                for vals, x in s_[2]:
+                    for v in vals:
+                        ex(v)
+                    st(x)
+                if s_[3]:
+                    st(s_[3])
+            elif k == "for":
+                st(s_[1]); ex(s_[2]); st(s_[3]); st(s_[4])
+            elif k in ("while", "repeat"):
+                ex(s_[1]); st(s_[2])
+
+        st(body)
+        for f in self.mod.functions.values():
+            st(f.body)
+        if not ok[0] or len(counts) < 2:
+            return None
+        return max(counts, key=lambda kk: (counts[kk], kk))
 
     def _c_function(self, f: Function) -> str:
         """value-only C translation of an analog function (used by the setup stream)"""

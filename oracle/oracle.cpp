@@ -323,7 +323,9 @@ struct Solver {
     // Returns 0 ok, 1 max iterations, 4 singular / non-finite.
     int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
                double gshunt, int maxit, double restol, std::vector<double>& qk) {
-        double lim = opt->dv_max;  // voltage-step limit; doubles while it keeps binding (trust-region growth)
+        // voltage-step limit: only nonlinear (Verilog-A) devices need it; a purely linear circuit
+        // converges in one full step whatever its voltage scale
+        const double lim = in.fc->n_va_insts > 0 ? opt->dv_max : 1e300;
         for (int it = 0; it < maxit; it++) {
             eval_system(in, vc, x.data(), t, dcop, s);
             cnt.newton++;
@@ -346,7 +348,6 @@ struct Solver {
             }
             if (!finite) return 4;
             double sc = dvmax > lim ? lim / dvmax : 1.0;
-            lim = sc < 1.0 ? 2.0 * lim : opt->dv_max;
             bool conv = (sc == 1.0) && (rmax <= restol);
             for (int i = 0; i < N; i++) {
                 double dx = sc * rhs[i];
@@ -473,7 +474,7 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
         for (int i = 0; i < N; i++) {
             double d = xp[i] - xn[i];
             double lim = np >= 1 ? std::fabs(xn[i] - x1[i]) * (h / h1) : 0.0;
-            if (i < S.NV) lim = std::min(lim, opt->dv_max);
+            if (i < S.NV) lim = std::min(lim, fc->n_va_insts > 0 ? opt->dv_max : 1e300);
             x[i] = xn[i] + std::max(-lim, std::min(lim, d));
         }
         int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);

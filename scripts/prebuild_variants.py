@@ -1,7 +1,5 @@
-# pre-compile NVRTC variants here (no GPU needed) so the GPU box only loads cubins
 import os, sys, subprocess
-variants = [dict(), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=3"), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=4"),
-            dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=6"), dict(CB_NVRTC_DEFS="-DVA_EVAL_THREADS=64 -DVA_EVAL_MINBLOCKS=6")]
+variants = [dict(), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=10"), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=12"), dict(CB_NVRTC_DEFS="-DVA_EVAL_MINBLOCKS=6")]
 procs = []
 for v in variants:
     env = dict(os.environ, **v)

@@ -15,10 +15,8 @@ def both_options(**kw):
 
 
 def x0_from(fc, nodeset):
-    x0 = np.zeros(fc.n_unknowns)
-    for n, v in nodeset.items():
-        x0[fc.unknown(n)] = v
-    return x0
+    from cedarsim.jl_b200.flat import nodeset_vector
+    return nodeset_vector(fc, nodeset)
 
 
 def run_dc_both(fc, models, P, x0=None, **kw):

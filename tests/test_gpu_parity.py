@@ -118,7 +118,7 @@ def test_bsimcmg_dff_mc_fixed(host_bsimcmg):
     assert sg.max() == 0 and so.max() == 0
     assert_tran_close(yg, yo)
     # borderline convergence decisions may differ by an iteration between FMA and non-FMA arithmetic
-    assert abs(stg["newton_iters"] - sto["newton_iters"]) <= 1e-3 * sto["newton_iters"]
+    assert abs(stg["newton_iters"] - sto["newton_iters"]) <= 5e-3 * sto["newton_iters"]
 
 
 def test_bsimcmg_dff_adaptive_known_answers(host_bsimcmg):
