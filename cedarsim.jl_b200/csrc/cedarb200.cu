@@ -470,7 +470,9 @@ static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
     std::string maxreg = std::getenv("CB_MAXREG") ? std::string("--maxrregcount=") + std::getenv("CB_MAXREG") : "";
     std::vector<std::string> extra;
     if (const char* d = std::getenv("CB_NVRTC_DEFS")) {
-        std::istringstream is(d);
+        std::string ds(d);
+        std::replace(ds.begin(), ds.end(), ',', ' ');
+        std::istringstream is(ds);
         std::string tok;
         while (is >> tok) extra.push_back(tok);
     }
@@ -559,6 +561,8 @@ struct cb_plan {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaLibrary_t lib = nullptr;
+    std::vector<unsigned> eval_threads;
+    std::vector<size_t> eval_smem;
     std::vector<cudaKernel_t> k_setup, k_eval;
     cudaKernel_t k_solve = nullptr;
     bool gen = true;         // generated straight-line k_solve + k_control (default)
@@ -650,6 +654,17 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
             cudaKernel_t ks, ke;
             CUDA_TRY(cudaLibraryGetKernel(&ks, p->lib, ("k_setup_" + m.name).c_str()));
             CUDA_TRY(cudaLibraryGetKernel(&ke, p->lib, ("k_eval_" + m.name).c_str()));
+            {   // block size and dynamic shared memory (cache ring) the generated kernel was compiled for
+                void* dmeta = nullptr;
+                size_t msz = 0;
+                int meta[2] = {128, 0};
+                CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_meta_" + m.name).c_str()));
+                CUDA_TRY(cudaMemcpy(meta, dmeta, sizeof meta, cudaMemcpyDeviceToHost));
+                p->eval_threads.push_back((unsigned)meta[0]);
+                p->eval_smem.push_back((size_t)meta[1]);
+                if (meta[1] > 48 * 1024)
+                    CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributeMaxDynamicSharedMemorySize, meta[1]));
+            }
             p->k_setup.push_back(ks);
             p->k_eval.push_back(ke);
         }
@@ -999,7 +1014,6 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
         CUDA_TRY(cudaGetLastError());
     }
-    const unsigned eval_threads = std::getenv("CB_EVAL_THREADS") ? (unsigned)std::atoi(std::getenv("CB_EVAL_THREADS")) : 128u;
     bool done = false;
     while (!done && rounds < max_rounds) {
         for (int r = 0; r < poll; r++) {
@@ -1011,8 +1025,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
                 void* kargs[] = {vargs[m]};
+                const unsigned eval_threads = p->eval_threads[m];
                 dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
-                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(eval_threads), kargs, 0, p->stream));
+                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(eval_threads), kargs, p->eval_smem[m], p->stream));
                 launches++;
             }
             if (timing) cudaEventRecord(e1, p->stream);

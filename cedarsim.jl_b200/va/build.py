@@ -38,6 +38,8 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define VA_EVAL_BEGIN(NAME) void NAME##_eval(const double* cache_, const double* v_, double* I_, double* Q_, double* G_, double* C_) {{
 #define VA_EVAL_END(NAME) }}
 #define CACHE_LD(s) cache_[s]
+#define CACHE_LDG(s) cache_[s]
+#define VA_CHUNK(k)
 #define VT(k) v_[k]
 #define OUT_I(k, v) I_[k] = (v)
 #define OUT_Q(k, v) Q_[k] = (v)

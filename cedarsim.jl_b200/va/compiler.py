@@ -25,11 +25,17 @@ from __future__ import annotations
 
 import hashlib
 import math
+import re
 from dataclasses import dataclass, field
 from typing import Dict, FrozenSet, List, Optional, Sequence, Set, Tuple
 
 from .parser import Function, Module, parse
 from .preproc import Preprocessor
+
+
+# cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
+CACHE_CHUNK_ROWS = 8
+CACHE_WINDOW = 16
 
 
 class VACompileError(Exception):
@@ -1567,6 +1573,7 @@ class _Compiler:
         if pruned is not None:
             self.stmt(pruned)
         self.flush_ops(self.E)
+        self._stage_cache()
         nt = len(self.terms)
         # outputs
         jrow, jcol = [], []
@@ -1605,6 +1612,79 @@ class _Compiler:
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
                              ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
                              param_defaults=defaults)
+
+    def _stage_cache(self):
+        """Re-lays the cache out as a *stream* in the order the eval function consumes it.
+
+        The eval code is long straight-line code whose cache reads are scattered through it; on the
+        GPU every read is an HBM access of ~1 us latency, and the register allocator can only hoist
+        a few of them.  Ordering the slots by first use turns the cache into a sequential stream that
+        the CUDA prelude moves through a shared-memory ring with per-thread `cp.async` copies, a
+        fixed number of chunks ahead of the consumer (see VA_CHUNK in csrc/va_prelude.h).
+
+        Guarantee given to the prelude: in the top-level statement that follows VA_CHUNK(k) markers
+        up to chunk k, every CACHE_LD(p) satisfies  need - VA_WINDOW < p <= need,  need = highest
+        stream position used so far.  A value whose uses are further apart than the window gets a
+        second stream position (the setup function stores it to all of them), so nothing is held in
+        registers across the ring.  Markers are only placed between top-level statements: the
+        sequence of copy groups is the same on every control path.
+        """
+        E, R, W = self.E, CACHE_CHUNK_ROWS, CACHE_WINDOW
+        ld = re.compile(r"CACHE_LD\((\d+)\)")
+        blocks, depth, start = [], 0, 0
+        for i, l in enumerate(E):
+            if depth == 0:
+                start = i
+            depth += l.count("{") - l.count("}")
+            if depth == 0:
+                blocks.append((start, i + 1))
+        stream: List[int] = []          # stream position -> old slot
+        latest: Dict[int, int] = {}     # old slot -> its most recent stream position
+        positions: Dict[int, List[int]] = {}
+        out: List[str] = []
+        for (a, b) in blocks:
+            used: List[int] = []
+            for l in E[a:b]:
+                for m in ld.finditer(l):
+                    k = int(m.group(1))
+                    if k not in used:
+                        used.append(k)
+            direct = len(used) > W   # too many for the window: this statement reads HBM directly
+            if used:
+                while True:
+                    new = [x for x in used if x not in latest]
+                    need = len(stream) + len(new)
+                    stale = [] if direct else [x for x in used if x in latest and latest[x] < need - W]
+                    if not stale:
+                        break
+                    for x in stale:
+                        del latest[x]
+                for x in new:
+                    if len(stream) % R == 0:
+                        out.append(f"VA_CHUNK({len(stream) // R})")
+                    latest[x] = len(stream)
+                    positions.setdefault(x, []).append(len(stream))
+                    stream.append(x)
+            for l in E[a:b]:
+                mac = "CACHE_LDG" if direct else "CACHE_LD"
+                out.append(ld.sub(lambda m: f"{mac}({latest[int(m.group(1))]})", l) if used else l)
+        self.E[:] = out
+        st = re.compile(r"^(\s*)CACHE_ST\((\d+), (.*)\);$")
+        S2: List[str] = []
+        for l in self.S:
+            m = st.match(l)
+            if not m:
+                S2.append(l)
+                continue
+            pos = positions.get(int(m.group(2)), [])
+            if len(pos) == 1:
+                S2.append(f"{m.group(1)}CACHE_ST({pos[0]}, {m.group(3)});")
+            elif pos:
+                S2.append(f"{m.group(1)}{{ const double cs_ = (double)({m.group(3)}); "
+                          + " ".join(f"CACHE_ST({q}, cs_);" for q in pos) + " }")
+        self.S[:] = S2
+        self.nslot = len(stream)
+        self.nchunk = (len(stream) + R - 1) // R
 
     def _pick_drop_seed(self, body) -> Optional[int]:
         """Translational invariance: when every probe is a difference V(a,b) of two terminals, every
@@ -1709,6 +1789,8 @@ class _Compiler:
         L: List[str] = []
         L.append(f"// generated by cedarsim.jl_b200.va.compiler from Verilog-A module '{self.mod.name}'")
         L.append(f"// terminals: {', '.join(self.terms)}   cache slots: {self.nslot}")
+        L.append("#undef VA_CHUNK_ROWS\n#undef VA_WINDOW\n#undef VA_NCHUNK")
+        L.append(f"#define VA_CHUNK_ROWS {CACHE_CHUNK_ROWS}\n#define VA_WINDOW {CACHE_WINDOW}\n#define VA_NCHUNK {self.nchunk}")
         # helper functions used by setup (emit in dependency-safe order: iterate to closure)
         done: Dict[str, str] = {}
         pending = set(self.used_funcs)

@@ -1,6 +1,9 @@
 #!/bin/bash
-run() { echo "== $*"; env "$@" CB_TIMING=1 python scripts/first_perf.py 16384 adaptive 6e-8 2>&1 | tail -1 | sed 's/.*rounds/rounds/'; }
-run A=1
-run CB_NVRTC_DEFS=-DVA_EVAL_MINBLOCKS=10
-run CB_NVRTC_DEFS=-DVA_EVAL_MINBLOCKS=12
-run CB_NVRTC_DEFS=-DVA_EVAL_MINBLOCKS=6
+# usage: variants_perf.sh variants.txt [span]   -- one line per variant: ENV=VAL ENV2=VAL2 (use , instead of spaces inside CB_NVRTC_DEFS)
+SPAN=${2:-6e-8}
+while read -r line; do
+  [ -z "$line" ] && continue
+  case "$line" in \#*) continue;; esac
+  echo "== $line"
+  env $line CB_TIMING=1 python scripts/first_perf.py 16384 adaptive $SPAN 2>&1 | tail -1 | sed 's/.*rounds/rounds/'
+done < "$1"
