@@ -565,7 +565,10 @@ struct cb_plan {
     std::vector<size_t> eval_smem;
     std::vector<cudaKernel_t> k_setup, k_eval;
     cudaKernel_t k_solve = nullptr;
-    bool gen = true;         // generated straight-line k_solve + k_control (default)
+    bool gen = true;         // k_control + a separate solve kernel (default): k_lu, or the generated k_solve
+    bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu)
+    LArgs la{};
+    size_t lu_smem = 0;
     double *d_DX = nullptr, *d_QK = nullptr, *d_RMAX = nullptr, *d_WV = nullptr, *d_DVMAX = nullptr;
     int* d_BAD = nullptr;
     std::vector<void*> allocs;
@@ -620,6 +623,83 @@ struct cb_plan {
         return CB_OK;
     }
 };
+
+// Level schedule of the static-pivot LU for k_lu (see kernels.cuh).  Pivot k is in level
+// 1 + max(level of every earlier pivot m that updates row k or column k); the ops of one level only
+// conflict through accumulation into a common destination, and those stay on one warp in pivot order.
+struct LuSchedule {
+    std::vector<int4> ops;
+    std::vector<int> op_ptr, piv, piv_ptr, brow, brow_ptr;
+    int nlev = 0, nblev = 0;
+};
+
+static void build_lu_schedule(const cb::Symbolic& S, int W, LuSchedule& out) {
+    const int N = S.N, nnz = S.nnz_lu;
+    std::vector<int> level(N, 0), blevel(N, 0);
+    for (int m = 0; m < N; m++) {
+        for (int li = S.l_ptr[m]; li < S.l_ptr[m + 1]; li++) level[S.l_row[li]] = std::max(level[S.l_row[li]], level[m] + 1);
+        for (int uj = S.u_ptr[m]; uj < S.u_ptr[m + 1]; uj++) level[S.u_col[uj]] = std::max(level[S.u_col[uj]], level[m] + 1);
+    }
+    for (int k = N - 1; k >= 0; k--)
+        for (int uj = S.u_ptr[k]; uj < S.u_ptr[k + 1]; uj++) blevel[k] = std::max(blevel[k], blevel[S.u_col[uj]] + 1);
+    out.nlev = N ? *std::max_element(level.begin(), level.end()) + 1 : 0;
+    out.nblev = N ? *std::max_element(blevel.begin(), blevel.end()) + 1 : 0;
+    out.op_ptr.assign(1, 0); out.piv_ptr.assign(1, 0); out.brow_ptr.assign(1, 0);
+    for (int lv = 0; lv < out.nlev; lv++) {
+        // ops of this level grouped by destination
+        std::map<int, std::vector<int4>> by_dst;
+        std::vector<int> pivots;
+        for (int k = 0; k < N; k++) {
+            if (level[k] != lv) continue;
+            pivots.push_back(k);
+            const int lp = S.l_ptr[k], nL = S.l_ptr[k + 1] - lp, up = S.u_ptr[k], nU = S.u_ptr[k + 1] - up, pp = S.pair_ptr[k];
+            for (int li = 0; li < nL; li++) {
+                const int lpos = S.l_pos[lp + li];
+                for (int uj = 0; uj < nU; uj++) {
+                    const int dst = S.pair_dst[pp + li * nU + uj];
+                    by_dst[dst].push_back(make_int4(lpos, S.u_pos[up + uj], dst, S.diag_pos[k]));
+                }
+                const int dst = nnz + S.l_row[lp + li];
+                by_dst[dst].push_back(make_int4(lpos, nnz + k, dst, S.diag_pos[k]));
+            }
+        }
+        std::vector<std::pair<int, int>> groups;   // (size, dst), largest first onto the least loaded warp
+        for (auto& kv : by_dst) groups.push_back({(int)kv.second.size(), kv.first});
+        std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+        std::vector<std::vector<int4>> per(W);
+        for (auto& g : groups) {
+            int best = 0;
+            for (int w = 1; w < W; w++) if (per[w].size() < per[best].size()) best = w;
+            per[best].insert(per[best].end(), by_dst[g.second].begin(), by_dst[g.second].end());   // ascending pivot order
+        }
+        for (int w = 0; w < W; w++) {
+            out.ops.insert(out.ops.end(), per[w].begin(), per[w].end());
+            out.op_ptr.push_back((int)out.ops.size());
+            for (size_t q = w; q < pivots.size(); q += W) out.piv.push_back(S.diag_pos[pivots[q]]);
+            out.piv_ptr.push_back((int)out.piv.size());
+        }
+    }
+    for (int lv = 0; lv < out.nblev; lv++) {
+        std::vector<int> rows;
+        for (int k = 0; k < N; k++) if (blevel[k] == lv) rows.push_back(k);
+        std::sort(rows.begin(), rows.end(), [&](int x, int y) {
+            const int nx = S.u_ptr[x + 1] - S.u_ptr[x], ny = S.u_ptr[y + 1] - S.u_ptr[y];
+            return nx != ny ? nx > ny : x < y;
+        });
+        std::vector<std::vector<int>> per(W);
+        std::vector<int> load(W, 0);
+        for (int k : rows) {
+            int best = 0;
+            for (int w = 1; w < W; w++) if (load[w] < load[best]) best = w;
+            per[best].push_back(k);
+            load[best] += 1 + S.u_ptr[k + 1] - S.u_ptr[k];
+        }
+        for (int w = 0; w < W; w++) {
+            out.brow.insert(out.brow.end(), per[w].begin(), per[w].end());
+            out.brow_ptr.push_back((int)out.brow.size());
+        }
+    }
+}
 
 static int pick_group(const cb_circuit* c) {
     const char* env = std::getenv("CB_GROUP");
@@ -768,10 +848,65 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
     const int per_raw = S.nnz_lu + 3 * N + a.nwaves;
     {
         const char* env = std::getenv("CB_NEWTON");
-        p->gen = !env || std::string(env) == "gen";
+        p->gen = !env || std::string(env) == "gen" || std::string(env) == "lu";
         p->glob = env && std::string(env) == "glob";
     }
     if (p->gen) {
+        // solve kernel: shared-memory batched LU when the factors of 32 points fit one SM, else generated code
+        int max_smem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
+        const char* env = std::getenv("CB_NEWTON");
+        p->lu_smem = (size_t)(S.nnz_lu + 2 * N) * LU_PTS * sizeof(double);
+        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 1024;
+        p->lu = !(env && std::string(env) == "gen") && p->lu_smem + lu_static <= (size_t)max_smem;
+        if (p->lu) {
+            LuSchedule sch;
+            build_lu_schedule(S, LU_W, sch);
+            LArgs& la = p->la;
+            int4* dops; int* ti;
+            TRY(p->upload(&dops, sch.ops)); la.ops = dops;
+            TRY(p->upload(&ti, sch.op_ptr)); la.op_ptr = ti;
+            TRY(p->upload(&ti, sch.piv)); la.piv = ti;
+            TRY(p->upload(&ti, sch.piv_ptr)); la.piv_ptr = ti;
+            TRY(p->upload(&ti, sch.brow)); la.brow = ti;
+            TRY(p->upload(&ti, sch.brow_ptr)); la.brow_ptr = ti;
+            TRY(p->upload(&ti, S.u_col)); la.u_col = ti;
+            la.nlev = sch.nlev; la.nblev = sch.nblev;
+            if (std::getenv("CB_DEBUG"))
+                std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu smem=%zu\n", N, S.nnz_lu, sch.nlev,
+                             sch.nblev, sch.ops.size(), p->lu_smem);
+            {   // gather items, grouped by destination and balanced over the warps
+                std::map<int, std::vector<int4>> by_dst;
+                auto item = [](int src, int dst, double m) {
+                    long long bits;
+                    std::memcpy(&bits, &m, sizeof bits);
+                    return make_int4(src, dst, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
+                };
+                for (int e = 0; e < S.nnz_lu; e++)
+                    for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, c->a_mult[q]));
+                for (int i = 0; i < N; i++) {
+                    for (int q = c->ri_ptr[i]; q < c->ri_ptr[i + 1]; q++)
+                        by_dst[S.nnz_lu + S.row_to_step[i]].push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], -c->ri_mult[q]));
+                    for (int q = c->rq_ptr[i]; q < c->rq_ptr[i + 1]; q++)
+                        by_dst[S.nnz_lu + N + i].push_back(item(c->rq_src[q], S.nnz_lu + N + i, c->rq_mult[q]));
+                }
+                std::vector<std::pair<int, int>> groups;
+                for (auto& kv : by_dst) groups.push_back({(int)kv.second.size(), kv.first});
+                std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+                std::vector<std::vector<int4>> per(LU_W);
+                for (auto& g : groups) {
+                    int best = 0;
+                    for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
+                    per[best].insert(per[best].end(), by_dst[g.second].begin(), by_dst[g.second].end());
+                }
+                std::vector<int4> items;
+                std::vector<int> iptr(1, 0);
+                for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
+                TRY(p->upload(&dops, items)); la.items = dops;
+                TRY(p->upload(&ti, iptr)); la.item_ptr = ti;
+            }
+            CUDA_TRY(cudaFuncSetAttribute(k_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+        }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
         TRY(p->alloc(&p->d_QK, (size_t)N * B));
         TRY(p->alloc(&p->d_RMAX, (size_t)B));
@@ -1010,6 +1145,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
     void* sargs_ptr[] = {&sargs};
     CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV};
+    LArgs largs = p->la;
+    largs.n = a; largs.WV = p->d_WV; largs.DX = p->d_DX; largs.QK = p->d_QK; largs.RMAX = p->d_RMAX; largs.DVMAX = p->d_DVMAX;
+    largs.BAD = p->d_BAD;
     if (p->gen) {
         k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
         CUDA_TRY(cudaGetLastError());
@@ -1032,8 +1170,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
             if (timing) cudaEventRecord(e1, p->stream);
             if (p->gen) {
-                CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
-                k_control<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(cargs);
+                if (p->lu) k_lu<<<(unsigned)((B + LU_PTS - 1) / LU_PTS), LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
+                k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
                 launches++;
             } else if (p->glob) k_newton<1, true><<<ngrid, nthreads, 0, p->stream>>>(a);
             else switch (p->G) {

@@ -525,70 +525,76 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
     for (int w = 0; w < a.nwaves; w++) WV[(size_t)w * a.B + inst] = wave_value(a.waves[w], t, dcop, a.params, a.B, inst);
 }
 
-__global__ void __launch_bounds__(128) k_control(const CArgs c) {
+// Mapping: a CTA owns CTRL_PTS consecutive points; warp l of the CTA ("lane l" of each point) owns the
+// unknowns i = l, l + CTRL_LANES, ...  Every warp access is one contiguous row segment of 32 points.  The
+// scalar control logic is replicated across the lanes of a point (same inputs, same result); the two
+// cross-lane reductions (Newton convergence AND, LTE max) and the three hand-offs of rows between lanes go
+// through shared memory / __syncthreads.  One thread per point (the previous version) left the GPU with
+// 16 384 threads -- under one warp per SM sub-partition -- and ran at 5 % of HBM bandwidth.
+#define CTRL_PTS 32
+#define CTRL_LANES 8
+__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c) {
+    __shared__ double s_err[CTRL_LANES][CTRL_PTS];
+    __shared__ int s_conv[CTRL_LANES][CTRL_PTS];
     const NArgs& a = c.n;
     const long long B = a.B;
-    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= B) return;
-    int phase = a.ist[(size_t)IS_PHASE * B + inst];
-    if (phase == PH_DONE) return;
+    const int pt = threadIdx.x % CTRL_PTS, lane = threadIdx.x / CTRL_PTS;
+    const long long inst = (long long)blockIdx.x * CTRL_PTS + pt;
+    const bool inb = inst < B;
+    int phase = inb ? a.ist[(size_t)IS_PHASE * B + inst] : PH_DONE;
+    const bool live = phase != PH_DONE;
     const int N = a.N, NV = a.NV;
     const Opts& o = a.o;
-    // restrict-qualified views: lets the compiler batch the loads of the unrolled vector loops
-    double* __restrict__ X = a.X + inst;   double* __restrict__ XN = a.XN + inst; double* __restrict__ X1 = a.X1 + inst;
-    double* __restrict__ X2 = a.X2 + inst; double* __restrict__ XP = a.XP + inst; double* __restrict__ QN = a.QN + inst;
-    double* __restrict__ Q1 = a.Q1 + inst; double* __restrict__ QD = a.QD + inst; double* __restrict__ BETA = a.BETA + inst;
-    const double* __restrict__ DX = c.DX + inst; const double* __restrict__ QK = c.QK + inst;
+    const long long ii = inb ? inst : 0;   // dead threads keep in-bounds addresses, never dereferenced
+    double* __restrict__ X = a.X + ii;   double* __restrict__ XN = a.XN + ii; double* __restrict__ X1 = a.X1 + ii;
+    double* __restrict__ X2 = a.X2 + ii; double* __restrict__ XP = a.XP + ii; double* __restrict__ QN = a.QN + ii;
+    double* __restrict__ Q1 = a.Q1 + ii; double* __restrict__ QD = a.QD + ii; double* __restrict__ BETA = a.BETA + ii;
+    const double* __restrict__ DX = c.DX + ii; const double* __restrict__ QK = c.QK + ii;
     const unsigned char* __restrict__ mask = a.lte_mask;
-#define IST(k) a.ist[(size_t)(k) * B + inst]
-#define DST(k) a.dst[(size_t)(k) * B + inst]
+#define IST(k) a.ist[(size_t)(k) * B + ii]
+#define DST(k) a.dst[(size_t)(k) * B + ii]
 #define V(arr, i) arr[(size_t)(i) * B]
-    int it = IST(IS_IT), stage = IST(IS_STAGE), nh = IST(IS_NH), bpi = IST(IS_BPI), kstep = IST(IS_KSTEP);
-    int status = IST(IS_STATUS), hit_bp = IST(IS_HITBP), method = IST(IS_METHOD), np = IST(IS_NP);
-    int sidx = IST(IS_SIDX), nnewton = IST(IS_NNEWTON), nacc = IST(IS_NACC), nrej = IST(IS_NREJ);
-    int retry = IST(IS_RETRY);
-    double t = DST(DS_T), tnew = DST(DS_TNEW), h = DST(DS_H), h1 = DST(DS_H1), h2 = DST(DS_H2);
-    double hprop = DST(DS_HPROP), gshunt = DST(DS_GSHUNT), lim = DST(DS_LIM);
-    double alpha = a.alpha[inst];
-    const double rmax = c.RMAX[inst];
+    int it = 0, stage = 0, nh = 0, bpi = 0, kstep = 0, status = 0, hit_bp = 0, method = 0, np = 0, sidx = 0, nnewton = 0,
+        nacc = 0, nrej = 0, retry = 0;
+    double t = 0, tnew = 0, h = 0, h1 = 0, h2 = 0, hprop = 0, gshunt = 0, lim = 0, alpha = 0, rmax = 0, dvmax = 0;
+    int badpt = 0;
+    if (live) {
+        it = IST(IS_IT); stage = IST(IS_STAGE); nh = IST(IS_NH); bpi = IST(IS_BPI); kstep = IST(IS_KSTEP);
+        status = IST(IS_STATUS); hit_bp = IST(IS_HITBP); method = IST(IS_METHOD); np = IST(IS_NP);
+        sidx = IST(IS_SIDX); nnewton = IST(IS_NNEWTON); nacc = IST(IS_NACC); nrej = IST(IS_NREJ); retry = IST(IS_RETRY);
+        t = DST(DS_T); tnew = DST(DS_TNEW); h = DST(DS_H); h1 = DST(DS_H1); h2 = DST(DS_H2);
+        hprop = DST(DS_HPROP); gshunt = DST(DS_GSHUNT); lim = DST(DS_LIM);
+        alpha = a.alpha[ii]; rmax = c.RMAX[ii]; dvmax = c.DVMAX[ii]; badpt = c.BAD[ii];
+    }
+    const double alpha_old = alpha;
     bool finish = false, begin = false, newton_ok = false, newton_fail = false;
-    // what the fused history pass at the end has to do
     bool do_accept = false;        // shift history, QD/QN from this iterate
     int copy_mode = 0;             // 1: X <- 0, XN <- 0   2: XN <- X   3: X <- XN   4: QN <- QK, QD <- 0
+    int out_from = 0, out_to = 0, nh_out = 0;  // save points [out_from, out_to) are emitted from the NEW history
+    bool out_init = false;         // PH_TRAN_INIT: save points at t0 are emitted from XN
 
-    if (phase == PH_TRAN_INIT) {
-        copy_mode = 4;
-        while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
-            for (int k = 0; k < a.O; k++) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
-            sidx++;
-        }
-        if (status != 0) finish = true;
-        else { begin = true; phase = PH_TRAN; }
-    } else {
-        nnewton++;
-        const double dvmax = c.DVMAX[inst];
-        if (c.BAD[inst]) {
-            newton_fail = true;
-            status = 4;
-        } else {
-            lim = o.dv_max;
-            const double sc = dvmax > lim ? lim / dvmax : 1.0;
-            const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
-            int conv = (sc == 1.0) && (rmax <= restol);
-            // update pass; the LTE estimate is accumulated speculatively in the same sweep
-            double ratio = 0.0;
-            const bool want_lte = phase == PH_TRAN && !o.fixed_step && np >= 1;
-            if (want_lte) {
-                if (method == 0) ratio = h / (2.0 * h + h1);
-                else {
-                    const double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
-                    const double lc = method == 1 ? h * h * h / 12.0 : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
-                    ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
-                }
+    // ---- pass 1: Newton update of this lane's unknowns, convergence and LTE partials ------------
+    const bool solving = live && phase != PH_TRAN_INIT && !badpt;
+    const bool want_lte = solving && phase == PH_TRAN && !o.fixed_step && np >= 1;
+    double sc = 1.0, ratio = 0.0;
+    if (solving) {
+        lim = o.dv_max;
+        sc = dvmax > lim ? lim / dvmax : 1.0;
+        if (want_lte) {
+            if (method == 0) ratio = h / (2.0 * h + h1);
+            else {
+                const double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
+                const double lc = method == 1 ? h * h * h / 12.0 : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
+                ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
             }
-            double err = 0.0;
+        }
+    }
+    {
+        int conv = 1;
+        double err = 0.0;
+        if (solving) {
 #pragma unroll 4
-            for (int i = 0; i < N; i++) {
+            for (int i = lane; i < N; i += CTRL_LANES) {
                 const double dx = sc * V(DX, i);
                 const double xo = V(X, i), xn = xo + dx;
                 const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
@@ -599,101 +605,132 @@ __global__ void __launch_bounds__(128) k_control(const CArgs c) {
                     err = fmax(err, ratio * fabs(xn - V(XP, i)) / tol);
                 }
             }
-            it++;
-            if (conv) newton_ok = true;
-            else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
+        }
+        s_conv[lane][pt] = conv;
+        s_err[lane][pt] = err;
+    }
+    __syncthreads();   // reductions; also publishes the updated X rows to the other lanes of the point
+    int conv_all = 1;
+    double err = 0.0;
+#pragma unroll
+    for (int l = 0; l < CTRL_LANES; l++) { conv_all &= s_conv[l][pt]; err = fmax(err, s_err[l][pt]); }
 
-            if (phase == PH_TRAN && newton_ok) {
-                double fac = 2.0;
-                bool reject = false;
-                if (want_lte) {
-                    const int p = (method == 0 || np < 2) ? 1 : 2;
-                    fac = err > 0.0 ? 0.9 * pow(err, -1.0 / (p + 1)) : 2.0;
-                    fac = fmin(2.0, fmax(0.2, fac));
-                    if (err > 1.0) {
-                        reject = true;
-                        nrej++;
-                        hprop = h * fac;
-                        if (hprop < o.dt_min) { status = 3; finish = true; }
-                        else begin = true;
+    // ---- scalar control, replicated across the lanes of a point ------------------------------------
+    if (live) {
+        if (phase == PH_TRAN_INIT) {
+            copy_mode = 4;
+            out_init = true;
+            if (status != 0) finish = true;
+            else { begin = true; phase = PH_TRAN; }
+        } else {
+            nnewton++;
+            if (badpt) {
+                newton_fail = true;
+                status = 4;
+            } else {
+                const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
+                const int conv = conv_all && (sc == 1.0) && (rmax <= restol);
+                it++;
+                if (conv) newton_ok = true;
+                else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
+
+                if (phase == PH_TRAN && newton_ok) {
+                    double fac = 2.0;
+                    bool reject = false;
+                    if (want_lte) {
+                        const int p = (method == 0 || np < 2) ? 1 : 2;
+                        fac = err > 0.0 ? 0.9 * pow(err, -1.0 / (p + 1)) : 2.0;
+                        fac = fmin(2.0, fmax(0.2, fac));
+                        if (err > 1.0) {
+                            reject = true;
+                            nrej++;
+                            hprop = h * fac;
+                            if (hprop < o.dt_min) { status = 3; finish = true; }
+                            else begin = true;
+                        }
+                    }
+                    if (!reject) {
+                        nacc++;
+                        do_accept = true;
+                        h2 = h1; h1 = h;
+                        nh = nh + 1 < 2 ? nh + 1 : 2;
+                        nh_out = nh;
+                        t = tnew;
+                        kstep++;
+                        out_from = sidx;
+                        while (sidx < o.nsave && a.saveat[sidx] <= t + o.teps) sidx++;
+                        out_to = sidx;
+                        if (!o.fixed_step) {
+                            hprop = h * fac;
+                            if (hit_bp) {
+                                nh = 0;
+                                const double nb = (bpi + 1 < a.nbp) ? a.bp[bpi + 1] - t : o.t1 - t;
+                                hprop = fmin(hprop, 0.1 * fmin(h, nb > 0.0 ? nb : h));
+                                hprop = fmax(hprop, o.span * 1e-9);
+                            }
+                        }
+                        begin = true;
                     }
                 }
-                if (!reject) {
-                    nacc++;
-                    do_accept = true;
-                    const double told = t;
-                    const double oh1 = h1, oh2 = h2;
-                    h2 = h1; h1 = h;
-                    nh = nh + 1 < 2 ? nh + 1 : 2;
-                    t = tnew;
-                    kstep++;
-                    // outputs from the NEW history: x_n = X, x_{n-1} = old XN, x_{n-2} = old X1 (not yet shifted)
-                    while (sidx < o.nsave && a.saveat[sidx] <= t + o.teps) {
-                        const double ts = a.saveat[sidx];
-                        const bool exact = fabs(ts - t) <= o.teps;
-                        const int ni = o.method == 0 ? 1 : (nh < 2 ? nh : 2);
-                        for (int k = 0; k < a.O; k++) {
-                            const int u = a.outputs[k];
-                            const double xn = V(X, u);
-                            a.y_out[((size_t)k * o.nsave + sidx) * B + inst] =
-                                exact ? xn : poly_at(ni, ts, t, xn, h1, V(XN, u), h2, V(X1, u));
-                        }
-                        sidx++;
+            }
+            if (phase == PH_DC && (newton_ok || newton_fail)) {
+                bool dc_done = false;
+                it = 0;
+                if (stage < 0) {
+                    if (newton_ok) { dc_done = true; status = 0; }
+                    else {
+                        copy_mode = 1;
+                        stage = 0; gshunt = 1e-2; status = 0;
+                        if (o.gmin_steps == 0) gshunt = 0.0;
                     }
-                    (void)told; (void)oh1; (void)oh2;
-                    if (!o.fixed_step) {
-                        hprop = h * fac;
-                        if (hit_bp) {
-                            nh = 0;
-                            const double nb = (bpi + 1 < a.nbp) ? a.bp[bpi + 1] - t : o.t1 - t;
-                            hprop = fmin(hprop, 0.1 * fmin(h, nb > 0.0 ? nb : h));
-                            hprop = fmax(hprop, o.span * 1e-9);
-                        }
+                } else if (stage < o.gmin_steps) {
+                    copy_mode = newton_ok ? 2 : 3;
+                    stage++; gshunt *= 0.1; status = 0;
+                    if (stage == o.gmin_steps) gshunt = 0.0;
+                } else {
+                    dc_done = true;
+                    status = newton_ok ? 0 : 2;
+                }
+                if (dc_done) {
+                    gshunt = 0.0;
+                    if (o.dc_only) {
+                        for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[(size_t)k * B + inst] = V(X, a.outputs[k]);
+                        phase = PH_DONE;
+                        if (lane == 0) atomicAdd(a.done_count, 1);
+                    } else {
+                        copy_mode = 2;
+                        phase = PH_TRAN_INIT;
                     }
-                    begin = true;
+                }
+            } else if (phase == PH_TRAN && newton_fail && o.fixed_step && !retry) {
+                copy_mode = 3;
+                retry = 1; it = 0; status = 0;
+            } else if (phase == PH_TRAN && newton_fail) {
+                nrej++;
+                if (o.fixed_step) finish = true;
+                else {
+                    hprop = h / 8.0;
+                    if (hprop < o.dt_min) { status = 3; finish = true; }
+                    else { status = 0; begin = true; }
                 }
             }
         }
-        if (phase == PH_DC && (newton_ok || newton_fail)) {
-            bool dc_done = false;
-            it = 0;
-            if (stage < 0) {
-                if (newton_ok) { dc_done = true; status = 0; }
-                else {
-                    copy_mode = 1;
-                    stage = 0; gshunt = 1e-2; status = 0;
-                    if (o.gmin_steps == 0) gshunt = 0.0;
-                }
-            } else if (stage < o.gmin_steps) {
-                copy_mode = newton_ok ? 2 : 3;
-                stage++; gshunt *= 0.1; status = 0;
-                if (stage == o.gmin_steps) gshunt = 0.0;
-            } else {
-                dc_done = true;
-                status = newton_ok ? 0 : 2;
-            }
-            if (dc_done) {
-                gshunt = 0.0;
-                if (o.dc_only) {
-                    for (int k = 0; k < a.O; k++) a.y_out[(size_t)k * B + inst] = V(X, a.outputs[k]);
-                    phase = PH_DONE;
-                    atomicAdd(a.done_count, 1);
-                } else {
-                    copy_mode = 2;
-                    phase = PH_TRAN_INIT;
-                }
-            }
-        } else if (phase == PH_TRAN && newton_fail && o.fixed_step && !retry) {
-            copy_mode = 3;
-            retry = 1; it = 0; status = 0;
-        } else if (phase == PH_TRAN && newton_fail) {
-            nrej++;
-            if (o.fixed_step) finish = true;
-            else {
-                hprop = h / 8.0;
-                if (hprop < o.dt_min) { status = 3; finish = true; }
-                else { status = 0; begin = true; }
-            }
+    }
+    // ---- output sampling (reads rows owned by other lanes: X = x_n, XN = x_{n-1}, X1 = x_{n-2}, not yet shifted)
+    if (out_init) {
+        while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
+            for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
+            sidx++;
+        }
+    }
+    for (int sx = out_from; sx < out_to; sx++) {
+        const double ts = a.saveat[sx];
+        const bool exact = fabs(ts - t) <= o.teps;
+        const int ni = o.method == 0 ? 1 : nh_out;   // history order before a breakpoint hit resets nh
+        for (int k = lane; k < a.O; k += CTRL_LANES) {
+            const int u = a.outputs[k];
+            const double xn = V(X, u);
+            a.y_out[((size_t)k * o.nsave + sx) * B + inst] = exact ? xn : poly_at(ni, ts, t, xn, h1, V(XN, u), h2, V(X1, u));
         }
     }
     // ---- next step attempt: scalars first (mirrors the top of the oracle's step loop)
@@ -731,11 +768,11 @@ __global__ void __launch_bounds__(128) k_control(const CArgs c) {
             retry = 0;
         }
     }
-    // ---- one fused pass over the unknowns: history shift (accept), DC copies, beta + predictor (begin)
-    const double alpha_old = a.alpha[inst];
+    __syncthreads();   // output sampling has read the un-shifted history rows of other lanes
+    // ---- pass 2 over this lane's unknowns: history shift (accept), DC copies, beta + predictor (begin)
     if (do_accept || copy_mode || begin) {
 #pragma unroll 4
-        for (int i = 0; i < N; i++) {
+        for (int i = lane; i < N; i += CTRL_LANES) {
             double x = V(X, i), xn = V(XN, i), x1 = V(X1, i), x2 = V(X2, i), qn = V(QN, i), q1 = V(Q1, i), qd = V(QD, i);
             if (do_accept) {
                 const double qk = V(QK, i);
@@ -760,25 +797,203 @@ __global__ void __launch_bounds__(128) k_control(const CArgs c) {
             }
         }
     }
+    __syncthreads();   // the fill below reads XN rows written by other lanes
     if (finish) {
         for (; sidx < o.nsave; sidx++)
-            for (int k = 0; k < a.O; k++)
+            for (int k = lane; k < a.O; k += CTRL_LANES)
                 a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
         phase = PH_DONE;
-        atomicAdd(a.done_count, 1);
+        if (lane == 0) atomicAdd(a.done_count, 1);
     }
-    IST(IS_PHASE) = phase; IST(IS_IT) = it; IST(IS_STAGE) = stage; IST(IS_NH) = nh; IST(IS_BPI) = bpi;
-    IST(IS_KSTEP) = kstep; IST(IS_STATUS) = status; IST(IS_HITBP) = hit_bp; IST(IS_METHOD) = method;
-    IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
-    IST(IS_RETRY) = retry;
-    DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
-    DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim;
-    a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
-    a.active[inst] = phase != PH_DONE;
-    if (phase != PH_DONE) store_waves(a, c.WV, inst, phase != PH_TRAN, tnew);
+    if (live) {
+        if (lane == 0) {
+            IST(IS_PHASE) = phase; IST(IS_IT) = it; IST(IS_STAGE) = stage; IST(IS_NH) = nh; IST(IS_BPI) = bpi;
+            IST(IS_KSTEP) = kstep; IST(IS_STATUS) = status; IST(IS_HITBP) = hit_bp; IST(IS_METHOD) = method;
+            IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
+            IST(IS_RETRY) = retry;
+            DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
+            DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim;
+            a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
+            a.active[inst] = phase != PH_DONE;
+        }
+        if (phase != PH_DONE)
+            for (int w = lane; w < a.nwaves; w += CTRL_LANES)
+                c.WV[(size_t)w * B + inst] = wave_value(a.waves[w], tnew, phase != PH_TRAN, a.params, B, inst);
+    }
 #undef IST
 #undef DST
 #undef V
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_lu: assembly + batched static-pivot sparse LU + triangular solves, factors staged in shared memory.
+//
+// A CTA owns LU_PTS = 32 consecutive sweep points (lane = point, so every global access is one contiguous
+// 256-byte row segment and there is no divergence) and keeps their matrices in shared memory as
+// vals[entry][lane]: nnz(L+U) entries, the right-hand side in elimination-step order, the charges.  Its LU_W warps
+// split the work of each phase by *entry*, not by point:
+//   1. assembly: warp w gathers the matrix entries / residual rows w, w + LU_W, ... from the batch-
+//      interleaved device outputs (each value is read from HBM exactly once);
+//   2. elimination, level by level: pivots whose rows and columns receive no update from one another are
+//      one level (the internal nodes of all transistors, for instance).  Per level the warps first invert
+//      the level's pivots, then apply its update ops  vals[dst] -= (vals[l] * inv) * vals[u];  ops that
+//      hit the same destination are kept on one warp in ascending pivot order, so the factors are
+//      bit-identical to a sequential right-looking sweep.  The forward substitution is the same op stream
+//      with the right-hand side as an extra column;
+//   3. backward substitution, also level-scheduled on the U-row dependency DAG;
+//   4. dx, max|dv|, max|r| and the singular / non-finite flag.
+// The op lists are warp-uniform int4 streams read through L1; the code is a handful of small loops, so it
+// stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
+// instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
+#define LU_PTS 32
+#define LU_W 16
+#define LU_GU 8
+struct LArgs {
+    NArgs n;
+    const int4* ops;          // (l, u, dst, pivot diag) positions into vals
+    const int* op_ptr;        // [nlev * LU_W + 1]
+    const int* piv;           // diag positions
+    const int* piv_ptr;       // [nlev * LU_W + 1]
+    const int* brow;          // elimination steps
+    const int* brow_ptr;      // [nblev * LU_W + 1]
+    const int* u_col;         // column step of every U entry (parallel to u_pos)
+    const int4* items;        // (dev_out row, dst position, mult lo, mult hi)
+    const int* item_ptr;      // [LU_W + 1]
+    int nlev, nblev;
+    const double* WV;
+    double *DX, *QK, *RMAX, *DVMAX;
+    int* BAD;
+};
+
+__global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
+    extern __shared__ double vals_[];
+    __shared__ double s_red[2][LU_W][LU_PTS];
+    __shared__ int s_bad[LU_W][LU_PTS];
+    const NArgs& a = c.n;
+    const long long B = a.B;
+    const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
+    const long long inst0 = (long long)blockIdx.x * LU_PTS + lane;
+    const bool on = inst0 < B && a.active[inst0] != 0;
+    if (!__syncthreads_or(on)) return;
+    const long long inst = on ? inst0 : (long long)blockIdx.x * LU_PTS;   // idle lanes shadow an in-range point, never store
+    const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
+    double* __restrict__ vals = vals_ + lane;
+#define VL(i) vals[(size_t)(i) * LU_PTS]
+    const double alpha = a.alpha[inst], gshunt = a.dst[(size_t)DS_GSHUNT * B + inst];
+    const double* __restrict__ od = a.dev_out + inst;
+    const double* __restrict__ X = a.X + inst;
+    // ---- 1a. linear part (cached / uniform loads only): A = G_lin + alpha C_lin (+ gshunt on node diagonals),
+    //          F = -(f_lin + beta) in step order, Q = q_lin in row order
+    double* __restrict__ Fv = vals + (size_t)nnz * LU_PTS;
+    double* __restrict__ Qv = vals + (size_t)(nnz + N) * LU_PTS;
+    for (int e = w; e < nnz; e += LU_W) {
+        double v = 0.0;
+        const int lin = a.a_lin[e];
+        if (lin >= 0) {
+            const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            v = a.lin_g[li] + alpha * a.lin_c[li];
+        }
+        if (a.a_diag[e]) v += gshunt;
+        VL(e) = v;
+    }
+    for (int i = w; i < N; i += LU_W) {
+        double f = 0.0, q = 0.0;
+        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
+            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            const double xc = X[(size_t)a.rl_col[p] * B];
+            f += a.lin_g[li] * xc;
+            q += a.lin_c[li] * xc;
+        }
+        for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * c.WV[(size_t)a.rs_wave[p] * B + inst];
+        if (i < NV) f += gshunt * X[(size_t)i * B];
+        Fv[(size_t)a.row_to_step[i] * LU_PTS] = -(f + a.BETA[(size_t)i * B + inst]);
+        Qv[(size_t)i * LU_PTS] = q;
+    }
+    __syncthreads();
+    // ---- 1b. device outputs: one flat stream of (src row, dst, mult) items, LU_GU independent HBM loads in
+    //          flight per warp; all items of one destination are on one warp
+    {
+        int q0 = c.item_ptr[w];
+        const int q1 = c.item_ptr[w + 1];
+        for (; q0 < q1; q0 += LU_GU) {
+            int4 it[LU_GU];
+            double v[LU_GU];
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) it[u] = __ldg(c.items + min(q0 + u, q1 - 1));
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++)
+                if (q0 + u < q1) VL(it[u].y) += __hiloint2double(it[u].w, it[u].z) * v[u];
+        }
+    }
+    __syncthreads();
+    // ---- 1c. residual rows: b = -(f + alpha q + beta), charges out
+    double rmax = 0.0;
+    for (int i = w; i < N; i += LU_W) {
+        const double q = Qv[(size_t)i * LU_PTS];
+        double* bp = Fv + (size_t)a.row_to_step[i] * LU_PTS;
+        const double b = *bp - alpha * q;
+        *bp = b;
+        if (on) c.QK[(size_t)i * B + inst] = q;
+        rmax = fmax(rmax, fabs(b));
+    }
+    s_red[0][w][lane] = rmax;
+    int bad = 0;
+    __syncthreads();
+    // ---- 2. elimination by levels (fused forward substitution) ------------------------------------------
+    for (int lv = 0; lv < c.nlev; lv++) {
+        const int slot = lv * LU_W + w;
+        for (int p = c.piv_ptr[slot]; p < c.piv_ptr[slot + 1]; p++) {
+            const int dp = c.piv[p];
+            const double d = VL(dp);
+            bad |= !(fabs(d) > 0.0);
+            VL(dp) = 1.0 / d;
+        }
+        __syncthreads();
+        int q0 = c.op_ptr[slot];
+        const int q1 = c.op_ptr[slot + 1];
+        if (q0 < q1) {
+            int4 op = __ldg(c.ops + q0);
+            for (; q0 < q1; q0++) {
+                const int4 cur = op;
+                if (q0 + 1 < q1) op = __ldg(c.ops + q0 + 1);
+                const double l = VL(cur.x) * VL(cur.w);
+                VL(cur.z) -= l * VL(cur.y);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 3. backward substitution by levels: x_k = (b_k - sum_j u_kj x_j) * inv_k, in place in the rhs slots
+    for (int lv = 0; lv < c.nblev; lv++) {
+        const int slot = lv * LU_W + w;
+        for (int p = c.brow_ptr[slot]; p < c.brow_ptr[slot + 1]; p++) {
+            const int k = c.brow[p];
+            double acc = VL(nnz + k);
+            for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) acc -= VL(a.u_pos[u]) * VL(nnz + c.u_col[u]);
+            VL(nnz + k) = acc * VL(a.diag_pos[k]);
+        }
+        __syncthreads();
+    }
+    // ---- 4. update vector and norms ---------------------------------------------------------------------
+    double dvm = 0.0;
+    for (int i = w; i < N; i += LU_W) {
+        const double dx = VL(nnz + a.col_to_step[i]);
+        if (on) c.DX[(size_t)i * B + inst] = dx;
+        if (i < NV) dvm = fmax(dvm, fabs(dx));
+        bad |= !isfinite(dx);
+    }
+    s_red[1][w][lane] = dvm;
+    s_bad[w][lane] = bad;
+    __syncthreads();
+    if (w == 0 && on) {
+        double r = 0.0, d = 0.0;
+        int b = 0;
+#pragma unroll
+        for (int k = 0; k < LU_W; k++) { r = fmax(r, s_red[0][k][lane]); d = fmax(d, s_red[1][k][lane]); b |= s_bad[k][lane]; }
+        c.RMAX[inst] = r; c.DVMAX[inst] = d; c.BAD[inst] = b;
+    }
+#undef VL
 }
 
 __global__ void k_init_waves(const NArgs a, double* WV) {

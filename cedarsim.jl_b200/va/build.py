@@ -39,6 +39,8 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define VA_EVAL_END(NAME) }}
 #define CACHE_LD(s) cache_[s]
 #define CACHE_LDG(s) cache_[s]
+#define VA_RCP(x) (1.0 / (x))
+#define VA_SQRT(x) sqrt(x)
 #define VA_CHUNK(k)
 #define VT(k) v_[k]
 #define OUT_I(k, v) I_[k] = (v)

@@ -876,12 +876,12 @@ class _Compiler:
             self.count("div")
             if not b.d:
                 if not a.d:
-                    return self.emit_val("r", f"{ac} / {bc}", {})
-                inv = self.emit_val("r", f"1.0 / {bc}", {})
+                    return self.emit_val("r", f"{ac} * VA_RCP({bc})", {})
+                inv = self.emit_val("r", f"VA_RCP({bc})", {})
                 d = {kk: self._dmul(inv.c, v) for kk, v in a.d.items()}
                 self.count("mul", 1 + len(d))
                 return self.emit_val("r", f"{ac} * {inv.c}", d)
-            inv = self.emit_val("r", f"1.0 / {bc}", {})
+            inv = self.emit_val("r", f"VA_RCP({bc})", {})
             q = self.emit_val("r", f"{ac} * {inv.c}", {})
             d = {}
             for kk in keys:
@@ -929,7 +929,7 @@ class _Compiler:
                     g = self.emit_val("r", f"{float(n)!r} * {pm1}", {})
                     self.count("mul", 1 + len(a.d))
                     return self.emit_val("r", val.c, {kk: self._dmul(g.c, x) for kk, x in a.d.items()})
-                inv = self.emit_val("r", f"1.0 / {val.c}", {})
+                inv = self.emit_val("r", f"VA_RCP({val.c})", {})
                 self.count("div")
                 if not a.d:
                     return inv
@@ -987,14 +987,14 @@ class _Compiler:
             return chain(v, f"va_dlimexp({ac})")
         if fn == "ln":
             self.count("log"); self.count("div", 1 if has_d else 0)
-            return chain(self.emit_val("r", f"log({ac})", {}), f"1.0 / {ac}")
+            return chain(self.emit_val("r", f"log({ac})", {}), f"VA_RCP({ac})")
         if fn == "log":
             self.count("log"); self.count("div", 1 if has_d else 0)
-            return chain(self.emit_val("r", f"log10({ac})", {}), f"{_lit(1.0 / math.log(10.0))} / {ac}")
+            return chain(self.emit_val("r", f"log10({ac})", {}), f"{_lit(1.0 / math.log(10.0))} * VA_RCP({ac})")
         if fn == "sqrt":
             self.count("sqrt"); self.count("div", 1 if has_d else 0)
-            v = self.emit_val("r", f"sqrt({ac})", {})
-            return chain(v, f"0.5 / {v.c}")
+            v = self.emit_val("r", f"VA_SQRT({ac})", {})
+            return chain(v, f"0.5 * VA_RCP({v.c})")
         if fn == "sin":
             self.count("trig", 2 if has_d else 1)
             return chain(self.emit_val("r", f"sin({ac})", {}), f"cos({ac})")
@@ -1007,13 +1007,13 @@ class _Compiler:
             return chain(v, f"1.0 + {v.c} * {v.c}")
         if fn == "asin":
             self.count("trig")
-            return chain(self.emit_val("r", f"asin({ac})", {}), f"1.0 / sqrt(1.0 - {ac} * {ac})")
+            return chain(self.emit_val("r", f"asin({ac})", {}), f"VA_RCP(VA_SQRT(1.0 - {ac} * {ac}))")
         if fn == "acos":
             self.count("trig")
-            return chain(self.emit_val("r", f"acos({ac})", {}), f"-1.0 / sqrt(1.0 - {ac} * {ac})")
+            return chain(self.emit_val("r", f"acos({ac})", {}), f"-VA_RCP(VA_SQRT(1.0 - {ac} * {ac}))")
         if fn == "atan":
             self.count("trig"); self.count("div", 1 if has_d else 0)
-            return chain(self.emit_val("r", f"atan({ac})", {}), f"1.0 / (1.0 + {ac} * {ac})")
+            return chain(self.emit_val("r", f"atan({ac})", {}), f"VA_RCP(1.0 + {ac} * {ac})")
         if fn == "sinh":
             self.count("exp", 2)
             return chain(self.emit_val("r", f"sinh({ac})", {}), f"cosh({ac})")
@@ -1026,13 +1026,13 @@ class _Compiler:
             return chain(v, f"1.0 - {v.c} * {v.c}")
         if fn == "asinh":
             self.count("log")
-            return chain(self.emit_val("r", f"asinh({ac})", {}), f"1.0 / sqrt({ac} * {ac} + 1.0)")
+            return chain(self.emit_val("r", f"asinh({ac})", {}), f"VA_RCP(VA_SQRT({ac} * {ac} + 1.0))")
         if fn == "acosh":
             self.count("log")
-            return chain(self.emit_val("r", f"acosh({ac})", {}), f"1.0 / sqrt({ac} * {ac} - 1.0)")
+            return chain(self.emit_val("r", f"acosh({ac})", {}), f"VA_RCP(VA_SQRT({ac} * {ac} - 1.0))")
         if fn == "atanh":
             self.count("log")
-            return chain(self.emit_val("r", f"atanh({ac})", {}), f"1.0 / (1.0 - {ac} * {ac})")
+            return chain(self.emit_val("r", f"atanh({ac})", {}), f"VA_RCP(1.0 - {ac} * {ac})")
         if fn == "abs":
             if a.typ == "i":
                 return self.emit_val("i", f"abs({a.c})", {})
@@ -1094,7 +1094,7 @@ class _Compiler:
             v = self.emit_val("r", f"atan2({y.c}, {x.c})", {})
             if not (y.d or x.d):
                 return v
-            den = self.emit_val("r", f"1.0 / ({x.c} * {x.c} + {y.c} * {y.c})", {})
+            den = self.emit_val("r", f"VA_RCP({x.c} * {x.c} + {y.c} * {y.c})", {})
             d = {}
             for kk in sorted(set(y.d) | set(x.d)):
                 d[kk] = (f"({x.c} * {self._datom(y.d.get(kk, 0.0))} - {y.c} * {self._datom(x.d.get(kk, 0.0))})"
