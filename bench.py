@@ -32,8 +32,13 @@ sys.path.insert(0, ROOT)
 DFF_NODESET = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki=0.0, cki=0.7)
 T0, T1, NSAVE = 0.0, 6e-7, 1801
 POINTS_PER_GPU = 16384
-OPTS = dict(reltol=1e-3)
-WORKLOAD = "dff30-bsimcmg107-asap7 monte-carlo transient, adaptive trap, reltol 1e-3, 0..600ns, S=1801 (stand-in for GF180 DFF)"
+# SURVEY.md 8(d) config 3, adaptive mode: reltol 1e-4, abstol 1e-6 V / 1e-12 A.  Newton tolerance = 0.1 x the LTE
+# tolerance with the contraction-rate acceptance test (Sundials IDA, the reference's solver, uses 0.33 x and the same
+# test); the CPU arm runs the same options.  value_rounds is the engine's chord-iteration schedule.
+OPTS = dict(reltol=1e-4, vabstol=1e-6, iabstol=1e-12, nr_reltol=1e-5, nr_vabstol=1e-7, nr_iabstol=1e-13, nr_rate_test=1)
+ENGINE_OPTS = dict(value_rounds=3)
+WORKLOAD = ("dff30-bsimcmg107-asap7 monte-carlo transient, adaptive trap, reltol 1e-4 / 1e-6 V / 1e-12 A, Newton tol 0.1x LTE tol "
+            "with rate test, 0..600ns, S=1801 (stand-in for GF180 DFF)")
 
 
 def nodeset(fc):
@@ -152,7 +157,7 @@ def main():
     P = np.ascontiguousarray(P_all[:, rank * B:(rank + 1) * B])
     del P_all
     ts = np.linspace(T0, T1, NSAVE)
-    opts = engine.default_options(**OPTS)
+    opts = engine.default_options(**OPTS, **ENGINE_OPTS)
     plan.set_x0(nodeset(fc))
     plan.set_params(P)           # inputs resident in HBM before the timed region
     O = len(fc.outputs)
@@ -180,7 +185,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     tot = {"newton_iters": 0, "kernel_launches": 0, "eval_seconds": 0.0, "newton_seconds": 0.0, "solve_seconds": 0.0,
-           "steps_accepted": 0, "steps_rejected": 0, "rounds": 0}
+           "steps_accepted": 0, "steps_rejected": 0, "rounds": 0, "value_rounds": 0, "full_iters": 0, "evalv_seconds": 0.0,
+           "newtonv_seconds": 0.0}
     for _ in range(args.steps):
         st = step_resident()
         for k in tot:
@@ -237,14 +243,19 @@ def main():
         except OSError:
             pass
         ev, nw = tot["eval_seconds"], tot["newton_seconds"]
-        achieved = (tot["newton_iters"] * n_fets * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
+        # k_eval_* runs in the full rounds only: full_iters point-iterations x FETs device evaluations
+        achieved = (tot["full_iters"] * n_fets * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
         roofline = {"bound": "fp64", "kernel": "k_eval_bsimcmg107_*", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
                     "peak_source": "FP64 DFMA microbenchmark run live in this process (MEASURED_PEAKS.json has no FP64 figure; its "
-                                   f"hbm_gbs = {peaks.get('hbm_gbs')} is the denominator for the HBM-bound k_newton)",
-                    "flops_per_device_eval": flops_per_eval, "device_evals": tot["newton_iters"] * n_fets,
+                                   f"hbm_gbs = {peaks.get('hbm_gbs')} is the denominator for the HBM-bound k_lu / k_control)",
+                    "flops_per_device_eval": flops_per_eval, "device_evals": tot["full_iters"] * n_fets,
                     "kernel_seconds": ev, "share_of_step": ev / max(tot["solve_seconds"], 1e-30),
-                    "k_newton_seconds": nw, "k_newton_share": nw / max(tot["solve_seconds"], 1e-30)}
+                    "k_lu_control_seconds": nw, "k_lu_control_share": nw / max(tot["solve_seconds"], 1e-30),
+                    "value_rounds": {"rounds": tot["value_rounds"], "of_rounds": tot["rounds"],
+                                     "point_iterations": tot["newton_iters"] - tot["full_iters"],
+                                     "k_evalv_seconds": tot["evalv_seconds"], "k_lu_solve_control_seconds": tot["newtonv_seconds"],
+                                     "share_of_step": (tot["evalv_seconds"] + tot["newtonv_seconds"]) / max(tot["solve_seconds"], 1e-30)}}
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             threads = os.cpu_count() or 1

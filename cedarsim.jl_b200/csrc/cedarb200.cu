@@ -564,18 +564,24 @@ struct cb_plan {
     std::vector<unsigned> eval_threads;
     std::vector<size_t> eval_smem;
     std::vector<cudaKernel_t> k_setup, k_eval;
+    // value-only variants (null when a model has none; then every round is a full round)
+    std::vector<cudaKernel_t> k_setupv, k_evalv;
+    std::vector<unsigned> evalv_threads;
+    std::vector<size_t> evalv_smem;
+    std::vector<long long> cachev_off;
+    double* d_cachev = nullptr;
+    bool have_v = false;     // all models have a value-only variant and the solve kernel is k_lu
+    long long cachev_slots = 0;
+    bool setupv_valid = false;
     cudaKernel_t k_solve = nullptr;
-    bool gen = true;         // k_control + a separate solve kernel (default): k_lu, or the generated k_solve
-    bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu)
+    bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
+    int* d_dc_count = nullptr;
     double *d_DX = nullptr, *d_QK = nullptr, *d_RMAX = nullptr, *d_WV = nullptr, *d_DVMAX = nullptr;
     int* d_BAD = nullptr;
     std::vector<void*> allocs;
     NArgs na{};
-    int G = 8, gpc = 1;
-    bool glob = false;       // thread-per-point k_newton with the matrix in global scratch
-    size_t smem_bytes = 0;
     // device arrays
     double* d_params = nullptr;
     double* d_cache = nullptr;
@@ -701,12 +707,40 @@ static void build_lu_schedule(const cb::Symbolic& S, int W, LuSchedule& out) {
     }
 }
 
-static int pick_group(const cb_circuit* c) {
-    const char* env = std::getenv("CB_GROUP");
-    if (env) { int g = std::atoi(env); if (g == 4 || g == 8 || g == 16 || g == 32) return g; }
-    if (c->sym.nnz_lu <= 64) return 4;
-    if (c->sym.nnz_lu <= 256) return 8;
-    return 32;
+// Forward substitution with stored factors (value-only rounds): op (l_rk, rhs_k, rhs_r, diag_k) runs at the level
+// of its source k = 1 + max level of the rows that update rhs_k; ops into one destination stay on one warp in
+// ascending pivot order, so the result is bit-identical to the fused sweep of the full factorisation.
+static void build_fwd_schedule(const cb::Symbolic& S, int W, std::vector<int4>& ops, std::vector<int>& op_ptr, int& nlev) {
+    const int N = S.N, nnz = S.nnz_lu;
+    std::vector<int> level(N, 0);
+    for (int k = 0; k < N; k++)
+        for (int li = S.l_ptr[k]; li < S.l_ptr[k + 1]; li++) level[S.l_row[li]] = std::max(level[S.l_row[li]], level[k] + 1);
+    nlev = N ? *std::max_element(level.begin(), level.end()) + 1 : 0;
+    ops.clear();
+    op_ptr.assign(1, 0);
+    for (int lv = 0; lv < nlev; lv++) {
+        std::map<int, std::vector<int4>> by_dst;
+        for (int k = 0; k < N; k++) {
+            if (level[k] != lv) continue;
+            for (int li = S.l_ptr[k]; li < S.l_ptr[k + 1]; li++) {
+                const int dst = nnz + S.l_row[li];
+                by_dst[dst].push_back(make_int4(S.l_pos[li], nnz + k, dst, S.diag_pos[k]));
+            }
+        }
+        std::vector<std::pair<int, int>> groups;
+        for (auto& kv : by_dst) groups.push_back({(int)kv.second.size(), kv.first});
+        std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+        std::vector<std::vector<int4>> per(W);
+        for (auto& g : groups) {
+            int best = 0;
+            for (int w = 1; w < W; w++) if (per[w].size() < per[best].size()) best = w;
+            per[best].insert(per[best].end(), by_dst[g.second].begin(), by_dst[g.second].end());
+        }
+        for (int w = 0; w < W; w++) {
+            ops.insert(ops.end(), per[w].begin(), per[w].end());
+            op_ptr.push_back((int)ops.size());
+        }
+    }
 }
 
 extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** out) {
@@ -737,7 +771,7 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
             {   // block size and dynamic shared memory (cache ring) the generated kernel was compiled for
                 void* dmeta = nullptr;
                 size_t msz = 0;
-                int meta[2] = {128, 0};
+                int meta[4] = {128, 0, 0, 0};
                 CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_meta_" + m.name).c_str()));
                 CUDA_TRY(cudaMemcpy(meta, dmeta, sizeof meta, cudaMemcpyDeviceToHost));
                 p->eval_threads.push_back((unsigned)meta[0]);
@@ -747,6 +781,25 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
             }
             p->k_setup.push_back(ks);
             p->k_eval.push_back(ke);
+            cudaKernel_t ksv = nullptr, kev = nullptr;
+            int metav[4] = {128, 0, 0, 0};
+            if (cudaLibraryGetKernel(&kev, p->lib, ("k_evalv_" + m.name).c_str()) == cudaSuccess &&
+                cudaLibraryGetKernel(&ksv, p->lib, ("k_setupv_" + m.name).c_str()) == cudaSuccess) {
+                void* dmeta = nullptr;
+                size_t msz = 0;
+                CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_metav_" + m.name).c_str()));
+                CUDA_TRY(cudaMemcpy(metav, dmeta, sizeof metav, cudaMemcpyDeviceToHost));
+                if (metav[1] > 48 * 1024)
+                    CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributeMaxDynamicSharedMemorySize, metav[1]));
+            } else {
+                (void)cudaGetLastError();
+                ksv = kev = nullptr;
+            }
+            p->k_setupv.push_back(ksv);
+            p->k_evalv.push_back(kev);
+            p->evalv_threads.push_back((unsigned)metav[0]);
+            p->evalv_smem.push_back((size_t)metav[1]);
+            p->cachev_off.push_back(metav[2]);   // slots per instance for now; turned into offsets below
         }
     }
     NArgs& a = p->na;
@@ -817,12 +870,25 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
     TRY(p->alloc(&a.ist, (size_t)IS_COUNT * B));
     TRY(p->alloc(&a.active, (size_t)B));
     TRY(p->alloc(&p->d_cache, (size_t)std::max<long long>(1, c->total_cache) * B));
+    {   // value-only variants: usable when every model with instances has one
+        bool all = !c->insts.empty();
+        long long total = 0;
+        for (size_t m = 0; m < c->models.size(); m++) {
+            const long long per = std::max<long long>(1, p->cachev_off[m]);
+            p->cachev_off[m] = total;
+            if (c->model_insts[m].empty()) continue;
+            if (!p->k_evalv[m]) all = false;
+            total += (long long)c->model_insts[m].size() * per;
+        }
+        p->have_v = all;
+        p->cachev_slots = total;
+    }
     TRY(p->alloc(&p->d_dev_out, (size_t)std::max<long long>(1, c->total_out) * B));
     a.dev_out = p->d_dev_out;
     TRY(p->alloc(&p->d_xout, (size_t)std::max<size_t>(1, c->outputs.size()) * B));
     TRY(p->alloc(&p->d_done, 1));
     a.done_count = p->d_done;
-    CUDA_TRY(cudaMallocHost((void**)&p->h_done, sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_done, 2 * sizeof(int)));
     // per-model tables
     for (size_t m = 0; m < c->models.size(); m++) {
         const ModelH& M = c->models[m];
@@ -842,23 +908,16 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
         TRY(p->upload(&dt_, term)); TRY(p->upload(&dc_, pcol)); TRY(p->upload(&dv_, pval)); TRY(p->upload(&dg_, giv));
         p->d_term.push_back(dt_); p->d_par_col.push_back(dc_); p->d_par_val.push_back(dv_); p->d_given.push_back(dg_);
     }
-    // launch geometry of k_newton.  Two variants: (a) one thread per point with the matrix in a
-    // batch-interleaved global scratch (default for batches that fill the GPU), (b) G lanes per point
-    // with the matrix in shared memory (small batches, where per-point parallelism matters).
-    const int per_raw = S.nnz_lu + 3 * N + a.nwaves;
+    // solve kernel: shared-memory batched LU (k_lu) when the factors of LU_PTS points fit one SM, else the generated
+    // straight-line k_solve (no value-only rounds then)
     {
-        const char* env = std::getenv("CB_NEWTON");
-        p->gen = !env || std::string(env) == "gen" || std::string(env) == "lu";
-        p->glob = env && std::string(env) == "glob";
-    }
-    if (p->gen) {
-        // solve kernel: shared-memory batched LU when the factors of 32 points fit one SM, else generated code
         int max_smem = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
         const char* env = std::getenv("CB_NEWTON");
         p->lu_smem = (size_t)(S.nnz_lu + 2 * N) * LU_PTS * sizeof(double);
         const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 1024;
         p->lu = !(env && std::string(env) == "gen") && p->lu_smem + lu_static <= (size_t)max_smem;
+        if (!p->lu) p->have_v = false;
         if (p->lu) {
             LuSchedule sch;
             build_lu_schedule(S, LU_W, sch);
@@ -872,18 +931,28 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
             TRY(p->upload(&ti, sch.brow_ptr)); la.brow_ptr = ti;
             TRY(p->upload(&ti, S.u_col)); la.u_col = ti;
             la.nlev = sch.nlev; la.nblev = sch.nblev;
+            std::vector<int4> sops;
+            std::vector<int> sop_ptr;
+            int nslev = 0;
+            build_fwd_schedule(S, LU_W, sops, sop_ptr, nslev);
+            TRY(p->upload(&dops, sops)); la.sops = dops;
+            TRY(p->upload(&ti, sop_ptr)); la.sop_ptr = ti;
+            la.nslev = nslev;
             if (std::getenv("CB_DEBUG"))
-                std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu smem=%zu\n", N, S.nnz_lu, sch.nlev,
-                             sch.nblev, sch.ops.size(), p->lu_smem);
-            {   // gather items, grouped by destination and balanced over the warps
+                std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu fwd-levels=%d fwd-ops=%zu smem=%zu\n", N,
+                             S.nnz_lu, sch.nlev, sch.nblev, sch.ops.size(), nslev, sops.size(), p->lu_smem);
+            // gather items, grouped by destination and balanced over the warps; the value-only list holds the
+            // residual and charge rows only
+            auto item = [](int src, int dst, double m) {
+                long long bits;
+                std::memcpy(&bits, &m, sizeof bits);
+                return make_int4(src, dst, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
+            };
+            for (int pass = 0; pass < 2; pass++) {
                 std::map<int, std::vector<int4>> by_dst;
-                auto item = [](int src, int dst, double m) {
-                    long long bits;
-                    std::memcpy(&bits, &m, sizeof bits);
-                    return make_int4(src, dst, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
-                };
-                for (int e = 0; e < S.nnz_lu; e++)
-                    for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, c->a_mult[q]));
+                if (pass == 0)
+                    for (int e = 0; e < S.nnz_lu; e++)
+                        for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, c->a_mult[q]));
                 for (int i = 0; i < N; i++) {
                     for (int q = c->ri_ptr[i]; q < c->ri_ptr[i + 1]; q++)
                         by_dst[S.nnz_lu + S.row_to_step[i]].push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], -c->ri_mult[q]));
@@ -902,10 +971,13 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
                 std::vector<int4> items;
                 std::vector<int> iptr(1, 0);
                 for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
-                TRY(p->upload(&dops, items)); la.items = dops;
-                TRY(p->upload(&ti, iptr)); la.item_ptr = ti;
+                TRY(p->upload(&dops, items));
+                TRY(p->upload(&ti, iptr));
+                if (pass == 0) { la.items = dops; la.item_ptr = ti; } else { la.sitems = dops; la.sitem_ptr = ti; }
             }
-            CUDA_TRY(cudaFuncSetAttribute(k_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            la.LUF = nullptr;
         }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
         TRY(p->alloc(&p->d_QK, (size_t)N * B));
@@ -913,37 +985,9 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
         TRY(p->alloc(&p->d_DVMAX, (size_t)B));
         TRY(p->alloc(&p->d_BAD, (size_t)B));
         TRY(p->alloc(&p->d_WV, (size_t)std::max(1, a.nwaves) * B));
+        TRY(p->alloc(&p->d_dc_count, 1));
         a.scratch = nullptr;
-        a.sm_stride = per_raw;
-    } else if (p->glob) {
-        p->G = 1; p->gpc = 64; p->smem_bytes = 0;
-        a.sm_stride = per_raw;
-        TRY(p->alloc(&a.scratch, (size_t)per_raw * B));
-    } else {
-        p->G = pick_group(c);
-        int per = per_raw;
-        {
-            const int want = p->G / 2;  // stagger groups of one warp across shared-memory banks
-            while (p->G < 32 && (per % 16) != want) per++;
-        }
-        a.sm_stride = per;
-        a.scratch = nullptr;
-        const size_t per_bytes = (size_t)per * sizeof(double);
-        int max_smem = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
-        if (per_bytes > (size_t)max_smem)
-            return fail(CB_ERR_INVALID, "circuit too large for the shared-memory LU (nnz(L+U) = " + std::to_string(S.nnz_lu) + ")");
-        int gpc = (int)std::min<size_t>(256 / p->G, (size_t)max_smem / per_bytes);
-        // keep at least 2 CTAs per SM resident when the circuit is small
-        while (gpc > 4 && (size_t)gpc * per_bytes > (size_t)max_smem / 2) gpc--;
-        const int warp_groups = 32 / p->G;
-        if (gpc >= warp_groups) gpc -= gpc % warp_groups;
-        p->gpc = std::max(1, gpc);
-        p->smem_bytes = (size_t)p->gpc * per_bytes;
-#define SET_SMEM(GG)                                                                                     \
-    CUDA_TRY(cudaFuncSetAttribute(k_newton<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes))
-        if (p->G == 4) SET_SMEM(4); else if (p->G == 8) SET_SMEM(8); else if (p->G == 16) SET_SMEM(16); else SET_SMEM(32);
-#undef SET_SMEM
+        a.sm_stride = 0;
     }
 #undef TRY
     *out = p.release();
@@ -985,17 +1029,18 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     return CB_OK;
 }
 
-static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args) {
+static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false) {
     // layout must match struct VaArgs in va_prelude.h
     struct VaArgsH {
         long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out;
         const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
-        double temp_val; double gmin_val; int temp_col; int gmin_col;
+        double temp_val; double gmin_val; int temp_col; int gmin_col; int vround; int pad;
     };
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha; a->active = p->na.active;
-    a->cache = p->d_cache + (size_t)c->cache_off[m] * p->B;
+    a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->B : p->d_cache + (size_t)c->cache_off[m] * p->B;
+    a->vround = value_only ? 1 : 0; a->pad = 0;
     a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
     a->given = p->d_given[m];
@@ -1026,7 +1071,24 @@ static int run_setup(cb_plan* p, const cb_options* opt) {
         CUDA_TRY(cudaLaunchKernel((const void*)p->k_setup[m], grid, dim3(128), kargs, 0, p->stream));
     }
     p->setup_valid = true;
+    p->setupv_valid = false;
     p->last_temp = opt->temp; p->last_gmin = opt->gmin;
+    return CB_OK;
+}
+
+// value-only variants: their own bias-independent cache, filled on first use after a parameter change
+static int run_setupv(cb_plan* p, const cb_options* opt) {
+    const cb_circuit* c = p->c;
+    if (p->setupv_valid) return CB_OK;
+    for (size_t m = 0; m < c->models.size(); m++) {
+        if (c->model_insts[m].empty()) continue;
+        char args[256];
+        fill_va_args(p, m, opt, args, true);
+        void* kargs[] = {args};
+        dim3 grid((unsigned)((p->B + 127) / 128), (unsigned)c->model_insts[m].size());
+        CUDA_TRY(cudaLaunchKernel((const void*)p->k_setupv[m], grid, dim3(128), kargs, 0, p->stream));
+    }
+    p->setupv_valid = true;
     return CB_OK;
 }
 
@@ -1079,6 +1141,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     o.max_newton_dc = opt->max_newton_dc; o.max_newton_tran = opt->max_newton_tran;
     o.method = opt->method; o.fixed_step = opt->fixed_step; o.gmin_steps = opt->gmin_steps;
     o.skip_dc = opt->skip_dc; o.dc_only = dc_only ? 1 : 0;
+    o.rate_test = opt->nr_rate_test;
     o.nsave = dc_only ? 0 : nsave;
     o.nfixed = 0;
     if (!dc_only) {
@@ -1126,17 +1189,23 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
                                                                           p->have_x0 ? p->d_x0 : nullptr, p->x0_stride, o);
     CUDA_TRY(cudaGetLastError());
 
-    const unsigned ngrid = (unsigned)((B + p->gpc - 1) / p->gpc);
-    const unsigned nthreads = (unsigned)(p->gpc * p->G);
+    // Round schedule.  While any point is still in its DC phase every round is a FULL round (Newton far from the
+    // solution needs fresh Jacobians).  Afterwards each full round is followed by v_rounds VALUE-ONLY rounds: chord
+    // iterations with the stored factors and derivative-free device evaluations (~1/5 of the instructions).
+    // A step attempt always starts on a full round (points marked ACT_FULL idle through value-only rounds).
     const int poll = std::getenv("CB_POLL") ? std::max(1, std::atoi(std::getenv("CB_POLL"))) : 16;
     const bool timing = p->timing || std::getenv("CB_TIMING") != nullptr;
     std::vector<cudaEvent_t> evs;
-    double t_eval = 0, t_newton = 0;
-    int64_t rounds = 0, launches = 0;
+    std::vector<int> ev_kind;
+    double t_eval = 0, t_newton = 0, t_evalv = 0, t_newtonv = 0;
+    int64_t rounds = 0, vrounds = 0, launches = 0;
     const int64_t max_rounds = std::getenv("CB_MAX_ROUNDS") ? std::atoll(std::getenv("CB_MAX_ROUNDS")) : (int64_t)1 << 40;
-    char vargs[8][256];
+    char vargs[8][256], vargs_v[8][256];
     if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
-    for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs[m]);
+    for (size_t m = 0; m < c->models.size(); m++) {
+        fill_va_args(p, m, opt, vargs[m]);
+        if (p->d_cachev) fill_va_args(p, m, opt, vargs_v[m], true);
+    }
     struct SArgsH {
         long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA; const double* dev_out;
         const double* lin_g; const double* lin_c; const double* WV; const int* active; double* DX; double* QK; double* RMAX; int* BAD;
@@ -1144,17 +1213,35 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     } sargs{B, a.X, a.alpha, a.dst + (size_t)DS_GSHUNT * B, a.BETA, a.dev_out, a.lin_g, a.lin_c, p->d_WV, a.active,
             p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
     void* sargs_ptr[] = {&sargs};
-    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV};
+    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, 0, p->d_dc_count};
     LArgs largs = p->la;
     largs.n = a; largs.WV = p->d_WV; largs.DX = p->d_DX; largs.QK = p->d_QK; largs.RMAX = p->d_RMAX; largs.DVMAX = p->d_DVMAX;
     largs.BAD = p->d_BAD;
-    if (p->gen) {
-        k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
-        CUDA_TRY(cudaGetLastError());
+    k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
+    CUDA_TRY(cudaGetLastError());
+    {
+        const int dc0 = (o.skip_dc && !o.dc_only) ? 0 : (int)B;
+        CUDA_TRY(cudaMemcpyAsync(p->d_dc_count, &dc0, sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        p->h_done[1] = dc0;
     }
+    const int v_rounds = std::getenv("CB_VROUNDS") ? std::max(0, std::atoi(std::getenv("CB_VROUNDS"))) : std::max(0, opt->value_rounds);
+    const bool use_v = p->have_v && !dc_only && v_rounds > 0;
+    if (use_v && !p->la.LUF) {   // first use: value-only cache and factor storage
+        int rc2 = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * B);
+        if (rc2 == CB_OK) rc2 = p->alloc(&p->la.LUF, (size_t)c->sym.nnz_lu * B);
+        if (rc2 != CB_OK) return rc2;
+        largs.LUF = p->la.LUF;
+        for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs_v[m], true);
+    }
+    if (use_v) { int rc2 = run_setupv(p, opt); if (rc2 != CB_OK) return rc2; }
+    if (!use_v) largs.LUF = nullptr;
     bool done = false;
+    int since_full = 0;   // value-only rounds since the last full round
     while (!done && rounds < max_rounds) {
+        const bool dc_phase = p->h_done[1] > 0;
         for (int r = 0; r < poll; r++) {
+            const bool vround = use_v && !dc_phase && rounds > 0 && since_full < v_rounds;
+            since_full = vround ? since_full + 1 : 0;
             cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
             if (timing) {
                 cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
@@ -1162,42 +1249,42 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
-                void* kargs[] = {vargs[m]};
-                const unsigned eval_threads = p->eval_threads[m];
+                void* kargs[] = {vround ? vargs_v[m] : vargs[m]};
+                const unsigned eval_threads = vround ? p->evalv_threads[m] : p->eval_threads[m];
                 dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
-                CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(eval_threads), kargs, p->eval_smem[m], p->stream));
+                CUDA_TRY(cudaLaunchKernel((const void*)(vround ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
+                                          vround ? p->evalv_smem[m] : p->eval_smem[m], p->stream));
                 launches++;
             }
             if (timing) cudaEventRecord(e1, p->stream);
-            if (p->gen) {
-                if (p->lu) k_lu<<<(unsigned)((B + LU_PTS - 1) / LU_PTS), LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
-                k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
-                launches++;
-            } else if (p->glob) k_newton<1, true><<<ngrid, nthreads, 0, p->stream>>>(a);
-            else switch (p->G) {
-                case 4: k_newton<4, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                case 8: k_newton<8, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                case 16: k_newton<16, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-                default: k_newton<32, false><<<ngrid, nthreads, p->smem_bytes, p->stream>>>(a); break;
-            }
-            launches++;
-            if (timing) { cudaEventRecord(e2, p->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); }
+            if (p->lu) {
+                const unsigned g = (unsigned)((B + LU_PTS - 1) / LU_PTS);
+                if (vround) k_lu<true><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                else k_lu<false><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+            } else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
+            cargs.vround = vround ? 1 : 0;
+            k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
+            launches += 2;
+            if (timing) { cudaEventRecord(e2, p->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); ev_kind.push_back(vround); }
             rounds++;
+            vrounds += vround;
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(p->h_done, p->d_done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(p->h_done + 1, p->d_dc_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         CUDA_TRY(cudaStreamSynchronize(p->stream));
-        done = *p->h_done >= B;
+        done = p->h_done[0] >= B;
         if (timing) {
             for (size_t k = 0; k + 2 < evs.size(); k += 3) {
                 float ms1 = 0, ms2 = 0;
                 cudaEventElapsedTime(&ms1, evs[k], evs[k + 1]);
                 cudaEventElapsedTime(&ms2, evs[k + 1], evs[k + 2]);
-                t_eval += ms1 * 1e-3; t_newton += ms2 * 1e-3;
+                if (ev_kind[k / 3]) { t_evalv += ms1 * 1e-3; t_newtonv += ms2 * 1e-3; }
+                else { t_eval += ms1 * 1e-3; t_newton += ms2 * 1e-3; }
                 cudaEventDestroy(evs[k]); cudaEventDestroy(evs[k + 1]); cudaEventDestroy(evs[k + 2]);
             }
             evs.clear();
+            ev_kind.clear();
         }
     }
     CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
@@ -1210,6 +1297,12 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         stats->solve_seconds = ms * 1e-3;
         stats->rounds = rounds; stats->kernel_launches = launches + 2 + (int64_t)c->models.size();
         stats->eval_seconds = t_eval; stats->newton_seconds = t_newton;
+        stats->value_rounds = vrounds; stats->evalv_seconds = t_evalv; stats->newtonv_seconds = t_newtonv;
+        {
+            std::vector<int> nf((size_t)B);
+            CUDA_TRY(cudaMemcpy(nf.data(), a.ist + (size_t)IS_NFULL * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
+            for (long long i = 0; i < B; i++) stats->full_iters += nf[i];
+        }
         std::vector<int> cnt((size_t)3 * B);
         CUDA_TRY(cudaMemcpy(cnt.data(), a.ist + (size_t)IS_NNEWTON * B, (size_t)3 * B * sizeof(int), cudaMemcpyDeviceToHost));
         for (long long i = 0; i < B; i++) {

@@ -26,14 +26,28 @@ struct VaArgs {
     const uint8_t* given;        // [ndev][NPARAM]
     double temp_val; double gmin_val;
     int temp_col; int gmin_col;
+    int vround; int pad_;        // value-only round: points with active[] == 2 (they need a full round) are skipped
 };
 
-// Branch-free reciprocal and square root for the eval stream.  The compiler's own x / y and sqrt() carry a
-// rarely-taken slow path behind BSSY / BRA / BSYNC: every one of them redirects instruction fetch, and in
-// these ~25k-instruction straight-line kernels fetch is the bottleneck (BSYNC alone drew 19 % of the stall
-// samples).  MUFU seed (>= 20 bits) + the same Newton steps the compiler emits; inputs outside the normal
-// range fall back to the raw seed, which is already the IEEE answer there (inf, 0, nan).  Result within
-// 1 ulp of the correctly rounded one.
+// Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
+// x / y, sqrt(), exp(), log(), pow() carry rarely-taken slow paths behind BSSY / BRA / BSYNC, and every one of them
+// redirects instruction fetch in these ~20k-instruction straight-line kernels; (2) the library versions materialise
+// every polynomial coefficient with two move instructions (exp: 55 instructions, log: 80, pow: 255), which made
+// the transcendental expansions about half of the whole device evaluation.  The versions below read their
+// coefficients from constant memory (uniform loads, two doubles per instruction): exp ~30, log ~40, pow ~75
+// instructions.  Accuracy (checked against libm on the CPU with the same operation sequence, tests/test_vamath.py):
+// exp <= 1 ulp, log <= 2 ulp, pow relative error <= 1e-14 for |b ln a| <= 100, 1/x and sqrt <= 2 ulp.
+// Deviations from IEEE library behaviour, all outside what compact models evaluate: exp underflows to 0 below
+// -708.39 (no denormal results); pow(a, b) = exp(b log |a|) with the sign rule for integer b.
+VA_FN double va_rcp_normal(const double x) {   // |x| normal and 1/x normal
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    e = fma(e, e, e);
+    double r = fma(r0, e, r0);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 VA_FN double va_rcp(const double x) {
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
@@ -42,7 +56,7 @@ VA_FN double va_rcp(const double x) {
     double r = fma(r0, e, r0);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
-    return fabs(r) <= 1.7976931348623157e308 ? r : r0;
+    return fabs(r) <= 1.7976931348623157e308 ? r : r0;   // inputs outside the normal range: the seed is the IEEE answer
 }
 VA_FN double va_sqrt(const double x) {
     double y0;
@@ -57,12 +71,77 @@ VA_FN double va_sqrt(const double x) {
     const bool normal = x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308;
     return normal ? g : (x >= 0.0 ? (x < 1.0 ? 0.0 : x) : NAN);
 }
+// exp(x) = 2^n (1 + r + r^2 q(r)),  n = rint(x log2 e),  r = x - n ln2 (two-part ln2), |r| <= ln2 / 2;
+// q = degree-9 near-minimax fit of (e^r - 1 - r) / r^2 (interpolation at Chebyshev nodes, max error 1.3e-17)
+__constant__ double va_kexp[14] = {
+    1.4426950408889634, 6755399441055744.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+    2.5100395159429244017e-8, 2.7620101012098000228e-7, 2.7557268439678002354e-6, 0.000024801521269532121095,
+    0.00019841269863066695027, 0.0013888888917230723233, 0.0083333333333300592137, 0.04166666666662409382,
+    0.16666666666666667454, 0.50000000000000010231};
+VA_FN double va_exp(const double x) {
+    const double* __restrict__ K = va_kexp;
+    double t = fma(x, K[0], K[1]);
+    const int n = __double2loint(t);
+    t -= K[1];
+    double r = fma(-t, K[2], x);
+    r = fma(-t, K[3], r);
+    double p = K[4];
+    p = fma(p, r, K[5]); p = fma(p, r, K[6]); p = fma(p, r, K[7]); p = fma(p, r, K[8]); p = fma(p, r, K[9]);
+    p = fma(p, r, K[10]); p = fma(p, r, K[11]); p = fma(p, r, K[12]); p = fma(p, r, K[13]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= __hiloint2double((n + 1023) << 20, 0);
+    p = x < -708.39 ? 0.0 : p;                 // 2^n would be subnormal (also covers -inf)
+    return x > 709.78 ? INFINITY : p;          // NaN falls through as NaN
+}
+// log(x) = e ln2 + 2 atanh(f),  x = 2^e m,  m in [sqrt(1/2), sqrt(2)),  f = (m - 1) / (m + 1),  s = f^2,
+// 2 atanh(f) = 2 f + f s P(s);  P = degree-7 fit of 2 (atanh(sqrt s) / sqrt s - 1) / s on [0, 0.0295] (error 6e-20)
+__constant__ double va_klog[10] = {
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,
+    0.1308803485092755383, 0.13268638369266823879, 0.15386244737621666606, 0.18181795547521136235,
+    0.22222222392581045097, 0.28571428570799785031, 0.40000000000000883236, 0.66666666666666666463};
+VA_FN double va_log(const double x0) {
+    const double* __restrict__ K = va_klog;
+    const bool tiny = x0 < 2.2250738585072014e-308;
+    const double x = tiny ? x0 * 18014398509481984.0 : x0;    // subnormal inputs: scale by 2^54
+    int hi = __double2hiint(x);
+    int e = (hi >> 20) - (tiny ? 1023 + 54 : 1023);
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    const bool up = hi >= 0x3ff6a09f;                        // m >= sqrt(2): halve m
+    hi = up ? hi - 0x00100000 : hi;
+    e = up ? e + 1 : e;
+    const double m = __hiloint2double(hi, __double2loint(x));
+    const double f = (m - 1.0) * va_rcp_normal(m + 1.0);
+    const double s = f * f;
+    double p = K[2];
+    p = fma(p, s, K[3]); p = fma(p, s, K[4]); p = fma(p, s, K[5]); p = fma(p, s, K[6]); p = fma(p, s, K[7]);
+    p = fma(p, s, K[8]); p = fma(p, s, K[9]);
+    const double de = (double)e;
+    double r = fma(s * f, p, de * K[1]);
+    r = fma(2.0, f, r);
+    r = fma(de, K[0], r);
+    const bool ok = x0 > 0.0 && x0 <= 1.7976931348623157e308;
+    return ok ? r : (x0 == 0.0 ? -INFINITY : (x0 > 0.0 ? x0 : NAN));
+}
+VA_FN double va_pow(const double a, const double b) {
+    const double t = b * va_log(fabs(a));
+    const double r = va_exp(b == 0.0 ? 0.0 : t);         // pow(a, 0) = 1 for every a, including 0 and inf
+    // negative base: defined for integer exponents only, sign by parity
+    const double hb = 0.5 * b;
+    const bool b_int = rint(b) == b, b_odd = b_int && rint(hb) != hb;
+    return a < 0.0 ? (b_int ? (b_odd ? -r : r) : NAN) : r;
+}
 #ifdef VA_EXACT_DIV
 #define VA_RCP(x) (1.0 / (x))
 #define VA_SQRT(x) sqrt(x)
 #else
 #define VA_RCP(x) va_rcp(x)
 #define VA_SQRT(x) va_sqrt(x)
+#endif
+#ifndef VA_LIBM
+#define exp(x) va_exp(x)
+#define log(x) va_log(x)
+#define pow(a, b) va_pow(a, b)
 #endif
 
 VA_FN double va_limexp(double x) { return x < 80.0 ? exp(x) : exp(80.0) * (1.0 + x - 80.0); }
@@ -78,8 +157,11 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
 #define OUT_J(idx, k, l, g, c) out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * (c)
 
-#define VA_SETUP_BEGIN(NAME)                                                                     \
-    extern "C" __global__ void __launch_bounds__(128) k_setup_##NAME(VaArgs a) {                 \
+#define VA_SETUP_BEGIN(NAME) VA_SETUP_BEGIN_(k_setup_##NAME)
+#define VA_SETUPV_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupv_##NAME)
+#define VA_SETUPV_END(NAME) }
+#define VA_SETUP_BEGIN_(KERNEL)                                                                  \
+    extern "C" __global__ void __launch_bounds__(128) KERNEL(VaArgs a) {                         \
         const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;                 \
         if (inst >= a.B) return;                                                                 \
         const int dev = blockIdx.y;                                                              \
@@ -132,10 +214,15 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #ifndef VA_CONVOY
 #define VA_CONVOY 0
 #endif
-#if VA_CONVOY
+#if VA_CONVOY == 1 || VA_CONVOY == 2
 #define VA_CONVOY_SYNC() __syncthreads()
 #else
 #define VA_CONVOY_SYNC()
+#endif
+#if VA_CONVOY == 3
+#define VA_SYNCPT() __syncthreads()
+#else
+#define VA_SYNCPT()
 #endif
 #define VA_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define VA_CHUNK(k)                                                                              \
@@ -149,15 +236,22 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define CACHE_LD(s) ring_[((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS]
 #define CACHE_LDG(s) __ldg(cache_ + (size_t)(s) * a.B)
 
-#define VA_EVAL_BEGIN(NAME)                                                                      \
-    extern "C" __device__ int va_meta_##NAME[2] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8}; \
-    extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, VA_EVAL_MINBLOCKS) k_eval_##NAME(VaArgs a) {      \
+// value-only variant (k_evalv_*: currents and charges, no Jacobian; its own cache, see CompiledModel.source_v)
+#ifndef VA_EVALV_MINBLOCKS
+#define VA_EVALV_MINBLOCKS 5
+#endif
+#define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
+#define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
+#define VA_EVALV_END(NAME) VA_EVAL_END(NAME)
+#define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
+    extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, 0}; \
+    extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ double va_ring_[];                                                     \
         if (blockDim.x != VA_EVAL_THREADS) __trap();                                             \
         const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;                 \
         if (inst >= a.B) return;                                                                 \
-        if (!a.active[inst]) return;                                                             \
+        { const int act_ = a.active[inst]; if (act_ == 0 || (a.vround && act_ == 2)) return; }   \
         const int dev = blockIdx.y;                                                              \
         const double* __restrict__ cache_ = a.cache + ((size_t)dev * NCACHE) * a.B + inst;       \
         const double* ring_ = va_ring_ + threadIdx.x;                                            \

@@ -74,6 +74,9 @@ def cuda_source(models: Sequence) -> str:
                      f"#define NT {len(cm.terminals)}\n#define NPARAM {max(1, len(cm.params))}\n"
                      f"#define NCACHE {max(1, cm.ncache)}\n#define NOUT {2 * len(cm.terminals) + len(cm.jrow)}\n")
         parts.append(cm.source)
+        if getattr(cm, "source_v", ""):   # value-only variant: its own cache layout
+            parts.append(f"#undef NCACHE\n#define NCACHE {max(1, cm.ncache_v)}\n")
+            parts.append(cm.source_v)
     return "\n".join(parts)
 
 

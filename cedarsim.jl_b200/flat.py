@@ -113,6 +113,8 @@ class cb_options(C.Structure):
         ("dt_max", C.c_double),
         ("gmin_steps", C.c_int32),
         ("skip_dc", C.c_int32),
+        ("nr_rate_test", C.c_int32),
+        ("value_rounds", C.c_int32),
     ]
 
 
@@ -129,6 +131,10 @@ class cb_stats(C.Structure):
         ("d2h_seconds", C.c_double),
         ("eval_seconds", C.c_double),
         ("newton_seconds", C.c_double),
+        ("value_rounds", C.c_int64),
+        ("full_iters", C.c_int64),
+        ("evalv_seconds", C.c_double),
+        ("newtonv_seconds", C.c_double),
     ]
 
     def as_dict(self):

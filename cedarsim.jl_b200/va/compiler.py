@@ -33,6 +33,7 @@ from .parser import Function, Module, parse
 from .preproc import Preprocessor
 
 
+SYNC_EVERY_LINES = 48   # generated lines between VA_SYNCPT() markers
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
 CACHE_CHUNK_ROWS = 8
 CACHE_WINDOW = 16
@@ -363,6 +364,10 @@ class CompiledModel:
     census: Dict[str, int] = field(default_factory=dict)  # static op counts of the eval function
     exec_ops: List[int] = field(default_factory=list)     # (add, mul, div, special) on the executed path, see models.py
     param_defaults: Dict[str, float] = field(default_factory=dict)  # constant defaults of the module's parameters
+    # value-only variant (currents and charges, no derivatives) for the engine's chord iterations: its own setup /
+    # eval pair (VA_SETUPV_* / VA_EVALV_* macros) and cache layout; empty when the module uses ddx()
+    source_v: str = ""
+    ncache_v: int = 0
 
     @property
     def key(self) -> str:
@@ -371,9 +376,11 @@ class CompiledModel:
 
 class _Compiler:
     def __init__(self, mod: Module, name: str, const_params: Optional[Dict[str, float]] = None,
-                 runtime_params: Optional[Sequence[str]] = None):
+                 runtime_params: Optional[Sequence[str]] = None, no_deriv: bool = False, skip_funcs=()):
         self.mod = mod
         self.name = name
+        self.no_deriv = no_deriv          # value-only variant: probes carry no seeds, no Jacobian outputs
+        self.skip_funcs = set(skip_funcs)  # helper functions the full variant already defined
         # specialisation: parameters with compile-time values (a model card) are folded; only
         # `runtime_params` are read through PAR(); every other parameter takes its default
         self.const_params = None if const_params is None else {k.upper(): v for k, v in const_params.items()}
@@ -817,13 +824,13 @@ class _Compiler:
             if a == b:
                 return Val("r", "0.0", {}, 0.0)
             self.count("add")
-            d = {a: 1.0, b: -1.0}
+            d = {} if self.no_deriv else {a: 1.0, b: -1.0}
             d.pop(getattr(self, "drop_seed", None), None)
             return self.emit_val("r", f"VT({a}) - VT({b})", d)
         if len(idx) == 1:
             sign = 1.0 if (len(nodes) == 1 or nodes[0] not in ("0", "gnd")) else -1.0
             a = idx[0]
-            return self.emit_val("r", f"VT({a})" if sign > 0 else f"-VT({a})", {a: sign})
+            return self.emit_val("r", f"VT({a})" if sign > 0 else f"-VT({a})", {} if self.no_deriv else {a: sign})
         return Val("r", "0.0", {}, 0.0)
 
     def _bin_dyn(self, e) -> Val:
@@ -1049,6 +1056,8 @@ class _Compiler:
         fn, args = e[1], e[2]
         if fn in NOISE_FUNCS:
             return Val("r", "0.0", {}, 0.0)
+        if fn == "ddx" and self.no_deriv:
+            raise VACompileError("ddx() needs derivatives: no value-only variant for this module")
         if fn == "ddx":
             v = self.force(self.gd(args[0]))
             pr = args[1]
@@ -1568,7 +1577,7 @@ class _Compiler:
             if bad:
                 raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
-        self.drop_seed = self._pick_drop_seed(body)
+        self.drop_seed = None if self.no_deriv else self._pick_drop_seed(body)
         pruned, _ = prune_dead(body, set(), mod.functions)
         if pruned is not None:
             self.stmt(pruned)
@@ -1642,7 +1651,14 @@ class _Compiler:
         latest: Dict[int, int] = {}     # old slot -> its most recent stream position
         positions: Dict[int, List[int]] = {}
         out: List[str] = []
+        since_sync = 0
         for (a, b) in blocks:
+            # lock-step marker between top-level statements (a CTA barrier when the CUDA prelude enables VA_CONVOY 3):
+            # warps of one CTA that stay within a few hundred instructions of each other share instruction fetches
+            if since_sync >= SYNC_EVERY_LINES:
+                out.append("VA_SYNCPT();")
+                since_sync = 0
+            since_sync += b - a
             used: List[int] = []
             for l in E[a:b]:
                 for m in ld.finditer(l):
@@ -1802,15 +1818,18 @@ class _Compiler:
             done[fn] = self._c_function(self.mod.functions[fn])
             pending |= (self.used_funcs - before) - set(done)
         order = [fn for fn in self.mod.functions if fn in done]  # declaration order
+        self.defined_funcs = list(order)
         for fn in order:
-            L.append(done[fn])
-        L.append(f"VA_SETUP_BEGIN({self.name})")
+            if fn not in self.skip_funcs:
+                L.append(done[fn])
+        V = "V" if self.no_deriv else ""
+        L.append(f"VA_SETUP{V}_BEGIN({self.name})")
         for cn in sorted(self.static_vars):
             ct = "int" if self.types.get(cn) == "i" else "double"
             L.append(f"    {ct} {cn} = 0;")
         L.extend("    " + l for l in self.S)
-        L.append(f"VA_SETUP_END({self.name})")
-        L.append(f"VA_EVAL_BEGIN({self.name})")
+        L.append(f"VA_SETUP{V}_END({self.name})")
+        L.append(f"VA_EVAL{V}_BEGIN({self.name})")
         for cn in sorted(self.dyn_vars):
             if self.types.get(cn) == "i":
                 L.append(f"    int {cn} = 0;")
@@ -1820,12 +1839,20 @@ class _Compiler:
                     L.append(f"    double {cn}__d{kk} = 0.0;")
         L.extend("    " + l for l in self.E)
         L.extend("    " + l for l in out_lines)
-        L.append(f"VA_EVAL_END({self.name})")
+        L.append(f"VA_EVAL{V}_END({self.name})")
         return "\n".join(L) + "\n"
 
 
 def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None) -> CompiledModel:
-    return _Compiler(mod, name or mod.name, const_params, runtime_params).compile()
+    full = _Compiler(mod, name or mod.name, const_params, runtime_params)
+    cm = full.compile()
+    try:
+        vc = _Compiler(mod, name or mod.name, const_params, runtime_params, no_deriv=True, skip_funcs=full.defined_funcs)
+        cv = vc.compile()
+        cm.source_v, cm.ncache_v = cv.source, cv.ncache
+    except VACompileError:
+        pass
+    return cm
 
 
 def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,

@@ -321,8 +321,12 @@ struct Solver {
     // One Newton solve of  f(x,t) + alpha*q(x) + beta + gshunt*x_nodes = 0  starting at x.
     // On success x holds the converged iterate and qk the charges of the last evaluation.
     // Returns 0 ok, 1 max iterations, 4 singular / non-finite.
+    // Convergence: weighted update norm n_k = max_i |dx_i| / (nr_reltol max(|x_i|, |x_i + dx_i|) + atol_i) <= 1; with
+    // `use_rate` (transient) iterations after the first accept as soon as 10 x the estimate n_k rho / (1 - rho) of the
+    // error left after the update is <= 1, rho = n_k / n_{k-1} (the rate test of Sundials IDA, the reference's solver).
     int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
-               double gshunt, int maxit, double restol, std::vector<double>& qk) {
+               double gshunt, int maxit, double restol, std::vector<double>& qk, bool use_rate = false) {
+        double nrm_prev = 0.0;
         // voltage-step limit: only nonlinear (Verilog-A) devices need it; a purely linear circuit
         // converges in one full step whatever its voltage scale
         const double lim = in.fc->n_va_insts > 0 ? opt->dv_max : 1e300;
@@ -348,14 +352,20 @@ struct Solver {
             }
             if (!finite) return 4;
             double sc = dvmax > lim ? lim / dvmax : 1.0;
-            bool conv = (sc == 1.0) && (rmax <= restol);
+            double nrm = 0.0;
             for (int i = 0; i < N; i++) {
                 double dx = sc * rhs[i];
                 double xn = x[i] + dx;
-                if (std::fabs(dx) > opt->nr_reltol * std::max(std::fabs(xn), std::fabs(x[i])) + atol_nr(i))
-                    conv = false;
+                nrm = std::max(nrm, std::fabs(dx) / (opt->nr_reltol * std::max(std::fabs(xn), std::fabs(x[i])) + atol_nr(i)));
                 x[i] = xn;
             }
+            double est = nrm;
+            if (use_rate && it >= 1 && nrm < nrm_prev) {
+                const double rho = nrm / nrm_prev;
+                est = nrm * std::min(1.0, 10.0 * rho / (1.0 - rho));
+            }
+            nrm_prev = nrm;
+            const bool conv = (est <= 1.0) && (sc == 1.0) && (rmax <= restol);
             if (debug) {
                 int im = 0; double dm = 0;
                 for (int i = 0; i < N; i++) if (std::fabs(sc * rhs[i]) > dm) { dm = std::fabs(sc * rhs[i]); im = i; }
@@ -477,10 +487,11 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
             if (i < S.NV) lim = std::min(lim, fc->n_va_insts > 0 ? opt->dv_max : 1e300);
             x[i] = xn[i] + std::max(-lim, std::min(lim, d));
         }
-        int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);
+        const bool rate = opt->nr_rate_test != 0;
+        int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk, rate);
         if (rc != 0 && fixed) {  // fixed step cannot shrink: retry once from the flat guess x_n
             x = xn;
-            rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk);
+            rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk, rate);
         }
         if (rc != 0) {
             S.cnt.rejected++;

@@ -5,5 +5,5 @@ while read -r line; do
   [ -z "$line" ] && continue
   case "$line" in \#*) continue;; esac
   echo "== $line"
-  env $line CB_TIMING=1 python scripts/first_perf.py 16384 adaptive $SPAN 2>&1 | tail -1 | sed 's/.*rounds/rounds/'
+  env $line CB_TIMING=1 python scripts/first_perf.py 16384 adaptive $SPAN 2>&1 | tail -1 | sed 's/.* dev /dev /'
 done < "$1"

@@ -34,8 +34,12 @@ def run_dc_both(fc, models, P, x0=None, **kw):
     return (xg, xfg, sg, stg), (xo, xfo, so, sto)
 
 
-def run_tran_both(fc, models, P, t0, t1, saveat, x0=None, B=None, **kw):
+def run_tran_both(fc, models, P, t0, t1, saveat, x0=None, B=None, engine_only=None, **kw):
+    """engine_only: options given to the CUDA engine but not to the oracle (throughput options whose results
+    are checked against the oracle's plain Newton)."""
     eo, oo = both_options(**kw)
+    for k, v in (engine_only or {}).items():
+        setattr(eo, k, v)
     B = P.shape[1] if P is not None and P.size else (B or 1)
     c = engine.Circuit(fc, models)
     p = c.plan(B)

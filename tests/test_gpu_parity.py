@@ -105,6 +105,43 @@ def test_bsimcmg_inverter_tran_fixed(host_bsimcmg):
     assert_tran_close(yg, yo)
 
 
+def test_bsimcmg_inverter_tran_value_rounds(host_bsimcmg):
+    # throughput options: chord iterations in value-only rounds (+ IDA-style rate test) must reach the same
+    # solutions as the oracle's plain full Newton.  Plain acceptance test: same tolerance as above; with the rate
+    # test the charges of an accepted step lag the iterate by the last update, hence the looser bound.
+    fc, ms = circuits.inverter(host=host_bsimcmg, tscale=0.01)
+    vdd, nfin, ln = np.meshgrid(np.linspace(0.56, 0.84, 3), np.linspace(2, 6, 3), np.linspace(21e-9, 40e-9, 3), indexing="ij")
+    P = np.zeros((3, 27))
+    P[fc.param_names.index("vvdd.dc")] = vdd.ravel(order="F")
+    P[fc.param_names.index("xneg.nfin")] = nfin.ravel(order="F")
+    P[fc.param_names.index("xneg.l")] = ln.ravel(order="F")
+    ts = np.linspace(0, 4e-9, 81)
+    kw = dict(fixed_step=1, dt=2e-12)
+    (yg, sg, stg), (yo, so, _) = run_tran_both(fc, ms, P, 0.0, 4e-9, ts, engine_only=dict(value_rounds=1), **kw)
+    assert sg.max() == 0 and so.max() == 0
+    assert stg["value_rounds"] > 0 and 0 < stg["full_iters"] < stg["newton_iters"]
+    assert_tran_close(yg, yo)
+    (yg, sg, stg), _ = run_tran_both(fc, ms, P, 0.0, 4e-9, ts, engine_only=dict(value_rounds=1, nr_rate_test=1), **kw)
+    assert sg.max() == 0 and stg["value_rounds"] > 0
+    assert_tran_close(yg, yo, rtol=2e-5, atol=5e-6)
+
+
+def test_bsimcmg_dff_adaptive_throughput_options(host_bsimcmg):
+    # the bench configuration (bench.py): adaptive, Newton tolerance tied to the LTE tolerance, rate test, value rounds
+    fc, ms = circuits.dff(host=host_bsimcmg)
+    P = circuits.dff_mc_params(fc, 32)
+    x0 = x0_from(fc, DFF_NODESET)
+    ts = np.linspace(0, 6e-7, 61)
+    kw = dict(reltol=1e-4, vabstol=1e-6, iabstol=1e-12)
+    fast = dict(nr_reltol=1e-5, nr_vabstol=1e-7, nr_iabstol=1e-13, nr_rate_test=1, value_rounds=1)
+    (yg, sg, stg), (yo, so, sto) = run_tran_both(fc, ms, P, 0.0, 6e-7, ts, x0=x0, engine_only=fast, **kw)
+    assert sg.max() == 0 and so.max() == 0
+    # both runs are within their LTE tolerance of the true waveform; edges are steep, so compare away from them
+    settled = np.abs(np.gradient(yo, axis=1)).max(axis=(0, 2)) < 1e-3
+    assert np.abs(yg - yo)[:, settled, :].max() < 2e-3
+    assert stg["newton_iters"] < sto["newton_iters"]
+
+
 DFF_NODESET = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki=0.0, cki=0.7)
 
 
