@@ -557,7 +557,7 @@ struct DevBuf {
 
 struct cb_plan {
     cb_circuit* c = nullptr;
-    long long B = 0;
+    long long B = 0, Bpad = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaLibrary_t lib = nullptr;
@@ -869,7 +869,8 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
     TRY(p->alloc(&a.dst, (size_t)DS_COUNT * B));
     TRY(p->alloc(&a.ist, (size_t)IS_COUNT * B));
     TRY(p->alloc(&a.active, (size_t)B));
-    TRY(p->alloc(&p->d_cache, (size_t)std::max<long long>(1, c->total_cache) * B));
+    p->Bpad = (B + 127) / 128 * 128;   // the per-instance caches are laid out in blocks of 128 points (va_prelude.h)
+    TRY(p->alloc(&p->d_cache, (size_t)std::max<long long>(1, c->total_cache) * p->Bpad));
     {   // value-only variants: usable when every model with instances has one
         bool all = !c->insts.empty();
         long long total = 0;
@@ -915,7 +916,7 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
         const char* env = std::getenv("CB_NEWTON");
         p->lu_smem = (size_t)(S.nnz_lu + 2 * N) * LU_PTS * sizeof(double);
-        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 1024;
+        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 2048;
         p->lu = !(env && std::string(env) == "gen") && p->lu_smem + lu_static <= (size_t)max_smem;
         if (!p->lu) p->have_v = false;
         if (p->lu) {
@@ -1039,7 +1040,7 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha; a->active = p->na.active;
-    a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->B : p->d_cache + (size_t)c->cache_off[m] * p->B;
+    a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->Bpad : p->d_cache + (size_t)c->cache_off[m] * p->Bpad;
     a->vround = value_only ? 1 : 0; a->pad = 0;
     a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
@@ -1227,7 +1228,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     const int v_rounds = std::getenv("CB_VROUNDS") ? std::max(0, std::atoi(std::getenv("CB_VROUNDS"))) : std::max(0, opt->value_rounds);
     const bool use_v = p->have_v && !dc_only && v_rounds > 0;
     if (use_v && !p->la.LUF) {   // first use: value-only cache and factor storage
-        int rc2 = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * B);
+        int rc2 = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * p->Bpad);
         if (rc2 == CB_OK) rc2 = p->alloc(&p->la.LUF, (size_t)c->sym.nnz_lu * B);
         if (rc2 != CB_OK) return rc2;
         largs.LUF = p->la.LUF;
@@ -1258,7 +1259,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
             if (timing) cudaEventRecord(e1, p->stream);
             if (p->lu) {
-                const unsigned g = (unsigned)((B + LU_PTS - 1) / LU_PTS);
+                const unsigned g = (unsigned)((B + LU_WIN - 1) / LU_WIN);
                 if (vround) k_lu<true><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
                 else k_lu<false><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
             } else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));

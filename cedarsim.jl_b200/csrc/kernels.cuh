@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c
 // stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
 // instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
 #define LU_PTS 32
+#define LU_WIN 64
 #define LU_W 16
 #define LU_GU 8
 struct LArgs {
@@ -549,11 +550,31 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
     const NArgs& a = c.n;
     const long long B = a.B;
     const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
-    const long long inst0 = (long long)blockIdx.x * LU_PTS + lane;
-    const bool on = inst0 < B && (SOLVE ? a.active[inst0] == ACT_ANY : a.active[inst0] != ACT_DONE);
-    if (!__syncthreads_or(on)) return;
-    const long long inst = on ? inst0 : (long long)blockIdx.x * LU_PTS;   // idle lanes shadow an in-range point, never store
+    // A CTA owns a window of LU_WIN consecutive points and works through the ones that take part in this round in
+    // groups of LU_PTS (compaction: in value-only rounds, where 30-50 % of the points iterate, half of the groups
+    // disappear; with every point live the mapping is the identity).
+    __shared__ short s_list[LU_WIN];
+    __shared__ int s_cnt[LU_WIN / 32];
+    const long long base = (long long)blockIdx.x * LU_WIN;
+    bool on0 = false;
+    unsigned bal0 = 0;
+    if (threadIdx.x < LU_WIN) {
+        const long long i0 = base + threadIdx.x;
+        const int act = i0 < B ? a.active[i0] : ACT_DONE;
+        on0 = SOLVE ? act == ACT_ANY : act != ACT_DONE;
+        bal0 = __ballot_sync(0xffffffffu, on0);
+        if (lane == 0) s_cnt[w] = __popc(bal0);
+    }
+    __syncthreads();
+    int total = 0, before = 0;
+#pragma unroll
+    for (int q = 0; q < LU_WIN / 32; q++) { if (q < w) before += s_cnt[q]; total += s_cnt[q]; }
+    if (on0) s_list[before + __popc(bal0 & ((1u << lane) - 1u))] = (short)threadIdx.x;
+    __syncthreads();
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
+    for (int g0 = 0; g0 < total; g0 += LU_PTS) {
+    const bool on = g0 + lane < total;
+    const long long inst = base + s_list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
     double* __restrict__ vals = vals_ + lane;
 #define VL(i) vals[(size_t)(i) * LU_PTS]
     const double alpha = a.alpha[inst], gshunt = a.dst[(size_t)DS_GSHUNT * B + inst];
@@ -687,6 +708,8 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
 #pragma unroll
         for (int k = 0; k < LU_W; k++) { r = fmax(r, s_red[0][k][lane]); d = fmax(d, s_red[1][k][lane]); b |= s_bad[k][lane]; }
         c.RMAX[inst] = r; c.DVMAX[inst] = d; c.BAD[inst] = b;
+    }
+    __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
     }
 #undef VL
 }

@@ -151,12 +151,21 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define GIVEN(i) (given_[i] != 0)
 #define TEMP_K (temp_c_ + 273.15)
 #define GMIN_V gmin_
-#define CACHE_ST(s, v) cache_[(size_t)(s) * a.B] = (double)(v)
+#define CACHE_ST(s, v) cache_[(s) * VA_CACHE_BLK] = (double)(v)
 #define VT(k) vt_[k]
 #define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
 #define OUT_J(idx, k, l, g, c) out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * (c)
 
+// Cache layout: [device][block of VA_CACHE_BLK points][slot][VA_CACHE_BLK].  Inside one block of points a slot is a
+// compile-time byte offset (slot * 1 KB) from the thread's base pointer, so the ~250 cache accesses of an
+// evaluation need no 64-bit address arithmetic (the [slot][B] layout cost two integer instructions per access),
+// and a CTA streams one contiguous region of HBM.
+#define VA_CACHE_BLK 128
+VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, const long long inst) {
+    const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
+    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncache) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK);
+}
 #define VA_SETUP_BEGIN(NAME) VA_SETUP_BEGIN_(k_setup_##NAME)
 #define VA_SETUPV_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupv_##NAME)
 #define VA_SETUPV_END(NAME) }
@@ -170,7 +179,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
         const uint8_t* given_ = a.given + (size_t)dev * NPARAM;                                  \
         const double temp_c_ = a.temp_col >= 0 ? a.params[(size_t)a.temp_col * a.B + inst] : a.temp_val; \
         const double gmin_ = a.gmin_col >= 0 ? a.params[(size_t)a.gmin_col * a.B + inst] : a.gmin_val;   \
-        double* cache_ = (double*)a.cache + ((size_t)dev * NCACHE) * a.B + inst;                 \
+        double* cache_ = (double*)a.cache + va_cache_index(a.B, dev, NCACHE, inst);              \
         (void)gmin_; (void)temp_c_; (void)par_val_; (void)par_col_; (void)given_;
 #define VA_SETUP_END(NAME) }
 
@@ -200,41 +209,26 @@ VA_FN void va_cp8(unsigned dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 template <int ROWS, int STAGES, int NTHR>
-VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache, const size_t B) {
+VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         const int p = chunk * ROWS + r;
-        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + (size_t)p * B);
+        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + p * VA_CACHE_BLK);
     }
 }
-// The eval body is ~25k straight-line instructions (hundreds of KB of SASS, far beyond the 32 KB L1.5
-// instruction cache): a warp that runs alone streams all of it from L2.  A block-wide barrier at every
-// chunk marker keeps the warps of a CTA within one chunk of each other, so one instruction fetch
-// serves all of them.  (Threads of finished sweep points have exited; barriers count live threads.)
-#ifndef VA_CONVOY
-#define VA_CONVOY 0
-#endif
-#if VA_CONVOY == 1 || VA_CONVOY == 2
-#define VA_CONVOY_SYNC() __syncthreads()
-#else
-#define VA_CONVOY_SYNC()
-#endif
-#if VA_CONVOY == 3
-#define VA_SYNCPT() __syncthreads()
-#else
-#define VA_SYNCPT()
-#endif
+// (Experiments that did not pay and were removed: CTA-wide barriers at the chunk markers or every ~50 generated
+// lines, and a leader warp running one chunk ahead, to make the warps of a CTA share instruction fetches -- at
+// 128..640 threads per CTA none changed the instruction-cache request count; see DESIGN.md section 5.)
 #define VA_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define VA_CHUNK(k)                                                                              \
     {                                                                                            \
         if ((k) + VA_AHEAD < VA_NCHUNK)                                                          \
-            va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE, sbase_, cache_, (size_t)a.B); \
+            va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE, sbase_, cache_); \
         VA_COMMIT();                                                                             \
         asm volatile("cp.async.wait_group %0;" ::"n"(VA_AHEAD) : "memory");                      \
-        VA_CONVOY_SYNC();                                                                        \
     }
 #define CACHE_LD(s) ring_[((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS]
-#define CACHE_LDG(s) __ldg(cache_ + (size_t)(s) * a.B)
+#define CACHE_LDG(s) __ldg(cache_ + (s) * VA_CACHE_BLK)
 
 // value-only variant (k_evalv_*: currents and charges, no Jacobian; its own cache, see CompiledModel.source_v)
 #ifndef VA_EVALV_MINBLOCKS
@@ -243,30 +237,52 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
 #define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
 #define VA_EVALV_END(NAME) VA_EVAL_END(NAME)
+// Thread mapping with in-CTA compaction: a CTA owns VA_EVAL_THREADS consecutive sweep points; thread k takes the
+// k-th point of them that takes part in this round, and threads beyond the count exit before any work.  When all
+// points are live (full rounds) the mapping is the identity and every access is coalesced; in value-only rounds,
+// where typically 30-50 % of the points iterate, whole warps retire instead of running with most lanes idle.
 #define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
     extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, 0}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ double va_ring_[];                                                     \
+        __shared__ int va_cnt_[VA_EVAL_THREADS / 32];                                            \
+        __shared__ short va_list_[VA_EVAL_THREADS];                                              \
         if (blockDim.x != VA_EVAL_THREADS) __trap();                                             \
-        const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;                 \
-        if (inst >= a.B) return;                                                                 \
-        { const int act_ = a.active[inst]; if (act_ == 0 || (a.vround && act_ == 2)) return; }   \
+        long long inst;                                                                          \
+        {                                                                                        \
+            const long long base_ = (long long)blockIdx.x * VA_EVAL_THREADS;                     \
+            const long long i0_ = base_ + threadIdx.x;                                           \
+            const int act_ = i0_ < a.B ? a.active[i0_] : 0;                                      \
+            const bool on_ = act_ != 0 && !(a.vround && act_ == 2);                              \
+            const unsigned bal_ = __ballot_sync(0xffffffffu, on_);                               \
+            if ((threadIdx.x & 31) == 0) va_cnt_[threadIdx.x >> 5] = __popc(bal_);               \
+            __syncthreads();                                                                     \
+            int before_ = 0, total_ = 0;                                                         \
+            _Pragma("unroll") for (int q_ = 0; q_ < VA_EVAL_THREADS / 32; q_++) {                \
+                const int c_ = va_cnt_[q_];                                                      \
+                if (q_ < (int)(threadIdx.x >> 5)) before_ += c_;                                 \
+                total_ += c_;                                                                    \
+            }                                                                                    \
+            if (on_) va_list_[before_ + __popc(bal_ & ((1u << (threadIdx.x & 31)) - 1u))] = (short)threadIdx.x; \
+            __syncthreads();                                                                     \
+            if ((int)threadIdx.x >= total_) return;                                              \
+            inst = base_ + va_list_[threadIdx.x];                                                \
+        }                                                                                        \
         const int dev = blockIdx.y;                                                              \
-        const double* __restrict__ cache_ = a.cache + ((size_t)dev * NCACHE) * a.B + inst;       \
+        const double* __restrict__ cache_ = a.cache + va_cache_index(a.B, dev, NCACHE, inst);    \
         const double* ring_ = va_ring_ + threadIdx.x;                                            \
         const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + threadIdx.x);      \
         _Pragma("unroll") for (int c_ = 0; c_ < VA_AHEAD; c_++) {                                \
-            if (c_ < VA_NCHUNK) va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE, sbase_, cache_, (size_t)a.B); \
+            if (c_ < VA_NCHUNK) va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE, sbase_, cache_); \
             VA_COMMIT();                                                                         \
         }                                                                                        \
         const double alpha_ = a.alpha[inst];                                                     \
-        if (VA_CONVOY == 2 && (threadIdx.x >> 5) != 0) __syncthreads();                          \
         double* __restrict__ out_ = a.out + ((size_t)dev * NOUT) * a.B + inst;                   \
         double vt_[NT];                                                                          \
         _Pragma("unroll") for (int k_ = 0; k_ < NT; k_++) {                                      \
             const int n_ = a.term[dev * NT + k_];                                                \
             vt_[k_] = n_ < 0 ? 0.0 : a.x[(size_t)n_ * a.B + inst];                               \
         }
-#define VA_EVAL_END(NAME) if (VA_CONVOY == 2 && (threadIdx.x >> 5) == 0) __syncthreads(); }
+#define VA_EVAL_END(NAME) }
 )CUDA";

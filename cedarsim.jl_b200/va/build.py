@@ -42,7 +42,6 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define VA_RCP(x) (1.0 / (x))
 #define VA_SQRT(x) sqrt(x)
 #define VA_CHUNK(k)
-#define VA_SYNCPT()
 #define VT(k) v_[k]
 #define OUT_I(k, v) I_[k] = (v)
 #define OUT_Q(k, v) Q_[k] = (v)

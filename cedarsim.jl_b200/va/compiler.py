@@ -33,7 +33,6 @@ from .parser import Function, Module, parse
 from .preproc import Preprocessor
 
 
-SYNC_EVERY_LINES = 48   # generated lines between VA_SYNCPT() markers
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
 CACHE_CHUNK_ROWS = 8
 CACHE_WINDOW = 16
@@ -1651,14 +1650,7 @@ class _Compiler:
         latest: Dict[int, int] = {}     # old slot -> its most recent stream position
         positions: Dict[int, List[int]] = {}
         out: List[str] = []
-        since_sync = 0
         for (a, b) in blocks:
-            # lock-step marker between top-level statements (a CTA barrier when the CUDA prelude enables VA_CONVOY 3):
-            # warps of one CTA that stay within a few hundred instructions of each other share instruction fetches
-            if since_sync >= SYNC_EVERY_LINES:
-                out.append("VA_SYNCPT();")
-                since_sync = 0
-            since_sync += b - a
             used: List[int] = []
             for l in E[a:b]:
                 for m in ld.finditer(l):
