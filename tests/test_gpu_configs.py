@@ -1,0 +1,79 @@
+"""BASELINE.json configs 2 and 4 at their FULL sizes on the GPU (through the C ABI), checked by
+(i) a seeded subset against the CPU oracle at the parity tolerances and (ii) size-independent properties of the
+domain (all points converge, I-V monotone, zero current at zero bias, logic levels at the reference's sample times).
+Config 3 at full size is what bench.py runs (its `parity_check` key); GF180 / BSIM4 are not in the reference tree, so
+the same topologies run on BSIM-CMG 107 + ASAP7 cards."""
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import circuits, engine
+from cedarsim.jl_b200.flat import params_matrix
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config4_fet_iv_1m_bias_points(host_bsimcmg):
+    # ProductSweep(vg.dc = linspace(0, 0.9, 1024), vd.dc = linspace(0, 0.9, 1024)), column-major
+    fc, ms = circuits.fet_iv(host=host_bsimcmg)
+    n = 1024
+    vg, vd = np.meshgrid(np.linspace(0, 0.9, n), np.linspace(0, 0.9, n), indexing="ij")
+    P = params_matrix([vg.ravel(order="F"), vd.ravel(order="F")])
+    B = P.shape[1]
+    assert B == 1048576
+    plan = engine.Circuit(fc, ms).plan(B)
+    plan.set_params(P)
+    x, xf, st, stats = plan.dc()
+    plan.close()
+    assert st.max() == 0
+    idrain = -x[0].reshape((n, n), order="F")      # current into the drain = -I(Vd); [i_vg, i_vd]
+    assert np.abs(idrain[:, 0]).max() < 1e-10       # vd = 0: only gate-to-drain tunnelling current (pA)
+    assert idrain.min() > -1e-10
+    assert np.all(np.diff(idrain, axis=1) > -1e-12)  # monotone in vd at fixed vg
+    assert np.all(np.diff(idrain, axis=0) > -1e-12)  # monotone in vg at fixed vd
+    assert 1e-5 < idrain[-1, -1] < 1e-3              # on-current of a 3-fin ASAP7 nFET, order of 100 uA
+    # seeded subset against the oracle, DC tolerance 1e-9 V (currents: 1e-9 relative to the largest)
+    rng = np.random.default_rng(4)
+    sel = np.sort(rng.choice(B, 512, replace=False))
+    xo, xfo, so, _ = orc.dc(fc, np.ascontiguousarray(P[:, sel]))
+    assert so.max() == 0
+    nv = fc.n_nodes
+    assert np.abs(xf[:nv, sel] - xfo[:nv]).max() < 1e-9
+    assert np.abs(xf[nv:, sel] - xfo[nv:]).max() < 1e-12 + 1e-9 * np.abs(xfo[nv:]).max()
+
+
+def test_config2_inverter_product_sweep_65536(host_bsimcmg):
+    # vvdd.dc (16) x xneg.nfin (64, 1x..4x) x xneg.l (64, 1x..3x), fixed-step trapezoidal,
+    # dt = 50 ps, 8 000 steps over 400 ns, Q and D saved every 1 ns (S = 401)
+    fc, ms = circuits.inverter(host=host_bsimcmg)
+    vdd, nfin, ln = np.meshgrid(np.linspace(0.8 * 0.7, 1.2 * 0.7, 16), np.linspace(3.0, 12.0, 64), np.linspace(21e-9, 63e-9, 64),
+                                indexing="ij")
+    B = vdd.size
+    assert B == 65536
+    P = np.zeros((3, B))
+    P[fc.param_names.index("vvdd.dc")] = vdd.ravel(order="F")
+    P[fc.param_names.index("xneg.nfin")] = nfin.ravel(order="F")
+    P[fc.param_names.index("xneg.l")] = ln.ravel(order="F")
+    ts = np.linspace(0, 4e-7, 401)
+    kw = dict(fixed_step=1, dt=50e-12)
+    plan = engine.Circuit(fc, ms).plan(B)
+    plan.set_params(P)
+    y, st, stats = plan.tran(0.0, 4e-7, ts, engine.default_options(**kw))
+    plan.close()
+    assert st.max() == 0
+    assert stats["steps_accepted"] == 8000 * B
+    # logic levels at the reference's sample times (test/inverter.jl:40-50: D/Q at 0.5, 1.5, 2.5, 3.5e-7 s)
+    q, d = y[0], y[1]
+    vsup = P[fc.param_names.index("vvdd.dc")]
+    for t, d_high in ((0.4e-7, False), (1.0e-7, True), (2.0e-7, False), (3.5e-7, True)):
+        k = int(round(t / 4e-7 * 400))
+        assert np.abs(d[k] - (0.7 if d_high else 0.0)).max() < 1e-9
+        want_q = 0.0 * vsup if d_high else vsup
+        assert np.abs(q[k] - want_q).max() < 5e-3, (t, np.abs(q[k] - want_q).max())
+    # seeded subset against the oracle at the fixed-step parity tolerance
+    rng = np.random.default_rng(2)
+    sel = np.sort(rng.choice(B, 24, replace=False))
+    yo, so, _ = orc.tran(fc, 0.0, 4e-7, ts, params=np.ascontiguousarray(P[:, sel]), opts=orc.default_options(**kw), nthreads=8)
+    assert so.max() == 0
+    err = np.abs(y[:, :, sel] - yo)
+    assert np.all(err <= 1e-6 * np.abs(yo) + 1e-9), err.max()
