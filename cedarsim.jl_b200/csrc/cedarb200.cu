@@ -53,7 +53,7 @@ struct ModelH {
     std::string name;
     int nterm, nparam, ncache, nj;
     std::vector<int> jrow, jcol;
-    int nout() const { return 2 * nterm + nj; }
+    int nout() const { return 2 * nterm + 2 * nj; }   // I | Q | J = dI/dV + alpha dQ/dV | C = dQ/dV
 };
 struct VaInstH {
     int model;
@@ -80,6 +80,9 @@ struct cb_circuit {
     std::vector<uint8_t> a_diag;
     std::vector<int> ri_ptr, ri_src, rq_ptr, rq_src, rl_ptr, rl_col, rl_lin, rs_ptr, rs_wave;
     std::vector<double> ri_mult, rq_mult, rs_coef;
+    // charge-update items: q_row += mult * C[src row of dev_out] * dx[col]
+    std::vector<int> cq_row, cq_src, cq_col;
+    std::vector<double> cq_mult;
     std::vector<LinContrib> lin_contrib;
     int nlin = 0;
     bool lin_swept = false;
@@ -292,6 +295,8 @@ static int build_tables(cb_circuit* c) {
             const int r = v.term[m.jrow[j]], col = v.term[m.jcol[j]];
             if (r < 0 || col < 0) continue;
             ent_src[S.pos_of_orig.at({r, col})].push_back({(int)(base + 2 * m.nterm + j), v.mult});
+            c->cq_row.push_back(r); c->cq_src.push_back((int)(base + 2 * m.nterm + m.nj + j)); c->cq_col.push_back(col);
+            c->cq_mult.push_back(v.mult);
         }
     }
     auto flatten = [](const std::vector<std::vector<std::pair<int, double>>>& src, std::vector<int>& ptr,
@@ -528,6 +533,7 @@ extern "C" int cb_circuit_compile(cb_circuit* c, const char* cache_dir, double* 
     if (!c) return fail(CB_ERR_INVALID, "null circuit");
     auto t0 = std::chrono::steady_clock::now();
     c->lin_contrib.clear();
+    c->cq_row.clear(); c->cq_src.clear(); c->cq_col.clear(); c->cq_mult.clear();
     c->lin_swept = false;
     int rc = build_tables(c);
     if (rc != CB_OK) return rc;
@@ -976,6 +982,27 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
                 TRY(p->upload(&ti, iptr));
                 if (pass == 0) { la.items = dops; la.item_ptr = ti; } else { la.sitems = dops; la.sitem_ptr = ti; }
             }
+            {   // charge-update items, all items of one row on one warp
+                std::map<int, std::vector<int>> by_row;
+                for (size_t q = 0; q < c->cq_row.size(); q++) by_row[c->cq_row[q]].push_back((int)q);
+                std::vector<std::pair<int, int>> groups;
+                for (auto& kv : by_row) groups.push_back({(int)kv.second.size(), kv.first});
+                std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+                std::vector<std::vector<int4>> per(LU_W);
+                for (auto& g : groups) {
+                    int best = 0;
+                    for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
+                    for (int q : by_row[g.second])
+                        per[best].push_back(make_int4(c->cq_src[q], S.nnz_lu + N + c->cq_row[q], S.nnz_lu + S.col_to_step[c->cq_col[q]], q));
+                }
+                std::vector<int4> items;
+                std::vector<int> iptr(1, 0);
+                for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
+                double* dm;
+                TRY(p->upload(&dops, items)); la.citems = dops;
+                TRY(p->upload(&ti, iptr)); la.citem_ptr = ti;
+                TRY(p->upload(&dm, c->cq_mult)); la.cmult = dm;
+            }
             CUDA_TRY(cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
             CUDA_TRY(cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
             la.LUF = nullptr;
@@ -1142,7 +1169,11 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     o.max_newton_dc = opt->max_newton_dc; o.max_newton_tran = opt->max_newton_tran;
     o.method = opt->method; o.fixed_step = opt->fixed_step; o.gmin_steps = opt->gmin_steps;
     o.skip_dc = opt->skip_dc; o.dc_only = dc_only ? 1 : 0;
-    o.rate_test = opt->nr_rate_test;
+    o.rate_test = p->lu ? opt->nr_rate_test : 0;   // needs the charge update of k_lu
+    // e_1 / tol ~ (e_0 / tol)^2 tol / (2 Vt): kappa = 20/V x (Newton tolerance of a 1 V signal); learnt values
+    // never drop below 1/30 of it
+    o.kappa0 = 20.0 * (opt->nr_reltol + opt->nr_vabstol);
+    o.kappa_floor = o.kappa0 / 30.0;
     o.nsave = dc_only ? 0 : nsave;
     o.nfixed = 0;
     if (!dc_only) {

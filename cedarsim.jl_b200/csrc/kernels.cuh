@@ -24,7 +24,7 @@ enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3 };
 enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HITBP, IS_METHOD, IS_NP,
        IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_NFULL, IS_COUNT };
 // double per-point state rows
-enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_NRM, DS_COUNT };
+enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_NRM, DS_KAPPA, DS_COUNT };
 // a.active[]: 0 = finished, 1 = mid-attempt (runs in every round), 2 = needs a full round (DC iterations and the
 // first iteration of a transient step attempt: fresh Jacobian), idles through value-only rounds
 enum { ACT_DONE = 0, ACT_ANY = 1, ACT_FULL = 2 };
@@ -42,7 +42,7 @@ struct WaveDev {
 
 struct Opts {
     double reltol, vabstol, iabstol, nr_reltol, nr_vabstol, nr_iabstol, dc_abstol, dv_max;
-    double dt, dt_min, dt_max, t0, t1, teps, span;
+    double dt, dt_min, dt_max, t0, t1, teps, span, kappa0, kappa_floor;
     int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only, rate_test;
     long long nfixed, nsave;
 };
@@ -167,7 +167,11 @@ __device__ __forceinline__ double poly_at(int nh, double tt, double tn, double x
 // Newton convergence (transient): weighted update norm  n_k = max_i |dx_i| / (nr_reltol max(|x_i|,|x_i + dx_i|) + atol_i).
 // Converged when n_k <= 1.  With cb_options.nr_rate_test, iterations after the first also use the observed contraction
 // rho = n_k / n_{k-1} (as Sundials IDA does, the solver behind the reference's tran!): the error left after this
-// update is about n_k rho / (1 - rho), and the attempt converges when 10 x that estimate is <= 1.  The DC operating
+// update is about n_k rho / (1 - rho), and the attempt converges when 3 x that estimate is <= 1.  Level 2 also
+// accepts the first update of an attempt when 3 kappa n_1^2 <= 1: a full Newton step converges quadratically, and
+// kappa = n_2 / n_1^2 is measured per point whenever a second iteration is taken (start value and floor from the
+// strongest nonlinearity a semiconductor device has, exp(v / Vt): e_1 ~ e_0^2 / (2 Vt)).  Both rely on the charges
+// handed over by k_lu being those of the updated iterate, q(x) + C dx.  The DC operating
 // point keeps the plain test n_k <= 1 together with the residual tolerance of CedarDCOp.
 struct CArgs {
     NArgs n;
@@ -190,7 +194,7 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 // 16 384 threads -- under one warp per SM sub-partition -- and ran at 5 % of HBM bandwidth.
 #define CTRL_PTS 32
 #define CTRL_LANES 8
-__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c) {
+__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, 3) k_control(const CArgs c) {
     __shared__ double s_err[CTRL_LANES][CTRL_PTS];
     __shared__ double s_nrm[CTRL_LANES][CTRL_PTS];
     const NArgs& a = c.n;
@@ -214,14 +218,14 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c
 #define V(arr, i) arr[(size_t)(i) * B]
     int it = 0, stage = 0, nh = 0, bpi = 0, kstep = 0, status = 0, hit_bp = 0, method = 0, np = 0, sidx = 0, nnewton = 0,
         nacc = 0, nrej = 0, retry = 0;
-    double t = 0, tnew = 0, h = 0, h1 = 0, h2 = 0, hprop = 0, gshunt = 0, lim = 0, alpha = 0, rmax = 0, dvmax = 0, nrm_prev = 0;
+    double t = 0, tnew = 0, h = 0, h1 = 0, h2 = 0, hprop = 0, gshunt = 0, lim = 0, alpha = 0, rmax = 0, dvmax = 0, nrm_prev = 0, kappa = 0;
     int badpt = 0;
     if (live) {
         it = IST(IS_IT); stage = IST(IS_STAGE); nh = IST(IS_NH); bpi = IST(IS_BPI); kstep = IST(IS_KSTEP);
         status = IST(IS_STATUS); hit_bp = IST(IS_HITBP); method = IST(IS_METHOD); np = IST(IS_NP);
         sidx = IST(IS_SIDX); nnewton = IST(IS_NNEWTON); nacc = IST(IS_NACC); nrej = IST(IS_NREJ); retry = IST(IS_RETRY);
         t = DST(DS_T); tnew = DST(DS_TNEW); h = DST(DS_H); h1 = DST(DS_H1); h2 = DST(DS_H2);
-        hprop = DST(DS_HPROP); gshunt = DST(DS_GSHUNT); lim = DST(DS_LIM); nrm_prev = DST(DS_NRM);
+        hprop = DST(DS_HPROP); gshunt = DST(DS_GSHUNT); lim = DST(DS_LIM); nrm_prev = DST(DS_NRM); kappa = DST(DS_KAPPA);
         alpha = a.alpha[ii]; rmax = c.RMAX[ii]; dvmax = c.DVMAX[ii]; badpt = c.BAD[ii];
     }
     const double alpha_old = alpha;
@@ -288,13 +292,21 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c
                 status = 4;
             } else {
                 const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
-                double est = nrm;   // bound on the weighted error left after this update
-                if (o.rate_test && phase == PH_TRAN && it >= 1 && nrm < nrm_prev) {
-                    // safety 10 keeps the error actually left an order below the tolerance, like the plain test
-                    // does; a chord update (value-only round) contracts half as fast as the ratio observed
-                    // across the preceding Newton update suggests (e_2 ~ 2 (e_1 / e_0) e_1)
-                    const double rho = nrm / nrm_prev;
-                    est = nrm * fmin(1.0, (c.vround ? 20.0 : 10.0) * rho / (1.0 - rho));
+                double est = nrm;   // estimate of the weighted error left after this update
+                if (o.rate_test && phase == PH_TRAN) {
+                    if (it == 0) {
+                        // level 2: the first (full Newton) update of an attempt leaves ~ kappa n_1^2 (quadratic
+                        // convergence; kappa learnt from the attempts that did take a second iteration)
+                        if (o.rate_test >= 2 && !c.vround) est = fmin(nrm, 3.0 * kappa * nrm * nrm);
+                    } else {
+                        if (it == 1 && nrm_prev > 0.0) kappa = fmax(fmax(nrm / (nrm_prev * nrm_prev), 0.7 * kappa), o.kappa_floor);
+                        if (nrm < nrm_prev) {
+                            // safety 3; a chord update (value-only round) contracts half as fast as the ratio observed
+                            // across the preceding Newton update suggests (e_2 ~ 2 (e_1 / e_0) e_1)
+                            const double rho = nrm / nrm_prev;
+                            est = nrm * fmin(1.0, (c.vround ? 6.0 : 3.0) * rho / (1.0 - rho));
+                        }
+                    }
                 }
                 const int conv = (est <= 1.0) && (sc == 1.0) && (rmax <= restol);
                 nrm_prev = nrm;
@@ -480,7 +492,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES) k_control(const CArgs c
             IST(IS_NP) = np; IST(IS_SIDX) = sidx; IST(IS_NNEWTON) = nnewton; IST(IS_NACC) = nacc; IST(IS_NREJ) = nrej;
             IST(IS_RETRY) = retry;
             DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
-            DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim; DST(DS_NRM) = nrm_prev;
+            DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim; DST(DS_NRM) = nrm_prev; DST(DS_KAPPA) = kappa;
             a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
             a.active[inst] = phase == PH_DONE ? ACT_DONE : (phase == PH_DC || (phase == PH_TRAN && it == 0)) ? ACT_FULL : ACT_ANY;
             if (phase_in == PH_DC && phase != PH_DC) atomicSub(c.dc_count, 1);
@@ -536,6 +548,11 @@ struct LArgs {
     const int4* sitems;       // gather items of the residual and charge rows only
     const int* sitem_ptr;     // [LU_W + 1]
     int nslev, pad1;
+    // first-order charge update  q(x + dx) ~ q(x) + C dx:  items (dev_out row of dQ/dV, vals slot of q_row, vals slot of
+    // dx_col, index into cmult), grouped by destination row like the gather items
+    const int4* citems;
+    const int* citem_ptr;     // [LU_W + 1]
+    const double* cmult;
     double* LUF;              // [nnz_lu][B] factors of the last full round: L (unscaled), U, inverted pivots
     const double* WV;
     double *DX, *QK, *RMAX, *DVMAX;
@@ -640,7 +657,6 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
         double* bp = Fv + (size_t)a.row_to_step[i] * LU_PTS;
         const double b = *bp - alpha * q;
         *bp = b;
-        if (on) c.QK[(size_t)i * B + inst] = q;
         rmax = fmax(rmax, fabs(b));
     }
     s_red[0][w][lane] = rmax;
@@ -691,6 +707,41 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
         }
         __syncthreads();
     }
+    // ---- 3b. charges of the updated iterate to first order: q(x + dx) ~ q(x) + C dx (linear capacitors exactly).
+    //          The accepted step keeps these charges, so they must belong to the iterate that is accepted, not to
+    //          the point of the last device evaluation (which lies |dx| away).  In value-only rounds dQ/dV is that
+    //          of the last full round.
+    //          Only the rate-based acceptance tests need it: the plain test accepts when |dx| is below the Newton
+    //          tolerance, where the update is negligible.
+    if (a.o.rate_test) {
+    for (int i = w; i < N; i += LU_W) {
+        double dq = 0.0;
+        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
+            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            dq += a.lin_c[li] * VL(nnz + a.col_to_step[a.rl_col[p]]);
+        }
+        Qv[(size_t)i * LU_PTS] += dq;
+    }
+    __syncthreads();
+    {
+        int q0 = c.citem_ptr[w];
+        const int q1 = c.citem_ptr[w + 1];
+        for (; q0 < q1; q0 += LU_GU) {
+            int4 it[LU_GU];
+            double v[LU_GU];
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) it[u] = __ldg(c.citems + min(q0 + u, q1 - 1));
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++)
+                if (q0 + u < q1) VL(it[u].y) += __ldg(c.cmult + it[u].w) * v[u] * VL(it[u].z);
+        }
+    }
+    __syncthreads();
+    }
+    if (on)
+        for (int i = w; i < N; i += LU_W) c.QK[(size_t)i * B + inst] = Qv[(size_t)i * LU_PTS];
     // ---- 4. update vector and norms ---------------------------------------------------------------------
     double dvm = 0.0;
     for (int i = w; i < N; i += LU_W) {
@@ -731,6 +782,7 @@ __global__ void k_init_state(long long B, int N, int* ist, double* dst, double* 
     ist[(size_t)IS_STAGE * B + inst] = -1;
     dst[(size_t)DS_T * B + inst] = o.t0;
     dst[(size_t)DS_HPROP * B + inst] = o.dt > 0.0 ? o.dt : o.span * 1e-5;
+    dst[(size_t)DS_KAPPA * B + inst] = o.kappa0;
     alpha[inst] = 0.0;
     active[inst] = o.skip_dc && !o.dc_only ? ACT_ANY : ACT_FULL;
     for (int i = 0; i < N; i++) {

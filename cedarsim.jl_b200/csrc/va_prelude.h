@@ -155,7 +155,10 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define VT(k) vt_[k]
 #define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
-#define OUT_J(idx, k, l, g, c) out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * (c)
+// J = dI/dV + alpha dQ/dV for the Newton matrix, and dQ/dV on its own (rows 2 NT + NJ ...) for the first-order
+// charge update q(x + dx) ~ q(x) + C dx of k_lu
+#define OUT_J(idx, k, l, g, c) { const double c_ = (c); out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * c_; \
+                                 out_[(size_t)(2 * NT + NJ + (idx)) * a.B] = c_; }
 
 // Cache layout: [device][block of VA_CACHE_BLK points][slot][VA_CACHE_BLK].  Inside one block of points a slot is a
 // compile-time byte offset (slot * 1 KB) from the thread's base pointer, so the ~250 cache accesses of an

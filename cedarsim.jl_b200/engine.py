@@ -70,9 +70,10 @@ def cuda_source(models: Sequence) -> str:
     """Concatenate generated model sources with their shape macros (see csrc/va_prelude.h)."""
     parts = []
     for cm in models:
-        parts.append(f"#undef NT\n#undef NPARAM\n#undef NCACHE\n#undef NOUT\n"
+        parts.append(f"#undef NT\n#undef NPARAM\n#undef NCACHE\n#undef NOUT\n#undef NJ\n"
                      f"#define NT {len(cm.terminals)}\n#define NPARAM {max(1, len(cm.params))}\n"
-                     f"#define NCACHE {max(1, cm.ncache)}\n#define NOUT {2 * len(cm.terminals) + len(cm.jrow)}\n")
+                     f"#define NCACHE {max(1, cm.ncache)}\n#define NJ {len(cm.jrow)}\n"
+                     f"#define NOUT {2 * len(cm.terminals) + 2 * len(cm.jrow)}\n")
         parts.append(cm.source)
         if getattr(cm, "source_v", ""):   # value-only variant: its own cache layout
             parts.append(f"#undef NCACHE\n#define NCACHE {max(1, cm.ncache_v)}\n")

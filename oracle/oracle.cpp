@@ -303,6 +303,7 @@ struct Solver {
     std::vector<uint8_t> lte_mask;
     Counters cnt;
     bool debug = std::getenv("ORC_DEBUG") != nullptr;
+    double kappa = 0.0, kappa_floor = 0.0;   // quadratic-convergence constant of the first Newton update (nr_rate_test 2)
 
     void init(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t b, const cb_options* o) {
         in.fc = fc; in.params = params; in.B = B; in.b = b;
@@ -310,6 +311,8 @@ struct Solver {
         s.resize(N);
         J.resize((size_t)N * N); rhs.resize(N);
         va_setup_all(in, in.pv(o->temp), in.pv(o->gmin), vc);
+        kappa = 20.0 * (o->nr_reltol + o->nr_vabstol);
+        kappa_floor = kappa / 30.0;
         lte_mask.assign(N, 0);
         for (int i = 0; i < NV; i++) lte_mask[i] = 1;
         for (int d = 0; d < fc->n_devices; d++)
@@ -322,8 +325,9 @@ struct Solver {
     // On success x holds the converged iterate and qk the charges of the last evaluation.
     // Returns 0 ok, 1 max iterations, 4 singular / non-finite.
     // Convergence: weighted update norm n_k = max_i |dx_i| / (nr_reltol max(|x_i|, |x_i + dx_i|) + atol_i) <= 1; with
-    // `use_rate` (transient) iterations after the first accept as soon as 10 x the estimate n_k rho / (1 - rho) of the
-    // error left after the update is <= 1, rho = n_k / n_{k-1} (the rate test of Sundials IDA, the reference's solver).
+    // `use_rate` (transient) iterations after the first accept as soon as 3 x the estimate n_k rho / (1 - rho) of the
+    // error left after the update is <= 1, rho = n_k / n_{k-1}; nr_rate_test 2 also accepts the first update when
+    // 3 kappa n_1^2 <= 1 (see cedarb200.h) (the rate test of Sundials IDA, the reference's solver).
     int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
                double gshunt, int maxit, double restol, std::vector<double>& qk, bool use_rate = false) {
         double nrm_prev = 0.0;
@@ -352,6 +356,18 @@ struct Solver {
             }
             if (!finite) return 4;
             double sc = dvmax > lim ? lim / dvmax : 1.0;
+            // charges of the updated iterate to first order, q(x + dx) ~ q(x) + C dx: these are what an accepted
+            // step keeps under the rate-based tests (the engine's k_lu does the same); the plain test accepts only
+            // when |dx| is below the Newton tolerance, where q(x) of the last evaluation is kept
+            qk = s.q;
+            for (int i = 0; use_rate && i < N; i++) {
+                double acc = 0.0;
+                for (int j = 0; j < N; j++) {
+                    const double cij = s.C[(size_t)i * N + j];
+                    if (cij != 0.0) acc += cij * rhs[j];
+                }
+                qk[i] += acc;
+            }
             double nrm = 0.0;
             for (int i = 0; i < N; i++) {
                 double dx = sc * rhs[i];
@@ -360,9 +376,12 @@ struct Solver {
                 x[i] = xn;
             }
             double est = nrm;
+            if (use_rate && it == 0 && opt->nr_rate_test >= 2) est = std::min(nrm, 3.0 * kappa * nrm * nrm);
+            if (use_rate && it == 1 && nrm_prev > 0.0)
+                kappa = std::max(std::max(nrm / (nrm_prev * nrm_prev), 0.7 * kappa), kappa_floor);
             if (use_rate && it >= 1 && nrm < nrm_prev) {
                 const double rho = nrm / nrm_prev;
-                est = nrm * std::min(1.0, 10.0 * rho / (1.0 - rho));
+                est = nrm * std::min(1.0, 3.0 * rho / (1.0 - rho));
             }
             nrm_prev = nrm;
             const bool conv = (est <= 1.0) && (sc == 1.0) && (rmax <= restol);
@@ -371,7 +390,7 @@ struct Solver {
                 for (int i = 0; i < N; i++) if (std::fabs(sc * rhs[i]) > dm) { dm = std::fabs(sc * rhs[i]); im = i; }
                 std::fprintf(stderr, "  t=%.6e it=%d rmax=%.3e dxmax=%.3e at %d (x=%.6e) sc=%.3g conv=%d\n", t, it, rmax, dm, im, x[im], sc, (int)conv);
             }
-            if (conv) { qk = s.q; return 0; }
+            if (conv) return 0;
         }
         return 1;
     }
