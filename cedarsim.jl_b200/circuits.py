@@ -14,7 +14,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from . import models
-from .flat import FlatCircuit, VAModelShape, Wave, W_PWL, W_DC
+from .flat import FlatCircuit, VAModelShape, Wave, W_PWL, W_DC, shape_of
 
 
 def _model(fc: FlatCircuit, card: str, host: bool, used: list) -> int:
@@ -27,7 +27,7 @@ def _model(fc: FlatCircuit, card: str, host: bool, used: list) -> int:
         from .va.build import build_host
         shape = build_host(cm).shape()
     else:
-        shape = VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol))
+        shape = shape_of(cm)
     return fc.va_model(shape)
 
 

@@ -46,6 +46,7 @@ class cb_wave(C.Structure):
         ("t", C.POINTER(C.c_double)),
         ("y", C.POINTER(cb_pref)),
         ("v", cb_pref * 7),
+        ("ac_mag", C.c_double),
     ]
 
 
@@ -60,6 +61,12 @@ class cb_va_model(C.Structure):
         ("jcol", C.POINTER(C.c_int32)),
         ("host_setup", C.c_void_p),
         ("host_eval", C.c_void_p),
+        ("n_noise", C.c_int32),
+        ("ncache_n", C.c_int32),
+        ("noise_pos", C.POINTER(C.c_int32)),
+        ("noise_neg", C.POINTER(C.c_int32)),
+        ("host_setupn", C.c_void_p),
+        ("host_noise", C.c_void_p),
     ]
 
 
@@ -173,6 +180,7 @@ class Wave:
     t: Sequence[float] = ()
     y: Sequence[Value] = ()
     v: Sequence[Value] = ()  # PULSE: v1 v2 td tr tf pw per | SIN: vo va freq td theta phase ncycles
+    ac: float = 0.0          # small-signal magnitude |ac| (src/simpledevices.jl:292-294; the phase is ignored there too)
 
 
 @dataclass
@@ -198,6 +206,20 @@ class VAModelShape:
     jcol: List[int]
     host_setup: int = 0  # function addresses, CPU oracle only
     host_eval: int = 0
+    # noise sources (va/compiler.py noise variant): independent current sources between two terminals
+    ncache_n: int = 0
+    noise_pos: List[int] = field(default_factory=list)   # terminal index, -1 = ground
+    noise_neg: List[int] = field(default_factory=list)
+    host_setupn: int = 0
+    host_noise: int = 0
+
+
+def shape_of(cm) -> VAModelShape:
+    """Shape of a va.compiler.CompiledModel without host function addresses (all the engine needs)."""
+    return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
+                        ncache_n=getattr(cm, "ncache_n", 0),
+                        noise_pos=[int(s[0]) for s in getattr(cm, "noise_sources", [])],
+                        noise_neg=[int(s[1]) for s in getattr(cm, "noise_sources", [])])
 
 
 @dataclass
@@ -374,15 +396,20 @@ class FlatCircuit:
                 vv = [0.0] * 7
             for k in range(7):
                 cw.v[k] = _pref(vv[k])
+            cw.ac_mag = abs(float(w.ac))
             waves[i] = cw
         models = (cb_va_model * max(1, len(self.va_models)))()
         for i, m in enumerate(self.va_models):
             jr = (C.c_int32 * max(1, len(m.jrow)))(*m.jrow)
             jc = (C.c_int32 * max(1, len(m.jcol)))(*m.jcol)
-            keep += [jr, jc]
+            npos = (C.c_int32 * max(1, len(m.noise_pos)))(*m.noise_pos)
+            nneg = (C.c_int32 * max(1, len(m.noise_neg)))(*m.noise_neg)
+            keep += [jr, jc, npos, nneg]
             models[i] = cb_va_model(m.name.encode(), len(m.terminals), len(m.params), m.ncache, len(m.jrow),
                                     C.cast(jr, C.POINTER(C.c_int32)), C.cast(jc, C.POINTER(C.c_int32)),
-                                    m.host_setup or None, m.host_eval or None)
+                                    m.host_setup or None, m.host_eval or None, len(m.noise_pos), m.ncache_n,
+                                    C.cast(npos, C.POINTER(C.c_int32)), C.cast(nneg, C.POINTER(C.c_int32)),
+                                    m.host_setupn or None, m.host_noise or None)
         insts = (cb_va_inst * max(1, len(self.va_insts)))()
         for i, vi in enumerate(self.va_insts):
             shape = self.va_models[vi.model]

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import models
 from .expr import ExprError, evaluate, free_vars, parse_expr, parse_number
-from .flat import (Col, FlatCircuit, VAModelShape, Wave, W_DC, W_PULSE, W_PWL, W_SIN)
+from .flat import (Col, FlatCircuit, VAModelShape, Wave, W_DC, W_PULSE, W_PWL, W_SIN, shape_of)
 from .modelcard import ModelCard, parse_model_cards
 
 
@@ -474,6 +474,15 @@ class _Flattener:
     def _wave(self, name: str, src: dict, scope: _Scope, over: Dict[str, Num]) -> Wave:
         dc = over.get("dc", scope.eval(src["dc"]) if src["dc"] is not None else None)
         dcv = None if dc is None else self.value(name + ".dc", dc)
+        w = self._wave_tran(name, src, scope, dcv)
+        if src.get("ac") is not None:
+            ac = scope.eval(src["ac"])
+            if isinstance(ac, np.ndarray):
+                raise NetlistError("the AC magnitude of a source cannot be swept")
+            w.ac = abs(float(ac))
+        return w
+
+    def _wave_tran(self, name: str, src: dict, scope: _Scope, dcv) -> Wave:
         if src["tran"] is None:
             return Wave(W_DC, dc=0.0 if dcv is None else dcv)
         kind, args = src["tran"]
@@ -510,7 +519,7 @@ class _Flattener:
             from .va.build import build_host
             shape = build_host(cm).shape()
         else:
-            shape = VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol))
+            shape = shape_of(cm)
         m = self.fc.va_model(shape)
         vals = {k: self.value(f"{name}.{k.lower()}", v) for k, v in inst.items()}
         for k in runtime:   # runtime parameters must always be supplied: card value or model default

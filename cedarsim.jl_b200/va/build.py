@@ -46,6 +46,13 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define OUT_I(k, v) I_[k] = (v)
 #define OUT_Q(k, v) Q_[k] = (v)
 #define OUT_J(idx, k, l, g, c) do {{ G_[(k) * NT + (l)] = (g); C_[(k) * NT + (l)] = (c); }} while (0)
+/* noise variant: power of every noise source at the bias point (and the flicker exponent) */
+#define VA_SETUPN_BEGIN(NAME) void NAME##_setupn(const double* par_, const uint8_t* given_, double temp_c_, double gmin_, double* cache_) {{
+#define VA_SETUPN_END(NAME) }}
+#define VA_EVALN_BEGIN(NAME) void NAME##_noise(const double* cache_, const double* v_, double* N_, double* NE_) {{
+#define VA_EVALN_END(NAME) }}
+#define OUT_N(k, v) N_[k] = (v)
+#define OUT_NE(k, v) NE_[k] = (v)
 """
 
 
@@ -59,15 +66,35 @@ class HostModel:
         self.eval = getattr(self.lib, cm.name + "_eval")
         self.setup_addr = C.cast(self.setup, C.c_void_p).value
         self.eval_addr = C.cast(self.eval, C.c_void_p).value
+        self.setupn = self.noise = None
+        self.setupn_addr = self.noise_addr = 0
+        if cm.source_n:
+            self.setupn = getattr(self.lib, cm.name + "_setupn")
+            self.noise = getattr(self.lib, cm.name + "_noise")
+            self.setupn_addr = C.cast(self.setupn, C.c_void_p).value
+            self.noise_addr = C.cast(self.noise, C.c_void_p).value
 
     def shape(self):
         from ..flat import VAModelShape
         cm = self.cm
         return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
-                            self.setup_addr, self.eval_addr)
+                            self.setup_addr, self.eval_addr, ncache_n=cm.ncache_n,
+                            noise_pos=[int(s[0]) for s in cm.noise_sources], noise_neg=[int(s[1]) for s in cm.noise_sources],
+                            host_setupn=self.setupn_addr, host_noise=self.noise_addr)
 
     # convenience for tests
-    def run_setup(self, params: dict, temp_c=27.0, gmin=1e-12):
+    def run_noise(self, params: dict, v, temp_c=27.0, gmin=1e-12):
+        """(pwr[K], exp[K]) of the model's noise sources at terminal voltages v."""
+        import numpy as np
+        cache = self.run_setup(params, temp_c, gmin, noise=True)
+        K = len(self.cm.noise_sources)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        pw = np.zeros(max(1, K)); ex = np.zeros(max(1, K))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self.noise(dp(cache), dp(v), dp(pw), dp(ex))
+        return pw[:K], ex[:K]
+
+    def run_setup(self, params: dict, temp_c=27.0, gmin=1e-12, noise=False):
         import numpy as np
         cm = self.cm
         lut = {p.lower(): i for i, p in enumerate(cm.params)}
@@ -76,8 +103,8 @@ class HostModel:
         for k, v in params.items():
             par[lut[k.lower()]] = v
             given[lut[k.lower()]] = 1
-        cache = np.zeros(max(1, cm.ncache))
-        self.setup(par.ctypes.data_as(C.POINTER(C.c_double)), given.ctypes.data_as(C.POINTER(C.c_uint8)),
+        cache = np.zeros(max(1, cm.ncache_n if noise else cm.ncache))
+        (self.setupn if noise else self.setup)(par.ctypes.data_as(C.POINTER(C.c_double)), given.ctypes.data_as(C.POINTER(C.c_uint8)),
                    C.c_double(temp_c), C.c_double(gmin), cache.ctypes.data_as(C.POINTER(C.c_double)))
         return cache
 
@@ -104,7 +131,7 @@ class HostModel:
 def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2", count_ops: bool = False) -> HostModel:
     out_dir = out_dir or GEN_DIR
     os.makedirs(out_dir, exist_ok=True)
-    text = c_prelude(len(cm.terminals), count_ops) + cm.source
+    text = c_prelude(len(cm.terminals), count_ops) + cm.source + (cm.source_n or "")
     key = hashlib.sha1((text + opt).encode()).hexdigest()[:16]
     base = os.path.join(out_dir, f"{cm.name}_{key}")
     so = base + ".so"

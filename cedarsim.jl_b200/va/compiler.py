@@ -162,6 +162,9 @@ def _lit(x) -> str:
 # liveness: drop assignments whose value can never reach a contribution
 # ---------------------------------------------------------------------------------------
 
+_NOISE_LIVE = [False]   # the noise variant keeps the arguments of white_noise()/flicker_noise() alive
+
+
 def _expr_vars(e, out: Set[str], funcs):
     k = e[0]
     if k == "var":
@@ -175,7 +178,7 @@ def _expr_vars(e, out: Set[str], funcs):
         for s in e[1:]:
             _expr_vars(s, out, funcs)
     elif k == "call":
-        if e[1] in NOISE_FUNCS:
+        if e[1] in NOISE_FUNCS and not _NOISE_LIVE[0]:
             return
         for a in e[2]:
             _expr_vars(a, out, funcs)
@@ -367,6 +370,11 @@ class CompiledModel:
     # eval pair (VA_SETUPV_* / VA_EVALV_* macros) and cache layout; empty when the module uses ddx()
     source_v: str = ""
     ncache_v: int = 0
+    # noise variant (VA_SETUPN_* / VA_EVALN_*): power pwr_k (and flicker exponent) of every noise source at a bias
+    # point; sources are independent current sources between two terminals (-1 = ground)
+    source_n: str = ""
+    ncache_n: int = 0
+    noise_sources: List[Tuple[int, int, str, str]] = field(default_factory=list)
 
     @property
     def key(self) -> str:
@@ -375,9 +383,13 @@ class CompiledModel:
 
 class _Compiler:
     def __init__(self, mod: Module, name: str, const_params: Optional[Dict[str, float]] = None,
-                 runtime_params: Optional[Sequence[str]] = None, no_deriv: bool = False, skip_funcs=()):
+                 runtime_params: Optional[Sequence[str]] = None, no_deriv: bool = False, skip_funcs=(),
+                 noise: bool = False):
         self.mod = mod
         self.name = name
+        self.noise = noise                # noise variant: outputs the power of every noise source, nothing else
+        self.noise_sources: List[Tuple[int, int, str, str]] = []   # (pos terminal, neg terminal, kind, name), -1 = ground
+        no_deriv = no_deriv or noise
         self.no_deriv = no_deriv          # value-only variant: probes carry no seeds, no Jacobian outputs
         self.skip_funcs = set(skip_funcs)  # helper functions the full variant already defined
         # specialisation: parameters with compile-time values (a model card) are folded; only
@@ -1298,19 +1310,98 @@ class _Compiler:
             return any(self._has_ddt(s) for s in e[1:])
         return False
 
+    # -- noise sources (reference: src/va_env.jl:82-90 makes every white_noise / flicker_noise call an epsilon
+    #    variable that is 0 in DC / transient and a unit-PSD input of the small-signal system in noise!(),
+    #    src/ac.jl:100-160: output PSD = sum_k |H_k(jw)|^2 pwr_k / f^exp_k) --
+    def _has_noise(self, e) -> bool:
+        k = e[0]
+        if k == "call":
+            return e[1] in NOISE_FUNCS or any(self._has_noise(a) for a in e[2])
+        if k == "bin":
+            return self._has_noise(e[2]) or self._has_noise(e[3])
+        if k == "un":
+            return self._has_noise(e[2])
+        if k == "cond":
+            return any(self._has_noise(s) for s in e[1:])
+        return False
+
+    def _split_noise(self, e):
+        """e = rest + sum coef_i * noise_call_i.  Returns (rest or None, [(coef, call)])."""
+        k = e[0]
+        one = ("num", 1.0, False)
+        if k == "call" and e[1] in NOISE_FUNCS:
+            return None, [(one, e)]
+        if not self._has_noise(e):
+            return e, []
+        if k == "bin" and e[1] in ("+", "-"):
+            ra, na = self._split_noise(e[2])
+            rb, nb = self._split_noise(e[3])
+            if e[1] == "-":
+                rb = None if rb is None else ("un", "-", rb)
+            r = ra if rb is None else (rb if ra is None else ("bin", "+", ra, rb))
+            return r, na + nb          # the sign of a noise term does not matter (powers)
+        if k == "bin" and e[1] == "*":
+            if self._has_noise(e[2]) and not self._has_noise(e[3]):
+                r, n = self._split_noise(e[2])
+                other = e[3]
+            elif self._has_noise(e[3]) and not self._has_noise(e[2]):
+                r, n = self._split_noise(e[3])
+                other = e[2]
+            else:
+                raise VACompileError("product of two noise sources")
+            r = None if r is None else ("bin", "*", other, r)
+            return r, [(("bin", "*", other, c), q) for c, q in n]
+        if k == "bin" and e[1] == "/" and not self._has_noise(e[3]):
+            r, n = self._split_noise(e[2])
+            r = None if r is None else ("bin", "/", r, e[3])
+            return r, [(("bin", "/", c, e[3]), q) for c, q in n]
+        if k == "un" and e[1] == "-":
+            r, n = self._split_noise(e[2])
+            return (None if r is None else ("un", "-", r)), n
+        raise VACompileError("noise sources must appear linearly in a contribution")
+
+    def _noise_contrib(self, pos, neg, noises):
+        for coef, call in noises:
+            fn, args = call[1], call[2]
+            if fn == "noise_table":
+                raise VACompileError("noise_table() is not supported")
+            k = len(self.noise_sources)
+            label = args[-1][1] if args and args[-1][0] == "str" else ""
+            self.noise_sources.append((-1 if pos is None else pos, -1 if neg is None else neg,
+                                       "flicker" if fn == "flicker_noise" else "white", str(label)))
+            pwr = ("bin", "*", ("bin", "*", coef, coef), args[0])
+            terms = [("N", pwr)]
+            if fn == "flicker_noise":
+                terms.append(("NE", args[1]))
+            for kind, expr in terms:
+                v = self.force(self.gd(expr))
+                c = self._cast(v.c, v.typ, "r")
+                an = f"acc{kind}_{k}"
+                self.types[an] = "r"
+                self.E.append(f"{an} = {c};")
+                self.dyn_vars.add(an)
+                self.decl_deps.setdefault(an, set())
+                self.state[an] = VS(True, frozenset(), None, None)
+
     def contrib(self, st):
         acc, nodes, e = st[1], st[2], st[3]
         if len(nodes) == 1 and nodes[0] in self.mod.branches:
             nodes = list(self.mod.branches[nodes[0]])
         if acc not in ("I", "flow"):
             raise VACompileError(f"{acc}() contributions are not supported yet (voltage branches need extra MNA unknowns)")
-        res, qs = self._split_ddt(e)
         pos = self.tindex.get(nodes[0]) if nodes[0] not in ("0", "gnd") else None
         neg = None
         if len(nodes) > 1 and nodes[1] not in ("0", "gnd"):
             neg = self.tindex.get(nodes[1])
         if pos is not None and pos == neg:
             return
+        e, noises = self._split_noise(e)
+        if self.noise:
+            self._noise_contrib(pos, neg, noises)
+            return   # the noise variant outputs source powers only
+        if e is None:
+            return
+        res, qs = self._split_ddt(e)
         saved = self.dynctl
         for c, _q in qs:
             if not self.is_static_expr(c):
@@ -1577,7 +1668,11 @@ class _Compiler:
                 raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
         self.drop_seed = None if self.no_deriv else self._pick_drop_seed(body)
-        pruned, _ = prune_dead(body, set(), mod.functions)
+        _NOISE_LIVE[0] = self.noise
+        try:
+            pruned, _ = prune_dead(body, set(), mod.functions)
+        finally:
+            _NOISE_LIVE[0] = False
         if pruned is not None:
             self.stmt(pruned)
         self.flush_ops(self.E)
@@ -1586,7 +1681,10 @@ class _Compiler:
         # outputs
         jrow, jcol = [], []
         out_lines = []
-        for kk in range(nt):
+        for k in range(len(self.noise_sources) if self.noise else 0):
+            out_lines.append(f"OUT_N({k}, accN_{k});")
+            out_lines.append(f"OUT_NE({k}, {'accNE_%d' % k if ('accNE_%d' % k) in self.dyn_vars else '0.0'});")
+        for kk in range(0 if self.noise else nt):
             si, sq = self.state.get(f"accI_{kk}"), self.state.get(f"accQ_{kk}")
             out_lines.append(f"OUT_I({kk}, {'accI_%d' % kk if si else '0.0'});")
             out_lines.append(f"OUT_Q({kk}, {'accQ_%d' % kk if sq else '0.0'});")
@@ -1814,7 +1912,7 @@ class _Compiler:
         for fn in order:
             if fn not in self.skip_funcs:
                 L.append(done[fn])
-        V = "V" if self.no_deriv else ""
+        V = "N" if self.noise else ("V" if self.no_deriv else "")
         L.append(f"VA_SETUP{V}_BEGIN({self.name})")
         for cn in sorted(self.static_vars):
             ct = "int" if self.types.get(cn) == "i" else "double"
@@ -1844,7 +1942,23 @@ def compile_module(mod: Module, name: Optional[str] = None, const_params=None, r
         cm.source_v, cm.ncache_v = cv.source, cv.ncache
     except VACompileError:
         pass
+    if _module_has_noise(mod):
+        nc = _Compiler(mod, name or mod.name, const_params, runtime_params, noise=True, skip_funcs=full.defined_funcs)
+        cn = nc.compile()
+        cm.source_n, cm.ncache_n, cm.noise_sources = cn.source, cn.ncache, list(nc.noise_sources)
     return cm
+
+
+def _module_has_noise(mod: Module) -> bool:
+    def walk(x) -> bool:
+        if isinstance(x, tuple):
+            if len(x) >= 2 and x[0] == "call" and x[1] in NOISE_FUNCS:
+                return True
+            return any(walk(y) for y in x)
+        if isinstance(x, (list, dict)):
+            return any(walk(y) for y in (x.values() if isinstance(x, dict) else x))
+        return False
+    return walk(list(mod.analog))
 
 
 def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,

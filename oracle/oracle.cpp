@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -44,6 +45,8 @@ typedef void (*va_setup_fn)(const double* par, const uint8_t* given, double temp
                             double* cache);
 typedef void (*va_eval_fn)(const double* cache, const double* v, double* I, double* Q, double* G,
                            double* C);
+typedef void (*va_noise_fn)(const double* cache, const double* v, double* pwr, double* ex);
+typedef std::complex<double> cplx;
 
 struct Inst {  // one sweep point
     const cb_flat_circuit* fc;
@@ -657,6 +660,159 @@ int orc_eval(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t
     std::memcpy(q, S.s.q.data(), sizeof(double) * N);
     std::memcpy(G, S.s.G.data(), sizeof(double) * N * N);
     std::memcpy(C, S.s.C.data(), sizeof(double) * N * N);
+    return 0;
+}
+
+// ---------------------------------------------------------------- small-signal analyses
+// Reference: ac!(circ) / noise!(circ), src/ac.jl:75-190.  The reference linearises the compiled DAE at the operating
+// point (Ju = dF/du, M = mass matrix, B = dF/d(eps)) and evaluates C (jw E - A)^-1 B with DescriptorSystems
+// (src/ac.jl:257-284); in MNA form that is  (G + jw C) x = b  with G = df/dx, C = dq/dx at the operating point.
+//   AC:    b = -dF/d(eps), eps scaling every source by |ac| (src/simpledevices.jl:292-294, :331-333)
+//   noise: every white_noise / flicker_noise call is an independent input eps_k of unit PSD scaled by
+//          pwr_k / f^exp_k (src/va_env.jl:82-90, src/ac.jl:265-276); PSD_out(f) = sum_k |H_k|^2 pwr_k / f^exp_k.
+//          Resistors carry 4 k T / R with k = 1.380649e-23 (src/simpledevices.jl:72-75).
+// Dense complex LU with partial pivoting; the transfer functions of all noise sources to one output come from one
+// adjoint solve (A^T y = e_out, H_k = y[pos_k] - y[neg_k]).
+
+static bool zlu_factor(std::vector<cplx>& A, std::vector<int>& piv, int N) {
+    piv.resize(N);
+    for (int k = 0; k < N; k++) {
+        int p = k;
+        double best = std::abs(A[(size_t)k * N + k]);
+        for (int i = k + 1; i < N; i++) {
+            double a = std::abs(A[(size_t)i * N + k]);
+            if (a > best) { best = a; p = i; }
+        }
+        if (!(best > 0.0) || !std::isfinite(best)) return false;
+        piv[k] = p;
+        if (p != k)
+            for (int j = 0; j < N; j++) std::swap(A[(size_t)k * N + j], A[(size_t)p * N + j]);
+        const cplx inv = 1.0 / A[(size_t)k * N + k];
+        for (int i = k + 1; i < N; i++) {
+            const cplx l = A[(size_t)i * N + k] * inv;
+            A[(size_t)i * N + k] = l;
+            if (l == cplx(0.0)) continue;
+            for (int j = k + 1; j < N; j++) A[(size_t)i * N + j] -= l * A[(size_t)k * N + j];
+        }
+    }
+    return true;
+}
+
+static void zlu_solve(const std::vector<cplx>& A, const std::vector<int>& piv, std::vector<cplx>& b, int N) {
+    for (int k = 0; k < N; k++)   // whole rows were swapped (LAPACK convention): permute first, then L
+        if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+    for (int k = 0; k < N; k++)
+        for (int i = k + 1; i < N; i++) b[i] -= A[(size_t)i * N + k] * b[k];
+    for (int i = N - 1; i >= 0; i--) {
+        cplx s = b[i];
+        for (int j = i + 1; j < N; j++) s -= A[(size_t)i * N + j] * b[j];
+        b[i] = s / A[(size_t)i * N + i];
+    }
+}
+
+struct NoiseSrc { int pos, neg; double pwr, ex; };
+
+// operating point + linearisation of sweep point b; returns the DC status
+static int linearise(Solver& S, std::vector<double>& x) {
+    const int st = S.dc(x);
+    eval_system(S.in, S.vc, x.data(), 0.0, true, S.s);
+    return st;
+}
+
+int orc_ac(const cb_flat_circuit* fc, const double* params, int64_t B, const double* freqs, int64_t F,
+           const cb_options* opt, double* y_out /* [O][F][B][2] */, int32_t* status, int nthreads) {
+    const int N = fc->n_unknowns;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t b = 0; b < B; b++) {
+        Solver S;
+        S.init(fc, params, B, b, opt);
+        S.x0 = g_x0; S.x0_stride = g_x0_stride;
+        std::vector<double> x;
+        status[b] = linearise(S, x);
+        std::vector<double> rhs(N, 0.0);
+        for (int d = 0; d < fc->n_devices; d++) {
+            const cb_device& dv = fc->devices[d];
+            if (dv.wave < 0) continue;
+            const double ac = fc->waves[dv.wave].ac_mag;
+            if (dv.kind == CB_DEV_VSRC) rhs[dv.branch] += ac;                 // f_b = vpn - (dc + eps ac)
+            else if (dv.kind == CB_DEV_ISRC) {                                // f_p += m (dc + eps ac)
+                if (dv.n[0] >= 0) rhs[dv.n[0]] -= dv.mult * ac;
+                if (dv.n[1] >= 0) rhs[dv.n[1]] += dv.mult * ac;
+            }
+        }
+        std::vector<cplx> A((size_t)N * N), v(N);
+        std::vector<int> piv;
+        for (int64_t k = 0; k < F; k++) {
+            const double w = 2.0 * M_PI * freqs[k];
+            for (size_t e = 0; e < (size_t)N * N; e++) A[e] = cplx(S.s.G[e], w * S.s.C[e]);
+            for (int i = 0; i < N; i++) v[i] = rhs[i];
+            const bool ok = zlu_factor(A, piv, N);
+            if (ok) zlu_solve(A, piv, v, N);
+            for (int o = 0; o < fc->n_outputs; o++) {
+                const cplx r = ok ? v[fc->outputs[o]] : cplx(NAN, NAN);
+                double* dst = y_out + (((int64_t)o * F + k) * B + b) * 2;
+                dst[0] = r.real(); dst[1] = r.imag();
+            }
+        }
+    }
+    return 0;
+}
+
+int orc_noise(const cb_flat_circuit* fc, const double* params, int64_t B, const double* freqs, int64_t F,
+              const cb_options* opt, double* psd /* [O][F][B] */, int32_t* status, int nthreads) {
+    const int N = fc->n_unknowns;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t b = 0; b < B; b++) {
+        Solver S;
+        S.init(fc, params, B, b, opt);
+        S.x0 = g_x0; S.x0_stride = g_x0_stride;
+        std::vector<double> x;
+        status[b] = linearise(S, x);
+        const double temp_c = S.in.pv(opt->temp), gmin = S.in.pv(opt->gmin);
+        std::vector<NoiseSrc> src;
+        for (int d = 0; d < fc->n_devices; d++) {
+            const cb_device& dv = fc->devices[d];
+            if (dv.kind != CB_DEV_R) continue;
+            const double kB = 1.380649e-23;
+            src.push_back({dv.n[0], dv.n[1], dv.mult * 4.0 * kB * (temp_c + 273.15) / S.in.pv(dv.value), 0.0});
+        }
+        for (int d = 0; d < fc->n_va_insts; d++) {
+            const cb_va_inst& vi = fc->va_insts[d];
+            const cb_va_model& m = fc->va_models[vi.model];
+            if (m.n_noise <= 0) continue;
+            std::vector<double> par(m.nparam), cache(std::max(1, m.ncache_n), 0.0), v(m.nterm), pw(m.n_noise, 0.0), ex(m.n_noise, 0.0);
+            for (int k = 0; k < m.nparam; k++) par[k] = vi.given[k] ? S.in.pv(vi.par[k]) : 0.0;
+            ((va_setup_fn)m.host_setupn)(par.data(), vi.given, temp_c, gmin, cache.data());
+            for (int k = 0; k < m.nterm; k++) v[k] = xv(x.data(), vi.term[k]);
+            ((va_noise_fn)m.host_noise)(cache.data(), v.data(), pw.data(), ex.data());
+            for (int k = 0; k < m.n_noise; k++) {
+                const int tp = m.noise_pos[k], tn = m.noise_neg[k];
+                src.push_back({tp < 0 ? -1 : vi.term[tp], tn < 0 ? -1 : vi.term[tn], vi.mult * pw[k], ex[k]});
+            }
+        }
+        std::vector<cplx> A((size_t)N * N), y(N);
+        std::vector<int> piv;
+        for (int64_t k = 0; k < F; k++) {
+            const double f = freqs[k], w = 2.0 * M_PI * f;
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) A[(size_t)j * N + i] = cplx(S.s.G[(size_t)i * N + j], w * S.s.C[(size_t)i * N + j]);  // A^T
+            const bool ok = zlu_factor(A, piv, N);
+            for (int o = 0; o < fc->n_outputs; o++) {
+                double acc = NAN;
+                if (ok) {
+                    for (int i = 0; i < N; i++) y[i] = 0.0;
+                    y[fc->outputs[o]] = 1.0;
+                    zlu_solve(A, piv, y, N);
+                    acc = 0.0;
+                    for (const NoiseSrc& q : src) {
+                        const cplx h = (q.pos >= 0 ? y[q.pos] : cplx(0.0)) - (q.neg >= 0 ? y[q.neg] : cplx(0.0));
+                        acc += std::norm(h) * (q.ex == 0.0 ? q.pwr : q.pwr / std::pow(f, q.ex));
+                    }
+                }
+                psd[((int64_t)o * F + k) * B + b] = acc;
+            }
+        }
+    }
     return 0;
 }
 

@@ -102,6 +102,38 @@ def tran(fc, t0, t1, saveat, params=None, B=1, opts=None, nthreads=1):
     return y, status, st.as_dict()
 
 
+def ac(fc, freqs, params=None, B=1, opts=None, nthreads=1):
+    """AC response of the outputs about each point's DC operating point: (y complex [O,F,B], status [B])."""
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), B)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    if params.size:
+        B = params.shape[1]
+    opts = opts or default_options()
+    freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+    O, F = len(fc.outputs), len(freqs)
+    y = np.zeros((O, F, B, 2)); status = np.zeros(B, dtype=np.int32)
+    rc = lib().orc_ac(pk.ref(), _dp(params), C.c_int64(B), _dp(freqs), C.c_int64(F), C.byref(opts), _dp(y),
+                      status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nthreads))
+    assert rc == 0
+    return y[..., 0] + 1j * y[..., 1], status
+
+
+def noise(fc, freqs, params=None, B=1, opts=None, nthreads=1):
+    """Output noise power spectral density about each point's DC operating point: (psd [O,F,B], status [B])."""
+    pk = fc.pack()
+    params = np.zeros((max(1, len(fc.param_names)), B)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    if params.size:
+        B = params.shape[1]
+    opts = opts or default_options()
+    freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+    O, F = len(fc.outputs), len(freqs)
+    psd = np.zeros((O, F, B)); status = np.zeros(B, dtype=np.int32)
+    rc = lib().orc_noise(pk.ref(), _dp(params), C.c_int64(B), _dp(freqs), C.c_int64(F), C.byref(opts), _dp(psd),
+                         status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nthreads))
+    assert rc == 0
+    return psd, status
+
+
 def eval_system(fc, x, t=0.0, dcop=False, params=None, b=0, opts=None):
     """One assembled evaluation: returns f[N], q[N], G[N,N], C[N,N]."""
     pk = fc.pack()
