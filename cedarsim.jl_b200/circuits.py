@@ -142,3 +142,33 @@ def two_resistor():
     fc.resistor("R2", "out", "0", fc.param("R2"))
     fc.set_outputs(["v.i", "out"])
     return fc
+
+
+# ---------------------------------------------------------------- decks of the small-signal parity tests
+# test/bsimcmg/inverter_cmg_cedar.cir, the circuit behind the reference's ngspice noise table (test/ac.jl:161-237)
+BSIMCMG_INVERTER_DECK = """** Test circuit
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+
+* built-in
+mneg Q D VSS VSS nmos_lvt
+mpos Q D VDD VDD pmos_lvt
+
+VVDD VDD 0 1.0
+VVSS VSS 0 0.0
+CQ D 0 1e-15
+VD D 0 AC 1 SIN (0.5 0.01 1e7)
+
+.TRAN 1e-9 4.0e-7
+
+.END
+"""
+# the same inverter with the input bias as a parameter (swept in tests/test_gpu_ac_noise.py)
+BSIMCMG_INVERTER_VIN_DECK = (BSIMCMG_INVERTER_DECK.replace("VD D 0 AC 1 SIN (0.5 0.01 1e7)", "VD D 0 DC 'vin' AC 1")
+                             .replace("* built-in", ".param vin=0.5"))
+
+
+def small_signal_decks():
+    """(deck text, swept columns) of the transistor-level small-signal tests; build() compiles them so that
+    the GPU box finds their cubins in the cache."""
+    return [(BSIMCMG_INVERTER_DECK, None),
+            (BSIMCMG_INVERTER_VIN_DECK, {"vin": np.array([0.5]), "mneg.nfin": np.array([1.0])})]

@@ -48,11 +48,14 @@ struct WaveH {
     std::vector<double> t;
     std::vector<cb_pref> y;
     cb_pref v[7];
+    double ac_mag = 0.0;
 };
 struct ModelH {
     std::string name;
     int nterm, nparam, ncache, nj;
     std::vector<int> jrow, jcol;
+    int ncache_n = 0;
+    std::vector<int> noise_pos, noise_neg;   // noise sources (terminal indices, -1 = ground)
     int nout() const { return 2 * nterm + 2 * nj; }   // I | Q | J = dI/dV + alpha dQ/dV | C = dQ/dV
 };
 struct VaInstH {
@@ -76,6 +79,7 @@ struct cb_circuit {
     cb::Symbolic sym;
     // assembly tables (host copies)
     std::vector<int> a_ptr, a_src, a_lin;
+    std::vector<int> a_csrc;   // dev_out row of dQ/dV next to every a_src row (small-signal analyses)
     std::vector<double> a_mult;
     std::vector<uint8_t> a_diag;
     std::vector<int> ri_ptr, ri_src, rq_ptr, rq_src, rl_ptr, rl_col, rl_lin, rs_ptr, rs_wave;
@@ -137,6 +141,7 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
             h.y.assign(w.y, w.y + w.npts);
         }
         for (int k = 0; k < 7; k++) h.v[k] = w.v[k];
+        h.ac_mag = w.ac_mag;
         if (w.kind == CB_W_PULSE)
             for (int k = 2; k < 7; k++)
                 if (w.v[k].col >= 0) return fail(CB_ERR_INVALID, "PULSE timing parameters cannot be swept");
@@ -149,6 +154,15 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
         h.nterm = m.nterm; h.nparam = m.nparam; h.ncache = m.ncache; h.nj = m.nj;
         h.jrow.assign(m.jrow, m.jrow + m.nj);
         h.jcol.assign(m.jcol, m.jcol + m.nj);
+        h.ncache_n = m.ncache_n;
+        if (m.n_noise > 0) {
+            if (!m.noise_pos || !m.noise_neg) return fail(CB_ERR_INVALID, "noise source tables missing");
+            h.noise_pos.assign(m.noise_pos, m.noise_pos + m.n_noise);
+            h.noise_neg.assign(m.noise_neg, m.noise_neg + m.n_noise);
+            for (int k = 0; k < m.n_noise; k++)
+                if (h.noise_pos[k] < -1 || h.noise_pos[k] >= m.nterm || h.noise_neg[k] < -1 || h.noise_neg[k] >= m.nterm)
+                    return fail(CB_ERR_INVALID, "noise source terminal out of range");
+        }
         c->models.push_back(std::move(h));
     }
     for (int i = 0; i < f->n_va_insts; i++) {
@@ -308,6 +322,15 @@ static int build_tables(cb_circuit* c) {
         }
     };
     flatten(ent_src, c->a_ptr, c->a_src, c->a_mult);
+    {   // the dQ/dV row of a Jacobian stamp sits nj rows after its J row (OUT_J in va_prelude.h)
+        std::map<int, int> shift;
+        for (size_t i = 0; i < c->insts.size(); i++) {
+            const ModelH& m = c->models[c->insts[i].model];
+            for (int j = 0; j < m.nj; j++) shift[(int)(c->inst_out_base[i] + 2 * m.nterm + j)] = m.nj;
+        }
+        c->a_csrc.resize(c->a_src.size());
+        for (size_t q = 0; q < c->a_src.size(); q++) c->a_csrc[q] = c->a_src[q] + shift.at(c->a_src[q]);
+    }
     flatten(rowI, c->ri_ptr, c->ri_src, c->ri_mult);
     flatten(rowQ, c->rq_ptr, c->rq_src, c->rq_mult);
     flatten(src_rows, c->rs_ptr, c->rs_wave, c->rs_coef);
@@ -576,6 +599,15 @@ struct cb_plan {
     std::vector<size_t> evalv_smem;
     std::vector<long long> cachev_off;
     double* d_cachev = nullptr;
+    // small-signal analyses (cb_ac / cb_noise): tables built on first use
+    std::vector<cudaKernel_t> k_setupn, k_evaln;
+    std::vector<unsigned> evaln_threads;
+    std::vector<size_t> evaln_smem;
+    std::vector<long long> cachen_off, noise_off;   // per model: cache slots / output rows before it
+    double *d_cachen = nullptr, *d_noise_out = nullptr, *d_ac_rhs = nullptr;
+    bool ac_ready = false, noise_ready = false, setupn_valid = false;
+    AArgs aa{};
+    size_t ac_smem = 0;
     bool have_v = false;     // all models have a value-only variant and the solve kernel is k_lu
     long long cachev_slots = 0;
     bool setupv_valid = false;
@@ -800,6 +832,26 @@ extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_p
             } else {
                 (void)cudaGetLastError();
                 ksv = kev = nullptr;
+            }
+            {   // noise variant (optional)
+                cudaKernel_t ksn = nullptr, ken = nullptr;
+                int metan[4] = {128, 0, 0, 0};
+                if (!m.noise_pos.empty() && cudaLibraryGetKernel(&ken, p->lib, ("k_evaln_" + m.name).c_str()) == cudaSuccess &&
+                    cudaLibraryGetKernel(&ksn, p->lib, ("k_setupn_" + m.name).c_str()) == cudaSuccess) {
+                    void* dmeta = nullptr;
+                    size_t msz = 0;
+                    CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_metan_" + m.name).c_str()));
+                    CUDA_TRY(cudaMemcpy(metan, dmeta, sizeof metan, cudaMemcpyDeviceToHost));
+                    if (metan[1] > 48 * 1024)
+                        CUDA_TRY(cudaFuncSetAttribute((const void*)ken, cudaFuncAttributeMaxDynamicSharedMemorySize, metan[1]));
+                } else {
+                    (void)cudaGetLastError();
+                    ksn = ken = nullptr;
+                }
+                p->k_setupn.push_back(ksn);
+                p->k_evaln.push_back(ken);
+                p->evaln_threads.push_back((unsigned)metan[0]);
+                p->evaln_smem.push_back((size_t)metan[1]);
             }
             p->k_setupv.push_back(ksv);
             p->k_evalv.push_back(kev);
@@ -1031,6 +1083,7 @@ extern "C" int cb_plan_set_params(cb_plan* p, const double* params) {
     }
     p->params_set = true;
     p->setup_valid = false;
+    p->setupn_valid = false;
     return CB_OK;
 }
 
@@ -1054,6 +1107,7 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     *d_params = p->d_params;
     p->params_set = true;   // caller writes the device buffer directly
     p->setup_valid = false;
+    p->setupn_valid = false;
     return CB_OK;
 }
 
@@ -1396,6 +1450,190 @@ extern "C" int cb_tran(cb_plan* p, double t0, double t1, const double* saveat, i
     if (status) CUDA_TRY(cudaMemcpy(status, p->na.ist + (size_t)IS_STATUS * B, B * sizeof(int), cudaMemcpyDeviceToHost));
     if (stats) stats->d2h_seconds = now_s() - t;
     return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small-signal analyses about the DC operating point (reference: ac! / noise!, src/ac.jl:75-190).
+static int ac_tables(cb_plan* p, bool noise) {
+    cb_circuit* c = p->c;
+    const cb::Symbolic& S = c->sym;
+    const int N = c->N;
+    int rc;
+#define TRY(x) do { rc = (x); if (rc != CB_OK) return rc; } while (0)
+    if (!p->ac_ready) {
+        int max_smem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+        p->ac_smem = (size_t)(S.nnz_lu + N) * AC_PTS * sizeof(double2);
+        if (p->ac_smem + sizeof(double) * AC_W * AC_PTS + 1024 > (size_t)max_smem)
+            return fail(CB_ERR_INVALID, "circuit too large for the shared-memory complex LU of cb_ac / cb_noise");
+        CUDA_TRY(cudaFuncSetAttribute(k_ac<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ac_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_ac<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ac_smem));
+        int* ti;
+        TRY(p->upload(&ti, S.u_col)); p->aa.u_col = ti;
+        TRY(p->upload(&ti, c->a_csrc)); p->aa.a_csrc = ti;
+        // b = -dF/d(eps): sources are dc + eps |ac| (src/simpledevices.jl:292-294, :331-333)
+        std::vector<double> rhs(N, 0.0);
+        for (const cb_device& d : c->devs) {
+            if (d.wave < 0) continue;
+            const double ac = c->waves[d.wave].ac_mag;
+            if (d.kind == CB_DEV_VSRC) rhs[S.row_to_step[d.branch]] += ac;
+            else if (d.kind == CB_DEV_ISRC) {
+                if (d.n[0] >= 0) rhs[S.row_to_step[d.n[0]]] -= d.mult * ac;
+                if (d.n[1] >= 0) rhs[S.row_to_step[d.n[1]]] += d.mult * ac;
+            }
+        }
+        TRY(p->upload(&p->d_ac_rhs, rhs)); p->aa.ac_rhs = p->d_ac_rhs;
+        p->ac_ready = true;
+    }
+    if (noise && !p->noise_ready) {
+        std::vector<ResTab> rt;
+        for (const cb_device& d : c->devs) {
+            if (d.kind != CB_DEV_R) continue;
+            ResTab r{};
+            r.pos = d.n[0] < 0 ? -1 : S.row_to_step[d.n[0]];
+            r.neg = d.n[1] < 0 ? -1 : S.row_to_step[d.n[1]];
+            r.r.value = d.value.value; r.r.col = d.value.col; r.r.pad = 0;
+            r.mult = d.mult;
+            rt.push_back(r);
+        }
+        std::vector<NoiseTab> nt;
+        long long rows = 0, slots = 0;
+        p->noise_off.assign(c->models.size(), 0);
+        p->cachen_off.assign(c->models.size(), 0);
+        for (size_t m = 0; m < c->models.size(); m++) {
+            const ModelH& M = c->models[m];
+            p->noise_off[m] = rows;
+            p->cachen_off[m] = slots;
+            const int K = (int)M.noise_pos.size();
+            if (K == 0 || c->model_insts[m].empty()) continue;
+            if (!p->k_evaln[m]) return fail(CB_ERR_STATE, "model " + M.name + " has noise sources but the CUDA source has no noise variant");
+            for (size_t k = 0; k < c->model_insts[m].size(); k++) {
+                const VaInstH& v = c->insts[c->model_insts[m][k]];
+                for (int s = 0; s < K; s++) {
+                    NoiseTab t{};
+                    const int tp = M.noise_pos[s] < 0 ? -1 : v.term[M.noise_pos[s]];
+                    const int tn = M.noise_neg[s] < 0 ? -1 : v.term[M.noise_neg[s]];
+                    if (tp == tn) continue;
+                    t.pos = tp < 0 ? -1 : S.row_to_step[tp];
+                    t.neg = tn < 0 ? -1 : S.row_to_step[tn];
+                    t.pwr_row = (int)(rows + (long long)k * 2 * K + s);
+                    t.exp_row = t.pwr_row + K;
+                    t.mult = v.mult;
+                    nt.push_back(t);
+                }
+            }
+            rows += (long long)c->model_insts[m].size() * 2 * K;
+            slots += (long long)c->model_insts[m].size() * std::max(1, M.ncache_n);
+        }
+        ResTab* dr; NoiseTab* dn;
+        TRY(p->upload(&dr, rt)); TRY(p->upload(&dn, nt));
+        p->aa.rtab = dr; p->aa.ntab = dn; p->aa.nres = (int)rt.size(); p->aa.nnoise = (int)nt.size();
+        TRY(p->alloc(&p->d_noise_out, (size_t)std::max<long long>(1, rows) * p->B));
+        TRY(p->alloc(&p->d_cachen, (size_t)std::max<long long>(1, slots) * p->Bpad));
+        p->aa.noise_out = p->d_noise_out;
+        p->noise_ready = true;
+    }
+#undef TRY
+    return CB_OK;
+}
+
+static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, const cb_options* opt, double* out,
+                        int32_t* status, cb_stats* stats) {
+    if (!p || !opt || !freqs || F <= 0 || !out) return fail(CB_ERR_INVALID, "null argument");
+    for (int64_t k = 0; k < F; k++)
+        if (!(freqs[k] > 0.0) || !std::isfinite(freqs[k])) return fail(CB_ERR_INVALID, "frequencies must be positive");
+    if (F > 65535) return fail(CB_ERR_INVALID, "more than 65535 frequencies in one call");
+    cb_circuit* c = p->c;
+    int rc = solve(p, opt, true, 0.0, 1.0, nullptr, 0, stats);   // operating point, X left on the device
+    if (rc != CB_OK) return rc;
+    rc = ac_tables(p, noise);
+    if (rc != CB_OK) return rc;
+    const long long B = p->B;
+    NArgs& a = p->na;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    CUDA_TRY(cudaEventRecord(e0, p->stream));
+    // linearisation: one full device evaluation at the operating point with alpha = 0 -> G rows and C rows of dev_out
+    k_ac_prepare<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.active, a.alpha);
+    CUDA_TRY(cudaGetLastError());
+    int64_t launches = 1;
+    for (size_t m = 0; m < c->models.size(); m++) {
+        if (c->model_insts[m].empty()) continue;
+        char args[256];
+        fill_va_args(p, m, opt, args);
+        void* kargs[] = {args};
+        dim3 grid((unsigned)((B + p->eval_threads[m] - 1) / p->eval_threads[m]), (unsigned)c->model_insts[m].size());
+        CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(p->eval_threads[m]), kargs, p->eval_smem[m], p->stream));
+        launches++;
+    }
+    if (noise) {
+        struct VaArgsHead { long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out; };
+        for (size_t m = 0; m < c->models.size(); m++) {
+            const ModelH& M = c->models[m];
+            if (c->model_insts[m].empty() || M.noise_pos.empty()) continue;
+            char args[256];
+            fill_va_args(p, m, opt, args);
+            VaArgsHead* h = (VaArgsHead*)args;
+            h->cache = p->d_cachen + (size_t)p->cachen_off[m] * p->Bpad;
+            h->out = p->d_noise_out + (size_t)p->noise_off[m] * B;
+            void* kargs[] = {args};
+            if (!p->setupn_valid) {
+                dim3 g((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());
+                CUDA_TRY(cudaLaunchKernel((const void*)p->k_setupn[m], g, dim3(128), kargs, 0, p->stream));
+                launches++;
+            }
+            dim3 grid((unsigned)((B + p->evaln_threads[m] - 1) / p->evaln_threads[m]), (unsigned)c->model_insts[m].size());
+            CUDA_TRY(cudaLaunchKernel((const void*)p->k_evaln[m], grid, dim3(p->evaln_threads[m]), kargs, p->evaln_smem[m], p->stream));
+            launches++;
+        }
+        p->setupn_valid = true;
+    }
+    double* d_freqs = nullptr;
+    double* d_out = nullptr;
+    const size_t out_count = (size_t)a.O * (size_t)F * (size_t)B * (noise ? 1 : 2);
+    CUDA_TRY(cudaMalloc((void**)&d_freqs, (size_t)F * sizeof(double)));
+    if (cudaMalloc((void**)&d_out, std::max<size_t>(1, out_count) * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_freqs);
+        return fail(CB_ERR_CUDA, "cudaMalloc of the small-signal result failed");
+    }
+    cudaMemcpyAsync(d_freqs, freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+    AArgs aa = p->aa;
+    aa.n = a; aa.freqs = d_freqs; aa.F = (int)F; aa.out = d_out;
+    aa.temp_val = opt->temp.value; aa.temp_col = opt->temp.col;
+    const dim3 grid((unsigned)((B + AC_PTS - 1) / AC_PTS), (unsigned)F);
+    if (noise) k_ac<true><<<grid, AC_PTS * AC_W, p->ac_smem, p->stream>>>(aa);
+    else k_ac<false><<<grid, AC_PTS * AC_W, p->ac_smem, p->stream>>>(aa);
+    launches++;
+    cudaError_t err = cudaGetLastError();
+    cudaEventRecord(e1, p->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(p->stream);
+    const double t = now_s();
+    if (err == cudaSuccess && out_count) err = cudaMemcpy(out, d_out, out_count * sizeof(double), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && status)
+        err = cudaMemcpy(status, a.ist + (size_t)IS_STATUS * B, B * sizeof(int), cudaMemcpyDeviceToHost);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_freqs); cudaFree(d_out);
+    if (err != cudaSuccess) return fail(CB_ERR_CUDA, std::string("small-signal solve: ") + cudaGetErrorString(err));
+    if (stats) {
+        stats->d2h_seconds = now_s() - t;
+        stats->newton_seconds += ms * 1e-3;   // linearisation + complex LU of all (point, frequency) systems
+        stats->solve_seconds += ms * 1e-3;
+        stats->kernel_launches += launches;
+        stats->lu_factors += (int64_t)B * F;
+    }
+    return CB_OK;
+}
+
+extern "C" int cb_ac(cb_plan* p, const double* freqs, int64_t n_freq, const cb_options* opt, double* y_out, int32_t* status,
+                     cb_stats* stats) {
+    return small_signal(p, false, freqs, n_freq, opt, y_out, status, stats);
+}
+
+extern "C" int cb_noise(cb_plan* p, const double* freqs, int64_t n_freq, const cb_options* opt, double* psd, int32_t* status,
+                        cb_stats* stats) {
+    return small_signal(p, true, freqs, n_freq, opt, psd, status, stats);
 }
 
 extern "C" int cb_plan_set_timing(cb_plan* p, int enable) {

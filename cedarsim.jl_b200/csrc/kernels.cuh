@@ -765,6 +765,212 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
 #undef VL
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Small-signal analyses (cb_ac / cb_noise; reference ac!/noise!, src/ac.jl:75-190, :257-284).
+//
+// After the DC operating point one more device evaluation with alpha = 0 leaves G = dI/dV in the J rows of dev_out
+// and C = dQ/dV in the rows next to them.  k_ac then factors the complex matrix A = G + j w C of every
+// (sweep point, frequency) pair with the SAME static pivot order and fill pattern as the Newton matrix:
+//   CTA = AC_PTS consecutive sweep points at one frequency (blockIdx.y); lane = point, AC_W groups of lanes split the
+//   work of every phase by matrix entry.  The factors of the AC_PTS systems live in shared memory as double2
+//   (re, im), [entry][lane]: consecutive lanes are consecutive sweep points, so the dev_out gathers are coalesced
+//   and the shared-memory accesses of a half-warp are one contiguous 256-byte row.
+//   1. assembly  (lin_g + j w lin_c for the built-in devices, a_ptr / a_src gather lists for the Verilog-A stamps)
+//   2. right-looking elimination, pivot by pivot (two barriers per pivot; L is kept unscaled, pivots inverted)
+//   3. AC:    forward / backward substitution with b = -dF/d(eps) (sources with ac_mag), outputs x[out]
+//      noise: one adjoint solve per output, A^T y = e_out  (U^T forward, L^T backward), then
+//             PSD = sum_k |y[pos_k] - y[neg_k]|^2 pwr_k / f^exp_k  over resistors (4 k T m / R) and the noise sources
+//             of the Verilog-A devices (k_evaln_<model> outputs), summed by all groups and reduced through shared memory.
+// Substitutions are sequential per system (one group of lanes does them): they are ~nnz complex multiply-adds
+// against ~flops/AC_W per group for the elimination plus 2 N barriers.
+#define AC_PTS 16
+#define AC_W 16
+struct NoiseTab { int pos, neg, pwr_row, exp_row; double mult; };   // pos / neg: elimination step of the KCL row or -1
+struct ResTab { int pos, neg, pad0, pad1; Pref r; double mult; };
+struct AArgs {
+    NArgs n;
+    const int* u_col;
+    const int* a_csrc;        // dev_out row of dQ/dV for every a_src item
+    const double* freqs;      // [F]
+    const double* ac_rhs;     // [N] in elimination-step order (AC)
+    const NoiseTab* ntab;     // Verilog-A noise sources
+    const ResTab* rtab;       // resistors
+    const double* noise_out;  // [rows][B] outputs of k_evaln_*
+    int nnoise, nres, F, pad;
+    double temp_val; int temp_col, pad2;
+    double* out;              // AC: [O][F][B][2]; noise: [O][F][B]
+};
+
+__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 crcp(const double2 a) {
+    // Smith's formula: no overflow / underflow of re^2 + im^2 (entries span ~1e-20 .. 1e+3 over 17 decades of frequency)
+    if (fabs(a.x) >= fabs(a.y)) {
+        const double r = a.y / a.x, d = a.x + a.y * r;
+        return make_double2(1.0 / d, -r / d);
+    }
+    const double r = a.x / a.y, d = a.x * r + a.y;
+    return make_double2(r / d, -1.0 / d);
+}
+
+template <bool NOISE>
+__global__ void __launch_bounds__(AC_PTS * AC_W) k_ac(const AArgs c) {
+    extern __shared__ double2 av_[];
+    __shared__ double s_acc[AC_W][AC_PTS];
+    const NArgs& a = c.n;
+    const long long B = a.B;
+    const int lane = threadIdx.x % AC_PTS, w = threadIdx.x / AC_PTS;
+    const long long i0 = (long long)blockIdx.x * AC_PTS + lane;
+    const bool on = i0 < B;
+    const long long inst = on ? i0 : B - 1;   // idle lanes shadow the last point, never store
+    const int fi = blockIdx.y;
+    const double freq = c.freqs[fi], omega = 6.283185307179586476925286766559 * freq;
+    const int N = a.N, nnz = a.nnz_lu;
+    double2* __restrict__ vals = av_ + lane;
+#define VA(i) vals[(size_t)(i) * AC_PTS]
+    const double* __restrict__ od = a.dev_out + inst;
+    // ---- 1. assembly
+    for (int e = w; e < nnz; e += AC_W) {
+        double2 v = make_double2(0.0, 0.0);
+        const int lin = a.a_lin[e];
+        if (lin >= 0) {
+            const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            v.x = a.lin_g[li];
+            v.y = omega * a.lin_c[li];
+        }
+        for (int q = a.a_ptr[e]; q < a.a_ptr[e + 1]; q++) {
+            const double m = a.a_mult[q];
+            v.x += m * __ldg(od + (size_t)a.a_src[q] * B);
+            v.y += m * omega * __ldg(od + (size_t)c.a_csrc[q] * B);
+        }
+        VA(e) = v;
+    }
+    for (int i = w; i < N; i += AC_W) VA(nnz + i) = make_double2(NOISE ? 0.0 : c.ac_rhs[i], 0.0);
+    __syncthreads();
+    // ---- 2. elimination
+    for (int k = 0; k < N; k++) {
+        const int dp = a.diag_pos[k];
+        const int l0 = a.l_ptr[k], nl = a.l_ptr[k + 1] - l0, u0 = a.u_ptr[k], nu = a.u_ptr[k + 1] - u0;
+        if (nl == 0 || nu == 0) {
+            if (w == 0) VA(dp) = crcp(VA(dp));
+            if (nl > 0) __syncthreads();   // the substitutions read the inverted pivot after the final barrier otherwise
+            continue;
+        }
+        const double2 inv = crcp(VA(dp));
+        __syncthreads();                    // every group has read the pivot
+        if (w == 0) VA(dp) = inv;
+        const int p0 = a.pair_ptr[k], np = nl * nu;
+        for (int q = w; q < np; q += AC_W) {
+            const int li = q / nu, uj = q - li * nu;
+            const double2 l = cmul(VA(a.l_pos[l0 + li]), inv);
+            const double2 u = VA(a.u_pos[u0 + uj]);
+            const double2 t = cmul(l, u);
+            double2 d = VA(a.pair_dst[p0 + q]);
+            d.x -= t.x; d.y -= t.y;
+            VA(a.pair_dst[p0 + q]) = d;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (!NOISE) {
+        // ---- 3a. A x = b: forward with M = L D^-1 (unit lower), backward with U
+        if (w == 0) {
+            for (int k = 0; k < N; k++) {
+                const double2 bk = cmul(VA(nnz + k), VA(a.diag_pos[k]));
+                for (int p = a.l_ptr[k]; p < a.l_ptr[k + 1]; p++) {
+                    const double2 t = cmul(VA(a.l_pos[p]), bk);
+                    double2 d = VA(nnz + a.l_row[p]);
+                    d.x -= t.x; d.y -= t.y;
+                    VA(nnz + a.l_row[p]) = d;
+                }
+            }
+            for (int k = N - 1; k >= 0; k--) {
+                double2 acc = VA(nnz + k);
+                for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) {
+                    const double2 t = cmul(VA(a.u_pos[u]), VA(nnz + c.u_col[u]));
+                    acc.x -= t.x; acc.y -= t.y;
+                }
+                VA(nnz + k) = cmul(acc, VA(a.diag_pos[k]));
+            }
+            if (on)
+                for (int o = 0; o < a.O; o++) {
+                    const double2 x = VA(nnz + a.col_to_step[a.outputs[o]]);
+                    double2* dst = (double2*)c.out + ((size_t)o * c.F + fi) * B + inst;
+                    *dst = x;
+                }
+        }
+    } else {
+        const double temp_c = c.temp_col >= 0 ? a.params[(size_t)c.temp_col * B + inst] : c.temp_val;
+        const double kT4 = 4.0 * 1.380649e-23 * (temp_c + 273.15);
+        for (int o = 0; o < a.O; o++) {
+            // ---- 3b. A^T y = e_out:  U^T w = e (forward, column-oriented over the rows of U), then M^T y = w
+            if (w == 0) {
+                for (int i = 0; i < N; i++) VA(nnz + i) = make_double2(0.0, 0.0);
+                VA(nnz + a.col_to_step[a.outputs[o]]) = make_double2(1.0, 0.0);
+                for (int k = 0; k < N; k++) {
+                    const double2 wk = cmul(VA(nnz + k), VA(a.diag_pos[k]));
+                    VA(nnz + k) = wk;
+                    for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) {
+                        const double2 t = cmul(VA(a.u_pos[u]), wk);
+                        double2 d = VA(nnz + c.u_col[u]);
+                        d.x -= t.x; d.y -= t.y;
+                        VA(nnz + c.u_col[u]) = d;
+                    }
+                }
+                for (int k = N - 1; k >= 0; k--) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int p = a.l_ptr[k]; p < a.l_ptr[k + 1]; p++) {
+                        const double2 t = cmul(VA(a.l_pos[p]), VA(nnz + a.l_row[p]));
+                        acc.x += t.x; acc.y += t.y;
+                    }
+                    const double2 t = cmul(acc, VA(a.diag_pos[k]));
+                    double2 y = VA(nnz + k);
+                    y.x -= t.x; y.y -= t.y;
+                    VA(nnz + k) = y;
+                }
+            }
+            __syncthreads();
+            // ---- 4. PSD: every group sums a slice of the sources
+            double acc = 0.0;
+            for (int q = w; q < c.nres; q += AC_W) {
+                const ResTab r = c.rtab[q];
+                double2 h = make_double2(0.0, 0.0);
+                if (r.pos >= 0) h = VA(nnz + r.pos);
+                if (r.neg >= 0) { const double2 g = VA(nnz + r.neg); h.x -= g.x; h.y -= g.y; }
+                acc += (h.x * h.x + h.y * h.y) * (kT4 * r.mult / pv(r.r, a.params, B, inst));
+            }
+            for (int q = w; q < c.nnoise; q += AC_W) {
+                const NoiseTab t = c.ntab[q];
+                double2 h = make_double2(0.0, 0.0);
+                if (t.pos >= 0) h = VA(nnz + t.pos);
+                if (t.neg >= 0) { const double2 g = VA(nnz + t.neg); h.x -= g.x; h.y -= g.y; }
+                const double pw = __ldg(c.noise_out + (size_t)t.pwr_row * B + inst);
+                const double ex = __ldg(c.noise_out + (size_t)t.exp_row * B + inst);
+                acc += (h.x * h.x + h.y * h.y) * t.mult * (ex == 0.0 ? pw : pw / pow(freq, ex));
+            }
+            s_acc[w][lane] = acc;
+            __syncthreads();
+            if (w == 0 && on) {
+                double tot = 0.0;
+#pragma unroll
+                for (int k = 0; k < AC_W; k++) tot += s_acc[k][lane];
+                c.out[((size_t)o * c.F + fi) * B + inst] = tot;
+            }
+            __syncthreads();
+        }
+    }
+#undef VA
+}
+
+// marks every point as taking part in the next (full) device evaluation with alpha = 0: G and C come out separately
+__global__ void k_ac_prepare(long long B, int* active, double* alpha) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    active[inst] = ACT_FULL;
+    alpha[inst] = 0.0;
+}
+
 __global__ void k_init_waves(const NArgs a, double* WV) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= a.B) return;

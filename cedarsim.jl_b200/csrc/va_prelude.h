@@ -237,6 +237,14 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #ifndef VA_EVALV_MINBLOCKS
 #define VA_EVALV_MINBLOCKS 5
 #endif
+// noise variant (k_setupn_* / k_evaln_*: power and flicker exponent of every noise source at the operating point,
+// rows [source] and [NNOISE + source] of its own output block; its own cache; used by cb_noise only)
+#define VA_SETUPN_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupn_##NAME)
+#define VA_SETUPN_END(NAME) }
+#define VA_EVALN_BEGIN(NAME) VA_EVAL_BEGIN_(k_evaln_##NAME, va_metan_##NAME, 1)
+#define VA_EVALN_END(NAME) VA_EVAL_END(NAME)
+#define OUT_N(k, v) out_[(size_t)(k) * a.B] = (v)
+#define OUT_NE(k, v) out_[(size_t)(NNOISE + (k)) * a.B] = (v)
 #define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
 #define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
 #define VA_EVALV_END(NAME) VA_EVAL_END(NAME)

@@ -23,7 +23,7 @@ _lib = None
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_options_default", "cb_circuit_create", "cb_circuit_set_cuda_source",
     "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_set_params", "cb_dc", "cb_tran",
-    "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
+    "cb_ac", "cb_noise", "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
 ]
 
 
@@ -78,6 +78,11 @@ def cuda_source(models: Sequence) -> str:
         if getattr(cm, "source_v", ""):   # value-only variant: its own cache layout
             parts.append(f"#undef NCACHE\n#define NCACHE {max(1, cm.ncache_v)}\n")
             parts.append(cm.source_v)
+        if getattr(cm, "source_n", ""):   # noise variant: source powers at the operating point (cb_noise)
+            K = len(cm.noise_sources)
+            parts.append(f"#undef NCACHE\n#undef NOUT\n#undef NNOISE\n#define NCACHE {max(1, cm.ncache_n)}\n"
+                         f"#define NNOISE {K}\n#define NOUT {2 * K}\n")
+            parts.append(cm.source_n)
     return "\n".join(parts)
 
 
@@ -184,6 +189,26 @@ class Plan:
         _check(self.lib.cb_tran(self.handle, C.c_double(t0), C.c_double(t1), _dp(saveat), C.c_int64(S), C.byref(opts),
                                 _dp(y), status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
         return y, status, st.as_dict()
+
+    def _small_signal(self, fn, freqs, opts, width):
+        opts = opts or default_options()
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        O, Fq = len(self.circuit.fc.outputs), len(freqs)
+        out = np.zeros((O, Fq, self.B) + ((2,) if width == 2 else ()))
+        status = np.zeros(self.B, dtype=np.int32)
+        st = F.cb_stats()
+        _check(fn(self.handle, _dp(freqs), C.c_int64(Fq), C.byref(opts), _dp(out),
+                  status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return out, status, st.as_dict()
+
+    def ac(self, freqs, opts: Optional[F.cb_options] = None):
+        """AC response of the outputs about every point's operating point: (y complex [O, F, B], status, stats)."""
+        out, status, st = self._small_signal(self.lib.cb_ac, freqs, opts, 2)
+        return out[..., 0] + 1j * out[..., 1], status, st
+
+    def noise(self, freqs, opts: Optional[F.cb_options] = None):
+        """Output noise PSD about every point's operating point: (psd [O, F, B], status, stats)."""
+        return self._small_signal(self.lib.cb_noise, freqs, opts, 1)
 
     def tran_device(self, t0: float, t1: float, saveat, opts: Optional[F.cb_options] = None):
         """Results stay in HBM; returns (device pointer of y, device pointer of status, stats)."""

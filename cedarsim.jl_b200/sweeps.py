@@ -499,6 +499,69 @@ def tran_(cs: CircuitSweep, tspan: Optional[Tuple[float, float]] = None, saveat=
     return SweepSolution(cs, y, status, _merge_stats([r[2] for r in res]), saveat)
 
 
+class FreqSolution:
+    """Result of ac_ / noise_: per sweep point the small-signal response about its DC operating point.
+    Mirrors how the reference's ACSol / NoiseSol are queried (src/ac.jl:257-284): `freqresp(sol, ref)` /
+    `PSD(sol, ref)` give arrays shaped size(cs) + (len(freqs),)."""
+
+    def __init__(self, cs: "CircuitSweep", y: np.ndarray, status: np.ndarray, stats: dict, freqs: np.ndarray, kind: str):
+        self.cs, self.fc, self.y, self.status, self.stats, self.freqs, self.kind = cs, cs.flat.fc, y, status, stats, freqs, kind
+        self.shape = cs.shape
+        self.out_index = {u: k for k, u in enumerate(self.fc.outputs)}
+
+    def __len__(self):
+        return len(self.status)
+
+    def array(self, ref) -> np.ndarray:
+        o = self.out_index[_resolve(self.fc, ref)]
+        return np.moveaxis(self.y[o], 0, -1).reshape(self.shape + (len(self.freqs),), order="F")
+
+    def point(self, idx, ref) -> np.ndarray:
+        i = int(idx) if isinstance(idx, (int, np.integer)) else int(np.ravel_multi_index(tuple(idx), self.shape, order="F"))
+        return self.y[self.out_index[_resolve(self.fc, ref)], :, i]
+
+    @property
+    def retcodes(self) -> np.ndarray:
+        return np.array([RETCODES[int(s)] for s in self.status]).reshape(self.shape, order="F")
+
+
+def acdec(nd: int, fstart: float, fstop: float) -> np.ndarray:
+    """`.ac dec nd fstart fstop` frequency vector in Hz (src/ac.jl:286-303)."""
+    a, b = np.log10(fstart), np.log10(fstop)
+    return 10.0 ** np.linspace(a, b, int(np.ceil((b - a) * nd)) + 1)
+
+
+def ac_(cs: CircuitSweep, freqs, **kw) -> FreqSolution:
+    """ac!(circ) for every sweep point (src/ac.jl:166-180; the reference has no CircuitSweep method): complex
+    response of the outputs to the sources carrying `AC mag`.  `freqs` in Hz (the reference's freqresp takes
+    omega = 2 pi f)."""
+    freqs = np.asarray(freqs, dtype=float)
+    opts = cs._options(kw)
+    res = cs._run(lambda plan: plan.ac(freqs, opts))
+    y = np.concatenate([r[0] for r in res], axis=2)
+    status = np.concatenate([r[1] for r in res])
+    return FreqSolution(cs, y, status, _merge_stats([r[2] for r in res]), freqs, "ac")
+
+
+def noise_(cs: CircuitSweep, freqs, **kw) -> FreqSolution:
+    """noise!(circ) for every sweep point (src/ac.jl:182-190): output noise power spectral density
+    PSD(sol, ref, 2 pi f) (src/ac.jl:265-284), V^2/Hz."""
+    freqs = np.asarray(freqs, dtype=float)
+    opts = cs._options(kw)
+    res = cs._run(lambda plan: plan.noise(freqs, opts))
+    y = np.concatenate([r[0] for r in res], axis=2)
+    status = np.concatenate([r[1] for r in res])
+    return FreqSolution(cs, y, status, _merge_stats([r[2] for r in res]), freqs, "noise")
+
+
+def freqresp(sol: FreqSolution, ref) -> np.ndarray:
+    return sol.array(ref)
+
+
+def PSD(sol: FreqSolution, ref) -> np.ndarray:
+    return sol.array(ref)
+
+
 def _merge_stats(stats: List[dict]) -> dict:
     out = dict(stats[0])
     for s in stats[1:]:
@@ -509,3 +572,5 @@ def _merge_stats(stats: List[dict]) -> dict:
 
 dc = dc_
 tran = tran_
+ac = ac_
+noise = noise_

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in cedarb200.h but not exported"
     assert set(engine.SYMBOLS) <= set(syms)
-    assert lib.cb_version() == 1
+    assert lib.cb_version() == 2
 
 
 def test_options_defaults_and_struct_layout():

@@ -17,7 +17,7 @@ import os
 import numpy as np
 import pytest
 
-from cedarsim.jl_b200 import netlist
+from cedarsim.jl_b200 import circuits, netlist
 from oracle import orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -34,22 +34,7 @@ R4 vout 0 '2*res'
 R5 vout 0 '2*res'
 """
 
-BSIMCMG_INVERTER = """** Test circuit
-.include "jlpkg://ASAP7PDK/7nm_TT.pm"
-
-* built-in
-mneg Q D VSS VSS nmos_lvt
-mpos Q D VDD VDD pmos_lvt
-
-VVDD VDD 0 1.0
-VVSS VSS 0 0.0
-CQ D 0 1e-15
-VD D 0 AC 1 SIN (0.5 0.01 1e7)
-
-.TRAN 1e-9 4.0e-7
-
-.END
-"""
+BSIMCMG_INVERTER = circuits.BSIMCMG_INVERTER_DECK   # test/bsimcmg/inverter_cmg_cedar.cir
 
 
 def acdec(nd, fstart, fstop):   # src/ac.jl:286-303
@@ -110,8 +95,7 @@ def test_bsimcmg_inverter_noise_vs_ngspice(host_bsimcmg):   # test/ac.jl:161-237
 
 def test_bsimcmg_inverter_ac_gain_matches_finite_difference(host_bsimcmg):
     """AC gain at low frequency == slope of the DC transfer curve (ties cb_ac's linearisation to the DC solver)."""
-    fl = netlist.flatten(netlist.parse_netlist(BSIMCMG_INVERTER.replace("VD D 0 AC 1 SIN (0.5 0.01 1e7)", "VD D 0 DC 'vin' AC 1")
-                                               .replace("* built-in", ".param vin=0.5")),
+    fl = netlist.flatten(netlist.parse_netlist(circuits.BSIMCMG_INVERTER_VIN_DECK),
                          {"vin": np.array([0.5 - 1e-5, 0.5, 0.5 + 1e-5])}, outputs=["q"], host=True)
     x, _, st, _ = orc.dc(fl.fc, fl.params)
     assert st.max() == 0
