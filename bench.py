@@ -179,7 +179,6 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
-    plan.set_timing(True)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -194,7 +193,19 @@ def main():
     barrier()
     el = time.perf_counter() - t0
     sampler.stop_flag.set()
-    plan.set_timing(False)
+    # ---- per-kernel timing for the roofline: the same step on a single-lane plan with CUDA events around every launch
+    # (in the timed region above the plan's lanes run concurrently, so a kernel's launch duration there includes the
+    # SMs it shares with other lanes' kernels; timed alone it is the figure the roofline peak is quoted for)
+    plan1 = circuit.plan(B, device=local, lanes=1)
+    plan1.set_x0(nodeset(fc))
+    plan1.set_params(P)
+    plan1.tran_device(T0, T1, ts, opts)
+    plan1.set_timing(True)
+    _, _, st1 = plan1.tran_device(T0, T1, ts, opts)
+    plan1.close()
+    for k in ("eval_seconds", "newton_seconds", "evalv_seconds", "newtonv_seconds", "solve_seconds", "full_iters", "value_rounds", "rounds",
+              "newton_iters"):
+        tot[k + "_1"] = st1[k]
     if world > 1:
         tmax = torch.tensor([el, tot["solve_seconds"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -242,20 +253,23 @@ def main():
                 traffic = json.load(f).get("k_eval_dram_bytes_per_launch")
         except OSError:
             pass
-        ev, nw = tot["eval_seconds"], tot["newton_seconds"]
+        ev, nw = tot["eval_seconds_1"], tot["newton_seconds_1"]
+        solve1 = max(tot["solve_seconds_1"], 1e-30)
         # k_eval_* runs in the full rounds only: full_iters point-iterations x FETs device evaluations
-        achieved = (tot["full_iters"] * n_fets * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
+        achieved = (tot["full_iters_1"] * n_fets * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
         roofline = {"bound": "fp64", "kernel": "k_eval_bsimcmg107_*", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
                     "peak_source": "FP64 DFMA microbenchmark run live in this process (MEASURED_PEAKS.json has no FP64 figure; its "
                                    f"hbm_gbs = {peaks.get('hbm_gbs')} is the denominator for the HBM-bound k_lu / k_control)",
-                    "flops_per_device_eval": flops_per_eval, "device_evals": tot["full_iters"] * n_fets,
-                    "kernel_seconds": ev, "share_of_step": ev / max(tot["solve_seconds"], 1e-30),
-                    "k_lu_control_seconds": nw, "k_lu_control_share": nw / max(tot["solve_seconds"], 1e-30),
-                    "value_rounds": {"rounds": tot["value_rounds"], "of_rounds": tot["rounds"],
-                                     "point_iterations": tot["newton_iters"] - tot["full_iters"],
-                                     "k_evalv_seconds": tot["evalv_seconds"], "k_lu_solve_control_seconds": tot["newtonv_seconds"],
-                                     "share_of_step": (tot["evalv_seconds"] + tot["newtonv_seconds"]) / max(tot["solve_seconds"], 1e-30)}}
+                    "how": "one extra step of the same workload on a single-lane plan with CUDA events around every launch "
+                           "(kernels timed alone); the timed region runs the plan's lanes concurrently",
+                    "flops_per_device_eval": flops_per_eval, "device_evals": tot["full_iters_1"] * n_fets,
+                    "kernel_seconds": ev, "share_of_step": ev / solve1, "single_lane_step_seconds": solve1,
+                    "k_lu_control_seconds": nw, "k_lu_control_share": nw / solve1,
+                    "value_rounds": {"rounds": tot["value_rounds_1"], "of_rounds": tot["rounds_1"],
+                                     "point_iterations": tot["newton_iters_1"] - tot["full_iters_1"],
+                                     "k_evalv_seconds": tot["evalv_seconds_1"], "k_lu_solve_control_seconds": tot["newtonv_seconds_1"],
+                                     "share_of_step": (tot["evalv_seconds_1"] + tot["newtonv_seconds_1"]) / solve1}}
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             threads = os.cpu_count() or 1
@@ -268,7 +282,7 @@ def main():
             "metric": "transient sweep points/s (DFF Monte-Carlo)", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu": B, "unknowns": fc.n_unknowns, "fets": n_fets, "swept_params": len(fc.param_names),
+            "config": {"workload": WORKLOAD, "points_per_gpu": B, "unknowns": fc.n_unknowns, "fets": n_fets, "swept_params": len(fc.param_names), "lanes_per_gpu": plan.lanes,
                        "l2": "per-round working set (cached device constants + device outputs, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
             "newton_iters_per_s": newton_all / el, "newton_iters_per_step": newton_all / args.steps,
             "lu": circuit.lu_info(),
