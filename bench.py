@@ -140,6 +140,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -278,6 +282,8 @@ def main():
             cpu = {"value": pts / cel, "unit": "points/s", "cores": threads, "kind": "port",
                    "sample": f"{pts} of the {B} Monte-Carlo points, same tolerances and outputs, {cel:.1f}s",
                    "newton_iters_per_s": cstats["newton_iters"] / cel}
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps({
             "metric": "transient sweep points/s (DFF Monte-Carlo)", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
@@ -292,7 +298,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": roofline, "cpu_baseline": cpu,
             "parity_check": {"converged_points": ok_points, "of": B, "max_abs_q_error_vs_known_pattern_V": max(q_known)},
-        }))
+        }), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
