@@ -298,10 +298,61 @@ class ScopeRef:
 
 def _resolve(fc: FlatCircuit, ref: Union[str, ScopeRef]) -> int:
     key = ref._path if isinstance(ref, ScopeRef) else str(ref)
-    key = key.lower()
-    if key.endswith(".i") or key.endswith(".v"):
-        pass
-    return fc.unknown(key)
+    return fc.unknown(key.lower())
+
+
+class _Observable:
+    """A named result: an unknown, or a branch observable of a two-terminal primitive reconstructed from the node
+    voltages the way the reference does (src/simulate_ir.jl:112-120: `<inst>.V` = V(net+) - V(net-), `<inst>.I` flows
+    net+ -> net- through the device; src/simpledevices.jl:62-77 I = V/R, :99-109 I = C dV/dt)."""
+
+    def __init__(self, fc: FlatCircuit, ref: Union[str, ScopeRef]):
+        from .flat import DEV_C, DEV_R
+        key = (ref._path if isinstance(ref, ScopeRef) else str(ref)).lower()
+        self.key, self.terms, self.div, self.cap = key, [], None, None
+        try:
+            self.terms = [(1.0, fc.unknown(key))]
+            return
+        except KeyError:
+            pass
+        if not (key.endswith(".i") or key.endswith(".v")):
+            raise KeyError(f"no unknown or observable named {key!r}")
+        dev = next((d for d in fc.devices if d.name == key[:-2]), None)
+        if dev is None:
+            raise KeyError(f"no device named {key[:-2]!r}")
+        self.terms = [(sg, n) for sg, n in ((1.0, dev.nodes[0]), (-1.0, dev.nodes[1])) if n >= 0]
+        if key.endswith(".i"):
+            if dev.kind == DEV_R:
+                self.div = dev.value
+            elif dev.kind == DEV_C:
+                self.cap = dev.value
+            else:
+                raise KeyError(f"{key!r}: the current of this device kind is not reconstructible from node voltages")
+
+    def unknowns(self) -> List[int]:
+        return [u for _, u in self.terms]
+
+    def value(self, sol: "SweepSolution", pts) -> np.ndarray:
+        """values for the points `pts` (slice or index): DC -> [..], transient -> [S, ..]"""
+        y = sol.y
+        acc = 0.0
+        for sg, u in self.terms:
+            if u not in sol.out_index:
+                raise KeyError(f"{self.key!r} needs unknown {sol.fc.node_names[u] if u < sol.fc.n_nodes else u} among the outputs")
+            acc = acc + sg * y[sol.out_index[u]][..., pts]
+        acc = np.asarray(acc, dtype=float) if self.terms else np.zeros(np.shape(y[0][..., pts]))
+        for val, op in ((self.div, "div"), (self.cap, "cap")):
+            if val is None:
+                continue
+            from .flat import Col
+            v = sol.cs.flat.params[val.index][pts] if isinstance(val, Col) else float(val)
+            if op == "div":
+                acc = acc / v
+            elif sol.t is None:
+                acc = acc * 0.0                       # DC: no current through a capacitor
+            else:
+                acc = np.gradient(acc, sol.t, axis=0) * v
+        return acc
 
 
 class PointSolution:
@@ -323,11 +374,8 @@ class PointSolution:
         return self._p.t
 
     def __getitem__(self, ref):
-        u = _resolve(self._p.fc, ref)
-        o = self._p.out_index[u]
-        if self._p.t is None:
-            return float(self._p.y[o, self._i])
-        return self._p.y[o, :, self._i]
+        v = _Observable(self._p.fc, ref).value(self._p, self._i)
+        return float(v) if self._p.t is None else v
 
     def __call__(self, t, idxs=None):
         """sol(t; idxs=sys.node_q): linear interpolation of the saved waveform"""
@@ -366,10 +414,32 @@ class SweepSolution:
 
     def array(self, ref) -> np.ndarray:
         """values of one unknown over the whole sweep, shaped size(cs) (+ time axis last for tran)"""
-        o = self.out_index[_resolve(self.fc, ref)]
+        v = _Observable(self.fc, ref).value(self, slice(None))
         if self.t is None:
-            return self.y[o].reshape(self.shape, order="F")
-        return np.moveaxis(self.y[o], 0, -1).reshape(self.shape + (len(self.t),), order="F")
+            return v.reshape(self.shape, order="F")
+        return np.moveaxis(v, 0, -1).reshape(self.shape + (len(self.t),), order="F")
+
+    def default_name_map(self) -> Dict[str, str]:
+        """top-level nets among the outputs -> column name, `node_` stripped, ground left out (src/util.jl:239-260)"""
+        out = {}
+        for u in self.fc.outputs:
+            if u < self.fc.n_nodes and "." not in self.fc.node_names[u]:
+                out["node_" + self.fc.node_names[u]] = self.fc.node_names[u]
+        return out
+
+    def write_csv(self, file: str, index=0, name_map: Optional[Dict[str, str]] = None):
+        """CSV.write(file, sol) of one sweep point (ext/CedarSimCSVExt.jl:13-19): column `t` followed by one column
+        per entry of `name_map` (ScopeRef path -> column name; default: the top-level nets)."""
+        if self.t is None:
+            raise TypeError("write_csv needs a transient solution")
+        name_map = name_map or self.default_name_map()
+        pt = self[index]
+        cols = [("t", self.t)] + [(name, pt[ref]) for ref, name in name_map.items()]
+        with open(file, "w") as f:
+            f.write(",".join(n for n, _ in cols) + "\n")
+            for k in range(len(self.t)):
+                f.write(",".join(repr(float(c[k])) for _, c in cols) + "\n")
+        return file
 
     @property
     def retcodes(self) -> np.ndarray:

@@ -41,6 +41,7 @@ v1 vss 0 'v_in'
     for sol in sols:
         p = sol.params
         assert abs(p["v_in"] / p["x1.r_load"] + sol[cs.sys.v1.I]) < DEFTOL
+        assert abs(p["v_in"] / p["x1.r_load"] - sol[cs.sys.x1.r1.I]) < DEFTOL     # the reference's own accessor, test/sweep.jl:369
 
 
 def test_serial_and_tandem_sweeps_keep_defaults():

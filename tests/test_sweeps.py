@@ -99,3 +99,40 @@ def test_columns_column_major():
     c = s.columns()
     assert c["R1"].tolist() == [100.0, 200.0, 300.0, 100.0, 200.0, 300.0]
     assert c["R2"].tolist() == [1.0, 1.0, 1.0, 2.0, 2.0, 2.0]
+
+
+def test_branch_observables_and_csv(tmp_path):
+    """`sol[cs.sys.x1.r1.I]` as the reference's own sweep test reads it (test/sweep.jl:363-369), reconstructed from the
+    node voltages; results come from the CPU oracle here (the GPU run of the same accessors is in test_gpu_sweep_api)."""
+    import numpy as np
+    from cedarsim.jl_b200.sweeps import CircuitSweep, ProductSweep, Sweep, SweepSolution
+    from oracle import orc
+    text = """* Parameter scoping test
+.subckt subcircuit1 vss gnd
+.param r_load=1
+r1 vss gnd 'r_load'
+.ends
+.param v_in=1
+x1 vss 0 subcircuit1
+v1 vss 0 'v_in'
+"""
+    cs = CircuitSweep(text, ProductSweep(**{"v_in": np.arange(1.0, 11), "x1.r_load": np.arange(1.0, 11)}))
+    x, _, st, stats = orc.dc(cs.flat.fc, cs.flat.params)
+    sols = SweepSolution(cs, x, st, stats, None)
+    for sol in sols:
+        p = sol.params
+        assert abs(p["v_in"] / p["x1.r_load"] - sol[cs.sys.x1.r1.I]) < 1e-7      # test/sweep.jl:369
+        assert abs(sol[cs.sys.x1.r1.V] - p["v_in"]) < 1e-7 and abs(sol[cs.sys.v1.I] + sol[cs.sys.x1.r1.I]) < 1e-7
+    assert sols.array(cs.sys.x1.r1.I).shape == (10, 10)
+    # transient: capacitor current of an RC step == resistor current; CSV export of one point
+    rc = "* rc\n.param r=1k\nV1 in 0 PULSE(0 1 0 1n 1n 1 2)\nR1 in out 'r'\nC1 out 0 1n\n.tran 10n 5u\n"
+    cs = CircuitSweep(rc, Sweep(r=[500.0, 2000.0]))
+    ts = np.linspace(0, 5e-6, 501)
+    y, st, stats = orc.tran(cs.flat.fc, 0.0, 5e-6, ts, params=cs.flat.params, opts=orc.default_options(reltol=1e-6))
+    sols = SweepSolution(cs, y, st, stats, ts)
+    ir, ic = sols[1][cs.sys.r1.I], sols[1][cs.sys.c1.I]
+    assert np.abs(ir[5:-5] - ic[5:-5]).max() < 2e-3 * np.abs(ir).max()
+    f = sols.write_csv(str(tmp_path / "rc.csv"), index=1)
+    rows = open(f).read().splitlines()
+    assert rows[0] == "t,in,out" and len(rows) == 502
+    assert abs(float(rows[-1].split(",")[2]) - y[cs.flat.fc.outputs.index(cs.flat.fc.unknown("out")), -1, 1]) < 1e-15
