@@ -167,8 +167,41 @@ BSIMCMG_INVERTER_VIN_DECK = (BSIMCMG_INVERTER_DECK.replace("VD D 0 AC 1 SIN (0.5
                              .replace("* built-in", ".param vin=0.5"))
 
 
+# BASELINE config 5 stand-in (SURVEY.md 8(d)): corner x temperature x mismatch transient sweep of one cell.  sky130 /
+# BSIM4 are not in the reference tree, so the cell is the CMOS inverter of configs 1/2 on BSIM-CMG 107 + ASAP7 cards;
+# a process corner is a pair of threshold shifts and mobility factors through the model's own variability handles
+# (DELVTRAND, U0MULT: bsimcmg_body.include:133-137), temperature is SimSpec.temp, mismatch a draw of both gate lengths.
+CONFIG5_DECK = """* corner x temperature x mismatch sweep of an inverter (config 5 stand-in)
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+.param dvtn=0 dvtp=0 u0n=1 u0p=1 ln=21n lp=21n
+mneg q d vss vss nmos_lvt l='ln' nfin=3 delvtrand='dvtn' u0mult='u0n'
+mpos q d vdd vdd pmos_lvt l='lp' nfin=3 delvtrand='dvtp' u0mult='u0p'
+VVDD vdd 0 0.7
+VVSS vss 0 0.0
+VD d 0 PWL(0 0 0.5n 0 0.6n 0.7 1.5n 0.7 1.6n 0 2.5n 0)
+CQ q 0 1e-15
+.TRAN 0.01n 2.5n
+"""
+CONFIG5_CORNERS = {   # tt, ff, ss, fs (nFET fast / pFET slow) as (dvtn, dvtp, u0n, u0p).  In BSIM-CMG 107 DELVTRAND adds to the gate
+    # drive of either polarity (bsimcmg_body.include:2332), so a positive value is the fast (low-threshold) direction
+    "dvtn": [0.0, 0.03, -0.03, 0.03], "dvtp": [0.0, 0.03, -0.03, -0.03], "u0n": [1.0, 1.08, 0.92, 1.08], "u0p": [1.0, 1.08, 0.92, 0.92]}
+
+
+def config5_sweep(n_temp: int = 32, n_mismatch: int = 1024, seed: int = 130, sigma: float = 0.02):
+    """ProductSweep(corner (4, tandem) x temp (-40 .. 125 C) x mismatch (tandem of pre-drawn gate lengths)),
+    size (4, n_temp, n_mismatch); 4 x 32 x 1024 = 131 072 instances."""
+    from .sweeps import ProductSweep, Sweep, TandemSweep
+    rng = np.random.default_rng(seed)
+    z = np.clip(rng.standard_normal((n_mismatch, 2)), -3.0, 3.0)
+    return ProductSweep(TandemSweep(**CONFIG5_CORNERS), Sweep(temp=np.linspace(-40.0, 125.0, n_temp)),
+                        TandemSweep(ln=21e-9 * (1.0 + sigma * z[:, 0]), lp=21e-9 * (1.0 + sigma * z[:, 1])))
+
+
 def small_signal_decks():
-    """(deck text, swept columns) of the transistor-level small-signal tests; build() compiles them so that
-    the GPU box finds their cubins in the cache."""
+    """(deck text, swept columns) of the deck-based GPU tests; build() compiles them so that the GPU box finds
+    their cubins in the cache."""
+    one = np.array([1.0])
     return [(BSIMCMG_INVERTER_DECK, None),
-            (BSIMCMG_INVERTER_VIN_DECK, {"vin": np.array([0.5]), "mneg.nfin": np.array([1.0])})]
+            (BSIMCMG_INVERTER_VIN_DECK, {"vin": np.array([0.5]), "mneg.nfin": one}),
+            (CONFIG5_DECK, {"dvtn": 0 * one, "dvtp": 0 * one, "u0n": one, "u0p": one, "temp": 27 * one, "ln": 21e-9 * one,
+                            "lp": 21e-9 * one})]

@@ -77,3 +77,38 @@ def test_config2_inverter_product_sweep_65536(host_bsimcmg):
     assert so.max() == 0
     err = np.abs(y[:, :, sel] - yo)
     assert np.all(err <= 1e-6 * np.abs(yo) + 1e-9), err.max()
+
+
+def test_config5_corner_temperature_mismatch_131072(host_bsimcmg):
+    """SURVEY 8(d) config 5 stand-in at full size: 4 corners x 32 temperatures (-40 .. 125 C, SimSpec.temp as a swept
+    column) x 1 024 mismatch draws = 131 072 transient instances of one cell through the sweep API.  sky130 / BSIM4 are
+    not in the reference tree (parity unpinned in the reference itself); the cell is the BSIM-CMG inverter, corners act
+    through the model's variability handles DELVTRAND / U0MULT (circuits.CONFIG5_DECK)."""
+    from cedarsim.jl_b200.sweeps import CircuitSweep, tran_
+    cs = CircuitSweep(circuits.CONFIG5_DECK, circuits.config5_sweep(), outputs=["q", "d", "vvdd.i"], host=True)
+    assert cs.shape == (4, 32, 1024) and len(cs) == 131072
+    ts = np.linspace(0, 2.5e-9, 251)
+    sols = tran_(cs, (0.0, 2.5e-9), saveat=ts, reltol=1e-3)
+    assert sols.status.max() == 0
+    q = sols.array(cs.sys.node_q)                      # (4, 32, 1024, 251)
+    assert np.abs(q[..., 40] - 0.7).max() < 1e-3 and np.abs(q[..., 110]).max() < 1e-3 and np.abs(q[..., 220] - 0.7).max() < 1e-3
+    # static supply current with the input low (sub-threshold leakage of the nFET): grows with temperature at every
+    # corner / draw, and fast corners leak more than slow ones
+    leak = -sols.array(cs.sys.vvdd.I)[..., 0]          # (4, 32, 1024)
+    assert leak.min() > 0
+    assert np.all(np.diff(leak, axis=1) > 0)
+    assert np.all(leak[1] > leak[0]) and np.all(leak[0] > leak[2])      # ff > tt > ss
+    # seeded subset against the oracle in the fixed-step comparison mode (1e-6 rel / 1e-9 abs)
+    rng = np.random.default_rng(5)
+    sel = np.sort(rng.choice(len(cs), 32, replace=False))
+    fc, P = cs.flat.fc, np.ascontiguousarray(cs.flat.params[:, sel])
+    kw = dict(fixed_step=1, dt=1e-12, temp=cs.flat.options["temp"])
+    plan = engine.Circuit(fc, cs.flat.models).plan(len(sel))
+    plan.set_params(P)
+    y, st, _ = plan.tran(0.0, 2.5e-9, ts, engine.default_options(**kw))
+    plan.close()
+    yo, so, _ = orc.tran(fc, 0.0, 2.5e-9, ts, params=P, opts=orc.default_options(**kw), nthreads=8)
+    assert st.max() == 0 and so.max() == 0
+    err = np.abs(y - yo)
+    scale = np.abs(yo).max(axis=(1, 2), keepdims=True)   # currents: relative to the waveform's peak
+    assert np.all(err <= 1e-6 * np.maximum(np.abs(yo), 1e-3 * scale) + 1e-9 * np.where(scale > 1e-2, 1.0, 0.0)), err.max()
