@@ -101,7 +101,8 @@ def specialized_model(card: ModelCard, runtime=("L", "NFIN"), rebuild: bool = Fa
     vdd = 0.7 if const.get("DEVTYPE", 1.0) else -0.7
     probe = {"params": {k: (21e-9 if k == "L" else 3.0 if k == "NFIN" else card.params.get(k, 0.0)) for k in runtime},
              "v": [0.5 * vdd, 0.5 * vdd, 0.0, 0.0, 0.5 * vdd, 0.0]}
-    return compiled_model(f"bsimcmg107_{card.name}_{key}", BSIMCMG_VA, rebuild, probe=probe, suppress_defines=["__OPINFO__"],
+    ident = "".join(ch if ch.isalnum() else "_" for ch in card.name)   # bins are named `<base>.<N>`
+    return compiled_model(f"bsimcmg107_{ident}_{key}", BSIMCMG_VA, rebuild, probe=probe, suppress_defines=["__OPINFO__"],
                           const_params=const, runtime_params=list(runtime))
 
 

@@ -25,7 +25,7 @@ import numpy as np
 from . import models
 from .expr import ExprError, evaluate, free_vars, parse_expr, parse_number
 from .flat import (Col, FlatCircuit, VAModelShape, Wave, W_DC, W_PULSE, W_PWL, W_SIN, shape_of)
-from .modelcard import ModelCard, parse_model_cards
+from .modelcard import ModelCard, NoBinException, bins_of, find_bin, parse_model_cards
 
 
 class NetlistError(Exception):
@@ -499,16 +499,62 @@ class _Flattener:
         v = [self.value(f"{name}.sin{i}", x) for i, x in enumerate(vals)]
         return Wave(W_SIN, dc=dcv, v=v)
 
+    def _binned(self, name: str, card: Card, scope: _Scope, over: Dict[str, Num]) -> ModelCard:
+        """`<model>.<N>` bins: the bin whose [lmin,lmax) x [wmin,wmax) window holds scale*l, scale*w
+        (src/spectre.jl:1160-1170; `scale` from `.option scale=`, :1217).  One bin per sweep: the card is
+        compiled into the device code, so all points of a sweep must fall into the same bin."""
+        geo = {}
+        for k in ("l", "w"):
+            if k in over:
+                geo[k] = np.atleast_1d(np.asarray(over[k], dtype=float))
+            elif k in card.params:
+                geo[k] = np.atleast_1d(np.asarray(scope.eval(card.params[k]), dtype=float))
+            else:
+                raise NetlistError(f"{name}: binned model {card.model!r} needs both l= and w= on the instance")
+        sc = self.nl.options.get("scale", 1.0)
+        sc = float(scope.eval(sc)) if isinstance(sc, str) else float(sc)
+        l, w = np.broadcast_arrays(geo["l"], geo["w"])
+        try:
+            picks = {find_bin(self.nl.cards, card.model, float(a), float(b), sc).name
+                     for a, b in set(zip(l.tolist(), w.tolist()))}
+        except NoBinException as e:
+            raise NetlistError(f"{name}: {e}") from None
+        if len(picks) != 1:
+            raise NetlistError(f"{name}: sweep crosses bins {sorted(picks)} of {card.model!r}; the model card is "
+                               "compiled into the device code -- split the sweep at the bin boundary")
+        return self.nl.cards[picks.pop()]
+
+    _BIN_KEYS = ("LMIN", "LMAX", "WMIN", "WMAX")
+
     def _mosfet(self, name: str, card: Card, nodes: List[str], scope: _Scope, over: Dict[str, Num], mult: float):
         mc = self.nl.cards.get(card.model)
+        binned = mc is None and bool(bins_of(self.nl.cards, card.model))
+        if binned:
+            mc = self._binned(name, card, scope, over)
         if mc is None:
             raise NetlistError(f"unknown model {card.model!r} for {name}")
+        if mc.exprs:   # card values written in terms of `.param`s: resolved in the instance's scope
+            mc = ModelCard(mc.name, mc.master, dict(mc.params))
+            for k, e in self.nl.cards[mc.name].exprs.items():
+                v = scope.eval(e)
+                if isinstance(v, np.ndarray) and v.ndim > 0:
+                    if not np.all(v == v.flat[0]):
+                        raise NetlistError(f"model {mc.name!r}: card parameter {k} varies over the sweep; cards are "
+                                           "compiled into the device code, sweep an instance parameter instead")
+                    v = v.flat[0]
+                mc.params[k] = float(v)
         if not mc.master.startswith("bsimcmg"):
             raise NetlistError(f"model {card.model!r}: device family {mc.master!r} is not available "
                                "(only BSIM-CMG 107 is vendored in the reference tree)")
+        if binned:
+            # BSIM-CMG has no LMIN/LMAX/WMIN/WMAX/W parameters (they are BSIM4's): for this family the window
+            # and the instance's w= only select the bin
+            mc = ModelCard(mc.name, mc.master, {k: v for k, v in mc.params.items() if k not in self._BIN_KEYS})
         inst: Dict[str, Num] = {}
         for k in set(card.params) | set(over):
-            if k == "m":
+            if k == "m" or (binned and k == "w"):
+                if k == "w" and k in over:
+                    self.used_sweep.add((name + ".w").lower())
                 continue
             inst[k.upper()] = over[k] if k in over else scope.eval(card.params[k])
         runtime = tuple(sorted(set(inst) | {"L", "NFIN"}))

@@ -1,8 +1,10 @@
 """SPICE-subset reader / flattener semantics (reference src/spectre.jl, see netlist.py)."""
+import os
+
 import numpy as np
 import pytest
 
-from cedarsim.jl_b200 import netlist
+from cedarsim.jl_b200 import modelcard, netlist
 from cedarsim.jl_b200.expr import evaluate, parse_expr, parse_number
 from cedarsim.jl_b200.flat import Col
 from cedarsim.jl_b200.sweeps import CircuitSweep, ProductSweep
@@ -101,3 +103,54 @@ VD D 0 AC 1 SIN (0.5 0.01 1e7)
     fl = netlist.flatten(nl, {"mneg.nfin": np.array([1.0, 2.0])})
     assert fl.tran == (1e-9, 4e-7) and len(fl.fc.va_insts) == 2 and fl.fc.n_nodes == 8
     assert "mneg.nfin" in fl.fc.param_names
+
+
+BINNED_DECK = """* binned FinFET cards
+.option scale={scale}
+.param vth_shift=0.01
+.model nf.0 nmos level=72 lmin=10n lmax=25n wmin=10n wmax=1u eot=1n dvt0='0.05+vth_shift'
+.model nf.1 nmos level=72 lmin=25n lmax=100n wmin=10n wmax=1u eot=1.2n
+.model pf.0 pmos level=17 version=107 lmin=10n lmax=100n wmin=10n wmax=1u
+m1 d g 0 0 nf l=21n w=50n nfin=2
+vg g 0 0.5
+vd d 0 0.7
+"""
+
+
+def test_model_level_selects_family_and_devtype():   # spice_select_device / devtype_param, src/spectre.jl:596-641
+    nl = netlist.parse_netlist(BINNED_DECK.format(scale=1.0))
+    assert {k: c.master for k, c in nl.cards.items()} == {"nf.0": "bsimcmg107", "nf.1": "bsimcmg107", "pf.0": "bsimcmg107"}
+    assert nl.cards["nf.0"].params["DEVTYPE"] == 1.0 and nl.cards["pf.0"].params["DEVTYPE"] == 0.0
+    assert nl.cards["nf.0"].exprs == {"DVT0": "0.05+vth_shift"}          # needs the `.param` scope
+    b4 = modelcard.parse_model_cards(".model n4 nmos level=54 version=4.5 toxe=4n\n.model p4 pmos level=14")
+    assert b4["n4"].master == "bsim4" and b4["n4"].params["TYPE"] == 1.0 and b4["p4"].params["TYPE"] == -1.0
+
+
+def test_model_binning(host_bsimcmg):   # find_bin, src/spectre.jl:1160-1170; test/binning/bins.jl:20-23
+    cards = netlist.parse_netlist(BINNED_DECK.format(scale=1.0)).cards
+    assert modelcard.find_bin(cards, "nf", 21e-9, 50e-9).name == "nf.0"
+    assert modelcard.find_bin(cards, "nf", 25e-9, 50e-9).name == "nf.1"      # lmax is exclusive, lmin inclusive
+    assert modelcard.find_bin(cards, "nf", 10e-9, 10e-9).name == "nf.0"
+    assert modelcard.find_bin(cards, "nf", 42e-9, 100e-9, scale=0.5).name == "nf.0"   # scale multiplies l and w
+    with pytest.raises(modelcard.NoBinException):
+        modelcard.find_bin(cards, "nf", 21e-9, 1e-6)                         # wmax exclusive
+    # through the flattener: the instance picks its bin, the bin's card (with `.param` expressions resolved) is compiled in
+    fl = netlist.flatten(netlist.parse_netlist(BINNED_DECK.format(scale=1.0)), {"m1.l": np.array([20e-9, 24e-9])})
+    assert len(fl.models) == 1 and "nf_0" in fl.models[0].name and fl.fc.param_names == ["m1.l"]
+    fl2 = netlist.flatten(netlist.parse_netlist(BINNED_DECK.format(scale=2.0)), {"m1.l": np.array([20e-9, 24e-9])})
+    assert "nf_1" in fl2.models[0].name                                       # `.option scale` moves the lookup only
+    assert fl2.params[0].tolist() == [20e-9, 24e-9]
+    with pytest.raises(netlist.NetlistError, match="crosses bins"):
+        netlist.flatten(netlist.parse_netlist(BINNED_DECK.format(scale=1.0)), {"m1.l": np.array([20e-9, 30e-9])})
+    with pytest.raises(netlist.NetlistError, match="NoBinExpection"):
+        netlist.flatten(netlist.parse_netlist(BINNED_DECK.format(scale=1.0)), {"m1.l": np.array([2e-7])})
+
+
+def test_reference_bins_deck():   # test/binning/bins.cir + bins.jl:20-23 (BSIM4 cards: lookup only, the family is not in tree)
+    path = "/root/reference/test/binning/bins.cir"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    cards = modelcard.load_model_cards(path)
+    assert len(modelcard.bins_of(cards, "nmos_3p3")) >= 5 and cards["nmos_3p3.0"].master == "bsim4"
+    assert modelcard.find_bin(cards, "nmos_3p3", 2.8e-7, 2.2e-7).name == "nmos_3p3.0"
+    assert modelcard.find_bin(cards, "nmos_3p3", 5.0e-7, 2.2e-7).name == "nmos_3p3.1"
