@@ -830,6 +830,10 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 p->eval_smem.push_back((size_t)meta[1]);
                 if (meta[1] > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributeMaxDynamicSharedMemorySize, meta[1]));
+                // experiment knob: shared-memory carve-out of the eval kernels in percent (the rest of the 256 KB is
+                // L1, which is where their register spills live)
+                if (const char* cv = std::getenv("CB_EVAL_CARVEOUT"))
+                    CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
             }
             p->k_setup.push_back(ks);
             p->k_eval.push_back(ke);
@@ -843,6 +847,8 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 CUDA_TRY(cudaMemcpy(metav, dmeta, sizeof metav, cudaMemcpyDeviceToHost));
                 if (metav[1] > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributeMaxDynamicSharedMemorySize, metav[1]));
+                if (const char* cv = std::getenv("CB_EVAL_CARVEOUT"))
+                    CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
             } else {
                 (void)cudaGetLastError();
                 ksv = kev = nullptr;

@@ -17,7 +17,7 @@ from . import flat as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcedarb200.so")
-CUBIN_CACHE = os.path.join(_HERE, "_gen", "cubin")
+CUBIN_CACHE = os.path.join(_HERE, os.environ.get("CB_GEN_DIR", "_gen"), "cubin")
 _lib = None
 
 SYMBOLS = [

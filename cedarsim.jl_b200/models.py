@@ -17,7 +17,7 @@ from .modelcard import ModelCard, load_model_cards
 from .va.compiler import CompiledModel, compile_va_file
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GEN_DIR = os.path.join(_HERE, "_gen")
+GEN_DIR = os.path.join(_HERE, os.environ.get("CB_GEN_DIR", "_gen"))   # CB_GEN_DIR: experiment variants keep their own cache
 REFERENCE_ROOT = os.environ.get("CEDAR_REFERENCE_ROOT", "/root/reference")
 BSIMCMG_VA = os.path.join(REFERENCE_ROOT, "VerilogAParser.jl/cmc_models/bsimcmg107/bsimcmg.va")
 ASAP7_CARDS = os.path.join(REFERENCE_ROOT, "SpectreNetlistParser.jl/test/examples/7nm_TT.scs")

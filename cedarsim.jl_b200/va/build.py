@@ -13,7 +13,7 @@ from typing import Optional
 from .compiler import CompiledModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GEN_DIR = os.path.join(os.path.dirname(_HERE), "_gen")
+GEN_DIR = os.path.join(os.path.dirname(_HERE), os.environ.get("CB_GEN_DIR", "_gen"))
 HOST_CC = "/usr/bin/gcc"
 
 

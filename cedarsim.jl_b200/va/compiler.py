@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import hashlib
 import math
+import os
 import re
 from dataclasses import dataclass, field
 from typing import Dict, FrozenSet, List, Optional, Sequence, Set, Tuple
@@ -34,8 +35,9 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-CACHE_CHUNK_ROWS = 8
-CACHE_WINDOW = 16
+# experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
+CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "8"))
+CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "16"))
 
 
 class VACompileError(Exception):
