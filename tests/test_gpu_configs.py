@@ -110,5 +110,9 @@ def test_config5_corner_temperature_mismatch_131072(host_bsimcmg):
     yo, so, _ = orc.tran(fc, 0.0, 2.5e-9, ts, params=P, opts=orc.default_options(**kw), nthreads=8)
     assert st.max() == 0 and so.max() == 0
     err = np.abs(y - yo)
-    scale = np.abs(yo).max(axis=(1, 2), keepdims=True)   # currents: relative to the waveform's peak
-    assert np.all(err <= 1e-6 * np.maximum(np.abs(yo), 1e-3 * scale) + 1e-9 * np.where(scale > 1e-2, 1.0, 0.0)), err.max()
+    # node voltages at the north-star bar
+    assert np.all(err[:2] <= 1e-6 * np.abs(yo[:2]) + 1e-9), err[:2].max()
+    # supply current: i = ... + C dv/dt, so a node-voltage difference inside that bar (dv <= 1e-9 V) shows as up to
+    # 2 C dv / dt ~ 1e-11 A at dt = 1 ps and ~10 fF of node capacitance; asserted at 1e-6 of the waveform's peak (~4e-5 A)
+    ipk = np.abs(yo[2]).max()
+    assert np.all(err[2] <= 1e-6 * np.abs(yo[2]) + 1e-6 * ipk), (err[2].max(), ipk)
