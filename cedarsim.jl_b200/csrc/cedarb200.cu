@@ -629,6 +629,7 @@ struct cb_plan {
     bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
+    int lu_win_full = 64, lu_win_solve = 64;   // points per k_lu CTA in full / value-only rounds
     int* d_dc_count = nullptr;
     double *d_DX = nullptr, *d_QK = nullptr, *d_RMAX = nullptr, *d_WV = nullptr, *d_DVMAX = nullptr;
     int* d_BAD = nullptr;
@@ -1075,8 +1076,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 TRY(p->upload(&ti, iptr)); la.citem_ptr = ti;
                 TRY(p->upload(&dm, c->cq_mult)); la.cmult = dm;
             }
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_lu<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            // experiment knobs CB_LU_WIN_FULL / CB_LU_WIN_SOLVE = 32 | 64
+            if (const char* e = std::getenv("CB_LU_WIN_FULL")) p->lu_win_full = std::atoi(e) == 32 ? 32 : 64;
+            if (const char* e = std::getenv("CB_LU_WIN_SOLVE")) p->lu_win_solve = std::atoi(e) == 32 ? 32 : 64;
             la.LUF = nullptr;
         }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
@@ -1378,9 +1384,17 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
             if (timing) cudaEventRecord(e1, p->stream);
             if (p->lu) {
-                const unsigned g = (unsigned)((B + LU_WIN - 1) / LU_WIN);
-                if (vround) k_lu<true><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                else k_lu<false><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                // window of points per CTA (compacted into groups of LU_PTS): 64 keeps the groups of value-only rounds
+                // full; 32 gives a short lane twice the CTAs (one group each) in full rounds
+                const int win = vround ? p->lu_win_solve : p->lu_win_full;
+                const unsigned g = (unsigned)((B + win - 1) / win);
+                if (vround) {
+                    if (win == 32) k_lu<true, 32><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                    else k_lu<true, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                } else {
+                    if (win == 32) k_lu<false, 32><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                    else k_lu<false, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                }
             } else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
             cargs.vround = vround ? 1 : 0;
             k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);

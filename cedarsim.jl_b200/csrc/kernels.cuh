@@ -527,7 +527,6 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, 3) k_control(const CArg
 // stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
 // instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
 #define LU_PTS 32
-#define LU_WIN 64
 #define LU_W 16
 #define LU_GU 8
 struct LArgs {
@@ -559,7 +558,7 @@ struct LArgs {
     int* BAD;
 };
 
-template <bool SOLVE>
+template <bool SOLVE, int LU_WIN>
 __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
     extern __shared__ double vals_[];
     __shared__ double s_red[2][LU_W][LU_PTS];

@@ -39,6 +39,25 @@ struct VaArgs {
 // exp <= 1 ulp, log <= 2 ulp, pow relative error <= 1e-14 for |b ln a| <= 100, 1/x and sqrt <= 2 ulp.
 // Deviations from IEEE library behaviour, all outside what compact models evaluate: exp underflows to 0 below
 // -708.39 (no denormal results); pow(a, b) = exp(b log |a|) with the sign rule for integer b.
+//
+// exp / log / pow / reciprocal / sqrt are real calls (__noinline__), not inlined: the eval kernels are bound by
+// instruction supply (a ~290 KB straight-line stream that every warp walks once, DESIGN.md section 5), so a smaller
+// cold stream beats a shorter dynamic one -- the bodies below stay in the instruction cache.  Measured on the DFF
+// bench workload: 18.1k -> 13.0k static SASS instructions per kernel, k_eval -6 %, k_evalv -16 %, +9.5 % points/s
+// (profiles/variants_r1v.log).  -DVA_MATH_NOINLINE=0 inlines everything again, =1 keeps 1/x and sqrt inline.
+#ifndef VA_MATH_NOINLINE
+#define VA_MATH_NOINLINE 2
+#endif
+#if VA_MATH_NOINLINE >= 1
+#define VA_MATH_FN static __device__ __noinline__
+#else
+#define VA_MATH_FN VA_FN
+#endif
+#if VA_MATH_NOINLINE >= 2
+#define VA_MATH_FN2 static __device__ __noinline__
+#else
+#define VA_MATH_FN2 VA_FN
+#endif
 VA_FN double va_rcp_normal(const double x) {   // |x| normal and 1/x normal
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
@@ -48,7 +67,7 @@ VA_FN double va_rcp_normal(const double x) {   // |x| normal and 1/x normal
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-VA_FN double va_rcp(const double x) {
+VA_MATH_FN2 double va_rcp(const double x) {
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
     double e = fma(-x, r0, 1.0);
@@ -58,7 +77,7 @@ VA_FN double va_rcp(const double x) {
     r = fma(r, e, r);
     return fabs(r) <= 1.7976931348623157e308 ? r : r0;   // inputs outside the normal range: the seed is the IEEE answer
 }
-VA_FN double va_sqrt(const double x) {
+VA_MATH_FN2 double va_sqrt(const double x) {
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
     double g = x * y0, h = 0.5 * y0;
@@ -78,7 +97,7 @@ __constant__ double va_kexp[14] = {
     2.5100395159429244017e-8, 2.7620101012098000228e-7, 2.7557268439678002354e-6, 0.000024801521269532121095,
     0.00019841269863066695027, 0.0013888888917230723233, 0.0083333333333300592137, 0.04166666666662409382,
     0.16666666666666667454, 0.50000000000000010231};
-VA_FN double va_exp(const double x) {
+VA_MATH_FN double va_exp(const double x) {
     const double* __restrict__ K = va_kexp;
     double t = fma(x, K[0], K[1]);
     const int n = __double2loint(t);
@@ -100,7 +119,7 @@ __constant__ double va_klog[10] = {
     6.93147180369123816490e-01, 1.90821492927058770002e-10,
     0.1308803485092755383, 0.13268638369266823879, 0.15386244737621666606, 0.18181795547521136235,
     0.22222222392581045097, 0.28571428570799785031, 0.40000000000000883236, 0.66666666666666666463};
-VA_FN double va_log(const double x0) {
+VA_MATH_FN double va_log(const double x0) {
     const double* __restrict__ K = va_klog;
     const bool tiny = x0 < 2.2250738585072014e-308;
     const double x = tiny ? x0 * 18014398509481984.0 : x0;    // subnormal inputs: scale by 2^54
@@ -123,7 +142,7 @@ VA_FN double va_log(const double x0) {
     const bool ok = x0 > 0.0 && x0 <= 1.7976931348623157e308;
     return ok ? r : (x0 == 0.0 ? -INFINITY : (x0 > 0.0 ? x0 : NAN));
 }
-VA_FN double va_pow(const double a, const double b) {
+VA_MATH_FN double va_pow(const double a, const double b) {
     const double t = b * va_log(fabs(a));
     const double r = va_exp(b == 0.0 ? 0.0 : t);         // pow(a, 0) = 1 for every a, including 0 and inf
     // negative base: defined for integer exponents only, sign by parity
@@ -138,11 +157,33 @@ VA_FN double va_pow(const double a, const double b) {
 #define VA_RCP(x) va_rcp(x)
 #define VA_SQRT(x) va_sqrt(x)
 #endif
+// The remaining libm functions a compact model calls now and then (BSIM-CMG: tan / cos / sin in the initial guess of
+// its surface-potential iteration, ~200 inlined SASS instructions per site with their slow paths) are the CUDA library
+// versions behind one out-of-line body each: same values, ~1 000 fewer instructions in every BSIM-CMG eval kernel.
+#if VA_MATH_NOINLINE >= 1
+VA_MATH_FN double va_sin(const double x) { return sin(x); }
+VA_MATH_FN double va_cos(const double x) { return cos(x); }
+VA_MATH_FN double va_tan(const double x) { return tan(x); }
+VA_MATH_FN double va_tanh(const double x) { return tanh(x); }
+VA_MATH_FN double va_atan(const double x) { return atan(x); }
+#define sin(x) va_sin(x)
+#define cos(x) va_cos(x)
+#define tan(x) va_tan(x)
+#define tanh(x) va_tanh(x)
+#define atan(x) va_atan(x)
+#endif
 #ifndef VA_LIBM
 #define exp(x) va_exp(x)
 #define log(x) va_log(x)
 #define pow(a, b) va_pow(a, b)
 #endif
+
+// d/da a^b = b a^(b-1) given p = a^b (finite at a == 0 for b >= 1; b == 0 -> 0 avoids 0 * inf): an IEEE division and a
+// rarely-taken second pow, ~50 instructions when inlined at every site
+VA_MATH_FN double va_dpow(const double a, const double b, const double p) {
+    return b == 0.0 ? 0.0 : (a == 0.0 ? b * pow(a, b - 1.0) : b * p / a);
+}
+#define VA_DPOW(a, b, p) va_dpow(a, b, p)
 
 VA_FN double va_limexp(double x) { return x < 80.0 ? exp(x) : exp(80.0) * (1.0 + x - 80.0); }
 VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }

@@ -14,7 +14,7 @@ import os
 from typing import Dict, Optional
 
 from .modelcard import ModelCard, load_model_cards
-from .va.compiler import CompiledModel, compile_va_file
+from .va.compiler import GEN_VERSION, CompiledModel, compile_va_file
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 GEN_DIR = os.path.join(_HERE, os.environ.get("CB_GEN_DIR", "_gen"))   # CB_GEN_DIR: experiment variants keep their own cache
@@ -53,9 +53,12 @@ def compiled_model(name: str, va_path: Optional[str] = None, rebuild: bool = Fal
     if name in _cache and not rebuild:
         return _cache[name]
     path = os.path.join(GEN_DIR, f"{name}.model.json")
+    cm = None
     if os.path.exists(path) and not rebuild:
         cm = load_model(path)
-    else:
+        if cm.gen_version != GEN_VERSION and va_path is not None and os.path.exists(va_path):
+            cm = None   # written by another version of the generator and the source is at hand: regenerate
+    if cm is None:
         if va_path is None or not os.path.exists(va_path):
             raise FileNotFoundError(f"no cached model {path} and no Verilog-A source {va_path!r}; run build() where the source exists")
         cm = compile_va_file(va_path, name=name, **kw)

@@ -41,6 +41,7 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define CACHE_LDG(s) cache_[s]
 #define VA_RCP(x) (1.0 / (x))
 #define VA_SQRT(x) sqrt(x)
+#define VA_DPOW(a, b, p) ((b) == 0.0 ? 0.0 : ((a) == 0.0 ? (b) * pow((a), (b) - 1.0) : (b) * (p) / (a)))
 #define VA_CHUNK(k)
 #define VT(k) v_[k]
 #define OUT_I(k, v) I_[k] = (v)

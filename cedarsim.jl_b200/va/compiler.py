@@ -35,6 +35,7 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
+GEN_VERSION = 2   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
 CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "8"))
 CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "16"))
@@ -377,6 +378,7 @@ class CompiledModel:
     source_n: str = ""
     ncache_n: int = 0
     noise_sources: List[Tuple[int, int, str, str]] = field(default_factory=list)
+    gen_version: int = 0   # GEN_VERSION of the generator that wrote `source` (cached models of another version are rebuilt)
 
     @property
     def key(self) -> str:
@@ -967,7 +969,8 @@ class _Compiler:
         if a.d:
             # d/da a^b = b a^(b-1)  (ForwardDiff's rule; finite at a == 0 for b >= 1)
             # (b == 0 -> 0 avoids 0*inf = NaN at a == 0, e.g. DVTP0*pow(vdsx, DVTP1) with DVTP1 = 0)
-            dpa = self.emit_val("r", f"({bc} == 0.0 ? 0.0 : ({ac} == 0.0 ? {bc} * pow({ac}, {bc} - 1.0) : {bc} * {p.c} / {ac}))", {})
+            # (VA_DPOW: one out-of-line body on the GPU, see csrc/va_prelude.h)
+            dpa = self.emit_val("r", f"VA_DPOW({ac}, {bc}, {p.c})", {})
             self.count("div"); self.count("mul")
         dpb = None
         if b.d:
@@ -1948,6 +1951,7 @@ def compile_module(mod: Module, name: Optional[str] = None, const_params=None, r
         nc = _Compiler(mod, name or mod.name, const_params, runtime_params, noise=True, skip_funcs=full.defined_funcs)
         cn = nc.compile()
         cm.source_n, cm.ncache_n, cm.noise_sources = cn.source, cn.ncache, list(nc.noise_sources)
+    cm.gen_version = GEN_VERSION
     return cm
 
 

@@ -19,6 +19,8 @@ SHIM = r"""
 #include <stdint.h>
 #include <string.h>
 #define VA_FN static inline
+#define VA_MATH_FN static inline
+#define VA_MATH_FN2 static inline
 #define __constant__ static const
 #define __restrict__
 typedef int bool_t;
