@@ -200,7 +200,9 @@ def main():
     # ---- per-kernel timing for the roofline: the same step on a single-lane plan with CUDA events around every launch
     # (in the timed region above the plan's lanes run concurrently, so a kernel's launch duration there includes the
     # SMs it shares with other lanes' kernels; timed alone it is the figure the roofline peak is quoted for)
+    os.environ["CB_EVAL_FORK"] = "0"   # one stream: the n- and p-FET eval kernels of a round run one after the other
     plan1 = circuit.plan(B, device=local, lanes=1)
+    del os.environ["CB_EVAL_FORK"]
     plan1.set_x0(nodeset(fc))
     plan1.set_params(P)
     plan1.tran_device(T0, T1, ts, opts)

@@ -664,6 +664,11 @@ struct cb_plan {
     bool timing = false;
     cb_pref last_temp{}, last_gmin{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // the eval kernels of different device models of one round are independent: models 1.. run on side streams,
+    // forked from / joined into `stream` with events (a lane's launches are often a partial wave)
+    cudaStream_t mstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool fork_models = true;
 
     template <class T>
     int alloc(T** out, size_t count) {
@@ -812,6 +817,12 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
     CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&p->ev0));
     CUDA_TRY(cudaEventCreate(&p->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    for (size_t m = 1; m < c->models.size() && m < 8; m++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->mstream[m], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[m], cudaEventDisableTiming));
+    }
+    if (const char* e = std::getenv("CB_EVAL_FORK")) p->fork_models = std::atoi(e) != 0;
     int rc;
 #define TRY(x) do { rc = (x); if (rc != CB_OK) return rc; } while (0)
     {
@@ -1361,6 +1372,8 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     }
     if (use_v) { int rc2 = run_setupv(p, opt); if (rc2 != CB_OK) return rc2; }
     if (!use_v) largs.LUF = nullptr;
+    int n_live_models = 0;
+    for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
     bool done = false;
     int since_full = 0;   // value-only rounds since the last full round
     while (!done && rounds < max_rounds) {
@@ -1373,13 +1386,23 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
                 cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
                 cudaEventRecord(e0, p->stream);
             }
+            const bool fork = p->fork_models && n_live_models > 1;
+            if (fork) CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
+            bool first_model = true;
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
                 void* kargs[] = {vround ? vargs_v[m] : vargs[m]};
                 const unsigned eval_threads = vround ? p->evalv_threads[m] : p->eval_threads[m];
                 dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
+                cudaStream_t ms = (fork && !first_model && p->mstream[m]) ? p->mstream[m] : p->stream;
+                if (ms != p->stream) CUDA_TRY(cudaStreamWaitEvent(ms, p->ev_fork, 0));
                 CUDA_TRY(cudaLaunchKernel((const void*)(vround ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
-                                          vround ? p->evalv_smem[m] : p->eval_smem[m], p->stream));
+                                          vround ? p->evalv_smem[m] : p->eval_smem[m], ms));
+                if (ms != p->stream) {
+                    CUDA_TRY(cudaEventRecord(p->ev_join[m], ms));
+                    CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join[m], 0));
+                }
+                first_model = false;
                 launches++;
             }
             if (timing) cudaEventRecord(e1, p->stream);
@@ -1947,6 +1970,11 @@ extern "C" void cb_plan_destroy(cb_plan* p) {
     if (p->lib) cudaLibraryUnload(p->lib);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (int m = 0; m < 8; m++) {
+        if (p->ev_join[m]) cudaEventDestroy(p->ev_join[m]);
+        if (p->mstream[m]) cudaStreamDestroy(p->mstream[m]);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }

@@ -192,9 +192,16 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 // cross-lane reductions (Newton convergence AND, LTE max) and the three hand-offs of rows between lanes go
 // through shared memory / __syncthreads.  One thread per point (the previous version) left the GPU with
 // 16 384 threads -- under one warp per SM sub-partition -- and ran at 5 % of HBM bandwidth.
+#ifndef CTRL_PTS
 #define CTRL_PTS 32
+#endif
+#ifndef CTRL_LANES
 #define CTRL_LANES 8
-__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, 3) k_control(const CArgs c) {
+#endif
+#ifndef CTRL_MINB
+#define CTRL_MINB 3
+#endif
+__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(const CArgs c) {
     __shared__ double s_err[CTRL_LANES][CTRL_PTS];
     __shared__ double s_nrm[CTRL_LANES][CTRL_PTS];
     const NArgs& a = c.n;

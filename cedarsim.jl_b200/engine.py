@@ -16,7 +16,7 @@ import numpy as np
 from . import flat as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcedarb200.so")
+LIB_PATH = os.environ.get("CB_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libcedarb200.so")   # CB_ENGINE_LIB: experiment builds
 CUBIN_CACHE = os.path.join(_HERE, os.environ.get("CB_GEN_DIR", "_gen"), "cubin")
 _lib = None
 
