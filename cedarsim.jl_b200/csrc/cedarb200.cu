@@ -801,6 +801,17 @@ static void build_fwd_schedule(const cb::Symbolic& S, int W, std::vector<int4>& 
     }
 }
 
+// Shared-memory carve-out (percent of the SM's maximum) of a generated eval kernel: what its resident CTAs need
+// (meta[3] CTAs of meta[1] bytes of cache ring + static + the driver's 1 KB), so that the rest of the 256 KB is L1 --
+// the eval kernels spill to local memory and are bound by those reloads (ncu: long-scoreboard stalls).  The driver's
+// default keeps the maximum shared-memory configuration (233 KB, ~28 KB of L1) whatever the kernel uses.
+// CB_EVAL_CARVEOUT=<percent> overrides, -1 = driver default.
+static int eval_carveout(const int* meta) {
+    if (const char* cv = std::getenv("CB_EVAL_CARVEOUT")) return std::atoi(cv);
+    const long long need = (long long)std::max(1, meta[3]) * ((long long)meta[1] + 2048);
+    return (int)std::min<long long>(100, (need * 100 + 233471) / 233472);
+}
+
 static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** out) {
     if (!c || !out || n_inst <= 0) return fail(CB_ERR_INVALID, "bad argument");
     if (!c->compiled) return fail(CB_ERR_STATE, "circuit not compiled");
@@ -842,10 +853,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 p->eval_smem.push_back((size_t)meta[1]);
                 if (meta[1] > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributeMaxDynamicSharedMemorySize, meta[1]));
-                // experiment knob: shared-memory carve-out of the eval kernels in percent (the rest of the 256 KB is
-                // L1, which is where their register spills live)
-                if (const char* cv = std::getenv("CB_EVAL_CARVEOUT"))
-                    CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
+                CUDA_TRY(cudaFuncSetAttribute((const void*)ke, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout(meta)));
             }
             p->k_setup.push_back(ks);
             p->k_eval.push_back(ke);
@@ -859,8 +867,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 CUDA_TRY(cudaMemcpy(metav, dmeta, sizeof metav, cudaMemcpyDeviceToHost));
                 if (metav[1] > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributeMaxDynamicSharedMemorySize, metav[1]));
-                if (const char* cv = std::getenv("CB_EVAL_CARVEOUT"))
-                    CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
+                CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout(metav)));
             } else {
                 (void)cudaGetLastError();
                 ksv = kev = nullptr;

@@ -242,11 +242,17 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, 
 #ifndef VA_EVAL_MINBLOCKS
 #define VA_EVAL_MINBLOCKS 5
 #endif
+// Ring geometry: 4-row chunks, 1 chunk ahead, 4 stages = 16 rows = 16 KB per 128-thread CTA.  Small on purpose: the
+// eval kernels spill (~900 B of local memory per thread at 96 registers) and what the ring does not take of the SM's
+// 256 KB is L1 for those spills -- the engine sets the shared-memory carve-out of these kernels to what their resident
+// CTAs need (META[3] = CTAs per SM).  A 40 KB ring (8-row chunks, 2 ahead, 5 stages) measured 3.5 % slower end to end
+// and 7 % slower for k_eval alone (profiles/variants_r1aa.log); 4 rows ahead are ~6 000 cycles of lead, several HBM
+// latencies.
 #ifndef VA_AHEAD
-#define VA_AHEAD 2
+#define VA_AHEAD 1
 #endif
 #ifndef VA_STAGES
-#define VA_STAGES 5
+#define VA_STAGES 4
 #endif
 
 VA_FN void va_cp8(unsigned dst, const double* src) {
@@ -294,7 +300,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 // points are live (full rounds) the mapping is the identity and every access is coalesced; in value-only rounds,
 // where typically 30-50 % of the points iterate, whole warps retire instead of running with most lanes idle.
 #define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
-    extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, 0}; \
+    extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ double va_ring_[];                                                     \

@@ -35,10 +35,10 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-GEN_VERSION = 2   # bump when the emitted code changes: models cached under _gen/ are regenerated
+GEN_VERSION = 3   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
-CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "8"))
-CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "16"))
+CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "4"))
+CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "8"))
 
 
 class VACompileError(Exception):
