@@ -199,7 +199,7 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 #define CTRL_LANES 8
 #endif
 #ifndef CTRL_MINB
-#define CTRL_MINB 3
+#define CTRL_MINB 4   // 64 registers: the 512 CTAs of a 16 384-point launch are one wave (148 SMs x 4), not 444 + a tail
 #endif
 __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(const CArgs c) {
     __shared__ double s_err[CTRL_LANES][CTRL_PTS];
