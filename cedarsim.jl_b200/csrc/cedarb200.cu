@@ -669,6 +669,8 @@ struct cb_plan {
     cudaStream_t mstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool fork_models = true;
+    cudaStream_t ustream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // mixed rounds: up to 8 eval kernels in flight
+    cudaEvent_t uev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     template <class T>
     int alloc(T** out, size_t count) {
@@ -832,6 +834,10 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
     for (size_t m = 1; m < c->models.size() && m < 8; m++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&p->mstream[m], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[m], cudaEventDisableTiming));
+    }
+    for (size_t k = 1; k < 2 * c->models.size() && k < 8; k++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->ustream[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->uev[k], cudaEventDisableTiming));
     }
     if (const char* e = std::getenv("CB_EVAL_FORK")) p->fork_models = std::atoi(e) != 0;
     int rc;
@@ -1169,7 +1175,7 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     return CB_OK;
 }
 
-static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false) {
+static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false, int only = -1) {
     // layout must match struct VaArgs in va_prelude.h
     struct VaArgsH {
         long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out;
@@ -1180,7 +1186,7 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha; a->active = p->na.active;
     a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->Bpad : p->d_cache + (size_t)c->cache_off[m] * p->Bpad;
-    a->vround = value_only ? 1 : 0; a->pad = 0;
+    a->vround = only >= 0 ? only : (value_only ? 1 : 0); a->pad = 0;   // which points take part, see VaArgs::vround
     a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
     a->given = p->d_given[m];
@@ -1341,6 +1347,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     const bool timing = p->timing || std::getenv("CB_TIMING") != nullptr;
     std::vector<cudaEvent_t> evs;
     std::vector<int> ev_kind;
+    std::vector<cudaEvent_t> uevs;   // mixed rounds: 5 events per round
     double t_eval = 0, t_newton = 0, t_evalv = 0, t_newtonv = 0;
     int64_t rounds = 0, vrounds = 0, launches = 0;
     const int64_t max_rounds = std::getenv("CB_MAX_ROUNDS") ? std::atoll(std::getenv("CB_MAX_ROUNDS")) : (int64_t)1 << 40;
@@ -1357,7 +1364,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     } sargs{B, a.X, a.alpha, a.dst + (size_t)DS_GSHUNT * B, a.BETA, a.dev_out, a.lin_g, a.lin_c, p->d_WV, a.active,
             p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
     void* sargs_ptr[] = {&sargs};
-    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, 0, p->d_dc_count};
+    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, 0, 0, p->d_dc_count, 1, 0};
     LArgs largs = p->la;
     largs.n = a; largs.WV = p->d_WV; largs.DX = p->d_DX; largs.QK = p->d_QK; largs.RMAX = p->d_RMAX; largs.DVMAX = p->d_DVMAX;
     largs.BAD = p->d_BAD;
@@ -1381,11 +1388,73 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     if (!use_v) largs.LUF = nullptr;
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
+    // Mixed rounds (experiment, CB_UNIFIED=1; off by default): every round advances EVERY unfinished point, the ones that
+    // need a fresh Jacobian through k_eval + k_lu<false>, the others through k_evalv + k_lu<true> with their stored
+    // factors; a point follows its own cycle (full, v_rounds value-only, full, ...) instead of idling until the global
+    // schedule reaches the kind of round it needs.  Same iterates bit for bit and 29 % fewer rounds on the DFF bench,
+    // but 1.85x SLOWER (profiles/variants_r1ad.log): every launch now covers ~half of the points, and with in-CTA
+    // compaction a half-filled launch of these latency-bound kernels takes as long as a full one (same number of CTAs
+    // and waves, half the warps per CTA).  It needs device-wide compaction (per-kind point lists) to pay off.
+    const bool unified = use_v && p->lu && std::getenv("CB_UNIFIED") && std::atoi(std::getenv("CB_UNIFIED")) != 0;
+    char vargs_f[8][256];
+    if (unified) {
+        cargs.unified = 1; cargs.vcycle = v_rounds + 1;
+        largs.only_full = 1;
+        for (size_t m = 0; m < c->models.size(); m++) {
+            std::memcpy(vargs_f[m], vargs[m], sizeof vargs_f[m]);
+            fill_va_args(p, m, opt, vargs_f[m], false, 2);
+        }
+    }
     bool done = false;
     int since_full = 0;   // value-only rounds since the last full round
     while (!done && rounds < max_rounds) {
         const bool dc_phase = p->h_done[1] > 0;
         for (int r = 0; r < poll; r++) {
+            if (unified) {
+                // timing (per-kernel figures of the roofline pass, run with CB_EVAL_FORK=0 so that nothing overlaps):
+                // e0 | k_eval_* | em | k_evalv_* | e1 | k_lu<false> | el | k_lu<true>, k_control | e2
+                cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr, el = nullptr, e2 = nullptr;
+                if (timing) {
+                    cudaEventCreate(&e0); cudaEventCreate(&em); cudaEventCreate(&e1); cudaEventCreate(&el); cudaEventCreate(&e2);
+                    cudaEventRecord(e0, p->stream);
+                }
+                // up to 2 x models eval kernels, all independent: stream 0 takes the first, the rest fork
+                CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
+                int slot = 0;
+                for (int kind = 0; kind < 2; kind++) {          // 0: full evaluation of ACT_FULL points, 1: value-only of ACT_ANY
+                    if (kind == 1 && timing) cudaEventRecord(em, p->stream);
+                    if (kind == 1 && rounds == 0) break;        // every point starts with a full iteration
+                    for (size_t m = 0; m < c->models.size(); m++) {
+                        if (c->model_insts[m].empty()) continue;
+                        void* kargs[] = {kind ? vargs_v[m] : vargs_f[m]};
+                        const unsigned eval_threads = kind ? p->evalv_threads[m] : p->eval_threads[m];
+                        dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
+                        cudaStream_t ms = (p->fork_models && slot > 0 && slot < 8 && p->ustream[slot]) ? p->ustream[slot] : p->stream;
+                        if (ms != p->stream) CUDA_TRY(cudaStreamWaitEvent(ms, p->ev_fork, 0));
+                        CUDA_TRY(cudaLaunchKernel((const void*)(kind ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
+                                                  kind ? p->evalv_smem[m] : p->eval_smem[m], ms));
+                        if (ms != p->stream) {
+                            CUDA_TRY(cudaEventRecord(p->uev[slot], ms));
+                            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->uev[slot], 0));
+                        }
+                        slot++;
+                        launches++;
+                    }
+                }
+                if (timing) cudaEventRecord(e1, p->stream);
+                const unsigned g = (unsigned)((B + 63) / 64);
+                k_lu<false, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                if (timing) cudaEventRecord(el, p->stream);
+                if (rounds > 0) k_lu<true, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
+                k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
+                launches += 3;
+                if (timing) {
+                    cudaEventRecord(e2, p->stream);
+                    uevs.push_back(e0); uevs.push_back(em); uevs.push_back(e1); uevs.push_back(el); uevs.push_back(e2);
+                }
+                rounds++;
+                continue;
+            }
             const bool vround = use_v && !dc_phase && rounds > 0 && since_full < v_rounds;
             since_full = vround ? since_full + 1 : 0;
             cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -1449,6 +1518,13 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
             evs.clear();
             ev_kind.clear();
+            for (size_t k = 0; k + 4 < uevs.size(); k += 5) {
+                float ms[4] = {0, 0, 0, 0};
+                for (int q = 0; q < 4; q++) cudaEventElapsedTime(&ms[q], uevs[k + q], uevs[k + q + 1]);
+                t_eval += ms[0] * 1e-3; t_evalv += ms[1] * 1e-3; t_newton += ms[2] * 1e-3; t_newtonv += ms[3] * 1e-3;
+                for (int q = 0; q < 5; q++) cudaEventDestroy(uevs[k + q]);
+            }
+            uevs.clear();
         }
     }
     CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
@@ -1981,6 +2057,8 @@ extern "C" void cb_plan_destroy(cb_plan* p) {
     for (int m = 0; m < 8; m++) {
         if (p->ev_join[m]) cudaEventDestroy(p->ev_join[m]);
         if (p->mstream[m]) cudaStreamDestroy(p->mstream[m]);
+        if (p->uev[m]) cudaEventDestroy(p->uev[m]);
+        if (p->ustream[m]) cudaStreamDestroy(p->ustream[m]);
     }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;

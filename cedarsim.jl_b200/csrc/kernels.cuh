@@ -179,7 +179,11 @@ struct CArgs {
     const int* BAD;
     double* WV;  // [nwaves][B] source values for the next evaluation
     int vround;  // this round was value-only: points marked ACT_FULL did not take part
+    int unified; // mixed rounds: every unfinished point took part, ACT_ANY points with a value-only iteration (stored
+                 // factors), ACT_FULL points with a full one; the kind of a point's next iteration follows its own
+                 // iteration count (full, then vcycle - 1 value-only, full, ...), not a global round schedule
     int* dc_count;  // number of points still in the DC phase (the host schedules full rounds only while > 0)
+    int vcycle, pad_;
 };
 
 __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long long inst, bool dcop, double t) {
@@ -210,7 +214,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     const long long inst = (long long)blockIdx.x * CTRL_PTS + pt;
     const bool inb = inst < B;
     const int act = inb ? a.active[inst] : ACT_DONE;
-    const bool live = act == ACT_ANY || (act == ACT_FULL && !c.vround);
+    const bool live = act == ACT_ANY || (act == ACT_FULL && (c.unified || !c.vround));
+    const bool pv = c.unified ? act == ACT_ANY : c.vround != 0;   // this point's iteration was value-only
     int phase = live ? a.ist[(size_t)IS_PHASE * B + inst] : PH_DONE;
     const int N = a.N, NV = a.NV;
     const Opts& o = a.o;
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             else { begin = true; phase = PH_TRAN; }
         } else {
             nnewton++;
-            if (!c.vround && lane == 0) a.ist[(size_t)IS_NFULL * B + ii]++;
+            if (!pv && lane == 0) a.ist[(size_t)IS_NFULL * B + ii]++;
             if (badpt) {
                 newton_fail = true;
                 status = 4;
@@ -304,14 +309,14 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
                     if (it == 0) {
                         // level 2: the first (full Newton) update of an attempt leaves ~ kappa n_1^2 (quadratic
                         // convergence; kappa learnt from the attempts that did take a second iteration)
-                        if (o.rate_test >= 2 && !c.vround) est = fmin(nrm, 3.0 * kappa * nrm * nrm);
+                        if (o.rate_test >= 2 && !pv) est = fmin(nrm, 3.0 * kappa * nrm * nrm);
                     } else {
                         if (it == 1 && nrm_prev > 0.0) kappa = fmax(fmax(nrm / (nrm_prev * nrm_prev), 0.7 * kappa), o.kappa_floor);
                         if (nrm < nrm_prev) {
                             // safety 3; a chord update (value-only round) contracts half as fast as the ratio observed
                             // across the preceding Newton update suggests (e_2 ~ 2 (e_1 / e_0) e_1)
                             const double rho = nrm / nrm_prev;
-                            est = nrm * fmin(1.0, (c.vround ? 6.0 : 3.0) * rho / (1.0 - rho));
+                            est = nrm * fmin(1.0, (pv ? 6.0 : 3.0) * rho / (1.0 - rho));
                         }
                     }
                 }
@@ -501,7 +506,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
             DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim; DST(DS_NRM) = nrm_prev; DST(DS_KAPPA) = kappa;
             a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
-            a.active[inst] = phase == PH_DONE ? ACT_DONE : (phase == PH_DC || (phase == PH_TRAN && it == 0)) ? ACT_FULL : ACT_ANY;
+            const bool want_full = c.unified ? (phase != PH_TRAN || it % c.vcycle == 0) : (phase == PH_DC || (phase == PH_TRAN && it == 0));
+            a.active[inst] = phase == PH_DONE ? ACT_DONE : want_full ? ACT_FULL : ACT_ANY;
             if (phase_in == PH_DC && phase != PH_DC) atomicSub(c.dc_count, 1);
         }
         if (phase != PH_DONE)
@@ -553,7 +559,7 @@ struct LArgs {
     const int* sop_ptr;       // [nslev * LU_W + 1]
     const int4* sitems;       // gather items of the residual and charge rows only
     const int* sitem_ptr;     // [LU_W + 1]
-    int nslev, pad1;
+    int nslev, only_full;     // only_full: k_lu<false> takes the ACT_FULL points only (mixed rounds)
     // first-order charge update  q(x + dx) ~ q(x) + C dx:  items (dev_out row of dQ/dV, vals slot of q_row, vals slot of
     // dx_col, index into cmult), grouped by destination row like the gather items
     const int4* citems;
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
     if (threadIdx.x < LU_WIN) {
         const long long i0 = base + threadIdx.x;
         const int act = i0 < B ? a.active[i0] : ACT_DONE;
-        on0 = SOLVE ? act == ACT_ANY : act != ACT_DONE;
+        on0 = SOLVE ? act == ACT_ANY : (c.only_full ? act == ACT_FULL : act != ACT_DONE);
         bal0 = __ballot_sync(0xffffffffu, on0);
         if (lane == 0) s_cnt[w] = __popc(bal0);
     }
@@ -996,7 +1002,7 @@ __global__ void k_init_state(long long B, int N, int* ist, double* dst, double* 
     dst[(size_t)DS_HPROP * B + inst] = o.dt > 0.0 ? o.dt : o.span * 1e-5;
     dst[(size_t)DS_KAPPA * B + inst] = o.kappa0;
     alpha[inst] = 0.0;
-    active[inst] = o.skip_dc && !o.dc_only ? ACT_ANY : ACT_FULL;
+    active[inst] = ACT_FULL;   // the first iteration of every point is a full one (fresh Jacobian, factors stored)
     for (int i = 0; i < N; i++) {
         const double v = x0 ? (x0_stride ? x0[(size_t)i * x0_stride + inst] : x0[i]) : 0.0;
         X[(size_t)i * B + inst] = v;

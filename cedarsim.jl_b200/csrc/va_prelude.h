@@ -26,7 +26,8 @@ struct VaArgs {
     const uint8_t* given;        // [ndev][NPARAM]
     double temp_val; double gmin_val;
     int temp_col; int gmin_col;
-    int vround; int pad_;        // value-only round: points with active[] == 2 (they need a full round) are skipped
+    int vround; int pad_;        // 0: every unfinished point; 1: only points with active[] == 1 (value-only evaluation,
+                                 // those that need a fresh Jacobian are skipped); 2: only points with active[] == 2
 };
 
 // Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
@@ -312,7 +313,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
             const long long base_ = (long long)blockIdx.x * VA_EVAL_THREADS;                     \
             const long long i0_ = base_ + threadIdx.x;                                           \
             const int act_ = i0_ < a.B ? a.active[i0_] : 0;                                      \
-            const bool on_ = act_ != 0 && !(a.vround && act_ == 2);                              \
+            const bool on_ = a.vround == 0 ? act_ != 0 : act_ == (a.vround == 1 ? 1 : 2);          \
             const unsigned bal_ = __ballot_sync(0xffffffffu, on_);                               \
             if ((threadIdx.x & 31) == 0) va_cnt_[threadIdx.x >> 5] = __popc(bal_);               \
             __syncthreads();                                                                     \
