@@ -163,7 +163,8 @@ def parse_netlist(text: str, path: Optional[str] = None, first_is_title: bool = 
     if _nl is None:
         nl.title = title
     stack: List[Subckt] = [nl.top]
-    cond_stack: List[bool] = []
+    cond_stack: List[bool] = []     # is the current branch of each open .if live
+    cond_taken: List[bool] = []     # has any branch of that .if been live yet (.elseif / .else chains)
     in_lib: Optional[str] = None
     base = os.path.dirname(path) if path else "."
     for line in lines:
@@ -172,23 +173,30 @@ def parse_netlist(text: str, path: Optional[str] = None, first_is_title: bool = 
             continue
         head = toks[0].lower()
         cur = stack[-1]
-        if head == ".lib" and len(toks) == 2 and _lib_section is not None:
-            in_lib = toks[1].lower()       # library section definition inside an included file
+        if head == ".lib" and len(toks) == 2:
+            in_lib = toks[1].strip("'\"").lower()   # `.LIB name` ... `.ENDL`: a library section definition
             continue
         if head == ".endl":
             in_lib = None
             continue
-        if _lib_section is not None and in_lib != _lib_section:
+        # a section is inert where it is defined and is read only through `.LIB "file" name` -- also from the file
+        # itself (test/basic.jl:312-336)
+        if (in_lib is not None) if _lib_section is None else (in_lib != _lib_section):
             continue
         if head in (".if", ".elseif", ".else", ".endif"):
+            cond_text = re.sub(r"^\s*\.\w+\s*", "", line).strip()   # from the raw line: the card tokenizer splits `==`
             if head == ".if":
-                cond_stack.append(bool(evaluate(parse_expr(" ".join(toks[1:]).strip("()")), _const_env(nl))))
+                cond_stack.append(bool(evaluate(parse_expr(cond_text), _const_env(nl))))
+                cond_taken.append(cond_stack[-1])
             elif head == ".else":
-                cond_stack[-1] = not cond_stack[-1]
+                cond_stack[-1] = not cond_taken[-1]
+                cond_taken[-1] = True
             elif head == ".elseif":
-                cond_stack[-1] = (not cond_stack[-1]) and bool(evaluate(parse_expr(" ".join(toks[1:]).strip("()")), _const_env(nl)))
+                cond_stack[-1] = (not cond_taken[-1]) and bool(evaluate(parse_expr(cond_text), _const_env(nl)))
+                cond_taken[-1] = cond_taken[-1] or cond_stack[-1]
             else:
                 cond_stack.pop()
+                cond_taken.pop()
             continue
         if cond_stack and not all(cond_stack):
             continue
@@ -428,6 +436,8 @@ class _Flattener:
             k = card.kind
             if k == "r":
                 v = inst_over.get("r", scope.eval(card.value) if card.value is not None else par("r"))
+                if v is None and card.model is not None and card.model not in self.nl.cards:
+                    v = scope.eval(card.model)   # `R2 vcc 0 res`: a bare identifier that is a parameter, not a model (test/basic.jl:725-737)
                 if v is None:   # model card / geometry: r = rsh*(l-short)/(w-narrow) (src/simpledevices.jl:62-70)
                     mp = {kk.lower(): vv for kk, vv in (self.nl.cards[card.model].params.items() if card.model in self.nl.cards else ())}
                     g = lambda key, d: par(key, mp.get(key, d))

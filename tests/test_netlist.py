@@ -154,3 +154,11 @@ def test_reference_bins_deck():   # test/binning/bins.cir + bins.jl:20-23 (BSIM4
     assert len(modelcard.bins_of(cards, "nmos_3p3")) >= 5 and cards["nmos_3p3.0"].master == "bsim4"
     assert modelcard.find_bin(cards, "nmos_3p3", 2.8e-7, 2.2e-7).name == "nmos_3p3.0"
     assert modelcard.find_bin(cards, "nmos_3p3", 5.0e-7, 2.2e-7).name == "nmos_3p3.1"
+
+
+def test_if_elseif_else_chain():   # `.if/.elseif/.else/.endif` (src/spectre.jl:1445-1525): exactly one branch is live
+    deck = "* chain\n.param sel={sel}\nv1 a 0 1\n.if (sel == 1)\nr1 a 0 1\n.elseif (sel == 2)\nr1 a 0 2\n.else\nr1 a 0 4\n.endif\n"
+    for sel, want in ((1, 1.0), (2, 2.0), (3, 4.0)):
+        nl = netlist.parse_netlist(deck.format(sel=sel))
+        cards = [c for c in nl.top.cards if c.name == "r1"]
+        assert len(cards) == 1 and float(cards[0].value) == want

@@ -186,3 +186,60 @@ def test_vrc_endpoints():   # test/basic.jl:111-141, uncharged start (u0 = 0 -> 
     assert st.max() == 0
     assert abs(y[0, 0, 0]) < DEFTOL and abs(y[0, -1, 0] - 5.0) < DEFTOL
     assert abs(y[1, -1, 0]) < DEFTOL
+
+
+def _branch_i(fc, xf, name):
+    return xf[fc.unknown(name + ".i"), 0] if (name + ".i") in getattr(fc, "unknown_names", []) else None
+
+
+def test_spice_lib_self_include(tmp_path):   # test/basic.jl:312-336: `.LIB "file" section` of the file itself, I(r1) = 1/1337
+    f = tmp_path / "selfinclude.cir"
+    f.write_text("* .LIB definition and include test\nV1 vdd 0 1\n\n.LIB my_lib\nr1 vdd 0 1337\n.ENDL\n.LIB \"selfinclude.cir\" my_lib\n")
+    fl = netlist.flatten(netlist.parse_file(str(f)))
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    assert st.max() == 0
+    # the source current is minus the resistor current (test/sweep.jl:338 sign convention)
+    assert abs(-xf[fl.fc.unknown("v1.i"), 0] - 1 / 1337) < DEFTOL
+
+
+def test_device_named_like_param():   # test/basic.jl:686-723: instance x1 and parameter x1; sys.x1.rload.V == 1000
+    text = """* device == param
+.param x1=1
+.subckt myres p n
+    .param rload=1k
+    rload p n 'rload*x1'
+.ends
+i1 vcc 0 DC -1
+x1 vcc 0 myres
+"""
+    # ParamSim(f; params=(;x1=2.0), x1=(;rload=500,)): top-level parameter x1 = 2, the subcircuit's rload = 500
+    fc, xf = solve_dc(text, {"x1": np.array([2.0]), "x1.rload": np.array([500.0])})
+    assert abs(xf[fc.unknown("vcc"), 0] - 1000.0) < 1e-9
+    fc, xf = solve_dc(text)                      # defaults: 1k * 1 -> 1000 V as well
+    assert abs(xf[fc.unknown("vcc"), 0] - 1000.0) < 1e-9
+    fc, xf = solve_dc(text, {"x1": np.array([2.0])})
+    assert abs(xf[fc.unknown("vcc"), 0] - 2000.0) < 1e-9
+
+
+def test_semiconductor_resistor_and_if_else():   # test/basic.jl:725-752
+    fc, xf = solve_dc("* semiconductor resistor\n.model myres r rsh=500\n.param res=1k\nv1 vcc 0 1\nR1 vcc 0 myres w=1m l=2m\nR2 vcc 0 res\n")
+    assert abs(-xf[fc.unknown("v1.i"), 0] - 2e-3) < 1e-12        # I(r1) = I(r2) = 1e-3 (rsh * l / w = 1k)
+    fc, xf = solve_dc("* ifelse resistor\n.param switch=1\nv1 vcc 0 1\n.if (switch == 1)\nR1 vcc 0 1\n.else\nR1 vcc 0 2\n.endif\n")
+    assert abs(-xf[fc.unknown("v1.i"), 0] - 1.0) < 1e-12
+    fc, xf = solve_dc("* ifelse resistor\n.param switch=0\nv1 vcc 0 1\n.if (switch == 1)\nR1 vcc 0 1\n.else\nR1 vcc 0 2\n.endif\n")
+    assert abs(-xf[fc.unknown("v1.i"), 0] - 0.5) < 1e-12
+
+
+def test_parallel_instances_rc():   # test/basic.jl:143-166: R with m = 10, uncharged start; C.I(0) = 10 v / r, C.V(end) = v
+    v_val, r_val, c_val = 5.0, 2000.0, 1e-9          # test/basic.jl:14-16 flavour: tau = r c / 10 << span
+    text = f"* multi vrc\nv1 vcc 0 {v_val}\nr1 vcc vrc {r_val} m=10\nc1 vrc 0 {c_val}\n"
+    fl = netlist.flatten(netlist.parse_netlist(text))
+    fc = fl.fc
+    tau = r_val * c_val / 10
+    ts = np.array([0.0, 1e-3 * tau, 50 * tau])
+    y, st, _ = orc.tran(fc, 0.0, 50 * tau, ts, opts=orc.default_options(skip_dc=1, reltol=1e-6, vabstol=1e-9))
+    assert st.max() == 0
+    vrc = y[fc.outputs.index(fc.unknown("vrc")) if hasattr(fc, "outputs") else fc.unknown("vrc")]
+    assert abs(vrc[0, 0]) < DEFTOL                                   # C.V(0) = 0
+    assert abs((v_val - vrc[0, 0]) / (r_val / 10) - 10 * v_val / r_val) < DEFTOL   # C.I(0) = current through the 10 parallel R
+    assert abs(vrc[2, 0] - v_val) < DEFTOL                           # C.V(end) = v, C.I(end) = 0
