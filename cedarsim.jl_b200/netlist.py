@@ -64,6 +64,8 @@ class Netlist:
     options: Dict[str, str] = field(default_factory=dict)
     tran: Optional[Tuple[float, float]] = None   # (tstep, tstop)
     includes: List[str] = field(default_factory=list)
+    va_modules: Dict[str, str] = field(default_factory=dict)   # Verilog-A module name (lower case) -> file, from `.hdl`
+    include_dirs: List[str] = field(default_factory=list)
 
 
 # ---------------------------------------------------------------- lexical level
@@ -122,7 +124,7 @@ def _parse_source(toks: List[str]) -> dict:
     """V/I source spec after the two nodes: [value] [DC v] [AC mag [phase]] [PWL(...)|PULSE(...)|SIN(...)]"""
     src = {"dc": None, "ac": None, "tran": None}
     i = 0
-    flat = [t for t in toks if t != ","]
+    flat = [t for t in toks if t not in (",", "=")]   # `dc=1` and `DC 1` are the same thing (test/basic.jl:373)
     while i < len(flat):
         t = flat[i].lower()
         if t == "dc":
@@ -157,8 +159,10 @@ def _parse_source(toks: List[str]) -> dict:
 
 
 def parse_netlist(text: str, path: Optional[str] = None, first_is_title: bool = True, _nl: Optional[Netlist] = None,
-                  _lib_section: Optional[str] = None) -> Netlist:
+                  _lib_section: Optional[str] = None, include_dirs: Optional[Sequence[str]] = None) -> Netlist:
     nl = _nl or Netlist()
+    if include_dirs:
+        nl.include_dirs.extend(include_dirs)
     title, lines = logical_lines(text, first_is_title)
     if _nl is None:
         nl.title = title
@@ -215,6 +219,12 @@ def parse_netlist(text: str, path: Optional[str] = None, first_is_title: bool = 
                     stack.pop()
             elif head == ".model":
                 nl.cards.update(parse_model_cards(line))
+            elif head == ".hdl":   # Verilog-A include (src/spectre.jl: `.hdl` / `ahdl_include`, test/basic.jl:353-380)
+                fname = toks[1].strip("'\"")
+                vpath = _resolve(nl, fname, base)
+                with open(vpath, "r", errors="replace") as f:
+                    for mname in re.findall(r"^\s*module\s+([A-Za-z_][A-Za-z0-9_$]*)", f.read(), re.M):
+                        nl.va_modules[mname.lower()] = vpath
             elif head in (".include", ".inc", ".lib"):
                 fname = toks[1].strip("'\"")
                 section = toks[2].lower() if head == ".lib" and len(toks) > 2 else None
@@ -247,6 +257,17 @@ def _const_env(nl: Netlist) -> Dict[str, float]:
     return env
 
 
+def _resolve(nl: Netlist, fname: str, base: str) -> str:
+    """A file named in the deck: absolute, next to the including file, or in one of the include directories."""
+    if os.path.isabs(fname):
+        return fname
+    for d in [base] + list(nl.include_dirs):
+        cand = os.path.join(d, fname)
+        if os.path.exists(cand):
+            return cand
+    raise NetlistError(f"cannot find {fname!r} (searched {[base] + list(nl.include_dirs)})")
+
+
 def _include(nl: Netlist, fname: str, base: str, section: Optional[str]):
     nl.includes.append(fname)
     low = fname.lower()
@@ -257,7 +278,7 @@ def _include(nl: Netlist, fname: str, base: str, section: Optional[str]):
             return
         raise NetlistError(f"package include {fname!r} is not available (BSIM4 / GF180 / sky130 PDKs are not in the "
                            "reference tree, SURVEY.md fact 5)")
-    path = fname if os.path.isabs(fname) else os.path.join(base, fname)
+    path = _resolve(nl, fname, base)
     with open(path, "r", errors="replace") as f:
         text = f.read()
     if re.search(r"^\s*simulator\s+lang\s*=\s*spectre", text, re.M | re.I) or path.endswith(".scs"):
@@ -460,6 +481,9 @@ class _Flattener:
                 self._mosfet(name, card, nodes, scope, inst_over, mult)
             elif k == "x":
                 child = self._find_subckt(sub, card.model)
+                if child is None and card.model in self.nl.va_modules:
+                    self._va_device(name, card, nodes, scope, mult)
+                    continue
                 if child is None:
                     raise NetlistError(f"unknown subcircuit {card.model!r} for {name}")
                 given = {kk: scope.eval(vv) for kk, vv in card.params.items() if kk != "m"}
@@ -508,6 +532,42 @@ class _Flattener:
             return Wave(W_PULSE, dc=dcv, v=v)
         v = [self.value(f"{name}.sin{i}", x) for i, x in enumerate(vals)]
         return Wave(W_SIN, dc=dcv, v=v)
+
+    def _va_device(self, name: str, card: Card, nodes: List[str], scope: _Scope, mult: float):
+        """Instance of a Verilog-A module brought in by `.hdl`: all module parameters stay run-time parameters (instance
+        values, swept columns), names matched case-insensitively as SPICE does (src/spectre.jl:17-23)."""
+        import hashlib
+        path = self.nl.va_modules[card.model]
+        with open(path, "rb") as f:
+            tag = hashlib.sha1(f.read()).hexdigest()[:10]
+        cm = models.compiled_model(f"{card.model}_{tag}", path, module=self._va_module_name(path, card.model))
+        if cm not in self.models:
+            self.models.append(cm)
+        if self.host:
+            from .va.build import build_host
+            shape = build_host(cm).shape()
+        else:
+            shape = shape_of(cm)
+        if len(nodes) > cm.nports:
+            raise NetlistError(f"{name}: {len(nodes)} nodes for Verilog-A module {cm.module} with {cm.nports} ports")
+        lut = {p.lower(): p for p in cm.params}
+        over = self.overrides(name + ".", list(lut))
+        vals: Dict[str, Num] = {}
+        for k in set(card.params) | set(over):
+            if k == "m":
+                continue
+            if k not in lut:
+                raise NetlistError(f"{name}: Verilog-A module {cm.module} has no parameter {k!r}")
+            vals[lut[k]] = self.value(f"{name}.{k}", over[k] if k in over else scope.eval(card.params[k]))
+        self.fc.va_instance(name, self.fc.va_model(shape), nodes, vals, m=mult)
+
+    @staticmethod
+    def _va_module_name(path: str, lower: str) -> str:
+        with open(path, "r", errors="replace") as f:
+            for mname in re.findall(r"^\s*module\s+([A-Za-z_][A-Za-z0-9_$]*)", f.read(), re.M):
+                if mname.lower() == lower:
+                    return mname
+        raise NetlistError(f"module {lower!r} not found in {path}")
 
     def _binned(self, name: str, card: Card, scope: _Scope, over: Dict[str, Num]) -> ModelCard:
         """`<model>.<N>` bins: the bin whose [lmin,lmax) x [wmin,wmax) window holds scale*l, scale*w

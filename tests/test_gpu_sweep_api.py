@@ -83,3 +83,15 @@ VD D 0 AC 1 SIN (0.35 0.3 1e7)
     assert st.max() == 0 and np.abs(sols.y - y).max() < 5e-3
     q = sols.array(cs.sys.node_q)
     assert q.shape == (3, 3, len(sols.t)) and q.min() < 0.1 and q.max() > 0.5   # the inverter switches rail to rail
+
+
+@pytest.mark.gpu
+def test_verilog_a_include_dc_sweep():   # test/basic.jl:368-380 through the sweep API: sys.v1.I == -1/r for every point
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = '* Verilog Include 2\n.hdl "va_resistor.va"\n\nx1 vcc 0 BasicVAResistor r=2k\nv1 vcc 0 dc=1\n'
+    r = np.linspace(500.0, 4000.0, 64)
+    cs = CircuitSweep(deck, Sweep("x1.r", r), include_dirs=[inc])
+    sols = dc_(cs)
+    assert sols.status.max() == 0
+    assert np.allclose(sols.array(cs.sys.v1.I), -1.0 / r, rtol=1e-12, atol=0)

@@ -243,3 +243,26 @@ def test_parallel_instances_rc():   # test/basic.jl:143-166: R with m = 10, unch
     assert abs(vrc[0, 0]) < DEFTOL                                   # C.V(0) = 0
     assert abs((v_val - vrc[0, 0]) / (r_val / 10) - 10 * v_val / r_val) < DEFTOL   # C.I(0) = current through the 10 parallel R
     assert abs(vrc[2, 0] - v_val) < DEFTOL                           # C.V(end) = v, C.I(end) = 0
+
+
+VA_INCLUDE_DECK = """* Verilog Include 2
+.hdl "va_resistor.va"
+
+x1 vcc 0 BasicVAResistor r=2k
+v1 vcc 0 dc=1
+"""
+
+
+def test_verilog_a_include():   # test/basic.jl:368-380: `.hdl` + an X instance of the module, sys.v1.I == -1/2e3
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    nl = netlist.parse_netlist(VA_INCLUDE_DECK, include_dirs=[inc])
+    fl = netlist.flatten(nl, host=True)
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    assert st.max() == 0 and abs(xf[fl.fc.unknown("v1.i"), 0] + 1 / 2e3) < 1e-15
+    # the module parameter as a sweep column, addressed SPICE-style in lower case
+    fl = netlist.flatten(nl, {"x1.r": np.array([1e3, 2e3, 4e3])}, host=True)
+    x, xf, st, _ = orc.dc(fl.fc, fl.params)
+    assert st.max() == 0 and np.allclose(xf[fl.fc.unknown("v1.i")], [-1e-3, -5e-4, -2.5e-4], rtol=1e-14, atol=0)
+    with pytest.raises(netlist.NetlistError, match="no parameter"):
+        netlist.flatten(netlist.parse_netlist(VA_INCLUDE_DECK.replace("r=2k", "rr=2k"), include_dirs=[inc]), host=True)
