@@ -1,7 +1,7 @@
-"""BASELINE.json configs 2 and 4 at their FULL sizes on the GPU (through the C ABI), checked by
+"""BASELINE.json configs 2, 3, 4 and 5 at their FULL sizes on the GPU (through the C ABI), checked by
 (i) a seeded subset against the CPU oracle at the parity tolerances and (ii) size-independent properties of the
 domain (all points converge, I-V monotone, zero current at zero bias, logic levels at the reference's sample times).
-Config 3 at full size is what bench.py runs (its `parity_check` key); GF180 / BSIM4 are not in the reference tree, so
+Config 3 is also what bench.py times (its `parity_check` key); GF180 / BSIM4 are not in the reference tree, so
 the same topologies run on BSIM-CMG 107 + ASAP7 cards."""
 import numpy as np
 import pytest
@@ -116,3 +116,40 @@ def test_config5_corner_temperature_mismatch_131072(host_bsimcmg):
     # 2 C dv / dt ~ 1e-11 A at dt = 1 ps and ~10 fF of node capacitance; asserted at 1e-6 of the waveform's peak (~4e-5 A)
     ipk = np.abs(yo[2]).max()
     assert np.all(err[2] <= 1e-6 * np.abs(yo[2]) + 1e-6 * ipk), (err[2].max(), ipk)
+
+
+def test_config3_dff_monte_carlo_16384(host_bsimcmg):
+    """SURVEY 8(d) config 3 at full size with the bench options: 16 384 Monte-Carlo instances of the 30-FET DFF, adaptive
+    trapezoidal, 0 .. 600 ns.  Every point converges, Q follows the reference's known pattern (test/gf180_dff.jl:29-33:
+    0, 0, VDD, VDD, VDD at 1.5 / 2.5 / 4.5 / 5.5 / 6.0e-7 s), and a seeded subset agrees with the oracle run with the same
+    options within the LTE tolerance away from the edges."""
+    from helpers import x0_from
+    nodeset = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki=0.0, cki=0.7)
+    fc, ms = circuits.dff(host=host_bsimcmg)
+    B = 16384
+    P = circuits.dff_mc_params(fc, B)
+    x0 = x0_from(fc, nodeset)
+    ts = np.linspace(0, 6e-7, 61)
+    kw = dict(reltol=1e-4, vabstol=1e-6, iabstol=1e-12, nr_reltol=1e-5, nr_vabstol=1e-7, nr_iabstol=1e-13, nr_rate_test=1)
+    plan = engine.Circuit(fc, ms).plan(B)
+    plan.set_params(P)
+    plan.set_x0(x0)
+    y, st, stats = plan.tran(0.0, 6e-7, ts, engine.default_options(value_rounds=2, **kw))
+    plan.close()
+    assert st.max() == 0
+    q = y[0]   # outputs of circuits.dff: node_q, node_d
+    for t, want in ((1.5e-7, 0.0), (2.5e-7, 0.0), (4.5e-7, 0.7), (5.5e-7, 0.7), (6.0e-7, 0.7)):
+        k = int(round(t / 6e-7 * 60))
+        assert np.abs(q[k] - want).max() < 1e-4, (t, np.abs(q[k] - want).max())   # the reference's atol
+    # work per point as DESIGN.md section 5 quotes it
+    assert 1500 < stats["steps_accepted"] / B < 2500 and stats["newton_iters"] / B < 6000
+    rng = np.random.default_rng(3)
+    sel = np.sort(rng.choice(B, 16, replace=False))
+    orc.set_x0(x0)
+    try:
+        yo, so, _ = orc.tran(fc, 0.0, 6e-7, ts, params=np.ascontiguousarray(P[:, sel]), opts=orc.default_options(**kw), nthreads=8)
+    finally:
+        orc.set_x0(None)
+    assert so.max() == 0
+    settled = np.abs(np.gradient(yo, axis=1)).max(axis=(0, 2)) < 1e-3
+    assert np.abs(y[:, :, sel] - yo)[:, settled, :].max() < 2e-3
