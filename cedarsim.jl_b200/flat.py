@@ -212,6 +212,7 @@ class VAModelShape:
     noise_neg: List[int] = field(default_factory=list)
     host_setupn: int = 0
     host_noise: int = 0
+    branch_terms: List[int] = field(default_factory=list)   # terminals that are branch currents (V() <+ branches, I() probes)
 
 
 def shape_of(cm) -> VAModelShape:
@@ -219,7 +220,8 @@ def shape_of(cm) -> VAModelShape:
     return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
                         ncache_n=getattr(cm, "ncache_n", 0),
                         noise_pos=[int(s[0]) for s in getattr(cm, "noise_sources", [])],
-                        noise_neg=[int(s[1]) for s in getattr(cm, "noise_sources", [])])
+                        noise_neg=[int(s[1]) for s in getattr(cm, "noise_sources", [])],
+                        branch_terms=list(getattr(cm, "branch_terms", [])))
 
 
 @dataclass
@@ -243,6 +245,7 @@ class FlatCircuit:
     outputs: List[int] = field(default_factory=list)
     _node_index: Dict[str, int] = field(default_factory=dict)
     _finalized: bool = False
+    va_branches: List[str] = field(default_factory=list)   # names of branch-current unknowns of Verilog-A instances
 
     # ---- construction helpers -------------------------------------------------
     def node(self, name: str) -> int:
@@ -310,8 +313,14 @@ class FlatCircuit:
         name = name.lower()
         nports = len(ports)
         term = [self.node(p) if isinstance(p, str) else p for p in ports]
-        for internal in shape.terminals[nports:]:
-            term.append(self.node(f"{name}.{internal}"))
+        for k, internal in enumerate(shape.terminals[nports:], start=nports):
+            if k in shape.branch_terms:
+                # a branch current of the device (its own MNA unknown): allocated after the node voltages by finalize();
+                # until then a placeholder -2 - <index into va_branches>
+                self.va_branches.append(f"{name}.{internal.lower()}")
+                term.append(-2 - (len(self.va_branches) - 1))
+            else:
+                term.append(self.node(f"{name}.{internal}"))
         lut = {p.lower(): i for i, p in enumerate(shape.params)}
         par = {}
         for k, v in params.items():
@@ -331,6 +340,12 @@ class FlatCircuit:
             if d.branch == -2:
                 d.branch = nn + len(self.branch_names)
                 self.branch_names.append(d.name + ".i")
+        slot = {}
+        for k, bname in enumerate(self.va_branches):
+            slot[-2 - k] = nn + len(self.branch_names)
+            self.branch_names.append(bname)
+        for vi in self.va_insts:
+            vi.term = [slot.get(t, t) for t in vi.term]
         return self
 
     @property

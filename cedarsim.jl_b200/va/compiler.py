@@ -35,7 +35,7 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-GEN_VERSION = 3   # bump when the emitted code changes: models cached under _gen/ are regenerated
+GEN_VERSION = 4   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
 CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "4"))
 CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "8"))
@@ -378,6 +378,7 @@ class CompiledModel:
     source_n: str = ""
     ncache_n: int = 0
     noise_sources: List[Tuple[int, int, str, str]] = field(default_factory=list)
+    branch_terms: List[int] = field(default_factory=list)   # terminals that are branch CURRENTS (voltage branches, I() probes)
     gen_version: int = 0   # GEN_VERSION of the generator that wrote `source` (cached models of another version are rebuilt)
 
     @property
@@ -402,6 +403,18 @@ class _Compiler:
         self.runtime_params = None if runtime_params is None else {k.upper() for k in runtime_params}
         self.terms = list(mod.nets)
         self.tindex = {n: i for i, n in enumerate(self.terms)}
+        # Branches that need a current unknown (src/vasim.jl:792,802-808: "only used ones get a current unknown"): the
+        # target of a `V(a,b) <+` contribution ('V') and a branch whose current is probed with `I(a,b)` ('P').  Each is
+        # one more terminal "I(a,b)" after the internal nodes; the circuit allocates it among the branch currents.
+        #   row of the unknown:  'V':  V(a) - V(b) - sum(contributions) = 0      'P':  I_br - sum(contributions) = 0
+        #   KCL:                 +I_br leaves a, enters b (src/simulate_ir.jl:112-120)
+        self.branch_kind: Dict[Tuple[str, str], str] = {}
+        self._scan_branches(list(mod.analog))
+        self.branch_terms: List[int] = []
+        for (a, b) in self.branch_kind:
+            self.tindex[f"I({a},{b})"] = len(self.terms)
+            self.branch_terms.append(len(self.terms))
+            self.terms.append(f"I({a},{b})")
         self.S: List[str] = []      # setup stream
         self.E: List[str] = []      # eval stream
         self.state: Dict[str, VS] = {}
@@ -823,8 +836,14 @@ class _Compiler:
 
     def _probe(self, e) -> Val:
         acc, nodes = e[1], e[2]
+        if acc in ("I", "flow"):
+            bro = self._branch_of(nodes)
+            if bro is None:
+                raise VACompileError(f"probe {acc}({', '.join(nodes)}): branch has no current unknown")
+            br, sign, _ = bro
+            return self.emit_val("r", f"VT({br})" if sign > 0 else f"-VT({br})", {} if self.no_deriv else {br: sign})
         if acc not in ("V", "potential"):
-            raise VACompileError(f"probe {acc}({', '.join(nodes)}) is not supported (branch currents are not MNA unknowns)")
+            raise VACompileError(f"probe {acc}({', '.join(nodes)}) is not supported")
         if len(nodes) == 1 and nodes[0] in self.mod.branches:
             nodes = list(self.mod.branches[nodes[0]])
         idx = []
@@ -1388,12 +1407,88 @@ class _Compiler:
                 self.decl_deps.setdefault(an, set())
                 self.state[an] = VS(True, frozenset(), None, None)
 
+    # ---- branches with a current unknown ---------------------------------------------------
+    def _branch_nodes(self, nodes) -> Tuple[str, str]:
+        nodes = list(nodes)
+        if len(nodes) == 1 and nodes[0] in self.mod.branches:
+            nodes = list(self.mod.branches[nodes[0]])
+        g = lambda n: "0" if n in ("0", "gnd") else n
+        return (g(nodes[0]), g(nodes[1]) if len(nodes) > 1 else "0")
+
+    def _scan_branches(self, x):
+        if isinstance(x, tuple):
+            if len(x) >= 3 and x[0] == "contrib" and x[1] in ("V", "potential"):
+                a, b = self._branch_nodes(x[2])
+                if (b, a) in self.branch_kind:
+                    self.branch_kind[(b, a)] = "V"
+                else:
+                    self.branch_kind[(a, b)] = "V"
+            elif len(x) >= 3 and x[0] == "probe" and x[1] in ("I", "flow"):
+                a, b = self._branch_nodes(x[2])
+                if (a, b) not in self.branch_kind and (b, a) not in self.branch_kind:
+                    self.branch_kind[(a, b)] = "P"
+            for y in x:
+                self._scan_branches(y)
+        elif isinstance(x, list):
+            for y in x:
+                self._scan_branches(y)
+        elif isinstance(x, dict):
+            for y in x.values():
+                self._scan_branches(y)
+
+    def _branch_of(self, nodes):
+        """(terminal index of the branch current, orientation sign, kind) or None for an ordinary branch."""
+        a, b = self._branch_nodes(nodes)
+        if (a, b) in self.branch_kind:
+            return self.tindex[f"I({a},{b})"], 1.0, self.branch_kind[(a, b)]
+        if (b, a) in self.branch_kind:
+            return self.tindex[f"I({b},{a})"], -1.0, self.branch_kind[(b, a)]
+        return None
+
+    def _acc(self, kind: str, node: int, sign: float, v: Val):
+        """acc<kind>_<node> += sign * v  (value and partials), in the eval stream"""
+        an = f"acc{kind}_{node}"
+        self.types[an] = "r"
+        s = self.vs(an)
+        op = "+=" if sign > 0 else "-="
+        self.E.append(f"{an} {op} {v.c};")
+        deps = set(s.deps) if s.dyn else set()
+        for kk, x in v.d.items():
+            self.E.append(f"{an}__d{kk} {op} {self._datom(x)};")
+            deps.add(kk)
+        self.count("add", 1 + len(v.d))
+        self.dyn_vars.add(an)
+        self.decl_deps.setdefault(an, set()).update(deps)
+        self.state[an] = VS(True, frozenset(deps), None, None)
+
+    def _open_branches(self):
+        """Base terms of every branch-current unknown, emitted once at the top of the eval stream."""
+        for (a, b), kind in self.branch_kind.items():
+            br = self.tindex[f"I({a},{b})"]
+            x = self.emit_val("r", f"VT({br})", {} if self.no_deriv else {br: 1.0})
+            ia = self.tindex.get(a) if a != "0" else None
+            ib = self.tindex.get(b) if b != "0" else None
+            if ia is not None:
+                self._acc("I", ia, 1.0, x)
+            if ib is not None:
+                self._acc("I", ib, -1.0, x)
+            if kind == "V":
+                self._acc("I", br, 1.0, self.force(self._probe(("probe", "V", [n for n in (a, b)]))))
+            else:
+                self._acc("I", br, 1.0, x)
+
     def contrib(self, st):
         acc, nodes, e = st[1], st[2], st[3]
         if len(nodes) == 1 and nodes[0] in self.mod.branches:
             nodes = list(self.mod.branches[nodes[0]])
-        if acc not in ("I", "flow"):
-            raise VACompileError(f"{acc}() contributions are not supported yet (voltage branches need extra MNA unknowns)")
+        if acc not in ("I", "flow", "V", "potential"):
+            raise VACompileError(f"{acc}() contributions are not supported")
+        bro = self._branch_of(nodes)
+        is_v = acc in ("V", "potential")
+        if bro is not None and (bro[2] == "V") != is_v:
+            # the reference resets the accumulator when the kind of contribution to a branch changes
+            # (src/vasim.jl:149-154,172-177: a switch branch); not needed by any model on the sweep path
+            raise VACompileError(f"branch ({', '.join(nodes)}) receives both I() and V() contributions (switch branch); unsupported")
         pos = self.tindex.get(nodes[0]) if nodes[0] not in ("0", "gnd") else None
         neg = None
         if len(nodes) > 1 and nodes[1] not in ("0", "gnd"):
@@ -1418,22 +1513,15 @@ class _Compiler:
             v = self.force(v)
             if v.typ == "i":
                 v = Val("r", self._cast(v.c, "i", "r"), {})
+            if bro is not None:
+                # the branch has its own unknown: its row is  (V(a,b) | I_br) - sum(contributions) = 0, the KCL flows
+                # were emitted by _open_branches; a reversed pair contributes with the opposite sign
+                self._acc(kind, bro[0], -bro[1], v)
+                continue
             for node, sign in ((pos, 1.0), (neg, -1.0)):
                 if node is None:
                     continue
-                an = f"acc{kind}_{node}"
-                self.types[an] = "r"
-                s = self.vs(an)
-                op = "+=" if sign > 0 else "-="
-                self.E.append(f"{an} {op} {v.c};")
-                deps = set(s.deps) if s.dyn else set()
-                for kk, x in v.d.items():
-                    self.E.append(f"{an}__d{kk} {op} {self._datom(x)};")
-                    deps.add(kk)
-                self.count("add", 1 + len(v.d))
-                self.dyn_vars.add(an)
-                self.decl_deps.setdefault(an, set()).update(deps)
-                self.state[an] = VS(True, frozenset(deps), None, None)
+                self._acc(kind, node, sign, v)
         self.dynctl = saved
 
     # -- control flow --
@@ -1672,7 +1760,10 @@ class _Compiler:
             if bad:
                 raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
-        self.drop_seed = None if self.no_deriv else self._pick_drop_seed(body)
+        # (translational invariance holds for node voltages only, not for branch-current unknowns)
+        self.drop_seed = None if (self.no_deriv or self.branch_terms) else self._pick_drop_seed(body)
+        if not self.noise:
+            self._open_branches()
         _NOISE_LIVE[0] = self.noise
         try:
             pruned, _ = prune_dead(body, set(), mod.functions)
@@ -1722,7 +1813,7 @@ class _Compiler:
                 pass
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
                              ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
-                             param_defaults=defaults)
+                             param_defaults=defaults, branch_terms=list(self.branch_terms))
 
     def _stage_cache(self):
         """Re-lays the cache out as a *stream* in the order the eval function consumes it.

@@ -170,3 +170,27 @@ def test_bsimcmg_dff_adaptive_known_answers(host_bsimcmg):
     want = np.array([0, 0, 0.7, 0.7, 0.7])[:, None]
     assert np.abs(yg[0] - want).max() < 1e-3
     assert np.abs(yg - yo).max() < 1e-3
+
+
+def test_verilog_a_voltage_branches():
+    """V() <+ branches and I() probes (branch-current unknowns of Verilog-A devices) on the GPU: DC known answers and a
+    fixed-step RL transient with a Verilog-A inductor against the oracle (decks of tests/test_va_compiler.py)."""
+    import os
+    from cedarsim.jl_b200 import netlist
+    from test_va_compiler import VBRANCH_DC, VBRANCH_RL
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    fl = netlist.flatten(netlist.parse_netlist(VBRANCH_DC, include_dirs=[inc]), host=True)
+    fc = fl.fc
+    (xg, xfg, sg, _), (xo, xfo, so, _) = run_dc_both(fc, fl.models, np.zeros((0, 4)))
+    assert sg.max() == 0 and so.max() == 0
+    assert np.abs(xfg - xfo).max() < DC_VTOL
+    assert np.abs(xfg[fc.unknown("a")] - 1.5).max() < 1e-12 and np.abs(xfg[fc.unknown("x1.i(p,n)")] + 0.05).max() < 1e-13
+    assert np.abs(xfg[fc.unknown("o")] - 0.5).max() < 1e-12
+    L = np.linspace(1e-6, 4e-6, 64)
+    fl = netlist.flatten(netlist.parse_netlist(VBRANCH_RL, include_dirs=[inc]), {"x1.l": L}, host=True)
+    ts = np.linspace(0, 5e-8, 51)
+    (yg, sg, _), (yo, so, _) = run_tran_both(fl.fc, fl.models, fl.params, 0.0, 5e-8, ts, fixed_step=1, dt=1e-10)
+    assert sg.max() == 0 and so.max() == 0
+    assert_tran_close(yg, yo, rtol=1e-6, atol=1e-9)
+    k = fl.fc.unknown("x1.i(p,n)")
+    assert np.all(np.diff(yg[k], axis=0) >= -1e-12) and np.all(yg[k, -1] < 0.01)      # the current rises towards V / R

@@ -87,8 +87,9 @@ end endmodule"""
 
 
 def test_unsupported_constructs_fail_loudly():
+    # a probe of a discipline access the engine has no unknown for
     src = """`include "disciplines.vams"
-module vs(p, n); inout p, n; electrical p, n; analog begin V(p,n) <+ 1.0; end endmodule"""
+module vs(p, n); inout p, n; electrical p, n; analog begin I(p,n) <+ Temp(p,n); end endmodule"""
     with pytest.raises(VACompileError):
         compile_va_text(src)
 
@@ -130,3 +131,59 @@ def test_bsimcmg_physical_sanity(host_bsimcmg):
         ids.append(I[4])   # current leaving di through the channel
     ids = np.array(ids)
     assert np.all(np.diff(ids) > 0) and ids[0] < 1e-8 and 5e-5 < ids[-1] < 5e-4   # monotone, off ~nA, on ~100 uA
+
+
+VBRANCH_DC = """* voltage branches and current probes
+.hdl "vbranch.va"
+x1 a 0 va_vsrc vdc=2 rs=10
+r1 a 0 30
+x2 a2 0 va_vsrc_rev vdc=2 rs=10
+r2 a2 0 30
+v3 c 0 1
+x3 c 0 o 0 va_ccvs rsense=100 k=50
+r3 o 0 1k
+"""
+VBRANCH_RL = """* RL with a Verilog-A inductor
+.hdl "vbranch.va"
+v1 in 0 PWL(0 0 1n 1)
+r1 in x 100
+x1 x 0 va_ind l=1u
+"""
+
+
+def test_voltage_branches_and_current_probes():
+    """`V(a,b) <+` branches and `I(a,b)` probes get a branch-current unknown each (src/vasim.jl:786-808: only used
+    branches do), row  V(a,b) - sum = 0  resp.  I_br - sum = 0, +I_br leaving a (src/simulate_ir.jl:112-120);
+    a reversed pair contributes with the opposite sign (src/vasim.jl:165,177)."""
+    from cedarsim.jl_b200 import netlist
+    from oracle import orc
+    inc = os.path.join(HERE, "va")
+    cm = compile_va_file(os.path.join(inc, "vbranch.va"), module="va_ccvs")
+    assert cm.terminals == ["p", "n", "op", "on", "I(op,on)", "I(p,n)"] and cm.branch_terms == [4, 5] and cm.nports == 4
+    fl = netlist.flatten(netlist.parse_netlist(VBRANCH_DC, include_dirs=[inc]), host=True)
+    fc = fl.fc
+    assert fc.branch_names == ["v3.i", "x1.i(p,n)", "x2.i(n,p)", "x3.i(op,on)", "x3.i(p,n)"]      # currents after the node voltages
+    x, xf, st, _ = orc.dc(fc, None)
+    assert st.max() == 0
+    val = lambda n: xf[fc.unknown(n), 0]
+    # Thevenin source 2 V / 10 Ohm into 30 Ohm, written on (p,n) and on the reversed pair
+    assert abs(val("a") - 1.5) < 1e-12 and abs(val("x1.i(p,n)") + 0.05) < 1e-14
+    assert abs(val("a2") - 1.5) < 1e-12 and abs(val("x2.i(n,p)") - 0.05) < 1e-14
+    # CCVS: the probed current of an I() <+ branch drives a V() <+ branch
+    assert abs(val("x3.i(p,n)") - 0.01) < 1e-15 and abs(val("o") - 0.5) < 1e-13 and abs(val("v3.i") + 0.01) < 1e-15
+    # inductor V <+ L ddt(I): ramp-and-hold response of the RL circuit against its closed form
+    fl = netlist.flatten(netlist.parse_netlist(VBRANCH_RL, include_dirs=[inc]), {"x1.l": np.array([1e-6, 2e-6])}, host=True)
+    fc = fl.fc
+    ts = np.linspace(0, 5e-8, 51)
+    y, st, _ = orc.tran(fc, 0.0, 5e-8, ts, params=fl.params, opts=orc.default_options(reltol=1e-6, vabstol=1e-9, iabstol=1e-12))
+    assert st.max() == 0
+    cur = y[fc.unknown("x1.i(p,n)")]
+    for k, L in enumerate((1e-6, 2e-6)):
+        tau, T = L / 100.0, 1e-9
+        ramp = lambda t: (1 / 100.0) * (t - tau * (1 - np.exp(-t / tau))) / T
+        exact = np.where(ts <= T, ramp(ts), ramp(ts) - ramp(np.maximum(ts - T, 0.0)))
+        assert np.abs(cur[:, k] - exact).max() < 5e-7
+    # a branch that receives both kinds of contribution is the reference's switch branch: refused, not mis-compiled
+    with pytest.raises(VACompileError, match="both"):
+        compile_va_text("`include \"disciplines.vams\"\nmodule sw(p,n); inout p,n; electrical p,n;\nanalog begin\n"
+                        "if (V(p,n) > 0) V(p,n) <+ 0; else I(p,n) <+ 0;\nend\nendmodule\n")
