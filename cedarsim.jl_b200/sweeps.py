@@ -452,7 +452,7 @@ class CircuitSweep:
     `builder(columns: dict, B: int) -> Flattened`."""
 
     def __init__(self, circuit, iterator, outputs: Optional[Sequence[str]] = None, devices: Optional[Sequence[int]] = None,
-                 host: bool = False, include_dirs: Optional[Sequence[str]] = None):
+                 host: bool = False, include_dirs: Optional[Sequence[str]] = None, lang: str = "spice"):
         self.iterator = sweepify(iterator)
         self.shape = self.iterator.shape
         self.circuit = circuit
@@ -460,7 +460,11 @@ class CircuitSweep:
         B = len(self.iterator)
         if isinstance(circuit, str):
             from .netlist import parse_netlist
-            circuit = parse_netlist(circuit, include_dirs=include_dirs)   # include_dirs as solve_spice_code(...; include_dirs)
+            if lang == "spectre":
+                from .spectre import parse_spectre
+                circuit = parse_spectre(circuit, include_dirs=include_dirs)
+            else:
+                circuit = parse_netlist(circuit, include_dirs=include_dirs)   # include_dirs as solve_spice_code(...; include_dirs)
         if isinstance(circuit, Netlist):
             self.flat: Flattened = flatten(circuit, self.columns, B=B, outputs=outputs, host=host)
         elif callable(circuit):

@@ -1,0 +1,99 @@
+"""Spectre-language subset reader (cedarsim.jl_b200/spectre.py) against the reference's own Spectre-syntax tests."""
+import os
+
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import netlist, spectre
+from cedarsim.jl_b200.sweeps import CircuitSweep, Sweep
+from oracle import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SOURCES = """
+I1 (0 1) isource dc=2.2u
+R1 (1 0) resistor r=1000
+
+I2 (0 2) isource type=pwl wave=[0 1m .5 2m 1 1.75m]
+R2 (2 0) resistor r=2k
+
+V3 (0 3) vsource dc=1.5
+R3 (3 0) resistor r=1k
+
+V4 (0 4) vsource type=pwl wave=[ 0 1 .5 2 \\
+        1 5]
+R4 (4 0) resistor r=4k
+"""
+
+
+def test_simple_spectre_sources(tmp_path):   # test/basic.jl:168-205 (read from a file, as there; the bsource rows are out of the subset)
+    f = tmp_path / "sources.scs"
+    f.write_text(SOURCES)
+    fl = netlist.flatten(spectre.parse_spectre_file(str(f)))
+    fc = fl.fc
+    ts = np.linspace(0.0, 1.0, 11)
+    y, st, _ = orc.tran(fc, 0.0, 1.0, ts, opts=orc.default_options())
+    assert st.max() == 0
+    v = lambda n: y[fc.unknown(n), :, 0]
+    assert np.allclose(v("1"), 2.2e-3) and np.allclose(v("1") / 1000, 2.2e-6)          # node_1, R1.I
+    assert np.allclose(v("3"), -1.5) and np.allclose(v("3") / 1e3, -1.5e-3)            # node_3, R3.I
+    assert np.isclose(v("2")[-1], 3.5) and np.isclose(v("2")[-1] / 2e3, 1.75e-3)       # node_2[end], R2.I[end]
+    assert np.isclose(v("4")[-1], -5.0) and np.isclose(v("4")[-1] / 4e3, -1.25e-3)     # node_4[end], R4.I[end]
+    with pytest.raises(netlist.NetlistError, match="behavioural"):
+        spectre.parse_spectre(SOURCES + "B5 (0 5) bsource v=$time*V(3)\n")
+
+
+SUBCKT = """
+subckt myres vcc gnd
+    parameters r=1k
+    r1 (vcc gnd) resistor r=r
+ends myres
+
+x1 (vcc 0) myres r=2k
+v1  (vcc 0) vsource dc=1
+"""
+
+
+def test_simple_spectre_subcircuit():   # test/basic.jl:265-278: sys.x1.r1.I == 0.5e-3
+    nl = spectre.parse_spectre(SUBCKT)
+    fl = netlist.flatten(nl)
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    assert st.max() == 0 and abs(-xf[fl.fc.unknown("v1.i"), 0] - 0.5e-3) < 1e-15
+    # the subcircuit parameter as a sweep column through the sweep API's naming (x1.r)
+    cs = CircuitSweep(nl, Sweep("x1.r", np.array([1e3, 2e3, 4e3])))
+    x, xf, st, _ = orc.dc(cs.flat.fc, cs.flat.params)
+    assert np.allclose(-xf[cs.flat.fc.unknown("v1.i")], [1e-3, 5e-4, 2.5e-4], rtol=1e-14, atol=0)
+
+
+def test_spectre_ahdl_include():   # test/basic.jl:353-367: ahdl_include + instance of the module, sys.v1.I == -1/2e3
+    ckt = 'ahdl_include "va_resistor.va"\n\nx1 (vcc 0) BasicVAResistor R=2k\nv1 (vcc 0) vsource dc=1\n'
+    fl = netlist.flatten(spectre.parse_spectre(ckt, include_dirs=[os.path.join(HERE, "va")]), host=True)
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    assert st.max() == 0 and abs(xf[fl.fc.unknown("v1.i"), 0] + 1 / 2e3) < 1e-15
+
+
+def test_spectre_model_cards_and_sources(host_bsimcmg):
+    # the BSIM-CMG inverter of test/bsimcmg/inverter_cmg_cedar.cir written in Spectre syntax: same flat circuit as the SPICE deck
+    scs = """
+include "jlpkg://ASAP7PDK/7nm_TT.scs"
+mneg (q d vss vss) nmos_lvt
+mpos (q d vdd vdd) pmos_lvt nfin=2
+vvdd (vdd 0) vsource dc=1.0
+vvss (vss 0) vsource dc=0.0
+cq (d 0) capacitor c=1e-15
+vd (d 0) vsource type=sine sinedc=0.5 ampl=0.01 freq=1e7 mag=1
+"""
+    spice = """** Test circuit
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+mneg Q D VSS VSS nmos_lvt
+mpos Q D VDD VDD pmos_lvt nfin=2
+VVDD VDD 0 1.0
+VVSS VSS 0 0.0
+CQ D 0 1e-15
+VD D 0 AC 1 SIN (0.5 0.01 1e7)
+"""
+    a = netlist.flatten(spectre.parse_spectre(scs), {"mneg.nfin": np.array([1.0, 2.0])})
+    b = netlist.flatten(netlist.parse_netlist(spice), {"mneg.nfin": np.array([1.0, 2.0])})
+    assert a.fc.node_names == b.fc.node_names and a.fc.branch_names == b.fc.branch_names
+    assert len(a.fc.va_insts) == 2 and a.fc.param_names == b.fc.param_names
+    assert [(w.kind, w.ac) for w in a.fc.waves] == [(w.kind, w.ac) for w in b.fc.waves]
