@@ -360,7 +360,7 @@ class FlatCircuit:
     def unknown(self, name: str) -> int:
         """Index of a node voltage ('q', 'node_q') or branch current ('v1.i', 'v1.I')."""
         self.finalize()
-        key = name.lower()
+        key = name.lower().replace(" ", "")   # `x1.I(p, n)` as the reference prints it == `x1.i(p,n)`
         if key.startswith("node_"):
             key = key[5:]
         if key in self._node_index:

@@ -367,8 +367,14 @@ class Flattened:
 
 
 class _Flattener:
-    def __init__(self, nl: Netlist, sweep: Dict[str, np.ndarray], B: int, host: bool):
+    def __init__(self, nl: Netlist, sweep: Dict[str, np.ndarray], B: int, host: bool, outputs: Optional[Sequence[str]] = None):
         self.nl, self.sweep, self.B, self.host = nl, {k.lower(): v for k, v in sweep.items()}, B, host
+        # branch currents of Verilog-A instances asked for as observables: `<inst>.i(a,b)`
+        self.want_branches: Dict[str, List[Tuple[str, str]]] = {}
+        for o in outputs or ():
+            m = re.match(r"^(.*)\.i\(([^,()]+),([^,()]+)\)$", str(o).lower().replace(" ", "")) if isinstance(o, str) else None
+            if m:
+                self.want_branches.setdefault(m.group(1), []).append((m.group(2), m.group(3)))
         self.fc = FlatCircuit()
         self.columns: List[np.ndarray] = []
         self.models: list = []
@@ -540,7 +546,11 @@ class _Flattener:
         path = self.nl.va_modules[card.model]
         with open(path, "rb") as f:
             tag = hashlib.sha1(f.read()).hexdigest()[:10]
-        cm = models.compiled_model(f"{card.model}_{tag}", path, module=self._va_module_name(path, card.model))
+        probes = tuple(self.want_branches.get(name, ()))   # sys.<inst>.var"I(p, n)" observables become unknowns of the device
+        if probes:
+            tag += "_" + hashlib.sha1(repr(probes).encode()).hexdigest()[:6]
+        cm = models.compiled_model(f"{card.model}_{tag}", path, module=self._va_module_name(path, card.model),
+                                   probe_branches=probes)
         if cm not in self.models:
             self.models.append(cm)
         if self.host:
@@ -650,7 +660,7 @@ def flatten(nl: Netlist, sweep: Optional[Dict[str, np.ndarray]] = None, B: int =
     sweep = sweep or {}
     if sweep:
         B = len(next(iter(sweep.values())))
-    fl = _Flattener(nl, sweep, B, host).run()
+    fl = _Flattener(nl, sweep, B, host, outputs).run()
     fl.fc.finalize()
     if outputs is not None:
         fl.fc.set_outputs(list(outputs))

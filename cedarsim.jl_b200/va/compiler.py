@@ -389,7 +389,7 @@ class CompiledModel:
 class _Compiler:
     def __init__(self, mod: Module, name: str, const_params: Optional[Dict[str, float]] = None,
                  runtime_params: Optional[Sequence[str]] = None, no_deriv: bool = False, skip_funcs=(),
-                 noise: bool = False):
+                 noise: bool = False, probe_branches: Sequence[Tuple[str, str]] = ()):
         self.mod = mod
         self.name = name
         self.noise = noise                # noise variant: outputs the power of every noise source, nothing else
@@ -408,7 +408,14 @@ class _Compiler:
         # one more terminal "I(a,b)" after the internal nodes; the circuit allocates it among the branch currents.
         #   row of the unknown:  'V':  V(a) - V(b) - sum(contributions) = 0      'P':  I_br - sum(contributions) = 0
         #   KCL:                 +I_br leaves a, enters b (src/simulate_ir.jl:112-120)
+        # `probe_branches`: branches whose current the caller wants as an observable (sys.<inst>.var"I(p, n)",
+        # src/vasim.jl:786-808) -- they become 'P' branches, i.e. unknowns the solution carries
         self.branch_kind: Dict[Tuple[str, str], str] = {}
+        for a, b in probe_branches:
+            if a not in self.tindex and a != "0" or b not in self.tindex and b != "0":
+                raise VACompileError(f"module {mod.name} has no branch ({a}, {b})")
+            if (b, a) not in self.branch_kind:
+                self.branch_kind[(a, b)] = "P"
         self._scan_branches(list(mod.analog))
         self.branch_terms: List[int] = []
         for (a, b) in self.branch_kind:
@@ -2029,17 +2036,20 @@ class _Compiler:
         return "\n".join(L) + "\n"
 
 
-def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None) -> CompiledModel:
-    full = _Compiler(mod, name or mod.name, const_params, runtime_params)
+def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None,
+                   probe_branches=()) -> CompiledModel:
+    full = _Compiler(mod, name or mod.name, const_params, runtime_params, probe_branches=probe_branches)
     cm = full.compile()
     try:
-        vc = _Compiler(mod, name or mod.name, const_params, runtime_params, no_deriv=True, skip_funcs=full.defined_funcs)
+        vc = _Compiler(mod, name or mod.name, const_params, runtime_params, no_deriv=True, skip_funcs=full.defined_funcs,
+                       probe_branches=probe_branches)
         cv = vc.compile()
         cm.source_v, cm.ncache_v = cv.source, cv.ncache
     except VACompileError:
         pass
     if _module_has_noise(mod):
-        nc = _Compiler(mod, name or mod.name, const_params, runtime_params, noise=True, skip_funcs=full.defined_funcs)
+        nc = _Compiler(mod, name or mod.name, const_params, runtime_params, noise=True, skip_funcs=full.defined_funcs,
+                       probe_branches=probe_branches)
         cn = nc.compile()
         cm.source_n, cm.ncache_n, cm.noise_sources = cn.source, cn.ncache, list(nc.noise_sources)
     cm.gen_version = GEN_VERSION
@@ -2060,19 +2070,20 @@ def _module_has_noise(mod: Module) -> bool:
 
 def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,
                     include_paths: Sequence[str] = (), defines=None, suppress_defines=(),
-                    const_params=None, runtime_params=None) -> CompiledModel:
+                    const_params=None, runtime_params=None, probe_branches=()) -> CompiledModel:
     pp = Preprocessor(include_paths, defines, suppress_defines)
     text = pp.process_file(path)
     return compile_va_text(text, module, name, preprocessed=True, const_params=const_params,
-                           runtime_params=runtime_params)
+                           runtime_params=runtime_params, probe_branches=probe_branches)
 
 
 def compile_va_text(text: str, module: Optional[str] = None, name: Optional[str] = None,
-                    preprocessed: bool = False, defines=None, const_params=None, runtime_params=None) -> CompiledModel:
+                    preprocessed: bool = False, defines=None, const_params=None, runtime_params=None,
+                    probe_branches=()) -> CompiledModel:
     if not preprocessed:
         text = Preprocessor((), defines).process_text(text)
     mods = parse(text)
     if not mods:
         raise VACompileError("no module found")
     mod = mods[-1] if module is None else next(m for m in mods if m.name == module)
-    return compile_module(mod, name, const_params, runtime_params)
+    return compile_module(mod, name, const_params, runtime_params, probe_branches=probe_branches)

@@ -95,3 +95,20 @@ def test_verilog_a_include_dc_sweep():   # test/basic.jl:368-380 through the swe
     sols = dc_(cs)
     assert sols.status.max() == 0
     assert np.allclose(sols.array(cs.sys.v1.I), -1.0 / r, rtol=1e-12, atol=0)
+
+
+def test_va_branch_current_observable_sweep():   # test/varegress.jl through the sweep API: sys.xr.var"I(p, n)" >= 0
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    r = np.linspace(500.0, 2000.0, 32)
+    ts = np.linspace(0, 1e-5, 101)
+    for mod in ("VAR", "VAR_rev"):
+        deck = f'* varegress\n.hdl "varegress.va"\nv1 vcc 0 1\nxr vcc out {mod} r=1000\nc1 out 0 1n\n'
+        cs = CircuitSweep(deck, Sweep("xr.r", r), outputs=["out", "xr.I(p, n)"], include_dirs=[inc])
+        sols = tran_(cs, (0.0, 1e-5), saveat=ts, reltol=1e-6, skip_dc=1)          # u0 = 0: uncharged start, as the reference's test
+        assert sols.status.max() == 0
+        cur = sols.array(getattr(cs.sys.xr, "I(p, n)"))          # (32, 101)
+        out = sols.array(cs.sys.node_out)
+        assert np.all(cur >= 0.0)
+        assert np.abs(cur - (1.0 - out) / r[:, None])[:, 1:].max() < 1e-9          # (the t0 sample is the start vector)
+        assert np.abs(out - (1.0 - np.exp(-ts[None, :] / (r[:, None] * 1e-9)))).max() < 1e-4

@@ -187,3 +187,23 @@ def test_voltage_branches_and_current_probes():
     with pytest.raises(VACompileError, match="both"):
         compile_va_text("`include \"disciplines.vams\"\nmodule sw(p,n); inout p,n; electrical p,n;\nanalog begin\n"
                         "if (V(p,n) > 0) V(p,n) <+ 0; else I(p,n) <+ 0;\nend\nendmodule\n")
+
+
+def test_branch_current_observable_of_a_va_device():
+    """test/varegress.jl:20-38, :49-67: sys.R.var"I(p, n)" >= 0 along the RC charge, for the resistor written on (p,n)
+    and for the one written on the reversed pair.  Asking for `<inst>.I(p, n)` as an output makes that branch current
+    an unknown of the device (src/vasim.jl:786-808)."""
+    from cedarsim.jl_b200 import netlist
+    from oracle import orc
+    inc = os.path.join(HERE, "va")
+    ts = np.linspace(0, 1e-5, 101)
+    for mod in ("VAR", "VAR_rev"):
+        deck = f'* varegress\n.hdl "varegress.va"\nv1 vcc 0 1\nxr vcc out {mod} r=1000\nc1 out 0 1n\n'
+        fl = netlist.flatten(netlist.parse_netlist(deck, include_dirs=[inc]), host=True, outputs=["out", "xr.I(p, n)"])
+        assert fl.fc.branch_names == ["v1.i", "xr.i(p,n)"]
+        y, st, _ = orc.tran(fl.fc, 0.0, 1e-5, ts, opts=orc.default_options(skip_dc=1, reltol=1e-6))   # u0 = 0: uncharged start
+        assert st.max() == 0
+        out, cur = y[0, :, 0], y[1, :, 0]
+        assert np.all(cur >= 0.0)
+        assert np.abs(cur[1:] - (1.0 - out[1:]) / 1000.0).max() < 1e-12          # the branch equation itself
+        assert np.abs(out - (1.0 - np.exp(-ts / 1e-6))).max() < 1e-4             # RC charge
