@@ -104,7 +104,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    points = max(threads * 4, 32)
+    points = max(threads * 16, 64)   # ~10 s of CPU work per step on the box's host cores
     for _ in range(args.warmup):
         cpu_arm(points, threads)
     t = time.perf_counter()
@@ -279,7 +279,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             threads = os.cpu_count() or 1
-            pts = max(threads * 4, 32)
+            pts = max(threads * 16, 64)   # a bounded sample: ~10 s of CPU work
             cel, cstats, cok = cpu_arm(pts, threads)
             cpu = {"value": pts / cel, "unit": "points/s", "cores": threads, "kind": "port",
                    "sample": f"{pts} of the {B} Monte-Carlo points, same tolerances and outputs, {cel:.1f}s",
