@@ -539,8 +539,15 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
 // The op lists are warp-uniform int4 streams read through L1; the code is a handful of small loops, so it
 // stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
 // instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
-#define LU_PTS 32
-#define LU_W 16
+#ifndef LU_PTS
+#define LU_PTS 32     // points per group (lane = point); 16: two entry-workers per warp, half the shared memory per CTA
+#endif
+#ifndef LU_W
+#define LU_W 16       // entry-workers per CTA
+#endif
+#ifndef LU_MINB
+#define LU_MINB 1
+#endif
 #define LU_GU 8
 struct LArgs {
     NArgs n;
@@ -572,7 +579,7 @@ struct LArgs {
 };
 
 template <bool SOLVE, int LU_WIN>
-__global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
+__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
     extern __shared__ double vals_[];
     __shared__ double s_red[2][LU_W][LU_PTS];
     __shared__ int s_bad[LU_W][LU_PTS];
@@ -592,13 +599,13 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, 1) k_lu(const LArgs c) {
         const int act = i0 < B ? a.active[i0] : ACT_DONE;
         on0 = SOLVE ? act == ACT_ANY : (c.only_full ? act == ACT_FULL : act != ACT_DONE);
         bal0 = __ballot_sync(0xffffffffu, on0);
-        if (lane == 0) s_cnt[w] = __popc(bal0);
+        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(bal0);
     }
     __syncthreads();
     int total = 0, before = 0;
 #pragma unroll
-    for (int q = 0; q < LU_WIN / 32; q++) { if (q < w) before += s_cnt[q]; total += s_cnt[q]; }
-    if (on0) s_list[before + __popc(bal0 & ((1u << lane) - 1u))] = (short)threadIdx.x;
+    for (int q = 0; q < LU_WIN / 32; q++) { if (q < (int)(threadIdx.x >> 5)) before += s_cnt[q]; total += s_cnt[q]; }
+    if (on0) s_list[before + __popc(bal0 & ((1u << (threadIdx.x & 31)) - 1u))] = (short)threadIdx.x;
     __syncthreads();
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
     for (int g0 = 0; g0 < total; g0 += LU_PTS) {
