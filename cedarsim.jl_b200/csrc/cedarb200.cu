@@ -56,6 +56,7 @@ struct ModelH {
     int nterm, nparam, ncache, nj;
     std::vector<int> jrow, jcol;
     int ncache_n = 0;
+    bool linear = false;                     // bias-independent Jacobian (cb_va_model.linear)
     std::vector<int> noise_pos, noise_neg;   // noise sources (terminal indices, -1 = ground)
     int nout() const { return 2 * nterm + 2 * nj; }   // I | Q | J = dI/dV + alpha dQ/dV | C = dQ/dV
 };
@@ -164,6 +165,7 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
                 if (h.noise_pos[k] < -1 || h.noise_pos[k] >= m.nterm || h.noise_neg[k] < -1 || h.noise_neg[k] >= m.nterm)
                     return fail(CB_ERR_INVALID, "noise source terminal out of range");
         }
+        h.linear = m.linear != 0;
         c->models.push_back(std::move(h));
     }
     for (int i = 0; i < f->n_va_insts; i++) {
@@ -1279,7 +1281,11 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     o.nr_reltol = opt->nr_reltol; o.nr_vabstol = opt->nr_vabstol; o.nr_iabstol = opt->nr_iabstol;
     o.dc_abstol = opt->dc_abstol;
     // the Newton voltage-step limit only exists for nonlinear (Verilog-A) devices
-    o.dv_max = c->insts.empty() ? 1e300 : opt->dv_max;
+    {   // the voltage-step limit is for nonlinear devices only
+        bool nonlinear = false;
+        for (const VaInstH& vi : c->insts) nonlinear = nonlinear || !c->models[vi.model].linear;
+        o.dv_max = nonlinear ? opt->dv_max : 1e300;
+    }
     o.dt = opt->dt; o.dt_min = opt->dt_min; o.t0 = t0; o.t1 = t1;
     o.span = t1 - t0;
     o.teps = 1e-12 * std::max(std::fabs(t1), o.span);

@@ -67,6 +67,8 @@ class cb_va_model(C.Structure):
         ("noise_neg", C.POINTER(C.c_int32)),
         ("host_setupn", C.c_void_p),
         ("host_noise", C.c_void_p),
+        ("linear", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -213,6 +215,7 @@ class VAModelShape:
     host_setupn: int = 0
     host_noise: int = 0
     branch_terms: List[int] = field(default_factory=list)   # terminals that are branch currents (V() <+ branches, I() probes)
+    linear: bool = False   # every Jacobian entry is bias-independent: no Newton step limiting on its account
 
 
 def shape_of(cm) -> VAModelShape:
@@ -221,7 +224,7 @@ def shape_of(cm) -> VAModelShape:
                         ncache_n=getattr(cm, "ncache_n", 0),
                         noise_pos=[int(s[0]) for s in getattr(cm, "noise_sources", [])],
                         noise_neg=[int(s[1]) for s in getattr(cm, "noise_sources", [])],
-                        branch_terms=list(getattr(cm, "branch_terms", [])))
+                        branch_terms=list(getattr(cm, "branch_terms", [])), linear=bool(getattr(cm, "linear", False)))
 
 
 @dataclass
@@ -424,7 +427,7 @@ class FlatCircuit:
                                     C.cast(jr, C.POINTER(C.c_int32)), C.cast(jc, C.POINTER(C.c_int32)),
                                     m.host_setup or None, m.host_eval or None, len(m.noise_pos), m.ncache_n,
                                     C.cast(npos, C.POINTER(C.c_int32)), C.cast(nneg, C.POINTER(C.c_int32)),
-                                    m.host_setupn or None, m.host_noise or None)
+                                    m.host_setupn or None, m.host_noise or None, 1 if m.linear else 0, 0)
         insts = (cb_va_inst * max(1, len(self.va_insts)))()
         for i, vi in enumerate(self.va_insts):
             shape = self.va_models[vi.model]

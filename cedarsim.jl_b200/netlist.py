@@ -302,6 +302,14 @@ def _parse_card(toks: List[str]) -> Card:
     if kind in "vi":
         nodes = [rest[0].lower(), rest[1].lower()]
         return Card(kind, name, nodes, source=_parse_source(rest[2:]))
+    if kind == "b" or (kind in "eg" and any(t.lower() in ("vol", "cur", "value") for t in rest[2:4])):
+        # behavioural source: `B1 p n v=<expr>` / `i=<expr>`, `E1 p n vol=<expr>`, `G1 p n cur=<expr>` (test/basic.jl:207-235)
+        eq = rest.index("=")
+        key = rest[eq - 1].lower()
+        expr = " ".join(rest[eq + 1:]).strip()
+        if len(expr) > 1 and expr[0] in "'{" and expr[-1] in "'}":
+            expr = expr[1:-1]
+        return Card("b", name, [rest[0].lower(), rest[1].lower()], None, {"v" if key in ("v", "vol", "value") else "i": expr})
     if kind in "eg":
         pos, kv = split_params([t for t in rest if t not in ("(", ")", ",")])
         nodes = [p.lower() for p in pos[:4]]
@@ -322,6 +330,8 @@ def parse_file(path: str) -> Netlist:
 
 
 # ---------------------------------------------------------------- flattening
+
+_VA_FUNCS = {"abs", "exp", "ln", "log", "sqrt", "pow", "min", "max", "sin", "cos", "tan", "atan", "tanh", "sinh", "cosh", "limexp"}
 
 Num = Union[float, np.ndarray]
 
@@ -483,6 +493,8 @@ class _Flattener:
                 g = inst_over.get("gain", scope.eval(card.value) if card.value is not None else 1.0)
                 (self.fc.vcvs if k == "e" else self.fc.vccs)(name, nodes[0], nodes[1], nodes[2], nodes[3],
                                                               self.value(name + ".gain", g), m=mult)
+            elif k == "b":
+                self._behavioural(name, card, nodes, scope, mult, net)
             elif k == "m":
                 self._mosfet(name, card, nodes, scope, inst_over, mult)
             elif k == "x":
@@ -538,6 +550,69 @@ class _Flattener:
             return Wave(W_PULSE, dc=dcv, v=v)
         v = [self.value(f"{name}.sin{i}", x) for i, x in enumerate(vals)]
         return Wave(W_SIN, dc=dcv, v=v)
+
+    def _behavioural(self, name: str, card: Card, nodes: List[str], scope: _Scope, mult: float, net):
+        """Behavioural source as a generated Verilog-A module: `V(p,n) <+ expr` (a voltage branch with its own current
+        unknown) or `I(p,n) <+ expr`; every net the expression probes with V(a) / V(a,b) becomes a port, every
+        netlist parameter it names a module parameter (so it can be a sweep column).  The reference lowers B / E vol= /
+        G cur= sources to closures over the same probes (src/spectre.jl:1020-1071)."""
+        import hashlib
+        kind, text = next(iter(card.params.items()))
+        ports: List[str] = []
+
+        def port(n: str) -> str:
+            n = n.strip().lower()
+            if n not in ports:
+                ports.append(n)
+            return f"c{ports.index(n)}"
+
+        def probe(m):
+            args = [a for a in m.group(1).split(",")]
+            return "V(" + ", ".join(port(a) for a in args) + ")"
+
+        body = re.sub(r"\b[vV]\s*\(([^()]*)\)", probe, text)
+        if re.search(r"\b[iI]\s*\(", body) or "$" in body:
+            raise NetlistError(f"{name}: only V() probes are supported in behavioural sources ({text!r})")
+        body = body.replace("**", "^")
+        # numbers with SPICE magnitudes -> plain literals; identifiers that are netlist parameters -> module parameters
+        from .expr import parse_number
+        pars: List[str] = []
+
+        def atom(m):
+            tok = m.group(0)
+            if re.match(r"^(\d|\.\d)", tok):
+                return repr(parse_number(tok))
+            low = tok.lower()
+            if low in ("v",) or re.match(r"^c\d+$", low) or low in _VA_FUNCS:
+                return low if low in _VA_FUNCS else tok
+            if low not in pars:
+                pars.append(low)
+            return "P_" + low
+        body = re.sub(r"(\d+\.?\d*(?:[eE][+-]?\d+)?[A-Za-z]*|\.\d+(?:[eE][+-]?\d+)?[A-Za-z]*|[A-Za-z_][A-Za-z0-9_]*)", atom, body)
+        body = body.replace("^", "**")
+        allp = ["p", "n"] + [f"c{k}" for k in range(len(ports))]
+        tag = hashlib.sha1((kind + body + repr(pars)).encode()).hexdigest()[:10]
+        mname = f"bsrc_{tag}"
+        va = ["`include \"disciplines.vams\"", f"module {mname}({', '.join(allp)});", f"    inout {', '.join(allp)};",
+              f"    electrical {', '.join(allp)};"]
+        va += [f"    parameter real P_{q} = 0.0;" for q in pars]
+        va += ["    analog begin", f"        {'V' if kind == 'v' else 'I'}(p, n) <+ {body};", "    end", "endmodule", ""]
+        os.makedirs(models.GEN_DIR, exist_ok=True)
+        path = os.path.join(models.GEN_DIR, mname + ".va")
+        if not os.path.exists(path):
+            with open(path + ".tmp", "w") as f:
+                f.write("\n".join(va))
+            os.replace(path + ".tmp", path)
+        cm = models.compiled_model(mname, path, module=mname)
+        if cm not in self.models:
+            self.models.append(cm)
+        if self.host:
+            from .va.build import build_host
+            shape = build_host(cm).shape()
+        else:
+            shape = shape_of(cm)
+        vals = {f"P_{q}": self.value(f"{name}.{q}", scope.lookup(q)) for q in pars}
+        self.fc.va_instance(name, self.fc.va_model(shape), nodes[:2] + [net(q) for q in ports], vals, m=mult)
 
     def _va_device(self, name: str, card: Card, nodes: List[str], scope: _Scope, mult: float):
         """Instance of a Verilog-A module brought in by `.hdl`: all module parameters stay run-time parameters (instance

@@ -81,7 +81,7 @@ class HostModel:
         return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
                             self.setup_addr, self.eval_addr, ncache_n=cm.ncache_n,
                             noise_pos=[int(s[0]) for s in cm.noise_sources], noise_neg=[int(s[1]) for s in cm.noise_sources],
-                            host_setupn=self.setupn_addr, host_noise=self.noise_addr, branch_terms=list(cm.branch_terms))
+                            host_setupn=self.setupn_addr, host_noise=self.noise_addr, branch_terms=list(cm.branch_terms), linear=bool(cm.linear))
 
     # convenience for tests
     def run_noise(self, params: dict, v, temp_c=27.0, gmin=1e-12):

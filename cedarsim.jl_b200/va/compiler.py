@@ -35,7 +35,7 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-GEN_VERSION = 4   # bump when the emitted code changes: models cached under _gen/ are regenerated
+GEN_VERSION = 5   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
 CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "4"))
 CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "8"))
@@ -379,6 +379,7 @@ class CompiledModel:
     ncache_n: int = 0
     noise_sources: List[Tuple[int, int, str, str]] = field(default_factory=list)
     branch_terms: List[int] = field(default_factory=list)   # terminals that are branch CURRENTS (voltage branches, I() probes)
+    linear: bool = False   # every Jacobian entry is independent of the terminal values (no Newton step limiting needed)
     gen_version: int = 0   # GEN_VERSION of the generator that wrote `source` (cached models of another version are rebuilt)
 
     @property
@@ -1807,6 +1808,7 @@ class _Compiler:
                 jrow.append(kk)
                 jcol.append(ll)
         src = self._render(out_lines)
+        linear = self._jacobian_is_static(out_lines)
         ptypes = [p.type for p in mod.params]
         defaults: Dict[str, float] = {}
         ce = _ConstEval(mod.functions)
@@ -1820,7 +1822,45 @@ class _Compiler:
                 pass
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
                              ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
-                             param_defaults=defaults, branch_terms=list(self.branch_terms))
+                             param_defaults=defaults, branch_terms=list(self.branch_terms), linear=linear)
+
+    def _jacobian_is_static(self, out_lines: List[str]) -> bool:
+        """True when no derivative output depends on a terminal value: taint every eval-stream name assigned from an
+        expression that reads VT(...) or a tainted name (one forward pass over the straight-line code; conditionals only
+        add assignments), then look at the derivative arguments of OUT_J."""
+        ident = re.compile(r"[A-Za-z_][A-Za-z0-9_]*")
+        tainted: Set[str] = set()
+        asg = re.compile(r"^\s*(?:const\s+)?(?:double|int)?\s*([A-Za-z_][A-Za-z0-9_]*)\s*(?:=|\+=|-=|\*=)\s*(.*);\s*$")
+        cond = re.compile(r"^\s*(?:\}\s*else\s+)?if\s*\((.*)\)\s*\{\s*$")
+        depth_taint: List[bool] = []      # inside a conditional whose condition is bias-dependent, every assignment is
+        for l in self.E:
+            m = cond.match(l)
+            if m:
+                t = "VT(" in m.group(1) or any(n in tainted for n in ident.findall(m.group(1)))
+                if l.lstrip().startswith("}"):
+                    if depth_taint:
+                        depth_taint[-1] = depth_taint[-1] or t
+                else:
+                    depth_taint.append(t)
+                continue
+            if l.strip().startswith("} else"):
+                continue
+            if l.strip() == "}":
+                if depth_taint:
+                    depth_taint.pop()
+                continue
+            m = asg.match(l)
+            if not m:
+                continue
+            name, rhs = m.group(1), m.group(2)
+            if any(depth_taint) or "VT(" in rhs or any(n in tainted for n in ident.findall(rhs)):
+                tainted.add(name)
+        for l in out_lines:
+            if l.startswith("OUT_J("):
+                args = l[len("OUT_J("):].rsplit(")", 1)[0].split(",", 3)[3]
+                if any(n in tainted for n in ident.findall(args)):
+                    return False
+        return True
 
     def _stage_cache(self):
         """Re-lays the cache out as a *stream* in the order the eval function consumes it.

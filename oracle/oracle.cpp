@@ -41,6 +41,13 @@
 
 namespace {
 
+// the Newton voltage-step limit is for nonlinear devices only (cb_va_model.linear)
+static bool has_nonlinear(const cb_flat_circuit* fc) {
+    for (int i = 0; i < fc->n_va_insts; i++)
+        if (!fc->va_models[fc->va_insts[i].model].linear) return true;
+    return false;
+}
+
 typedef void (*va_setup_fn)(const double* par, const uint8_t* given, double temp_c, double gmin,
                             double* cache);
 typedef void (*va_eval_fn)(const double* cache, const double* v, double* I, double* Q, double* G,
@@ -336,7 +343,7 @@ struct Solver {
         double nrm_prev = 0.0;
         // voltage-step limit: only nonlinear (Verilog-A) devices need it; a purely linear circuit
         // converges in one full step whatever its voltage scale
-        const double lim = in.fc->n_va_insts > 0 ? opt->dv_max : 1e300;
+        const double lim = has_nonlinear(in.fc) ? opt->dv_max : 1e300;
         for (int it = 0; it < maxit; it++) {
             eval_system(in, vc, x.data(), t, dcop, s);
             cnt.newton++;
@@ -506,7 +513,7 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
         for (int i = 0; i < N; i++) {
             double d = xp[i] - xn[i];
             double lim = np >= 1 ? std::fabs(xn[i] - x1[i]) * (h / h1) : 0.0;
-            if (i < S.NV) lim = std::min(lim, fc->n_va_insts > 0 ? opt->dv_max : 1e300);
+            if (i < S.NV) lim = std::min(lim, has_nonlinear(fc) ? opt->dv_max : 1e300);
             x[i] = xn[i] + std::max(-lim, std::min(lim, d));
         }
         const bool rate = opt->nr_rate_test != 0;

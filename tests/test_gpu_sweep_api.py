@@ -112,3 +112,15 @@ def test_va_branch_current_observable_sweep():   # test/varegress.jl through the
         assert np.all(cur >= 0.0)
         assert np.abs(cur - (1.0 - out) / r[:, None])[:, 1:].max() < 1e-9          # (the t0 sample is the start vector)
         assert np.abs(out - (1.0 - np.exp(-ts[None, :] / (r[:, None] * 1e-9)))).max() < 1e-4
+
+
+def test_behavioural_sources_dc_sweep():   # test/basic.jl:207-235 on the GPU, with the controlling gain as a sweep column
+    deck = ("* Simple SPICE sources\n.param gain=2\nV1 0 1 1\nR1 1 0 1k\nB5 0 5 v='V(1)*gain'\nR5 5 0 1k\n"
+            "E8 0 8 vol='V(0, 5)*gain'\nR8 8 0 r=1k\nG9 0 9 cur='V(0, 5)*gain'\nR9 9 0 r=1k\n")
+    g = np.linspace(0.5, 4.0, 64)
+    cs = CircuitSweep(deck, Sweep("gain", g))
+    sols = dc_(cs)
+    assert sols.status.max() == 0
+    assert np.allclose(sols.array(cs.sys.node_5), g, rtol=1e-12)                    # 2.0 at gain = 2
+    assert np.allclose(sols.array(cs.sys.node_8), g * g, rtol=1e-12)                # 4.0
+    assert np.allclose(sols.array(cs.sys.node_9), -1000.0 * g * g, rtol=1e-12)      # -4000.0: no step limit for linear devices

@@ -266,3 +266,37 @@ def test_verilog_a_include():   # test/basic.jl:368-380: `.hdl` + an X instance 
     assert st.max() == 0 and np.allclose(xf[fl.fc.unknown("v1.i")], [-1e-3, -5e-4, -2.5e-4], rtol=1e-14, atol=0)
     with pytest.raises(netlist.NetlistError, match="no parameter"):
         netlist.flatten(netlist.parse_netlist(VA_INCLUDE_DECK.replace("r=2k", "rr=2k"), include_dirs=[inc]), host=True)
+
+
+def test_simple_spice_sources_behavioural():   # test/basic.jl:207-235, verbatim: B (v=), E (gain and vol=), G (gain and cur=)
+    text = """* Simple SPICE sources
+V1 0 1 1
+R1 1 0 1k
+
+B5 0 5 v=V(1)*2
+R5 5 0 1k
+
+E6 0 6 0 5 2
+R6 6 0 r=1k
+
+E8 0 8 vol=V(0, 5)*2
+R8 8 0 r=1k
+
+G7 0 7 0 5 2
+R7 7 0 r=1k
+
+G9 0 9 cur=V(0, 5)*2
+R9 9 0 r=1k
+"""
+    fl = netlist.flatten(netlist.parse_netlist(text), host=True)
+    assert all(m.linear for m in fl.models)          # behavioural sources here are linear: no Newton step limit, -4000 V is one step
+    x, xf, st, stats = orc.dc(fl.fc, None)
+    assert st.max() == 0
+    v = lambda n: xf[fl.fc.unknown(n), 0]
+    assert abs(v("5") - 2.0) < DEFTOL and abs(v("6") - 4.0) < DEFTOL and abs(v("8") - 4.0) < DEFTOL
+    assert abs(v("7") + 4000.0) < 1e-6 and abs(v("9") + 4000.0) < 1e-6
+    # a netlist parameter inside the expression is a parameter of the generated module: it can be a sweep column
+    deck = "* b\n.param gain=2\nV1 1 0 1\nR1 1 0 1k\nB5 5 0 v='V(1)*gain + 1m'\nR5 5 0 1k\n"
+    fl = netlist.flatten(netlist.parse_netlist(deck), {"gain": np.array([1.0, 2.0, 3.0])}, host=True)
+    x, xf, st, _ = orc.dc(fl.fc, fl.params)
+    assert st.max() == 0 and np.allclose(xf[fl.fc.unknown("5")], [1.001, 2.001, 3.001], rtol=1e-14, atol=0)
