@@ -458,6 +458,8 @@ class CircuitSweep:
         self.circuit = circuit
         self.columns = self.iterator.columns()
         B = len(self.iterator)
+        if B == 0:   # the reference compiles from `first(iterator)` (src/sweeps.jl:414-417) and fails on an empty one as well
+            raise ValueError("empty sweep: a CircuitSweep needs at least one point")
         if isinstance(circuit, str):
             from .netlist import parse_netlist
             if lang == "spectre":

@@ -194,3 +194,19 @@ def test_verilog_a_voltage_branches():
     assert_tran_close(yg, yo, rtol=1e-6, atol=1e-9)
     k = fl.fc.unknown("x1.i(p,n)")
     assert np.all(np.diff(yg[k], axis=0) >= -1e-12) and np.all(yg[k, -1] < 0.01)      # the current rises towards V / R
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 65, 129, 257])
+def test_ragged_batch_sizes(host_bsimcmg, B):
+    """Batch sizes that are not multiples of the warp, of the k_lu window (64) or of the eval CTA (128): tail lanes idle
+    without touching memory, and the points that exist match the oracle at the fixed-step parity tolerance."""
+    fc, ms = circuits.inverter(host=host_bsimcmg, tscale=0.01)
+    P = np.zeros((3, B))
+    P[fc.param_names.index("vvdd.dc")] = np.linspace(0.6, 0.8, B)
+    P[fc.param_names.index("xneg.nfin")] = 3.0
+    P[fc.param_names.index("xneg.l")] = np.linspace(21e-9, 30e-9, B)
+    ts = np.linspace(0, 1e-9, 21)
+    (yg, sg, _), (yo, so, _) = run_tran_both(fc, ms, P, 0.0, 1e-9, ts, fixed_step=1, dt=2e-12)
+    assert yg.shape == yo.shape == (len(fc.outputs), 21, B)
+    assert sg.max() == 0 and so.max() == 0
+    assert_tran_close(yg, yo)

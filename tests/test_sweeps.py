@@ -136,3 +136,9 @@ v1 vss 0 'v_in'
     rows = open(f).read().splitlines()
     assert rows[0] == "t,in,out" and len(rows) == 502
     assert abs(float(rows[-1].split(",")[2]) - y[cs.flat.fc.outputs.index(cs.flat.fc.unknown("out")), -1, 1]) < 1e-15
+
+
+def test_empty_sweep_is_refused():   # src/sweeps.jl:414-417: the circuit is compiled from the first sweep point
+    from cedarsim.jl_b200.sweeps import CircuitSweep
+    with pytest.raises(ValueError, match="empty sweep"):
+        CircuitSweep("* r\nv1 a 0 1\nr1 a 0 1k\n", Sweep("r1.r", np.array([])))
