@@ -249,6 +249,7 @@ class FlatCircuit:
     _node_index: Dict[str, int] = field(default_factory=dict)
     _finalized: bool = False
     va_branches: List[str] = field(default_factory=list)   # names of branch-current unknowns of Verilog-A instances
+    aliases: Dict[str, str] = field(default_factory=dict)   # subcircuit port 'x1.pos' -> the parent's net ('vcc' or '0')
 
     # ---- construction helpers -------------------------------------------------
     def node(self, name: str) -> int:
@@ -364,8 +365,15 @@ class FlatCircuit:
         """Index of a node voltage ('q', 'node_q') or branch current ('v1.i', 'v1.I')."""
         self.finalize()
         key = name.lower().replace(" ", "")   # `x1.I(p, n)` as the reference prints it == `x1.i(p,n)`
-        if key.startswith("node_"):
-            key = key[5:]
+        head, _, last = key.rpartition(".")
+        if last.startswith("node_"):             # sys.node_q, sys.x1.node_pos (src/spectre.jl:736-749)
+            key = (head + "." if head else "") + last[5:]
+        seen = set()
+        while key in self.aliases and key not in seen:   # a subcircuit port is the parent's net (test/alias.jl)
+            seen.add(key)
+            key = self.aliases[key]
+        if key in ("0", "gnd", "gnd!"):
+            raise KeyError(f"{name!r} is the ground net (0 V, not an unknown)")
         if key in self._node_index:
             return self._node_index[key]
         if key in self.branch_names:

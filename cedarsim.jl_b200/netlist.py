@@ -446,6 +446,11 @@ class _Flattener:
                 scope.values[k] = np.where(np.isnan(v), default, v)
 
     def instantiate(self, sub: Subckt, scope: _Scope, prefix: str, portmap: Dict[str, str], mult_ctx: float):
+        # a subcircuit's ports are aliases of the parent's nets: sys.x1.node_pos == sys.node_vcc (net_alias,
+        # src/spectre.jl:911-913,951; test/alias.jl:21-33)
+        for port, parent in portmap.items():
+            self.fc.aliases[(prefix + port).lower()] = parent.lower()
+
         def net(n: str) -> str:
             if n in ("0", "gnd", "gnd!"):
                 return "0"

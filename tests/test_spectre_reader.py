@@ -97,3 +97,24 @@ VD D 0 AC 1 SIN (0.5 0.01 1e7)
     assert a.fc.node_names == b.fc.node_names and a.fc.branch_names == b.fc.branch_names
     assert len(a.fc.va_insts) == 2 and a.fc.param_names == b.fc.param_names
     assert [(w.kind, w.ac) for w in a.fc.waves] == [(w.kind, w.ac) for w in b.fc.waves]
+
+
+def test_subcircuit_port_aliases():   # test/alias.jl:5-33: sys.x1.node_pos == sys.node_vcc, sys.x1.node_neg == sys.node_0
+    ckt = """
+subckt myres pos neg
+    parameters r=1k
+    r1 (pos neg) resistor r=r
+ends myres
+
+x1 (vcc 0) myres r=2k
+v1 (vcc 0) vsource dc=1
+"""
+    fl = netlist.flatten(spectre.parse_spectre(ckt))
+    fc = fl.fc
+    assert fc.aliases == {"x1.pos": "vcc", "x1.neg": "0"}                       # the reference's aliasmap
+    assert fc.unknown("x1.node_pos") == fc.unknown("node_vcc")
+    with pytest.raises(KeyError, match="ground"):
+        fc.unknown("x1.node_neg")
+    # through the result objects: a grounded port reads as 0 V
+    from cedarsim.jl_b200.sweeps import _Observable
+    assert _Observable(fc, "x1.node_neg").terms == [] and _Observable(fc, "x1.node_pos").terms == [(1.0, fc.unknown("vcc"))]
