@@ -42,7 +42,7 @@ def parse_number(tok: str) -> float:
 
 
 _TOK = re.compile(r"\s*(?:(\d+\.?\d*(?:[eE][+-]?\d+)?[A-Za-z_]*|\.\d+(?:[eE][+-]?\d+)?[A-Za-z_]*)"
-                  r"|([A-Za-z_$][A-Za-z0-9_.$]*)|(\*\*|==|!=|<=|>=|&&|\|\||[-+*/^(),<>?:!]))")
+                  r"|([A-Za-z_$][A-Za-z0-9_.$]*)|(\*\*|==|!=|<=|>=|&&|\|\||~\^|\^~|<<|>>|[-+*/^(),<>?:!&|~]))")
 
 _FUNCS: Dict[str, Callable] = {
     "sqrt": np.sqrt, "exp": np.exp, "ln": np.log, "log": np.log, "log10": np.log10, "abs": np.abs,
@@ -53,7 +53,9 @@ _FUNCS: Dict[str, Callable] = {
     "agauss": lambda nom, avar, sigma: nom,   # rng disabled in the reference (src/spectre_env.jl:178-187)
     "gauss": lambda nom, rvar, sigma: nom,
 }
-_CONSTS = {"pi": math.pi, "e": math.e, "true": 1.0, "false": 0.0}
+_CONSTS = {"pi": math.pi, "e": math.e, "true": 1.0, "false": 0.0,
+           "m_1_pi": 1 / math.pi,   # the one Spectre constant the reference defines (src/spectre_env.jl:142)
+           "m_pi": math.pi, "m_e": math.e, "m_two_pi": 2 * math.pi, "m_sqrt2": math.sqrt(2.0)}
 
 
 def tokenize(text: str):
@@ -97,7 +99,9 @@ class _P:
             return ("cond", c, a, b)
         return c
 
-    LEVELS = [("||",), ("&&",), ("==", "!="), ("<", "<=", ">", ">="), ("+", "-"), ("*", "/"), ]
+    # C-like precedence; the bitwise operators are those of Spectre expressions (test/spectre_expr.jl:11: `1&2~^3`)
+    LEVELS = [("||",), ("&&",), ("|",), ("~^", "^~"), ("&",), ("==", "!="), ("<", "<=", ">", ">="), ("<<", ">>"),
+              ("+", "-"), ("*", "/"), ]
 
     def binary(self, lvl):
         if lvl == len(self.LEVELS):
@@ -119,6 +123,9 @@ class _P:
         if tok == ("op", "!"):
             self.eat()
             return ("not", self.unary())
+        if tok == ("op", "~"):
+            self.eat()
+            return ("inv", self.unary())
         return self.power()
 
     def power(self):
@@ -203,9 +210,17 @@ def evaluate(e, env: Mapping[str, Number]) -> Number:
     if k == "not":
         v = evaluate(e[1], env)
         return np.where(v != 0, 0.0, 1.0) if isinstance(v, np.ndarray) else float(not v)
+    if k == "inv":
+        v = evaluate(e[1], env)
+        return (~np.asarray(v).astype(np.int64)).astype(float) if isinstance(v, np.ndarray) else float(~int(v))
     if k == "bin":
         a, b = evaluate(e[2], env), evaluate(e[3], env)
         op = e[1]
+        if op in ("&", "|", "~^", "^~", "<<", ">>"):   # integer operators
+            ia, ib = np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64)
+            r = {"&": lambda: ia & ib, "|": lambda: ia | ib, "~^": lambda: ~(ia ^ ib), "^~": lambda: ~(ia ^ ib),
+                 "<<": lambda: ia << ib, ">>": lambda: ia >> ib}[op]()
+            return r.astype(float) if r.ndim > 0 else float(r)
         if op == "+":
             return a + b
         if op == "-":

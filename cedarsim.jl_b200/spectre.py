@@ -72,6 +72,19 @@ def _kv(toks: List[str]):
     return pos, kv
 
 
+_ASSIGN = re.compile(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?<![=!<>])=(?!=)")
+
+
+def _assignments(text: str) -> Dict[str, str]:
+    """`a=1 b = x*2 c = p ? 1 : 2` -> {a: '1', b: 'x*2', c: 'p ? 1 : 2'}: a value runs up to the next `name =`"""
+    ms = list(_ASSIGN.finditer(text))
+    out: Dict[str, str] = {}
+    for k, m in enumerate(ms):
+        end = ms[k + 1].start() if k + 1 < len(ms) else len(text)
+        out[m.group(1).lower()] = text[m.end():end].strip()
+    return out
+
+
 def _source(kv: Dict[str, str]) -> dict:
     """vsource / isource parameters -> the source dict of the SPICE reader (dc / ac / tran)."""
     src = {"dc": kv.get("dc"), "ac": kv.get("mag"), "tran": None}
@@ -108,7 +121,7 @@ def parse_spectre(text: str, path: Optional[str] = None, include_dirs: Optional[
                 raise NetlistError("`simulator lang=spice` sections are outside the Spectre subset; use the SPICE reader")
             continue
         if head == "parameters":
-            _, kv = _kv(toks[1:])
+            kv = _assignments(line[len(toks[0]):])
             (cur.local_params if cur is not nl.top else cur.params).update(kv)
             continue
         if head in ("subckt", "inline"):
@@ -147,6 +160,9 @@ def parse_spectre(text: str, path: Optional[str] = None, include_dirs: Optional[
         else:
             pos, kv = _kv(rest)
             nodes, master = pos[:-1], pos[-1] if pos else ""
+        if master:   # values may be whole expressions (`r=(p1+p2)/p3`): re-read the assignments from the raw text
+            tail = line[line.index(master, len(toks[0])) + len(master):]
+            kv = _assignments(tail) or kv
         nodes = [n.lower() for n in nodes]
         m = master.lower()
         if m in _PRIMS:

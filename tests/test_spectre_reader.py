@@ -118,3 +118,26 @@ v1 (vcc 0) vsource dc=1
     # through the result objects: a grounded port reads as 0 V
     from cedarsim.jl_b200.sweeps import _Observable
     assert _Observable(fc, "x1.node_neg").terms == [] and _Observable(fc, "x1.node_pos").terms == [(1.0, fc.unknown("vcc"))]
+
+
+def test_spectre_parameter_expressions():   # test/spectre_expr.jl:10-43
+    code = """
+parameters p1=23pf p2=.3 p3 = 1&2~^3 p4 = true && false || true p5 = M_1_PI * 3.0
+r1 (1 0) resistor r=p1      // another simple expression // fdsfdsf
+r2 (1 0) resistor r=p2*p2   // a binary multiply expression
+r3 (1 0) resistor r=(p1+p2)/p3      // a more complex expression
+r4 (1 0) resistor r=sqrt(p1+p2)     // an algebraic function call
+r5 (1 0) resistor r=3+atan(p1/p2) //a trigonometric function call
+r6 (1 0) resistor r=((p1<1) ? p4+1 : p3)  // the ternary operator
+"""
+    import math
+    nl = spectre.parse_spectre(code)
+    fl = netlist.flatten(nl)
+    val = {d.name: d.value for d in fl.fc.devices}
+    p1, p2, p3, p4, p5 = 23e-12, 0.3, float(~((1 & 2) ^ 3)), 1.0, 3.0 / math.pi
+    from cedarsim.jl_b200.expr import evaluate, parse_expr
+    got = {k: evaluate(parse_expr(v), {}) for k, v in nl.top.params.items()}
+    assert abs(got["p1"] - p1) < 1e-26 and got["p2"] == p2 and got["p3"] == p3 and got["p4"] == p4 and got["p5"] == p5
+    assert val["r1"] == pytest.approx(p1) and val["r2"] == pytest.approx(p2 * p2) and val["r3"] == pytest.approx((p1 + p2) / p3)
+    assert val["r4"] == pytest.approx(math.sqrt(p1 + p2)) and val["r5"] == pytest.approx(3 + math.atan(p1 / p2))
+    assert val["r6"] == pytest.approx(p4 + 1)
