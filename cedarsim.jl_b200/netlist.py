@@ -351,6 +351,10 @@ class _Scope:
             return self.values[name]
         if name in self.exprs:
             if name in self._busy:
+                # `.subckt inner a b foo=foo+2000`: inside its own default a name means the enclosing scope's value
+                # (dynamic scoping, src/spectre.jl:494-512; test/params.jl:58-99)
+                if self.parent is not None:
+                    return self.parent.lookup(name)
                 raise NetlistError(f"circular parameter definition for {name!r}")
             self._busy.add(name)
             v = self.eval(self.exprs[name])

@@ -300,3 +300,28 @@ R9 9 0 r=1k
     fl = netlist.flatten(netlist.parse_netlist(deck), {"gain": np.array([1.0, 2.0, 3.0])}, host=True)
     x, xf, st, _ = orc.dc(fl.fc, fl.params)
     assert st.max() == 0 and np.allclose(xf[fl.fc.unknown("5")], [1.001, 2.001, 3.001], rtol=1e-14, atol=0)
+
+
+def test_subcircuit_parameters_dynamic_scope():   # test/params.jl:58-99: nested subcircuits, `foo=foo+2000`, three overrides
+    text = """* Subcircuit parameters
+.subckt inner a b foo=foo+2000
+R1 a b r= 'foo'
+.ends
+
+.subckt outer a b
+x1 a b inner
+.ends
+
+.param inner  =1
+.param foo =  1
+i1 vcc 0 'foo'
+l1 vcc out 1m
+x1 out 0 outer
+"""
+    def r1_v(sweep):
+        fc, xf = solve_dc(text, sweep)
+        return xf[fc.unknown("out"), 0]          # sys.x1.x1.r1.V = V(out) - V(0); the inductor is a short at DC
+    assert abs(r1_v({"x1.x1.foo": np.array([2.0])}) + 2.0) < DEFTOL            # ParamSim(circuit; x1=(x1=(foo=2.0,),))
+    assert abs(r1_v({"foo": np.array([2.0])}) + 4004.0) < 1e-6                 # ParamSim(circuit; foo=2.0)
+    assert abs(r1_v({"x1.x1.r1.r": np.array([100.0])}) + 100.0) < DEFTOL       # ParamSim(circuit; x1=(x1=(r1=(r=100.0,),),))
+    assert abs(r1_v(None) + 2001.0) < 1e-6                                     # defaults: foo = 1 -> 2001 Ohm, 1 A
