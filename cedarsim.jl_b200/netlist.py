@@ -423,6 +423,14 @@ class _Flattener:
         top_over = self.overrides("", list(nl.top.params))
         top = _Scope(nl.top.params, None, top_over)
         self._fill_defaults(top, nl.top.params, top_over)
+        # `temper` in expressions = the simulation temperature in Celsius: a swept `temp`, else `.option temp=` / `.temp`,
+        # else 27 (src/spectre_env.jl temper, src/simulate_ir.jl:12-20; test/basic.jl:469-517)
+        if "temp" in self.sweep:
+            top.values["temper"] = self.sweep["temp"]
+        elif "temp" in {k.lower() for k in nl.options}:
+            top.values["temper"] = float(parse_number(str({k.lower(): v for k, v in nl.options.items()}["temp"])))
+        else:
+            top.values["temper"] = 27.0
         self.instantiate(nl.top, top, prefix="", portmap={}, mult_ctx=1.0)
         opts: Dict[str, Num] = {}
         for k, v in nl.options.items():
@@ -513,7 +521,10 @@ class _Flattener:
                     continue
                 if child is None:
                     raise NetlistError(f"unknown subcircuit {card.model!r} for {name}")
-                given = {kk: scope.eval(vv) for kk, vv in card.params.items() if kk != "m"}
+                # instance parameters may refer to one another (`x1 ... w=4 nrd='w/2'`, test/basic.jl:519-536) and to
+                # the caller's scope; a name inside its own value means the caller's (`foo=foo+1`)
+                inst_scope = _Scope({kk: vv for kk, vv in card.params.items() if kk != "m"}, scope, {})
+                given = {kk: inst_scope.lookup(kk) for kk in card.params if kk != "m"}
                 given.update(self.overrides(name + ".", list(child.params) + list(child.local_params)))
                 exprs = dict(child.params)
                 exprs.update(child.local_params)

@@ -325,3 +325,24 @@ x1 out 0 outer
     assert abs(r1_v({"foo": np.array([2.0])}) + 4004.0) < 1e-6                 # ParamSim(circuit; foo=2.0)
     assert abs(r1_v({"x1.x1.r1.r": np.array([100.0])}) + 100.0) < DEFTOL       # ParamSim(circuit; x1=(x1=(r1=(r=100.0,),),))
     assert abs(r1_v(None) + 2001.0) < 1e-6                                     # defaults: foo = 1 -> 2001 Ohm, 1 A
+
+
+def test_temper_in_parameters():   # test/basic.jl:469-517: .option temp / .temp / ParamSim(temp=20) / default 27
+    body = ".param foo = temper\ni1 vcc 0 'foo'\nr1 vcc 0 1\n"
+    v = lambda text, sweep=None: (lambda r: r[1][r[0].unknown("vcc"), 0])(solve_dc(text, sweep))
+    assert abs(v("* param temp\n.option temp=10\n" + body) + 10.0) < DEFTOL
+    assert abs(v("* .temp\n.temp 10\n" + body) + 10.0) < DEFTOL
+    assert abs(v("* .temp\n.temp 10\n" + body, {"temp": np.array([20.0])}) + 20.0) < DEFTOL      # overriding the temperature
+    assert abs(v("* temper\n" + body) + 27.0) < DEFTOL
+
+
+def test_instance_parameters_refer_to_other_parameters():   # test/basic.jl:519-536: x1 ... w=4 nrd='w/2' -> I(r1) = 1/2
+    text = """* Parameter scoping test
+.subckt subcircuit1 vss gnd w=2 rsh=1 nrd=1
+r1 vss gnd 'rsh*nrd'
+.ends
+x1 vss 0 subcircuit1 w=4 nrd='w/2'
+v1 vss 0 1
+"""
+    fc, xf = solve_dc(text)
+    assert abs(-xf[fc.unknown("v1.i"), 0] - 0.5) < DEFTOL
