@@ -300,6 +300,14 @@ R9 9 0 r=1k
     fl = netlist.flatten(netlist.parse_netlist(deck), {"gain": np.array([1.0, 2.0, 3.0])}, host=True)
     x, xf, st, _ = orc.dc(fl.fc, fl.params)
     assert st.max() == 0 and np.allclose(xf[fl.fc.unknown("5")], [1.001, 2.001, 3.001], rtol=1e-14, atol=0)
+    # nonlinear expressions (functions, **, two-node probes), a current-output source fed by another one
+    deck = ("* b\n.param k=3\nV1 1 0 2\nR1 1 0 1k\nB5 5 0 v='V(1)**2 + exp(-V(1,0))*k + max(V(1), 0.5) + 1e-3'\nR5 5 0 1k\n"
+            "B6 6 0 i='V(5)/1k'\nR6 6 0 2k\n")
+    fl = netlist.flatten(netlist.parse_netlist(deck), host=True)
+    assert [m.linear for m in fl.models] == [False, True]
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    want5 = 4 + np.exp(-2.0) * 3 + 2 + 1e-3
+    assert st.max() == 0 and abs(xf[fl.fc.unknown("5"), 0] - want5) < 1e-9 and abs(xf[fl.fc.unknown("6"), 0] + 2 * want5) < 1e-9
 
 
 def test_subcircuit_parameters_dynamic_scope():   # test/params.jl:58-99: nested subcircuits, `foo=foo+2000`, three overrides
