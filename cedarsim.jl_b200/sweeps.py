@@ -443,6 +443,30 @@ class SweepSolution:
                 f.write(",".join(repr(float(c[k])) for _, c in cols) + "\n")
         return file
 
+    def plot_spec(self, index=0, name_map: Optional[Dict[str, str]] = None, title: Optional[str] = None) -> dict:
+        """PlotlyLight.Plot(sol; name_map, title) of one sweep point (ext/CedarSimPlotlyLightExt.jl:11-35): one
+        "scatter" / "lines" trace per entry of `name_map`, keys in sorted order, x = sol.t."""
+        if self.t is None:
+            raise TypeError("plot_spec needs a transient solution")
+        name_map = name_map or self.default_name_map()
+        pt = self[index]
+        data = [{"x": [float(v) for v in self.t], "y": [float(v) for v in pt[ref]], "type": "scatter", "mode": "lines",
+                 "name": name_map[ref]} for ref in sorted(name_map)]
+        layout = {"template": "plotly"}
+        if title is not None:
+            layout["title"] = title
+        return {"data": data, "layout": layout}
+
+    def save_html(self, file: str, index=0, **kw) -> str:
+        """Cobweb.save(sol, filename) (ext/CedarSimPlotlyLightExt.jl:37-46): a self-contained page with the plot."""
+        import json
+        spec = json.dumps(self.plot_spec(index, **kw))
+        with open(file, "w") as f:
+            f.write("<!DOCTYPE html><html><head><meta charset=\"utf-8\"><script src=\"https://cdn.plot.ly/plotly-latest.min.js\">"
+                    "</script></head><body><div id=\"plot\"></div><script>const s = " + spec +
+                    "; Plotly.newPlot(\"plot\", s.data, s.layout);</script></body></html>\n")
+        return file
+
     @property
     def retcodes(self) -> np.ndarray:
         return self.status.reshape(self.shape, order="F")

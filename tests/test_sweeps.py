@@ -136,6 +136,12 @@ v1 vss 0 'v_in'
     rows = open(f).read().splitlines()
     assert rows[0] == "t,in,out" and len(rows) == 502
     assert abs(float(rows[-1].split(",")[2]) - y[cs.flat.fc.outputs.index(cs.flat.fc.unknown("out")), -1, 1]) < 1e-15
+    # the Plotly extension's figure (ext/CedarSimPlotlyLightExt.jl:11-46): one line trace per top-level net, sorted keys
+    spec = sols.plot_spec(index=1, title="rc")
+    assert [tr["name"] for tr in spec["data"]] == ["in", "out"] and spec["layout"]["title"] == "rc"
+    assert all(tr["type"] == "scatter" and tr["mode"] == "lines" and len(tr["x"]) == len(tr["y"]) == 501 for tr in spec["data"])
+    page = open(sols.save_html(str(tmp_path / "rc.html"), index=1)).read()
+    assert "Plotly.newPlot" in page and '"name": "out"' in page
 
 
 def test_empty_sweep_is_refused():   # src/sweeps.jl:414-417: the circuit is compiled from the first sweep point
