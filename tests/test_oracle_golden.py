@@ -354,3 +354,12 @@ v1 vss 0 1
 """
     fc, xf = solve_dc(text)
     assert abs(-xf[fc.unknown("v1.i"), 0] - 0.5) < DEFTOL
+
+
+def test_ddx_known_answer():   # test/ddx.jl:9-21: sol[sys.V1.I][end] == -5*2*2*3
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = '* ddx\n.hdl "ddx_vcr.va"\nv1 vcc 0 5\nv2 vg 0 3\nxr vcc vg 0 ddx_vcr r=2\n'
+    fl = netlist.flatten(netlist.parse_netlist(deck, include_dirs=[inc]), host=True)
+    x, xf, st, _ = orc.dc(fl.fc, None)
+    assert st.max() == 0 and xf[fl.fc.unknown("v1.i"), 0] == -5.0 * 2 * 2 * 3
