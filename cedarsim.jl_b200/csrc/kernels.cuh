@@ -548,7 +548,9 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
 #ifndef LU_MINB
 #define LU_MINB 1
 #endif
-#define LU_GU 8
+#ifndef LU_GU
+#define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
+#endif
 struct LArgs {
     NArgs n;
     const int4* ops;          // (l, u, dst, pivot diag) positions into vals
