@@ -482,6 +482,7 @@ class CircuitSweep:
         self.iterator = sweepify(iterator)
         self.shape = self.iterator.shape
         self.circuit = circuit
+        self._ctor = dict(outputs=outputs, host=host, include_dirs=include_dirs, lang=lang)
         self.columns = self.iterator.columns()
         B = len(self.iterator)
         if B == 0:   # the reference compiles from `first(iterator)` (src/sweeps.jl:414-417) and fails on an empty one as well
@@ -672,7 +673,130 @@ def _merge_stats(stats: List[dict]) -> dict:
     return out
 
 
+# ---- forward parameter sensitivities, batched (reference test/sensitivity.jl:31-41, :58-67:
+# ODEForwardSensitivityProblem over the circuit's parameters -> one d(solution)/d(parameter) per parameter).
+# The reference integrates the sensitivity ODEs next to the circuit (SciMLSensitivity, un-vendored).  Here the
+# perturbed circuits of a central-difference stencil are simply MORE SWEEP POINTS of the same batched call: a
+# sweep of B points with n parameters becomes one batch of B*(1 + K*n) points (K = 2 or 4 stencil offsets), solved
+# by the same kernels, and the stencil is combined on the host.  No new device code, any observable, DC or transient.
+
+_STENCILS = {2: ((-1, 1), (-0.5, 0.5)),
+             4: ((-2, -1, 1, 2), (1.0 / 12.0, -2.0 / 3.0, 2.0 / 3.0, -1.0 / 12.0))}
+
+
+class _ColumnSweep(SweepBase):
+    """A sweep given as explicit per-point columns (internal: the expanded batch of a sensitivity stencil)."""
+
+    def __init__(self, cols: Dict[str, np.ndarray]):
+        self._cols = {k: np.asarray(v, dtype=float) for k, v in cols.items()}
+        self.shape = (len(next(iter(self._cols.values()))),)
+
+    def sweepvars(self):
+        return set(self._cols)
+
+    def columns(self):
+        return dict(self._cols)
+
+    def __iter__(self):
+        names = sorted(self._cols)
+        for i in range(self.shape[0]):
+            yield tuple((k, None if np.isnan(self._cols[k][i]) else float(self._cols[k][i])) for k in names)
+
+
+def sensitivity_columns(columns: Dict[str, np.ndarray], wrt: Sequence[str], rel_step: float = 1e-3, order: int = 4):
+    """Columns of the expanded batch and the step of every (parameter, point).
+
+    Block 0 (the first B points) is the sweep itself; block 1 + j*K + k is the sweep with parameter wrt[j] moved by
+    offsets[k] * h_j, where h_j = rel_step * |p_j| per point (rel_step itself where p_j == 0)."""
+    if order not in _STENCILS:
+        raise ValueError("order must be 2 or 4")
+    offs, _ = _STENCILS[order]
+    B = len(next(iter(columns.values())))
+    steps = {}
+    blocks = {k: [np.asarray(v, dtype=float)] for k, v in columns.items()}
+    for name in wrt:
+        if name not in columns:
+            raise KeyError(f"sensitivity parameter {name!r} is not a swept variable of this CircuitSweep "
+                           f"(add it as a one-value Sweep to differentiate at its nominal value)")
+        p = np.asarray(columns[name], dtype=float)
+        if np.isnan(p).any():
+            raise ValueError(f"sensitivity parameter {name!r} is left at its default (None) at some points")
+        h = np.where(p != 0.0, rel_step * np.abs(p), rel_step)
+        steps[name] = h
+        for o in offs:
+            for k, v in columns.items():
+                blocks[k].append(np.asarray(v, dtype=float) + (o * h if k == name else 0.0))
+    assert all(len(b[0]) == B for b in blocks.values())
+    return {k: np.concatenate(b) for k, b in blocks.items()}, steps
+
+
+def combine_stencil(v: np.ndarray, B: int, j: int, h: np.ndarray, order: int = 4) -> np.ndarray:
+    """d v / d p_j from values `v[..., B*(1+K*n)]` laid out as `sensitivity_columns` does."""
+    offs, coef = _STENCILS[order]
+    K = len(offs)
+    acc = 0.0
+    for k, c in enumerate(coef):
+        blk = 1 + j * K + k
+        acc = acc + c * v[..., blk * B:(blk + 1) * B]
+    return acc / h
+
+
+class SensitivitySolution:
+    """Result of `sensitivities_`: `.solution` is the SweepSolution of the sweep itself, `.array(ref, name)` /
+    `.point(idx, ref, name)` the derivative of any unknown or observable with respect to swept parameter `name`."""
+
+    def __init__(self, cs: "CircuitSweep", big: SweepSolution, wrt: List[str], steps: Dict[str, np.ndarray], order: int):
+        self.cs, self.big, self.wrt, self.steps, self.order = cs, big, list(wrt), steps, order
+        B = len(cs)
+        self.t = big.t
+        self.solution = SweepSolution(cs, big.y[..., :B], big.status[:B], big.stats, big.t)
+        # a derivative is valid where every point of its stencil converged
+        self.status = big.status.reshape(-1, B).max(axis=0)
+
+    def _d(self, ref, name: str) -> np.ndarray:
+        j = self.wrt.index(name)
+        v = _Observable(self.big.fc, ref).value(self.big, slice(None))
+        return combine_stencil(v, len(self.cs), j, self.steps[name], self.order)
+
+    def array(self, ref, name: str) -> np.ndarray:
+        """d ref / d name over the whole sweep, shaped size(cs) (+ time axis last for transient)"""
+        d = self._d(ref, name)
+        if self.t is None:
+            return d.reshape(self.cs.shape, order="F")
+        return np.moveaxis(d, 0, -1).reshape(self.cs.shape + (len(self.t),), order="F")
+
+    def point(self, idx, ref, name: str):
+        """d ref / d name at one sweep point: a number (DC) or the waveform over `.t` (transient)"""
+        return self._d(ref, name)[..., self.solution._linear(idx)]
+
+    @property
+    def retcodes(self) -> np.ndarray:
+        return np.array([RETCODES.get(int(s), "Failure") for s in self.status], dtype=object).reshape(self.cs.shape, order="F")
+
+
+def sensitivities_(cs: CircuitSweep, wrt: Optional[Sequence[str]] = None, analysis: str = "dc", tspan=None, saveat=None,
+                   rel_step: float = 1e-3, order: int = 4, **kw) -> SensitivitySolution:
+    """Forward sensitivities of every sweep point with respect to the swept parameters `wrt` (default: all of
+    them, like the reference's sensitivity problem over the ParamSim's parameters, test/sensitivity.jl:58-67).
+    For `analysis="tran"` use `fixed_step=1` (or tolerances well below the derivative accuracy wanted), so that the
+    stencil points share their time grid and step-control noise does not enter the difference."""
+    wrt = [w for w in (sorted(cs.columns) if wrt is None else wrt)]
+    cols, steps = sensitivity_columns(cs.columns, wrt, rel_step, order)
+    big_cs = CircuitSweep(cs.circuit, _ColumnSweep(cols), devices=cs.devices, **cs._ctor)
+    if cs.x0 is not None:
+        reps = len(big_cs) // len(cs)
+        big_cs.x0 = cs.x0 if cs.x0.ndim == 1 else np.tile(cs.x0, (1, reps))
+    if analysis == "dc":
+        big = dc_(big_cs, **kw)
+    elif analysis == "tran":
+        big = tran_(big_cs, tspan, saveat, **kw)
+    else:
+        raise ValueError("analysis must be 'dc' or 'tran'")
+    return SensitivitySolution(cs, big, wrt, steps, order)
+
+
 dc = dc_
 tran = tran_
+sensitivities = sensitivities_
 ac = ac_
 noise = noise_

@@ -137,12 +137,15 @@ def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2
     base = os.path.join(out_dir, f"{cm.name}_{key}")
     so = base + ".so"
     if not os.path.exists(so):
-        with open(base + ".c", "w") as f:
+        # per-process scratch names + atomic rename: concurrent builders (pytest-xdist workers, ranks) never
+        # see or clobber each other's half-written files
+        src, tmp = f"{base}.{os.getpid()}.c", f"{so}.{os.getpid()}.tmp"
+        with open(src, "w") as f:
             f.write(text)
-        cmd = [HOST_CC, opt, "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-w", "-o", so + ".tmp",
-               base + ".c", "-lm"]
+        cmd = [HOST_CC, opt, "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-w", "-o", tmp, src, "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"host compile of generated model failed:\n{r.stderr[:4000]}")
-        os.replace(so + ".tmp", so)
+        os.replace(src, base + ".c")
+        os.replace(tmp, so)
     return HostModel(cm, so)
