@@ -678,7 +678,7 @@ def _merge_stats(stats: List[dict]) -> dict:
 # The reference integrates the sensitivity ODEs next to the circuit (SciMLSensitivity, un-vendored).  Here the
 # perturbed circuits of a central-difference stencil are simply MORE SWEEP POINTS of the same batched call: a
 # sweep of B points with n parameters becomes one batch of B*(1 + K*n) points (K = 2 or 4 stencil offsets), solved
-# by the same kernels, and the stencil is combined on the host.  No new device code, any observable, DC or transient.
+# by the same kernels, and the stencil is combined on the host.  No new device code, any observable, DC, transient, AC or noise.
 
 _STENCILS = {2: ((-1, 1), (-0.5, 0.5)),
              4: ((-2, -1, 1, 2), (1.0 / 12.0, -2.0 / 3.0, 2.0 / 3.0, -1.0 / 12.0))}
@@ -743,38 +743,48 @@ def combine_stencil(v: np.ndarray, B: int, j: int, h: np.ndarray, order: int = 4
 
 class SensitivitySolution:
     """Result of `sensitivities_`: `.solution` is the SweepSolution of the sweep itself, `.array(ref, name)` /
-    `.point(idx, ref, name)` the derivative of any unknown or observable with respect to swept parameter `name`."""
+    `.point(idx, ref, name)` the derivative of any unknown or observable with respect to swept parameter `name`
+    (`analysis="ac"` / `"noise"`: `.solution` is a FreqSolution and the derivative has a frequency axis)."""
 
-    def __init__(self, cs: "CircuitSweep", big: SweepSolution, wrt: List[str], steps: Dict[str, np.ndarray], order: int):
+    def __init__(self, cs: "CircuitSweep", big, wrt: List[str], steps: Dict[str, np.ndarray], order: int):
         self.cs, self.big, self.wrt, self.steps, self.order = cs, big, list(wrt), steps, order
         B = len(cs)
-        self.t = big.t
-        self.solution = SweepSolution(cs, big.y[..., :B], big.status[:B], big.stats, big.t)
+        self.freq = isinstance(big, FreqSolution)
+        self.freqs = big.freqs if self.freq else None
+        self.t = None if self.freq else big.t
+        if self.freq:
+            self.solution = FreqSolution(cs, big.y[..., :B], big.status[:B], big.stats, big.freqs, big.kind)
+        else:
+            self.solution = SweepSolution(cs, big.y[..., :B], big.status[:B], big.stats, big.t)
         # a derivative is valid where every point of its stencil converged
         self.status = big.status.reshape(-1, B).max(axis=0)
 
     def _d(self, ref, name: str) -> np.ndarray:
         j = self.wrt.index(name)
-        v = _Observable(self.big.fc, ref).value(self.big, slice(None))
+        if self.freq:
+            v = self.big.y[self.big.out_index[_resolve(self.big.fc, ref)]]
+        else:
+            v = _Observable(self.big.fc, ref).value(self.big, slice(None))
         return combine_stencil(v, len(self.cs), j, self.steps[name], self.order)
 
     def array(self, ref, name: str) -> np.ndarray:
-        """d ref / d name over the whole sweep, shaped size(cs) (+ time axis last for transient)"""
+        """d ref / d name over the whole sweep, shaped size(cs) (+ time or frequency axis last)"""
         d = self._d(ref, name)
-        if self.t is None:
+        if d.ndim == 1:
             return d.reshape(self.cs.shape, order="F")
-        return np.moveaxis(d, 0, -1).reshape(self.cs.shape + (len(self.t),), order="F")
+        return np.moveaxis(d, 0, -1).reshape(self.cs.shape + (d.shape[0],), order="F")
 
     def point(self, idx, ref, name: str):
         """d ref / d name at one sweep point: a number (DC) or the waveform over `.t` (transient)"""
-        return self._d(ref, name)[..., self.solution._linear(idx)]
+        i = int(idx) if isinstance(idx, (int, np.integer)) else int(np.ravel_multi_index(tuple(idx), self.cs.shape, order="F"))
+        return self._d(ref, name)[..., i]
 
     @property
     def retcodes(self) -> np.ndarray:
         return np.array([RETCODES.get(int(s), "Failure") for s in self.status], dtype=object).reshape(self.cs.shape, order="F")
 
 
-def sensitivities_(cs: CircuitSweep, wrt: Optional[Sequence[str]] = None, analysis: str = "dc", tspan=None, saveat=None,
+def sensitivities_(cs: CircuitSweep, wrt: Optional[Sequence[str]] = None, analysis: str = "dc", tspan=None, saveat=None, freqs=None,
                    rel_step: float = 1e-3, order: int = 4, **kw) -> SensitivitySolution:
     """Forward sensitivities of every sweep point with respect to the swept parameters `wrt` (default: all of
     them, like the reference's sensitivity problem over the ParamSim's parameters, test/sensitivity.jl:58-67).
@@ -790,8 +800,12 @@ def sensitivities_(cs: CircuitSweep, wrt: Optional[Sequence[str]] = None, analys
         big = dc_(big_cs, **kw)
     elif analysis == "tran":
         big = tran_(big_cs, tspan, saveat, **kw)
+    elif analysis in ("ac", "noise"):      # derivative of the complex response / of the output PSD over `freqs`
+        if freqs is None:
+            raise ValueError("analysis='ac' / 'noise' needs freqs")
+        big = (ac_ if analysis == "ac" else noise_)(big_cs, freqs, **kw)
     else:
-        raise ValueError("analysis must be 'dc' or 'tran'")
+        raise ValueError("analysis must be 'dc', 'tran', 'ac' or 'noise'")
     return SensitivitySolution(cs, big, wrt, steps, order)
 
 
