@@ -137,3 +137,27 @@ def test_sensitivities_nonlinear_va_diode_gpu(tmp_path):   # Newton-solved point
     # (vin - v)/r = Id(v):  dv/dr = -(vin - v)/r^2 / (1/r + gd),  dv/dvin = (1/r) / (1/r + gd)
     assert np.allclose(sens.array(cs.sys.node_d, "r"), -(VIN - v) / R ** 2 / (1 / R + gd), rtol=1e-6, atol=0)
     assert np.allclose(sens.array(cs.sys.node_d, "vin"), (1 / R) / (1 / R + gd), rtol=1e-6, atol=0)
+
+
+RC_AC = "* rc low-pass\n.param r=1k c=1n\nV1 in 0 DC 0 AC 1\nR1 in out 'r'\nC1 out 0 'c'\n"
+
+
+@pytest.mark.gpu
+def test_sensitivities_ac_and_noise_gpu():   # H = 1/(1 + j w r c): dH/dr = -j w c H^2;  S_out = 4 k T r |H|^2
+    r = np.array([500.0, 1000.0, 2000.0])
+    f = np.logspace(3, 7, 9)
+    cs = CircuitSweep(RC_AC, Sweep(r=r), outputs=["out"])
+    sens = sensitivities_(cs, analysis="ac", freqs=f, gmin=0.0)
+    w = 2 * np.pi * f[None, :]
+    H = 1.0 / (1.0 + 1j * w * r[:, None] * 1e-9)
+    assert np.abs(sens.solution.array(cs.sys.node_out) - H).max() < 1e-12
+    d = sens.array(cs.sys.node_out, "r")
+    assert d.shape == (3, 9) and np.abs(d - (-1j * w * 1e-9 * H * H)).max() <= 1e-9 * np.abs(w * 1e-9 * H * H).max()
+    sens = sensitivities_(cs, analysis="noise", freqs=f, temp=27.0, gmin=0.0)
+    S = sens.solution.array(cs.sys.node_out)
+    kT4 = 4 * 1.380649e-23 * 300.15
+    assert np.allclose(S, kT4 * r[:, None] * np.abs(H) ** 2, rtol=1e-6, atol=0)
+    x = (w * r[:, None] * 1e-9) ** 2
+    want = S / r[:, None] * (1 - x) / (1 + x)          # d/dr [ r / (1 + (w r c)^2) ]
+    assert np.abs(sens.array(cs.sys.node_out, "r") - want).max() <= 1e-7 * np.abs(S / r[:, None]).max()
+    assert sens.point(1, cs.sys.node_out, "r").shape == (9,)
