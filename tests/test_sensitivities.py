@@ -161,3 +161,25 @@ def test_sensitivities_ac_and_noise_gpu():   # H = 1/(1 + j w r c): dH/dr = -j w
     want = S / r[:, None] * (1 - x) / (1 + x)          # d/dr [ r / (1 + (w r c)^2) ]
     assert np.abs(sens.array(cs.sys.node_out, "r") - want).max() <= 1e-7 * np.abs(S / r[:, None]).max()
     assert sens.point(1, cs.sys.node_out, "r").shape == (9,)
+
+
+
+@pytest.mark.gpu
+def test_sensitivities_bsimcmg_inverter_gain_gpu():
+    # Transistor level, two independent routes to the same number: d q / d vin from the difference stencil over Newton-solved
+    # operating points, and the low-frequency AC gain from the generated Jacobians (cb_ac) at the same points.
+    from cedarsim.jl_b200 import circuits
+    from cedarsim.jl_b200.sweeps import ac_
+    cs = CircuitSweep(circuits.BSIMCMG_INVERTER_VIN_DECK, ProductSweep(**{"vin": np.linspace(0.1, 0.9, 17), "mneg.nfin": [1.0, 2.0, 3.0]}),
+                      outputs=["q"], host=True)
+    sens = sensitivities_(cs, rel_step=1e-3)
+    assert (sens.retcodes == "Success").all()
+    gain = sens.array(cs.sys.node_q, "vin")
+    H = ac_(cs, [1.0]).array(cs.sys.node_q)[..., 0]
+    assert gain.shape == H.shape == (17, 3)
+    assert gain.min() < -3.0 and gain.max() < 0.0        # an inverting stage with gain in the transition region
+    assert np.abs(H.imag).max() < 1e-6 * np.abs(H.real).max()
+    assert np.abs(gain - H.real).max() <= 1e-5 * np.abs(H.real).max()
+    # more nFET fins pull the output down: d q / d nfin < 0 everywhere, largest in the transition region
+    dn = sens.array(cs.sys.node_q, "mneg.nfin")
+    assert dn.max() < 0.0 and np.abs(dn).max() > 0.05
