@@ -197,11 +197,25 @@ def config5_sweep(n_temp: int = 32, n_mismatch: int = 1024, seed: int = 130, sig
                         TandemSweep(ln=21e-9 * (1.0 + sigma * z[:, 0]), lp=21e-9 * (1.0 + sigma * z[:, 1])))
 
 
+# test/bsimcmg/asap7_inv.scs restated for the SPICE reader (the reference reads the cards from a Spectre file that is
+# not in its tree): the gate is driven by a behavioural source in `$time`
+ASAP7_INV_TIME_DECK = """* asap7_inv.scs: inverter on the ASAP7 cards, gate = 1.8*(1-sin(2 pi 1e7 t))
+.include "jlpkg://ASAP7PDK/7nm_TT.pm"
+.param vcc=1.8
+M1p Vout Vgate VDD VDD pmos_lvt
+M1n Vout Vgate 0 0 nmos_lvt
+R1 Vout 0 10k
+VScc VDD 0 'vcc'
+Bgate Vgate 0 v=vcc*(1-sin(10.0**7*2*pi*$time))
+"""
+
+
 def small_signal_decks():
     """(deck text, swept columns) of the deck-based GPU tests; build() compiles them so that the GPU box finds
     their cubins in the cache."""
     one = np.array([1.0])
     return [(BSIMCMG_INVERTER_DECK, None),
             (BSIMCMG_INVERTER_VIN_DECK, {"vin": np.array([0.5]), "mneg.nfin": one}),
+            (ASAP7_INV_TIME_DECK, {"vcc": 1.8 * one}),
             (CONFIG5_DECK, {"dvtn": 0 * one, "dvtp": 0 * one, "u0n": one, "u0p": one, "temp": 27 * one, "ln": 21e-9 * one,
                             "lp": 21e-9 * one})]

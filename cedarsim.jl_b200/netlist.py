@@ -380,6 +380,9 @@ class Flattened:
     tran: Optional[Tuple[float, float]]
 
 
+_TIME_NET = "time__"   # hidden net carrying simulation time for `$time` in behavioural sources
+
+
 class _Flattener:
     def __init__(self, nl: Netlist, sweep: Dict[str, np.ndarray], B: int, host: bool, outputs: Optional[Sequence[str]] = None):
         self.nl, self.sweep, self.B, self.host = nl, {k.lower(): v for k, v in sweep.items()}, B, host
@@ -590,12 +593,15 @@ class _Flattener:
             args = [a for a in m.group(1).split(",")]
             return "V(" + ", ".join(port(a) for a in args) + ")"
 
+        # `$time` / `$abstime`: the device code takes no time argument, so simulation time enters as the voltage of a
+        # hidden net driven by V(t) = t (one shared ramp source per circuit); the module probes it like any other net
+        text = re.sub(r"\$(?:abs)?time\b", f"V({_TIME_NET})", text, flags=re.I)
         body = re.sub(r"\b[vV]\s*\(([^()]*)\)", probe, text)
         if re.search(r"\b[iI]\s*\(", body) or "$" in body:
             raise NetlistError(f"{name}: only V() probes are supported in behavioural sources ({text!r})")
         body = body.replace("**", "^")
         # numbers with SPICE magnitudes -> plain literals; identifiers that are netlist parameters -> module parameters
-        from .expr import parse_number
+        from .expr import parse_number, _CONSTS
         pars: List[str] = []
 
         def atom(m):
@@ -605,6 +611,11 @@ class _Flattener:
             low = tok.lower()
             if low in ("v",) or re.match(r"^c\d+$", low) or low in _VA_FUNCS:
                 return low if low in _VA_FUNCS else tok
+            if low in _CONSTS:      # pi, e, M_PI, ...: constants of the expression language unless a parameter shadows them
+                try:
+                    scope.lookup(low)
+                except ExprError:
+                    return repr(float(_CONSTS[low]))
             if low not in pars:
                 pars.append(low)
             return "P_" + low
@@ -632,7 +643,17 @@ class _Flattener:
         else:
             shape = shape_of(cm)
         vals = {f"P_{q}": self.value(f"{name}.{q}", scope.lookup(q)) for q in pars}
-        self.fc.va_instance(name, self.fc.va_model(shape), nodes[:2] + [net(q) for q in ports], vals, m=mult)
+        self.fc.va_instance(name, self.fc.va_model(shape),
+                            nodes[:2] + [self._time_net() if q == _TIME_NET else net(q) for q in ports], vals, m=mult)
+
+    def _time_net(self) -> str:
+        """The net whose voltage is the simulation time: a PWL source 0 -> T over [0, T] with T = 2^20 s (slope exactly
+        1; 0 V at the DC operating point, like `$time` there).  Created on first use; shows up as unknown `$time`."""
+        if not getattr(self, "_has_time_net", False):
+            T = float(2 ** 20)
+            self.fc.vsource(_TIME_NET, _TIME_NET, "0", Wave(W_PWL, dc=0.0, t=[0.0, T], y=[0.0, T]))
+            self._has_time_net = True
+        return _TIME_NET
 
     def _va_device(self, name: str, card: Card, nodes: List[str], scope: _Scope, mult: float):
         """Instance of a Verilog-A module brought in by `.hdl`: all module parameters stay run-time parameters (instance

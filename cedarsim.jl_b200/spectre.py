@@ -6,7 +6,8 @@ instances `name (n1 n2 ...) master k=v ...` of the primitives `resistor capacito
 of subcircuits, of model cards and of Verilog-A modules; `subckt ... ends` with `parameters`; `model`; `include`,
 `ahdl_include`; `type=pwl wave=[...]`, `type=sine`, `type=pulse` sources; `\\` continuations, `//` and `*` comments.
 Names are kept as the flattener wants them (lower case; results are addressed case-insensitively).
-Behavioural sources (`bsource`), analyses and `simulator lang=spice` sections are outside the subset and raise.
+Behavioural sources (`bsource v=` / `i=` over V() probes, parameters and `$time`) become the same cards the SPICE
+reader makes of B sources; analyses are skipped and `simulator lang=spice` sections are outside the subset and raise.
 
 Device / parameter names follow the reference's lowering (src/spectre.jl:999-1071: `r`, `c`, `l`, `gain`, `gm`;
 source parameters src/spectre_env.jl:144-176).
@@ -174,8 +175,11 @@ def parse_spectre(text: str, path: Optional[str] = None, include_dirs: Optional[
                 cur.cards.append(Card(kind, name, nodes[:4], None, kv, val))
             else:
                 cur.cards.append(Card(kind, name, nodes[:2], None, kv, None))
-        elif m == "bsource":
-            raise NetlistError(f"{toks[0]}: behavioural sources are outside the Spectre subset")
+        elif m == "bsource":   # `B5 (0 5) bsource v=$time*V(3)`: same behavioural card the SPICE reader makes of `B5 0 5 v=...`
+            key = next((k for k in kv if k.lower() in ("v", "i")), None)
+            if key is None:
+                raise NetlistError(f"{toks[0]}: bsource needs v=<expr> or i=<expr>")
+            cur.cards.append(Card("b", name, nodes[:2], None, {key.lower(): str(kv[key])}))
         elif m in nl.cards or any(k.startswith(m + ".") for k in nl.cards):
             card = nl.cards.get(m)
             kind = "m" if (card is None or card.master.startswith(("bsim", "nmos", "pmos"))) else card.master[:1]

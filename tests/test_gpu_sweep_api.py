@@ -124,3 +124,23 @@ def test_behavioural_sources_dc_sweep():   # test/basic.jl:207-235 on the GPU, w
     assert np.allclose(sols.array(cs.sys.node_5), g, rtol=1e-12)                    # 2.0 at gain = 2
     assert np.allclose(sols.array(cs.sys.node_8), g * g, rtol=1e-12)                # 4.0
     assert np.allclose(sols.array(cs.sys.node_9), -1000.0 * g * g, rtol=1e-12)      # -4000.0: no step limit for linear devices
+
+
+def test_bsource_time_inverter_sweep(host_bsimcmg):   # test/bsimcmg/bsimcmg_spectre.jl:33-37 as a supply sweep on the GPU
+    """`$time` in a behavioural source (the hidden ramp net `time__`): out node positive after DC init, transient succeeds,
+    fixed-step parity with the oracle at the north star's tolerance."""
+    from cedarsim.jl_b200 import circuits
+    vcc = np.array([1.2, 1.5, 1.8])
+    cs = CircuitSweep(circuits.ASAP7_INV_TIME_DECK, Sweep(vcc=vcc), outputs=["vout", "vgate", "time__"], host=True)
+    dc = dc_(cs)
+    assert all(s.retcode == "Success" for s in dc) and dc.array(cs.sys.node_vout).min() > 0.0
+    ts = np.linspace(0.0, 1e-7, 101)
+    kw = dict(fixed_step=1, dt=1e-10)
+    sols = tran_(cs, (0.0, 1e-7), saveat=ts, **kw)
+    assert all(s.retcode == "Success" for s in sols)
+    assert np.abs(sols.array("time__") - ts[None, :]).max() < 1e-20
+    assert np.abs(sols.array(cs.sys.node_vgate) - vcc[:, None] * (1 - np.sin(2e7 * np.pi * ts))[None, :]).max() < 1e-9
+    yo, so, _ = orc.tran(cs.flat.fc, 0.0, 1e-7, ts, params=cs.flat.params, opts=orc.default_options(**kw))
+    assert so.max() == 0
+    err = np.abs(sols.y - yo)
+    assert np.all(err <= 1e-6 * np.abs(yo) + 1e-9), err.max()

@@ -363,3 +363,22 @@ def test_ddx_known_answer():   # test/ddx.jl:9-21: sol[sys.V1.I][end] == -5*2*2*
     fl = netlist.flatten(netlist.parse_netlist(deck, include_dirs=[inc]), host=True)
     x, xf, st, _ = orc.dc(fl.fc, None)
     assert st.max() == 0 and xf[fl.fc.unknown("v1.i"), 0] == -5.0 * 2 * 2 * 3
+
+
+def test_bsimcmg_inverter_bsource_time():   # test/bsimcmg/bsimcmg_spectre.jl:33-37 on test/bsimcmg/asap7_inv.scs
+    """`VSgate bsource v=1.8*(1-sin(10.0**7*2*pi*$time))` driving the ASAP7 inverter: after DC init the out node is positive
+    (a non-DC initialisation could leave it negative through the capacitances) and the transient to 1e-7 s succeeds."""
+    from cedarsim.jl_b200 import circuits, models
+    if not models.available():
+        pytest.skip("BSIM-CMG sources not available")
+    fl = netlist.flatten(netlist.parse_netlist(circuits.ASAP7_INV_TIME_DECK), host=True)
+    fc = fl.fc
+    _, xf, st, _ = orc.dc(fc, None)
+    assert st.max() == 0 and xf[fc.unknown("vout"), 0] > 0.0
+    assert abs(xf[fc.unknown("vgate"), 0] - 1.8) < 1e-12 and abs(xf[fc.unknown("time__"), 0]) < 1e-30   # $time == 0 in the DC solve
+    ts = np.linspace(0.0, 1e-7, 201)
+    y, st, _ = orc.tran(fc, 0.0, 1e-7, ts, opts=orc.default_options(reltol=1e-4))
+    assert st.max() == 0                                                                          # retcode == Success
+    assert np.abs(y[fc.unknown("vgate"), :, 0] - 1.8 * (1 - np.sin(2e7 * np.pi * ts))).max() < 2e-4   # saveat interpolation between accepted steps
+    vout = y[fc.unknown("vout"), :, 0]
+    assert vout.max() > 0.7 and vout.min() > -0.05      # pulled up through the PMOS while the gate dips below threshold

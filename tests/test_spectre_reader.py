@@ -26,7 +26,7 @@ R4 (4 0) resistor r=4k
 """
 
 
-def test_simple_spectre_sources(tmp_path):   # test/basic.jl:168-205 (read from a file, as there; the bsource rows are out of the subset)
+def test_simple_spectre_sources(tmp_path):   # test/basic.jl:168-205 (read from a file, as there; the bsource rows follow in the next test)
     f = tmp_path / "sources.scs"
     f.write_text(SOURCES)
     fl = netlist.flatten(spectre.parse_spectre_file(str(f)))
@@ -39,8 +39,19 @@ def test_simple_spectre_sources(tmp_path):   # test/basic.jl:168-205 (read from 
     assert np.allclose(v("3"), -1.5) and np.allclose(v("3") / 1e3, -1.5e-3)            # node_3, R3.I
     assert np.isclose(v("2")[-1], 3.5) and np.isclose(v("2")[-1] / 2e3, 1.75e-3)       # node_2[end], R2.I[end]
     assert np.isclose(v("4")[-1], -5.0) and np.isclose(v("4")[-1] / 4e3, -1.25e-3)     # node_4[end], R4.I[end]
-    with pytest.raises(netlist.NetlistError, match="behavioural"):
-        spectre.parse_spectre(SOURCES + "B5 (0 5) bsource v=$time*V(3)\n")
+
+
+def test_spectre_bsource_with_time():   # test/basic.jl:185-186, :203: B5 (0 5) bsource v=$time*V(3) -> node_5[end] == 1.5
+    fl = netlist.flatten(spectre.parse_spectre(SOURCES + "B5 (0 5) bsource v=$time*V(3)\nR5 (5 0) resistor r=1k\n"), host=True)
+    fc = fl.fc
+    ts = np.linspace(0.0, 1.0, 11)
+    y, st, _ = orc.tran(fc, 0.0, 1.0, ts, opts=orc.default_options())
+    assert st.max() == 0
+    assert np.allclose(y[fc.unknown("time__"), :, 0], ts, rtol=0, atol=1e-15)        # the hidden ramp IS the time
+    assert np.allclose(y[fc.unknown("5"), :, 0], 1.5 * ts, atol=1e-9)                # V(0,5) = t * V(3) = -1.5 t
+    assert np.isclose(y[fc.unknown("5"), -1, 0], 1.5) and np.isclose(y[fc.unknown("3"), -1, 0], -1.5)
+    with pytest.raises(netlist.NetlistError, match="bsource needs"):
+        spectre.parse_spectre(SOURCES + "B5 (0 5) bsource r=1\n")
 
 
 SUBCKT = """
