@@ -27,9 +27,9 @@ _cache: Dict[str, CompiledModel] = {}
 
 def save_model(cm: CompiledModel, path: str):
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    with open(path + ".tmp", "w") as f:
+    with open(f"{path}.{os.getpid()}.tmp", "w") as f:
         json.dump(dataclasses.asdict(cm), f)
-    os.replace(path + ".tmp", path)
+    os.replace(f"{path}.{os.getpid()}.tmp", path)
 
 
 def load_model(path: str) -> CompiledModel:

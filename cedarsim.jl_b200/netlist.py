@@ -631,9 +631,9 @@ class _Flattener:
         os.makedirs(models.GEN_DIR, exist_ok=True)
         path = os.path.join(models.GEN_DIR, mname + ".va")
         if not os.path.exists(path):
-            with open(path + ".tmp", "w") as f:
+            with open(f"{path}.{os.getpid()}.tmp", "w") as f:
                 f.write("\n".join(va))
-            os.replace(path + ".tmp", path)
+            os.replace(f"{path}.{os.getpid()}.tmp", path)
         cm = models.compiled_model(mname, path, module=mname)
         if cm not in self.models:
             self.models.append(cm)
