@@ -382,3 +382,15 @@ def test_bsimcmg_inverter_bsource_time():   # test/bsimcmg/bsimcmg_spectre.jl:33
     assert np.abs(y[fc.unknown("vgate"), :, 0] - 1.8 * (1 - np.sin(2e7 * np.pi * ts))).max() < 2e-4   # saveat interpolation between accepted steps
     vout = y[fc.unknown("vout"), :, 0]
     assert vout.max() > 0.7 and vout.min() > -0.05      # pulled up through the PMOS while the gate dips below threshold
+
+
+def test_mc_vr_circuit_agauss_is_nominal():   # test/basic.jl:45-79: R(agauss(2, 3, 3)) with the RNG disabled -> the same current at every time step
+    fl = netlist.flatten(netlist.parse_netlist("* MC VR\nV vcc 0 5\nR vcc 0 'agauss(2, 3, 3)'\n"))
+    y, st, _ = orc.tran(fl.fc, 0.0, 1e-3, np.linspace(0, 1e-3, 11), opts=orc.default_options())
+    i = -y[fl.fc.unknown("v.i"), :, 0]
+    assert st.max() == 0 and np.abs(i - i[0]).max() < DEFTOL and abs(i[0] - 2.5) < DEFTOL
+
+
+def test_option_card_only():   # test/basic.jl:640-649: a deck of nothing but `.option temp=10 filemode=ascii noinit` is accepted
+    nl = netlist.parse_netlist("* .option\n.option temp=10 filemode=ascii noinit\n")
+    assert {k.lower(): v for k, v in nl.options.items()}["temp"] == "10" and not nl.top.cards
