@@ -7,6 +7,9 @@
     tran_(cs) == tran!(cs::CircuitSweep, tspan)  src/sweeps.jl:450-463, 488-502 (with the defects
                                              listed in SURVEY.md 3.2 fixed: tspan is an argument)
 
+    sensitivities_(cs, wrt)                  test/sensitivity.jl:14-68 (forward sensitivities over the ParamSim's
+                                             parameters), as a batched difference stencil: extra sweep points
+
 Iteration order and shapes are the reference's: a point is a tuple of (name, value) pairs sorted by
 name; a product varies its FIRST axis fastest and `size(cs)` is the tuple of axis lengths (Julia
 column-major), tandem zips, serial concatenates with None ("keep default") for inactive names.
