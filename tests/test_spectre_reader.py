@@ -50,6 +50,10 @@ def test_spectre_bsource_with_time():   # test/basic.jl:185-186, :203: B5 (0 5) 
     assert np.allclose(y[fc.unknown("time__"), :, 0], ts, rtol=0, atol=1e-15)        # the hidden ramp IS the time
     assert np.allclose(y[fc.unknown("5"), :, 0], 1.5 * ts, atol=1e-9)                # V(0,5) = t * V(3) = -1.5 t
     assert np.isclose(y[fc.unknown("5"), -1, 0], 1.5) and np.isclose(y[fc.unknown("3"), -1, 0], -1.5)
+    # a current-mode source, nonlinear in time: I(0,1) = 2 mA * t^2 into 1 kOhm
+    fl = netlist.flatten(spectre.parse_spectre("B1 (0 1) bsource i=2m*$time*$time\nR1 (1 0) resistor r=1k\n"), host=True)
+    y, st, _ = orc.tran(fl.fc, 0.0, 1.0, ts, opts=orc.default_options())
+    assert st.max() == 0 and np.allclose(y[fl.fc.unknown("1"), :, 0], 2.0 * ts ** 2, atol=1e-9)
     with pytest.raises(netlist.NetlistError, match="bsource needs"):
         spectre.parse_spectre(SOURCES + "B5 (0 5) bsource r=1\n")
 
