@@ -73,6 +73,28 @@ def test_sweep_of_closed_forms_oracle():   # d out / d R1 = -R2/(R1+R2)^2, d out
     assert np.allclose(d2, cols["R1"] / (cols["R1"] + cols["R2"]) ** 2, rtol=1e-9, atol=0)
 
 
+def test_column_sweep_and_no_cpu_fallback():
+    """The expanded batch is an ordinary sweep of explicit columns; without a GPU the public call fails loudly in the
+    engine (no CPU fallback) instead of differencing oracle solutions."""
+    from cedarsim.jl_b200 import engine
+    from cedarsim.jl_b200.sweeps import _ColumnSweep
+    sw = _ColumnSweep({"b": [1.0, 2.0, np.nan], "a": [5.0, 6.0, 7.0]})
+    assert sw.shape == (3,) and len(sw) == 3 and sw.sweepvars() == {"a", "b"}
+    assert list(sw) == [(("a", 5.0), ("b", 1.0)), (("a", 6.0), ("b", 2.0)), (("a", 7.0), ("b", None))]
+    cs = CircuitSweep(TWO_R, ProductSweep(R1=[1.0, 2.0], R2=[1.0]))
+    with pytest.raises(KeyError, match="not a swept variable"):
+        sensitivities_(cs, wrt=["R3"])
+    with pytest.raises(ValueError, match="analysis must be"):
+        sensitivities_(cs, analysis="pz")
+    with pytest.raises(ValueError, match="order must be"):
+        sensitivity_columns(cs.columns, ["R1"], order=3)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(engine.EngineError) as e:
+            sensitivities_(cs)
+        assert "no CPU fallback" in str(e.value)
+
+
 # ---------------------------------------------------------------- GPU: the public call
 @pytest.mark.gpu
 def test_sensitivities_two_resistor_gpu():
