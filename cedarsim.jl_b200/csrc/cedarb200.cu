@@ -103,8 +103,31 @@ struct cb_circuit {
 extern "C" int cb_version(void) { return CB_ABI_VERSION; }
 extern "C" const char* cb_last_error(void) { return g_err.c_str(); }
 
+extern "C" size_t cb_options_size(void) { return sizeof(cb_options); }
+extern "C" size_t cb_stats_size(void) { return sizeof(cb_stats); }
+extern "C" int cb_options_init(cb_options* o, size_t caller_sizeof) {
+    if (!o) return fail(CB_ERR_INVALID, "null argument");
+    if (caller_sizeof != sizeof(cb_options))
+        return fail(CB_ERR_INVALID, "cb_options layout mismatch: the caller's struct has " + std::to_string(caller_sizeof) +
+                                        " bytes, this library's has " + std::to_string(sizeof(cb_options)) + " (ABI version " +
+                                        std::to_string(CB_ABI_VERSION) + ")");
+    cb_options_default(o);
+    return CB_OK;
+}
+// every entry point that takes options: refuse a struct that was not initialised by this library's layout
+static int check_options(const cb_options* o) {
+    if (!o) return fail(CB_ERR_INVALID, "null options");
+    if (o->struct_size != sizeof(cb_options) || o->abi_version != CB_ABI_VERSION)
+        return fail(CB_ERR_INVALID, "cb_options was not initialised by cb_options_default / cb_options_init of this library (size " +
+                                        std::to_string(o->struct_size) + " / ABI " + std::to_string(o->abi_version) + ", expected " +
+                                        std::to_string(sizeof(cb_options)) + " / " + std::to_string(CB_ABI_VERSION) + ")");
+    return CB_OK;
+}
+
 extern "C" void cb_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
+    o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
+    o->mixed_rounds = 0; o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e8;
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
@@ -122,7 +145,7 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
     auto c = std::make_unique<cb_circuit>();
     c->N = f->n_unknowns; c->NV = f->n_nodes; c->P = f->n_params;
     auto chk = [&](int idx) { return idx >= -1 && idx < c->N; };
-    auto chkp = [&](const cb_pref& p) { return p.col < f->n_params; };
+    auto chkp = [&](const cb_pref& p) { return p.col >= -1 && p.col < f->n_params; };
     for (int i = 0; i < f->n_devices; i++) {
         const cb_device& d = f->devices[i];
         for (int k = 0; k < 4; k++) if (!chk(d.n[k])) return fail(CB_ERR_INVALID, "device node index out of range");
@@ -144,9 +167,20 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
         }
         for (int k = 0; k < 7; k++) h.v[k] = w.v[k];
         h.ac_mag = w.ac_mag;
-        if (w.kind == CB_W_PULSE)
+        // every parameter reference of a waveform must name a row of params[P][B] (or -1): they are dereferenced on the device
+        if (!chkp(w.dc)) return fail(CB_ERR_INVALID, "waveform dc parameter column out of range");
+        for (const cb_pref& y : h.y) if (!chkp(y)) return fail(CB_ERR_INVALID, "PWL value parameter column out of range");
+        if (w.kind == CB_W_PULSE || w.kind == CB_W_SIN)
+            for (int k = 0; k < 7; k++) if (!chkp(w.v[k])) return fail(CB_ERR_INVALID, "waveform parameter column out of range");
+        if (w.kind == CB_W_PULSE) {
             for (int k = 2; k < 7; k++)
                 if (w.v[k].col >= 0) return fail(CB_ERR_INVALID, "PULSE timing parameters cannot be swept");
+            // a period <= 0 (or NaN) means "no period" as in SPICE: one pulse (fmod(t, 0) is NaN, and the breakpoint
+            // collection would never terminate)
+            if (!(h.v[6].value > 0.0)) h.v[6].value = INFINITY;
+            for (int k = 2; k < 6; k++)
+                if (!(h.v[k].value >= 0.0) || !std::isfinite(h.v[k].value)) return fail(CB_ERR_INVALID, "PULSE td / tr / tf / pw must be finite and >= 0");
+        }
         c->waves.push_back(std::move(h));
     }
     for (int i = 0; i < f->n_va_models; i++) {
@@ -177,12 +211,101 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
         h.term.assign(v.term, v.term + m.nterm);
         for (int t : h.term) if (!chk(t)) return fail(CB_ERR_INVALID, "VA terminal index out of range");
         h.par.assign(v.par, v.par + m.nparam);
+        for (const cb_pref& q : h.par) if (!chkp(q)) return fail(CB_ERR_INVALID, "VA instance parameter column out of range");
         h.given.assign(v.given, v.given + m.nparam);
         c->insts.push_back(std::move(h));
     }
     c->outputs.assign(f->outputs, f->outputs + f->n_outputs);
     for (int o : c->outputs) if (o < 0 || o >= c->N) return fail(CB_ERR_INVALID, "output index out of range");
     *out = c.release();
+    return CB_OK;
+}
+
+
+// ---- "flatckt" files: a flat circuit + its generated device code, written by the host front end
+//      (cedarsim.jl_b200/flat.py save_flatckt, `python -m cedarsim.jl_b200.flatten`) so that a binding without a
+//      front end of its own (the Julia extension, ext/CedarSimB200Ext.jl) needs no struct packing: little-endian,
+//      "CBFC" u32 version | 8 x i32 counts | cb_device[] | waves | models | instances | outputs | u64 len, CUDA C.
+namespace {
+struct Reader {
+    const unsigned char* p; size_t n, off = 0; bool ok = true;
+    template <class T> T get() { T v{}; if (off + sizeof(T) > n) { ok = false; return v; } std::memcpy(&v, p + off, sizeof(T)); off += sizeof(T); return v; }
+    template <class T> void vec(std::vector<T>& v, size_t cnt) {
+        if (cnt > (n - std::min(n, off)) / sizeof(T)) { ok = false; return; }
+        v.resize(cnt); if (cnt) std::memcpy(v.data(), p + off, cnt * sizeof(T)); off += cnt * sizeof(T);
+    }
+};
+}  // namespace
+
+extern "C" int cb_circuit_load(const char* path, cb_circuit** out) {
+    if (!path || !out) return fail(CB_ERR_INVALID, "null argument");
+    std::vector<unsigned char> buf;
+    {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return fail(CB_ERR_INVALID, std::string("cannot open ") + path);
+        std::fseek(f, 0, SEEK_END); const long sz = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+        buf.resize(sz > 0 ? (size_t)sz : 0);
+        const size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
+        std::fclose(f);
+        if (got != buf.size()) return fail(CB_ERR_INVALID, std::string("short read of ") + path);
+    }
+    Reader r{buf.data(), buf.size()};
+    if (r.get<uint32_t>() != 0x43464243u /* "CBFC" */ || r.get<uint32_t>() != 1u) return fail(CB_ERR_INVALID, "not a flatckt v1 file");
+    cb_flat_circuit fc{};
+    fc.n_unknowns = r.get<int32_t>(); fc.n_nodes = r.get<int32_t>(); fc.n_params = r.get<int32_t>(); fc.n_devices = r.get<int32_t>();
+    fc.n_waves = r.get<int32_t>(); fc.n_va_models = r.get<int32_t>(); fc.n_va_insts = r.get<int32_t>(); fc.n_outputs = r.get<int32_t>();
+    if (!r.ok || fc.n_devices < 0 || fc.n_waves < 0 || fc.n_va_models < 0 || fc.n_va_insts < 0 || fc.n_outputs < 0)
+        return fail(CB_ERR_INVALID, "flatckt: bad header");
+    std::vector<cb_device> devs; r.vec(devs, (size_t)fc.n_devices);
+    std::vector<cb_wave> waves((size_t)fc.n_waves);
+    std::vector<std::vector<double>> wt((size_t)fc.n_waves);
+    std::vector<std::vector<cb_pref>> wy((size_t)fc.n_waves);
+    for (int i = 0; i < fc.n_waves && r.ok; i++) {
+        cb_wave& w = waves[i]; w = cb_wave{};
+        w.kind = r.get<int32_t>(); w.has_dc = r.get<int32_t>(); w.dc = r.get<cb_pref>(); w.npts = r.get<int32_t>();
+        if (w.npts < 0) { r.ok = false; break; }
+        r.vec(wt[i], (size_t)w.npts); r.vec(wy[i], (size_t)w.npts);
+        for (int k = 0; k < 7; k++) w.v[k] = r.get<cb_pref>();
+        w.ac_mag = r.get<double>();
+        w.t = wt[i].data(); w.y = wy[i].data();
+    }
+    std::vector<cb_va_model> models((size_t)fc.n_va_models);
+    std::vector<std::string> mname((size_t)fc.n_va_models);
+    std::vector<std::vector<int32_t>> mjr(models.size()), mjc(models.size()), mnp(models.size()), mnn(models.size());
+    for (size_t i = 0; i < models.size() && r.ok; i++) {
+        cb_va_model& m = models[i]; m = cb_va_model{};
+        std::vector<char> nm; r.vec(nm, r.get<uint32_t>()); mname[i].assign(nm.begin(), nm.end());
+        m.nterm = r.get<int32_t>(); m.nparam = r.get<int32_t>(); m.ncache = r.get<int32_t>(); m.nj = r.get<int32_t>();
+        if (m.nterm < 0 || m.nparam < 0 || m.nj < 0) { r.ok = false; break; }
+        r.vec(mjr[i], (size_t)m.nj); r.vec(mjc[i], (size_t)m.nj);
+        m.n_noise = r.get<int32_t>(); m.ncache_n = r.get<int32_t>();
+        if (m.n_noise < 0) { r.ok = false; break; }
+        r.vec(mnp[i], (size_t)m.n_noise); r.vec(mnn[i], (size_t)m.n_noise);
+        m.linear = r.get<int32_t>();
+        m.name = mname[i].c_str(); m.jrow = mjr[i].data(); m.jcol = mjc[i].data(); m.noise_pos = mnp[i].data(); m.noise_neg = mnn[i].data();
+    }
+    std::vector<cb_va_inst> insts((size_t)fc.n_va_insts);
+    std::vector<std::vector<int32_t>> it(insts.size());
+    std::vector<std::vector<cb_pref>> ip(insts.size());
+    std::vector<std::vector<uint8_t>> ig(insts.size());
+    for (size_t i = 0; i < insts.size() && r.ok; i++) {
+        cb_va_inst& v = insts[i]; v = cb_va_inst{};
+        v.model = r.get<int32_t>();
+        if (v.model < 0 || v.model >= fc.n_va_models) { r.ok = false; break; }
+        r.vec(it[i], (size_t)models[v.model].nterm); r.vec(ip[i], (size_t)models[v.model].nparam); r.vec(ig[i], (size_t)models[v.model].nparam);
+        v.mult = r.get<double>();
+        v.term = it[i].data(); v.par = ip[i].data(); v.given = ig[i].data();
+    }
+    std::vector<int32_t> outs; r.vec(outs, (size_t)fc.n_outputs);
+    const uint64_t slen = r.get<uint64_t>();
+    std::vector<char> src; r.vec(src, (size_t)slen);
+    if (!r.ok) return fail(CB_ERR_INVALID, "flatckt: truncated or corrupt file");
+    fc.devices = devs.data(); fc.waves = waves.data(); fc.va_models = models.data(); fc.va_insts = insts.data(); fc.outputs = outs.data();
+    cb_circuit* c = nullptr;
+    int rc = cb_circuit_create(&fc, &c);
+    if (rc != CB_OK) return rc;
+    if (!src.empty()) c->cuda_source.assign(src.data(), src.size());
+    *out = c;
     return CB_OK;
 }
 
@@ -824,7 +947,9 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         return fail(CB_ERR_NO_DEVICE, "no CUDA device available; this engine has no CPU fallback");
     if (device_id < 0 || device_id >= ndev) return fail(CB_ERR_INVALID, "device id out of range");
     CUDA_TRY(cudaSetDevice(device_id));
-    auto p = std::make_unique<cb_plan>();
+    // an error return below releases the streams, events and device allocations made so far
+    struct PlanDeleter { void operator()(cb_plan* q) const { cb_plan_destroy(q); } };
+    std::unique_ptr<cb_plan, PlanDeleter> p(new cb_plan());
     p->c = c; p->B = n_inst; p->device = device_id;
     const long long B = n_inst;
     const int N = c->N;
@@ -1220,6 +1345,7 @@ static int run_setup(cb_plan* p, const cb_options* opt) {
     }
     p->setup_valid = true;
     p->setupv_valid = false;
+    p->setupn_valid = false;   // the noise variant's cache depends on temp / gmin as well
     p->last_temp = opt->temp; p->last_gmin = opt->gmin;
     return CB_OK;
 }
@@ -1240,16 +1366,18 @@ static int run_setupv(cb_plan* p, const cb_options* opt) {
     return CB_OK;
 }
 
-static void collect_breakpoints(const cb_circuit* c, double t0, double t1, std::vector<double>& out) {
+static int collect_breakpoints(const cb_circuit* c, double t0, double t1, std::vector<double>& out) {
     std::vector<double> bp;
     for (const WaveH& w : c->waves) {
+        if (w.kind == CB_W_PULSE && w.v[6].value > 0.0 && std::isfinite(w.v[6].value) && t1 / w.v[6].value > 4e6)
+            return fail(CB_ERR_INVALID, "PULSE period gives more than 4e6 periods (16e6 breakpoints) inside the transient span");
         if (w.kind == CB_W_PWL) for (double t : w.t) bp.push_back(t);
         else if (w.kind == CB_W_PULSE) {
             const double td = w.v[2].value, tr = w.v[3].value, tf = w.v[4].value, pw = w.v[5].value, per = w.v[6].value;
             const double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
             for (int k = 0; k < 4; k++) {
                 if (!std::isfinite(ts[k])) continue;
-                if (std::isinf(per)) bp.push_back(ts[k]);
+                if (!(per > 0.0) || std::isinf(per)) bp.push_back(ts[k]);
                 else for (double base = 0.0; base + ts[k] <= t1; base += per) bp.push_back(base + ts[k]);
             }
         } else if (w.kind == CB_W_SIN) bp.push_back(w.v[3].value);
@@ -1263,6 +1391,7 @@ static void collect_breakpoints(const cb_circuit* c, double t0, double t1, std::
         if (!out.empty() && b - out.back() <= tiny) continue;
         out.push_back(b);
     }
+    return CB_OK;
 }
 
 static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, double t1, const double* saveat,
@@ -1322,7 +1451,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         if (nsave > 0)
             CUDA_TRY(cudaMemcpyAsync(p->d_saveat, saveat, nsave * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         std::vector<double> bp;
-        collect_breakpoints(c, t0, t1, bp);
+        { const int rcb = collect_breakpoints(c, t0, t1, bp); if (rcb != CB_OK) return rcb; }
         if (bp.size() > p->bp_capacity) {
             if (p->d_bp) cudaFree(p->d_bp);
             CUDA_TRY(cudaMalloc((void**)&p->d_bp, std::max<size_t>(1, bp.size()) * sizeof(double)));
@@ -1938,6 +2067,7 @@ extern "C" int cb_plan_set_x0(cb_plan* p, const double* x0, int per_point) {
 
 extern "C" int cb_dc(cb_plan* p, const cb_options* opt, double* x_out, double* x_full, int32_t* status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return dc1(p, opt, x_out, x_full, status, stats, p->B);
     int rc = scatter_params(p);
     if (rc != CB_OK) return rc;
@@ -1953,6 +2083,7 @@ extern "C" int cb_dc(cb_plan* p, const cb_options* opt, double* x_out, double* x
 extern "C" int cb_tran(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save, const cb_options* opt,
                        double* y_out, int32_t* status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return tran1(p, t0, t1, saveat, n_save, opt, y_out, status, stats, p->B);
     int rc = scatter_params(p);
     if (rc != CB_OK) return rc;
@@ -1993,6 +2124,7 @@ static int gather_device(cb_plan* p, size_t rows, bool tran, double** d_out, int
 
 extern "C" int cb_dc_device(cb_plan* p, const cb_options* opt, double** d_x_out, int32_t** d_status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return dc_device1(p, opt, d_x_out, d_status, stats);
     int rc = scatter_params(p);
     if (rc != CB_OK) return rc;
@@ -2006,6 +2138,7 @@ extern "C" int cb_dc_device(cb_plan* p, const cb_options* opt, double** d_x_out,
 extern "C" int cb_tran_device(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save,
                               const cb_options* opt, double** d_y_out, int32_t** d_status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return tran_device1(p, t0, t1, saveat, n_save, opt, d_y_out, d_status, stats);
     int rc = scatter_params(p);
     if (rc != CB_OK) return rc;
@@ -2019,6 +2152,7 @@ extern "C" int cb_tran_device(cb_plan* p, double t0, double t1, const double* sa
 static int small_signal_lanes(cb_plan* p, bool noise, const double* freqs, int64_t F, const cb_options* opt, double* out,
                               int32_t* status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return small_signal(p, noise, freqs, F, opt, out, status, stats, p->B);
     int rc = scatter_params(p);
     if (rc != CB_OK) return rc;

@@ -21,7 +21,7 @@ CUBIN_CACHE = os.path.join(_HERE, os.environ.get("CB_GEN_DIR", "_gen"), "cubin")
 _lib = None
 
 SYMBOLS = [
-    "cb_version", "cb_last_error", "cb_options_default", "cb_circuit_create", "cb_circuit_set_cuda_source",
+    "cb_version", "cb_last_error", "cb_options_default", "cb_options_size", "cb_stats_size", "cb_options_init", "cb_circuit_create", "cb_circuit_load", "cb_circuit_set_cuda_source",
     "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_create_lanes", "cb_plan_lanes", "cb_plan_set_params", "cb_dc", "cb_tran",
     "cb_ac", "cb_noise", "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
 ]
@@ -44,6 +44,12 @@ def load() -> C.CDLL:
         lib.cb_plan_destroy.restype = None
         lib.cb_circuit_destroy.restype = None
         lib.cb_options_default.restype = None
+        lib.cb_options_size.restype = C.c_size_t
+        lib.cb_stats_size.restype = C.c_size_t
+        # layout guard: this binding's mirrors of the option / statistics structs must be the library's
+        if lib.cb_options_size() != C.sizeof(F.cb_options) or lib.cb_stats_size() != C.sizeof(F.cb_stats):
+            raise EngineError(-101, f"{LIB_PATH}: struct layout mismatch (cb_options {lib.cb_options_size()} vs "
+                              f"{C.sizeof(F.cb_options)} bytes, cb_stats {lib.cb_stats_size()} vs {C.sizeof(F.cb_stats)}); rebuild the library")
         _lib = lib
     return _lib
 
@@ -55,7 +61,7 @@ def _check(rc: int):
 
 def default_options(**kw) -> F.cb_options:
     o = F.cb_options()
-    load().cb_options_default(C.byref(o))
+    _check(load().cb_options_init(C.byref(o), C.c_size_t(C.sizeof(o))))
     for k, v in kw.items():
         if k in ("temp", "gmin"):
             setattr(o, k, F._pref(v))

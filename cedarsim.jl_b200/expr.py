@@ -178,7 +178,7 @@ def free_vars(e, out=None):
     if k == "var":
         if e[1] not in _CONSTS:
             out.add(e[1])
-    elif k in ("neg", "not"):
+    elif k in ("neg", "not", "inv"):
         free_vars(e[1], out)
     elif k == "bin":
         free_vars(e[2], out)

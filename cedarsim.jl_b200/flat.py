@@ -103,6 +103,8 @@ class cb_flat_circuit(C.Structure):
 
 class cb_options(C.Structure):
     _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("abi_version", C.c_uint32),
         ("temp", cb_pref),
         ("gmin", cb_pref),
         ("reltol", C.c_double),
@@ -124,6 +126,11 @@ class cb_options(C.Structure):
         ("skip_dc", C.c_int32),
         ("nr_rate_test", C.c_int32),
         ("value_rounds", C.c_int32),
+        ("mixed_rounds", C.c_int32),
+        ("source_steps", C.c_int32),
+        ("t0_reinit", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("pivot_growth_max", C.c_double),
     ]
 
 
@@ -144,6 +151,8 @@ class cb_stats(C.Structure):
         ("full_iters", C.c_int64),
         ("evalv_seconds", C.c_double),
         ("newtonv_seconds", C.c_double),
+        ("pivot_fallbacks", C.c_int64),
+        ("dc_source_stepped", C.c_int64),
     ]
 
     def as_dict(self):
@@ -415,6 +424,11 @@ class FlatCircuit:
                 for k in range(2, 7):
                     if isinstance(vv[k], Col):
                         raise ValueError("PULSE timing parameters cannot be swept (shared breakpoints)")
+                # a period <= 0 means "no period" (one pulse), as in SPICE; fmod(t, 0) would be NaN
+                if not float(vv[6]) > 0.0:
+                    vv[6] = math.inf
+                if any(not (0.0 <= float(vv[k]) < math.inf) for k in range(2, 6)):
+                    raise ValueError("PULSE td / tr / tf / pw must be finite and >= 0")
             elif w.kind == W_SIN:
                 dflt = [0.0, 0.0, 1.0, 0.0, 0.0, 0.0, math.inf]
                 vv = vv + dflt[len(vv):]
@@ -497,3 +511,47 @@ def params_matrix(cols: Sequence[np.ndarray]) -> np.ndarray:
     if len(cols) == 0:
         return np.zeros((0, 0))
     return np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.float64) for c in cols], axis=0))
+
+
+def save_flatckt(fc: "FlatCircuit", models: Sequence, path: str) -> None:
+    """Write `fc` and the generated CUDA C of its Verilog-A `models` (va.compiler.CompiledModel) as a "flatckt" file,
+    the input of cb_circuit_load (include/cedarb200.h): what a binding without a front end of its own hands to the
+    engine (ext/CedarSimB200Ext.jl).  Layout: see cb_circuit_load in csrc/cedarb200.cu."""
+    import struct as S
+    from . import engine
+    pk = fc.pack()
+    f = pk.struct
+    out = [b"CBFC", S.pack("<I", 1),
+           S.pack("<8i", f.n_unknowns, f.n_nodes, f.n_params, f.n_devices, f.n_waves, f.n_va_models, f.n_va_insts, f.n_outputs)]
+    raw = lambda obj: bytes(memoryview(obj).cast("B")) if not isinstance(obj, C.Structure) else C.string_at(C.addressof(obj), C.sizeof(obj))  # noqa: E731
+    for i in range(f.n_devices):
+        out.append(raw(f.devices[i]))
+    for i in range(f.n_waves):
+        w = f.waves[i]
+        out += [S.pack("<2i", w.kind, w.has_dc), raw(w.dc), S.pack("<i", w.npts if w.kind == W_PWL else 0)]
+        if w.kind == W_PWL:
+            out.append(S.pack(f"<{w.npts}d", *[w.t[k] for k in range(w.npts)]))
+            out += [raw(w.y[k]) for k in range(w.npts)]
+        out += [raw(w.v[k]) for k in range(7)]
+        out.append(S.pack("<d", w.ac_mag))
+    for i in range(f.n_va_models):
+        m = f.va_models[i]
+        out += [S.pack("<I", len(m.name)), m.name, S.pack("<4i", m.nterm, m.nparam, m.ncache, m.nj),
+                S.pack(f"<{m.nj}i", *[m.jrow[k] for k in range(m.nj)]), S.pack(f"<{m.nj}i", *[m.jcol[k] for k in range(m.nj)]),
+                S.pack("<2i", m.n_noise, m.ncache_n),
+                S.pack(f"<{m.n_noise}i", *[m.noise_pos[k] for k in range(m.n_noise)]),
+                S.pack(f"<{m.n_noise}i", *[m.noise_neg[k] for k in range(m.n_noise)]), S.pack("<i", m.linear)]
+    for i in range(f.n_va_insts):
+        v = f.va_insts[i]
+        m = f.va_models[v.model]
+        out += [S.pack("<i", v.model), S.pack(f"<{m.nterm}i", *[v.term[k] for k in range(m.nterm)])]
+        out += [raw(v.par[k]) for k in range(m.nparam)]
+        out += [bytes(bytearray(v.given[k] for k in range(m.nparam))), S.pack("<d", v.mult)]
+    out.append(S.pack(f"<{f.n_outputs}i", *[f.outputs[k] for k in range(f.n_outputs)]))
+    src = b""
+    if fc.va_models:
+        by_name = {cm.name: cm for cm in models}
+        src = engine.cuda_source([by_name[m.name] for m in fc.va_models]).encode()
+    out += [S.pack("<Q", len(src)), src]
+    with open(path, "wb") as fh:
+        fh.write(b"".join(out))

@@ -97,7 +97,7 @@ double wave_tran(const Inst& in, const cb_wave& w, double t) {
                    tf = in.pv(w.v[4]), pw = in.pv(w.v[5]), per = in.pv(w.v[6]);
             double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
             double ys[4] = {v1, v2, v2, v1};
-            double tt = std::isinf(per) ? t : std::fmod(t, per);
+            double tt = (std::isinf(per) || !(per > 0.0)) ? t : std::fmod(t, per);   // per <= 0: one pulse (SPICE)
             return pwl_at_time(ts, ys, 4, tt);
         }
         case CB_W_SIN: {  // src/spectre_env.jl:169-176
@@ -129,7 +129,7 @@ void collect_breakpoints(const cb_flat_circuit* fc, double t0, double t1, std::v
             double ts[4] = {td, td + tr, td + tr + pw, td + tr + pw + tf};
             for (int k = 0; k < 4; k++) {
                 if (!std::isfinite(ts[k])) continue;
-                if (std::isinf(per)) {
+                if (std::isinf(per) || !(per > 0.0) || t1 / per > 4e6) {
                     bp.push_back(ts[k]);
                 } else {
                     for (double base = 0.0; base + ts[k] <= t1; base += per) bp.push_back(base + ts[k]);
@@ -596,6 +596,8 @@ extern "C" {
 
 void orc_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
+    o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
+    o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e8;
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
