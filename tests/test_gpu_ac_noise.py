@@ -92,3 +92,21 @@ def test_dff_noise_vs_oracle(host_bsimcmg):
     assert st.max() == 0 and so.max() == 0 and st2.max() == 0
     assert np.all(np.abs(psd - po) <= 1e-6 * po + 1e-40)
     assert np.all(np.abs(y - yo) <= 1e-6 * np.abs(yo) + 1e-20)
+
+
+def test_noise_twice_on_one_plan_with_different_temperature(host_bsimcmg):
+    """The noise variant's per-instance cache depends on temp: a second cb_noise on the same plan at another temperature
+    must refill it (round-1 advisor finding: it kept the old-temperature cache)."""
+    fl = netlist.flatten(netlist.parse_netlist(BSIMCMG_INVERTER), None, outputs=["q"], host=True)
+    f = acdec(2, 1e3, 1e9)
+    plan = engine.Circuit(fl.fc, fl.models).plan(1)
+    plan.set_params(None)
+    res = {}
+    for temp in (27.0, 85.0, 27.0):
+        psd, st, _ = plan.noise(f, engine.default_options(temp=temp))
+        assert st.max() == 0
+        po, _ = orc.noise(fl.fc, f, None, opts=orc.default_options(temp=temp))
+        assert np.all(np.abs(psd - po) <= 1e-6 * po), temp
+        res.setdefault(temp, []).append(psd)
+    assert np.array_equal(res[27.0][0], res[27.0][1])
+    assert np.abs(res[85.0][0] / res[27.0][0] - 1).max() > 0.05     # the two temperatures do differ
