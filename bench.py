@@ -5,14 +5,17 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm on the box's host cores
 
 One "step" = one full pass of the hot path over one batch: DC operating point + adaptive
-transient (0 .. 600 ns, LTE-controlled trapezoidal) of B = 16 384 Monte-Carlo instances of the
-30-FET D flip-flop per GPU (BASELINE.json configs[2]; GF180/BSIM4 are not in the reference tree,
-so the same topology runs on BSIM-CMG 107 + ASAP7 cards -- SURVEY.md fact 5).
+transient (0 .. 600 ns, LTE-controlled trapezoidal) of the 16 384 Monte-Carlo instances of the
+30-FET D flip-flop (BASELINE.json configs[2] as written: 16 384 instances TOTAL at 1/2/4/8 GPUs, i.e.
+STRONG scaling; GF180/BSIM4 are not in the reference tree, so the same topology runs on BSIM-CMG 107 +
+ASAP7 cards -- SURVEY.md fact 5).
 
 `value` is timed with inputs resident in HBM and results left in HBM; `e2e` goes through the
 C-ABI calls with pinned host buffers (H2D of the parameter matrix and D2H of all waveforms inside
-the timed region).  Under torchrun every rank runs its own block of sweep points (no data-path
-collective, weak scaling) and rank 0 gathers the waveforms over NCCL.
+the timed region).  Under torchrun rank r owns the contiguous block [r B/N, (r+1) B/N) of the same 16 384 draws (no
+data-path collective) and rank 0 gathers the waveforms over NCCL.  Extra legs on the same JSON line: `fixed_step`
+(config 3's second timing mode, dt = 25 ps), `weak` (N > 1: 16 384 points per GPU), `compile_seconds` (N = 1: cold
+NVRTC + symbolic analysis; the Verilog-A code generation time recorded at build()).
 """
 import argparse
 import ctypes
@@ -31,7 +34,9 @@ sys.path.insert(0, ROOT)
 
 DFF_NODESET = dict(q=0.0, q_neg=0.7, net0=0.0, net7=0.0, vdd=0.7, clkn=0.7, ncki=0.0, cki=0.7)
 T0, T1, NSAVE = 0.0, 6e-7, 1801
-POINTS_PER_GPU = 16384
+TOTAL_POINTS = 16384          # BASELINE config 3: instances in the whole job, whatever the number of GPUs
+POINTS_PER_GPU = TOTAL_POINTS   # weak-scaling leg and the single-GPU case
+FIXED_DT = 25e-12             # config 3's fixed-step comparison mode
 # SURVEY.md 8(d) config 3, adaptive mode: reltol 1e-4, abstol 1e-6 V / 1e-12 A.  Newton tolerance = 0.1 x the LTE
 # tolerance with the contraction-rate acceptance test (Sundials IDA, the reference's solver, uses 0.33 x and the same
 # test); the CPU arm runs the same options.  value_rounds is the engine's chord-iteration schedule.
@@ -85,28 +90,44 @@ class DevArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def cpu_arm(points, threads):
-    """The CPU restatement (oracle, kind 'port') on `points` sweep points with `threads` host threads."""
+def cpu_arm(points, threads, fast=True):
+    """The CPU restatement on `points` sweep points with `threads` host threads.
+    fast=True : `cpu_fast` -- same equations and step control, static-pivot sparse LU (the engine's symbolic analysis),
+                -O3 -march=native for the solver and the generated device models: the honest CPU baseline.
+    fast=False: the CHECKER as it is used in the parity tests (dense partial-pivoting LU, -O2, no FP contraction)."""
     from cedarsim.jl_b200 import circuits
     from oracle import orc
-    fc, _ = circuits.dff(host=True)
-    P = circuits.dff_mc_params(fc, points)
-    orc.set_x0(nodeset(fc))
-    ts = np.linspace(T0, T1, NSAVE)
-    t = time.perf_counter()
-    y, st, stats = orc.tran(fc, T0, T1, ts, params=P, opts=orc.default_options(**OPTS), nthreads=threads)
-    el = time.perf_counter() - t
-    orc.set_x0(None)
-    return el, stats, int((st == 0).sum())
+
+    def run():
+        fc, _ = circuits.dff(host=("fast:" + orc.cpu_tag()) if fast else True)
+        P = circuits.dff_mc_params(fc, TOTAL_POINTS)[:, :points]
+        P = np.ascontiguousarray(P)
+        orc.set_x0(nodeset(fc))
+        ts = np.linspace(T0, T1, NSAVE)
+        t = time.perf_counter()
+        y, st, stats = orc.tran(fc, T0, T1, ts, params=P, opts=orc.default_options(**OPTS), nthreads=threads)
+        el = time.perf_counter() - t
+        orc.set_x0(None)
+        return el, stats, int((st == 0).sum())
+    if fast:
+        with orc.fast_arm():
+            return run()
+    return run()
+
+
+def cpu_sample_points(threads):
+    return max(threads * 32, 256)   # ~15-30 s of CPU work per step on the box's host cores (fast arm)
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation cannot run here (Julia, un-vendored packages), so this is
+    the CPU restatement at its fastest (`cpu_fast`) on all host threads, on a bounded sample of the same draws."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    points = max(threads * 16, 64)   # ~10 s of CPU work per step on the box's host cores
-    for _ in range(args.warmup):
-        cpu_arm(points, threads)
+    points = cpu_sample_points(threads)
+    for _ in range(min(args.warmup, 1)):   # builds the -march=native libraries on first use
+        cpu_arm(min(points, threads * 4), threads)
     t = time.perf_counter()
     iters = 0
     for _ in range(args.steps):
@@ -117,13 +138,23 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": "transient sweep points/s (DFF Monte-Carlo)", "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_per_step": points},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_step": points, "total_points": TOTAL_POINTS},
         "newton_iters_per_s": iters / el,
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"{points} of the {POINTS_PER_GPU} Monte-Carlo points per step, same tolerances and outputs"},
+                         "arm": "cpu_fast: sparse static-pivot LU, -O3 -march=native, OpenMP over points",
+                         "sample": f"the first {points} of the {TOTAL_POINTS} Monte-Carlo points per step, same tolerances and outputs"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def codegen_seconds(ms):
+    """Verilog-A -> CUDA C generation time of the models, recorded when build() generated them (the model sources are
+    not on the GPU box)."""
+    try:
+        return float(sum(getattr(cm, "codegen_seconds", 0.0) for cm in ms))
+    except TypeError:
+        return None
 
 
 def main():
@@ -132,8 +163,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--points", type=int, default=POINTS_PER_GPU, help="sweep points per GPU")
+    ap.add_argument("--points", type=int, default=0, help="sweep points per GPU (default: 16384 / number of GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the fixed-step, weak-scaling and cold-compile legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,14 +184,12 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.points
+    B = args.points or TOTAL_POINTS // world            # strong scaling: the job is 16 384 points whatever N is
     fc, ms = circuits.dff()
     circuit = engine.Circuit(fc, ms)
     plan = circuit.plan(B, device=local)
-    # per-rank Monte-Carlo draws: rank r owns sweep points [r*B, (r+1)*B)
-    P_all = circuits.dff_mc_params(fc, B * world)
+    P_all = circuits.dff_mc_params(fc, max(TOTAL_POINTS, B * world))
     P = np.ascontiguousarray(P_all[:, rank * B:(rank + 1) * B])
-    del P_all
     ts = np.linspace(T0, T1, NSAVE)
     opts = engine.default_options(**OPTS, **ENGINE_OPTS)
     plan.set_x0(nodeset(fc))
@@ -172,31 +202,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_buf = [torch.empty((O, NSAVE, B), dtype=torch.float64, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    def step_resident():
-        dy, ds, st = plan.tran_device(T0, T1, ts, opts)
-        if world > 1:   # final waveforms to rank 0 over NVLink (NCCL); no collective on the solve path
-            y = torch.as_tensor(DevArray(dy, (O, NSAVE, B)), device="cuda")
-            dist.gather(y, gather_buf, dst=0)
-        return st
+    def resident_leg(pl, Bl, o, warm, steps, sample_clocks=False):
+        """`steps` timed passes of plan `pl` (Bl points per GPU), inputs and results in HBM, waveforms gathered on rank 0."""
+        gbuf = [torch.empty((O, NSAVE, Bl), dtype=torch.float64, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    tot = {"newton_iters": 0, "kernel_launches": 0, "eval_seconds": 0.0, "newton_seconds": 0.0, "solve_seconds": 0.0,
-           "steps_accepted": 0, "steps_rejected": 0, "rounds": 0, "value_rounds": 0, "full_iters": 0, "evalv_seconds": 0.0,
-           "newtonv_seconds": 0.0}
-    for _ in range(args.steps):
-        st = step_resident()
-        for k in tot:
-            tot[k] += st[k]
-    barrier()
-    el = time.perf_counter() - t0
-    sampler.stop_flag.set()
+        def step():
+            dy, ds, st = pl.tran_device(T0, T1, ts, o)
+            if world > 1:   # final waveforms to rank 0 over NVLink (NCCL); no collective on the solve path
+                dist.gather(torch.as_tensor(DevArray(dy, (O, NSAVE, Bl)), device="cuda"), gbuf, dst=0)
+            return st
+        for _ in range(warm):
+            step()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        tot = {}
+        for _ in range(steps):
+            st = step()
+            for k, v in st.items():
+                tot[k] = tot.get(k, 0) + v
+        barrier()
+        el = allmax(time.perf_counter() - t0)
+        if sampler:
+            sampler.stop_flag.set()
+        return el, tot, sampler
+
+    el, tot, sampler = resident_leg(plan, B, opts, args.warmup, args.steps, sample_clocks=True)
     # ---- per-kernel timing for the roofline: the same step on a single-lane plan with CUDA events around every launch
     # (in the timed region above the plan's lanes run concurrently, so a kernel's launch duration there includes the
     # SMs it shares with other lanes' kernels; timed alone it is the figure the roofline peak is quoted for)
@@ -213,9 +253,6 @@ def main():
               "newton_iters"):
         tot[k + "_1"] = st1[k]
     if world > 1:
-        tmax = torch.tensor([el, tot["solve_seconds"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        el = float(tmax[0])
         sums = torch.tensor([tot["newton_iters"], tot["kernel_launches"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(sums)
         newton_all, launches_all = float(sums[0]), float(sums[1])
@@ -233,17 +270,37 @@ def main():
         plan.set_params(P_host)
         y_host, status, _ = plan.tran(T0, T1, ts, opts, out=y_host)
     barrier()
-    el_e2e = time.perf_counter() - t0
-    if world > 1:
-        tmax = torch.tensor([el_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        el_e2e = float(tmax[0])
+    el_e2e = allmax(time.perf_counter() - t0)
     ok_points = int((status == 0).sum())
     q_known = [float(np.abs(y_host[0, int(round(tt / T1 * (NSAVE - 1)))] - want).max())
                for tt, want in ((1.5e-7, 0.0), (2.5e-7, 0.0), (4.5e-7, 0.7), (5.5e-7, 0.7))]
 
+    # ---- config 3's second timing mode: fixed step, dt = 25 ps (24 000 steps per point), one timed pass
+    fixed = None
+    if not args.no_extra_legs:
+        fopts = engine.default_options(**OPTS, **ENGINE_OPTS, fixed_step=1, dt=FIXED_DT)
+        elf, totf, _ = resident_leg(plan, B, fopts, 0, 1)
+        fixed = {"value": B * world / elf, "unit": "points/s", "dt": FIXED_DT, "ms_per_step": 1e3 * elf, "steps": 1,
+                 "rounds": totf["rounds"],
+                 "newton_iters_per_point": totf["newton_iters"] / B, "accepted_steps_per_point": totf["steps_accepted"] / B}
+    # ---- weak scaling next to the strong-scaling headline: 16 384 points on EVERY GPU
+    weak = None
+    if world > 1 and not args.no_extra_legs and not args.points:
+        planw = circuit.plan(POINTS_PER_GPU, device=local)
+        planw.set_x0(nodeset(fc))
+        planw.set_params(np.ascontiguousarray(circuits.dff_mc_params(fc, POINTS_PER_GPU, seed=20240607 + rank)))
+        elw, _, _ = resident_leg(planw, POINTS_PER_GPU, opts, 1, 2)
+        planw.close()
+        weak = {"value": 2 * POINTS_PER_GPU * world / elw, "unit": "points/s", "points_per_gpu": POINTS_PER_GPU, "steps": 2,
+                "ms_per_step": 1e3 * elw / 2}
+    # ---- compile latency (north star: reported separately): cold NVRTC + symbolic analysis, no cubin cache
+    compile_s = None
+    if rank == 0 and world == 1 and not args.no_extra_legs:
+        compile_s = {"nvrtc_and_symbolic_cold": engine.Circuit(fc, ms, cache_dir=None).compile_seconds,
+                     "with_cubin_cache": circuit.compile_seconds, "verilog_a_codegen_at_build": codegen_seconds(ms)}
+
     if rank == 0:
-        # ---- roofline of the dominant kernel (device evaluation, FP64-pipe bound: SURVEY.md 8(d))
+        # ---- roofline of the dominant kernel (device evaluation): both roofs, the binding one is the slower floor
         flops_per_eval = float(np.mean([sum(cm.exec_ops) for cm in ms])) if all(getattr(cm, "exec_ops", None) for cm in ms) else None
         n_fets = len(fc.va_insts)
         fp64_peak = engine.measure_fp64_peak(local)
@@ -253,6 +310,7 @@ def main():
                 peaks = json.load(f)
         except OSError:
             pass
+        hbm_peak = float(peaks.get("hbm_gbs") or 6557.8)   # fallback: the figure of B200_PROFILING.md's recipe on this pool
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
@@ -261,37 +319,55 @@ def main():
             pass
         ev, nw = tot["eval_seconds_1"], tot["newton_seconds_1"]
         solve1 = max(tot["solve_seconds_1"], 1e-30)
-        # k_eval_* runs in the full rounds only: full_iters point-iterations x FETs device evaluations
-        achieved = (tot["full_iters_1"] * n_fets * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
-        roofline = {"bound": "fp64", "kernel": "k_eval_bsimcmg107_*", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
-                    "peak_source": "FP64 DFMA microbenchmark run live in this process (MEASURED_PEAKS.json has no FP64 figure; its "
-                                   f"hbm_gbs = {peaks.get('hbm_gbs')} is the denominator for the HBM-bound k_lu / k_control)",
+        # k_eval_* runs in the full iterations only: full_iters point-iterations x FETs device evaluations.
+        # Algorithmic bytes per evaluation: the per-instance cache row (ncache slots), the terminal voltages, the outputs
+        # (I, Q per terminal; J and C per Jacobian entry).
+        evals = tot["full_iters_1"] * n_fets
+        bytes_per_eval = float(np.mean([8 * (cm.ncache + len(cm.terminals) + 2 * len(cm.terminals) + 2 * len(cm.jrow)) for cm in ms]))
+        tf = (evals * flops_per_eval / ev / 1e12) if (flops_per_eval and ev > 0) else None
+        gbs = evals * bytes_per_eval / ev / 1e9 if ev > 0 else None
+        frac_fp64 = tf / fp64_peak if tf else None
+        frac_hbm = gbs / hbm_peak if gbs else None
+        bound = "hbm" if (frac_hbm or 0) > (frac_fp64 or 0) else "fp64"
+        roofline = {"bound": bound, "kernel": "k_eval_bsimcmg107_*",
+                    "achieved": gbs if bound == "hbm" else tf, "peak": hbm_peak if bound == "hbm" else fp64_peak,
+                    "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": frac_hbm if bound == "hbm" else frac_fp64,
+                    "traffic": traffic,
+                    "fp64": {"achieved_tflops": tf, "peak_tflops": fp64_peak, "frac": frac_fp64, "flops_per_device_eval": flops_per_eval},
+                    "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": frac_hbm, "bytes_per_device_eval": bytes_per_eval},
+                    "peak_source": "fp64: DFMA microbenchmark run live in this process (MEASURED_PEAKS.json has no FP64 figure); "
+                                   f"hbm: MEASURED_PEAKS.json hbm_gbs = {peaks.get('hbm_gbs')}; the binding roof is the one with the larger fraction",
                     "how": "one extra step of the same workload on a single-lane plan with CUDA events around every launch "
                            "(kernels timed alone); the timed region runs the plan's lanes concurrently",
-                    "flops_per_device_eval": flops_per_eval, "device_evals": tot["full_iters_1"] * n_fets,
-                    "kernel_seconds": ev, "share_of_step": ev / solve1, "single_lane_step_seconds": solve1,
+                    "device_evals": evals, "kernel_seconds": ev, "share_of_step": ev / solve1, "single_lane_step_seconds": solve1,
                     "k_lu_control_seconds": nw, "k_lu_control_share": nw / solve1,
                     "value_rounds": {"rounds": tot["value_rounds_1"], "of_rounds": tot["rounds_1"],
                                      "point_iterations": tot["newton_iters_1"] - tot["full_iters_1"],
                                      "k_evalv_seconds": tot["evalv_seconds_1"], "k_lu_solve_control_seconds": tot["newtonv_seconds_1"],
                                      "share_of_step": (tot["evalv_seconds_1"] + tot["newtonv_seconds_1"]) / solve1}}
         cpu = None
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            pts = max(threads * 16, 64)   # a bounded sample: ~10 s of CPU work
+            pts = cpu_sample_points(threads)
+            cpu_arm(threads * 2, threads)        # builds the -march=native libraries on first use, untimed
             cel, cstats, cok = cpu_arm(pts, threads)
+            dpts = max(threads * 4, 32)
+            del_, dstats, _ = cpu_arm(dpts, threads, fast=False)
             cpu = {"value": pts / cel, "unit": "points/s", "cores": threads, "kind": "port",
-                   "sample": f"{pts} of the {B} Monte-Carlo points, same tolerances and outputs, {cel:.1f}s",
-                   "newton_iters_per_s": cstats["newton_iters"] / cel}
+                   "arm": "cpu_fast: same equations / step control, static-pivot sparse LU (engine's symbolic analysis), -O3 -march=native, OpenMP over points",
+                   "sample": f"the first {pts} of the {TOTAL_POINTS} Monte-Carlo points, same tolerances and outputs, {cel:.1f}s",
+                   "newton_iters_per_s": cstats["newton_iters"] / cel,
+                   "checker_dense": {"value": dpts / del_, "unit": "points/s", "sample": f"{dpts} points, {del_:.1f}s",
+                                     "note": "the parity checker as the tests use it: dense partial-pivoting LU, -O2, no FP contraction"}}
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps({
             "metric": "transient sweep points/s (DFF Monte-Carlo)", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu": B, "unknowns": fc.n_unknowns, "fets": n_fets, "swept_params": len(fc.param_names), "lanes_per_gpu": plan.lanes,
-                       "l2": "per-round working set (cached device constants + device outputs, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "scaling": "strong" if not args.points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "total_points": B * world, "points_per_gpu": B, "unknowns": fc.n_unknowns, "fets": n_fets,
+                       "swept_params": len(fc.param_names), "lanes_per_gpu": plan.lanes, "engine_options": ENGINE_OPTS,
+                       "l2": "per-round working set (cached device constants + device outputs, > 1 GB at 16 384 points) exceeds the 126 MB L2; no explicit flush"},
             "newton_iters_per_s": newton_all / el, "newton_iters_per_step": newton_all / args.steps,
             "lu": circuit.lu_info(),
             "e2e": {"value": args.steps * B * world / el_e2e, "unit": "points/s", "h2d_bytes_per_step": int(P.nbytes + ts.nbytes),
@@ -299,6 +375,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": sampler.summary(),
             "roofline": roofline, "cpu_baseline": cpu,
+            "fixed_step": fixed, "weak": weak, "compile_seconds": compile_s,
             "parity_check": {"converged_points": ok_points, "of": B, "max_abs_q_error_vs_known_pattern_V": max(q_known)},
         }), flush=True)
         os.dup2(2, 1)

@@ -25,7 +25,8 @@ def _model(fc: FlatCircuit, card: str, host: bool, used: list) -> int:
         used.append(cm)
     if host:
         from .va.build import build_host
-        shape = build_host(cm).shape()
+        # host="fast:<cpu tag>": the -O3 -march=native build of bench.py's cpu_fast baseline arm (not the checker's)
+        shape = build_host(cm, fast_tag=host.split(":", 1)[1] if isinstance(host, str) and host.startswith("fast:") else None).shape()
     else:
         shape = shape_of(cm)
     return fc.va_model(shape)

@@ -1,6 +1,6 @@
 """Host-side build of generated model code: C prelude + gcc -> shared object (used by the CPU
 oracle and by tests that check the generator against finite differences).  The CUDA prelude
-for the same generated text lives in csrc/va_device.cuh and is compiled by NVRTC in the engine.
+for the same generated text lives in csrc/va_prelude.h and is compiled by NVRTC in the engine.
 """
 from __future__ import annotations
 
@@ -129,11 +129,15 @@ class HostModel:
         return I, Q, G, Cm
 
 
-def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2", count_ops: bool = False) -> HostModel:
+def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2", count_ops: bool = False,
+               fast_tag: Optional[str] = None) -> HostModel:
+    """fast_tag: build for bench.py's `cpu_fast` baseline arm instead of the checker: -O3 -march=native with the
+    compiler's default FP contraction; the tag (a hash of the host CPU's flags) keeps such builds per host."""
     out_dir = out_dir or GEN_DIR
     os.makedirs(out_dir, exist_ok=True)
     text = c_prelude(len(cm.terminals), count_ops) + cm.source + (cm.source_n or "")
-    key = hashlib.sha1((text + opt).encode()).hexdigest()[:16]
+    flags = [opt, "-ffp-contract=off"] if fast_tag is None else ["-O3", "-march=native"]
+    key = hashlib.sha1((text + opt + (fast_tag or "")).encode()).hexdigest()[:16]
     base = os.path.join(out_dir, f"{cm.name}_{key}")
     so = base + ".so"
     if not os.path.exists(so):
@@ -142,7 +146,7 @@ def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2
         src, tmp = f"{base}.{os.getpid()}.c", f"{so}.{os.getpid()}.tmp"
         with open(src, "w") as f:
             f.write(text)
-        cmd = [HOST_CC, opt, "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-w", "-o", tmp, src, "-lm"]
+        cmd = [HOST_CC, *flags, "-fPIC", "-shared", "-fno-math-errno", "-w", "-o", tmp, src, "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"host compile of generated model failed:\n{r.stderr[:4000]}")

@@ -381,6 +381,7 @@ class CompiledModel:
     branch_terms: List[int] = field(default_factory=list)   # terminals that are branch CURRENTS (voltage branches, I() probes)
     linear: bool = False   # every Jacobian entry is independent of the terminal values (no Newton step limiting needed)
     gen_version: int = 0   # GEN_VERSION of the generator that wrote `source` (cached models of another version are rebuilt)
+    codegen_seconds: float = 0.0   # wall time of parsing + code generation of all variants (bench.py reports it as compile latency)
 
     @property
     def key(self) -> str:
@@ -2111,10 +2112,14 @@ def _module_has_noise(mod: Module) -> bool:
 def compile_va_file(path: str, module: Optional[str] = None, name: Optional[str] = None,
                     include_paths: Sequence[str] = (), defines=None, suppress_defines=(),
                     const_params=None, runtime_params=None, probe_branches=()) -> CompiledModel:
+    import time
+    t0 = time.perf_counter()
     pp = Preprocessor(include_paths, defines, suppress_defines)
     text = pp.process_file(path)
-    return compile_va_text(text, module, name, preprocessed=True, const_params=const_params,
-                           runtime_params=runtime_params, probe_branches=probe_branches)
+    cm = compile_va_text(text, module, name, preprocessed=True, const_params=const_params,
+                         runtime_params=runtime_params, probe_branches=probe_branches)
+    cm.codegen_seconds = time.perf_counter() - t0
+    return cm
 
 
 def compile_va_text(text: str, module: Optional[str] = None, name: Optional[str] = None,

@@ -30,6 +30,7 @@
 // "No cleverness": dense matrices, partial pivoting, one instance at a time.
 
 #include "../include/cedarb200.h"
+#include "../cedarsim.jl_b200/csrc/symbolic.hpp"   // fast arm only: the engine's host-side symbolic analysis (static pivots, fill)
 
 #include <algorithm>
 #include <cmath>
@@ -154,13 +155,20 @@ void collect_breakpoints(const cb_flat_circuit* fc, double t0, double t1, std::v
 // ---------------------------------------------------------------- system evaluation
 struct Sys {
     int N;
-    std::vector<double> f, q, G, C;  // G, C dense row-major N x N
+    std::vector<double> f, q, G, C;  // G, C dense row-major N x N (checker) ...
+    const int* pos = nullptr;        // ... or, fast arm only: [N x N] -> position in the sparse L+U value arrays (-1 = not in the pattern)
+    std::vector<double> v_, I_, Q_, Gl_, Cl_;   // scratch of the Verilog-A device loop
     void resize(int n) {
         N = n;
         f.assign(n, 0);
         q.assign(n, 0);
         G.assign((size_t)n * n, 0);
         C.assign((size_t)n * n, 0);
+    }
+    void resize_sparse(int n, const int* pos_, int nnz) {
+        N = n; pos = pos_;
+        f.assign(n, 0); q.assign(n, 0);
+        G.assign((size_t)nnz, 0); C.assign((size_t)nnz, 0);
     }
     void zero() {
         std::fill(f.begin(), f.end(), 0.0);
@@ -195,8 +203,17 @@ void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, b
     s.zero();
     auto addf = [&](int r, double v) { if (r >= 0) s.f[r] += v; };
     auto addq = [&](int r, double v) { if (r >= 0) s.q[r] += v; };
-    auto addG = [&](int r, int c, double v) { if (r >= 0 && c >= 0) s.G[(size_t)r * N + c] += v; };
-    auto addC = [&](int r, int c, double v) { if (r >= 0 && c >= 0) s.C[(size_t)r * N + c] += v; };
+    const int* const pos = s.pos;
+    auto addG = [&](int r, int c, double v) {
+        if (r < 0 || c < 0) return;
+        if (!pos) s.G[(size_t)r * N + c] += v;
+        else if (pos[(size_t)r * N + c] >= 0) s.G[pos[(size_t)r * N + c]] += v;
+    };
+    auto addC = [&](int r, int c, double v) {
+        if (r < 0 || c < 0) return;
+        if (!pos) s.C[(size_t)r * N + c] += v;
+        else if (pos[(size_t)r * N + c] >= 0) s.C[pos[(size_t)r * N + c]] += v;
+    };
     for (int d = 0; d < fc->n_devices; d++) {
         const cb_device& dv = fc->devices[d];
         const int p = dv.n[0], n = dv.n[1], cp = dv.n[2], cn = dv.n[3], b = dv.branch;
@@ -247,7 +264,7 @@ void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, b
         }
     }
     // Verilog-A devices: I(a,b) <+ e  puts +e on KCL(a), -e on KCL(b) (src/vasim.jl:819-839)
-    std::vector<double> v, I, Q, Gl, Cl;
+    std::vector<double>&v = s.v_, &I = s.I_, &Q = s.Q_, &Gl = s.Gl_, &Cl = s.Cl_;
     for (int d = 0; d < fc->n_va_insts; d++) {
         const cb_va_inst& vi = fc->va_insts[d];
         const cb_va_model& m = fc->va_models[vi.model];
@@ -299,6 +316,77 @@ bool lu_solve(std::vector<double>& A, std::vector<double>& b, int N) {
     return true;
 }
 
+// ---------------------------------------------------------------- fast arm (bench.py `cpu_fast` baseline only)
+// The same equations and the same Newton / step control as above, but the linear algebra a production CPU simulator
+// would use: one symbolic analysis per circuit (the engine's own, csrc/symbolic.hpp: matching, Markowitz order, exact
+// fill), then static-pivot sparse LU on value arrays -- ~1 kflop per factorisation of the 85-unknown DFF instead of
+// ~410 kflop dense.  NOT the checker: parity tests use the dense partial-pivoting path; tests/test_oracle_fast.py
+// checks this path against it.
+static int g_sparse =
+#ifdef ORC_SPARSE_DEFAULT
+    1;
+#else
+    0;
+#endif
+
+struct SparseLU {
+    cb::Symbolic S;
+    std::vector<int> pos;        // [N x N] original (row, col) -> L+U position
+    bool build(const cb_flat_circuit* fc) {
+        const int N = fc->n_unknowns, NV = fc->n_nodes;
+        std::vector<cb::PatternEntry> pat;
+        auto add = [&](int r, int c, int cls) { if (r >= 0 && c >= 0) pat.push_back({r, c, r == c && cls < 2 ? 2 : cls}); };
+        for (int d = 0; d < fc->n_devices; d++) {
+            const cb_device& dv = fc->devices[d];
+            const int p = dv.n[0], n = dv.n[1], cp = dv.n[2], cn = dv.n[3], b = dv.branch;
+            switch (dv.kind) {
+                case CB_DEV_R: case CB_DEV_C: add(p, p, 2); add(p, n, 1); add(n, p, 1); add(n, n, 2); break;
+                case CB_DEV_L: add(p, b, 3); add(n, b, 3); add(b, p, 3); add(b, n, 3); pat.push_back({b, b, 1}); break;
+                case CB_DEV_VSRC: add(p, b, 3); add(n, b, 3); add(b, p, 3); add(b, n, 3); break;
+                case CB_DEV_VCVS: add(p, b, 3); add(n, b, 3); add(b, p, 3); add(b, n, 3); add(b, cp, 1); add(b, cn, 1); break;
+                case CB_DEV_VCCS: add(p, cp, 1); add(p, cn, 1); add(n, cp, 1); add(n, cn, 1); break;
+                default: break;
+            }
+        }
+        for (int d = 0; d < fc->n_va_insts; d++) {
+            const cb_va_inst& vi = fc->va_insts[d];
+            const cb_va_model& m = fc->va_models[vi.model];
+            for (int k = 0; k < m.nj; k++) add(vi.term[m.jrow[k]], vi.term[m.jcol[k]], 1);
+        }
+        for (int i = 0; i < NV; i++) pat.push_back({i, i, 0});   // gmin-stepping shunts
+        if (!cb::analyze(N, pat, S)) return false;
+        pos.assign((size_t)N * N, -1);
+        for (const auto& kv : S.pos_of_orig) pos[(size_t)kv.first.first * N + kv.first.second] = kv.second;
+        return true;
+    }
+    // LU holds J on entry; b the right-hand side in step order.  On success b holds the solution in step order.
+    bool factor_solve(double* LU, double* b) const {
+        const int N = S.N;
+        for (int k = 0; k < N; k++) {
+            const double d = LU[S.diag_pos[k]];
+            if (!(std::fabs(d) > 0.0) || !std::isfinite(d)) return false;
+            const double inv = 1.0 / d;
+            LU[S.diag_pos[k]] = inv;
+            const int l0 = S.l_ptr[k], nl = S.l_ptr[k + 1] - l0, u0 = S.u_ptr[k], nu = S.u_ptr[k + 1] - u0;
+            const int* dst = S.pair_dst.data() + S.pair_ptr[k];
+            const double bk = b[k];
+            for (int li = 0; li < nl; li++) {
+                const double l = LU[S.l_pos[l0 + li]] * inv;
+                if (l == 0.0) { dst += nu; continue; }
+                for (int uj = 0; uj < nu; uj++) LU[dst[uj]] -= l * LU[S.u_pos[u0 + uj]];
+                dst += nu;
+                b[S.l_row[l0 + li]] -= l * bk;
+            }
+        }
+        for (int k = N - 1; k >= 0; k--) {
+            double acc = b[k];
+            for (int u = S.u_ptr[k]; u < S.u_ptr[k + 1]; u++) acc -= LU[S.u_pos[u]] * b[S.u_col[u]];
+            b[k] = acc * LU[S.diag_pos[k]];
+        }
+        return true;
+    }
+};
+
 struct Counters {
     int64_t newton = 0, factors = 0, accepted = 0, rejected = 0;
 };
@@ -312,14 +400,18 @@ struct Solver {
     std::vector<double> J, rhs;
     std::vector<uint8_t> lte_mask;
     Counters cnt;
+    const SparseLU* sp = nullptr;   // fast arm: symbolic analysis shared by all points of a call (set before init)
+    std::vector<double> spLU, spb;  // this point's values / right-hand side in elimination-step order
     bool debug = std::getenv("ORC_DEBUG") != nullptr;
     double kappa = 0.0, kappa_floor = 0.0;   // quadratic-convergence constant of the first Newton update (nr_rate_test 2)
 
     void init(const cb_flat_circuit* fc, const double* params, int64_t B, int64_t b, const cb_options* o) {
         in.fc = fc; in.params = params; in.B = B; in.b = b;
         opt = o; N = fc->n_unknowns; NV = fc->n_nodes;
-        s.resize(N);
-        J.resize((size_t)N * N); rhs.resize(N);
+        if (sp) { s.resize_sparse(N, sp->pos.data(), sp->S.nnz_lu); spLU.assign(sp->S.nnz_lu, 0.0); spb.assign(N, 0.0); }
+        else s.resize(N);
+        if (!sp) J.resize((size_t)N * N);
+        rhs.resize(N);
         va_setup_all(in, in.pv(o->temp), in.pv(o->gmin), vc);
         kappa = 20.0 * (o->nr_reltol + o->nr_vabstol);
         kappa_floor = kappa / 30.0;
@@ -354,10 +446,19 @@ struct Solver {
                 rhs[i] = -r;
                 rmax = std::max(rmax, std::fabs(r));
             }
-            for (size_t k = 0; k < (size_t)N * N; k++) J[k] = s.G[k] + alpha * s.C[k];
-            for (int i = 0; i < NV; i++) J[(size_t)i * N + i] += gshunt;
             cnt.factors++;
-            if (!lu_solve(J, rhs, N)) return 4;
+            if (sp) {
+                const int nnz = sp->S.nnz_lu;
+                for (int k = 0; k < nnz; k++) spLU[k] = s.G[k] + alpha * s.C[k];
+                if (gshunt != 0.0) for (int i = 0; i < NV; i++) spLU[sp->pos[(size_t)i * N + i]] += gshunt;
+                for (int i = 0; i < N; i++) spb[sp->S.row_to_step[i]] = rhs[i];
+                if (!sp->factor_solve(spLU.data(), spb.data())) return 4;
+                for (int i = 0; i < N; i++) rhs[i] = spb[sp->S.col_to_step[i]];
+            } else {
+                for (size_t k = 0; k < (size_t)N * N; k++) J[k] = s.G[k] + alpha * s.C[k];
+                for (int i = 0; i < NV; i++) J[(size_t)i * N + i] += gshunt;
+                if (!lu_solve(J, rhs, N)) return 4;
+            }
             double dvmax = 0.0;
             bool finite = true;
             for (int i = 0; i < N; i++) {
@@ -370,7 +471,12 @@ struct Solver {
             // step keeps under the rate-based tests (the engine's k_lu does the same); the plain test accepts only
             // when |dx| is below the Newton tolerance, where q(x) of the last evaluation is kept
             qk = s.q;
-            for (int i = 0; use_rate && i < N; i++) {
+            if (use_rate && sp) {
+                const cb::Symbolic& S = sp->S;
+                for (int k = 0; k < S.nnz_lu; k++)
+                    if (s.C[k] != 0.0) qk[S.prow[S.lu_i[k]]] += s.C[k] * rhs[S.pcol[S.lu_j[k]]];
+            }
+            for (int i = 0; use_rate && !sp && i < N; i++) {
                 double acc = 0.0;
                 for (int j = 0; j < N; j++) {
                     const double cij = s.C[(size_t)i * N + j];
@@ -594,6 +700,9 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
 
 extern "C" {
 
+// 1 = fast arm (static-pivot sparse LU), 0 = checker (dense partial pivoting).  Applies to solvers created afterwards.
+void orc_set_sparse(int on) { g_sparse = on; }
+
 void orc_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
@@ -620,9 +729,12 @@ int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_
            double* x_out, double* x_full, int32_t* status, cb_stats* stats, int nthreads) {
     int64_t newton = 0, factors = 0;
     const int N = fc->n_unknowns;
+    SparseLU shared;
+    const SparseLU* sp = (g_sparse && shared.build(fc)) ? &shared : nullptr;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors)
     for (int64_t b = 0; b < B; b++) {
         Solver S;
+        S.sp = sp;
         S.init(fc, params, B, b, opt);
         S.x0 = g_x0; S.x0_stride = g_x0_stride;
         std::vector<double> x;
@@ -640,9 +752,12 @@ int orc_tran(const cb_flat_circuit* fc, const double* params, int64_t B, double 
              const double* saveat, int64_t nsave, const cb_options* opt, double* y_out,
              int32_t* status, cb_stats* stats, int nthreads) {
     int64_t newton = 0, factors = 0, acc = 0, rej = 0;
+    SparseLU shared;
+    const SparseLU* sp = (g_sparse && shared.build(fc)) ? &shared : nullptr;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors, acc, rej)
     for (int64_t b = 0; b < B; b++) {
         Solver S;
+        S.sp = sp;
         S.init(fc, params, B, b, opt);
         S.x0 = g_x0; S.x0_stride = g_x0_stride;
         status[b] = tran_one(S, t0, t1, saveat, nsave, y_out, B, b);

@@ -11,14 +11,62 @@ import numpy as np
 
 _here = os.path.dirname(os.path.abspath(__file__))
 _lib = None
+_fast_lib = None
+_use_fast = False
 
 
 def build():
     subprocess.run(["make", "-C", _here, "-s"], check=True)
 
 
+def cpu_tag() -> str:
+    """Identifies the host CPU's instruction set: -march=native builds (the fast arm) are per host, they must not travel
+    from the build container to the GPU box."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("flags", "Features")):
+                    flags = " ".join(sorted(line.split(":", 1)[1].split()))
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+def fast_lib():
+    """bench.py's `cpu_fast` baseline arm: the same source at -O3 -march=native with the static-pivot sparse LU
+    (oracle.cpp, "fast arm").  Built on first use on the host it runs on.  Never used as the checker."""
+    global _fast_lib
+    if _fast_lib is None:
+        name = f"_build/liboracle_fast_{cpu_tag()}.so"
+        path = os.path.join(_here, name)
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", _here, "-s", "fast", f"FAST_OUT={name}"], check=True)
+        _fast_lib = C.CDLL(path)
+        _fast_lib.orc_wave_value.restype = C.c_double
+    return _fast_lib
+
+
+class fast_arm:
+    """with orc.fast_arm(): ... -- route orc.dc / orc.tran through the fast library (timing baseline only)."""
+
+    def __enter__(self):
+        global _use_fast
+        fast_lib()
+        self.prev, _use_fast = _use_fast, True
+        return self
+
+    def __exit__(self, *exc):
+        global _use_fast
+        _use_fast = self.prev
+
+
 def lib():
     global _lib
+    if _use_fast:
+        return fast_lib()
     if _lib is None:
         path = os.path.join(_here, "_build", "liboracle.so")
         if not os.path.exists(path):
@@ -26,6 +74,12 @@ def lib():
         _lib = C.CDLL(path)
         _lib.orc_wave_value.restype = C.c_double
     return _lib
+
+
+def set_sparse(on: bool):
+    """Static-pivot sparse LU instead of dense partial pivoting in orc.dc / orc.tran (what the fast arm defaults to);
+    tests use it to check the sparse path against the dense checker inside the checker's own build."""
+    lib().orc_set_sparse(C.c_int(1 if on else 0))
 
 
 def _flat():
