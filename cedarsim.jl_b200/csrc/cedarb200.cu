@@ -211,8 +211,11 @@ extern "C" int cb_circuit_create(const cb_flat_circuit* f, cb_circuit** out) {
         h.term.assign(v.term, v.term + m.nterm);
         for (int t : h.term) if (!chk(t)) return fail(CB_ERR_INVALID, "VA terminal index out of range");
         h.par.assign(v.par, v.par + m.nparam);
-        for (const cb_pref& q : h.par) if (!chkp(q)) return fail(CB_ERR_INVALID, "VA instance parameter column out of range");
         h.given.assign(v.given, v.given + m.nparam);
+        for (int k = 0; k < m.nparam; k++) {
+            if (!h.given[k]) { h.par[k].col = -1; continue; }   // only meaningful where given: never dereferenced otherwise
+            if (!chkp(h.par[k])) return fail(CB_ERR_INVALID, "VA instance parameter column out of range");
+        }
         c->insts.push_back(std::move(h));
     }
     c->outputs.assign(f->outputs, f->outputs + f->n_outputs);
@@ -512,7 +515,7 @@ static std::string gen_solve_source(const cb_circuit* c) {
          "  double* DX; double* QK; double* RMAX; int* BAD; double* DVMAX; };\n";
     o << "extern \"C\" __global__ void __launch_bounds__(64, 1) k_solve(SArgs a) {\n";
     o << "  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
-    o << "  if (inst >= a.B) return;\n  if (!a.active[inst]) return;\n";
+    o << "  if (inst >= a.B) return;\n  if (a.active[inst] != 1 && a.active[inst] != 2) return;\n";
     o << "  const size_t B = (size_t)a.B;\n";
     o << "  const double al = a.alpha[inst], gs = a.gshunt[inst];\n";
     o << "  const double* __restrict__ od = a.dev_out + inst;\n";
@@ -754,8 +757,11 @@ struct cb_plan {
     bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
-    int lu_win_full = 64, lu_win_solve = 64;   // points per k_lu CTA in full / value-only rounds
     int* d_dc_count = nullptr;
+    // point lists of the rounds (device-wide compaction, kernels.cuh): [parity][kind][B] and counters [parity][2]
+    int* d_lists = nullptr;
+    int* d_cnt = nullptr;
+    int num_sms = 148;
     double *d_DX = nullptr, *d_QK = nullptr, *d_RMAX = nullptr, *d_WV = nullptr, *d_DVMAX = nullptr;
     int* d_BAD = nullptr;
     std::vector<void*> allocs;
@@ -1119,7 +1125,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
     TRY(p->alloc(&p->d_xout, (size_t)std::max<size_t>(1, c->outputs.size()) * B));
     TRY(p->alloc(&p->d_done, 1));
     a.done_count = p->d_done;
-    CUDA_TRY(cudaMallocHost((void**)&p->h_done, 2 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_done, 8 * sizeof(int)));
     // per-model tables
     for (size_t m = 0; m < c->models.size(); m++) {
         const ModelH& M = c->models[m];
@@ -1227,13 +1233,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 TRY(p->upload(&ti, iptr)); la.citem_ptr = ti;
                 TRY(p->upload(&dm, c->cq_mult)); la.cmult = dm;
             }
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_lu<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-            // experiment knobs CB_LU_WIN_FULL / CB_LU_WIN_SOLVE = 32 | 64
-            if (const char* e = std::getenv("CB_LU_WIN_FULL")) p->lu_win_full = std::atoi(e) == 32 ? 32 : 64;
-            if (const char* e = std::getenv("CB_LU_WIN_SOLVE")) p->lu_win_solve = std::atoi(e) == 32 ? 32 : 64;
+            CUDA_TRY(cudaFuncSetAttribute(k_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
             la.LUF = nullptr;
         }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
@@ -1243,6 +1243,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         TRY(p->alloc(&p->d_BAD, (size_t)B));
         TRY(p->alloc(&p->d_WV, (size_t)std::max(1, a.nwaves) * B));
         TRY(p->alloc(&p->d_dc_count, 1));
+        TRY(p->alloc(&p->d_lists, (size_t)4 * B));
+        TRY(p->alloc(&p->d_cnt, 4));
+        {
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+            p->num_sms = std::max(1, prop.multiProcessorCount);
+        }
         a.scratch = nullptr;
         a.sm_stride = 0;
     }
@@ -1302,18 +1309,20 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     return CB_OK;
 }
 
-static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false, int only = -1) {
+// which point list a device-evaluation launch runs over: this round's full-iteration or value-only points
+static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false, int parity = 0) {
     // layout must match struct VaArgs in va_prelude.h
     struct VaArgsH {
-        long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out;
+        long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
         const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
-        double temp_val; double gmin_val; int temp_col; int gmin_col; int vround; int pad;
+        double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
     };
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
-    a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha; a->active = p->na.active;
+    a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha;
+    a->list = p->d_lists + ((size_t)parity * 2 + (value_only ? 1 : 0)) * p->B;
+    a->count = p->d_cnt + parity * 2 + (value_only ? 1 : 0);
     a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->Bpad : p->d_cache + (size_t)c->cache_off[m] * p->Bpad;
-    a->vround = only >= 0 ? only : (value_only ? 1 : 0); a->pad = 0;   // which points take part, see VaArgs::vround
     a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
     a->given = p->d_given[m];
@@ -1470,39 +1479,35 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     int rc = run_setup(p, opt);
     if (rc != CB_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->d_done, 0, sizeof(int), p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_cnt, 0, 4 * sizeof(int), p->stream));
     k_init_state<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.N, a.ist, a.dst, a.alpha, a.active, a.X, a.XN, a.BETA,
-                                                                          p->have_x0 ? p->d_x0 : nullptr, p->x0_stride, o);
+                                                                          p->have_x0 ? p->d_x0 : nullptr, p->x0_stride, o,
+                                                                          p->d_lists, p->d_cnt);
     CUDA_TRY(cudaGetLastError());
 
-    // Round schedule.  While any point is still in its DC phase every round is a FULL round (Newton far from the
-    // solution needs fresh Jacobians).  Afterwards each full round is followed by v_rounds VALUE-ONLY rounds: chord
-    // iterations with the stored factors and derivative-free device evaluations (~1/5 of the instructions).
-    // A step attempt always starts on a full round (points marked ACT_FULL idle through value-only rounds).
-    const int poll = std::getenv("CB_POLL") ? std::max(1, std::atoi(std::getenv("CB_POLL"))) : 16;
+    // ---- round schedule.  Every round: the eval kernels of the points that take a FULL iteration (k_eval_*: currents,
+    // charges, Jacobian stamps) and of the points that take a VALUE-ONLY iteration (k_evalv_*: derivative-free, ~1/2 of
+    // the instructions), k_lu over both lists (refactor + solve / solve with the stored factors), k_control (Newton
+    // update, step control, and the point lists of the next round).  Two schedules:
+    //   mixed rounds (default with value_rounds > 0): every unfinished point iterates in EVERY round and follows its own
+    //     cycle: full iteration, value_rounds chord iterations, full, ...  No point ever idles, the host makes no
+    //     scheduling decision, and the launches stay dense through the device-wide compaction.
+    //   lock-step rounds (mixed_rounds = 0): one full round, then value_rounds value-only rounds in which the points that
+    //     need a fresh Jacobian idle; all rounds are full while any point is still in its DC phase.
+    // Both produce the same iterates.  A window of rounds is captured in a CUDA graph (argument buffers alternate with the
+    // round parity) and replayed; the host polls two device counters once per window and keeps one window queued ahead,
+    // so launch and polling latency stay off the critical path however small the batch is.
     const bool timing = p->timing || std::getenv("CB_TIMING") != nullptr;
-    std::vector<cudaEvent_t> evs;
-    std::vector<int> ev_kind;
-    std::vector<cudaEvent_t> uevs;   // mixed rounds: 5 events per round
     double t_eval = 0, t_newton = 0, t_evalv = 0, t_newtonv = 0;
     int64_t rounds = 0, vrounds = 0, launches = 0;
     const int64_t max_rounds = std::getenv("CB_MAX_ROUNDS") ? std::atoll(std::getenv("CB_MAX_ROUNDS")) : (int64_t)1 << 40;
-    char vargs[8][256], vargs_v[8][256];
     if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
-    for (size_t m = 0; m < c->models.size(); m++) {
-        fill_va_args(p, m, opt, vargs[m]);
-        if (p->d_cachev) fill_va_args(p, m, opt, vargs_v[m], true);
-    }
     struct SArgsH {
         long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA; const double* dev_out;
         const double* lin_g; const double* lin_c; const double* WV; const int* active; double* DX; double* QK; double* RMAX; int* BAD;
         double* DVMAX;
     } sargs{B, a.X, a.alpha, a.dst + (size_t)DS_GSHUNT * B, a.BETA, a.dev_out, a.lin_g, a.lin_c, p->d_WV, a.active,
             p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
-    void* sargs_ptr[] = {&sargs};
-    CArgs cargs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, 0, 0, p->d_dc_count, 1, 0};
-    LArgs largs = p->la;
-    largs.n = a; largs.WV = p->d_WV; largs.DX = p->d_DX; largs.QK = p->d_QK; largs.RMAX = p->d_RMAX; largs.DVMAX = p->d_DVMAX;
-    largs.BAD = p->d_BAD;
     k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
     CUDA_TRY(cudaGetLastError());
     {
@@ -1516,150 +1521,173 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         int rc2 = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * p->Bpad);
         if (rc2 == CB_OK) rc2 = p->alloc(&p->la.LUF, (size_t)c->sym.nnz_lu * B);
         if (rc2 != CB_OK) return rc2;
-        largs.LUF = p->la.LUF;
-        for (size_t m = 0; m < c->models.size(); m++) fill_va_args(p, m, opt, vargs_v[m], true);
     }
     if (use_v) { int rc2 = run_setupv(p, opt); if (rc2 != CB_OK) return rc2; }
-    if (!use_v) largs.LUF = nullptr;
+    int mixed = use_v && opt->mixed_rounds != 0;
+    if (const char* e = std::getenv("CB_MIXED")) mixed = use_v && std::atoi(e) != 0;
+    // per-parity argument blocks
+    char vargs[2][8][256], vargs_v[2][8][256];
+    CArgs cargs[2];
+    LArgs largs[2];
+    for (int par = 0; par < 2; par++) {
+        for (size_t m = 0; m < c->models.size(); m++) {
+            fill_va_args(p, m, opt, vargs[par][m], false, par);
+            if (use_v) fill_va_args(p, m, opt, vargs_v[par][m], true, par);
+        }
+        int* lists_next = p->d_lists + (size_t)(1 - par) * 2 * B;
+        cargs[par] = CArgs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, mixed, 0, p->d_dc_count, v_rounds + 1, 0,
+                           lists_next, lists_next + B, p->d_cnt + (1 - par) * 2};
+        largs[par] = p->la;
+        largs[par].n = a; largs[par].WV = p->d_WV; largs[par].DX = p->d_DX; largs[par].QK = p->d_QK; largs[par].RMAX = p->d_RMAX;
+        largs[par].DVMAX = p->d_DVMAX; largs[par].BAD = p->d_BAD;
+        largs[par].LUF = use_v ? p->la.LUF : nullptr;
+        largs[par].cur = Lists{p->d_lists + (size_t)par * 2 * B, p->d_lists + (size_t)par * 2 * B + B, p->d_cnt + par * 2};
+        largs[par].zero_cnt = p->d_cnt + (1 - par) * 2;
+    }
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
-    // Mixed rounds (experiment, CB_UNIFIED=1; off by default): every round advances EVERY unfinished point, the ones that
-    // need a fresh Jacobian through k_eval + k_lu<false>, the others through k_evalv + k_lu<true> with their stored
-    // factors; a point follows its own cycle (full, v_rounds value-only, full, ...) instead of idling until the global
-    // schedule reaches the kind of round it needs.  Same iterates bit for bit and 29 % fewer rounds on the DFF bench,
-    // but 1.85x SLOWER (profiles/variants_r1ad.log): every launch now covers ~half of the points, and with in-CTA
-    // compaction a half-filled launch of these latency-bound kernels takes as long as a full one (same number of CTAs
-    // and waves, half the warps per CTA).  It needs device-wide compaction (per-kind point lists) to pay off.
-    const bool unified = use_v && p->lu && std::getenv("CB_UNIFIED") && std::atoi(std::getenv("CB_UNIFIED")) != 0;
-    char vargs_f[8][256];
-    if (unified) {
-        cargs.unified = 1; cargs.vcycle = v_rounds + 1;
-        largs.only_full = 1;
-        for (size_t m = 0; m < c->models.size(); m++) {
-            std::memcpy(vargs_f[m], vargs[m], sizeof vargs_f[m]);
-            fill_va_args(p, m, opt, vargs_f[m], false, 2);
-        }
-    }
-    bool done = false;
-    int since_full = 0;   // value-only rounds since the last full round
-    while (!done && rounds < max_rounds) {
-        const bool dc_phase = p->h_done[1] > 0;
-        for (int r = 0; r < poll; r++) {
-            if (unified) {
-                // timing (per-kernel figures of the roofline pass, run with CB_EVAL_FORK=0 so that nothing overlaps):
-                // e0 | k_eval_* | em | k_evalv_* | e1 | k_lu<false> | el | k_lu<true>, k_control | e2
-                cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr, el = nullptr, e2 = nullptr;
-                if (timing) {
-                    cudaEventCreate(&e0); cudaEventCreate(&em); cudaEventCreate(&e1); cudaEventCreate(&el); cudaEventCreate(&e2);
-                    cudaEventRecord(e0, p->stream);
-                }
-                // up to 2 x models eval kernels, all independent: stream 0 takes the first, the rest fork
-                CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
-                int slot = 0;
-                for (int kind = 0; kind < 2; kind++) {          // 0: full evaluation of ACT_FULL points, 1: value-only of ACT_ANY
-                    if (kind == 1 && timing) cudaEventRecord(em, p->stream);
-                    if (kind == 1 && rounds == 0) break;        // every point starts with a full iteration
-                    for (size_t m = 0; m < c->models.size(); m++) {
-                        if (c->model_insts[m].empty()) continue;
-                        void* kargs[] = {kind ? vargs_v[m] : vargs_f[m]};
-                        const unsigned eval_threads = kind ? p->evalv_threads[m] : p->eval_threads[m];
-                        dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
-                        cudaStream_t ms = (p->fork_models && slot > 0 && slot < 8 && p->ustream[slot]) ? p->ustream[slot] : p->stream;
-                        if (ms != p->stream) CUDA_TRY(cudaStreamWaitEvent(ms, p->ev_fork, 0));
-                        CUDA_TRY(cudaLaunchKernel((const void*)(kind ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
-                                                  kind ? p->evalv_smem[m] : p->eval_smem[m], ms));
-                        if (ms != p->stream) {
-                            CUDA_TRY(cudaEventRecord(p->uev[slot], ms));
-                            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->uev[slot], 0));
-                        }
-                        slot++;
-                        launches++;
-                    }
-                }
-                if (timing) cudaEventRecord(e1, p->stream);
-                const unsigned g = (unsigned)((B + 63) / 64);
-                k_lu<false, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                if (timing) cudaEventRecord(el, p->stream);
-                if (rounds > 0) k_lu<true, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
-                launches += 3;
-                if (timing) {
-                    cudaEventRecord(e2, p->stream);
-                    uevs.push_back(e0); uevs.push_back(em); uevs.push_back(e1); uevs.push_back(el); uevs.push_back(e2);
-                }
-                rounds++;
-                continue;
-            }
-            const bool vround = use_v && !dc_phase && rounds > 0 && since_full < v_rounds;
-            since_full = vround ? since_full + 1 : 0;
-            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-            if (timing) {
-                cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-                cudaEventRecord(e0, p->stream);
-            }
-            const bool fork = p->fork_models && n_live_models > 1;
-            if (fork) CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
-            bool first_model = true;
+    const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
+    // one round on the plan's streams; `vround`: lock-step value-only round (only the value-only list is non-empty);
+    // `next_v`: lock-step schedule of the next round; ev: optional timing events {start, after eval, after evalv, end}
+    auto launch_round = [&](int par, bool full_kernels, bool value_kernels, int next_v, cudaEvent_t* ev) -> int {
+        if (ev) cudaEventRecord(ev[0], p->stream);
+        const bool fork = p->fork_models && (n_live_models > 1 || (full_kernels && value_kernels)) && !ev;
+        if (fork) CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
+        int slot = 0;
+        for (int kind = 0; kind < 2; kind++) {          // 0: full evaluation of the full list, 1: value-only of the other
+            if (kind == 1 && ev) cudaEventRecord(ev[1], p->stream);
+            if (kind == 0 ? !full_kernels : !value_kernels) continue;
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
-                void* kargs[] = {vround ? vargs_v[m] : vargs[m]};
-                const unsigned eval_threads = vround ? p->evalv_threads[m] : p->eval_threads[m];
+                void* kargs[] = {kind ? vargs_v[par][m] : vargs[par][m]};
+                const unsigned eval_threads = kind ? p->evalv_threads[m] : p->eval_threads[m];
                 dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
-                cudaStream_t ms = (fork && !first_model && p->mstream[m]) ? p->mstream[m] : p->stream;
+                cudaStream_t ms = (fork && slot > 0 && slot < 8 && p->ustream[slot]) ? p->ustream[slot] : p->stream;
                 if (ms != p->stream) CUDA_TRY(cudaStreamWaitEvent(ms, p->ev_fork, 0));
-                CUDA_TRY(cudaLaunchKernel((const void*)(vround ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
-                                          vround ? p->evalv_smem[m] : p->eval_smem[m], ms));
+                CUDA_TRY(cudaLaunchKernel((const void*)(kind ? p->k_evalv[m] : p->k_eval[m]), grid, dim3(eval_threads), kargs,
+                                          kind ? p->evalv_smem[m] : p->eval_smem[m], ms));
                 if (ms != p->stream) {
-                    CUDA_TRY(cudaEventRecord(p->ev_join[m], ms));
-                    CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join[m], 0));
+                    CUDA_TRY(cudaEventRecord(p->uev[slot], ms));
+                    CUDA_TRY(cudaStreamWaitEvent(p->stream, p->uev[slot], 0));
                 }
-                first_model = false;
+                slot++;
                 launches++;
             }
-            if (timing) cudaEventRecord(e1, p->stream);
-            if (p->lu) {
-                // window of points per CTA (compacted into groups of LU_PTS): 64 keeps the groups of value-only rounds
-                // full; 32 gives a short lane twice the CTAs (one group each) in full rounds
-                const int win = vround ? p->lu_win_solve : p->lu_win_full;
-                const unsigned g = (unsigned)((B + win - 1) / win);
-                if (vround) {
-                    if (win == 32) k_lu<true, 32><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                    else k_lu<true, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                } else {
-                    if (win == 32) k_lu<false, 32><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                    else k_lu<false, 64><<<g, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs);
-                }
-            } else CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
-            cargs.vround = vround ? 1 : 0;
-            k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(cargs);
-            launches += 2;
-            if (timing) { cudaEventRecord(e2, p->stream); evs.push_back(e0); evs.push_back(e1); evs.push_back(e2); ev_kind.push_back(vround); }
-            rounds++;
-            vrounds += vround;
         }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(p->h_done, p->d_done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(p->h_done + 1, p->d_dc_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-        done = p->h_done[0] >= B;
-        if (timing) {
-            for (size_t k = 0; k + 2 < evs.size(); k += 3) {
-                float ms1 = 0, ms2 = 0;
-                cudaEventElapsedTime(&ms1, evs[k], evs[k + 1]);
-                cudaEventElapsedTime(&ms2, evs[k + 1], evs[k + 2]);
-                if (ev_kind[k / 3]) { t_evalv += ms1 * 1e-3; t_newtonv += ms2 * 1e-3; }
-                else { t_eval += ms1 * 1e-3; t_newton += ms2 * 1e-3; }
-                cudaEventDestroy(evs[k]); cudaEventDestroy(evs[k + 1]); cudaEventDestroy(evs[k + 2]);
+        if (ev) cudaEventRecord(ev[2], p->stream);
+        if (p->lu) k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs[par]);
+        else {
+            void* sargs_ptr[] = {&sargs};
+            CUDA_TRY(cudaMemsetAsync(p->d_cnt + (1 - par) * 2, 0, 2 * sizeof(int), p->stream));
+            CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
+        }
+        CArgs ca = cargs[par];
+        ca.next_vround = next_v;
+        k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(ca);
+        launches += 2;
+        if (ev) cudaEventRecord(ev[3], p->stream);
+        return CB_OK;
+    };
+    // lock-step schedule: kind of round r (0-based round index since the transient phase began)
+    auto is_vround = [&](int64_t since_tran) { return use_v && !mixed && since_tran % (v_rounds + 1) != 0; };
+
+    const bool use_graph = !timing && !(std::getenv("CB_NOGRAPH") && std::atoi(std::getenv("CB_NOGRAPH")) != 0);
+    int window = std::getenv("CB_POLL") ? std::max(2, std::atoi(std::getenv("CB_POLL"))) : 24;
+    window = ((window + 2 * (v_rounds + 1) - 1) / (2 * (v_rounds + 1))) * (2 * (v_rounds + 1));   // whole cycles, even parity
+    bool done = false;
+    int par = 0;
+    if (use_graph) {
+        // two graphs: the DC phase of the lock-step schedule (all rounds full) and the steady pattern.  Mixed rounds
+        // need only one (every round launches both kinds; an empty list costs an empty launch).
+        cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+        auto capture = [&](bool dc_pattern, cudaGraphExec_t* out) -> int {
+            cudaGraph_t g = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+            int rcl = CB_OK;
+            for (int r = 0; r < window && rcl == CB_OK; r++) {
+                const bool v = !dc_pattern && is_vround(r), nv = !dc_pattern && is_vround(r + 1);
+                rcl = launch_round(r & 1, mixed || !v, mixed ? use_v : v, nv, nullptr);
+            }
+            cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+            if (rcl != CB_OK) { if (g) cudaGraphDestroy(g); return rcl; }
+            if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(out, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(CB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+            return CB_OK;
+        };
+        const int64_t launches_before = launches;
+        rc = capture(false, &gexec[0]);
+        const int64_t per_window = launches - launches_before;
+        launches = launches_before;
+        if (rc == CB_OK && !mixed && use_v) { rc = capture(true, &gexec[1]); launches = launches_before; }
+        if (rc != CB_OK) { for (auto g : gexec) if (g) cudaGraphExecDestroy(g); return rc; }
+        // keep one window queued behind the one being polled: the counters read after window k decide about window k + 2
+        int queued = 0;
+        cudaEvent_t evw[2];
+        cudaEventCreateWithFlags(&evw[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&evw[1], cudaEventDisableTiming);
+        int* h_snap = p->h_done + 2;   // pinned: [done, dc] snapshots of the two windows in flight (h_done has 8 ints)
+        bool dc_phase = p->h_done[1] > 0;
+        cudaError_t gerr = cudaSuccess;
+        int64_t k = 0;
+        while (!done && rounds < max_rounds && gerr == cudaSuccess) {
+            while (queued < 2 && gerr == cudaSuccess) {
+                const bool dcg = dc_phase && gexec[1];
+                gerr = cudaGraphLaunch(dcg ? gexec[1] : gexec[0], p->stream);
+                if (gerr != cudaSuccess) break;
+                const int sl = (int)((k + queued) & 1);
+                cudaMemcpyAsync(h_snap + 2 * sl, p->d_done, sizeof(int), cudaMemcpyDeviceToHost, p->stream);
+                cudaMemcpyAsync(h_snap + 2 * sl + 1, p->d_dc_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream);
+                gerr = cudaEventRecord(evw[sl], p->stream);
+                rounds += window; launches += per_window;
+                if (mixed) vrounds += window;   // every round carries value-only iterations
+                else if (!dcg && use_v) vrounds += (int64_t)window / (v_rounds + 1) * v_rounds;
+                queued++;
+            }
+            if (gerr != cudaSuccess) break;
+            const int sl = (int)(k & 1);
+            gerr = cudaEventSynchronize(evw[sl]);
+            queued--; k++;
+            done = h_snap[2 * sl] >= B;
+            dc_phase = h_snap[2 * sl + 1] > 0;
+        }
+        if (gerr == cudaSuccess) gerr = cudaStreamSynchronize(p->stream);
+        cudaEventDestroy(evw[0]); cudaEventDestroy(evw[1]);
+        for (auto g : gexec) if (g) cudaGraphExecDestroy(g);
+        if (gerr != cudaSuccess) return fail(CB_ERR_CUDA, std::string("round graph: ") + cudaGetErrorString(gerr));
+        p->h_done[0] = h_snap[2 * ((k - 1) & 1)];
+    } else {
+        std::vector<cudaEvent_t> evs;
+        int64_t since_tran = 0;
+        while (!done && rounds < max_rounds) {
+            const bool dc_phase = p->h_done[1] > 0;
+            for (int r = 0; r < window; r++) {
+                const bool v = !dc_phase && is_vround(since_tran), nv = !dc_phase && is_vround(since_tran + 1);
+                cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+                if (timing) for (auto& e : ev) { cudaEventCreate(&e); evs.push_back(e); }
+                rc = launch_round(par, mixed || !v, mixed ? use_v : v, nv, timing ? ev : nullptr);
+                if (rc != CB_OK) return rc;
+                par ^= 1;
+                rounds++;
+                vrounds += (mixed || v) ? 1 : 0;
+                if (!dc_phase) since_tran++;
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(p->h_done, p->d_done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaMemcpyAsync(p->h_done + 1, p->d_dc_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+            done = p->h_done[0] >= B;
+            // timing: e0 | k_eval_* | e1 | k_evalv_* | e2 | k_lu, k_control | e3  (one stream: nothing overlaps).  k_lu and
+            // k_control serve both kinds of iteration; their time is split in proportion to the eval kernels' times.
+            for (size_t q = 0; q + 3 < evs.size(); q += 4) {
+                float ms[3] = {0, 0, 0};
+                for (int z = 0; z < 3; z++) cudaEventElapsedTime(&ms[z], evs[q + z], evs[q + z + 1]);
+                t_eval += ms[0] * 1e-3; t_evalv += ms[1] * 1e-3;
+                const double wv = (ms[0] + ms[1]) > 0 ? ms[1] / (ms[0] + ms[1]) : 0.0;
+                t_newton += ms[2] * 1e-3 * (1.0 - wv); t_newtonv += ms[2] * 1e-3 * wv;
+                for (int z = 0; z < 4; z++) cudaEventDestroy(evs[q + z]);
             }
             evs.clear();
-            ev_kind.clear();
-            for (size_t k = 0; k + 4 < uevs.size(); k += 5) {
-                float ms[4] = {0, 0, 0, 0};
-                for (int q = 0; q < 4; q++) cudaEventElapsedTime(&ms[q], uevs[k + q], uevs[k + q + 1]);
-                t_eval += ms[0] * 1e-3; t_evalv += ms[1] * 1e-3; t_newton += ms[2] * 1e-3; t_newtonv += ms[3] * 1e-3;
-                for (int q = 0; q < 5; q++) cudaEventDestroy(uevs[k + q]);
-            }
-            uevs.clear();
         }
     }
     CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
@@ -1849,7 +1877,7 @@ static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, 
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     CUDA_TRY(cudaEventRecord(e0, p->stream));
     // linearisation: one full device evaluation at the operating point with alpha = 0 -> G rows and C rows of dev_out
-    k_ac_prepare<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.active, a.alpha);
+    k_ac_prepare<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.active, a.alpha, p->d_lists, p->d_cnt);
     CUDA_TRY(cudaGetLastError());
     int64_t launches = 1;
     for (size_t m = 0; m < c->models.size(); m++) {
@@ -1862,7 +1890,7 @@ static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, 
         launches++;
     }
     if (noise) {
-        struct VaArgsHead { long long B; const double* x; const double* alpha; const int* active; const double* cache; double* out; };
+        struct VaArgsHead { long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out; };
         for (size_t m = 0; m < c->models.size(); m++) {
             const ModelH& M = c->models[m];
             if (c->model_insts[m].empty() || M.noise_pos.empty()) continue;

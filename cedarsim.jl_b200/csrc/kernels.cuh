@@ -4,9 +4,13 @@
 //   k_eval_<model> / k_evalv_<model>  (generated, va/compiler.py)  device currents, charges (+ Jacobian stamps)
 //   k_lu<false> / k_lu<true>          assembly + batched sparse LU + solves / solves only with the stored factors
 //   k_control                         Newton update, convergence, DC / transient state machine of every point
-// A round is either FULL (devices evaluated with their Jacobians, matrix refactored) or VALUE-ONLY (devices
-// evaluated without derivatives, chord iteration with the factors of the last full round).  Every step
-// attempt starts on a full round; see solve() in cedarb200.cu for the schedule.
+// An ITERATION of a point is either FULL (devices evaluated with their Jacobians, matrix refactored) or VALUE-ONLY
+// (devices evaluated without derivatives, chord iteration with the factors of the point's last full iteration).  Every
+// step attempt starts with a full iteration.  k_control decides the kind of every point's next iteration and compacts
+// the points of each kind DEVICE-WIDE into two dense lists (list_full / list_any + counters, double-buffered by round
+// parity); the eval kernels and k_lu of the next round run over those lists, so their launches are dense whatever
+// fraction of the points takes part.  See solve() in cedarb200.cu for the two schedules (mixed rounds: every unfinished
+// point iterates in every round; lock-step rounds: full round, then value_rounds value-only rounds).
 //
 // Layout: every per-point array is [k][B] (batch-interleaved, B fastest): consecutive threads are
 // consecutive sweep points, so a warp access is one contiguous 256-byte row segment.
@@ -25,9 +29,12 @@ enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HIT
        IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_NFULL, IS_COUNT };
 // double per-point state rows
 enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_NRM, DS_KAPPA, DS_COUNT };
-// a.active[]: 0 = finished, 1 = mid-attempt (runs in every round), 2 = needs a full round (DC iterations and the
-// first iteration of a transient step attempt: fresh Jacobian), idles through value-only rounds
-enum { ACT_DONE = 0, ACT_ANY = 1, ACT_FULL = 2 };
+// a.active[]: the point's role in the coming round: 0 = finished, 1 = value-only iteration (stored factors), 2 = full
+// iteration (fresh Jacobian: DC iterations, first iteration of a step attempt, every vcycle-th iteration), 3 = idle:
+// waits for the next full round (lock-step schedule only; in mixed rounds nobody idles)
+enum { ACT_DONE = 0, ACT_ANY = 1, ACT_FULL = 2, ACT_IDLE = 3 };
+// compacted point lists of one round: counters cnt[0] = full, cnt[1] = value-only
+struct Lists { const int* full; const int* any; const int* cnt; };
 
 struct Pref { double value; int col; int pad; };
 
@@ -178,12 +185,12 @@ struct CArgs {
     const double *DX, *QK, *RMAX, *DVMAX;
     const int* BAD;
     double* WV;  // [nwaves][B] source values for the next evaluation
-    int vround;  // this round was value-only: points marked ACT_FULL did not take part
-    int unified; // mixed rounds: every unfinished point took part, ACT_ANY points with a value-only iteration (stored
-                 // factors), ACT_FULL points with a full one; the kind of a point's next iteration follows its own
-                 // iteration count (full, then vcycle - 1 value-only, full, ...), not a global round schedule
-    int* dc_count;  // number of points still in the DC phase (the host schedules full rounds only while > 0)
+    int mixed;   // 1 = mixed rounds: the kind of a point's next iteration follows its own iteration count (full, then
+                 // vcycle - 1 value-only, full, ...); 0 = lock-step rounds: the host's schedule decides (next_vround)
+    int next_vround;  // lock-step: the next round is value-only (points that need a fresh Jacobian idle through it)
+    int* dc_count;  // number of points still in the DC phase (lock-step: the host schedules full rounds only while > 0)
     int vcycle, pad_;
+    int *next_full, *next_any, *next_cnt;   // lists of the NEXT round, built here (counters zeroed by this round's k_lu)
 };
 
 __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long long inst, bool dcop, double t) {
@@ -206,6 +213,7 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 #define CTRL_MINB 4   // 64 registers: the 512 CTAs of a 16 384-point launch are one wave (148 SMs x 4), not 444 + a tail
 #endif
 __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(const CArgs c) {
+    static_assert(CTRL_PTS == 32, "lane 0 of the points of a CTA must be exactly one warp (list compaction by ballot)");
     __shared__ double s_err[CTRL_LANES][CTRL_PTS];
     __shared__ double s_nrm[CTRL_LANES][CTRL_PTS];
     const NArgs& a = c.n;
@@ -214,8 +222,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     const long long inst = (long long)blockIdx.x * CTRL_PTS + pt;
     const bool inb = inst < B;
     const int act = inb ? a.active[inst] : ACT_DONE;
-    const bool live = act == ACT_ANY || (act == ACT_FULL && (c.unified || !c.vround));
-    const bool pv = c.unified ? act == ACT_ANY : c.vround != 0;   // this point's iteration was value-only
+    const bool live = act == ACT_ANY || act == ACT_FULL;   // took part in this round
+    const bool pv = act == ACT_ANY;                         // ... with a value-only iteration
     int phase = live ? a.ist[(size_t)IS_PHASE * B + inst] : PH_DONE;
     const int N = a.N, NV = a.NV;
     const Opts& o = a.o;
@@ -506,13 +514,38 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
             DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim; DST(DS_NRM) = nrm_prev; DST(DS_KAPPA) = kappa;
             a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
-            const bool want_full = c.unified ? (phase != PH_TRAN || it % c.vcycle == 0) : (phase == PH_DC || (phase == PH_TRAN && it == 0));
-            a.active[inst] = phase == PH_DONE ? ACT_DONE : want_full ? ACT_FULL : ACT_ANY;
             if (phase_in == PH_DC && phase != PH_DC) atomicSub(c.dc_count, 1);
         }
         if (phase != PH_DONE)
             for (int w = lane; w < a.nwaves; w += CTRL_LANES)
                 c.WV[(size_t)w * B + inst] = wave_value(a.waves[w], tnew, phase != PH_TRAN, a.params, B, inst);
+    }
+    // ---- role of every point in the NEXT round + device-wide compaction.  Warp 0 of the CTA (lane 0 of every point)
+    //      holds the scalar state.  Each CTA reserves one contiguous range of each list with a single atomicAdd: the
+    //      lists are ordered by CTA completion, but inside a range the points ascend, so a warp of the consumer kernels
+    //      still reads a few contiguous row segments.  Results do not depend on the order (every point is solved on its
+    //      own); an idle point (lock-step schedule) is re-examined every round.
+    if (lane == 0) {
+        int role = ACT_DONE;
+        if (inb && (live ? phase != PH_DONE : act == ACT_IDLE)) {
+            // a fresh Jacobian for DC iterations, the first iteration of a step attempt and every vcycle-th iteration
+            const bool want_full = !live ? true : c.mixed ? (phase != PH_TRAN || it % c.vcycle == 0)
+                                                          : (phase != PH_TRAN || it == 0);
+            role = c.mixed ? (want_full ? ACT_FULL : ACT_ANY)
+                           : (c.next_vround ? (want_full ? ACT_IDLE : ACT_ANY) : ACT_FULL);
+        }
+        if (inb && (live || act == ACT_IDLE)) a.active[inst] = role;
+        const unsigned bf = __ballot_sync(0xffffffffu, role == ACT_FULL), ba = __ballot_sync(0xffffffffu, role == ACT_ANY);
+        int basef = 0, basea = 0;
+        if (pt == 0) {
+            if (bf) basef = atomicAdd(c.next_cnt + 0, __popc(bf));
+            if (ba) basea = atomicAdd(c.next_cnt + 1, __popc(ba));
+        }
+        basef = __shfl_sync(0xffffffffu, basef, 0);
+        basea = __shfl_sync(0xffffffffu, basea, 0);
+        const unsigned below = (1u << pt) - 1u;
+        if (role == ACT_FULL) c.next_full[basef + __popc(bf & below)] = (int)inst;
+        if (role == ACT_ANY) c.next_any[basea + __popc(ba & below)] = (int)inst;
     }
 #undef IST
 #undef DST
@@ -568,7 +601,9 @@ struct LArgs {
     const int* sop_ptr;       // [nslev * LU_W + 1]
     const int4* sitems;       // gather items of the residual and charge rows only
     const int* sitem_ptr;     // [LU_W + 1]
-    int nslev, only_full;     // only_full: k_lu<false> takes the ACT_FULL points only (mixed rounds)
+    int nslev, pad1_;
+    Lists cur;                // this round's point lists: groups of LU_PTS full-iteration points, then of value-only points
+    int* zero_cnt;            // counters of the NEXT round's lists (k_control of this round fills them): zeroed here
     // first-order charge update  q(x + dx) ~ q(x) + C dx:  items (dev_out row of dQ/dV, vals slot of q_row, vals slot of
     // dx_col, index into cmult), grouped by destination row like the gather items
     const int4* citems;
@@ -580,39 +615,13 @@ struct LArgs {
     int* BAD;
 };
 
-template <bool SOLVE, int LU_WIN>
-__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
-    extern __shared__ double vals_[];
-    __shared__ double s_red[2][LU_W][LU_PTS];
-    __shared__ int s_bad[LU_W][LU_PTS];
+// One group of LU_PTS points (lane = point) of one kind: SOLVE = value-only iteration with the stored factors.
+template <bool SOLVE>
+__device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (*s_red)[LU_W][LU_PTS], int (*s_bad)[LU_PTS],
+                                         const long long inst, const bool on, const int lane, const int w) {
     const NArgs& a = c.n;
     const long long B = a.B;
-    const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
-    // A CTA owns a window of LU_WIN consecutive points and works through the ones that take part in this round in
-    // groups of LU_PTS (compaction: in value-only rounds, where 30-50 % of the points iterate, half of the groups
-    // disappear; with every point live the mapping is the identity).
-    __shared__ short s_list[LU_WIN];
-    __shared__ int s_cnt[LU_WIN / 32];
-    const long long base = (long long)blockIdx.x * LU_WIN;
-    bool on0 = false;
-    unsigned bal0 = 0;
-    if (threadIdx.x < LU_WIN) {
-        const long long i0 = base + threadIdx.x;
-        const int act = i0 < B ? a.active[i0] : ACT_DONE;
-        on0 = SOLVE ? act == ACT_ANY : (c.only_full ? act == ACT_FULL : act != ACT_DONE);
-        bal0 = __ballot_sync(0xffffffffu, on0);
-        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(bal0);
-    }
-    __syncthreads();
-    int total = 0, before = 0;
-#pragma unroll
-    for (int q = 0; q < LU_WIN / 32; q++) { if (q < (int)(threadIdx.x >> 5)) before += s_cnt[q]; total += s_cnt[q]; }
-    if (on0) s_list[before + __popc(bal0 & ((1u << (threadIdx.x & 31)) - 1u))] = (short)threadIdx.x;
-    __syncthreads();
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
-    for (int g0 = 0; g0 < total; g0 += LU_PTS) {
-    const bool on = g0 + lane < total;
-    const long long inst = base + s_list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
     double* __restrict__ vals = vals_ + lane;
 #define VL(i) vals[(size_t)(i) * LU_PTS]
     const double alpha = a.alpha[inst], gshunt = a.dst[(size_t)DS_GSHUNT * B + inst];
@@ -782,8 +791,30 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
         c.RMAX[inst] = r; c.DVMAX[inst] = d; c.BAD[inst] = b;
     }
     __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
-    }
 #undef VL
+}
+
+// A CTA works through groups g = blockIdx.x, blockIdx.x + gridDim.x, ... of this round's lists: first the groups of
+// full-iteration points (assembly + LU + solves, factors stored), then the groups of value-only points (solves with the
+// stored factors).  The lists are dense (device-wide compaction by k_control), so every group but the last of each kind
+// is full whatever fraction of the sweep points takes part in the round.
+__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
+    extern __shared__ double vals_[];
+    __shared__ double s_red[2][LU_W][LU_PTS];
+    __shared__ int s_bad[LU_W][LU_PTS];
+    const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
+    if (blockIdx.x == 0 && threadIdx.x < 2) c.zero_cnt[threadIdx.x] = 0;
+    const int nf = c.cur.cnt[0], na = c.cur.cnt[1];
+    const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS;
+    for (int g = blockIdx.x; g < gf + ga; g += gridDim.x) {
+        const bool solve = g >= gf;
+        const int g0 = (solve ? g - gf : g) * LU_PTS, n = solve ? na : nf;
+        const int* __restrict__ list = solve ? c.cur.any : c.cur.full;
+        const bool on = g0 + lane < n;
+        const long long inst = list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
+        if (solve) lu_group<true>(c, vals_, s_red, s_bad, inst, on, lane, w);
+        else lu_group<false>(c, vals_, s_red, s_bad, inst, on, lane, w);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -985,11 +1016,13 @@ __global__ void __launch_bounds__(AC_PTS * AC_W) k_ac(const AArgs c) {
 }
 
 // marks every point as taking part in the next (full) device evaluation with alpha = 0: G and C come out separately
-__global__ void k_ac_prepare(long long B, int* active, double* alpha) {
+__global__ void k_ac_prepare(long long B, int* active, double* alpha, int* list_full, int* cnt) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst == 0) { cnt[0] = (int)B; cnt[1] = 0; }
     if (inst >= B) return;
     active[inst] = ACT_FULL;
     alpha[inst] = 0.0;
+    list_full[inst] = (int)inst;
 }
 
 __global__ void k_init_waves(const NArgs a, double* WV) {
@@ -1000,9 +1033,11 @@ __global__ void k_init_waves(const NArgs a, double* WV) {
 
 // ---- small helper kernels ---------------------------------------------------------------------
 __global__ void k_init_state(long long B, int N, int* ist, double* dst, double* alpha, int* active, double* X,
-                             double* XN, double* BETA, const double* x0, long long x0_stride, Opts o) {
+                             double* XN, double* BETA, const double* x0, long long x0_stride, Opts o, int* list_full, int* cnt) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst == 0) { cnt[0] = (int)B; cnt[1] = 0; }   // first round: every point, full iteration (identity list)
     if (inst >= B) return;
+    list_full[inst] = (int)inst;
     for (int k = 0; k < IS_COUNT; k++) ist[(size_t)k * B + inst] = 0;
     for (int k = 0; k < DS_COUNT; k++) dst[(size_t)k * B + inst] = 0.0;
     ist[(size_t)IS_PHASE * B + inst] = o.skip_dc && !o.dc_only ? PH_TRAN_INIT : PH_DC;

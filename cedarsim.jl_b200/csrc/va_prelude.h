@@ -16,7 +16,7 @@ struct VaArgs {
     long long B;                 // sweep points on this device
     const double* x;             // [N][B] current Newton iterate
     const double* alpha;         // [B]    d/dt discretisation coefficient of each point
-    const int* active;           // [B]    0 = point finished, skip
+    const int* list;             // [*count] sweep points that take part in this launch (device-wide compaction by k_control)
     const double* cache;         // [ndev][NCACHE][B] bias-independent values
     double* out;                 // [ndev][NOUT][B]   I | Q | J = dI/dV + alpha dQ/dV
     const int* term;             // [ndev][NT] unknown index per terminal, -1 = ground
@@ -26,8 +26,8 @@ struct VaArgs {
     const uint8_t* given;        // [ndev][NPARAM]
     double temp_val; double gmin_val;
     int temp_col; int gmin_col;
-    int vround; int pad_;        // 0: every unfinished point; 1: only points with active[] == 1 (value-only evaluation,
-                                 // those that need a fresh Jacobian are skipped); 2: only points with active[] == 2
+    const int* count;            // number of entries of `list` (a device counter: the grid is sized for all B points and
+                                 // CTAs beyond the count exit at once)
 };
 
 // Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
@@ -193,7 +193,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define GIVEN(i) (given_[i] != 0)
 #define TEMP_K (temp_c_ + 273.15)
 #define GMIN_V gmin_
-#define CACHE_ST(s, v) cache_[(s) * VA_CACHE_BLK] = (double)(v)
+#define CACHE_ST(s, v) cache_[(s)] = (double)(v)
 #define VT(k) vt_[k]
 #define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
@@ -202,14 +202,17 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define OUT_J(idx, k, l, g, c) { const double c_ = (c); out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * c_; \
                                  out_[(size_t)(2 * NT + NJ + (idx)) * a.B] = c_; }
 
-// Cache layout: [device][block of VA_CACHE_BLK points][slot][VA_CACHE_BLK].  Inside one block of points a slot is a
-// compile-time byte offset (slot * 1 KB) from the thread's base pointer, so the ~250 cache accesses of an
-// evaluation need no 64-bit address arithmetic (the [slot][B] layout cost two integer instructions per access),
-// and a CTA streams one contiguous region of HBM.
-#define VA_CACHE_BLK 128
+// Cache layout: [device][point][slot] -- every (device, point) owns one contiguous row of NCACHE doubles in the order
+// the eval function consumes it.  A thread streams ITS OWN row, 32 bytes (one DRAM sector) per chunk, so the bytes
+// fetched from HBM are exactly the rows of the points that take part in the launch: with the point lists of mixed
+// rounds about half of the points take part in each of the two eval kernels of a round, and the batch-interleaved
+// layout of round 1 ([slot][128 points]) then fetched nearly every sector for half of its bytes (measured: mixed rounds
+// 24 % SLOWER than lock-step rounds despite 27 % fewer rounds, profiles/probe_r2b.log).  The setup kernels write the
+// rows once per sweep (uncoalesced 8-byte stores, off the hot path).
+#define VA_CACHE_BLK 128   // rows are allocated for B rounded up to a multiple of this
 VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, const long long inst) {
-    const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
-    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncache) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK);
+    const size_t bpad = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK) * VA_CACHE_BLK;
+    return ((size_t)dev * bpad + (size_t)inst) * (size_t)ncache;
 }
 #define VA_SETUP_BEGIN(NAME) VA_SETUP_BEGIN_(k_setup_##NAME)
 #define VA_SETUPV_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupv_##NAME)
@@ -264,7 +267,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         const int p = chunk * ROWS + r;
-        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + p * VA_CACHE_BLK);
+        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + p);
     }
 }
 // (Experiments that did not pay and were removed: CTA-wide barriers at the chunk markers or every ~50 generated
@@ -279,7 +282,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
         asm volatile("cp.async.wait_group %0;" ::"n"(VA_AHEAD) : "memory");                      \
     }
 #define CACHE_LD(s) ring_[((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS]
-#define CACHE_LDG(s) __ldg(cache_ + (s) * VA_CACHE_BLK)
+#define CACHE_LDG(s) __ldg(cache_ + (s))
 
 // value-only variant (k_evalv_*: currents and charges, no Jacobian; its own cache, see CompiledModel.source_v)
 #ifndef VA_EVALV_MINBLOCKS
@@ -296,37 +299,21 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
 #define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
 #define VA_EVALV_END(NAME) VA_EVAL_END(NAME)
-// Thread mapping with in-CTA compaction: a CTA owns VA_EVAL_THREADS consecutive sweep points; thread k takes the
-// k-th point of them that takes part in this round, and threads beyond the count exit before any work.  When all
-// points are live (full rounds) the mapping is the identity and every access is coalesced; in value-only rounds,
-// where typically 30-50 % of the points iterate, whole warps retire instead of running with most lanes idle.
+// Thread mapping: thread k of the launch takes the k-th entry of the point list of this kind of iteration (full /
+// value-only), which k_control compacted device-wide; threads beyond the count exit before any work.  The lists ascend
+// inside runs of up to 32 points, so a warp reads a few contiguous row segments; with every point live the launch is as
+// coalesced as the identity mapping.
 #define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
     extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ double va_ring_[];                                                     \
-        __shared__ int va_cnt_[VA_EVAL_THREADS / 32];                                            \
-        __shared__ short va_list_[VA_EVAL_THREADS];                                              \
         if (blockDim.x != VA_EVAL_THREADS) __trap();                                             \
         long long inst;                                                                          \
         {                                                                                        \
-            const long long base_ = (long long)blockIdx.x * VA_EVAL_THREADS;                     \
-            const long long i0_ = base_ + threadIdx.x;                                           \
-            const int act_ = i0_ < a.B ? a.active[i0_] : 0;                                      \
-            const bool on_ = a.vround == 0 ? act_ != 0 : act_ == (a.vround == 1 ? 1 : 2);          \
-            const unsigned bal_ = __ballot_sync(0xffffffffu, on_);                               \
-            if ((threadIdx.x & 31) == 0) va_cnt_[threadIdx.x >> 5] = __popc(bal_);               \
-            __syncthreads();                                                                     \
-            int before_ = 0, total_ = 0;                                                         \
-            _Pragma("unroll") for (int q_ = 0; q_ < VA_EVAL_THREADS / 32; q_++) {                \
-                const int c_ = va_cnt_[q_];                                                      \
-                if (q_ < (int)(threadIdx.x >> 5)) before_ += c_;                                 \
-                total_ += c_;                                                                    \
-            }                                                                                    \
-            if (on_) va_list_[before_ + __popc(bal_ & ((1u << (threadIdx.x & 31)) - 1u))] = (short)threadIdx.x; \
-            __syncthreads();                                                                     \
-            if ((int)threadIdx.x >= total_) return;                                              \
-            inst = base_ + va_list_[threadIdx.x];                                                \
+            const long long k_ = (long long)blockIdx.x * VA_EVAL_THREADS + threadIdx.x;          \
+            if (k_ >= (long long)*a.count) return;                                               \
+            inst = a.list[k_];                                                                   \
         }                                                                                        \
         const int dev = blockIdx.y;                                                              \
         const double* __restrict__ cache_ = a.cache + va_cache_index(a.B, dev, NCACHE, inst);    \

@@ -35,10 +35,11 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-GEN_VERSION = 5   # bump when the emitted code changes: models cached under _gen/ are regenerated
+GEN_VERSION = 6   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
 CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "4"))
 CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "8"))
+FOLD_CONST_DIV = os.environ.get("CB_FOLD_CONST_DIV", "1") != "0"
 
 
 class VACompileError(Exception):
@@ -923,6 +924,17 @@ class _Compiler:
             self.count("mul")
             return self.emit_val("r", f"{ac} * {bc}", d)
         if op == "/":
+            if b.const is not None and not b.d and b.typ in ("r", "i") and float(b.const) != 0.0 and FOLD_CONST_DIV:
+                # division by a compile-time constant (a folded model-card value): multiply by its reciprocal, computed
+                # here in IEEE double.  On the GPU a division is an out-of-line call (csrc/va_prelude.h) that the compiler
+                # cannot fold; both targets compile the same text, so oracle and engine stay on the same arithmetic.
+                r = 1.0 / float(b.const)
+                if math.isfinite(r) and r != 0.0:
+                    if r == 1.0:
+                        return a if a.typ == "r" else self.emit_val("r", ac, {})
+                    self.count("mul", 1 + len(a.d))
+                    rl = _lit(r)
+                    return self.emit_val("r", f"{ac} * {rl}", {kk: self._dmul(rl, v) for kk, v in a.d.items()})
             self.count("div")
             if not b.d:
                 if not a.d:

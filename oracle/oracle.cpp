@@ -284,9 +284,10 @@ void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, b
     }
 }
 
-// dense LU, partial pivoting; returns false when singular
-bool lu_solve(std::vector<double>& A, std::vector<double>& b, int N) {
-    std::vector<int> piv(N);
+// dense LU, partial pivoting (row swaps applied to whole rows, LAPACK convention); returns false when singular.
+// On return A holds L (unit lower, multipliers) and U, piv the row exchanges: lu_apply solves further right-hand sides.
+bool lu_factor(std::vector<double>& A, std::vector<int>& piv, int N) {
+    piv.resize(N);
     for (int k = 0; k < N; k++) {
         int p = k;
         double best = std::fabs(A[(size_t)k * N + k]);
@@ -295,24 +296,37 @@ bool lu_solve(std::vector<double>& A, std::vector<double>& b, int N) {
             if (a > best) { best = a; p = i; }
         }
         if (!(best > 0.0) || !std::isfinite(best)) return false;
-        if (p != k) {
+        piv[k] = p;
+        if (p != k)
             for (int j = 0; j < N; j++) std::swap(A[(size_t)k * N + j], A[(size_t)p * N + j]);
-            std::swap(b[k], b[p]);
-        }
         double inv = 1.0 / A[(size_t)k * N + k];
         for (int i = k + 1; i < N; i++) {
             double l = A[(size_t)i * N + k] * inv;
-            if (l == 0.0) continue;
             A[(size_t)i * N + k] = l;
+            if (l == 0.0) continue;
             for (int j = k + 1; j < N; j++) A[(size_t)i * N + j] -= l * A[(size_t)k * N + j];
-            b[i] -= l * b[k];
         }
+    }
+    return true;
+}
+void lu_apply(const std::vector<double>& A, const std::vector<int>& piv, std::vector<double>& b, int N) {
+    for (int k = 0; k < N; k++)     // whole rows were swapped (L part included): P A = L U, permute first
+        if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+    for (int k = 0; k < N; k++) {
+        const double bk = b[k];
+        if (bk != 0.0)
+            for (int i = k + 1; i < N; i++) b[i] -= A[(size_t)i * N + k] * bk;
     }
     for (int i = N - 1; i >= 0; i--) {
         double s = b[i];
         for (int j = i + 1; j < N; j++) s -= A[(size_t)i * N + j] * b[j];
         b[i] = s / A[(size_t)i * N + i];
     }
+}
+bool lu_solve(std::vector<double>& A, std::vector<double>& b, int N) {
+    std::vector<int> piv;
+    if (!lu_factor(A, piv, N)) return false;
+    lu_apply(A, piv, b, N);
     return true;
 }
 
@@ -359,8 +373,8 @@ struct SparseLU {
         for (const auto& kv : S.pos_of_orig) pos[(size_t)kv.first.first * N + kv.first.second] = kv.second;
         return true;
     }
-    // LU holds J on entry; b the right-hand side in step order.  On success b holds the solution in step order.
-    bool factor_solve(double* LU, double* b) const {
+    // LU holds J on entry; on return L (unscaled), U and the inverted pivots (the layout of the engine's stored factors).
+    bool factor(double* LU) const {
         const int N = S.N;
         for (int k = 0; k < N; k++) {
             const double d = LU[S.diag_pos[k]];
@@ -369,21 +383,28 @@ struct SparseLU {
             LU[S.diag_pos[k]] = inv;
             const int l0 = S.l_ptr[k], nl = S.l_ptr[k + 1] - l0, u0 = S.u_ptr[k], nu = S.u_ptr[k + 1] - u0;
             const int* dst = S.pair_dst.data() + S.pair_ptr[k];
-            const double bk = b[k];
             for (int li = 0; li < nl; li++) {
                 const double l = LU[S.l_pos[l0 + li]] * inv;
-                if (l == 0.0) { dst += nu; continue; }
-                for (int uj = 0; uj < nu; uj++) LU[dst[uj]] -= l * LU[S.u_pos[u0 + uj]];
+                if (l != 0.0)
+                    for (int uj = 0; uj < nu; uj++) LU[dst[uj]] -= l * LU[S.u_pos[u0 + uj]];
                 dst += nu;
-                b[S.l_row[l0 + li]] -= l * bk;
             }
+        }
+        return true;
+    }
+    // b: right-hand side in step order -> solution in step order
+    void solve(const double* LU, double* b) const {
+        const int N = S.N;
+        for (int k = 0; k < N; k++) {
+            const double bk = b[k] * LU[S.diag_pos[k]];
+            if (bk != 0.0)
+                for (int p = S.l_ptr[k]; p < S.l_ptr[k + 1]; p++) b[S.l_row[p]] -= LU[S.l_pos[p]] * bk;
         }
         for (int k = N - 1; k >= 0; k--) {
             double acc = b[k];
             for (int u = S.u_ptr[k]; u < S.u_ptr[k + 1]; u++) acc -= LU[S.u_pos[u]] * b[S.u_col[u]];
             b[k] = acc * LU[S.diag_pos[k]];
         }
-        return true;
     }
 };
 
@@ -397,7 +418,8 @@ struct Solver {
     int N, NV;
     VaCache vc;
     Sys s;
-    std::vector<double> J, rhs;
+    std::vector<double> J, rhs, keepG, keepC;
+    std::vector<int> Jpiv;
     std::vector<uint8_t> lte_mask;
     Counters cnt;
     const SparseLU* sp = nullptr;   // fast arm: symbolic analysis shared by all points of a call (set before init)
@@ -436,8 +458,20 @@ struct Solver {
         // voltage-step limit: only nonlinear (Verilog-A) devices need it; a purely linear circuit
         // converges in one full step whatever its voltage scale
         const double lim = has_nonlinear(in.fc) ? opt->dv_max : 1e300;
+        // Chord (value-only) iterations, transient only: with cb_options.value_rounds = v every (v + 1)-th iteration of a
+        // step attempt (0, v + 1, ...) is a full Newton iteration with a fresh Jacobian; the ones in between re-use its
+        // LU factors and its dQ/dV (the engine evaluates them with the derivative-free device kernels).  v = 0: plain Newton.
+        const int vcycle = (!dcop && alpha != 0.0) ? std::max(0, opt->value_rounds) + 1 : 1;
         for (int it = 0; it < maxit; it++) {
-            eval_system(in, vc, x.data(), t, dcop, s);
+            const bool full = it % vcycle == 0;
+            if (full || vcycle == 1) eval_system(in, vc, x.data(), t, dcop, s);
+            else {
+                // value-only evaluation: currents and charges at x; G / C (and the factors) stay those of the last full iteration
+                keepG.swap(s.G); keepC.swap(s.C);
+                if (s.G.size() != keepG.size()) { s.G.assign(keepG.size(), 0.0); s.C.assign(keepC.size(), 0.0); }
+                eval_system(in, vc, x.data(), t, dcop, s);
+                keepG.swap(s.G); keepC.swap(s.C);
+            }
             cnt.newton++;
             double rmax = 0.0;
             for (int i = 0; i < N; i++) {
@@ -446,18 +480,24 @@ struct Solver {
                 rhs[i] = -r;
                 rmax = std::max(rmax, std::fabs(r));
             }
-            cnt.factors++;
+            if (full) cnt.factors++;
             if (sp) {
                 const int nnz = sp->S.nnz_lu;
-                for (int k = 0; k < nnz; k++) spLU[k] = s.G[k] + alpha * s.C[k];
-                if (gshunt != 0.0) for (int i = 0; i < NV; i++) spLU[sp->pos[(size_t)i * N + i]] += gshunt;
+                if (full) {
+                    for (int k = 0; k < nnz; k++) spLU[k] = s.G[k] + alpha * s.C[k];
+                    if (gshunt != 0.0) for (int i = 0; i < NV; i++) spLU[sp->pos[(size_t)i * N + i]] += gshunt;
+                    if (!sp->factor(spLU.data())) return 4;
+                }
                 for (int i = 0; i < N; i++) spb[sp->S.row_to_step[i]] = rhs[i];
-                if (!sp->factor_solve(spLU.data(), spb.data())) return 4;
+                sp->solve(spLU.data(), spb.data());
                 for (int i = 0; i < N; i++) rhs[i] = spb[sp->S.col_to_step[i]];
             } else {
-                for (size_t k = 0; k < (size_t)N * N; k++) J[k] = s.G[k] + alpha * s.C[k];
-                for (int i = 0; i < NV; i++) J[(size_t)i * N + i] += gshunt;
-                if (!lu_solve(J, rhs, N)) return 4;
+                if (full) {
+                    for (size_t k = 0; k < (size_t)N * N; k++) J[k] = s.G[k] + alpha * s.C[k];
+                    for (int i = 0; i < NV; i++) J[(size_t)i * N + i] += gshunt;
+                    if (!lu_factor(J, Jpiv, N)) return 4;
+                }
+                lu_apply(J, Jpiv, rhs, N);
             }
             double dvmax = 0.0;
             bool finite = true;
@@ -497,7 +537,9 @@ struct Solver {
                 kappa = std::max(std::max(nrm / (nrm_prev * nrm_prev), 0.7 * kappa), kappa_floor);
             if (use_rate && it >= 1 && nrm < nrm_prev) {
                 const double rho = nrm / nrm_prev;
-                est = nrm * std::min(1.0, 3.0 * rho / (1.0 - rho));
+                // safety 3; a chord update contracts half as fast as the ratio observed across the preceding Newton update
+                // suggests (the engine's k_control uses the same factors)
+                est = nrm * std::min(1.0, (full ? 3.0 : 6.0) * rho / (1.0 - rho));
             }
             nrm_prev = nrm;
             const bool conv = (est <= 1.0) && (sc == 1.0) && (rmax <= restol);
