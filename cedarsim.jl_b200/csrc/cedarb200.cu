@@ -319,6 +319,9 @@ extern "C" int cb_circuit_set_cuda_source(cb_circuit* c, const char* src, size_t
     return CB_OK;
 }
 
+// slots of one per-instance cache row as the device code lays it out: whole 32-byte sectors (va_prelude.h, NCACHE_P)
+static long long pad4(int n) { return ((long long)std::max(1, n) + 3) / 4 * 4; }
+
 static uint64_t fnv1a(const std::string& s) {
     uint64_t h = 1469598103934665603ULL;
     for (unsigned char ch : s) { h ^= ch; h *= 1099511628211ULL; }
@@ -406,7 +409,7 @@ static int build_tables(cb_circuit* c) {
         for (size_t k = 0; k < c->model_insts[m].size(); k++)
             c->inst_out_base[c->model_insts[m][k]] = c->total_out + (long long)k * c->models[m].nout();
         c->total_out += (long long)c->model_insts[m].size() * c->models[m].nout();
-        c->total_cache += (long long)c->model_insts[m].size() * std::max(1, c->models[m].ncache);
+        c->total_cache += (long long)c->model_insts[m].size() * pad4(c->models[m].ncache);
     }
     for (size_t i = 0; i < c->insts.size(); i++) {
         const VaInstH& v = c->insts[i];
@@ -1111,7 +1114,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         bool all = !c->insts.empty();
         long long total = 0;
         for (size_t m = 0; m < c->models.size(); m++) {
-            const long long per = std::max<long long>(1, p->cachev_off[m]);
+            const long long per = pad4((int)p->cachev_off[m]);
             p->cachev_off[m] = total;
             if (c->model_insts[m].empty()) continue;
             if (!p->k_evalv[m]) all = false;
@@ -1846,7 +1849,7 @@ static int ac_tables(cb_plan* p, bool noise) {
                 }
             }
             rows += (long long)c->model_insts[m].size() * 2 * K;
-            slots += (long long)c->model_insts[m].size() * std::max(1, M.ncache_n);
+            slots += (long long)c->model_insts[m].size() * pad4(M.ncache_n);
         }
         ResTab* dr; NoiseTab* dn;
         TRY(p->upload(&dr, rt)); TRY(p->upload(&dn, nt));

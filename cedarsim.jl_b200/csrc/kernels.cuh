@@ -529,8 +529,9 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
         int role = ACT_DONE;
         if (inb && (live ? phase != PH_DONE : act == ACT_IDLE)) {
             // a fresh Jacobian for DC iterations, the first iteration of a step attempt and every vcycle-th iteration
-            const bool want_full = !live ? true : c.mixed ? (phase != PH_TRAN || it % c.vcycle == 0)
-                                                          : (phase != PH_TRAN || it == 0);
+            // (the fixed-step retry of a failed attempt takes full iterations only: chord iterations are what failed)
+            const bool want_full = !live ? true : c.mixed ? (phase != PH_TRAN || retry || it % c.vcycle == 0)
+                                                          : (phase != PH_TRAN || retry || it == 0);
             role = c.mixed ? (want_full ? ACT_FULL : ACT_ANY)
                            : (c.next_vround ? (want_full ? ACT_IDLE : ACT_ANY) : ACT_FULL);
         }

@@ -193,7 +193,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define GIVEN(i) (given_[i] != 0)
 #define TEMP_K (temp_c_ + 273.15)
 #define GMIN_V gmin_
-#define CACHE_ST(s, v) cache_[(s)] = (double)(v)
+#define CACHE_ST(s, v) cache_[VA_SLOT_OFF(s)] = (double)(v)
 #define VT(k) vt_[k]
 #define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
@@ -202,18 +202,41 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define OUT_J(idx, k, l, g, c) { const double c_ = (c); out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * c_; \
                                  out_[(size_t)(2 * NT + NJ + (idx)) * a.B] = c_; }
 
-// Cache layout: [device][point][slot] -- every (device, point) owns one contiguous row of NCACHE doubles in the order
-// the eval function consumes it.  A thread streams ITS OWN row, 32 bytes (one DRAM sector) per chunk, so the bytes
-// fetched from HBM are exactly the rows of the points that take part in the launch: with the point lists of mixed
-// rounds about half of the points take part in each of the two eval kernels of a round, and the batch-interleaved
-// layout of round 1 ([slot][128 points]) then fetched nearly every sector for half of its bytes (measured: mixed rounds
-// 24 % SLOWER than lock-step rounds despite 27 % fewer rounds, profiles/probe_r2b.log).  The setup kernels write the
-// rows once per sweep (uncoalesced 8-byte stores, off the hot path).
+// Per-instance cache: NCACHE_P = NCACHE rounded up to whole 32-byte sectors of doubles per (device, point), in the order
+// the eval function consumes it.  Layouts (VA_CACHE_LAYOUT, the engine only sizes the allocation):
+//   0  [device][block of 128 points][slot][128]          batch-interleaved: a warp of consecutive points reads whole rows,
+//                                                         but a launch over a point LIST with gaps fetches every sector
+//                                                         for the fraction of its bytes that belong to listed points
+//   1  [device][point][slot]                              one contiguous row per point, 8-byte copies
+//   2  [device][point][slot]                              ... 16-byte copies that bypass L1 (cp.async.cg)
+//   3  [device][block of 128][chunk of 4 slots][128][4]   SECTOR-interleaved: the 4-slot chunk of a point is one 32-byte
+//                                                         DRAM sector, the sectors of 128 consecutive points are contiguous;
+//                                                         two 16-byte cp.async.cg per chunk.  HBM traffic = the rows of the
+//                                                         listed points only, and a warp request still spans few lines
+#ifndef VA_CACHE_LAYOUT
+#define VA_CACHE_LAYOUT 3
+#endif
 #define VA_CACHE_BLK 128   // rows are allocated for B rounded up to a multiple of this
-VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, const long long inst) {
-    const size_t bpad = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK) * VA_CACHE_BLK;
-    return ((size_t)dev * bpad + (size_t)inst) * (size_t)ncache;
+#define NCACHE_P ((NCACHE + 3) / 4 * 4)
+#if VA_CACHE_LAYOUT == 0
+#define VA_SLOT_OFF(s) ((s) * VA_CACHE_BLK)
+VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
+    const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
+    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK);
 }
+#elif VA_CACHE_LAYOUT == 3
+#define VA_SLOT_OFF(s) (((s) / 4) * (4 * VA_CACHE_BLK) + ((s) % 4))
+VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
+    const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
+    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK) * 4;
+}
+#else
+#define VA_SLOT_OFF(s) (s)
+VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
+    const size_t bpad = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK) * VA_CACHE_BLK;
+    return ((size_t)dev * bpad + (size_t)inst) * (size_t)ncp;
+}
+#endif
 #define VA_SETUP_BEGIN(NAME) VA_SETUP_BEGIN_(k_setup_##NAME)
 #define VA_SETUPV_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupv_##NAME)
 #define VA_SETUPV_END(NAME) }
@@ -227,7 +250,7 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, 
         const uint8_t* given_ = a.given + (size_t)dev * NPARAM;                                  \
         const double temp_c_ = a.temp_col >= 0 ? a.params[(size_t)a.temp_col * a.B + inst] : a.temp_val; \
         const double gmin_ = a.gmin_col >= 0 ? a.params[(size_t)a.gmin_col * a.B + inst] : a.gmin_val;   \
-        double* cache_ = (double*)a.cache + va_cache_index(a.B, dev, NCACHE, inst);              \
+        double* cache_ = (double*)a.cache + va_cache_index(a.B, dev, NCACHE_P, inst);              \
         (void)gmin_; (void)temp_c_; (void)par_val_; (void)par_col_; (void)given_;
 #define VA_SETUP_END(NAME) }
 
@@ -262,14 +285,35 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncache, 
 VA_FN void va_cp8(unsigned dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
+VA_FN void va_cp16(unsigned dst, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// Ring geometry in shared memory.  8-byte copies: [stage][row][thread] (a thread's slots are NTHR doubles apart,
+// conflict-free).  16-byte copies: [stage][row pair][thread][2].
+#if VA_CACHE_LAYOUT >= 2
+#define VA_RING_IDX(s) (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * (VA_CHUNK_ROWS / 2) + ((s) % VA_CHUNK_ROWS) / 2) * (2 * VA_EVAL_THREADS) + ((s) & 1))
+#define VA_RING_TID(t) (2 * (t))
+template <int ROWS, int STAGES, int NTHR>
+VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
+    static_assert(ROWS % 2 == 0, "16-byte cache copies need an even number of rows per chunk");
+#pragma unroll
+    for (int r = 0; r < ROWS; r += 2) {
+        const int p = chunk * ROWS + r;
+        if (p < ncache) va_cp16(sbase + (unsigned)((((chunk % STAGES) * (ROWS / 2) + r / 2) * (2 * NTHR)) * 8), cache + VA_SLOT_OFF(p));
+    }
+}
+#else
+#define VA_RING_IDX(s) (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS)
+#define VA_RING_TID(t) (t)
 template <int ROWS, int STAGES, int NTHR>
 VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         const int p = chunk * ROWS + r;
-        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + p);
+        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + VA_SLOT_OFF(p));
     }
 }
+#endif
 // (Experiments that did not pay and were removed: CTA-wide barriers at the chunk markers or every ~50 generated
 // lines, and a leader warp running one chunk ahead, to make the warps of a CTA share instruction fetches -- at
 // 128..640 threads per CTA none changed the instruction-cache request count; see DESIGN.md section 5.)
@@ -277,12 +321,12 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_CHUNK(k)                                                                              \
     {                                                                                            \
         if ((k) + VA_AHEAD < VA_NCHUNK)                                                          \
-            va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE, sbase_, cache_); \
+            va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE_P, sbase_, cache_); \
         VA_COMMIT();                                                                             \
         asm volatile("cp.async.wait_group %0;" ::"n"(VA_AHEAD) : "memory");                      \
     }
-#define CACHE_LD(s) ring_[((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS]
-#define CACHE_LDG(s) __ldg(cache_ + (s))
+#define CACHE_LD(s) ring_[VA_RING_IDX(s)]
+#define CACHE_LDG(s) __ldg(cache_ + VA_SLOT_OFF(s))
 
 // value-only variant (k_evalv_*: currents and charges, no Jacobian; its own cache, see CompiledModel.source_v)
 #ifndef VA_EVALV_MINBLOCKS
@@ -307,7 +351,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
     extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
-        extern __shared__ double va_ring_[];                                                     \
+        extern __shared__ __align__(16) double va_ring_[];                                       \
         if (blockDim.x != VA_EVAL_THREADS) __trap();                                             \
         long long inst;                                                                          \
         {                                                                                        \
@@ -316,11 +360,11 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
             inst = a.list[k_];                                                                   \
         }                                                                                        \
         const int dev = blockIdx.y;                                                              \
-        const double* __restrict__ cache_ = a.cache + va_cache_index(a.B, dev, NCACHE, inst);    \
-        const double* ring_ = va_ring_ + threadIdx.x;                                            \
-        const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + threadIdx.x);      \
+        const double* __restrict__ cache_ = a.cache + va_cache_index(a.B, dev, NCACHE_P, inst);    \
+        const double* ring_ = va_ring_ + VA_RING_TID(threadIdx.x);                               \
+        const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + VA_RING_TID(threadIdx.x)); \
         _Pragma("unroll") for (int c_ = 0; c_ < VA_AHEAD; c_++) {                                \
-            if (c_ < VA_NCHUNK) va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE, sbase_, cache_); \
+            if (c_ < VA_NCHUNK) va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE_P, sbase_, cache_); \
             VA_COMMIT();                                                                         \
         }                                                                                        \
         const double alpha_ = a.alpha[inst];                                                     \

@@ -453,7 +453,7 @@ struct Solver {
     // error left after the update is <= 1, rho = n_k / n_{k-1}; nr_rate_test 2 also accepts the first update when
     // 3 kappa n_1^2 <= 1 (see cedarb200.h) (the rate test of Sundials IDA, the reference's solver).
     int newton(std::vector<double>& x, double t, bool dcop, double alpha, const double* beta,
-               double gshunt, int maxit, double restol, std::vector<double>& qk, bool use_rate = false) {
+               double gshunt, int maxit, double restol, std::vector<double>& qk, bool use_rate = false, bool all_full = false) {
         double nrm_prev = 0.0;
         // voltage-step limit: only nonlinear (Verilog-A) devices need it; a purely linear circuit
         // converges in one full step whatever its voltage scale
@@ -461,7 +461,8 @@ struct Solver {
         // Chord (value-only) iterations, transient only: with cb_options.value_rounds = v every (v + 1)-th iteration of a
         // step attempt (0, v + 1, ...) is a full Newton iteration with a fresh Jacobian; the ones in between re-use its
         // LU factors and its dQ/dV (the engine evaluates them with the derivative-free device kernels).  v = 0: plain Newton.
-        const int vcycle = (!dcop && alpha != 0.0) ? std::max(0, opt->value_rounds) + 1 : 1;
+        // all_full: the fixed-step retry of a failed attempt takes full Newton iterations only
+        const int vcycle = (!dcop && alpha != 0.0 && !all_full) ? std::max(0, opt->value_rounds) + 1 : 1;
         for (int it = 0; it < maxit; it++) {
             const bool full = it % vcycle == 0;
             if (full || vcycle == 1) eval_system(in, vc, x.data(), t, dcop, s);
@@ -666,9 +667,9 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
         }
         const bool rate = opt->nr_rate_test != 0;
         int rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk, rate);
-        if (rc != 0 && fixed) {  // fixed step cannot shrink: retry once from the flat guess x_n
+        if (rc != 0 && fixed) {  // fixed step cannot shrink: retry once from the flat guess x_n, fresh Jacobian every iteration
             x = xn;
-            rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk, rate);
+            rc = S.newton(x, tnew, false, alpha, beta.data(), 0.0, opt->max_newton_tran, 1e300, qk, rate, true);
         }
         if (rc != 0) {
             S.cnt.rejected++;
