@@ -11,6 +11,7 @@
 #include <nvrtc.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -724,6 +725,7 @@ struct cb_plan {
     // kernels (+12 % points/s at 4 lanes on the 16 384-point DFF sweep).  lanes.empty() = this is a single lane.
     std::vector<cb_plan*> lanes;
     long long lane_off = 0;            // first sweep point of this lane within its parent
+    bool multi_device = false;         // parent: lanes on more than one GPU (host-array entry points only)
     double* d_params_all = nullptr;    // parent: [P][B] buffer handed out by cb_plan_device_params
     bool params_all_dirty = false;
     double* d_y_all = nullptr;         // parent: contiguous results of the *_device entry points
@@ -1296,6 +1298,7 @@ static int set_x01(cb_plan* p, const double* x0, int per_point, long long pitch)
 
 extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     if (!p || !d_params) return fail(CB_ERR_INVALID, "null argument");
+    if (p->multi_device) return fail(CB_ERR_INVALID, "device-resident entry points need a single-device plan");
     if (!p->lanes.empty()) {   // one [P][B] buffer for the caller; scattered to the lanes before the next solve
         CUDA_TRY(cudaSetDevice(p->device));
         if (!p->d_params_all)
@@ -1998,6 +2001,24 @@ static int default_lanes(int64_t n_inst) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(4, n_inst / 2048));
 }
 
+// points [off, off + n) of the parent on device `device_id`, split into n_lanes lanes
+static int add_lanes(cb_plan* parent, cb_circuit* c, long long off, long long n, int device_id, int n_lanes) {
+    if (n_lanes <= 0) n_lanes = default_lanes(n);
+    n_lanes = (int)std::min<long long>(n_lanes, n);
+    // lane sizes: multiples of 128 points (cache blocks of the device kernels), the last lane takes the remainder
+    const long long per = ((n + n_lanes - 1) / n_lanes + 127) / 128 * 128, end = off + n;
+    while (off < end) {
+        const long long nb = std::min<long long>(per, end - off);
+        cb_plan* l = nullptr;
+        int rc = plan_create1(c, nb, device_id, &l);
+        if (rc != CB_OK) return rc;
+        l->lane_off = off;
+        parent->lanes.push_back(l);
+        off += nb;
+    }
+    return CB_OK;
+}
+
 extern "C" int cb_plan_create_lanes(cb_circuit* c, int64_t n_inst, int device_id, int n_lanes, cb_plan** out) {
     if (!c || !out || n_inst <= 0) return fail(CB_ERR_INVALID, "bad argument");
     if (n_lanes <= 0) n_lanes = default_lanes(n_inst);
@@ -2006,20 +2027,46 @@ extern "C" int cb_plan_create_lanes(cb_circuit* c, int64_t n_inst, int device_id
     if (!c->compiled) return fail(CB_ERR_STATE, "circuit not compiled");
     auto p = std::make_unique<cb_plan>();
     p->c = c; p->B = n_inst; p->device = device_id;
-    // lane sizes: multiples of 128 points (cache blocks of the device kernels), the last lane takes the remainder
-    long long per = ((n_inst + n_lanes - 1) / n_lanes + 127) / 128 * 128, off = 0;
-    while (off < n_inst) {
-        const long long nb = std::min<long long>(per, n_inst - off);
-        cb_plan* l = nullptr;
-        int rc = plan_create1(c, nb, device_id, &l);
+    int rc = add_lanes(p.get(), c, 0, n_inst, device_id, n_lanes);
+    if (rc != CB_OK) { cb_plan_destroy(p.release()); return rc; }
+    p->na.O = (int)c->outputs.size(); p->na.N = c->N;
+    *out = p.release();
+    return CB_OK;
+}
+
+// One plan over several GPUs of this process: device g of G owns the contiguous block
+// [g ceil(B / G), min(B, (g + 1) ceil(B / G))) of the sweep points (blocks rounded up to 128 points), split into lanes
+// like a single-device plan.  Every lane has its own host thread, stream and device context; there is no collective:
+// each device copies its slice of the results straight into the caller's host arrays.
+extern "C" int cb_plan_create_multi(cb_circuit* c, int64_t n_inst, const int* device_ids, int n_devices, int lanes_per_device,
+                                    cb_plan** out) {
+    if (!c || !out || n_inst <= 0 || !device_ids || n_devices <= 0) return fail(CB_ERR_INVALID, "bad argument");
+    if (!c->compiled) return fail(CB_ERR_STATE, "circuit not compiled");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CB_ERR_NO_DEVICE, "no CUDA device available; this engine has no CPU fallback");
+    for (int g = 0; g < n_devices; g++)
+        if (device_ids[g] < 0 || device_ids[g] >= ndev) return fail(CB_ERR_INVALID, "device id out of range");
+    auto p = std::make_unique<cb_plan>();
+    p->c = c; p->B = n_inst; p->device = device_ids[0];
+    const long long per = ((n_inst + n_devices - 1) / n_devices + 127) / 128 * 128;
+    for (int g = 0; g < n_devices; g++) {
+        const long long lo = std::min<long long>(n_inst, (long long)g * per), hi = std::min<long long>(n_inst, lo + per);
+        if (lo >= hi) break;
+        int rc = add_lanes(p.get(), c, lo, hi - lo, device_ids[g], lanes_per_device);
         if (rc != CB_OK) { cb_plan_destroy(p.release()); return rc; }
-        l->lane_off = off;
-        p->lanes.push_back(l);
-        off += nb;
+        if (device_ids[g] != device_ids[0]) p->multi_device = true;
     }
     p->na.O = (int)c->outputs.size(); p->na.N = c->N;
     *out = p.release();
     return CB_OK;
+}
+
+extern "C" int cb_plan_devices(const cb_plan* p) {
+    if (!p) return 0;
+    std::vector<int> seen;
+    for (const cb_plan* l : p->lanes) if (std::find(seen.begin(), seen.end(), l->device) == seen.end()) seen.push_back(l->device);
+    return seen.empty() ? 1 : (int)seen.size();
 }
 
 extern "C" int cb_plan_create(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** out) {
@@ -2155,6 +2202,7 @@ static int gather_device(cb_plan* p, size_t rows, bool tran, double** d_out, int
 
 extern "C" int cb_dc_device(cb_plan* p, const cb_options* opt, double** d_x_out, int32_t** d_status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    if (p->multi_device) return fail(CB_ERR_INVALID, "device-resident entry points need a single-device plan");
     { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return dc_device1(p, opt, d_x_out, d_status, stats);
     int rc = scatter_params(p);
@@ -2169,6 +2217,7 @@ extern "C" int cb_dc_device(cb_plan* p, const cb_options* opt, double** d_x_out,
 extern "C" int cb_tran_device(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save,
                               const cb_options* opt, double** d_y_out, int32_t** d_status, cb_stats* stats) {
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
+    if (p->multi_device) return fail(CB_ERR_INVALID, "device-resident entry points need a single-device plan");
     { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
     if (p->lanes.empty()) return tran_device1(p, t0, t1, saveat, n_save, opt, d_y_out, d_status, stats);
     int rc = scatter_params(p);

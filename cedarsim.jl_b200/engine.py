@@ -22,7 +22,7 @@ _lib = None
 
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_options_default", "cb_options_size", "cb_stats_size", "cb_options_init", "cb_circuit_create", "cb_circuit_load", "cb_circuit_set_cuda_source",
-    "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_create_lanes", "cb_plan_lanes", "cb_plan_set_params", "cb_dc", "cb_tran",
+    "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_create_lanes", "cb_plan_create_multi", "cb_plan_devices", "cb_plan_lanes", "cb_plan_set_params", "cb_dc", "cb_tran",
     "cb_ac", "cb_noise", "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
 ]
 
@@ -127,8 +127,10 @@ class Circuit:
         _check(self.lib.cb_circuit_lu_info(self.handle, C.byref(a), C.byref(l), C.byref(f)))
         return {"nnz_a": a.value, "nnz_lu": l.value, "lu_flops": f.value}
 
-    def plan(self, n_inst: int, device: int = 0, lanes: int = 0) -> "Plan":
-        return Plan(self, n_inst, device, lanes)
+    def plan(self, n_inst: int, device: int = 0, lanes: int = 0, devices: Optional[Sequence[int]] = None) -> "Plan":
+        """devices: several GPUs of this process (cb_plan_create_multi: contiguous block of points per GPU, `lanes`
+        lanes on each); else one GPU."""
+        return Plan(self, n_inst, device, lanes, devices)
 
     def __del__(self):
         try:
@@ -140,16 +142,22 @@ class Circuit:
 
 
 class Plan:
-    def __init__(self, circuit: Circuit, n_inst: int, device: int = 0, lanes: int = 0):
+    def __init__(self, circuit: Circuit, n_inst: int, device: int = 0, lanes: int = 0, devices: Optional[Sequence[int]] = None):
         """lanes: concurrent sub-plans on the device (0 = automatic, see cb_plan_create_lanes)."""
         self.circuit = circuit
         self.lib = circuit.lib
         self.B = int(n_inst)
-        self.device = device
+        self.device = device if not devices else int(devices[0])
         self.handle = C.c_void_p()
-        _check(self.lib.cb_plan_create_lanes(circuit.handle, C.c_int64(self.B), C.c_int(device), C.c_int(lanes),
-                                             C.byref(self.handle)))
+        if devices is not None and len(devices) > 1:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(self.lib.cb_plan_create_multi(circuit.handle, C.c_int64(self.B), ids, C.c_int(len(devices)), C.c_int(lanes),
+                                                 C.byref(self.handle)))
+        else:
+            _check(self.lib.cb_plan_create_lanes(circuit.handle, C.c_int64(self.B), C.c_int(self.device), C.c_int(lanes),
+                                                 C.byref(self.handle)))
         self.lanes = int(self.lib.cb_plan_lanes(self.handle))
+        self.n_devices = int(self.lib.cb_plan_devices(self.handle))
 
     def set_params(self, params: Optional[np.ndarray]):
         P = len(self.circuit.fc.param_names)

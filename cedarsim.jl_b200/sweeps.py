@@ -533,16 +533,11 @@ class CircuitSweep:
         if self._plans:
             return
         self._compiled = engine.Circuit(self.flat.fc, self.flat.models)
-        B, G = len(self), len(self.devices)
-        per = -(-B // G)
-        for g, dev in enumerate(self.devices):
-            lo, hi = g * per, min(B, (g + 1) * per)
-            if lo >= hi:
-                continue
-            plan = self._compiled.plan(hi - lo, device=dev)
-            P = self.flat.params[:, lo:hi] if self.flat.params.size else None
-            plan.set_params(np.ascontiguousarray(P) if P is not None else None)
-            self._plans.append((plan, slice(lo, hi)))
+        # one plan over all the GPUs named in `devices` (cb_plan_create_multi: contiguous block of points per GPU, one
+        # host thread per lane inside the library, results copied straight into the caller's arrays)
+        plan = self._compiled.plan(len(self), devices=self.devices)
+        plan.set_params(np.ascontiguousarray(self.flat.params) if self.flat.params.size else None)
+        self._plans.append((plan, slice(0, len(self))))
 
     def _options(self, kw):
         opts = dict(kw)

@@ -62,3 +62,43 @@ def test_lanes_small_signal(host_bsimcmg):
         out[lanes] = (p.ac(f)[0], p.noise(f)[0])
         p.close()
     assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1], out[2][1])
+
+
+def _multi_case(devices):
+    fc, ms = circuits.inverter(tscale=0.01)
+    B = 700                                    # blocks of 384 + 316 points over two device entries
+    P = np.zeros((3, B))
+    P[fc.param_names.index("vvdd.dc")] = np.linspace(0.6, 0.8, B)
+    P[fc.param_names.index("xneg.nfin")] = 3.0
+    P[fc.param_names.index("xneg.l")] = np.linspace(21e-9, 30e-9, B)
+    ts = np.linspace(0, 2e-9, 41)
+    c = engine.Circuit(fc, ms)
+    out = []
+    for kw in (dict(lanes=1), dict(devices=devices, lanes=2)):
+        p = c.plan(B, **kw)
+        p.set_params(P)
+        xd, xf, sd, _ = p.dc()
+        y, st, _ = p.tran(0.0, 2e-9, ts, engine.default_options(reltol=1e-4))
+        out.append((xd, xf, sd, y, st, p.n_devices, p.lanes))
+        if "devices" in kw and len(set(devices)) > 1:
+            with pytest.raises(engine.EngineError):     # device-resident entry points need a single-device plan
+                p.tran_device(0.0, 2e-9, ts)
+        p.close()
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert np.array_equal(a, b)
+    return out[1][5], out[1][6]
+
+
+def test_multi_device_plan_blocks_on_one_gpu(host_bsimcmg):
+    """cb_plan_create_multi with the same GPU named twice: the partition into per-device blocks and lanes is exercised on
+    a single-GPU box; results equal the single-lane plan bit for bit."""
+    ndev, lanes = _multi_case([0, 0])
+    assert ndev == 1 and lanes == 4
+
+
+def test_multi_device_plan_two_gpus(host_bsimcmg):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    ndev, lanes = _multi_case([0, 1])
+    assert ndev == 2 and lanes == 4
