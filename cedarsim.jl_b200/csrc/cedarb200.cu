@@ -1447,6 +1447,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     o.max_newton_dc = opt->max_newton_dc; o.max_newton_tran = opt->max_newton_tran;
     o.method = opt->method; o.fixed_step = opt->fixed_step; o.gmin_steps = opt->gmin_steps;
     o.skip_dc = opt->skip_dc; o.dc_only = dc_only ? 1 : 0;
+    o.source_steps = std::max(0, opt->source_steps);
     o.rate_test = p->lu ? opt->nr_rate_test : 0;   // needs the charge update of k_lu
     // e_1 / tol ~ (e_0 / tol)^2 tol / (2 Vt): kappa = 20/V x (Newton tolerance of a 1 V signal); learnt values
     // never drop below 1/30 of it
@@ -1726,6 +1727,11 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             std::vector<int> nf((size_t)B);
             CUDA_TRY(cudaMemcpy(nf.data(), a.ist + (size_t)IS_NFULL * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
             for (long long i = 0; i < B; i++) stats->full_iters += nf[i];
+        }
+        {
+            std::vector<int> sg((size_t)2 * B);
+            CUDA_TRY(cudaMemcpy(sg.data(), a.ist + (size_t)IS_SRCSTEP * B, (size_t)2 * B * sizeof(int), cudaMemcpyDeviceToHost));
+            for (long long i = 0; i < B; i++) { stats->dc_source_stepped += sg[i]; stats->pivot_fallbacks += sg[(size_t)B + i]; }
         }
         std::vector<int> cnt((size_t)3 * B);
         CUDA_TRY(cudaMemcpy(cnt.data(), a.ist + (size_t)IS_NNEWTON * B, (size_t)3 * B * sizeof(int), cudaMemcpyDeviceToHost));
@@ -2123,6 +2129,7 @@ static void merge_stats(cb_stats* dst, const std::vector<cb_stats>& st) {
         dst->steps_accepted += s.steps_accepted; dst->steps_rejected += s.steps_rejected;
         dst->rounds += s.rounds; dst->kernel_launches += s.kernel_launches;
         dst->value_rounds += s.value_rounds; dst->full_iters += s.full_iters;
+        dst->pivot_fallbacks += s.pivot_fallbacks; dst->dc_source_stepped += s.dc_source_stepped;
         // lanes run concurrently: wall-like times are the maximum over lanes, per-kernel times add up
         dst->solve_seconds = std::max(dst->solve_seconds, s.solve_seconds);
         dst->h2d_seconds = std::max(dst->h2d_seconds, s.h2d_seconds);

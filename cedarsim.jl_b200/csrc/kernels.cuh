@@ -26,7 +26,7 @@ namespace cbk {
 enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3 };
 // integer per-point state rows
 enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HITBP, IS_METHOD, IS_NP,
-       IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_NFULL, IS_COUNT };
+       IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_NFULL, IS_SRCSTEP, IS_NGROWTH, IS_COUNT };
 // double per-point state rows
 enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_NRM, DS_KAPPA, DS_COUNT };
 // a.active[]: the point's role in the coming round: 0 = finished, 1 = value-only iteration (stored factors), 2 = full
@@ -50,7 +50,7 @@ struct WaveDev {
 struct Opts {
     double reltol, vabstol, iabstol, nr_reltol, nr_vabstol, nr_iabstol, dc_abstol, dv_max;
     double dt, dt_min, dt_max, t0, t1, teps, span, kappa0, kappa_floor;
-    int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only, rate_test;
+    int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only, rate_test, source_steps, pad_o;
     long long nfixed, nsave;
 };
 
@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             if (badpt) {
                 newton_fail = true;
                 status = 4;
+                if ((badpt & 2) && lane == 0) a.ist[(size_t)IS_NGROWTH * B + ii]++;   // pivot-growth monitor of k_lu
             } else {
                 const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
                 double est = nrm;   // estimate of the weighted error left after this update
@@ -388,9 +389,18 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
                     copy_mode = newton_ok ? 2 : 3;
                     stage++; gshunt *= 0.1; status = 0;
                     if (stage == o.gmin_steps) gshunt = 0.0;
-                } else {
-                    dc_done = true;
-                    status = newton_ok ? 0 : 2;
+                } else if (stage == o.gmin_steps) {          // the shunt-free solve that ends the gmin ladder
+                    if (newton_ok) { dc_done = true; status = 0; }
+                    else if (o.source_steps > 0) {           // source stepping: sources ramped from 0, first stage from x = 0
+                        copy_mode = 1;
+                        stage++; gshunt = 0.0; status = 0;
+                    } else { dc_done = true; status = 2; }
+                } else {                                     // source-stepping stage s = stage - gmin_steps of source_steps
+                    if (!newton_ok) { dc_done = true; status = 2; }
+                    else if (stage - o.gmin_steps >= o.source_steps) {
+                        dc_done = true; status = 0;
+                        if (lane == 0) a.ist[(size_t)IS_SRCSTEP * B + ii] = 1;
+                    } else { copy_mode = 2; stage++; status = 0; }
                 }
                 if (dc_done) {
                     gshunt = 0.0;
@@ -517,9 +527,12 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
             if (phase_in == PH_DC && phase != PH_DC) atomicSub(c.dc_count, 1);
         }
-        if (phase != PH_DONE)
+        if (phase != PH_DONE) {
+            // source stepping of the operating point: every independent source times stage / source_steps
+            const double src_scale = (phase == PH_DC && stage > o.gmin_steps) ? (double)(stage - o.gmin_steps) / (double)o.source_steps : 1.0;
             for (int w = lane; w < a.nwaves; w += CTRL_LANES)
-                c.WV[(size_t)w * B + inst] = wave_value(a.waves[w], tnew, phase != PH_TRAN, a.params, B, inst);
+                c.WV[(size_t)w * B + inst] = src_scale * wave_value(a.waves[w], tnew, phase != PH_TRAN, a.params, B, inst);
+        }
     }
     // ---- role of every point in the NEXT round + device-wide compaction.  Warp 0 of the CTA (lane 0 of every point)
     //      holds the scalar state.  Each CTA reserves one contiguous range of each list with a single atomicAdd: the

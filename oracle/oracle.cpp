@@ -60,6 +60,7 @@ struct Inst {  // one sweep point
     const cb_flat_circuit* fc;
     const double* params;  // [P][B]
     int64_t B, b;
+    double src_scale = 1.0;   // source stepping of the operating point: every independent source times this factor
     double pv(const cb_pref& p) const { return p.col < 0 ? p.value : params[(int64_t)p.col * B + b]; }
 };
 
@@ -241,11 +242,11 @@ void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, b
                 double ib = x[b];
                 addf(p, m * ib); addf(n, -m * ib);
                 addG(p, b, m); addG(n, b, -m);
-                s.f[b] += vpn - wave_value(in, fc->waves[dv.wave], t, dcop);
+                s.f[b] += vpn - in.src_scale * wave_value(in, fc->waves[dv.wave], t, dcop);
                 addG(b, p, 1.0); addG(b, n, -1.0);
             } break;
             case CB_DEV_ISRC: {  // I - Isrc = 0, I flows p -> n through the source
-                double i = m * wave_value(in, fc->waves[dv.wave], t, dcop);
+                double i = m * in.src_scale * wave_value(in, fc->waves[dv.wave], t, dcop);
                 addf(p, i); addf(n, -i);
             } break;
             case CB_DEV_VCVS: {
@@ -409,7 +410,7 @@ struct SparseLU {
 };
 
 struct Counters {
-    int64_t newton = 0, factors = 0, accepted = 0, rejected = 0;
+    int64_t newton = 0, factors = 0, accepted = 0, rejected = 0, source_stepped = 0;
 };
 
 struct Solver {
@@ -572,6 +573,19 @@ struct Solver {
             if (rc == 0) x = xs;  // keep the last good point if a stage fails
         }
         rc = newton(x, 0.0, true, 0.0, nullptr, 0.0, opt->max_newton_dc, opt->dc_abstol, qk);
+        if (rc == 0) return CB_ST_SUCCESS;
+        // source stepping (the engine's k_control restates the same ladder): all independent sources ramped from 0 in
+        // source_steps equal steps, every stage starting from the previous solution; any failing stage ends it
+        const int ns = opt->source_steps;
+        if (ns <= 0) return CB_ST_INITIAL_FAILURE;
+        x.assign(N, 0.0);
+        for (int k = 1; k <= ns; k++) {
+            in.src_scale = (double)k / (double)ns;
+            rc = newton(x, 0.0, true, 0.0, nullptr, 0.0, opt->max_newton_dc, opt->dc_abstol, qk);
+            if (rc != 0) break;
+        }
+        in.src_scale = 1.0;
+        if (rc == 0) cnt.source_stepped++;
         return rc == 0 ? CB_ST_SUCCESS : CB_ST_INITIAL_FAILURE;
     }
 };
@@ -770,11 +784,11 @@ void orc_set_x0(const double* x0, int64_t stride) { g_x0 = x0; g_x0_stride = str
 
 int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_options* opt,
            double* x_out, double* x_full, int32_t* status, cb_stats* stats, int nthreads) {
-    int64_t newton = 0, factors = 0;
+    int64_t newton = 0, factors = 0, srcstep = 0;
     const int N = fc->n_unknowns;
     SparseLU shared;
     const SparseLU* sp = (g_sparse && shared.build(fc)) ? &shared : nullptr;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : newton, factors, srcstep)
     for (int64_t b = 0; b < B; b++) {
         Solver S;
         S.sp = sp;
@@ -785,9 +799,9 @@ int orc_dc(const cb_flat_circuit* fc, const double* params, int64_t B, const cb_
         for (int o = 0; o < fc->n_outputs; o++) x_out[(int64_t)o * B + b] = x[fc->outputs[o]];
         if (x_full)
             for (int i = 0; i < N; i++) x_full[(int64_t)i * B + b] = x[i];
-        newton += S.cnt.newton; factors += S.cnt.factors;
+        newton += S.cnt.newton; factors += S.cnt.factors; srcstep += S.cnt.source_stepped;
     }
-    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->newton_iters = newton; stats->lu_factors = factors; }
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->newton_iters = newton; stats->lu_factors = factors; stats->dc_source_stepped = srcstep; }
     return 0;
 }
 
