@@ -128,7 +128,7 @@ static int check_options(const cb_options* o) {
 extern "C" void cb_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
-    o->mixed_rounds = 0; o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e8;
+    o->mixed_rounds = 0; o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e14;
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
@@ -516,14 +516,14 @@ static std::string gen_solve_source(const cb_circuit* c) {
     o << "\n// ---- generated: assembly + static-pivot LU + solve for this circuit (N=" << N << ", nnz(L+U)=" << S.nnz_lu << ")\n";
     o << "struct SArgs { long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA;\n"
          "  const double* dev_out; const double* lin_g; const double* lin_c; const double* WV; const int* active;\n"
-         "  double* DX; double* QK; double* RMAX; int* BAD; double* DVMAX; long long out_stride; };\n";
+         "  double* DX; double* QK; double* RMAX; int* BAD; double* DVMAX; };\n";
     o << "extern \"C\" __global__ void __launch_bounds__(64, 1) k_solve(SArgs a) {\n";
     o << "  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
     o << "  if (inst >= a.B) return;\n  if (a.active[inst] != 1 && a.active[inst] != 2) return;\n";
     o << "  const size_t B = (size_t)a.B;\n";
     o << "  const double al = a.alpha[inst], gs = a.gshunt[inst];\n";
-    o << "  const double* __restrict__ od = a.dev_out + (size_t)inst * a.out_stride;\n";
-    o << "#define OD(s) __ldg(od + (s))\n";
+    o << "  const double* __restrict__ od = a.dev_out + inst;\n";
+    o << "#define OD(s) __ldg(od + (size_t)(s) * B)\n";
     for (int i = 0; i < N; i++) o << "  const double x" << i << " = a.X[" << i << " * B + inst];\n";
     for (size_t w = 0; w < c->waves.size(); w++) o << "  const double w" << w << " = a.WV[" << w << " * B + inst];\n";
     auto LG = [&](int l) { return c->lin_swept ? "lg" + std::to_string(l) : dlit(lg[l]); };
@@ -762,8 +762,6 @@ struct cb_plan {
     bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
-    int lu_warps = 8;
-    long long out_stride = 0, noise_stride = 0;
     int* d_dc_count = nullptr;
     // point lists of the rounds (device-wide compaction, kernels.cuh): [parity][kind][B] and counters [parity][2]
     int* d_lists = nullptr;
@@ -1127,10 +1125,8 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         p->have_v = all;
         p->cachev_slots = total;
     }
-    p->out_stride = pad4((int)c->total_out);   // one contiguous row of device outputs per point
-    TRY(p->alloc(&p->d_dev_out, (size_t)p->out_stride * B));
+    TRY(p->alloc(&p->d_dev_out, (size_t)std::max<long long>(1, c->total_out) * B));
     a.dev_out = p->d_dev_out;
-    a.out_stride = p->out_stride;
     TRY(p->alloc(&p->d_xout, (size_t)std::max<size_t>(1, c->outputs.size()) * B));
     TRY(p->alloc(&p->d_done, 1));
     a.done_count = p->d_done;
@@ -1154,21 +1150,19 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         TRY(p->upload(&dt_, term)); TRY(p->upload(&dc_, pcol)); TRY(p->upload(&dv_, pval)); TRY(p->upload(&dg_, giv));
         p->d_term.push_back(dt_); p->d_par_col.push_back(dc_); p->d_par_val.push_back(dv_); p->d_given.push_back(dg_);
     }
-    // solve kernel: warp-per-point shared-memory LU (k_lu) when one point's matrix fits the shared memory a CTA may
-    // use, else the generated straight-line k_solve (no value-only rounds then; CB_NEWTON=gen forces it)
+    // solve kernel: shared-memory batched LU (k_lu) when the factors of LU_PTS points fit one SM, else the generated
+    // straight-line k_solve (no value-only rounds then)
     {
         int max_smem = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
         const char* env = std::getenv("CB_NEWTON");
-        a.sm_stride = (S.nnz_lu + 2 * N + 3) / 4 * 4;
-        p->lu_warps = WLU_WARPS;
-        p->lu_smem = (size_t)a.sm_stride * WLU_WARPS * sizeof(double);
-        p->lu = !(env && std::string(env) == "gen") && p->lu_smem + 1024 <= (size_t)max_smem;
+        p->lu_smem = (size_t)(S.nnz_lu + 2 * N) * LU_PTS * sizeof(double);
+        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 2048;
+        p->lu = !(env && std::string(env) == "gen") && p->lu_smem + lu_static <= (size_t)max_smem;
         if (!p->lu) p->have_v = false;
         if (p->lu) {
-            const int W = 32;   // the lanes of the warp that owns a point
             LuSchedule sch;
-            build_lu_schedule(S, W, sch);
+            build_lu_schedule(S, LU_W, sch);
             LArgs& la = p->la;
             int4* dops; int* ti;
             TRY(p->upload(&dops, sch.ops)); la.ops = dops;
@@ -1182,72 +1176,70 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             std::vector<int4> sops;
             std::vector<int> sop_ptr;
             int nslev = 0;
-            build_fwd_schedule(S, W, sops, sop_ptr, nslev);
+            build_fwd_schedule(S, LU_W, sops, sop_ptr, nslev);
             TRY(p->upload(&dops, sops)); la.sops = dops;
             TRY(p->upload(&ti, sop_ptr)); la.sop_ptr = ti;
             la.nslev = nslev;
-            // Gather steps.  Items (dev_out row, destination slot, multiplier) sorted by source row; a step takes the next
-            // items, up to 32, whose destinations are pairwise distinct (an item whose destination is already taken in
-            // the step waits for the next one, and so do all later items of that destination: the accumulation order
-            // into a destination is the source-row order, whatever the packing).  Consecutive source rows in a step =
-            // one coalesced warp read of the point's dev_out row.
+            if (std::getenv("CB_DEBUG"))
+                std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu fwd-levels=%d fwd-ops=%zu smem=%zu\n", N,
+                             S.nnz_lu, sch.nlev, sch.nblev, sch.ops.size(), nslev, sops.size(), p->lu_smem);
+            // gather items, grouped by destination and balanced over the warps; the value-only list holds the
+            // residual and charge rows only
             auto item = [](int src, int dst, double m) {
                 long long bits;
                 std::memcpy(&bits, &m, sizeof bits);
                 return make_int4(src, dst, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
             };
-            auto pack_steps = [&](std::vector<int4>& items, std::vector<int4>& steps) {
-                std::stable_sort(items.begin(), items.end(), [](const int4& x, const int4& y) { return x.x < y.x; });
-                std::vector<char> used(items.size(), 0);
-                size_t first = 0;
-                steps.clear();
-                while (first < items.size()) {
-                    std::vector<int4> st;
-                    std::set<int> dsts, blocked;
-                    for (size_t q = first; q < items.size() && st.size() < 32 && q < first + 256; q++) {
-                        if (used[q]) continue;
-                        const int d = items[q].y;
-                        if (dsts.count(d) || blocked.count(d)) { blocked.insert(d); continue; }
-                        dsts.insert(d);
-                        st.push_back(items[q]);
-                        used[q] = 1;
-                    }
-                    while (first < items.size() && used[first]) first++;
-                    st.resize(32, make_int4(-1, 0, 0, 0));
-                    steps.insert(steps.end(), st.begin(), st.end());
-                }
-            };
             for (int pass = 0; pass < 2; pass++) {
-                std::vector<int4> items, steps;
+                std::map<int, std::vector<int4>> by_dst;
                 if (pass == 0)
                     for (int e = 0; e < S.nnz_lu; e++)
-                        for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) items.push_back(item(c->a_src[q], e, c->a_mult[q]));
+                        for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, c->a_mult[q]));
                 for (int i = 0; i < N; i++) {
                     for (int q = c->ri_ptr[i]; q < c->ri_ptr[i + 1]; q++)
-                        items.push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], -c->ri_mult[q]));
+                        by_dst[S.nnz_lu + S.row_to_step[i]].push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], -c->ri_mult[q]));
                     for (int q = c->rq_ptr[i]; q < c->rq_ptr[i + 1]; q++)
-                        items.push_back(item(c->rq_src[q], S.nnz_lu + N + i, c->rq_mult[q]));
+                        by_dst[S.nnz_lu + N + i].push_back(item(c->rq_src[q], S.nnz_lu + N + i, c->rq_mult[q]));
                 }
-                pack_steps(items, steps);
-                TRY(p->upload(&dops, steps));
-                if (pass == 0) { la.gsteps = dops; la.n_gsteps = (int)(steps.size() / 32); }
-                else { la.ssteps = dops; la.n_ssteps = (int)(steps.size() / 32); }
+                std::vector<std::pair<int, int>> groups;
+                for (auto& kv : by_dst) groups.push_back({(int)kv.second.size(), kv.first});
+                std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+                std::vector<std::vector<int4>> per(LU_W);
+                for (auto& g : groups) {
+                    int best = 0;
+                    for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
+                    per[best].insert(per[best].end(), by_dst[g.second].begin(), by_dst[g.second].end());
+                }
+                std::vector<int4> items;
+                std::vector<int> iptr(1, 0);
+                for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
+                TRY(p->upload(&dops, items));
+                TRY(p->upload(&ti, iptr));
+                if (pass == 0) { la.items = dops; la.item_ptr = ti; } else { la.sitems = dops; la.sitem_ptr = ti; }
             }
-            {   // charge-update steps: (dev_out row of dQ/dV, slot of q_row, slot of dx_col, index into cmult)
-                std::vector<int4> items, steps;
-                for (size_t q = 0; q < c->cq_row.size(); q++)
-                    items.push_back(make_int4(c->cq_src[q], S.nnz_lu + N + c->cq_row[q], S.nnz_lu + S.col_to_step[c->cq_col[q]], (int)q));
-                pack_steps(items, steps);
+            {   // charge-update items, all items of one row on one warp
+                std::map<int, std::vector<int>> by_row;
+                for (size_t q = 0; q < c->cq_row.size(); q++) by_row[c->cq_row[q]].push_back((int)q);
+                std::vector<std::pair<int, int>> groups;
+                for (auto& kv : by_row) groups.push_back({(int)kv.second.size(), kv.first});
+                std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+                std::vector<std::vector<int4>> per(LU_W);
+                for (auto& g : groups) {
+                    int best = 0;
+                    for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
+                    for (int q : by_row[g.second])
+                        per[best].push_back(make_int4(c->cq_src[q], S.nnz_lu + N + c->cq_row[q], S.nnz_lu + S.col_to_step[c->cq_col[q]], q));
+                }
+                std::vector<int4> items;
+                std::vector<int> iptr(1, 0);
+                for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
                 double* dm;
-                TRY(p->upload(&dops, steps)); la.csteps = dops; la.n_csteps = (int)(steps.size() / 32);
+                TRY(p->upload(&dops, items)); la.citems = dops;
+                TRY(p->upload(&ti, iptr)); la.citem_ptr = ti;
                 TRY(p->upload(&dm, c->cq_mult)); la.cmult = dm;
             }
-            if (std::getenv("CB_DEBUG"))
-                std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu fwd-levels=%d fwd-ops=%zu gather steps %d / %d / %d smem/CTA=%zu\n",
-                             N, S.nnz_lu, sch.nlev, sch.nblev, sch.ops.size(), nslev, sops.size(), la.n_gsteps, la.n_ssteps, la.n_csteps, p->lu_smem);
             CUDA_TRY(cudaFuncSetAttribute(k_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
             la.LUF = nullptr;
-            la.luf_stride = (S.nnz_lu + 3) / 4 * 4;
         }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
         TRY(p->alloc(&p->d_QK, (size_t)N * B));
@@ -1264,6 +1256,7 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             p->num_sms = std::max(1, prop.multiProcessorCount);
         }
         a.scratch = nullptr;
+        a.sm_stride = 0;
     }
 #undef TRY
     *out = p.release();
@@ -1322,24 +1315,21 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     return CB_OK;
 }
 
-// layout must match struct VaArgs in va_prelude.h
-struct VaArgsH {
-    long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
-    const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
-    double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count; long long out_stride;
-};
-static size_t offsetof_va_count() { return offsetof(VaArgsH, count); }
-
 // which point list a device-evaluation launch runs over: this round's full-iteration or value-only points
 static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false, int parity = 0) {
+    // layout must match struct VaArgs in va_prelude.h
+    struct VaArgsH {
+        long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
+        const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
+        double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
+    };
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha;
     a->list = p->d_lists + ((size_t)parity * 2 + (value_only ? 1 : 0)) * p->B;
     a->count = p->d_cnt + parity * 2 + (value_only ? 1 : 0);
     a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->Bpad : p->d_cache + (size_t)c->cache_off[m] * p->Bpad;
-    a->out = p->d_dev_out + c->out_off[m];
-    a->out_stride = p->out_stride;
+    a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
     a->given = p->d_given[m];
     a->temp_val = opt->temp.value; a->gmin_val = opt->gmin.value;
@@ -1522,9 +1512,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     struct SArgsH {
         long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA; const double* dev_out;
         const double* lin_g; const double* lin_c; const double* WV; const int* active; double* DX; double* QK; double* RMAX; int* BAD;
-        double* DVMAX; long long out_stride;
+        double* DVMAX;
     } sargs{B, a.X, a.alpha, a.dst + (size_t)DS_GSHUNT * B, a.BETA, a.dev_out, a.lin_g, a.lin_c, p->d_WV, a.active,
-            p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX, p->out_stride};
+            p->d_DX, p->d_QK, p->d_RMAX, p->d_BAD, p->d_DVMAX};
     k_init_waves<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(a, p->d_WV);
     CUDA_TRY(cudaGetLastError());
     {
@@ -1536,7 +1526,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     const bool use_v = p->have_v && !dc_only && v_rounds > 0;
     if (use_v && !p->la.LUF) {   // first use: value-only cache and factor storage
         int rc2 = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * p->Bpad);
-        if (rc2 == CB_OK) rc2 = p->alloc(&p->la.LUF, (size_t)p->la.luf_stride * B);
+        if (rc2 == CB_OK) rc2 = p->alloc(&p->la.LUF, (size_t)c->sym.nnz_lu * B);
         if (rc2 != CB_OK) return rc2;
     }
     if (use_v) { int rc2 = run_setupv(p, opt); if (rc2 != CB_OK) return rc2; }
@@ -1564,11 +1554,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     }
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
-    // warp-per-point solver: persistent CTAs of WLU_WARPS points, as many as can be resident
-    int lu_per_sm = 1;
-    if (p->lu) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lu_per_sm, k_lu, 32 * WLU_WARPS, p->lu_smem);
-    const unsigned lu_grid = (unsigned)std::max<long long>(1, std::min<long long>((B + WLU_WARPS - 1) / WLU_WARPS,
-                                                                                  (long long)p->num_sms * std::max(1, lu_per_sm)));
+    const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
     // one round on the plan's streams; `vround`: lock-step value-only round (only the value-only list is non-empty);
     // `next_v`: lock-step schedule of the next round; ev: optional timing events {start, after eval, after evalv, end}
     auto launch_round = [&](int par, bool full_kernels, bool value_kernels, int next_v, cudaEvent_t* ev) -> int {
@@ -1597,7 +1583,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
         }
         if (ev) cudaEventRecord(ev[2], p->stream);
-        if (p->lu) k_lu<<<lu_grid, 32 * WLU_WARPS, p->lu_smem, p->stream>>>(largs[par]);
+        if (p->lu) k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs[par]);
         else {
             void* sargs_ptr[] = {&sargs};
             CUDA_TRY(cudaMemsetAsync(p->d_cnt + (1 - par) * 2, 0, 2 * sizeof(int), p->stream));
@@ -1878,9 +1864,7 @@ static int ac_tables(cb_plan* p, bool noise) {
         ResTab* dr; NoiseTab* dn;
         TRY(p->upload(&dr, rt)); TRY(p->upload(&dn, nt));
         p->aa.rtab = dr; p->aa.ntab = dn; p->aa.nres = (int)rt.size(); p->aa.nnoise = (int)nt.size();
-        p->noise_stride = pad4((int)rows);
-        TRY(p->alloc(&p->d_noise_out, (size_t)p->noise_stride * p->B));
-        p->aa.noise_stride = p->noise_stride;
+        TRY(p->alloc(&p->d_noise_out, (size_t)std::max<long long>(1, rows) * p->B));
         TRY(p->alloc(&p->d_cachen, (size_t)std::max<long long>(1, slots) * p->Bpad));
         p->aa.noise_out = p->d_noise_out;
         p->noise_ready = true;
@@ -1927,12 +1911,7 @@ static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, 
             fill_va_args(p, m, opt, args);
             VaArgsHead* h = (VaArgsHead*)args;
             h->cache = p->d_cachen + (size_t)p->cachen_off[m] * p->Bpad;
-            h->out = p->d_noise_out + p->noise_off[m];
-            {   // the noise kernels write rows of the noise-output array, not of dev_out
-                struct VaArgsTail { const int* count; long long out_stride; };
-                VaArgsTail* tl = (VaArgsTail*)(args + offsetof_va_count());
-                tl->out_stride = p->noise_stride;
-            }
+            h->out = p->d_noise_out + (size_t)p->noise_off[m] * B;
             void* kargs[] = {args};
             if (!p->setupn_valid) {
                 dim3 g((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());

@@ -79,8 +79,7 @@ struct NArgs {
     double *X, *XN, *X1, *X2, *XP, *QN, *Q1, *QD, *BETA, *alpha, *dst;
     int *ist, *active;
     double* scratch;  // GLOB kernels: [nnz_lu + 3N + nwaves][B]
-    const double* dev_out;   // [B][out_stride]: all device outputs of a point are contiguous (written by the eval kernels)
-    long long out_stride;
+    const double* dev_out;
     double* y_out;  // tran: [O][S][B]; dc: [O][B]
     int* done_count;
     Opts o;
@@ -568,97 +567,102 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_lu: assembly + static-pivot sparse LU + triangular solves, ONE WARP PER SWEEP POINT.
+// k_lu: assembly + batched static-pivot sparse LU + triangular solves, factors staged in shared memory.
 //
-// Round 1 gave a CTA 32 points (lane = point) and split every phase over 16 warps with __syncthreads between the ~60
-// phases; its factors took the whole shared memory of an SM, so 32 points were in flight per SM and the kernel ran at
-// 14 % of HBM bandwidth, latency-bound (~100 us per group whatever the batch size).  Here a warp owns one point:
-//   * the point's matrix (nnz(L+U) values), right-hand side and charges live in the warp's own slice of shared memory
-//     (DFF: 6.6 KB), so 32 points are in flight per SM with 4 CTAs of 8 warps -- and a circuit needs only
-//     (nnz + 2 N) * 8 bytes <= 227 KB per WARP, not per 32 points (no fallback kernel for BSIM4-sized circuits);
-//   * phases are separated by __syncwarp, never by a CTA barrier; warps of a CTA run independent points;
-//   * all per-point data the kernel streams is CONTIGUOUS per point: the device outputs of a point are one row of
-//     dev_out ([B][out_stride], written by the eval kernels), its stored factors one row of LUF, so every global access
-//     of the gather phases is one coalesced 256-byte warp access, whatever subset of the points takes part in the round
-//     (the point lists of mixed rounds have gaps; with batch-interleaved rows every gap cost sector efficiency);
-//   * the work of every phase is split over the 32 lanes by host-built schedules:
-//       gather steps   : up to 32 (source, destination, multiplier) items per step, consecutive sources (coalesced),
-//                        distinct destinations inside a step; the order of accumulation into a destination is fixed,
-//                        so results are reproducible bit for bit
-//       elimination    : level by level (pivots whose rows and columns do not update one another form a level), the
-//                        update ops  vals[dst] -= (vals[l] * inv) * vals[u]  of a level split over the lanes with all
-//                        ops into one destination on one lane in ascending pivot order -- the factors equal those of a
-//                        sequential right-looking sweep; forward substitution rides along as an extra column
-//       back substitution: level-scheduled on the U-row dependency DAG
-// Value-only iterations (SOLVE) load the stored factors instead of assembling and eliminating.
-#ifndef WLU_WARPS
-#define WLU_WARPS 8     // points per CTA
+// A CTA owns LU_PTS = 32 consecutive sweep points (lane = point, so every global access is one contiguous
+// 256-byte row segment and there is no divergence) and keeps their matrices in shared memory as
+// vals[entry][lane]: nnz(L+U) entries, the right-hand side in elimination-step order, the charges.  Its LU_W warps
+// split the work of each phase by *entry*, not by point:
+//   1. assembly: warp w gathers the matrix entries / residual rows w, w + LU_W, ... from the batch-
+//      interleaved device outputs (each value is read from HBM exactly once);
+//   2. elimination, level by level: pivots whose rows and columns receive no update from one another are
+//      one level (the internal nodes of all transistors, for instance).  Per level the warps first invert
+//      the level's pivots, then apply its update ops  vals[dst] -= (vals[l] * inv) * vals[u];  ops that
+//      hit the same destination are kept on one warp in ascending pivot order, so the factors are
+//      bit-identical to a sequential right-looking sweep.  The forward substitution is the same op stream
+//      with the right-hand side as an extra column;
+//   3. backward substitution, also level-scheduled on the U-row dependency DAG;
+//   4. dx, max|dv|, max|r| and the singular / non-finite flag.
+// The op lists are warp-uniform int4 streams read through L1; the code is a handful of small loops, so it
+// stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
+// instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
+#ifndef LU_PTS
+#define LU_PTS 32     // points per group (lane = point); 16: two entry-workers per warp, half the shared memory per CTA
 #endif
-#ifndef WLU_MINB
-#define WLU_MINB 4      // 32 warps = 32 points in flight per SM when a point's slice is <= 6.9 KB
+#ifndef LU_W
+#define LU_W 16       // entry-workers per CTA
+#endif
+#ifndef LU_MINB
+#define LU_MINB 1
+#endif
+#ifndef LU_GU
+#define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
 #endif
 struct LArgs {
     NArgs n;
-    // elimination: ops (l, u, dst, pivot diag) per (level, lane)
-    const int4* ops;
-    const int* op_ptr;        // [nlev * 32 + 1]
-    const int* piv;           // diag positions per (level, lane)
-    const int* piv_ptr;       // [nlev * 32 + 1]
-    const int* brow;          // elimination steps per (back level, lane)
-    const int* brow_ptr;      // [nblev * 32 + 1]
+    const int4* ops;          // (l, u, dst, pivot diag) positions into vals
+    const int* op_ptr;        // [nlev * LU_W + 1]
+    const int* piv;           // diag positions
+    const int* piv_ptr;       // [nlev * LU_W + 1]
+    const int* brow;          // elimination steps
+    const int* brow_ptr;      // [nblev * LU_W + 1]
     const int* u_col;         // column step of every U entry (parallel to u_pos)
+    const int4* items;        // (dev_out row, dst position, mult lo, mult hi)
+    const int* item_ptr;      // [LU_W + 1]
     int nlev, nblev;
-    // value-only iterations: forward substitution with the stored factors, (l, rhs source, rhs dst, pivot diag)
-    const int4* sops;
-    const int* sop_ptr;       // [nslev * 32 + 1]
+    // value-only rounds (k_lu<true>): forward substitution with the stored factors
+    const int4* sops;         // (l, rhs source, rhs dst, pivot diag), level-scheduled on the L dependency DAG
+    const int* sop_ptr;       // [nslev * LU_W + 1]
+    const int4* sitems;       // gather items of the residual and charge rows only
+    const int* sitem_ptr;     // [LU_W + 1]
     int nslev, pad1_;
-    // gather steps: item = (dev_out row or -1, destination slot, multiplier lo, hi); [nsteps][32]
-    const int4* gsteps;       // full iterations: Jacobian entries, residual rows, charge rows
-    const int4* ssteps;       // value-only iterations: residual and charge rows
-    int n_gsteps, n_ssteps;
-    // first-order charge update q(x + dx) ~ q(x) + C dx: item = (dev_out row of dQ/dV or -1, slot of q_row, slot of dx_col,
-    // index into cmult); [n_csteps][32]
-    const int4* csteps;
-    const double* cmult;
-    int n_csteps, pad2_;
-    Lists cur;                // this round's point lists: full-iteration points, then value-only points
+    Lists cur;                // this round's point lists: groups of LU_PTS full-iteration points, then of value-only points
     int* zero_cnt;            // counters of the NEXT round's lists (k_control of this round fills them): zeroed here
-    double* LUF;              // [B][luf_stride] factors of each point's last full iteration: L (unscaled), U, inverted pivots
-    long long luf_stride;
+    // first-order charge update  q(x + dx) ~ q(x) + C dx:  items (dev_out row of dQ/dV, vals slot of q_row, vals slot of
+    // dx_col, index into cmult), grouped by destination row like the gather items
+    const int4* citems;
+    const int* citem_ptr;     // [LU_W + 1]
+    const double* cmult;
+    double* LUF;              // [nnz_lu][B] factors of the last full round: L (unscaled), U, inverted pivots
     const double* WV;
     double *DX, *QK, *RMAX, *DVMAX;
     int* BAD;
-    double growth_max;        // pivot-growth bound: |multiplier| above it flags the point (BAD bit 1)
+    double growth_max;        // pivot-growth bound: an elimination multiplier above it flags the point (BAD bit 1)
 };
 
+// One group of LU_PTS points (lane = point) of one kind: SOLVE = value-only iteration with the stored factors.
 template <bool SOLVE>
-__device__ __forceinline__ void wlu_point(const LArgs& c, double* __restrict__ v, const long long inst, const int lane) {
+__device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (*s_red)[LU_W][LU_PTS], int (*s_bad)[LU_PTS],
+                                         const long long inst, const bool on, const int lane, const int w) {
     const NArgs& a = c.n;
     const long long B = a.B;
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
+    double* __restrict__ vals = vals_ + lane;
+#define VL(i) vals[(size_t)(i) * LU_PTS]
     const double alpha = a.alpha[inst], gshunt = a.dst[(size_t)DS_GSHUNT * B + inst];
-    const double* __restrict__ od = a.dev_out + (size_t)inst * a.out_stride;
+    const double* __restrict__ od = a.dev_out + inst;
     const double* __restrict__ X = a.X + inst;
-    double* __restrict__ Fv = v + nnz;        // right-hand side in elimination-step order
-    double* __restrict__ Qv = v + nnz + N;    // charges in row order
-    double* __restrict__ lf = c.LUF ? c.LUF + (size_t)inst * c.luf_stride : nullptr;
-    // ---- 1a. stored factors (value-only) or the linear part: A = G_lin + alpha C_lin (+ gshunt on node diagonals);
+    // ---- 1a. linear part (cached / uniform loads only): A = G_lin + alpha C_lin (+ gshunt on node diagonals),
     //          F = -(f_lin + beta) in step order, Q = q_lin in row order
+    double* __restrict__ Fv = vals + (size_t)nnz * LU_PTS;
+    double* __restrict__ Qv = vals + (size_t)(nnz + N) * LU_PTS;
     if (SOLVE) {
-        for (int e = lane; e < nnz; e += 32) v[e] = lf[e];
+        const double* __restrict__ lf = c.LUF + inst;
+#pragma unroll 4
+        for (int e = w; e < nnz; e += LU_W) VL(e) = lf[(size_t)e * B];
     } else {
-        for (int e = lane; e < nnz; e += 32) {
-            double x = 0.0;
+        for (int e = w; e < nnz; e += LU_W) {
+            double v = 0.0;
             const int lin = a.a_lin[e];
             if (lin >= 0) {
                 const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
-                x = a.lin_g[li] + alpha * a.lin_c[li];
+                v = a.lin_g[li] + alpha * a.lin_c[li];
             }
-            if (a.a_diag[e]) x += gshunt;
-            v[e] = x;
+            if (a.a_diag[e]) v += gshunt;
+            VL(e) = v;
         }
     }
-    for (int i = lane; i < N; i += 32) {
+    for (int i = w; i < N; i += LU_W) {
         double f = 0.0, q = 0.0;
         for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
             const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
@@ -668,52 +672,55 @@ __device__ __forceinline__ void wlu_point(const LArgs& c, double* __restrict__ v
         }
         for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * c.WV[(size_t)a.rs_wave[p] * B + inst];
         if (i < NV) f += gshunt * X[(size_t)i * B];
-        Fv[a.row_to_step[i]] = -(f + a.BETA[(size_t)i * B + inst]);
-        Qv[i] = q;
+        Fv[(size_t)a.row_to_step[i] * LU_PTS] = -(f + a.BETA[(size_t)i * B + inst]);
+        Qv[(size_t)i * LU_PTS] = q;
     }
-    __syncwarp();
-    // ---- 1b. device outputs: coalesced reads of the point's dev_out row, 4 steps of loads in flight
+    __syncthreads();
+    // ---- 1b. device outputs: one flat stream of (src row, dst, mult) items, LU_GU independent HBM loads in
+    //          flight per warp; all items of one destination are on one warp
     {
-        const int4* __restrict__ st = SOLVE ? c.ssteps : c.gsteps;
-        const int ns = SOLVE ? c.n_ssteps : c.n_gsteps;
-        for (int s0 = 0; s0 < ns; s0 += 4) {
-            int4 it[4];
-            double x[4];
+        const int4* __restrict__ items = SOLVE ? c.sitems : c.items;
+        int q0 = SOLVE ? c.sitem_ptr[w] : c.item_ptr[w];
+        const int q1 = SOLVE ? c.sitem_ptr[w + 1] : c.item_ptr[w + 1];
+        for (; q0 < q1; q0 += LU_GU) {
+            int4 it[LU_GU];
+            double v[LU_GU];
 #pragma unroll
-            for (int u = 0; u < 4; u++) it[u] = s0 + u < ns ? __ldg(st + (size_t)(s0 + u) * 32 + lane) : make_int4(-1, 0, 0, 0);
+            for (int u = 0; u < LU_GU; u++) it[u] = __ldg(items + min(q0 + u, q1 - 1));
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = it[u].x >= 0 ? __ldg(od + it[u].x) : 0.0;
+            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (it[u].x >= 0) v[it[u].y] += __hiloint2double(it[u].w, it[u].z) * x[u];
-                __syncwarp();
-            }
+            for (int u = 0; u < LU_GU; u++)
+                if (q0 + u < q1) VL(it[u].y) += __hiloint2double(it[u].w, it[u].z) * v[u];
         }
     }
-    // ---- 1c. residual rows: b = -(f + alpha q + beta)
+    __syncthreads();
+    // ---- 1c. residual rows: b = -(f + alpha q + beta), charges out
     double rmax = 0.0;
-    for (int i = lane; i < N; i += 32) {
-        double* bp = Fv + a.row_to_step[i];
-        const double b = *bp - alpha * Qv[i];
+    for (int i = w; i < N; i += LU_W) {
+        const double q = Qv[(size_t)i * LU_PTS];
+        double* bp = Fv + (size_t)a.row_to_step[i] * LU_PTS;
+        const double b = *bp - alpha * q;
         *bp = b;
         rmax = fmax(rmax, fabs(b));
     }
+    s_red[0][w][lane] = rmax;
     int bad = 0;
-    __syncwarp();
-    // ---- 2. elimination by levels (fused forward substitution)
+    __syncthreads();
+    // ---- 2. elimination by levels (fused forward substitution) ------------------------------------------
     const int nlev = SOLVE ? c.nslev : c.nlev;
     const int4* __restrict__ ops = SOLVE ? c.sops : c.ops;
     const int* __restrict__ op_ptr = SOLVE ? c.sop_ptr : c.op_ptr;
     for (int lv = 0; lv < nlev; lv++) {
-        const int slot = lv * 32 + lane;
+        const int slot = lv * LU_W + w;
         if (!SOLVE) {
             for (int p = c.piv_ptr[slot]; p < c.piv_ptr[slot + 1]; p++) {
                 const int dp = c.piv[p];
-                const double d = v[dp];
+                const double d = VL(dp);
                 bad |= !(fabs(d) > 0.0);
-                v[dp] = 1.0 / d;
+                VL(dp) = 1.0 / d;
             }
-            __syncwarp();
+            __syncthreads();
         }
         int q0 = op_ptr[slot];
         const int q1 = op_ptr[slot + 1];
@@ -722,82 +729,107 @@ __device__ __forceinline__ void wlu_point(const LArgs& c, double* __restrict__ v
             for (; q0 < q1; q0++) {
                 const int4 cur = op;
                 if (q0 + 1 < q1) op = __ldg(ops + q0 + 1);
-                const double l = v[cur.x] * v[cur.w];
-                if (!SOLVE) bad |= (fabs(l) > c.growth_max) << 1;
-                v[cur.z] -= l * v[cur.y];
+                const double l = VL(cur.x) * VL(cur.w);
+                if (!SOLVE) bad |= (fabs(l) > c.growth_max) << 1;   // pivot-growth monitor (BAD bit 1)
+                VL(cur.z) -= l * VL(cur.y);
             }
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (!SOLVE && lf)   // keep the factors for the value-only iterations that follow
-        for (int e = lane; e < nnz; e += 32) lf[e] = v[e];
+    if (!SOLVE && c.LUF) {   // keep the factors for the value-only rounds that follow
+        double* __restrict__ lf = c.LUF + inst;
+        if (on)
+#pragma unroll 4
+            for (int e = w; e < nnz; e += LU_W) lf[(size_t)e * B] = VL(e);
+    }
     // ---- 3. backward substitution by levels: x_k = (b_k - sum_j u_kj x_j) * inv_k, in place in the rhs slots
     for (int lv = 0; lv < c.nblev; lv++) {
-        const int slot = lv * 32 + lane;
+        const int slot = lv * LU_W + w;
         for (int p = c.brow_ptr[slot]; p < c.brow_ptr[slot + 1]; p++) {
             const int k = c.brow[p];
-            double acc = Fv[k];
-            for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) acc -= v[a.u_pos[u]] * Fv[c.u_col[u]];
-            Fv[k] = acc * v[a.diag_pos[k]];
+            double acc = VL(nnz + k);
+            for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) acc -= VL(a.u_pos[u]) * VL(nnz + c.u_col[u]);
+            VL(nnz + k) = acc * VL(a.diag_pos[k]);
         }
-        __syncwarp();
+        __syncthreads();
     }
-    // ---- 3b. charges of the updated iterate to first order: q(x + dx) ~ q(x) + C dx (linear capacitors exactly).  The
-    //          accepted step keeps these charges, so they must belong to the iterate that is accepted, not to the point of
-    //          the last device evaluation (|dx| away).  In value-only iterations dQ/dV is that of the last full iteration
-    //          (the C rows of dev_out are written by full evaluations only).  Only the rate-based acceptance tests need it.
+    // ---- 3b. charges of the updated iterate to first order: q(x + dx) ~ q(x) + C dx (linear capacitors exactly).
+    //          The accepted step keeps these charges, so they must belong to the iterate that is accepted, not to
+    //          the point of the last device evaluation (which lies |dx| away).  In value-only rounds dQ/dV is that
+    //          of the last full round.
+    //          Only the rate-based acceptance tests need it: the plain test accepts when |dx| is below the Newton
+    //          tolerance, where the update is negligible.
     if (a.o.rate_test) {
-        for (int i = lane; i < N; i += 32) {
-            double dq = 0.0;
-            for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
-                const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
-                dq += a.lin_c[li] * Fv[a.col_to_step[a.rl_col[p]]];
-            }
-            Qv[i] += dq;
+    for (int i = w; i < N; i += LU_W) {
+        double dq = 0.0;
+        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
+            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+            dq += a.lin_c[li] * VL(nnz + a.col_to_step[a.rl_col[p]]);
         }
-        __syncwarp();
-        for (int s0 = 0; s0 < c.n_csteps; s0 += 4) {
-            int4 it[4];
-            double x[4];
+        Qv[(size_t)i * LU_PTS] += dq;
+    }
+    __syncthreads();
+    {
+        int q0 = c.citem_ptr[w];
+        const int q1 = c.citem_ptr[w + 1];
+        for (; q0 < q1; q0 += LU_GU) {
+            int4 it[LU_GU];
+            double v[LU_GU];
 #pragma unroll
-            for (int u = 0; u < 4; u++) it[u] = s0 + u < c.n_csteps ? __ldg(c.csteps + (size_t)(s0 + u) * 32 + lane) : make_int4(-1, 0, 0, 0);
+            for (int u = 0; u < LU_GU; u++) it[u] = __ldg(c.citems + min(q0 + u, q1 - 1));
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = it[u].x >= 0 ? __ldg(od + it[u].x) * __ldg(c.cmult + it[u].w) : 0.0;
+            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (it[u].x >= 0) v[it[u].y] += x[u] * v[it[u].z];
-                __syncwarp();
-            }
+            for (int u = 0; u < LU_GU; u++)
+                if (q0 + u < q1) VL(it[u].y) += __ldg(c.cmult + it[u].w) * v[u] * VL(it[u].z);
         }
     }
-    // ---- 4. charges, update vector, norms
+    __syncthreads();
+    }
+    if (on)
+        for (int i = w; i < N; i += LU_W) c.QK[(size_t)i * B + inst] = Qv[(size_t)i * LU_PTS];
+    // ---- 4. update vector and norms ---------------------------------------------------------------------
     double dvm = 0.0;
-    for (int i = lane; i < N; i += 32) {
-        c.QK[(size_t)i * B + inst] = Qv[i];
-        const double dx = Fv[a.col_to_step[i]];
-        c.DX[(size_t)i * B + inst] = dx;
+    for (int i = w; i < N; i += LU_W) {
+        const double dx = VL(nnz + a.col_to_step[i]);
+        if (on) c.DX[(size_t)i * B + inst] = dx;
         if (i < NV) dvm = fmax(dvm, fabs(dx));
         bad |= !isfinite(dx);
     }
+    s_red[1][w][lane] = dvm;
+    s_bad[w][lane] = bad;
+    __syncthreads();
+    if (w == 0 && on) {
+        double r = 0.0, d = 0.0;
+        int b = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-        dvm = fmax(dvm, __shfl_xor_sync(0xffffffffu, dvm, o));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        for (int k = 0; k < LU_W; k++) { r = fmax(r, s_red[0][k][lane]); d = fmax(d, s_red[1][k][lane]); b |= s_bad[k][lane]; }
+        c.RMAX[inst] = r; c.DVMAX[inst] = d; c.BAD[inst] = b;
     }
-    if (lane == 0) { c.RMAX[inst] = rmax; c.DVMAX[inst] = dvm; c.BAD[inst] = bad; }
-    __syncwarp();   // the next point of this warp reuses the slice
+    __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
+#undef VL
 }
 
-__global__ void __launch_bounds__(32 * WLU_WARPS, WLU_MINB) k_lu(const LArgs c) {
+// A CTA works through groups g = blockIdx.x, blockIdx.x + gridDim.x, ... of this round's lists: first the groups of
+// full-iteration points (assembly + LU + solves, factors stored), then the groups of value-only points (solves with the
+// stored factors).  The lists are dense (device-wide compaction by k_control), so every group but the last of each kind
+// is full whatever fraction of the sweep points takes part in the round.
+__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
     extern __shared__ double vals_[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ double s_red[2][LU_W][LU_PTS];
+    __shared__ int s_bad[LU_W][LU_PTS];
+    const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
     if (blockIdx.x == 0 && threadIdx.x < 2) c.zero_cnt[threadIdx.x] = 0;
     const int nf = c.cur.cnt[0], na = c.cur.cnt[1];
-    double* v = vals_ + (size_t)w * c.n.sm_stride;
-    for (int k = blockIdx.x * WLU_WARPS + w; k < nf + na; k += gridDim.x * WLU_WARPS) {
-        if (k < nf) wlu_point<false>(c, v, c.cur.full[k], lane);
-        else wlu_point<true>(c, v, c.cur.any[k - nf], lane);
+    const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS;
+    for (int g = blockIdx.x; g < gf + ga; g += gridDim.x) {
+        const bool solve = g >= gf;
+        const int g0 = (solve ? g - gf : g) * LU_PTS, n = solve ? na : nf;
+        const int* __restrict__ list = solve ? c.cur.any : c.cur.full;
+        const bool on = g0 + lane < n;
+        const long long inst = list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
+        if (solve) lu_group<true>(c, vals_, s_red, s_bad, inst, on, lane, w);
+        else lu_group<false>(c, vals_, s_red, s_bad, inst, on, lane, w);
     }
 }
 
@@ -831,8 +863,7 @@ struct AArgs {
     const double* ac_rhs;     // [N] in elimination-step order (AC)
     const NoiseTab* ntab;     // Verilog-A noise sources
     const ResTab* rtab;       // resistors
-    const double* noise_out;  // [B][noise_stride] outputs of k_evaln_*
-    long long noise_stride;
+    const double* noise_out;  // [rows][B] outputs of k_evaln_*
     int nnoise, nres, F, pad;
     double temp_val; int temp_col, pad2;
     double* out;              // AC: [O][F][B][2]; noise: [O][F][B]
@@ -866,7 +897,7 @@ __global__ void __launch_bounds__(AC_PTS * AC_W) k_ac(const AArgs c) {
     const int N = a.N, nnz = a.nnz_lu;
     double2* __restrict__ vals = av_ + lane;
 #define VA(i) vals[(size_t)(i) * AC_PTS]
-    const double* __restrict__ od = a.dev_out + (size_t)inst * a.out_stride;
+    const double* __restrict__ od = a.dev_out + inst;
     // ---- 1. assembly
     for (int e = w; e < nnz; e += AC_W) {
         double2 v = make_double2(0.0, 0.0);
@@ -878,8 +909,8 @@ __global__ void __launch_bounds__(AC_PTS * AC_W) k_ac(const AArgs c) {
         }
         for (int q = a.a_ptr[e]; q < a.a_ptr[e + 1]; q++) {
             const double m = a.a_mult[q];
-            v.x += m * __ldg(od + a.a_src[q]);
-            v.y += m * omega * __ldg(od + c.a_csrc[q]);
+            v.x += m * __ldg(od + (size_t)a.a_src[q] * B);
+            v.y += m * omega * __ldg(od + (size_t)c.a_csrc[q] * B);
         }
         VA(e) = v;
     }
@@ -982,8 +1013,8 @@ __global__ void __launch_bounds__(AC_PTS * AC_W) k_ac(const AArgs c) {
                 double2 h = make_double2(0.0, 0.0);
                 if (t.pos >= 0) h = VA(nnz + t.pos);
                 if (t.neg >= 0) { const double2 g = VA(nnz + t.neg); h.x -= g.x; h.y -= g.y; }
-                const double pw = __ldg(c.noise_out + (size_t)inst * c.noise_stride + t.pwr_row);
-                const double ex = __ldg(c.noise_out + (size_t)inst * c.noise_stride + t.exp_row);
+                const double pw = __ldg(c.noise_out + (size_t)t.pwr_row * B + inst);
+                const double ex = __ldg(c.noise_out + (size_t)t.exp_row * B + inst);
                 acc += (h.x * h.x + h.y * h.y) * t.mult * (ex == 0.0 ? pw : pw / pow(freq, ex));
             }
             s_acc[w][lane] = acc;

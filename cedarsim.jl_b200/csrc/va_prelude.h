@@ -18,8 +18,7 @@ struct VaArgs {
     const double* alpha;         // [B]    d/dt discretisation coefficient of each point
     const int* list;             // [*count] sweep points that take part in this launch (device-wide compaction by k_control)
     const double* cache;         // [ndev][NCACHE][B] bias-independent values
-    double* out;                 // [B][out_stride]: per point one contiguous row; this model's devices at [dev][NOUT]:
-                                 //                   I | Q | J = dI/dV + alpha dQ/dV | C = dQ/dV
+    double* out;                 // [ndev][NOUT][B]   I | Q | J = dI/dV + alpha dQ/dV
     const int* term;             // [ndev][NT] unknown index per terminal, -1 = ground
     const double* params;        // [P][B] swept parameters
     const double* par_val;       // [ndev][NPARAM]
@@ -29,8 +28,6 @@ struct VaArgs {
     int temp_col; int gmin_col;
     const int* count;            // number of entries of `list` (a device counter: the grid is sized for all B points and
                                  // CTAs beyond the count exit at once)
-    long long out_stride;        // doubles per point in `out` (all device outputs of a point are contiguous: the solver
-                                 // kernel reads them with one warp per point, fully coalesced whatever points take part)
 };
 
 // Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
@@ -198,12 +195,12 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define GMIN_V gmin_
 #define CACHE_ST(s, v) cache_[VA_SLOT_OFF(s)] = (double)(v)
 #define VT(k) vt_[k]
-#define OUT_I(k, v) out_[(k)] = (v)
-#define OUT_Q(k, v) out_[NT + (k)] = (v)
+#define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
+#define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
 // J = dI/dV + alpha dQ/dV for the Newton matrix, and dQ/dV on its own (rows 2 NT + NJ ...) for the first-order
 // charge update q(x + dx) ~ q(x) + C dx of k_lu
-#define OUT_J(idx, k, l, g, c) { const double c_ = (c); out_[2 * NT + (idx)] = (g) + alpha_ * c_; \
-                                 out_[2 * NT + NJ + (idx)] = c_; }
+#define OUT_J(idx, k, l, g, c) { const double c_ = (c); out_[(size_t)(2 * NT + (idx)) * a.B] = (g) + alpha_ * c_; \
+                                 out_[(size_t)(2 * NT + NJ + (idx)) * a.B] = c_; }
 
 // Per-instance cache: NCACHE_P = NCACHE rounded up to whole 32-byte sectors of doubles per (device, point), in the order
 // the eval function consumes it.  Layouts (VA_CACHE_LAYOUT, the engine only sizes the allocation):
@@ -217,7 +214,7 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 //                                                         two 16-byte cp.async.cg per chunk.  HBM traffic = the rows of the
 //                                                         listed points only, and a warp request still spans few lines
 #ifndef VA_CACHE_LAYOUT
-#define VA_CACHE_LAYOUT 3
+#define VA_CACHE_LAYOUT 0
 #endif
 #define VA_CACHE_BLK 128   // rows are allocated for B rounded up to a multiple of this
 #define NCACHE_P ((NCACHE + 3) / 4 * 4)
@@ -341,8 +338,8 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_SETUPN_END(NAME) }
 #define VA_EVALN_BEGIN(NAME) VA_EVAL_BEGIN_(k_evaln_##NAME, va_metan_##NAME, 1)
 #define VA_EVALN_END(NAME) VA_EVAL_END(NAME)
-#define OUT_N(k, v) out_[(k)] = (v)
-#define OUT_NE(k, v) out_[NNOISE + (k)] = (v)
+#define OUT_N(k, v) out_[(size_t)(k) * a.B] = (v)
+#define OUT_NE(k, v) out_[(size_t)(NNOISE + (k)) * a.B] = (v)
 #define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
 #define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
 #define VA_EVALV_END(NAME) VA_EVAL_END(NAME)
@@ -371,7 +368,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
             VA_COMMIT();                                                                         \
         }                                                                                        \
         const double alpha_ = a.alpha[inst];                                                     \
-        double* __restrict__ out_ = a.out + (size_t)inst * a.out_stride + (size_t)dev * NOUT;    \
+        double* __restrict__ out_ = a.out + ((size_t)dev * NOUT) * a.B + inst;                   \
         double vt_[NT];                                                                          \
         _Pragma("unroll") for (int k_ = 0; k_ < NT; k_++) {                                      \
             const int n_ = a.term[dev * NT + k_];                                                \

@@ -763,7 +763,7 @@ void orc_set_sparse(int on) { g_sparse = on; }
 void orc_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
-    o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e8;
+    o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e14;
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;

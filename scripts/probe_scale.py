@@ -39,7 +39,8 @@ def main():
         print(json.dumps({"B": B, "lanes": plan.lanes, "fixed": fixed, "sec": el, "points_per_s": B / el, "rounds": st["rounds"],
                           "value_rounds": st["value_rounds"], "us_per_round": 1e6 * el / max(1, st["rounds"]) * plan.lanes,
                           "iters_per_point": st["newton_iters"] / B, "full_iters_per_point": st["full_iters"] / B,
-                          "launches": st["kernel_launches"]}), flush=True)
+                          "launches": st["kernel_launches"],
+                          "timing_s": {k: round(st[k], 4) for k in ("eval_seconds", "evalv_seconds", "newton_seconds", "newtonv_seconds", "solve_seconds")}}), flush=True)
         plan.close()
 
 

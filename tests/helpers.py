@@ -7,7 +7,7 @@ from oracle import orc
 
 OPT_KEYS = ("reltol", "vabstol", "iabstol", "nr_reltol", "nr_vabstol", "nr_iabstol", "dc_abstol", "dv_max",
             "max_newton_dc", "max_newton_tran", "method", "fixed_step", "dt", "dt_min", "dt_max", "gmin_steps", "skip_dc",
-            "temp", "gmin", "nr_rate_test", "value_rounds", "mixed_rounds")
+            "temp", "gmin", "nr_rate_test", "value_rounds", "mixed_rounds", "source_steps")
 
 
 def both_options(**kw):

@@ -210,3 +210,40 @@ def test_ragged_batch_sizes(host_bsimcmg, B):
     assert yg.shape == yo.shape == (len(fc.outputs), 21, B)
     assert sg.max() == 0 and so.max() == 0
     assert_tran_close(yg, yo)
+
+
+def test_source_stepping_rescues_the_operating_point(host_bsimcmg):
+    """Newton limited to 6 iterations and no gmin ladder: the plain solve fails for 7 of the 8 points, source stepping
+    (all independent sources ramped from 0 in 20 stages, each from the previous solution) finds their operating points.
+    Same ladder in the engine's k_control and in the oracle."""
+    fc, ms = circuits.inverter(host=host_bsimcmg, tscale=0.01)
+    B = 8
+    P = np.zeros((3, B))
+    P[fc.param_names.index("vvdd.dc")] = np.linspace(0.6, 0.8, B)
+    P[fc.param_names.index("xneg.nfin")] = 3.0
+    P[fc.param_names.index("xneg.l")] = 21e-9
+    kw = dict(max_newton_dc=6, gmin_steps=0)
+    (xg, xfg, sg, stg), (xo, xfo, so, sto) = run_dc_both(fc, ms, P, source_steps=0, **kw)
+    assert np.array_equal(sg, so) and (sg != 0).sum() == 7
+    (xg, xfg, sg, stg), (xo, xfo, so, sto) = run_dc_both(fc, ms, P, source_steps=20, **kw)
+    assert sg.max() == 0 and so.max() == 0
+    assert stg["dc_source_stepped"] == sto["dc_source_stepped"] == 7
+    assert np.abs(xfg - xfo).max() < DC_VTOL
+
+
+def test_pivot_growth_monitor_flags_instead_of_losing_accuracy(host_bsimcmg):
+    fc, ms = circuits.inverter(host=host_bsimcmg, tscale=0.01)
+    B = 4
+    P = np.zeros((3, B))
+    P[fc.param_names.index("vvdd.dc")] = 0.7
+    P[fc.param_names.index("xneg.nfin")] = 3.0
+    P[fc.param_names.index("xneg.l")] = 21e-9
+    from cedarsim.jl_b200 import engine
+    plan = engine.Circuit(fc, ms).plan(B)
+    plan.set_params(P)
+    x, xf, st, stats = plan.dc(engine.default_options())
+    assert st.max() == 0 and stats["pivot_fallbacks"] == 0
+    # an absurdly small bound: every factorisation is flagged, no point may be reported as converged
+    x, xf, st, stats = plan.dc(engine.default_options(pivot_growth_max=1e-6, gmin_steps=2, source_steps=2, max_newton_dc=10))
+    assert st.min() != 0 and stats["pivot_fallbacks"] > 0
+    plan.close()
