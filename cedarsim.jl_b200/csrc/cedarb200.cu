@@ -1438,6 +1438,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     o.method = opt->method; o.fixed_step = opt->fixed_step; o.gmin_steps = opt->gmin_steps;
     o.skip_dc = opt->skip_dc; o.dc_only = dc_only ? 1 : 0;
     o.source_steps = std::max(0, opt->source_steps);
+    o.reinit = 0;   // t0 re-initialisation only when a source's DC value may differ from its transient value at t0
+    if (opt->t0_reinit && !dc_only)
+        for (const WaveH& w : c->waves) if (w.has_dc && w.kind != CB_W_DC) o.reinit = 1;
     o.rate_test = p->lu ? opt->nr_rate_test : 0;   // needs the charge update of k_lu
     // e_1 / tol ~ (e_0 / tol)^2 tol / (2 Vt): kappa = 20/V x (Newton tolerance of a 1 V signal); learnt values
     // never drop below 1/30 of it

@@ -23,7 +23,10 @@
 
 namespace cbk {
 
-enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3 };
+// PH_REINIT: consistent re-initialisation at t0 between the operating point and the first step (cb_options.t0_reinit):
+// a Newton solve of the backward-Euler equations of a step of vanishing length h0 with the sources at their transient
+// values -- charges are held, algebraic unknowns follow the sources (reference src/dcop.jl:146-153)
+enum { PH_DC = 0, PH_TRAN_INIT = 1, PH_TRAN = 2, PH_DONE = 3, PH_REINIT = 4 };
 // integer per-point state rows
 enum { IS_PHASE = 0, IS_IT, IS_STAGE, IS_NH, IS_BPI, IS_KSTEP, IS_STATUS, IS_HITBP, IS_METHOD, IS_NP,
        IS_SIDX, IS_NNEWTON, IS_NACC, IS_NREJ, IS_RETRY, IS_NFULL, IS_SRCSTEP, IS_NGROWTH, IS_COUNT };
@@ -50,7 +53,7 @@ struct WaveDev {
 struct Opts {
     double reltol, vabstol, iabstol, nr_reltol, nr_vabstol, nr_iabstol, dc_abstol, dv_max;
     double dt, dt_min, dt_max, t0, t1, teps, span, kappa0, kappa_floor;
-    int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only, rate_test, source_steps, pad_o;
+    int max_newton_dc, max_newton_tran, method, fixed_step, gmin_steps, skip_dc, dc_only, rate_test, source_steps, reinit;
     long long nfixed, nsave;
 };
 
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     bool do_accept = false;        // shift history, QD/QN from this iterate
     int copy_mode = 0;             // 1: X <- 0, XN <- 0   2: XN <- X   3: X <- XN   4: QN <- QK, QD <- 0
     int out_from = 0, out_to = 0, nh_out = 0;  // save points [out_from, out_to) are emitted from the NEW history
-    bool out_init = false;         // PH_TRAN_INIT: save points at t0 are emitted from XN
+    bool out_init = false;         // save points at t0 are emitted from XN (operating point), or from X after PH_REINIT
+    bool out_from_x = false, reinit_begin = false;
 
     // ---- pass 1: Newton update of this lane's unknowns, convergence and LTE partials ------------
     const bool solving = live && phase != PH_TRAN_INIT && !badpt;
@@ -301,9 +305,9 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     if (live) {
         if (phase == PH_TRAN_INIT) {
             copy_mode = 4;
-            out_init = true;
-            if (status != 0) finish = true;
-            else { begin = true; phase = PH_TRAN; }
+            if (status != 0) { out_init = true; finish = true; }
+            else if (o.reinit) { reinit_begin = true; phase = PH_REINIT; it = 0; }   // t0 samples wait for the re-initialised state
+            else { out_init = true; begin = true; phase = PH_TRAN; }
         } else {
             nnewton++;
             if (!pv && lane == 0) a.ist[(size_t)IS_NFULL * B + ii]++;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
                 nrm_prev = nrm;
                 it++;
                 if (conv) newton_ok = true;
-                else if (it >= (phase == PH_DC ? o.max_newton_dc : o.max_newton_tran)) { newton_fail = true; status = 1; }
+                else if (it >= (phase == PH_TRAN ? o.max_newton_tran : o.max_newton_dc)) { newton_fail = true; status = 1; }
 
                 if (phase == PH_TRAN && newton_ok) {
                     double fac = 2.0;
@@ -374,7 +378,14 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
                     }
                 }
             }
-            if (phase == PH_DC && (newton_ok || newton_fail)) {
+            if (phase == PH_REINIT && (newton_ok || newton_fail)) {
+                // converged: X is the state at t0 (charges kept, algebraic unknowns at the transient source values);
+                // failed: the operating point stands.  Either way the transient starts now.
+                copy_mode = newton_ok ? 5 : 3;
+                out_init = true; out_from_x = newton_ok;
+                status = 0; it = 0;
+                begin = true; phase = PH_TRAN;
+            } else if (phase == PH_DC && (newton_ok || newton_fail)) {
                 bool dc_done = false;
                 it = 0;
                 if (stage < 0) {
@@ -428,8 +439,9 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     }
     // ---- output sampling (reads rows owned by other lanes: X = x_n, XN = x_{n-1}, X1 = x_{n-2}, not yet shifted)
     if (out_init) {
+        const double* __restrict__ src0 = out_from_x ? X : XN;
         while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
-            for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
+            for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(src0, a.outputs[k]);
             sidx++;
         }
     }
@@ -445,6 +457,11 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     }
     // ---- next step attempt: scalars first (mirrors the top of the oracle's step loop)
     double a1 = 0.0, a2 = 0.0;
+    if (reinit_begin) {   // backward Euler over h0 = span * 1e-12 "from t0 to t0": beta = -q_dc / h0, Newton starts at the operating point
+        tnew = o.t0; h = o.span * 1e-12;
+        alpha = 1.0 / h; a1 = -alpha;
+        method = 0; np = 0; retry = 0;
+    }
     if (begin) {
         bool more;
         if (o.fixed_step) {
@@ -480,7 +497,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
     }
     __syncthreads();   // output sampling has read the un-shifted history rows of other lanes
     // ---- pass 2 over this lane's unknowns: history shift (accept), DC copies, beta + predictor (begin)
-    if (do_accept || copy_mode || begin) {
+    if (do_accept || copy_mode || begin || reinit_begin) {
 #pragma unroll 4
         for (int i = lane; i < N; i += CTRL_LANES) {
             double x = V(X, i), xn = V(XN, i), x1 = V(X1, i), x2 = V(X2, i), qn = V(QN, i), q1 = V(Q1, i), qd = V(QD, i);
@@ -494,6 +511,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             else if (copy_mode == 2) { xn = x; V(XN, i) = xn; }
             else if (copy_mode == 3) { x = xn; V(X, i) = x; }
             else if (copy_mode == 4) { qn = V(QK, i); qd = 0.0; V(QN, i) = qn; V(QD, i) = qd; }
+            else if (copy_mode == 5) { xn = x; qn = V(QK, i); qd = 0.0; V(XN, i) = xn; V(QN, i) = qn; V(QD, i) = qd; }
+            if (reinit_begin) V(BETA, i) = a1 * qn;
             if (begin) {
                 double beta = a1 * qn;
                 if (method == 1) beta -= qd;
@@ -523,14 +542,14 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(co
             IST(IS_RETRY) = retry;
             DST(DS_T) = t; DST(DS_TNEW) = tnew; DST(DS_H) = h; DST(DS_H1) = h1; DST(DS_H2) = h2;
             DST(DS_HPROP) = hprop; DST(DS_GSHUNT) = gshunt; DST(DS_LIM) = lim; DST(DS_NRM) = nrm_prev; DST(DS_KAPPA) = kappa;
-            a.alpha[inst] = (phase == PH_TRAN) ? alpha : 0.0;
+            a.alpha[inst] = (phase == PH_TRAN || phase == PH_REINIT) ? alpha : 0.0;
             if (phase_in == PH_DC && phase != PH_DC) atomicSub(c.dc_count, 1);
         }
         if (phase != PH_DONE) {
             // source stepping of the operating point: every independent source times stage / source_steps
             const double src_scale = (phase == PH_DC && stage > o.gmin_steps) ? (double)(stage - o.gmin_steps) / (double)o.source_steps : 1.0;
             for (int w = lane; w < a.nwaves; w += CTRL_LANES)
-                c.WV[(size_t)w * B + inst] = src_scale * wave_value(a.waves[w], tnew, phase != PH_TRAN, a.params, B, inst);
+                c.WV[(size_t)w * B + inst] = src_scale * wave_value(a.waves[w], tnew, phase != PH_TRAN && phase != PH_REINIT, a.params, B, inst);
         }
     }
     // ---- role of every point in the NEXT round + device-wide compaction.  Warp 0 of the CTA (lane 0 of every point)

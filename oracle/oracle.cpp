@@ -590,6 +590,13 @@ struct Solver {
     }
 };
 
+// a source whose DC value may differ from its transient value at t0 (`V1 n 0 DC 5 SIN(10 3 1k)`)
+bool needs_reinit(const cb_flat_circuit* fc) {
+    for (int i = 0; i < fc->n_waves; i++)
+        if (fc->waves[i].has_dc && fc->waves[i].kind != CB_W_DC) return true;
+    return false;
+}
+
 // polynomial through the last accepted points, evaluated at tt (nh = how many older points valid)
 void predict(int N, int nh, double tt, double tn, const double* xn, double h1, const double* x1,
              double h2, const double* x2, double* out) {
@@ -623,6 +630,20 @@ int tran_one(Solver& S, double t0, double t1, const double* saveat, int64_t nsav
     qn = S.s.q;
     const double span = t1 - t0;
     const double teps = 1e-12 * std::max(std::fabs(t1), span);
+    // Consistent re-initialisation at t0 (reference src/dcop.jl:146-153: after the :dcop solve "fix the differential vars
+    // and do regular BrownFullBasicInit" in transient mode; test/basic.jl:534-552: `v1 vcc 0 DC 5 SIN(10 3 1k)` reads 10 V
+    // at t0).  Restated as the limit of a backward-Euler step of vanishing length h0 from the operating point with the
+    // sources at their TRANSIENT values: charges (differential variables) are held, algebraic unknowns follow the sources.
+    if (st == CB_ST_SUCCESS && opt->t0_reinit && needs_reinit(fc)) {
+        const double h0 = span * 1e-12, a0 = 1.0 / h0;
+        std::vector<double> b0(N), xr = xn, qr;
+        for (int i = 0; i < N; i++) b0[i] = -a0 * qn[i];
+        if (S.newton(xr, t0, false, a0, b0.data(), 0.0, opt->max_newton_dc, 1e300, qr, false, true) == 0) {
+            xn = xr;
+            eval_system(S.in, S.vc, xn.data(), t0, false, S.s);
+            qn = S.s.q;
+        }
+    }
     int64_t sidx = 0;
     while (sidx < nsave && saveat[sidx] <= t0 + teps) emit(sidx++, xn.data());
     if (st != CB_ST_SUCCESS) {

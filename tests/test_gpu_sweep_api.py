@@ -144,3 +144,28 @@ def test_bsource_time_inverter_sweep(host_bsimcmg):   # test/bsimcmg/bsimcmg_spe
     assert so.max() == 0
     err = np.abs(sols.y - yo)
     assert np.all(err <= 1e-6 * np.abs(yo) + 1e-9), err.max()
+
+
+def test_multimode_source_reinitialised_at_t0_on_gpu():
+    """test/basic.jl:534-552 (`v1 vcc 0 DC 5 SIN(10 3 1k)`: 10 V at t0 after the operating point at 5 V) as a sweep of the
+    load resistor; and the RC variant: the algebraic node jumps, the capacitor voltage is held.  GPU == oracle."""
+    from test_oracle_golden import MULTIMODE_DECK, MULTIMODE_RC_DECK
+    cs = CircuitSweep(MULTIMODE_DECK.replace("r1 vcc 0 1k", ".param rl=1k\nr1 vcc 0 'rl'"), Sweep(rl=np.linspace(500.0, 2000.0, 40)),
+                      outputs=["vcc", "v1.i"])
+    dc = dc_(cs)
+    assert np.abs(dc.array(cs.sys.node_vcc) - 5.0).max() < 1e-12
+    ts = np.linspace(0.0, 1e-3, 11)
+    sols = tran_(cs, (0.0, 1e-3), saveat=ts)
+    assert all(s.retcode == "Success" for s in sols)
+    assert np.abs(sols.array(cs.sys.node_vcc)[:, 0] - 10.0).max() < 1e-9
+    yo, so, _ = orc.tran(cs.flat.fc, 0.0, 1e-3, ts, params=cs.flat.params)
+    assert np.abs(sols.y - yo).max() < 1e-9
+    cs = CircuitSweep(MULTIMODE_RC_DECK.replace("c1 out 0 1u", ".param cl=1u\nc1 out 0 'cl'"), Sweep(cl=np.linspace(0.5e-6, 2e-6, 33)),
+                      outputs=["in", "out"])
+    kw = dict(fixed_step=1, dt=1e-5)
+    sols = tran_(cs, (0.0, 1e-3), saveat=ts, **kw)
+    assert np.abs(sols.array("in")[:, 0] - 10.0).max() < 1e-9 and np.abs(sols.array("out")[:, 0] - 5.0).max() < 1e-6
+    yo, so, _ = orc.tran(cs.flat.fc, 0.0, 1e-3, ts, params=cs.flat.params, opts=orc.default_options(**kw))
+    assert np.all(np.abs(sols.y - yo) <= 1e-6 * np.abs(yo) + 1e-9)
+    sols = tran_(cs, (0.0, 1e-3), saveat=ts, t0_reinit=0, **kw)
+    assert np.abs(sols.array("in")[:, 0] - 5.0).max() < 1e-12

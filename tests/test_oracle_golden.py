@@ -394,3 +394,30 @@ def test_mc_vr_circuit_agauss_is_nominal():   # test/basic.jl:45-79: R(agauss(2,
 def test_option_card_only():   # test/basic.jl:640-649: a deck of nothing but `.option temp=10 filemode=ascii noinit` is accepted
     nl = netlist.parse_netlist("* .option\n.option temp=10 filemode=ascii noinit\n")
     assert {k.lower(): v for k, v in nl.options.items()}["temp"] == "10" and not nl.top.cards
+
+
+MULTIMODE_DECK = """* multimode spice source
+v1 vcc 0 DC 5 AC 1 SIN(10 3 1k)
+r1 vcc 0 1k
+"""
+# the same source behind an RC: the capacitor voltage is a differential variable and keeps its operating-point value at t0
+MULTIMODE_RC_DECK = """* multimode source into an RC
+v1 in 0 DC 5 SIN(10 3 1k)
+r1 in out 1k
+c1 out 0 1u
+"""
+
+
+def test_multimode_source_is_reinitialised_at_t0():   # test/basic.jl:534-552: vcc == 10 after CedarDCOp initialisation, DC value 5
+    fl = netlist.flatten(netlist.parse_netlist(MULTIMODE_DECK), None, outputs=["vcc"], host=True)
+    x, _, st, _ = orc.dc(fl.fc)
+    assert st.max() == 0 and abs(x[0, 0] - 5.0) < 1e-12                       # :dcop mode sees the DC value
+    y, st, _ = orc.tran(fl.fc, 0.0, 0.01, np.array([0.0, 2.5e-4]))
+    assert st.max() == 0 and abs(y[0, 0, 0] - 10.0) < 1e-9                    # transient mode at t0: vo of SIN(10 3 1k)
+    assert abs(y[0, 1, 0] - 13.0) < 1e-2
+    y, st, _ = orc.tran(fl.fc, 0.0, 0.01, np.array([0.0]), opts=orc.default_options(t0_reinit=0))
+    assert abs(y[0, 0, 0] - 5.0) < 1e-12                                      # without re-initialisation: the operating point
+    fl = netlist.flatten(netlist.parse_netlist(MULTIMODE_RC_DECK), None, outputs=["in", "out"], host=True)
+    y, st, _ = orc.tran(fl.fc, 0.0, 0.01, np.array([0.0, 0.01]))
+    assert st.max() == 0
+    assert abs(y[0, 0, 0] - 10.0) < 1e-9 and abs(y[1, 0, 0] - 5.0) < 1e-6     # algebraic node jumps, capacitor voltage is held
