@@ -1557,6 +1557,9 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     }
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
+    // k_control: 32 lanes per point while the launch is under one wave of 1024-thread CTAs (latency-bound), else 8
+    int ctrl_lanes = (B + CTRL_PTS - 1) / CTRL_PTS <= 2LL * p->num_sms ? 32 : 8;
+    if (const char* e = std::getenv("CB_CTRL_LANES")) ctrl_lanes = std::atoi(e) == 32 ? 32 : 8;
     const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
     // one round on the plan's streams; `vround`: lock-step value-only round (only the value-only list is non-empty);
     // `next_v`: lock-step schedule of the next round; ev: optional timing events {start, after eval, after evalv, end}
@@ -1594,7 +1597,8 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         }
         CArgs ca = cargs[par];
         ca.next_vround = next_v;
-        k_control<<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * CTRL_LANES, 0, p->stream>>>(ca);
+        if (ctrl_lanes == 32) k_control<32><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 32, 0, p->stream>>>(ca);
+        else k_control<8><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 8, 0, p->stream>>>(ca);
         launches += 2;
         if (ev) cudaEventRecord(ev[3], p->stream);
         return CB_OK;

@@ -209,13 +209,10 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 #ifndef CTRL_PTS
 #define CTRL_PTS 32
 #endif
-#ifndef CTRL_LANES
-#define CTRL_LANES 8
-#endif
-#ifndef CTRL_MINB
-#define CTRL_MINB 4   // 64 registers: the 512 CTAs of a 16 384-point launch are one wave (148 SMs x 4), not 444 + a tail
-#endif
-__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_MINB) k_control(const CArgs c) {
+// Lanes per point: 8 for large batches (256-thread CTAs, 4 per SM: a 16 384-point launch is one wave); 32 for small ones, where the
+// launch is a fraction of a wave and only its latency counts (3 instead of 11 unknowns per thread in the two passes).
+template <int CTRL_LANES>
+__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1) k_control(const CArgs c) {
     static_assert(CTRL_PTS == 32, "lane 0 of the points of a CTA must be exactly one warp (list compaction by ballot)");
     __shared__ double s_err[CTRL_LANES][CTRL_PTS];
     __shared__ double s_nrm[CTRL_LANES][CTRL_PTS];
@@ -670,14 +667,15 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (
 #pragma unroll 4
         for (int e = w; e < nnz; e += LU_W) VL(e) = lf[(size_t)e * B];
     } else {
+#pragma unroll 4
         for (int e = w; e < nnz; e += LU_W) {
             double v = 0.0;
-            const int lin = a.a_lin[e];
+            const int lin = __ldg(a.a_lin + e);
             if (lin >= 0) {
                 const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
                 v = a.lin_g[li] + alpha * a.lin_c[li];
             }
-            if (a.a_diag[e]) v += gshunt;
+            if (__ldg(a.a_diag + e)) v += gshunt;
             VL(e) = v;
         }
     }
