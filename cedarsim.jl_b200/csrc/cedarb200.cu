@@ -1315,14 +1315,15 @@ extern "C" int cb_plan_device_params(cb_plan* p, double** d_params) {
     return CB_OK;
 }
 
+// layout must match struct VaArgs in va_prelude.h
+struct VaArgsH {
+    long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
+    const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
+    double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
+};
+
 // which point list a device-evaluation launch runs over: this round's full-iteration or value-only points
 static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_args, bool value_only = false, int parity = 0) {
-    // layout must match struct VaArgs in va_prelude.h
-    struct VaArgsH {
-        long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
-        const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
-        double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
-    };
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha;
@@ -1770,6 +1771,111 @@ static int dc1(cb_plan* p, const cb_options* opt, double* x_out, double* x_full,
     return CB_OK;
 }
 
+// ---- forward sensitivities of the operating point, direct method (reference test/sensitivity.jl:31-41:
+// ODEForwardSensitivityProblem over the ParamSim's parameters).  After the operating point x* has been found and the
+// Jacobian J(x*) factored (the factors k_lu stores for its value-only iterations), a direction d -- the caller's
+// parameter matrices P+ and P- = the sweep's parameters with one swept quantity moved by +-step -- costs two chord
+// updates with those factors and NO new nonlinear solve:
+//       dx+- = -J^-1 F(x*; P+-)           (k_setupv + k_evalv with the moved parameters, k_lu with the stored factors)
+//       dx*/dp = (dx+ - dx-) / (2 step)   (F(x*; P) cancels; the error is O(step^2) from the devices' own curvature in p)
+// i.e. dF/dp comes from central differences of the DEVICE equations at fixed x*, the linear algebra is one forward /
+// backward substitution per direction with the Newton factors.  The stencil form (sweeps.sensitivities_ with
+// method="stencil": every direction re-solved as extra sweep points) stays as the check.
+static int sens_dc1(cb_plan* p, const cb_options* opt, int64_t n_dir, const double* pp, const double* pm, const double* step,
+                    double* x_out, double* sens_out, int32_t* status, cb_stats* stats, long long pitch) {
+    cb_circuit* c = p->c;
+    if (!p->lu || (!p->have_v && !c->insts.empty()))
+        return fail(CB_ERR_STATE, "direct sensitivities need the shared-memory solver and value-only variants of every device model");
+    int rc = dc1(p, opt, x_out, nullptr, status, stats, pitch);
+    if (rc != CB_OK) return rc;
+    const long long B = p->B;
+    const int O = p->na.O, P = c->P;
+    NArgs a = p->na;
+    if (!p->la.LUF) {
+        rc = p->alloc(&p->la.LUF, (size_t)c->sym.nnz_lu * B);
+        if (rc == CB_OK && p->have_v && !p->d_cachev) rc = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * p->Bpad);
+        if (rc != CB_OK) return rc;
+    } else if (p->have_v && !p->d_cachev) {
+        rc = p->alloc(&p->d_cachev, (size_t)std::max<long long>(1, p->cachev_slots) * p->Bpad);
+        if (rc != CB_OK) return rc;
+    }
+    double *d_pert = nullptr, *d_step = nullptr, *d_sens = nullptr, *d_lg = nullptr, *d_lc = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pert); cudaFree(d_step); cudaFree(d_sens); cudaFree(d_lg); cudaFree(d_lc); };
+    const long long Bl = c->lin_swept ? B : 1;
+    if (cudaMalloc((void**)&d_pert, (size_t)std::max(1, P) * B * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_step, (size_t)B * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_sens, (size_t)std::max(1, O) * B * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_lg, (size_t)std::max(1, c->nlin) * Bl * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_lc, (size_t)std::max(1, c->nlin) * Bl * sizeof(double)) != cudaSuccess) {
+        cleanup();
+        return fail(CB_ERR_CUDA, "cudaMalloc of the sensitivity scratch failed");
+    }
+    cudaStream_t st = p->stream;
+    const unsigned gB = (unsigned)((B + 127) / 128);
+    LArgs la = p->la;
+    la.WV = p->d_WV; la.DX = p->d_DX; la.QK = p->d_QK; la.RMAX = p->d_RMAX; la.DVMAX = p->d_DVMAX; la.BAD = p->d_BAD;
+    la.cur = Lists{p->d_lists, p->d_lists + B, p->d_cnt};
+    la.zero_cnt = p->d_cnt + 2;
+    la.growth_max = 1e300;
+    a.o.rate_test = 0;
+    const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
+    // 1. factors of J(x*): one full iteration of every point at the solution (alpha = 0: the DC Jacobian)
+    k_ac_prepare<<<gB, 128, 0, st>>>(B, a.active, a.alpha, p->d_lists, p->d_cnt);
+    for (size_t m = 0; m < c->models.size(); m++) {
+        if (c->model_insts[m].empty()) continue;
+        char args[256];
+        fill_va_args(p, m, opt, args);
+        void* kargs[] = {args};
+        dim3 grid((unsigned)((B + p->eval_threads[m] - 1) / p->eval_threads[m]), (unsigned)c->model_insts[m].size());
+        CUDA_TRY(cudaLaunchKernel((const void*)p->k_eval[m], grid, dim3(p->eval_threads[m]), kargs, p->eval_smem[m], st));
+    }
+    k_init_waves<<<gB, 128, 0, st>>>(a, p->d_WV);
+    la.n = a;
+    k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+    CUDA_TRY(cudaGetLastError());
+    // 2. two chord updates per direction with the moved parameters
+    a.params = d_pert;
+    if (c->lin_swept) { a.lin_g = d_lg; a.lin_c = d_lc; }
+    la.n = a;
+    cudaError_t err = cudaSuccess;
+    for (int64_t d = 0; d < n_dir && err == cudaSuccess; d++) {
+        cudaMemsetAsync(d_sens, 0, (size_t)std::max(1, O) * B * sizeof(double), st);
+        cudaMemcpyAsync(d_step, step + (size_t)d * pitch, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st);
+        for (int sg = 0; sg < 2 && err == cudaSuccess; sg++) {
+            const double* src = (sg == 0 ? pp : pm) + (size_t)d * std::max(1, P) * pitch;
+            if (P > 0)
+                cudaMemcpy2DAsync(d_pert, (size_t)B * sizeof(double), src, (size_t)pitch * sizeof(double), (size_t)B * sizeof(double),
+                                  (size_t)P, cudaMemcpyHostToDevice, st);
+            if (c->lin_swept)
+                k_lin_setup<<<gB, 128, 0, st>>>(Bl, B, c->nlin, (int)c->lin_contrib.size(), p->d_lin_contrib, d_pert, d_lg, d_lc);
+            k_init_waves<<<gB, 128, 0, st>>>(a, p->d_WV);
+            k_list_identity_any<<<gB, 128, 0, st>>>(B, p->d_lists + B, p->d_cnt);
+            for (size_t m = 0; m < c->models.size(); m++) {
+                if (c->model_insts[m].empty()) continue;
+                char args[256];
+                fill_va_args(p, m, opt, args, true);
+                ((VaArgsH*)args)->params = d_pert;
+                void* kargs[] = {args};
+                dim3 gs((unsigned)((B + 127) / 128), (unsigned)c->model_insts[m].size());
+                cudaLaunchKernel((const void*)p->k_setupv[m], gs, dim3(128), kargs, 0, st);
+                dim3 grid((unsigned)((B + p->evalv_threads[m] - 1) / p->evalv_threads[m]), (unsigned)c->model_insts[m].size());
+                cudaLaunchKernel((const void*)p->k_evalv[m], grid, dim3(p->evalv_threads[m]), kargs, p->evalv_smem[m], st);
+            }
+            k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+            k_sens_accum<<<gB, 128, 0, st>>>(B, O, a.outputs, p->d_DX, d_step, sg == 0 ? 1.0 : -1.0, d_sens);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err == cudaSuccess && O > 0)
+            err = rows_to_host(sens_out + (size_t)d * O * pitch, d_sens, (size_t)O, B, pitch, sizeof(double));
+    }
+    cleanup();
+    p->setupv_valid = false;   // the value-only cache now holds the last moved parameters
+    if (err != cudaSuccess) return fail(CB_ERR_CUDA, std::string("sensitivity pass: ") + cudaGetErrorString(err));
+    if (stats) { stats->kernel_launches += 4 + n_dir * 2 * (4 + 2 * (int64_t)c->models.size()); stats->lu_factors += B; }
+    return CB_OK;
+}
+
 static int tran_device1(cb_plan* p, double t0, double t1, const double* saveat, int64_t n_save,
                         const cb_options* opt, double** d_y_out, int32_t** d_status, cb_stats* stats) {
     if (!p || !opt || (n_save > 0 && !saveat)) return fail(CB_ERR_INVALID, "null argument");
@@ -2184,6 +2290,24 @@ extern "C" int cb_tran(cb_plan* p, double t0, double t1, const double* saveat, i
     rc = for_lanes(p, [&](cb_plan* l, size_t k) {
         return tran1(l, t0, t1, saveat, n_save, opt, y_out ? y_out + l->lane_off : nullptr,
                      status ? status + l->lane_off : nullptr, &st[k], p->B);
+    });
+    merge_stats(stats, st);
+    return rc;
+}
+
+extern "C" int cb_sens_dc(cb_plan* p, const cb_options* opt, int64_t n_dir, const double* params_plus, const double* params_minus,
+                          const double* step, double* x_out, double* sens_out, int32_t* status, cb_stats* stats) {
+    if (!p || !opt || n_dir < 0 || (n_dir > 0 && (!step || !sens_out || (p->c->P > 0 && (!params_plus || !params_minus)))))
+        return fail(CB_ERR_INVALID, "null argument");
+    { const int rco = check_options(opt); if (rco != CB_OK) return rco; }
+    if (p->lanes.empty()) return sens_dc1(p, opt, n_dir, params_plus, params_minus, step, x_out, sens_out, status, stats, p->B);
+    int rc = scatter_params(p);
+    if (rc != CB_OK) return rc;
+    std::vector<cb_stats> st(p->lanes.size());
+    rc = for_lanes(p, [&](cb_plan* l, size_t k) {
+        return sens_dc1(l, opt, n_dir, params_plus ? params_plus + l->lane_off : nullptr, params_minus ? params_minus + l->lane_off : nullptr,
+                        step ? step + l->lane_off : nullptr, x_out ? x_out + l->lane_off : nullptr,
+                        sens_out ? sens_out + l->lane_off : nullptr, status ? status + l->lane_off : nullptr, &st[k], p->B);
     });
     merge_stats(stats, st);
     return rc;

@@ -1118,6 +1118,20 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// direct-method sensitivities: the first B entries of the value-only list, no full-iteration points
+__global__ void k_list_identity_any(long long B, int* list_any, int* cnt) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst == 0) { cnt[0] = 0; cnt[1] = (int)B; }
+    if (inst < B) list_any[inst] = (int)inst;
+}
+// sens[o][b] += sign * dx[outputs[o]][b] / (2 step[b])
+__global__ void k_sens_accum(long long B, int O, const int* outputs, const double* DX, const double* step, double sign, double* sens) {
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    const double w = sign / (2.0 * step[inst]);
+    for (int o = 0; o < O; o++) sens[(size_t)o * B + inst] += w * DX[(size_t)outputs[o] * B + inst];
+}
+
 __global__ void k_gather_rows(long long B, int n, const int* idx, const double* src, double* dst) {
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= B) return;

@@ -22,7 +22,7 @@ _lib = None
 
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_options_default", "cb_options_size", "cb_stats_size", "cb_options_init", "cb_circuit_create", "cb_circuit_load", "cb_circuit_set_cuda_source",
-    "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_create_lanes", "cb_plan_create_multi", "cb_plan_devices", "cb_plan_lanes", "cb_plan_set_params", "cb_dc", "cb_tran",
+    "cb_circuit_compile", "cb_circuit_lu_info", "cb_plan_create", "cb_plan_create_lanes", "cb_plan_create_multi", "cb_plan_devices", "cb_plan_lanes", "cb_plan_set_params", "cb_dc", "cb_tran", "cb_sens_dc",
     "cb_ac", "cb_noise", "cb_plan_device_params", "cb_plan_set_x0", "cb_plan_set_timing", "cb_measure_fp64_peak", "cb_tran_device", "cb_dc_device", "cb_plan_destroy", "cb_circuit_destroy",
 ]
 
@@ -195,6 +195,25 @@ class Plan:
         _check(self.lib.cb_dc(self.handle, C.byref(opts), _dp(x_out), _dp(x_full) if want_full else None,
                               status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
         return x_out, x_full, status, st.as_dict()
+
+    def sens_dc(self, params_plus: np.ndarray, params_minus: np.ndarray, step: np.ndarray, opts: Optional[F.cb_options] = None):
+        """Operating point and its forward sensitivities by the direct method (cb_sens_dc): direction d moves the
+        parameters to params_plus[d] / params_minus[d] ([n_dir, P, B]), step[d] ([n_dir, B]) is the distance moved.
+        Returns (x_out [O, B], sens [n_dir, O, B], status, stats)."""
+        opts = opts or default_options()
+        fc = self.circuit.fc
+        O, P = len(fc.outputs), len(fc.param_names)
+        step = np.ascontiguousarray(step, dtype=np.float64)
+        n_dir = step.shape[0]
+        pp = np.ascontiguousarray(params_plus, dtype=np.float64).reshape(n_dir, max(1, P), self.B) if P else np.zeros((n_dir, 1, self.B))
+        pm = np.ascontiguousarray(params_minus, dtype=np.float64).reshape(n_dir, max(1, P), self.B) if P else np.zeros((n_dir, 1, self.B))
+        x_out = np.zeros((O, self.B))
+        sens = np.zeros((n_dir, O, self.B))
+        status = np.zeros(self.B, dtype=np.int32)
+        st = F.cb_stats()
+        _check(self.lib.cb_sens_dc(self.handle, C.byref(opts), C.c_int64(n_dir), _dp(pp), _dp(pm), _dp(step), _dp(x_out), _dp(sens),
+                                   status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return x_out, sens, status, st.as_dict()
 
     def tran(self, t0: float, t1: float, saveat, opts: Optional[F.cb_options] = None, out: Optional[np.ndarray] = None):
         opts = opts or default_options()

@@ -782,13 +782,101 @@ class SensitivitySolution:
         return np.array([RETCODES.get(int(s), "Failure") for s in self.status], dtype=object).reshape(self.cs.shape, order="F")
 
 
+class DirectSensitivitySolution:
+    """Result of `sensitivities_(..., method="direct")` (DC): `.solution` is the SweepSolution of the sweep itself,
+    `.array(ref, name)` / `.point(idx, ref, name)` the derivative of an unknown among the outputs (or of a `<inst>.V`
+    observable, a difference of two of them) with respect to swept parameter `name`."""
+
+    def __init__(self, cs: "CircuitSweep", x: np.ndarray, sens: np.ndarray, status: np.ndarray, stats, wrt: List[str]):
+        self.cs, self.sens, self.wrt, self.status, self.stats = cs, sens, list(wrt), status, stats
+        self.solution = SweepSolution(cs, x, status, stats, None)
+        self.t = self.freqs = None
+        self.freq = False
+
+    def _d(self, ref, name: str) -> np.ndarray:
+        obs = _Observable(self.cs.flat.fc, ref)
+        if obs.div is not None or obs.cap is not None:
+            raise KeyError(f"{obs.key!r}: the direct method differentiates unknowns and `.V` observables; use method='stencil'")
+        j = self.wrt.index(name)
+        acc = np.zeros(len(self.cs))
+        for sg, u in obs.terms:
+            if u not in self.solution.out_index:
+                raise KeyError(f"{obs.key!r} needs its unknowns among the outputs")
+            acc = acc + sg * self.sens[j, self.solution.out_index[u]]
+        return acc
+
+    def array(self, ref, name: str) -> np.ndarray:
+        return self._d(ref, name).reshape(self.cs.shape, order="F")
+
+    def point(self, idx, ref, name: str):
+        i = int(idx) if isinstance(idx, (int, np.integer)) else int(np.ravel_multi_index(tuple(idx), self.cs.shape, order="F"))
+        return self._d(ref, name)[i]
+
+    @property
+    def retcodes(self) -> np.ndarray:
+        return np.array([RETCODES.get(int(s), "Failure") for s in self.status], dtype=object).reshape(self.cs.shape, order="F")
+
+
+def _direct_dc_sensitivities(cs: CircuitSweep, wrt: List[str], rel_step: float, **kw) -> DirectSensitivitySolution:
+    """cb_sens_dc: one operating-point solve of the sweep, then per swept quantity two chord updates with the stored
+    factors of J(x*) and the parameters moved by +-h (h = rel_step |p|): no nonlinear re-solve, B points instead of the
+    B (1 + 4 n) of the stencil form.  A swept quantity may feed several parameter columns through netlist expressions: the
+    moved columns come from re-flattening the circuit with the moved value (directional derivative)."""
+    cs._ensure_plans()
+    plan, _ = cs._plans[0]
+    B = len(cs)
+    base = cs.flat.params
+
+    def params_for(cols):
+        if isinstance(cs.circuit, str) or not callable(cs.circuit):
+            from .netlist import parse_netlist
+            nl = cs.circuit
+            if isinstance(nl, str):
+                if cs._ctor["lang"] == "spectre":
+                    from .spectre import parse_spectre
+                    nl = parse_spectre(nl, include_dirs=cs._ctor["include_dirs"])
+                else:
+                    nl = parse_netlist(nl, include_dirs=cs._ctor["include_dirs"])
+            fl = flatten(nl, cols, B=B, outputs=cs._ctor["outputs"], host=cs._ctor["host"])
+        else:
+            fl = cs.circuit(cols, B)
+        if list(fl.fc.param_names) != list(cs.flat.fc.param_names):
+            raise ValueError("moving a swept parameter changed the set of parameter columns")
+        return fl.params
+
+    pp, pm, steps = [], [], []
+    for name in wrt:
+        if name not in cs.columns:
+            raise KeyError(f"sensitivity parameter {name!r} is not a swept variable of this CircuitSweep")
+        p = np.asarray(cs.columns[name], dtype=float)
+        h = np.where(p != 0.0, rel_step * np.abs(p), rel_step)
+        steps.append(h)
+        for sign, dst in ((1.0, pp), (-1.0, pm)):
+            cols = dict(cs.columns)
+            cols[name] = p + sign * h
+            dst.append(params_for(cols) if base.size else np.zeros((0, B)))
+    plan.set_x0(cs.x0)
+    x, sens, status, stats = plan.sens_dc(np.stack(pp) if base.size else np.zeros((len(wrt), 0, B)),
+                                          np.stack(pm) if base.size else np.zeros((len(wrt), 0, B)), np.stack(steps), cs._options(kw))
+    return DirectSensitivitySolution(cs, x, sens, status, stats, wrt)
+
+
 def sensitivities_(cs: CircuitSweep, wrt: Optional[Sequence[str]] = None, analysis: str = "dc", tspan=None, saveat=None, freqs=None,
-                   rel_step: float = 1e-3, order: int = 4, **kw) -> SensitivitySolution:
+                   rel_step: float = 1e-3, order: int = 4, method: str = "stencil", **kw):
     """Forward sensitivities of every sweep point with respect to the swept parameters `wrt` (default: all of
     them, like the reference's sensitivity problem over the ParamSim's parameters, test/sensitivity.jl:58-67).
+    method="stencil": every stencil point is one more sweep point of the same batched solve (any analysis);
+    method="direct" (analysis="dc"): the direct method of cb_sens_dc -- one solve, then one pair of triangular solves per
+    parameter with the factors of the Newton matrix.
     For `analysis="tran"` use `fixed_step=1` (or tolerances well below the derivative accuracy wanted), so that the
     stencil points share their time grid and step-control noise does not enter the difference."""
     wrt = [w for w in (sorted(cs.columns) if wrt is None else wrt)]
+    if method == "direct":
+        if analysis != "dc":
+            raise ValueError("method='direct' is available for analysis='dc'")
+        return _direct_dc_sensitivities(cs, wrt, 1e-4 if rel_step == 1e-3 else rel_step, **kw)
+    if method != "stencil":
+        raise ValueError("method must be 'stencil' or 'direct'")
     cols, steps = sensitivity_columns(cs.columns, wrt, rel_step, order)
     big_cs = CircuitSweep(cs.circuit, _ColumnSweep(cols), devices=cs.devices, **cs._ctor)
     if cs.x0 is not None:

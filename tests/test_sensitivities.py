@@ -205,3 +205,64 @@ def test_sensitivities_bsimcmg_inverter_gain_gpu():
     # more nFET fins pull the output down: d q / d nfin < 0 everywhere, largest in the transition region
     dn = sens.array(cs.sys.node_q, "mneg.nfin")
     assert dn.max() < 0.0 and np.abs(dn).max() > 0.05
+
+
+# ---- direct method (cb_sens_dc): one solve + a pair of triangular solves per parameter with the stored Newton factors
+@pytest.mark.gpu
+def test_direct_sensitivities_two_resistor_known_answer_gpu():   # test/sensitivity.jl:31-41,58-67: dR1 == -dR2 == -out/2
+    cs = CircuitSweep(TWO_R, ProductSweep(R1=[1.0], R2=[1.0]))
+    sens = sensitivities_(cs, method="direct")
+    out = sens.solution.array(cs.sys.node_out)
+    d1, d2 = sens.array(cs.sys.node_out, "R1"), sens.array(cs.sys.node_out, "R2")
+    assert sens.retcodes[0, 0] == "Success" and abs(out[0, 0] - 0.5) < 1e-12
+    assert abs(d1[0, 0] + d2[0, 0]) < 1e-9 and abs(d1[0, 0] + out[0, 0] / 2) < 1e-8
+
+
+@pytest.mark.gpu
+def test_direct_sensitivities_match_closed_forms_and_the_stencil_gpu(tmp_path):
+    R1v, R2v = np.arange(100.0, 1001, 100), np.arange(100.0, 1001, 100)
+    cs = CircuitSweep(TWO_R, ProductSweep(R1=R1v, R2=R2v))
+    sens = sensitivities_(cs, wrt=["R2", "R1"], method="direct")
+    R1, R2 = np.meshgrid(R1v, R2v, indexing="ij")
+    assert np.allclose(sens.array(cs.sys.node_out, "R2"), R1 / (R1 + R2) ** 2, rtol=1e-7, atol=0)
+    assert np.allclose(sens.array(cs.sys.node_out, "R1"), -R2 / (R1 + R2) ** 2, rtol=1e-7, atol=0)
+    assert np.allclose(sens.array(cs.sys.v.I, "R2"), 1.0 / (R1 + R2) ** 2, rtol=1e-7, atol=0)
+    # a Newton-solved nonlinear point: V -- R -- diode, implicit differentiation
+    (tmp_path / "dio.va").write_text(DIODE_VA)
+    text = f"* diode\n.hdl \"{tmp_path / 'dio.va'}\"\n.param r=1k vin=1\nV1 in 0 'vin'\nR1 in d 'r'\nX1 d 0 dio\n"
+    cs = CircuitSweep(text, ProductSweep(r=[500.0, 1e3, 2e3], vin=[0.8, 1.0, 2.0]), outputs=["d"])
+    direct = sensitivities_(cs, method="direct")
+    stencil = sensitivities_(cs)
+    v = direct.solution.array(cs.sys.node_d)
+    R, VIN = np.meshgrid([500.0, 1e3, 2e3], [0.8, 1.0, 2.0], indexing="ij")
+    gd = 1e-14 * np.exp(v / 0.025852) / 0.025852
+    assert np.allclose(direct.array(cs.sys.node_d, "r"), -(VIN - v) / R ** 2 / (1 / R + gd), rtol=1e-6, atol=0)
+    assert np.allclose(direct.array(cs.sys.node_d, "vin"), (1 / R) / (1 / R + gd), rtol=1e-6, atol=0)
+    for name in ("r", "vin"):
+        assert np.allclose(direct.array(cs.sys.node_d, name), stencil.array(cs.sys.node_d, name), rtol=1e-6, atol=0)
+    assert direct.stats["newton_iters"] < stencil.solution.stats["newton_iters"] / 5      # B points solved, not B (1 + 4 n)
+
+
+@pytest.mark.gpu
+def test_direct_sensitivities_bsimcmg_inverter_gpu(host_bsimcmg):
+    """Transistor level: d V(q) / d (supply, nFET fin count) of the BSIM-CMG inverter near its switching threshold, direct
+    method (value-only device evaluations at fixed x*, stored factors) against the stencil of re-solved points."""
+    from cedarsim.jl_b200 import circuits
+    cs = CircuitSweep(circuits.BSIMCMG_INVERTER_VIN_DECK, ProductSweep(**{"vin": np.linspace(0.35, 0.65, 7), "mneg.nfin": [2.0, 3.0]}),
+                      outputs=["q", "vvdd.i"])
+    direct = sensitivities_(cs, method="direct")
+    stencil = sensitivities_(cs)
+    assert (direct.retcodes == "Success").all()
+    for ref in (cs.sys.node_q, cs.sys.vvdd.I):
+        for name in ("vin", "mneg.nfin"):
+            a, b = direct.array(ref, name), stencil.array(ref, name)
+            assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-9 * np.abs(b).max()), (name, np.abs(a - b).max(), np.abs(b).max())
+    assert np.abs(direct.array(cs.sys.node_q, "vin")).max() > 3.0      # gain of the inverter
+
+
+def test_direct_method_argument_errors_without_gpu():
+    cs = CircuitSweep(TWO_R, ProductSweep(R1=[1.0], R2=[1.0]))
+    with pytest.raises(ValueError):
+        sensitivities_(cs, analysis="tran", method="direct")
+    with pytest.raises(ValueError):
+        sensitivities_(cs, method="adjoint")
