@@ -611,6 +611,9 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
 #ifndef LU_MINB
 #define LU_MINB 1
 #endif
+#ifndef CB_LU_LIN_UNROLL
+#define CB_LU_LIN_UNROLL 1
+#endif
 #ifndef LU_GU
 #define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
 #endif
@@ -667,7 +670,9 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (
 #pragma unroll 4
         for (int e = w; e < nnz; e += LU_W) VL(e) = lf[(size_t)e * B];
     } else {
+#if CB_LU_LIN_UNROLL
 #pragma unroll 4
+#endif
         for (int e = w; e < nnz; e += LU_W) {
             double v = 0.0;
             const int lin = __ldg(a.a_lin + e);
