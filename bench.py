@@ -108,7 +108,8 @@ def cpu_arm(points, threads, fast=True):
         orc.set_x0(nodeset(fc))
         ts = np.linspace(T0, T1, NSAVE)
         t = time.perf_counter()
-        y, st, stats = orc.tran(fc, T0, T1, ts, params=P, opts=orc.default_options(**OPTS), nthreads=threads)
+        # the same algorithm as the engine: chord iterations (value_rounds) with the derivative-free device functions
+        y, st, stats = orc.tran(fc, T0, T1, ts, params=P, opts=orc.default_options(**OPTS, **ENGINE_OPTS_BASE), nthreads=threads)
         el = time.perf_counter() - t
         orc.set_x0(None)
         return el, stats, int((st == 0).sum())
@@ -118,8 +119,10 @@ def cpu_arm(points, threads, fast=True):
     return run()
 
 
-def cpu_sample_points(threads):
-    return max(threads * 32, 256)   # ~15-30 s of CPU work per step on the box's host cores (fast arm)
+def cpu_sample_points(threads, big=False):
+    """bounded samples of the 16 384 draws: ~10 s of CPU work per step for the reference arm (many steps), 2 048 points
+    (~1 min on 16 cores) for the cpu_baseline figure of the engine's own line"""
+    return 2048 if big else max(threads * 16, 256)
 
 
 def run_reference(args, rank, world):
@@ -145,7 +148,7 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD, "points_per_step": points, "total_points": TOTAL_POINTS},
         "newton_iters_per_s": iters / el,
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
-                         "arm": "cpu_fast: sparse static-pivot LU, -O3 -march=native, OpenMP over points",
+                         "arm": "cpu_fast: chord iterations with value-only device functions, sparse static-pivot LU, -O3 -march=native, OpenMP over points",
                          "sample": f"the first {points} of the {TOTAL_POINTS} Monte-Carlo points per step, same tolerances and outputs"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -351,13 +354,14 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            pts = cpu_sample_points(threads)
+            pts = cpu_sample_points(threads, big=True)
             cpu_arm(threads * 2, threads)        # builds the -march=native libraries on first use, untimed
             cel, cstats, cok = cpu_arm(pts, threads)
             dpts = max(threads * 4, 32)
             del_, dstats, _ = cpu_arm(dpts, threads, fast=False)
             cpu = {"value": pts / cel, "unit": "points/s", "cores": threads, "kind": "port",
-                   "arm": "cpu_fast: same equations / step control, static-pivot sparse LU (engine's symbolic analysis), -O3 -march=native, OpenMP over points",
+                   "arm": "cpu_fast: same equations, step control and chord iterations (value-only device functions), static-pivot sparse LU "
+                          "(engine's symbolic analysis), -O3 -march=native, OpenMP over points",
                    "sample": f"the first {pts} of the {TOTAL_POINTS} Monte-Carlo points, same tolerances and outputs, {cel:.1f}s",
                    "newton_iters_per_s": cstats["newton_iters"] / cel,
                    "checker_dense": {"value": dpts / del_, "unit": "points/s", "sample": f"{dpts} points, {del_:.1f}s",

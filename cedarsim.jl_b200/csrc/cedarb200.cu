@@ -725,6 +725,7 @@ struct cb_plan {
     // kernels (+12 % points/s at 4 lanes on the 16 384-point DFF sweep).  lanes.empty() = this is a single lane.
     std::vector<cb_plan*> lanes;
     long long lane_off = 0;            // first sweep point of this lane within its parent
+    long long device_points = 0;       // lane: sweep points of all lanes of its parent on this lane's GPU (0 = a plan of its own)
     bool multi_device = false;         // parent: lanes on more than one GPU (host-array entry points only)
     double* d_params_all = nullptr;    // parent: [P][B] buffer handed out by cb_plan_device_params
     bool params_all_dirty = false;
@@ -1512,7 +1513,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     double t_eval = 0, t_newton = 0, t_evalv = 0, t_newtonv = 0;
     int64_t rounds = 0, vrounds = 0, launches = 0;
     const int64_t max_rounds = std::getenv("CB_MAX_ROUNDS") ? std::atoll(std::getenv("CB_MAX_ROUNDS")) : (int64_t)1 << 40;
-    if (c->models.size() > 8) return fail(CB_ERR_INVALID, "more than 8 Verilog-A models in one circuit");
+
     struct SArgsH {
         long long B; const double* X; const double* alpha; const double* gshunt; const double* BETA; const double* dev_out;
         const double* lin_g; const double* lin_c; const double* WV; const int* active; double* DX; double* QK; double* RMAX; int* BAD;
@@ -1537,13 +1538,17 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     int mixed = use_v && opt->mixed_rounds != 0;
     if (const char* e = std::getenv("CB_MIXED")) mixed = use_v && std::atoi(e) != 0;
     // per-parity argument blocks
-    char vargs[2][8][256], vargs_v[2][8][256];
+    struct VaArgBuf { char b[256]; };
+    std::vector<VaArgBuf> vargs_store[2], vargs_v_store[2];   // per round parity, one argument block per device model
+    for (int par = 0; par < 2; par++) { vargs_store[par].resize(c->models.size()); vargs_v_store[par].resize(c->models.size()); }
+    auto vargs = [&](int par, size_t m) { return (void*)vargs_store[par][m].b; };
+    auto vargs_v = [&](int par, size_t m) { return (void*)vargs_v_store[par][m].b; };
     CArgs cargs[2];
     LArgs largs[2];
     for (int par = 0; par < 2; par++) {
         for (size_t m = 0; m < c->models.size(); m++) {
-            fill_va_args(p, m, opt, vargs[par][m], false, par);
-            if (use_v) fill_va_args(p, m, opt, vargs_v[par][m], true, par);
+            fill_va_args(p, m, opt, vargs(par, m), false, par);
+            if (use_v) fill_va_args(p, m, opt, vargs_v(par, m), true, par);
         }
         int* lists_next = p->d_lists + (size_t)(1 - par) * 2 * B;
         cargs[par] = CArgs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, mixed, 0, p->d_dc_count, v_rounds + 1, 0,
@@ -1558,8 +1563,10 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     }
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
-    // k_control: 32 lanes per point while the launch is under one wave of 1024-thread CTAs (latency-bound), else 8
-    int ctrl_lanes = (B + CTRL_PTS - 1) / CTRL_PTS <= 2LL * p->num_sms ? 32 : 8;
+    // k_control: 32 lanes per point (1024-thread CTAs: one per SM) only while the whole GPU runs a small batch, where a
+    // round is latency-bound (+4 % at 2 048 points); with several busy lanes such CTAs crowd out the other lanes' kernels
+    // (-9 % at 4 lanes x 4 096 points, profiles/probe_r2g.log, probe_r2h.log)
+    int ctrl_lanes = std::max(B, p->device_points) <= 4096 && B <= 2048 ? 32 : 8;
     if (const char* e = std::getenv("CB_CTRL_LANES")) ctrl_lanes = std::atoi(e) == 32 ? 32 : 8;
     const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
     // one round on the plan's streams; `vround`: lock-step value-only round (only the value-only list is non-empty);
@@ -1574,7 +1581,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             if (kind == 0 ? !full_kernels : !value_kernels) continue;
             for (size_t m = 0; m < c->models.size(); m++) {
                 if (c->model_insts[m].empty()) continue;
-                void* kargs[] = {kind ? vargs_v[par][m] : vargs[par][m]};
+                void* kargs[] = {kind ? vargs_v(par, m) : vargs(par, m)};
                 const unsigned eval_threads = kind ? p->evalv_threads[m] : p->eval_threads[m];
                 dim3 grid((unsigned)((B + eval_threads - 1) / eval_threads), (unsigned)c->model_insts[m].size());
                 cudaStream_t ms = (fork && slot > 0 && slot < 8 && p->ustream[slot]) ? p->ustream[slot] : p->stream;
@@ -2133,6 +2140,7 @@ static int add_lanes(cb_plan* parent, cb_circuit* c, long long off, long long n,
         int rc = plan_create1(c, nb, device_id, &l);
         if (rc != CB_OK) return rc;
         l->lane_off = off;
+        l->device_points = n;
         parent->lanes.push_back(l);
         off += nb;
     }

@@ -68,7 +68,9 @@ class cb_va_model(C.Structure):
         ("host_setupn", C.c_void_p),
         ("host_noise", C.c_void_p),
         ("linear", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("ncache_v", C.c_int32),
+        ("host_setupv", C.c_void_p),
+        ("host_evalv", C.c_void_p),
     ]
 
 
@@ -223,6 +225,9 @@ class VAModelShape:
     noise_neg: List[int] = field(default_factory=list)
     host_setupn: int = 0
     host_noise: int = 0
+    ncache_v: int = 0        # value-only variant on the host (the oracle's chord iterations)
+    host_setupv: int = 0
+    host_evalv: int = 0
     branch_terms: List[int] = field(default_factory=list)   # terminals that are branch currents (V() <+ branches, I() probes)
     linear: bool = False   # every Jacobian entry is bias-independent: no Newton step limiting on its account
 
@@ -449,7 +454,8 @@ class FlatCircuit:
                                     C.cast(jr, C.POINTER(C.c_int32)), C.cast(jc, C.POINTER(C.c_int32)),
                                     m.host_setup or None, m.host_eval or None, len(m.noise_pos), m.ncache_n,
                                     C.cast(npos, C.POINTER(C.c_int32)), C.cast(nneg, C.POINTER(C.c_int32)),
-                                    m.host_setupn or None, m.host_noise or None, 1 if m.linear else 0, 0)
+                                    m.host_setupn or None, m.host_noise or None, 1 if m.linear else 0, m.ncache_v,
+                                    m.host_setupv or None, m.host_evalv or None)
         insts = (cb_va_inst * max(1, len(self.va_insts)))()
         for i, vi in enumerate(self.va_insts):
             shape = self.va_models[vi.model]

@@ -384,8 +384,10 @@ _TIME_NET = "time__"   # hidden net carrying simulation time for `$time` in beha
 
 
 class _Flattener:
-    def __init__(self, nl: Netlist, sweep: Dict[str, np.ndarray], B: int, host: bool, outputs: Optional[Sequence[str]] = None):
+    def __init__(self, nl: Netlist, sweep: Dict[str, np.ndarray], B: int, host: bool, outputs: Optional[Sequence[str]] = None,
+                 force_columns: bool = False):
         self.nl, self.sweep, self.B, self.host = nl, {k.lower(): v for k, v in sweep.items()}, B, host
+        self.force_columns = force_columns   # keep every sweep-dependent value a parameter column, even a uniform one
         # branch currents of Verilog-A instances asked for as observables: `<inst>.i(a,b)`
         self.want_branches: Dict[str, List[Tuple[str, str]]] = {}
         for o in outputs or ():
@@ -406,7 +408,7 @@ class _Flattener:
     def value(self, tag: str, v: Num):
         """constant or per-point column"""
         if isinstance(v, np.ndarray) and v.ndim > 0:
-            if np.all(v == v.flat[0]):
+            if np.all(v == v.flat[0]) and not self.force_columns:
                 return float(v.flat[0])
             return self.col(tag, v)
         return float(v)
@@ -771,12 +773,14 @@ class _Flattener:
 
 
 def flatten(nl: Netlist, sweep: Optional[Dict[str, np.ndarray]] = None, B: int = 1, host: bool = False,
-            outputs: Optional[Sequence[str]] = None) -> Flattened:
-    """Flatten `nl` for a sweep given as {name: array of B values}."""
+            outputs: Optional[Sequence[str]] = None, force_columns: bool = False) -> Flattened:
+    """Flatten `nl` for a sweep given as {name: array of B values}.  force_columns: every value that depends on a swept
+    name stays a per-point parameter column even when it is the same at all points (the direct sensitivity method moves
+    those columns; by default a uniform value is folded into the circuit as a constant)."""
     sweep = sweep or {}
     if sweep:
         B = len(next(iter(sweep.values())))
-    fl = _Flattener(nl, sweep, B, host, outputs).run()
+    fl = _Flattener(nl, sweep, B, host, outputs, force_columns).run()
     fl.fc.finalize()
     if outputs is not None:
         fl.fc.set_outputs(list(outputs))

@@ -822,25 +822,32 @@ def _direct_dc_sensitivities(cs: CircuitSweep, wrt: List[str], rel_step: float, 
     factors of J(x*) and the parameters moved by +-h (h = rel_step |p|): no nonlinear re-solve, B points instead of the
     B (1 + 4 n) of the stencil form.  A swept quantity may feed several parameter columns through netlist expressions: the
     moved columns come from re-flattening the circuit with the moved value (directional derivative)."""
-    cs._ensure_plans()
-    plan, _ = cs._plans[0]
     B = len(cs)
-    base = cs.flat.params
+    netlist_circuit = isinstance(cs.circuit, str) or not callable(cs.circuit)
+    nl = cs.circuit
+    if isinstance(nl, str):
+        from .netlist import parse_netlist
+        if cs._ctor["lang"] == "spectre":
+            from .spectre import parse_spectre
+            nl = parse_spectre(nl, include_dirs=cs._ctor["include_dirs"])
+        else:
+            nl = parse_netlist(nl, include_dirs=cs._ctor["include_dirs"])
+
+    def flat_for(cols):
+        # every sweep-dependent value stays a parameter column (a swept value that is the same at all points would
+        # otherwise be folded into the circuit as a constant and could not be moved)
+        if netlist_circuit:
+            return flatten(nl, cols, B=B, outputs=cs._ctor["outputs"], host=cs._ctor["host"], force_columns=True)
+        return cs.circuit(cols, B)
+
+    flat0 = flat_for(cs.columns)
+    base = flat0.params
+    plan = engine.Circuit(flat0.fc, flat0.models).plan(B, devices=cs.devices)
+    plan.set_params(np.ascontiguousarray(base) if base.size else None)
 
     def params_for(cols):
-        if isinstance(cs.circuit, str) or not callable(cs.circuit):
-            from .netlist import parse_netlist
-            nl = cs.circuit
-            if isinstance(nl, str):
-                if cs._ctor["lang"] == "spectre":
-                    from .spectre import parse_spectre
-                    nl = parse_spectre(nl, include_dirs=cs._ctor["include_dirs"])
-                else:
-                    nl = parse_netlist(nl, include_dirs=cs._ctor["include_dirs"])
-            fl = flatten(nl, cols, B=B, outputs=cs._ctor["outputs"], host=cs._ctor["host"])
-        else:
-            fl = cs.circuit(cols, B)
-        if list(fl.fc.param_names) != list(cs.flat.fc.param_names):
+        fl = flat_for(cols)
+        if list(fl.fc.param_names) != list(flat0.fc.param_names):
             raise ValueError("moving a swept parameter changed the set of parameter columns")
         return fl.params
 
@@ -858,6 +865,7 @@ def _direct_dc_sensitivities(cs: CircuitSweep, wrt: List[str], rel_step: float, 
     plan.set_x0(cs.x0)
     x, sens, status, stats = plan.sens_dc(np.stack(pp) if base.size else np.zeros((len(wrt), 0, B)),
                                           np.stack(pm) if base.size else np.zeros((len(wrt), 0, B)), np.stack(steps), cs._options(kw))
+    plan.close()
     return DirectSensitivitySolution(cs, x, sens, status, stats, wrt)
 
 

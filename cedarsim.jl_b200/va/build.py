@@ -47,6 +47,11 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define OUT_I(k, v) I_[k] = (v)
 #define OUT_Q(k, v) Q_[k] = (v)
 #define OUT_J(idx, k, l, g, c) do {{ G_[(k) * NT + (l)] = (g); C_[(k) * NT + (l)] = (c); }} while (0)
+/* value-only variant: currents and charges, no derivatives (the oracle's chord iterations, like the engine's k_evalv_*) */
+#define VA_SETUPV_BEGIN(NAME) void NAME##_setupv(const double* par_, const uint8_t* given_, double temp_c_, double gmin_, double* cache_) {{
+#define VA_SETUPV_END(NAME) }}
+#define VA_EVALV_BEGIN(NAME) void NAME##_evalv(const double* cache_, const double* v_, double* I_, double* Q_) {{
+#define VA_EVALV_END(NAME) }}
 /* noise variant: power of every noise source at the bias point (and the flicker exponent) */
 #define VA_SETUPN_BEGIN(NAME) void NAME##_setupn(const double* par_, const uint8_t* given_, double temp_c_, double gmin_, double* cache_) {{
 #define VA_SETUPN_END(NAME) }}
@@ -69,6 +74,10 @@ class HostModel:
         self.eval_addr = C.cast(self.eval, C.c_void_p).value
         self.setupn = self.noise = None
         self.setupn_addr = self.noise_addr = 0
+        self.setupv_addr = self.evalv_addr = 0
+        if cm.source_v:
+            self.setupv_addr = C.cast(getattr(self.lib, cm.name + "_setupv"), C.c_void_p).value
+            self.evalv_addr = C.cast(getattr(self.lib, cm.name + "_evalv"), C.c_void_p).value
         if cm.source_n:
             self.setupn = getattr(self.lib, cm.name + "_setupn")
             self.noise = getattr(self.lib, cm.name + "_noise")
@@ -81,7 +90,8 @@ class HostModel:
         return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
                             self.setup_addr, self.eval_addr, ncache_n=cm.ncache_n,
                             noise_pos=[int(s[0]) for s in cm.noise_sources], noise_neg=[int(s[1]) for s in cm.noise_sources],
-                            host_setupn=self.setupn_addr, host_noise=self.noise_addr, branch_terms=list(cm.branch_terms), linear=bool(cm.linear))
+                            host_setupn=self.setupn_addr, host_noise=self.noise_addr, branch_terms=list(cm.branch_terms), linear=bool(cm.linear),
+                            ncache_v=cm.ncache_v, host_setupv=self.setupv_addr, host_evalv=self.evalv_addr)
 
     # convenience for tests
     def run_noise(self, params: dict, v, temp_c=27.0, gmin=1e-12):
@@ -135,7 +145,9 @@ def build_host(cm: CompiledModel, out_dir: Optional[str] = None, opt: str = "-O2
     compiler's default FP contraction; the tag (a hash of the host CPU's flags) keeps such builds per host."""
     out_dir = out_dir or GEN_DIR
     os.makedirs(out_dir, exist_ok=True)
-    text = c_prelude(len(cm.terminals), count_ops) + cm.source + (cm.source_n or "")
+    # (a value-only variant may still carry OUT_J lines of bias-independent Jacobian entries: it has no G / C arguments)
+    text = c_prelude(len(cm.terminals), count_ops) + cm.source + \
+        ("#undef OUT_J\n#define OUT_J(idx, k, l, g, c) do { } while (0)\n" + cm.source_v if cm.source_v else "") + (cm.source_n or "")
     flags = [opt, "-ffp-contract=off"] if fast_tag is None else ["-O3", "-march=native"]
     key = hashlib.sha1((text + opt + (fast_tag or "")).encode()).hexdigest()[:16]
     base = os.path.join(out_dir, f"{cm.name}_{key}")

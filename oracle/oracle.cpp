@@ -53,6 +53,7 @@ typedef void (*va_setup_fn)(const double* par, const uint8_t* given, double temp
                             double* cache);
 typedef void (*va_eval_fn)(const double* cache, const double* v, double* I, double* Q, double* G,
                            double* C);
+typedef void (*va_evalv_fn)(const double* cache, const double* v, double* I, double* Q);
 typedef void (*va_noise_fn)(const double* cache, const double* v, double* pwr, double* ex);
 typedef std::complex<double> cplx;
 
@@ -183,6 +184,7 @@ inline double xv(const double* x, int i) { return i < 0 ? 0.0 : x[i]; }
 
 struct VaCache {  // per instance: bias-independent values of every VA device
     std::vector<std::vector<double>> cache;
+    std::vector<std::vector<double>> cachev;   // of the value-only variant (chord iterations), when the model has one
 };
 
 void va_setup_all(const Inst& in, double temp_c, double gmin, VaCache& vc) {
@@ -195,10 +197,17 @@ void va_setup_all(const Inst& in, double temp_c, double gmin, VaCache& vc) {
         for (int k = 0; k < m.nparam; k++) par[k] = vi.given[k] ? in.pv(vi.par[k]) : 0.0;
         vc.cache[d].assign(std::max(1, m.ncache), 0.0);
         ((va_setup_fn)m.host_setup)(par.data(), vi.given, temp_c, gmin, vc.cache[d].data());
+        vc.cachev.resize(fc->n_va_insts);
+        if (m.host_setupv && m.host_evalv) {
+            vc.cachev[d].assign(std::max(1, m.ncache_v), 0.0);
+            ((va_setup_fn)m.host_setupv)(par.data(), vi.given, temp_c, gmin, vc.cachev[d].data());
+        }
     }
 }
 
-void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, bool dcop, Sys& s) {
+// value_only: the Verilog-A devices are evaluated by their derivative-free variant (currents and charges only, as the
+// engine's k_evalv_* kernels do in its chord iterations); their G / C contributions are then absent from s
+void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, bool dcop, Sys& s, bool value_only = false) {
     const cb_flat_circuit* fc = in.fc;
     const int N = s.N;
     s.zero();
@@ -273,6 +282,14 @@ void eval_system(const Inst& in, const VaCache& vc, const double* x, double t, b
         v.assign(nt, 0); I.assign(nt, 0); Q.assign(nt, 0);
         Gl.assign((size_t)nt * nt, 0); Cl.assign((size_t)nt * nt, 0);
         for (int k = 0; k < nt; k++) v[k] = xv(x, vi.term[k]);
+        if (value_only && m.host_evalv && !vc.cachev[d].empty()) {
+            ((va_evalv_fn)m.host_evalv)(vc.cachev[d].data(), v.data(), I.data(), Q.data());
+            for (int k = 0; k < nt; k++) {
+                addf(vi.term[k], vi.mult * I[k]);
+                addq(vi.term[k], vi.mult * Q[k]);
+            }
+            continue;
+        }
         ((va_eval_fn)m.host_eval)(vc.cache[d].data(), v.data(), I.data(), Q.data(), Gl.data(), Cl.data());
         for (int k = 0; k < nt; k++) {
             addf(vi.term[k], vi.mult * I[k]);
@@ -471,7 +488,7 @@ struct Solver {
                 // value-only evaluation: currents and charges at x; G / C (and the factors) stay those of the last full iteration
                 keepG.swap(s.G); keepC.swap(s.C);
                 if (s.G.size() != keepG.size()) { s.G.assign(keepG.size(), 0.0); s.C.assign(keepC.size(), 0.0); }
-                eval_system(in, vc, x.data(), t, dcop, s);
+                eval_system(in, vc, x.data(), t, dcop, s, true);
                 keepG.swap(s.G); keepC.swap(s.C);
             }
             cnt.newton++;

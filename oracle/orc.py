@@ -42,8 +42,8 @@ def fast_lib():
     if _fast_lib is None:
         name = f"_build/liboracle_fast_{cpu_tag()}.so"
         path = os.path.join(_here, name)
-        if not os.path.exists(path):
-            subprocess.run(["make", "-C", _here, "-s", "fast", f"FAST_OUT={name}"], check=True)
+        # always through make: a library left over from an older oracle.cpp / header (same CPU tag) must not be loaded
+        subprocess.run(["make", "-C", _here, "-s", "fast", f"FAST_OUT={name}"], check=True)
         _fast_lib = C.CDLL(path)
         _fast_lib.orc_wave_value.restype = C.c_double
     return _fast_lib

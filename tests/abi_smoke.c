@@ -28,7 +28,7 @@ static int layout(void) {
     S_(cb_va_model); F(cb_va_model, name); F(cb_va_model, nterm); F(cb_va_model, nparam); F(cb_va_model, ncache); F(cb_va_model, nj);
     F(cb_va_model, jrow); F(cb_va_model, jcol); F(cb_va_model, host_setup); F(cb_va_model, host_eval); F(cb_va_model, n_noise);
     F(cb_va_model, ncache_n); F(cb_va_model, noise_pos); F(cb_va_model, noise_neg); F(cb_va_model, host_setupn);
-    F(cb_va_model, host_noise); F(cb_va_model, linear);
+    F(cb_va_model, host_noise); F(cb_va_model, linear); F(cb_va_model, ncache_v); F(cb_va_model, host_setupv); F(cb_va_model, host_evalv);
     S_(cb_va_inst); F(cb_va_inst, model); F(cb_va_inst, term); F(cb_va_inst, par); F(cb_va_inst, given); F(cb_va_inst, mult);
     S_(cb_flat_circuit); F(cb_flat_circuit, n_unknowns); F(cb_flat_circuit, n_nodes); F(cb_flat_circuit, n_params);
     F(cb_flat_circuit, n_devices); F(cb_flat_circuit, devices); F(cb_flat_circuit, n_waves); F(cb_flat_circuit, n_va_models);
