@@ -282,8 +282,20 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
 #define VA_STAGES 4
 #endif
 
+// VA_CACHE_HINT=1: the cache rows are read once per launch and never again before ~1 GB of other rows has passed: mark
+// them evict-first in L2 so that they do not push out the lines that ARE re-used (register spills of the eval kernels,
+// the device outputs k_lu reads next).
+#ifndef VA_CACHE_HINT
+#define VA_CACHE_HINT 0
+#endif
 VA_FN void va_cp8(unsigned dst, const double* src) {
+#if VA_CACHE_HINT
+    unsigned long long pol_;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_));
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol_) : "memory");
+#else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 VA_FN void va_cp16(unsigned dst, const double* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");

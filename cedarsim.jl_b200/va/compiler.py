@@ -392,8 +392,9 @@ class CompiledModel:
 class _Compiler:
     def __init__(self, mod: Module, name: str, const_params: Optional[Dict[str, float]] = None,
                  runtime_params: Optional[Sequence[str]] = None, no_deriv: bool = False, skip_funcs=(),
-                 noise: bool = False, probe_branches: Sequence[Tuple[str, str]] = ()):
+                 noise: bool = False, probe_branches: Sequence[Tuple[str, str]] = (), part: Optional[str] = None):
         self.mod = mod
+        self.part = part                  # None | "I" | "Q": keep only the resistive / only the ddt() part of every contribution
         self.name = name
         self.noise = noise                # noise variant: outputs the power of every noise source, nothing else
         self.noise_sources: List[Tuple[int, int, str, str]] = []   # (pos terminal, neg terminal, kind, name), -1 = ground
@@ -1343,6 +1344,34 @@ class _Compiler:
             return (None if r is None else ("un", "-", r)), [(("un", "-", c), qq) for c, qq in q]
         raise VACompileError("ddt() must appear linearly in a contribution")
 
+    def _strip_part(self, st):
+        """Half of the model: every contribution keeps only its resistive part ("I") or only its ddt() part ("Q"); dead-code
+        elimination then drops what only the other half needs."""
+        k = st[0]
+        if k == "contrib":
+            e, noises = self._split_noise(st[3]) if not self.noise else (st[3], [])
+            if e is None:
+                return ("nop",)
+            res, qs = self._split_ddt(e)
+            if self.part == "I":
+                return ("contrib", st[1], st[2], res) if res is not None else ("nop",)
+            new = None
+            for c, q in qs:
+                term = ("bin", "*", c, ("call", "ddt", [q]))
+                new = term if new is None else ("bin", "+", new, term)
+            return ("contrib", st[1], st[2], new) if new is not None else ("nop",)
+        if k == "block":
+            return ("block", st[1], [self._strip_part(x) for x in st[2]], st[3])
+        if k == "if":
+            return ("if", st[1], self._strip_part(st[2]), self._strip_part(st[3]) if st[3] else None)
+        if k == "case":
+            return ("case", st[1], [(vals, self._strip_part(x)) for vals, x in st[2]], self._strip_part(st[3]) if st[3] else None)
+        if k == "for":
+            return ("for", st[1], st[2], st[3], self._strip_part(st[4]))
+        if k in ("while", "repeat"):
+            return (k, st[1], self._strip_part(st[2]))
+        return st
+
     def _has_ddt(self, e) -> bool:
         k = e[0]
         if k == "call":
@@ -1781,6 +1810,8 @@ class _Compiler:
             if bad:
                 raise VACompileError(f"module {mod.name} has no parameter(s) {bad}")
         body = ("block", None, list(mod.analog), {})
+        if self.part in ("I", "Q"):
+            body = self._strip_part(body)
         # (translational invariance holds for node voltages only, not for branch-current unknowns)
         self.drop_seed = None if (self.no_deriv or self.branch_terms) else self._pick_drop_seed(body)
         if not self.noise:
