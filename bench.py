@@ -286,7 +286,10 @@ def main():
     if not args.no_extra_legs:
         fopts = engine.default_options(**OPTS, **ENGINE_OPTS, fixed_step=1, dt=FIXED_DT)
         elf, totf, _ = resident_leg(plan, B, fopts, 0, 1)
+        _, ds_f, _ = 0, plan.last_status_ptr, 0
+        st_f = torch.as_tensor(DevArray(ds_f, (B,), "<i4"), device="cuda").cpu().numpy() if ds_f else None
         fixed = {"value": B * world / elf, "unit": "points/s", "dt": FIXED_DT, "ms_per_step": 1e3 * elf, "steps": 1,
+                 "converged_points_this_rank": int((st_f == 0).sum()) if st_f is not None else None,
                  "rounds": totf["rounds"],
                  "newton_iters_per_point": totf["newton_iters"] / B, "accepted_steps_per_point": totf["steps_accepted"] / B}
     # ---- weak scaling next to the strong-scaling headline: 16 384 points on EVERY GPU

@@ -286,7 +286,7 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
 // them evict-first in L2 so that they do not push out the lines that ARE re-used (register spills of the eval kernels,
 // the device outputs k_lu reads next).
 #ifndef VA_CACHE_HINT
-#define VA_CACHE_HINT 0
+#define VA_CACHE_HINT 1   // measured +3 % points/s on the bench workload (profiles/probe_r2i.log: 4 733 -> 4 874)
 #endif
 VA_FN void va_cp8(unsigned dst, const double* src) {
 #if VA_CACHE_HINT

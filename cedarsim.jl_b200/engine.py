@@ -157,6 +157,7 @@ class Plan:
             _check(self.lib.cb_plan_create_lanes(circuit.handle, C.c_int64(self.B), C.c_int(self.device), C.c_int(lanes),
                                                  C.byref(self.handle)))
         self.lanes = int(self.lib.cb_plan_lanes(self.handle))
+        self.last_status_ptr = None
         self.n_devices = int(self.lib.cb_plan_devices(self.handle))
 
     def set_params(self, params: Optional[np.ndarray]):
@@ -254,6 +255,7 @@ class Plan:
         st = F.cb_stats()
         _check(self.lib.cb_tran_device(self.handle, C.c_double(t0), C.c_double(t1), _dp(saveat), C.c_int64(len(saveat)),
                                        C.byref(opts), C.byref(dy), C.byref(ds), C.byref(st)))
+        self.last_status_ptr = ds.value
         return dy.value, ds.value, st.as_dict()
 
     def dc_device(self, opts: Optional[F.cb_options] = None):
