@@ -216,27 +216,26 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #ifndef VA_CACHE_LAYOUT
 #define VA_CACHE_LAYOUT 0
 #endif
+#ifndef VA_CACHE_LAYOUT_V
+#define VA_CACHE_LAYOUT_V VA_CACHE_LAYOUT   // layout of the value-only variant's cache (its launches have gaps in lock-step rounds)
+#endif
+// VA_LAYOUT: the layout of the variant being compiled; the engine redefines it between the full / value-only / noise
+// blocks of a model (engine.py cuda_source), every macro below is evaluated where the generated code expands it.
+#define VA_LAYOUT VA_CACHE_LAYOUT
 #define VA_CACHE_BLK 128   // rows are allocated for B rounded up to a multiple of this
 #define NCACHE_P ((NCACHE + 3) / 4 * 4)
-#if VA_CACHE_LAYOUT == 0
-#define VA_SLOT_OFF(s) ((s) * VA_CACHE_BLK)
+template <int L>
+VA_FN constexpr int va_slot_off(const int s) {
+    return L == 0 ? s * VA_CACHE_BLK : L == 3 ? (s / 4) * (4 * VA_CACHE_BLK) + (s % 4) : s;
+}
+#define VA_SLOT_OFF(s) va_slot_off<VA_LAYOUT>(s)
+template <int L>
 VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
     const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
-    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK);
+    if (L == 0) return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK);
+    if (L == 3) return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK) * 4;
+    return ((size_t)dev * (nblk * VA_CACHE_BLK) + (size_t)inst) * (size_t)ncp;
 }
-#elif VA_CACHE_LAYOUT == 3
-#define VA_SLOT_OFF(s) (((s) / 4) * (4 * VA_CACHE_BLK) + ((s) % 4))
-VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
-    const size_t nblk = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK);
-    return (((size_t)dev * nblk + (size_t)(inst / VA_CACHE_BLK)) * ncp) * VA_CACHE_BLK + (size_t)(inst % VA_CACHE_BLK) * 4;
-}
-#else
-#define VA_SLOT_OFF(s) (s)
-VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, const long long inst) {
-    const size_t bpad = (size_t)((B + VA_CACHE_BLK - 1) / VA_CACHE_BLK) * VA_CACHE_BLK;
-    return ((size_t)dev * bpad + (size_t)inst) * (size_t)ncp;
-}
-#endif
 #define VA_SETUP_BEGIN(NAME) VA_SETUP_BEGIN_(k_setup_##NAME)
 #define VA_SETUPV_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupv_##NAME)
 #define VA_SETUPV_END(NAME) }
@@ -250,7 +249,7 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
         const uint8_t* given_ = a.given + (size_t)dev * NPARAM;                                  \
         const double temp_c_ = a.temp_col >= 0 ? a.params[(size_t)a.temp_col * a.B + inst] : a.temp_val; \
         const double gmin_ = a.gmin_col >= 0 ? a.params[(size_t)a.gmin_col * a.B + inst] : a.gmin_val;   \
-        double* cache_ = (double*)a.cache + va_cache_index(a.B, dev, NCACHE_P, inst);              \
+        double* cache_ = (double*)a.cache + va_cache_index<VA_LAYOUT>(a.B, dev, NCACHE_P, inst);              \
         (void)gmin_; (void)temp_c_; (void)par_val_; (void)par_col_; (void)given_;
 #define VA_SETUP_END(NAME) }
 
@@ -291,7 +290,7 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
 VA_FN void va_cp8(unsigned dst, const double* src) {
 #if VA_CACHE_HINT
     unsigned long long pol_;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_));   // not volatile: one per kernel after CSE
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol_) : "memory");
 #else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -302,30 +301,26 @@ VA_FN void va_cp16(unsigned dst, const double* src) {
 }
 // Ring geometry in shared memory.  8-byte copies: [stage][row][thread] (a thread's slots are NTHR doubles apart,
 // conflict-free).  16-byte copies: [stage][row pair][thread][2].
-#if VA_CACHE_LAYOUT >= 2
-#define VA_RING_IDX(s) (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * (VA_CHUNK_ROWS / 2) + ((s) % VA_CHUNK_ROWS) / 2) * (2 * VA_EVAL_THREADS) + ((s) & 1))
-#define VA_RING_TID(t) (2 * (t))
-template <int ROWS, int STAGES, int NTHR>
+#define VA_RING_IDX(s) (VA_LAYOUT >= 2 ? (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * (VA_CHUNK_ROWS / 2) + ((s) % VA_CHUNK_ROWS) / 2) * (2 * VA_EVAL_THREADS) + ((s) & 1)) \
+                                       : (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS))
+#define VA_RING_TID(t) (VA_LAYOUT >= 2 ? 2 * (t) : (t))
+template <int L, int ROWS, int STAGES, int NTHR>
 VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
-    static_assert(ROWS % 2 == 0, "16-byte cache copies need an even number of rows per chunk");
+    if (L >= 2) {
+        static_assert(ROWS % 2 == 0, "16-byte cache copies need an even number of rows per chunk");
 #pragma unroll
-    for (int r = 0; r < ROWS; r += 2) {
-        const int p = chunk * ROWS + r;
-        if (p < ncache) va_cp16(sbase + (unsigned)((((chunk % STAGES) * (ROWS / 2) + r / 2) * (2 * NTHR)) * 8), cache + VA_SLOT_OFF(p));
+        for (int r = 0; r < ROWS; r += 2) {
+            const int p = chunk * ROWS + r;
+            if (p < ncache) va_cp16(sbase + (unsigned)((((chunk % STAGES) * (ROWS / 2) + r / 2) * (2 * NTHR)) * 8), cache + va_slot_off<L>(p));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const int p = chunk * ROWS + r;
+            if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + va_slot_off<L>(p));
+        }
     }
 }
-#else
-#define VA_RING_IDX(s) (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS)
-#define VA_RING_TID(t) (t)
-template <int ROWS, int STAGES, int NTHR>
-VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
-#pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        const int p = chunk * ROWS + r;
-        if (p < ncache) va_cp8(sbase + (unsigned)((((chunk % STAGES) * ROWS + r) * NTHR) * 8), cache + VA_SLOT_OFF(p));
-    }
-}
-#endif
 // (Experiments that did not pay and were removed: CTA-wide barriers at the chunk markers or every ~50 generated
 // lines, and a leader warp running one chunk ahead, to make the warps of a CTA share instruction fetches -- at
 // 128..640 threads per CTA none changed the instruction-cache request count; see DESIGN.md section 5.)
@@ -333,7 +328,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_CHUNK(k)                                                                              \
     {                                                                                            \
         if ((k) + VA_AHEAD < VA_NCHUNK)                                                          \
-            va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE_P, sbase_, cache_); \
+            va_issue<VA_LAYOUT, VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE_P, sbase_, cache_); \
         VA_COMMIT();                                                                             \
         asm volatile("cp.async.wait_group %0;" ::"n"(VA_AHEAD) : "memory");                      \
     }
@@ -372,11 +367,11 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
             inst = a.list[k_];                                                                   \
         }                                                                                        \
         const int dev = blockIdx.y;                                                              \
-        const double* __restrict__ cache_ = a.cache + va_cache_index(a.B, dev, NCACHE_P, inst);    \
+        const double* __restrict__ cache_ = a.cache + va_cache_index<VA_LAYOUT>(a.B, dev, NCACHE_P, inst);    \
         const double* ring_ = va_ring_ + VA_RING_TID(threadIdx.x);                               \
         const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + VA_RING_TID(threadIdx.x)); \
         _Pragma("unroll") for (int c_ = 0; c_ < VA_AHEAD; c_++) {                                \
-            if (c_ < VA_NCHUNK) va_issue<VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE_P, sbase_, cache_); \
+            if (c_ < VA_NCHUNK) va_issue<VA_LAYOUT, VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE_P, sbase_, cache_); \
             VA_COMMIT();                                                                         \
         }                                                                                        \
         const double alpha_ = a.alpha[inst];                                                     \

@@ -79,11 +79,13 @@ def cuda_source(models: Sequence) -> str:
         parts.append(f"#undef NT\n#undef NPARAM\n#undef NCACHE\n#undef NOUT\n#undef NJ\n"
                      f"#define NT {len(cm.terminals)}\n#define NPARAM {max(1, len(cm.params))}\n"
                      f"#define NCACHE {max(1, cm.ncache)}\n#define NJ {len(cm.jrow)}\n"
-                     f"#define NOUT {2 * len(cm.terminals) + 2 * len(cm.jrow)}\n")
+                     f"#define NOUT {2 * len(cm.terminals) + 2 * len(cm.jrow)}\n"
+                     "#undef VA_LAYOUT\n#define VA_LAYOUT VA_CACHE_LAYOUT\n")
         parts.append(cm.source)
-        if getattr(cm, "source_v", ""):   # value-only variant: its own cache layout
-            parts.append(f"#undef NCACHE\n#define NCACHE {max(1, cm.ncache_v)}\n")
+        if getattr(cm, "source_v", ""):   # value-only variant: its own cache (and cache layout, csrc/va_prelude.h)
+            parts.append(f"#undef NCACHE\n#define NCACHE {max(1, cm.ncache_v)}\n#undef VA_LAYOUT\n#define VA_LAYOUT VA_CACHE_LAYOUT_V\n")
             parts.append(cm.source_v)
+            parts.append("#undef VA_LAYOUT\n#define VA_LAYOUT VA_CACHE_LAYOUT\n")
         if getattr(cm, "source_n", ""):   # noise variant: source powers at the operating point (cb_noise)
             K = len(cm.noise_sources)
             parts.append(f"#undef NCACHE\n#undef NOUT\n#undef NNOISE\n#define NCACHE {max(1, cm.ncache_n)}\n"
