@@ -747,6 +747,10 @@ struct cb_plan {
     std::vector<size_t> evalv_smem;
     std::vector<long long> cachev_off;
     double* d_cachev = nullptr;
+    // uniform cache slots (va_prelude.h CACHE_LDU): per variant (0 full, 1 value-only, 2 noise) and model the slot count and a
+    // table of [B][nuni] doubles (only the first row is used unless temperature / gmin are swept)
+    std::vector<int> nuni[3];
+    std::vector<double*> d_uni[3];
     // small-signal analyses (cb_ac / cb_noise): tables built on first use
     std::vector<cudaKernel_t> k_setupn, k_evaln;
     std::vector<unsigned> evaln_threads;
@@ -763,6 +767,8 @@ struct cb_plan {
     bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
+    bool lu_staged = false;                  // k_lu's table blob lives in shared memory behind the matrices
+    std::vector<unsigned char> lu_blob;
     int* d_dc_count = nullptr;
     // point lists of the rounds (device-wide compaction, kernels.cuh): [parity][kind][B] and counters [parity][2]
     int* d_lists = nullptr;
@@ -991,9 +997,10 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             {   // block size and dynamic shared memory (cache ring) the generated kernel was compiled for
                 void* dmeta = nullptr;
                 size_t msz = 0;
-                int meta[4] = {128, 0, 0, 0};
+                int meta[6] = {128, 0, 0, 0, 1, 0};
                 CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_meta_" + m.name).c_str()));
-                CUDA_TRY(cudaMemcpy(meta, dmeta, sizeof meta, cudaMemcpyDeviceToHost));
+                CUDA_TRY(cudaMemcpy(meta, dmeta, std::min(msz, sizeof meta), cudaMemcpyDeviceToHost));
+                p->nuni[0].push_back(std::max(1, meta[4]));
                 p->eval_threads.push_back((unsigned)meta[0]);
                 p->eval_smem.push_back((size_t)meta[1]);
                 if (meta[1] > 48 * 1024)
@@ -1003,13 +1010,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             p->k_setup.push_back(ks);
             p->k_eval.push_back(ke);
             cudaKernel_t ksv = nullptr, kev = nullptr;
-            int metav[4] = {128, 0, 0, 0};
+            int metav[6] = {128, 0, 0, 0, 1, 0};
             if (cudaLibraryGetKernel(&kev, p->lib, ("k_evalv_" + m.name).c_str()) == cudaSuccess &&
                 cudaLibraryGetKernel(&ksv, p->lib, ("k_setupv_" + m.name).c_str()) == cudaSuccess) {
                 void* dmeta = nullptr;
                 size_t msz = 0;
                 CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_metav_" + m.name).c_str()));
-                CUDA_TRY(cudaMemcpy(metav, dmeta, sizeof metav, cudaMemcpyDeviceToHost));
+                CUDA_TRY(cudaMemcpy(metav, dmeta, std::min(msz, sizeof metav), cudaMemcpyDeviceToHost));
                 if (metav[1] > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributeMaxDynamicSharedMemorySize, metav[1]));
                 CUDA_TRY(cudaFuncSetAttribute((const void*)kev, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout(metav)));
@@ -1019,13 +1026,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             }
             {   // noise variant (optional)
                 cudaKernel_t ksn = nullptr, ken = nullptr;
-                int metan[4] = {128, 0, 0, 0};
+                int metan[6] = {128, 0, 0, 0, 1, 0};
                 if (!m.noise_pos.empty() && cudaLibraryGetKernel(&ken, p->lib, ("k_evaln_" + m.name).c_str()) == cudaSuccess &&
                     cudaLibraryGetKernel(&ksn, p->lib, ("k_setupn_" + m.name).c_str()) == cudaSuccess) {
                     void* dmeta = nullptr;
                     size_t msz = 0;
                     CUDA_TRY(cudaLibraryGetGlobal(&dmeta, &msz, p->lib, ("va_metan_" + m.name).c_str()));
-                    CUDA_TRY(cudaMemcpy(metan, dmeta, sizeof metan, cudaMemcpyDeviceToHost));
+                    CUDA_TRY(cudaMemcpy(metan, dmeta, std::min(msz, sizeof metan), cudaMemcpyDeviceToHost));
                     if (metan[1] > 48 * 1024)
                         CUDA_TRY(cudaFuncSetAttribute((const void*)ken, cudaFuncAttributeMaxDynamicSharedMemorySize, metan[1]));
                 } else {
@@ -1036,12 +1043,14 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 p->k_evaln.push_back(ken);
                 p->evaln_threads.push_back((unsigned)metan[0]);
                 p->evaln_smem.push_back((size_t)metan[1]);
+                p->nuni[2].push_back(std::max(1, metan[4]));
             }
             p->k_setupv.push_back(ksv);
             p->k_evalv.push_back(kev);
             p->evalv_threads.push_back((unsigned)metav[0]);
             p->evalv_smem.push_back((size_t)metav[1]);
             p->cachev_off.push_back(metav[2]);   // slots per instance for now; turned into offsets below
+            p->nuni[1].push_back(std::max(1, metav[4]));
         }
     }
     NArgs& a = p->na;
@@ -1151,6 +1160,12 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         TRY(p->upload(&dt_, term)); TRY(p->upload(&dc_, pcol)); TRY(p->upload(&dv_, pval)); TRY(p->upload(&dg_, giv));
         p->d_term.push_back(dt_); p->d_par_col.push_back(dc_); p->d_par_val.push_back(dv_); p->d_given.push_back(dg_);
     }
+    for (int v = 0; v < 3; v++)
+        for (size_t m = 0; m < c->models.size(); m++) {
+            double* du = nullptr;
+            TRY(p->alloc(&du, (size_t)p->nuni[v][m] * B));
+            p->d_uni[v].push_back(du);
+        }
     // solve kernel: shared-memory batched LU (k_lu) when the factors of LU_PTS points fit one SM, else the generated
     // straight-line k_solve (no value-only rounds then)
     {
@@ -1158,88 +1173,132 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id));
         const char* env = std::getenv("CB_NEWTON");
         p->lu_smem = (size_t)(S.nnz_lu + 2 * N) * LU_PTS * sizeof(double);
-        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_W * LU_PTS + 2048;
+        const size_t lu_static = (size_t)(2 * sizeof(double) + sizeof(int)) * LU_PTS + 2048;   // reduction slots + the driver's reserve
         p->lu = !(env && std::string(env) == "gen") && p->lu_smem + lu_static <= (size_t)max_smem;
         if (!p->lu) p->have_v = false;
         if (p->lu) {
             LuSchedule sch;
             build_lu_schedule(S, LU_W, sch);
             LArgs& la = p->la;
-            int4* dops; int* ti;
-            TRY(p->upload(&dops, sch.ops)); la.ops = dops;
-            TRY(p->upload(&ti, sch.op_ptr)); la.op_ptr = ti;
-            TRY(p->upload(&ti, sch.piv)); la.piv = ti;
-            TRY(p->upload(&ti, sch.piv_ptr)); la.piv_ptr = ti;
-            TRY(p->upload(&ti, sch.brow)); la.brow = ti;
-            TRY(p->upload(&ti, sch.brow_ptr)); la.brow_ptr = ti;
-            TRY(p->upload(&ti, S.u_col)); la.u_col = ti;
             la.nlev = sch.nlev; la.nblev = sch.nblev;
             std::vector<int4> sops;
             std::vector<int> sop_ptr;
             int nslev = 0;
             build_fwd_schedule(S, LU_W, sops, sop_ptr, nslev);
-            TRY(p->upload(&dops, sops)); la.sops = dops;
-            TRY(p->upload(&ti, sop_ptr)); la.sop_ptr = ti;
             la.nslev = nslev;
+            // the table blob (kernels.cuh LuTabs): 16-bit entries, every table 16-byte aligned
+            std::vector<unsigned char>& blob = p->lu_blob;
+            bool blob_ok = true;
+            auto add16 = [&](const std::vector<int>& v) {
+                const int off = (int)blob.size();
+                for (int x : v) {
+                    if (x < 0 || x > 65535) blob_ok = false;
+                    const unsigned short u = (unsigned short)x;
+                    blob.push_back((unsigned char)(u & 0xff)); blob.push_back((unsigned char)(u >> 8));
+                }
+                while (blob.size() % 16) blob.push_back(0);
+                return off;
+            };
+            auto add_ops = [&](const std::vector<int4>& v) {
+                std::vector<int> flat;
+                for (const int4& o : v) { flat.push_back(o.x); flat.push_back(o.y); flat.push_back(o.z); flat.push_back(o.w); }
+                return add16(flat);
+            };
+            LuTabs& t = la.t;
+            t.op_ptr = add16(sch.op_ptr); t.piv_ptr = add16(sch.piv_ptr); t.piv = add16(sch.piv); t.ops = add_ops(sch.ops);
+            t.brow_ptr = add16(sch.brow_ptr); t.brow = add16(sch.brow);
+            t.u_ptr = add16(S.u_ptr); t.u_pos = add16(S.u_pos); t.u_col = add16(S.u_col); t.diag_pos = add16(S.diag_pos);
+            t.sop_ptr = add16(sop_ptr); t.sops = add_ops(sops);
+            {
+                std::vector<int> al(S.nnz_lu);
+                for (int e = 0; e < S.nnz_lu; e++) {
+                    if (c->a_lin[e] + 1 >= 0x8000) blob_ok = false;
+                    al[e] = ((c->a_lin[e] + 1) & 0x7fff) | (c->a_diag[e] ? 0x8000 : 0);
+                }
+                t.a_lin = add16(al);
+            }
+            t.rl_ptr = add16(c->rl_ptr); t.rl_lin = add16(c->rl_lin); t.rl_col = add16(c->rl_col);
+            t.rs_ptr = add16(c->rs_ptr); t.rs_wave = add16(c->rs_wave);
+            t.row_to_step = add16(S.row_to_step); t.col_to_step = add16(S.col_to_step);
             if (std::getenv("CB_DEBUG"))
                 std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu fwd-levels=%d fwd-ops=%zu smem=%zu\n", N,
                              S.nnz_lu, sch.nlev, sch.nblev, sch.ops.size(), nslev, sops.size(), p->lu_smem);
             // gather items, grouped by destination and balanced over the warps; the value-only list holds the
             // residual and charge rows only
-            auto item = [](int src, int dst, double m) {
-                long long bits;
-                std::memcpy(&bits, &m, sizeof bits);
-                return make_int4(src, dst, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
+            // items are (dev_out row | multiplier code << 20, destination | second position << 16); the distinct multipliers
+            // (+-1, +-m of the instances, source coefficients) are a small table of doubles in the blob
+            std::vector<double> mtab;
+            auto mcode = [&](double m) {
+                for (size_t k = 0; k < mtab.size(); k++) if (std::memcmp(&mtab[k], &m, sizeof m) == 0) return (int)k;
+                mtab.push_back(m);
+                return (int)mtab.size() - 1;
             };
-            for (int pass = 0; pass < 2; pass++) {
-                std::map<int, std::vector<int4>> by_dst;
-                if (pass == 0)
-                    for (int e = 0; e < S.nnz_lu; e++)
-                        for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, c->a_mult[q]));
-                for (int i = 0; i < N; i++) {
-                    for (int q = c->ri_ptr[i]; q < c->ri_ptr[i + 1]; q++)
-                        by_dst[S.nnz_lu + S.row_to_step[i]].push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], -c->ri_mult[q]));
-                    for (int q = c->rq_ptr[i]; q < c->rq_ptr[i + 1]; q++)
-                        by_dst[S.nnz_lu + N + i].push_back(item(c->rq_src[q], S.nnz_lu + N + i, c->rq_mult[q]));
-                }
-                std::vector<std::pair<int, int>> groups;
+            auto item = [&](int src, int dst, int aux, double m) {
+                const int code = mcode(m);
+                if (src < 0 || src >= (1 << 20) || code >= (1 << 12) || dst < 0 || dst > 65535 || aux < 0 || aux > 65535) blob_ok = false;
+                return make_int2((int)((unsigned)src | ((unsigned)code << 20)), (int)((unsigned)dst | ((unsigned)aux << 16)));
+            };
+            auto balance = [&](std::map<int, std::vector<int2>>& by_dst, std::vector<int2>& items, std::vector<int>& iptr) {
+                std::vector<std::pair<int, int>> groups;   // (size, dst), largest first onto the least loaded warp
                 for (auto& kv : by_dst) groups.push_back({(int)kv.second.size(), kv.first});
                 std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
-                std::vector<std::vector<int4>> per(LU_W);
+                std::vector<std::vector<int2>> per(LU_W);
                 for (auto& g : groups) {
                     int best = 0;
                     for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
                     per[best].insert(per[best].end(), by_dst[g.second].begin(), by_dst[g.second].end());
                 }
-                std::vector<int4> items;
-                std::vector<int> iptr(1, 0);
+                items.clear(); iptr.assign(1, 0);
                 for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
-                TRY(p->upload(&dops, items));
-                TRY(p->upload(&ti, iptr));
-                if (pass == 0) { la.items = dops; la.item_ptr = ti; } else { la.sitems = dops; la.sitem_ptr = ti; }
+            };
+            int2* ditems;
+            // gather items, grouped by destination and balanced over the warps; the value-only list holds the
+            // residual and charge rows only
+            for (int pass = 0; pass < 2; pass++) {
+                std::map<int, std::vector<int2>> by_dst;
+                if (pass == 0)
+                    for (int e = 0; e < S.nnz_lu; e++)
+                        for (int q = c->a_ptr[e]; q < c->a_ptr[e + 1]; q++) by_dst[e].push_back(item(c->a_src[q], e, 0, c->a_mult[q]));
+                for (int i = 0; i < N; i++) {
+                    for (int q = c->ri_ptr[i]; q < c->ri_ptr[i + 1]; q++)
+                        by_dst[S.nnz_lu + S.row_to_step[i]].push_back(item(c->ri_src[q], S.nnz_lu + S.row_to_step[i], 0, -c->ri_mult[q]));
+                    for (int q = c->rq_ptr[i]; q < c->rq_ptr[i + 1]; q++)
+                        by_dst[S.nnz_lu + N + i].push_back(item(c->rq_src[q], S.nnz_lu + N + i, 0, c->rq_mult[q]));
+                }
+                std::vector<int2> items;
+                std::vector<int> iptr;
+                balance(by_dst, items, iptr);
+                TRY(p->upload(&ditems, items));
+                if (pass == 0) { la.items = ditems; t.item_ptr = add16(iptr); } else { la.sitems = ditems; t.sitem_ptr = add16(iptr); }
             }
             {   // charge-update items, all items of one row on one warp
-                std::map<int, std::vector<int>> by_row;
-                for (size_t q = 0; q < c->cq_row.size(); q++) by_row[c->cq_row[q]].push_back((int)q);
-                std::vector<std::pair<int, int>> groups;
-                for (auto& kv : by_row) groups.push_back({(int)kv.second.size(), kv.first});
-                std::sort(groups.begin(), groups.end(), [](auto& x, auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
-                std::vector<std::vector<int4>> per(LU_W);
-                for (auto& g : groups) {
-                    int best = 0;
-                    for (int w = 1; w < LU_W; w++) if (per[w].size() < per[best].size()) best = w;
-                    for (int q : by_row[g.second])
-                        per[best].push_back(make_int4(c->cq_src[q], S.nnz_lu + N + c->cq_row[q], S.nnz_lu + S.col_to_step[c->cq_col[q]], q));
-                }
-                std::vector<int4> items;
-                std::vector<int> iptr(1, 0);
-                for (int w = 0; w < LU_W; w++) { items.insert(items.end(), per[w].begin(), per[w].end()); iptr.push_back((int)items.size()); }
-                double* dm;
-                TRY(p->upload(&dops, items)); la.citems = dops;
-                TRY(p->upload(&ti, iptr)); la.citem_ptr = ti;
-                TRY(p->upload(&dm, c->cq_mult)); la.cmult = dm;
+                std::map<int, std::vector<int2>> by_row;
+                for (size_t q = 0; q < c->cq_row.size(); q++)
+                    by_row[c->cq_row[q]].push_back(item(c->cq_src[q], S.nnz_lu + N + c->cq_row[q], S.nnz_lu + S.col_to_step[c->cq_col[q]], c->cq_mult[q]));
+                std::vector<int2> items;
+                std::vector<int> iptr;
+                balance(by_row, items, iptr);
+                TRY(p->upload(&ditems, items)); la.citems = ditems;
+                t.citem_ptr = add16(iptr);
             }
-            CUDA_TRY(cudaFuncSetAttribute(k_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            {
+                t.mtab = (int)blob.size();
+                const unsigned char* mb = (const unsigned char*)mtab.data();
+                blob.insert(blob.end(), mb, mb + mtab.size() * sizeof(double));
+                while (blob.size() % 16) blob.push_back(0);
+            }
+            t.bytes = (int)blob.size();
+            if (!blob_ok) { p->lu = false; p->have_v = false; }   // an index beyond 16 bits (never at sizes whose matrices fit one SM): generated k_solve
+            else {
+                unsigned char* dblob;
+                TRY(p->upload(&dblob, blob)); la.tab = dblob;
+                // stage the blob in shared memory when it fits behind the matrices
+                p->lu_staged = p->lu_smem + blob.size() + lu_static <= (size_t)max_smem && !std::getenv("CB_LU_NOSTAGE");
+                if (p->lu_staged) p->lu_smem += blob.size();
+                if (std::getenv("CB_DEBUG")) std::fprintf(stderr, "k_lu tables: %zu bytes, staged=%d\n", blob.size(), (int)p->lu_staged);
+                if (p->lu_staged) CUDA_TRY(cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                else CUDA_TRY(cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+            }
             la.LUF = nullptr;
         }
         TRY(p->alloc(&p->d_DX, (size_t)N * B));
@@ -1321,6 +1380,7 @@ struct VaArgsH {
     long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
     const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
     double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
+    double* uni; int uni_per_inst; int pad_;
 };
 
 // which point list a device-evaluation launch runs over: this round's full-iteration or value-only points
@@ -1336,6 +1396,13 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     a->given = p->d_given[m];
     a->temp_val = opt->temp.value; a->gmin_val = opt->gmin.value;
     a->temp_col = opt->temp.col; a->gmin_col = opt->gmin.col;
+    a->uni = p->d_uni[value_only ? 1 : 0][m];
+    a->uni_per_inst = (opt->temp.col >= 0 || opt->gmin.col >= 0) ? 1 : 0; a->pad_ = 0;
+}
+
+static inline void launch_lu(cb_plan* p, unsigned grid, cudaStream_t st, const LArgs& la) {
+    if (p->lu_staged) k_lu<true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+    else k_lu<false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
 }
 
 static int run_setup(cb_plan* p, const cb_options* opt) {
@@ -1597,7 +1664,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
         }
         if (ev) cudaEventRecord(ev[2], p->stream);
-        if (p->lu) k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, p->stream>>>(largs[par]);
+        if (p->lu) launch_lu(p, lu_grid, p->stream, largs[par]);
         else {
             void* sargs_ptr[] = {&sargs};
             CUDA_TRY(cudaMemsetAsync(p->d_cnt + (1 - par) * 2, 0, 2 * sizeof(int), p->stream));
@@ -1838,7 +1905,7 @@ static int sens_dc1(cb_plan* p, const cb_options* opt, int64_t n_dir, const doub
     }
     k_init_waves<<<gB, 128, 0, st>>>(a, p->d_WV);
     la.n = a;
-    k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+    launch_lu(p, lu_grid, st, la);
     CUDA_TRY(cudaGetLastError());
     // 2. two chord updates per direction with the moved parameters
     a.params = d_pert;
@@ -1868,7 +1935,7 @@ static int sens_dc1(cb_plan* p, const cb_options* opt, int64_t n_dir, const doub
                 dim3 grid((unsigned)((B + p->evalv_threads[m] - 1) / p->evalv_threads[m]), (unsigned)c->model_insts[m].size());
                 cudaLaunchKernel((const void*)p->k_evalv[m], grid, dim3(p->evalv_threads[m]), kargs, p->evalv_smem[m], st);
             }
-            k_lu<<<lu_grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+            launch_lu(p, lu_grid, st, la);
             k_sens_accum<<<gB, 128, 0, st>>>(B, O, a.outputs, p->d_DX, d_step, sg == 0 ? 1.0 : -1.0, d_sens);
             err = cudaGetLastError();
         }
@@ -2031,6 +2098,7 @@ static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, 
             fill_va_args(p, m, opt, args);
             VaArgsHead* h = (VaArgsHead*)args;
             h->cache = p->d_cachen + (size_t)p->cachen_off[m] * p->Bpad;
+            ((VaArgsH*)args)->uni = p->d_uni[2][m];
             h->out = p->d_noise_out + (size_t)p->noise_off[m] * B;
             void* kargs[] = {args};
             if (!p->setupn_valid) {

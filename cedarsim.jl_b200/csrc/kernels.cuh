@@ -617,31 +617,39 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
 #ifndef LU_GU
 #define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
 #endif
+// Index tables of k_lu: every small table (level schedules, pivot / row lists, the U pattern, the linear-part maps) is
+// packed as 16-bit entries into ONE blob (ops as four 16-bit positions = 8 bytes).  When the blob fits behind the matrices
+// of the group (DFF: 207 KB of matrices + ~12 KB of tables of the 227 KB a CTA may have) every CTA copies it into shared
+// memory once, so the ~60 barrier-separated level phases of a group read their schedules at shared-memory latency
+// instead of L2 latency (L1 is ~16 KB at this carve-out); otherwise the same code reads the blob from global memory.
+// The members are byte offsets into the blob.
+struct LuTabs {
+    int op_ptr, piv_ptr, piv, ops, brow_ptr, brow, u_ptr, u_pos, u_col, diag_pos, sop_ptr, sops;
+    int a_lin;                // per LU entry: bit 15 = node diagonal (gshunt), low bits = index of its linear stamp + 1 (0: none)
+    int rl_ptr, rl_lin, rl_col, rs_ptr, rs_wave, row_to_step, col_to_step;
+    int item_ptr, sitem_ptr, citem_ptr;
+    int mtab;                 // the distinct multipliers of the gather items (doubles)
+    int bytes;                // size of the blob (multiple of 16)
+};
+typedef unsigned short u16;
+
 struct LArgs {
     NArgs n;
-    const int4* ops;          // (l, u, dst, pivot diag) positions into vals
-    const int* op_ptr;        // [nlev * LU_W + 1]
-    const int* piv;           // diag positions
-    const int* piv_ptr;       // [nlev * LU_W + 1]
-    const int* brow;          // elimination steps
-    const int* brow_ptr;      // [nblev * LU_W + 1]
-    const int* u_col;         // column step of every U entry (parallel to u_pos)
-    const int4* items;        // (dev_out row, dst position, mult lo, mult hi)
-    const int* item_ptr;      // [LU_W + 1]
-    int nlev, nblev;
-    // value-only rounds (k_lu<true>): forward substitution with the stored factors
-    const int4* sops;         // (l, rhs source, rhs dst, pivot diag), level-scheduled on the L dependency DAG
-    const int* sop_ptr;       // [nslev * LU_W + 1]
-    const int4* sitems;       // gather items of the residual and charge rows only
-    const int* sitem_ptr;     // [LU_W + 1]
-    int nslev, pad1_;
+    const unsigned char* tab; // the blob in global memory
+    LuTabs t;
+    // full rounds: ops (l, u, dst, pivot diag) positions into vals, [nlev * LU_W + 1] op_ptr / piv_ptr; backward
+    // substitution rows brow by level, [nblev * LU_W + 1] brow_ptr; value-only rounds: sops (l, rhs source, rhs dst,
+    // pivot diag), level-scheduled on the L dependency DAG, [nslev * LU_W + 1] sop_ptr
+    int nlev, nblev, nslev, pad1_;
+    // gather items: x = dev_out row | index into mtab << 20, y = dst position (| second position << 16 for citems);
+    // [LU_W + 1] item_ptr per kind in the blob
+    const int2* items;
+    const int2* sitems;       // gather items of the residual and charge rows only (value-only rounds)
     Lists cur;                // this round's point lists: groups of LU_PTS full-iteration points, then of value-only points
     int* zero_cnt;            // counters of the NEXT round's lists (k_control of this round fills them): zeroed here
     // first-order charge update  q(x + dx) ~ q(x) + C dx:  items (dev_out row of dQ/dV, vals slot of q_row, vals slot of
-    // dx_col, index into cmult), grouped by destination row like the gather items
-    const int4* citems;
-    const int* citem_ptr;     // [LU_W + 1]
-    const double* cmult;
+    // dx_col), grouped by destination row like the gather items
+    const int2* citems;
     double* LUF;              // [nnz_lu][B] factors of the last full round: L (unscaled), U, inverted pivots
     const double* WV;
     double *DX, *QK, *RMAX, *DVMAX;
@@ -650,9 +658,15 @@ struct LArgs {
 };
 
 // One group of LU_PTS points (lane = point) of one kind: SOLVE = value-only iteration with the stored factors.
+// tb = base of the table blob (shared or global memory).
 template <bool SOLVE>
-__device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (*s_red)[LU_W][LU_PTS], int (*s_bad)[LU_PTS],
+__device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const unsigned char* __restrict__ tb,
+                                         unsigned long long (*s_red)[LU_PTS], int* s_bad,
                                          const long long inst, const bool on, const int lane, const int w) {
+#define T16(name) ((const u16*)(tb + c.t.name))
+    // per-point reductions over the workers: max |r|, max |dv| (non-negative, never NaN: fmax drops NaNs -> the bit
+    // patterns order like the values) and the singular / non-finite / growth flags, by shared-memory atomics
+    if (w == 0) { s_red[0][lane] = 0ull; s_red[1][lane] = 0ull; s_bad[lane] = 0; }
     const NArgs& a = c.n;
     const long long B = a.B;
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
@@ -661,59 +675,80 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (
     const double alpha = a.alpha[inst], gshunt = a.dst[(size_t)DS_GSHUNT * B + inst];
     const double* __restrict__ od = a.dev_out + inst;
     const double* __restrict__ X = a.X + inst;
+    const u16* __restrict__ row_to_step = T16(row_to_step);
+    const u16* __restrict__ col_to_step = T16(col_to_step);
+    const u16* __restrict__ rl_ptr = T16(rl_ptr);
+    const u16* __restrict__ rl_lin = T16(rl_lin);
+    const u16* __restrict__ rl_col = T16(rl_col);
+    const double* __restrict__ mtab = (const double*)(tb + c.t.mtab);
     // ---- 1a. linear part (cached / uniform loads only): A = G_lin + alpha C_lin (+ gshunt on node diagonals),
     //          F = -(f_lin + beta) in step order, Q = q_lin in row order
     double* __restrict__ Fv = vals + (size_t)nnz * LU_PTS;
     double* __restrict__ Qv = vals + (size_t)(nnz + N) * LU_PTS;
     if (SOLVE) {
         const double* __restrict__ lf = c.LUF + inst;
-#pragma unroll 4
+#pragma unroll 8
         for (int e = w; e < nnz; e += LU_W) VL(e) = lf[(size_t)e * B];
     } else {
+        const u16* __restrict__ alin = T16(a_lin);
 #if CB_LU_LIN_UNROLL
 #pragma unroll 4
 #endif
         for (int e = w; e < nnz; e += LU_W) {
             double v = 0.0;
-            const int lin = __ldg(a.a_lin + e);
+            const unsigned al = alin[e];
+            const int lin = (int)(al & 0x7fffu) - 1;
             if (lin >= 0) {
                 const size_t li = (size_t)lin * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
                 v = a.lin_g[li] + alpha * a.lin_c[li];
             }
-            if (__ldg(a.a_diag + e)) v += gshunt;
+            if (al & 0x8000u) v += gshunt;
             VL(e) = v;
         }
     }
-    for (int i = w; i < N; i += LU_W) {
-        double f = 0.0, q = 0.0;
-        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
-            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
-            const double xc = X[(size_t)a.rl_col[p] * B];
-            f += a.lin_g[li] * xc;
-            q += a.lin_c[li] * xc;
+    {
+        const u16* __restrict__ rs_ptr = T16(rs_ptr);
+        const u16* __restrict__ rs_wave = T16(rs_wave);
+        for (int i = w; i < N; i += LU_W) {
+            double f = 0.0, q = 0.0;
+            for (int p = rl_ptr[i]; p < rl_ptr[i + 1]; p++) {
+                const size_t li = (size_t)rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+                const double xc = X[(size_t)rl_col[p] * B];
+                f += a.lin_g[li] * xc;
+                q += a.lin_c[li] * xc;
+            }
+            for (int p = rs_ptr[i]; p < rs_ptr[i + 1]; p++) f += a.rs_coef[p] * c.WV[(size_t)rs_wave[p] * B + inst];
+            if (i < NV) f += gshunt * X[(size_t)i * B];
+            Fv[(size_t)row_to_step[i] * LU_PTS] = -(f + a.BETA[(size_t)i * B + inst]);
+            Qv[(size_t)i * LU_PTS] = q;
         }
-        for (int p = a.rs_ptr[i]; p < a.rs_ptr[i + 1]; p++) f += a.rs_coef[p] * c.WV[(size_t)a.rs_wave[p] * B + inst];
-        if (i < NV) f += gshunt * X[(size_t)i * B];
-        Fv[(size_t)a.row_to_step[i] * LU_PTS] = -(f + a.BETA[(size_t)i * B + inst]);
-        Qv[(size_t)i * LU_PTS] = q;
     }
     __syncthreads();
     // ---- 1b. device outputs: one flat stream of (src row, dst, mult) items, LU_GU independent HBM loads in
-    //          flight per warp; all items of one destination are on one warp
+    //          flight per warp (the items of the next batch are fetched while this batch's values are on their way);
+    //          all items of one destination are on one warp
     {
-        const int4* __restrict__ items = SOLVE ? c.sitems : c.items;
-        int q0 = SOLVE ? c.sitem_ptr[w] : c.item_ptr[w];
-        const int q1 = SOLVE ? c.sitem_ptr[w + 1] : c.item_ptr[w + 1];
-        for (; q0 < q1; q0 += LU_GU) {
-            int4 it[LU_GU];
-            double v[LU_GU];
+        const int2* __restrict__ items = SOLVE ? c.sitems : c.items;
+        const u16* __restrict__ iptr = SOLVE ? T16(sitem_ptr) : T16(item_ptr);
+        int q0 = iptr[w];
+        const int q1 = iptr[w + 1];
+        int2 it[LU_GU];
+        if (q0 < q1) {
 #pragma unroll
             for (int u = 0; u < LU_GU; u++) it[u] = __ldg(items + min(q0 + u, q1 - 1));
+        }
+        for (; q0 < q1; q0 += LU_GU) {
+            double v[LU_GU];
+            int2 nx[LU_GU];
 #pragma unroll
-            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
+            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)(it[u].x & 0xfffff) * B);
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) nx[u] = __ldg(items + min(q0 + LU_GU + u, q1 - 1));
 #pragma unroll
             for (int u = 0; u < LU_GU; u++)
-                if (q0 + u < q1) VL(it[u].y) += __hiloint2double(it[u].w, it[u].z) * v[u];
+                if (q0 + u < q1) VL(it[u].y) += mtab[(unsigned)it[u].x >> 20] * v[u];
+#pragma unroll
+            for (int u = 0; u < LU_GU; u++) it[u] = nx[u];
         }
     }
     __syncthreads();
@@ -721,59 +756,67 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (
     double rmax = 0.0;
     for (int i = w; i < N; i += LU_W) {
         const double q = Qv[(size_t)i * LU_PTS];
-        double* bp = Fv + (size_t)a.row_to_step[i] * LU_PTS;
+        double* bp = Fv + (size_t)row_to_step[i] * LU_PTS;
         const double b = *bp - alpha * q;
         *bp = b;
         rmax = fmax(rmax, fabs(b));
     }
-    s_red[0][w][lane] = rmax;
+    atomicMax(&s_red[0][lane], (unsigned long long)__double_as_longlong(rmax));
     int bad = 0;
     __syncthreads();
     // ---- 2. elimination by levels (fused forward substitution) ------------------------------------------
-    const int nlev = SOLVE ? c.nslev : c.nlev;
-    const int4* __restrict__ ops = SOLVE ? c.sops : c.ops;
-    const int* __restrict__ op_ptr = SOLVE ? c.sop_ptr : c.op_ptr;
-    for (int lv = 0; lv < nlev; lv++) {
-        const int slot = lv * LU_W + w;
-        if (!SOLVE) {
-            for (int p = c.piv_ptr[slot]; p < c.piv_ptr[slot + 1]; p++) {
-                const int dp = c.piv[p];
-                const double d = VL(dp);
-                bad |= !(fabs(d) > 0.0);
-                VL(dp) = 1.0 / d;
+    {
+        const int nlev = SOLVE ? c.nslev : c.nlev;
+        const ushort4* __restrict__ ops = (const ushort4*)(tb + (SOLVE ? c.t.sops : c.t.ops));
+        const u16* __restrict__ op_ptr = SOLVE ? T16(sop_ptr) : T16(op_ptr);
+        const u16* __restrict__ piv_ptr = T16(piv_ptr);
+        const u16* __restrict__ piv = T16(piv);
+        for (int lv = 0; lv < nlev; lv++) {
+            const int slot = lv * LU_W + w;
+            if (!SOLVE) {
+                for (int p = piv_ptr[slot]; p < piv_ptr[slot + 1]; p++) {
+                    const int dp = piv[p];
+                    const double d = VL(dp);
+                    bad |= !(fabs(d) > 0.0);
+                    VL(dp) = 1.0 / d;
+                }
+                __syncthreads();
             }
-            __syncthreads();
-        }
-        int q0 = op_ptr[slot];
-        const int q1 = op_ptr[slot + 1];
-        if (q0 < q1) {
-            int4 op = __ldg(ops + q0);
+            int q0 = op_ptr[slot];
+            const int q1 = op_ptr[slot + 1];
             for (; q0 < q1; q0++) {
-                const int4 cur = op;
-                if (q0 + 1 < q1) op = __ldg(ops + q0 + 1);
+                const ushort4 cur = ops[q0];
                 const double l = VL(cur.x) * VL(cur.w);
                 if (!SOLVE) bad |= (fabs(l) > c.growth_max) << 1;   // pivot-growth monitor (BAD bit 1)
                 VL(cur.z) -= l * VL(cur.y);
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     if (!SOLVE && c.LUF) {   // keep the factors for the value-only rounds that follow
         double* __restrict__ lf = c.LUF + inst;
         if (on)
-#pragma unroll 4
+#pragma unroll 8
             for (int e = w; e < nnz; e += LU_W) lf[(size_t)e * B] = VL(e);
     }
     // ---- 3. backward substitution by levels: x_k = (b_k - sum_j u_kj x_j) * inv_k, in place in the rhs slots
-    for (int lv = 0; lv < c.nblev; lv++) {
-        const int slot = lv * LU_W + w;
-        for (int p = c.brow_ptr[slot]; p < c.brow_ptr[slot + 1]; p++) {
-            const int k = c.brow[p];
-            double acc = VL(nnz + k);
-            for (int u = a.u_ptr[k]; u < a.u_ptr[k + 1]; u++) acc -= VL(a.u_pos[u]) * VL(nnz + c.u_col[u]);
-            VL(nnz + k) = acc * VL(a.diag_pos[k]);
+    {
+        const u16* __restrict__ brow_ptr = T16(brow_ptr);
+        const u16* __restrict__ brow = T16(brow);
+        const u16* __restrict__ u_ptr = T16(u_ptr);
+        const u16* __restrict__ u_pos = T16(u_pos);
+        const u16* __restrict__ u_col = T16(u_col);
+        const u16* __restrict__ diag_pos = T16(diag_pos);
+        for (int lv = 0; lv < c.nblev; lv++) {
+            const int slot = lv * LU_W + w;
+            for (int p = brow_ptr[slot]; p < brow_ptr[slot + 1]; p++) {
+                const int k = brow[p];
+                double acc = VL(nnz + k);
+                for (int u = u_ptr[k]; u < u_ptr[k + 1]; u++) acc -= VL(u_pos[u]) * VL(nnz + u_col[u]);
+                VL(nnz + k) = acc * VL(diag_pos[k]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- 3b. charges of the updated iterate to first order: q(x + dx) ~ q(x) + C dx (linear capacitors exactly).
     //          The accepted step keeps these charges, so they must belong to the iterate that is accepted, not to
@@ -782,76 +825,94 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, double (
     //          Only the rate-based acceptance tests need it: the plain test accepts when |dx| is below the Newton
     //          tolerance, where the update is negligible.
     if (a.o.rate_test) {
-    for (int i = w; i < N; i += LU_W) {
-        double dq = 0.0;
-        for (int p = a.rl_ptr[i]; p < a.rl_ptr[i + 1]; p++) {
-            const size_t li = (size_t)a.rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
-            dq += a.lin_c[li] * VL(nnz + a.col_to_step[a.rl_col[p]]);
+        for (int i = w; i < N; i += LU_W) {
+            double dq = 0.0;
+            for (int p = rl_ptr[i]; p < rl_ptr[i + 1]; p++) {
+                const size_t li = (size_t)rl_lin[p] * a.lin_ent_stride + (size_t)inst * a.lin_inst_stride;
+                dq += a.lin_c[li] * VL(nnz + col_to_step[rl_col[p]]);
+            }
+            Qv[(size_t)i * LU_PTS] += dq;
         }
-        Qv[(size_t)i * LU_PTS] += dq;
-    }
-    __syncthreads();
-    {
-        int q0 = c.citem_ptr[w];
-        const int q1 = c.citem_ptr[w + 1];
-        for (; q0 < q1; q0 += LU_GU) {
-            int4 it[LU_GU];
-            double v[LU_GU];
+        __syncthreads();
+        {
+            const u16* __restrict__ iptr = T16(citem_ptr);
+            int q0 = iptr[w];
+            const int q1 = iptr[w + 1];
+            int2 it[LU_GU];
+            if (q0 < q1) {
 #pragma unroll
-            for (int u = 0; u < LU_GU; u++) it[u] = __ldg(c.citems + min(q0 + u, q1 - 1));
+                for (int u = 0; u < LU_GU; u++) it[u] = __ldg(c.citems + min(q0 + u, q1 - 1));
+            }
+            for (; q0 < q1; q0 += LU_GU) {
+                double v[LU_GU];
+                int2 nx[LU_GU];
 #pragma unroll
-            for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)it[u].x * B);
+                for (int u = 0; u < LU_GU; u++) v[u] = __ldg(od + (size_t)(it[u].x & 0xfffff) * B);
 #pragma unroll
-            for (int u = 0; u < LU_GU; u++)
-                if (q0 + u < q1) VL(it[u].y) += __ldg(c.cmult + it[u].w) * v[u] * VL(it[u].z);
+                for (int u = 0; u < LU_GU; u++) nx[u] = __ldg(c.citems + min(q0 + LU_GU + u, q1 - 1));
+#pragma unroll
+                for (int u = 0; u < LU_GU; u++)
+                    if (q0 + u < q1) VL(it[u].y & 0xffff) += mtab[(unsigned)it[u].x >> 20] * v[u] * VL((unsigned)it[u].y >> 16);
+#pragma unroll
+                for (int u = 0; u < LU_GU; u++) it[u] = nx[u];
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
     }
     if (on)
         for (int i = w; i < N; i += LU_W) c.QK[(size_t)i * B + inst] = Qv[(size_t)i * LU_PTS];
     // ---- 4. update vector and norms ---------------------------------------------------------------------
     double dvm = 0.0;
     for (int i = w; i < N; i += LU_W) {
-        const double dx = VL(nnz + a.col_to_step[i]);
+        const double dx = VL(nnz + col_to_step[i]);
         if (on) c.DX[(size_t)i * B + inst] = dx;
         if (i < NV) dvm = fmax(dvm, fabs(dx));
         bad |= !isfinite(dx);
     }
-    s_red[1][w][lane] = dvm;
-    s_bad[w][lane] = bad;
+    atomicMax(&s_red[1][lane], (unsigned long long)__double_as_longlong(dvm));
+    if (bad) atomicOr(&s_bad[lane], bad);
     __syncthreads();
     if (w == 0 && on) {
-        double r = 0.0, d = 0.0;
-        int b = 0;
-#pragma unroll
-        for (int k = 0; k < LU_W; k++) { r = fmax(r, s_red[0][k][lane]); d = fmax(d, s_red[1][k][lane]); b |= s_bad[k][lane]; }
-        c.RMAX[inst] = r; c.DVMAX[inst] = d; c.BAD[inst] = b;
+        c.RMAX[inst] = __longlong_as_double((long long)s_red[0][lane]);
+        c.DVMAX[inst] = __longlong_as_double((long long)s_red[1][lane]);
+        c.BAD[inst] = s_bad[lane];
     }
     __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
 #undef VL
+#undef T16
 }
 
 // A CTA works through groups g = blockIdx.x, blockIdx.x + gridDim.x, ... of this round's lists: first the groups of
 // full-iteration points (assembly + LU + solves, factors stored), then the groups of value-only points (solves with the
 // stored factors).  The lists are dense (device-wide compaction by k_control), so every group but the last of each kind
 // is full whatever fraction of the sweep points takes part in the round.
+// STAGED: the table blob is copied behind the matrices in shared memory (launch with lu_smem + t.bytes dynamic bytes).
+template <bool STAGED>
 __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
-    extern __shared__ double vals_[];
-    __shared__ double s_red[2][LU_W][LU_PTS];
-    __shared__ int s_bad[LU_W][LU_PTS];
+    extern __shared__ __align__(16) double vals_[];
+    __shared__ unsigned long long s_red[2][LU_PTS];
+    __shared__ int s_bad[LU_PTS];
     const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
     if (blockIdx.x == 0 && threadIdx.x < 2) c.zero_cnt[threadIdx.x] = 0;
     const int nf = c.cur.cnt[0], na = c.cur.cnt[1];
     const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS;
+    if ((int)blockIdx.x >= gf + ga) return;
+    const unsigned char* tb = c.tab;
+    if (STAGED) {
+        unsigned char* st = (unsigned char*)(vals_ + (size_t)(c.n.nnz_lu + 2 * c.n.N) * LU_PTS);
+        const int4* __restrict__ src = (const int4*)c.tab;
+        for (int k = threadIdx.x; k < c.t.bytes / 16; k += LU_PTS * LU_W) ((int4*)st)[k] = __ldg(src + k);
+        tb = st;
+        __syncthreads();
+    }
     for (int g = blockIdx.x; g < gf + ga; g += gridDim.x) {
         const bool solve = g >= gf;
         const int g0 = (solve ? g - gf : g) * LU_PTS, n = solve ? na : nf;
         const int* __restrict__ list = solve ? c.cur.any : c.cur.full;
         const bool on = g0 + lane < n;
         const long long inst = list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
-        if (solve) lu_group<true>(c, vals_, s_red, s_bad, inst, on, lane, w);
-        else lu_group<false>(c, vals_, s_red, s_bad, inst, on, lane, w);
+        if (solve) lu_group<true>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
+        else lu_group<false>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
     }
 }
 

@@ -28,6 +28,9 @@ struct VaArgs {
     int temp_col; int gmin_col;
     const int* count;            // number of entries of `list` (a device counter: the grid is sized for all B points and
                                  // CTAs beyond the count exit at once)
+    double* uni;                 // [NUNI] cached values that are the same for every device of the model (they depend on the
+                                 // model card, temperature and gmin only), or [B][NUNI] when temperature / gmin are swept
+    int uni_per_inst; int pad_;
 };
 
 // Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
@@ -194,6 +197,9 @@ VA_FN double va_dlimexp(double x) { return x < 80.0 ? exp(x) : exp(80.0); }
 #define TEMP_K (temp_c_ + 273.15)
 #define GMIN_V gmin_
 #define CACHE_ST(s, v) cache_[VA_SLOT_OFF(s)] = (double)(v)
+// uniform slots: written by device 0 of the model (by its first point only, unless the table is per point)
+#define CACHE_STU(k, v) { if (uni_on_) uni_w_[(k)] = (double)(v); }
+#define CACHE_LDU(k) __ldg(uni_ + (k))
 #define VT(k) vt_[k]
 #define OUT_I(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_Q(k, v) out_[(size_t)(NT + (k)) * a.B] = (v)
@@ -250,6 +256,9 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
         const double temp_c_ = a.temp_col >= 0 ? a.params[(size_t)a.temp_col * a.B + inst] : a.temp_val; \
         const double gmin_ = a.gmin_col >= 0 ? a.params[(size_t)a.gmin_col * a.B + inst] : a.gmin_val;   \
         double* cache_ = (double*)a.cache + va_cache_index<VA_LAYOUT>(a.B, dev, NCACHE_P, inst);              \
+        double* uni_w_ = a.uni + (a.uni_per_inst ? (size_t)inst * NUNI : 0);                      \
+        const bool uni_on_ = dev == 0 && (a.uni_per_inst || inst == 0);                          \
+        (void)uni_w_; (void)uni_on_;                                                             \
         (void)gmin_; (void)temp_c_; (void)par_val_; (void)par_col_; (void)given_;
 #define VA_SETUP_END(NAME) }
 
@@ -355,7 +364,7 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 // inside runs of up to 32 points, so a warp reads a few contiguous row segments; with every point live the launch is as
 // coalesced as the identity mapping.
 #define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
-    extern "C" __device__ int META[4] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS}; \
+    extern "C" __device__ int META[6] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS, NUNI, 0}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
         static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ __align__(16) double va_ring_[];                                       \
@@ -368,6 +377,8 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
         }                                                                                        \
         const int dev = blockIdx.y;                                                              \
         const double* __restrict__ cache_ = a.cache + va_cache_index<VA_LAYOUT>(a.B, dev, NCACHE_P, inst);    \
+        const double* __restrict__ uni_ = a.uni + (a.uni_per_inst ? (size_t)inst * NUNI : 0);    \
+        (void)uni_;                                                                              \
         const double* ring_ = va_ring_ + VA_RING_TID(threadIdx.x);                               \
         const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + VA_RING_TID(threadIdx.x)); \
         _Pragma("unroll") for (int c_ = 0; c_ < VA_AHEAD; c_++) {                                \

@@ -234,8 +234,9 @@ class VAModelShape:
 
 def shape_of(cm) -> VAModelShape:
     """Shape of a va.compiler.CompiledModel without host function addresses (all the engine needs)."""
-    return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
-                        ncache_n=getattr(cm, "ncache_n", 0),
+    # (the counts include the model's uniform slots: rows are over-allocated by them on the GPU, where they live in a table)
+    return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache + getattr(cm, "nuni", 0), list(cm.jrow), list(cm.jcol),
+                        ncache_n=getattr(cm, "ncache_n", 0) + getattr(cm, "nuni_n", 0),
                         noise_pos=[int(s[0]) for s in getattr(cm, "noise_sources", [])],
                         noise_neg=[int(s[1]) for s in getattr(cm, "noise_sources", [])],
                         branch_terms=list(getattr(cm, "branch_terms", [])), linear=bool(getattr(cm, "linear", False)))

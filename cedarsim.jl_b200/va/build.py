@@ -35,6 +35,9 @@ static inline double va_dlimexp(double x) {{ return x < 80.0 ? exp(x) : exp(80.0
 #define TEMP_K (temp_c_ + 273.15)
 #define GMIN_V gmin_
 #define CACHE_ST(s, v) cache_[s] = (double)(v)
+/* uniform slots (the same for every device of the model): on the host they sit behind the stream slots of the row */
+#define CACHE_STU(k, v) cache_[VA_NSTREAM + (k)] = (double)(v)
+#define CACHE_LDU(k) cache_[VA_NSTREAM + (k)]
 #define VA_EVAL_BEGIN(NAME) void NAME##_eval(const double* cache_, const double* v_, double* I_, double* Q_, double* G_, double* C_) {{
 #define VA_EVAL_END(NAME) }}
 #define CACHE_LD(s) cache_[s]
@@ -87,11 +90,12 @@ class HostModel:
     def shape(self):
         from ..flat import VAModelShape
         cm = self.cm
-        return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache, list(cm.jrow), list(cm.jcol),
-                            self.setup_addr, self.eval_addr, ncache_n=cm.ncache_n,
+        # host cache rows = stream slots + uniform slots (CACHE_LDU reads behind the stream)
+        return VAModelShape(cm.name, list(cm.terminals), list(cm.params), cm.ncache + cm.nuni, list(cm.jrow), list(cm.jcol),
+                            self.setup_addr, self.eval_addr, ncache_n=cm.ncache_n + cm.nuni_n,
                             noise_pos=[int(s[0]) for s in cm.noise_sources], noise_neg=[int(s[1]) for s in cm.noise_sources],
                             host_setupn=self.setupn_addr, host_noise=self.noise_addr, branch_terms=list(cm.branch_terms), linear=bool(cm.linear),
-                            ncache_v=cm.ncache_v, host_setupv=self.setupv_addr, host_evalv=self.evalv_addr)
+                            ncache_v=cm.ncache_v + cm.nuni_v, host_setupv=self.setupv_addr, host_evalv=self.evalv_addr)
 
     # convenience for tests
     def run_noise(self, params: dict, v, temp_c=27.0, gmin=1e-12):
@@ -114,7 +118,7 @@ class HostModel:
         for k, v in params.items():
             par[lut[k.lower()]] = v
             given[lut[k.lower()]] = 1
-        cache = np.zeros(max(1, cm.ncache_n if noise else cm.ncache))
+        cache = np.zeros(max(1, (cm.ncache_n + cm.nuni_n) if noise else (cm.ncache + cm.nuni)))
         (self.setupn if noise else self.setup)(par.ctypes.data_as(C.POINTER(C.c_double)), given.ctypes.data_as(C.POINTER(C.c_uint8)),
                    C.c_double(temp_c), C.c_double(gmin), cache.ctypes.data_as(C.POINTER(C.c_double)))
         return cache

@@ -35,10 +35,11 @@ from .preproc import Preprocessor
 
 
 # cache streaming (see _Compiler._stage_cache): rows per ring chunk and residency window, in stream positions
-GEN_VERSION = 6   # bump when the emitted code changes: models cached under _gen/ are regenerated
+GEN_VERSION = 7   # bump when the emitted code changes: models cached under _gen/ are regenerated
 # experiment knobs (a non-default value needs its own CB_GEN_DIR: cached models are looked up by name)
 CACHE_CHUNK_ROWS = int(os.environ.get("CB_CACHE_ROWS", "4"))
 CACHE_WINDOW = int(os.environ.get("CB_CACHE_WINDOW", "8"))
+UNIFORM_SLOTS = os.environ.get("CB_UNIFORM_SLOTS", "1") != "0"
 FOLD_CONST_DIV = os.environ.get("CB_FOLD_CONST_DIV", "1") != "0"
 
 
@@ -383,6 +384,11 @@ class CompiledModel:
     linear: bool = False   # every Jacobian entry is independent of the terminal values (no Newton step limiting needed)
     gen_version: int = 0   # GEN_VERSION of the generator that wrote `source` (cached models of another version are rebuilt)
     codegen_seconds: float = 0.0   # wall time of parsing + code generation of all variants (bench.py reports it as compile latency)
+    # cached values that do not depend on any instance parameter (only on the model card, temperature, gmin): one small
+    # table per model instead of a slot in every instance's cache row (CACHE_LDU / CACHE_STU); per variant
+    nuni: int = 0
+    nuni_v: int = 0
+    nuni_n: int = 0
 
     @property
     def key(self) -> str:
@@ -1866,7 +1872,7 @@ class _Compiler:
                 pass
         return CompiledModel(self.name, mod.name, list(self.terms), len(mod.ports), [p.name for p in mod.params],
                              ptypes, self.nslot, jrow, jcol, src, len(self.E), len(self.S), dict(self.census),
-                             param_defaults=defaults, branch_terms=list(self.branch_terms), linear=linear)
+                             param_defaults=defaults, branch_terms=list(self.branch_terms), linear=linear, nuni=self.nuni)
 
     def _jacobian_is_static(self, out_lines: List[str]) -> bool:
         """True when no derivative output depends on a terminal value: taint every eval-stream name assigned from an
@@ -1923,6 +1929,9 @@ class _Compiler:
         sequence of copy groups is the same on every control path.
         """
         E, R, W = self.E, CACHE_CHUNK_ROWS, CACHE_WINDOW
+        self.nuni = 0
+        if UNIFORM_SLOTS:
+            self._split_uniform_slots()
         ld = re.compile(r"CACHE_LD\((\d+)\)")
         blocks, depth, start = [], 0, 0
         for i, l in enumerate(E):
@@ -1978,6 +1987,69 @@ class _Compiler:
         self.S[:] = S2
         self.nslot = len(stream)
         self.nchunk = (len(stream) + R - 1) // R
+
+    def _split_uniform_slots(self):
+        """Cache slots whose value does not depend on an instance parameter (PAR / GIVEN reads) -- only on the folded model
+        card, the temperature and gmin -- are the same for every device of the model: they move from the per-instance
+        cache rows (HBM, streamed by every evaluation) to one small table per model (CACHE_STU / CACHE_LDU).  BSIM-CMG on
+        an ASAP7 card with L and NFIN as instance parameters: 84 of 256 stream positions.
+        One forward taint pass over the setup stream; a name once tainted stays tainted (conservative), a store inside a
+        conditional whose condition is tainted is tainted."""
+        ident = re.compile(r"[A-Za-z_][A-Za-z0-9_]*")
+        st = re.compile(r"CACHE_ST\((\d+), (.*)\);\s*$")
+        asg = re.compile(r"^\s*(?:const\s+)?(?:double|int)?\s*([A-Za-z_][A-Za-z0-9_]*)\s*(?:=|\+=|-=|\*=|/=)\s*(.*);\s*$")
+        ctl = re.compile(r"^\s*(?:\}\s*else\s+)?(?:if|while|for)\s*\((.*)\)\s*\{\s*$")
+        tainted: Set[str] = set()
+        stack: List[bool] = []
+        dep: Dict[int, bool] = {}
+
+        def is_t(text: str) -> bool:
+            return "PAR(" in text or "GIVEN(" in text or any(n in tainted for n in ident.findall(text))
+
+        for l in self.S:
+            m = ctl.match(l)
+            if m:
+                t = is_t(m.group(1))
+                if l.lstrip().startswith("}"):
+                    if stack:
+                        stack[-1] = stack[-1] or t
+                else:
+                    stack.append(t)
+                continue
+            ls = l.strip()
+            if ls.startswith("} else"):
+                continue
+            if ls == "}":
+                if stack:
+                    stack.pop()
+                continue
+            if ls == "{":
+                stack.append(False)
+                continue
+            m = st.search(l)
+            if m:
+                k = int(m.group(1))
+                dep[k] = dep.get(k, False) or any(stack) or is_t(m.group(2))
+                continue
+            t = any(stack) or is_t(l)
+            m = asg.match(l)
+            if m and t:
+                tainted.add(m.group(1))
+            if t:
+                for out in re.findall(r"&\s*([A-Za-z_][A-Za-z0-9_]*)", l):   # output arguments of analog functions
+                    tainted.add(out)
+            elif not m and "(" in l and "=" not in l:
+                pass
+        used = set(int(k) for l in self.E for k in re.findall(r"CACHE_LD\((\d+)\)", l))
+        uni = sorted(k for k in used if k in dep and not dep[k])
+        if not uni:
+            return
+        umap = {k: i for i, k in enumerate(uni)}
+        self.nuni = len(uni)
+        ld = re.compile(r"CACHE_LD\((\d+)\)")
+        self.E[:] = [ld.sub(lambda m: f"CACHE_LDU({umap[int(m.group(1))]})" if int(m.group(1)) in umap else m.group(0), l) for l in self.E]
+        sst = re.compile(r"CACHE_ST\((\d+), ")
+        self.S[:] = [sst.sub(lambda m: f"CACHE_STU({umap[int(m.group(1))]}, " if int(m.group(1)) in umap else m.group(0), l) for l in self.S]
 
     def _pick_drop_seed(self, body) -> Optional[int]:
         """Translational invariance: when every probe is a difference V(a,b) of two terminals, every
@@ -2084,6 +2156,7 @@ class _Compiler:
         L.append(f"// terminals: {', '.join(self.terms)}   cache slots: {self.nslot}")
         L.append("#undef VA_CHUNK_ROWS\n#undef VA_WINDOW\n#undef VA_NCHUNK")
         L.append(f"#define VA_CHUNK_ROWS {CACHE_CHUNK_ROWS}\n#define VA_WINDOW {CACHE_WINDOW}\n#define VA_NCHUNK {self.nchunk}")
+        L.append(f"#undef VA_NSTREAM\n#undef NUNI\n#define VA_NSTREAM {self.nslot}\n#define NUNI {max(1, self.nuni)}")
         # helper functions used by setup (emit in dependency-safe order: iterate to closure)
         done: Dict[str, str] = {}
         pending = set(self.used_funcs)
@@ -2128,14 +2201,14 @@ def compile_module(mod: Module, name: Optional[str] = None, const_params=None, r
         vc = _Compiler(mod, name or mod.name, const_params, runtime_params, no_deriv=True, skip_funcs=full.defined_funcs,
                        probe_branches=probe_branches)
         cv = vc.compile()
-        cm.source_v, cm.ncache_v = cv.source, cv.ncache
+        cm.source_v, cm.ncache_v, cm.nuni_v = cv.source, cv.ncache, cv.nuni
     except VACompileError:
         pass
     if _module_has_noise(mod):
         nc = _Compiler(mod, name or mod.name, const_params, runtime_params, noise=True, skip_funcs=full.defined_funcs,
                        probe_branches=probe_branches)
         cn = nc.compile()
-        cm.source_n, cm.ncache_n, cm.noise_sources = cn.source, cn.ncache, list(nc.noise_sources)
+        cm.source_n, cm.ncache_n, cm.noise_sources, cm.nuni_n = cn.source, cn.ncache, list(nc.noise_sources), cn.nuni
     cm.gen_version = GEN_VERSION
     return cm
 
