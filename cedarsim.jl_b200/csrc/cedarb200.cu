@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#define CB_NBUF 3   // rotating buffers of the per-round point lists (solve())
 #include "symbolic.hpp"
 #include "va_prelude.h"
 
@@ -1296,8 +1297,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 p->lu_staged = p->lu_smem + blob.size() + lu_static <= (size_t)max_smem && !std::getenv("CB_LU_NOSTAGE");
                 if (p->lu_staged) p->lu_smem += blob.size();
                 if (std::getenv("CB_DEBUG")) std::fprintf(stderr, "k_lu tables: %zu bytes, staged=%d\n", blob.size(), (int)p->lu_staged);
-                if (p->lu_staged) CUDA_TRY(cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-                else CUDA_TRY(cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                if (p->lu_staged) {
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                } else {
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                }
             }
             la.LUF = nullptr;
         }
@@ -1308,8 +1314,8 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
         TRY(p->alloc(&p->d_BAD, (size_t)B));
         TRY(p->alloc(&p->d_WV, (size_t)std::max(1, a.nwaves) * B));
         TRY(p->alloc(&p->d_dc_count, 1));
-        TRY(p->alloc(&p->d_lists, (size_t)4 * B));
-        TRY(p->alloc(&p->d_cnt, 4));
+        TRY(p->alloc(&p->d_lists, (size_t)CB_NBUF * 3 * B));   // rotating buffers of [full | value-only | idle] point lists
+        TRY(p->alloc(&p->d_cnt, CB_NBUF * 4));
         {
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
@@ -1388,8 +1394,8 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     VaArgsH* a = (VaArgsH*)out_args;
     const cb_circuit* c = p->c;
     a->B = p->B; a->x = p->na.X; a->alpha = p->na.alpha;
-    a->list = p->d_lists + ((size_t)parity * 2 + (value_only ? 1 : 0)) * p->B;
-    a->count = p->d_cnt + parity * 2 + (value_only ? 1 : 0);
+    a->list = p->d_lists + ((size_t)parity * 3 + (value_only ? 1 : 0)) * p->B;   // parity = list buffer of the round
+    a->count = p->d_cnt + parity * 4 + (value_only ? 1 : 0);
     a->cache = value_only ? p->d_cachev + (size_t)p->cachev_off[m] * p->Bpad : p->d_cache + (size_t)c->cache_off[m] * p->Bpad;
     a->out = p->d_dev_out + (size_t)c->out_off[m] * p->B;
     a->term = p->d_term[m]; a->params = p->d_params; a->par_val = p->d_par_val[m]; a->par_col = p->d_par_col[m];
@@ -1400,9 +1406,14 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     a->uni_per_inst = (opt->temp.col >= 0 || opt->gmin.col >= 0) ? 1 : 0; a->pad_ = 0;
 }
 
-static inline void launch_lu(cb_plan* p, unsigned grid, cudaStream_t st, const LArgs& la) {
-    if (p->lu_staged) k_lu<true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
-    else k_lu<false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+static inline void launch_lu(cb_plan* p, unsigned grid, cudaStream_t st, const LArgs& la, bool fused = false) {
+    if (p->lu_staged) {
+        if (fused) k_lu<true, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else k_lu<true, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+    } else {
+        if (fused) k_lu<false, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else k_lu<false, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+    }
 }
 
 static int run_setup(cb_plan* p, const cb_options* opt) {
@@ -1558,7 +1569,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     int rc = run_setup(p, opt);
     if (rc != CB_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(p->d_done, 0, sizeof(int), p->stream));
-    CUDA_TRY(cudaMemsetAsync(p->d_cnt, 0, 4 * sizeof(int), p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_cnt, 0, CB_NBUF * 4 * sizeof(int), p->stream));
     k_init_state<<<(unsigned)((B + 127) / 128), 128, 0, p->stream>>>(B, a.N, a.ist, a.dst, a.alpha, a.active, a.X, a.XN, a.BETA,
                                                                           p->have_x0 ? p->d_x0 : nullptr, p->x0_stride, o,
                                                                           p->d_lists, p->d_cnt);
@@ -1606,26 +1617,36 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     if (const char* e = std::getenv("CB_MIXED")) mixed = use_v && std::atoi(e) != 0;
     // per-parity argument blocks
     struct VaArgBuf { char b[256]; };
-    std::vector<VaArgBuf> vargs_store[2], vargs_v_store[2];   // per round parity, one argument block per device model
-    for (int par = 0; par < 2; par++) { vargs_store[par].resize(c->models.size()); vargs_v_store[par].resize(c->models.size()); }
+    std::vector<VaArgBuf> vargs_store[CB_NBUF], vargs_v_store[CB_NBUF];   // per list buffer, one argument block per device model
+    for (int par = 0; par < CB_NBUF; par++) { vargs_store[par].resize(c->models.size()); vargs_v_store[par].resize(c->models.size()); }
     auto vargs = [&](int par, size_t m) { return (void*)vargs_store[par][m].b; };
     auto vargs_v = [&](int par, size_t m) { return (void*)vargs_v_store[par][m].b; };
-    CArgs cargs[2];
-    LArgs largs[2];
-    for (int par = 0; par < 2; par++) {
+    // The control step as the tail of k_lu (kernels.cuh, k_lu<.., true>) instead of a k_control launch per round
+    // (off by default: measured 2.7x SLOWER, profiles/probe_r2o.log -- see DESIGN.md section 4; CB_FUSE=1 selects it)
+    bool fused = false;
+    if (const char* e = std::getenv("CB_FUSE")) fused = p->lu && std::atoi(e) != 0;
+    // Round r reads list buffer r % 3 and fills buffer (r + 1) % 3; its k_lu zeroes the counters of the buffer that is
+    // filled next: (r + 1) % 3 when k_control fills it after k_lu, (r + 2) % 3 when k_lu fills (r + 1) % 3 itself.
+    CArgs cargs[CB_NBUF];
+    LArgs largs[CB_NBUF];
+    for (int par = 0; par < CB_NBUF; par++) {
         for (size_t m = 0; m < c->models.size(); m++) {
             fill_va_args(p, m, opt, vargs(par, m), false, par);
             if (use_v) fill_va_args(p, m, opt, vargs_v(par, m), true, par);
         }
-        int* lists_next = p->d_lists + (size_t)(1 - par) * 2 * B;
-        cargs[par] = CArgs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD, p->d_WV, mixed, 0, p->d_dc_count, v_rounds + 1, 0,
-                           lists_next, lists_next + B, p->d_cnt + (1 - par) * 2};
+        const int nxt = (par + 1) % CB_NBUF, nxt2 = (par + 2) % CB_NBUF;
+        int* lists_next = p->d_lists + (size_t)nxt * 3 * B;
+        cargs[par] = CArgs{a, p->d_DX, p->d_QK, p->d_RMAX, p->d_DVMAX, p->d_BAD,
+                           CtlArgs{p->d_WV, mixed, 0, p->d_dc_count, v_rounds + 1, 0, lists_next, lists_next + B, lists_next + 2 * B,
+                                   p->d_cnt + nxt * 4}};
         largs[par] = p->la;
         largs[par].n = a; largs[par].WV = p->d_WV; largs[par].DX = p->d_DX; largs[par].QK = p->d_QK; largs[par].RMAX = p->d_RMAX;
         largs[par].DVMAX = p->d_DVMAX; largs[par].BAD = p->d_BAD;
         largs[par].LUF = use_v ? p->la.LUF : nullptr;
-        largs[par].cur = Lists{p->d_lists + (size_t)par * 2 * B, p->d_lists + (size_t)par * 2 * B + B, p->d_cnt + par * 2};
-        largs[par].zero_cnt = p->d_cnt + (1 - par) * 2;
+        largs[par].cur = Lists{p->d_lists + (size_t)par * 3 * B, p->d_lists + (size_t)par * 3 * B + B, p->d_lists + (size_t)par * 3 * B + 2 * B,
+                               p->d_cnt + par * 4};
+        largs[par].zero_cnt = p->d_cnt + (fused ? nxt2 : nxt) * 4;
+        largs[par].k = cargs[par].k;
         largs[par].growth_max = opt->pivot_growth_max > 0.0 ? opt->pivot_growth_max : 1e300;
     }
     int n_live_models = 0;
@@ -1664,17 +1685,23 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             }
         }
         if (ev) cudaEventRecord(ev[2], p->stream);
-        if (p->lu) launch_lu(p, lu_grid, p->stream, largs[par]);
-        else {
+        if (p->lu) {
+            LArgs la = largs[par];
+            la.k.next_vround = next_v;
+            launch_lu(p, lu_grid, p->stream, la, fused);
+        } else {
             void* sargs_ptr[] = {&sargs};
-            CUDA_TRY(cudaMemsetAsync(p->d_cnt + (1 - par) * 2, 0, 2 * sizeof(int), p->stream));
+            CUDA_TRY(cudaMemsetAsync(p->d_cnt + ((par + 1) % CB_NBUF) * 4, 0, 4 * sizeof(int), p->stream));
             CUDA_TRY(cudaLaunchKernel((const void*)p->k_solve, dim3((unsigned)((B + 63) / 64)), dim3(64), sargs_ptr, 0, p->stream));
         }
-        CArgs ca = cargs[par];
-        ca.next_vround = next_v;
-        if (ctrl_lanes == 32) k_control<32><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 32, 0, p->stream>>>(ca);
-        else k_control<8><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 8, 0, p->stream>>>(ca);
-        launches += 2;
+        launches++;
+        if (!fused) {
+            CArgs ca = cargs[par];
+            ca.k.next_vround = next_v;
+            if (ctrl_lanes == 32) k_control<32><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 32, 0, p->stream>>>(ca);
+            else k_control<8><<<(unsigned)((B + CTRL_PTS - 1) / CTRL_PTS), CTRL_PTS * 8, 0, p->stream>>>(ca);
+            launches++;
+        }
         if (ev) cudaEventRecord(ev[3], p->stream);
         return CB_OK;
     };
@@ -1683,7 +1710,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
 
     const bool use_graph = !timing && !(std::getenv("CB_NOGRAPH") && std::atoi(std::getenv("CB_NOGRAPH")) != 0);
     int window = std::getenv("CB_POLL") ? std::max(2, std::atoi(std::getenv("CB_POLL"))) : 24;
-    window = ((window + 2 * (v_rounds + 1) - 1) / (2 * (v_rounds + 1))) * (2 * (v_rounds + 1));   // whole cycles, even parity
+    window = ((window + CB_NBUF * (v_rounds + 1) - 1) / (CB_NBUF * (v_rounds + 1))) * (CB_NBUF * (v_rounds + 1));   // whole cycles of the schedule and of the list buffers
     bool done = false;
     int par = 0;
     if (use_graph) {
@@ -1696,7 +1723,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
             int rcl = CB_OK;
             for (int r = 0; r < window && rcl == CB_OK; r++) {
                 const bool v = !dc_pattern && is_vround(r), nv = !dc_pattern && is_vround(r + 1);
-                rcl = launch_round(r & 1, mixed || !v, mixed ? use_v : v, nv, nullptr);
+                rcl = launch_round(r % CB_NBUF, mixed || !v, mixed ? use_v : v, nv, nullptr);
             }
             cudaError_t e = cudaStreamEndCapture(p->stream, &g);
             if (rcl != CB_OK) { if (g) cudaGraphDestroy(g); return rcl; }
@@ -1757,7 +1784,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
                 if (timing) for (auto& e : ev) { cudaEventCreate(&e); evs.push_back(e); }
                 rc = launch_round(par, mixed || !v, mixed ? use_v : v, nv, timing ? ev : nullptr);
                 if (rc != CB_OK) return rc;
-                par ^= 1;
+                par = (par + 1) % CB_NBUF;
                 rounds++;
                 vrounds += (mixed || v) ? 1 : 0;
                 if (!dc_phase) since_tran++;
@@ -1888,8 +1915,8 @@ static int sens_dc1(cb_plan* p, const cb_options* opt, int64_t n_dir, const doub
     const unsigned gB = (unsigned)((B + 127) / 128);
     LArgs la = p->la;
     la.WV = p->d_WV; la.DX = p->d_DX; la.QK = p->d_QK; la.RMAX = p->d_RMAX; la.DVMAX = p->d_DVMAX; la.BAD = p->d_BAD;
-    la.cur = Lists{p->d_lists, p->d_lists + B, p->d_cnt};
-    la.zero_cnt = p->d_cnt + 2;
+    la.cur = Lists{p->d_lists, p->d_lists + B, p->d_lists + 2 * B, p->d_cnt};
+    la.zero_cnt = p->d_cnt + 4;
     la.growth_max = 1e300;
     a.o.rate_test = 0;
     const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);

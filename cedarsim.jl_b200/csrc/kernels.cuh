@@ -36,8 +36,9 @@ enum { DS_T = 0, DS_TNEW, DS_H, DS_H1, DS_H2, DS_HPROP, DS_GSHUNT, DS_LIM, DS_NR
 // iteration (fresh Jacobian: DC iterations, first iteration of a step attempt, every vcycle-th iteration), 3 = idle:
 // waits for the next full round (lock-step schedule only; in mixed rounds nobody idles)
 enum { ACT_DONE = 0, ACT_ANY = 1, ACT_FULL = 2, ACT_IDLE = 3 };
-// compacted point lists of one round: counters cnt[0] = full, cnt[1] = value-only
-struct Lists { const int* full; const int* any; const int* cnt; };
+// compacted point lists of one round: counters cnt[0] = full, cnt[1] = value-only, cnt[2] = idle (the idle list exists
+// only when the control step is fused into k_lu, which visits the points of its lists instead of scanning all B)
+struct Lists { const int* full; const int* any; const int* idle; const int* cnt; };
 
 struct Pref { double value; int col; int pad; };
 
@@ -183,22 +184,42 @@ __device__ __forceinline__ double poly_at(int nh, double tt, double tn, double x
 // strongest nonlinearity a semiconductor device has, exp(v / Vt): e_1 ~ e_0^2 / (2 Vt)).  Both rely on the charges
 // handed over by k_lu being those of the updated iterate, q(x) + C dx.  The DC operating
 // point keeps the plain test n_k <= 1 together with the residual tolerance of CedarDCOp.
-struct CArgs {
-    NArgs n;
-    const double *DX, *QK, *RMAX, *DVMAX;
-    const int* BAD;
+struct CtlArgs {
     double* WV;  // [nwaves][B] source values for the next evaluation
     int mixed;   // 1 = mixed rounds: the kind of a point's next iteration follows its own iteration count (full, then
                  // vcycle - 1 value-only, full, ...); 0 = lock-step rounds: the host's schedule decides (next_vround)
     int next_vround;  // lock-step: the next round is value-only (points that need a fresh Jacobian idle through it)
     int* dc_count;  // number of points still in the DC phase (lock-step: the host schedules full rounds only while > 0)
     int vcycle, pad_;
-    int *next_full, *next_any, *next_cnt;   // lists of the NEXT round, built here (counters zeroed by this round's k_lu)
+    int *next_full, *next_any, *next_idle, *next_cnt;   // lists of the NEXT round, built here (counters zeroed by an earlier k_lu)
+};
+struct CArgs {
+    NArgs n;
+    const double *DX, *QK, *RMAX, *DVMAX;
+    const int* BAD;
+    CtlArgs k;
 };
 
 __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long long inst, bool dcop, double t) {
     for (int w = 0; w < a.nwaves; w++) WV[(size_t)w * a.B + inst] = wave_value(a.waves[w], t, dcop, a.params, a.B, inst);
 }
+
+#ifndef LU_PTS
+#define LU_PTS 32     // points per group (lane = point); 16: two entry-workers per warp, half the shared memory per CTA
+#endif
+#ifndef LU_W
+#define LU_W 16       // entry-workers per CTA
+#endif
+#ifndef LU_MINB
+#define LU_MINB 1
+#endif
+#ifndef CB_LU_LIN_UNROLL
+#define CB_LU_LIN_UNROLL 1
+#endif
+#ifndef LU_GU
+#define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
+#endif
+typedef unsigned short u16;
 
 // Mapping: a CTA owns CTRL_PTS consecutive points; warp l of the CTA ("lane l" of each point) owns the
 // unknowns i = l, l + CTRL_LANES, ...  Every warp access is one contiguous row segment of 32 points.  The
@@ -211,31 +232,39 @@ __device__ __forceinline__ void store_waves(const NArgs& a, double* WV, long lon
 #endif
 // Lanes per point: 8 for large batches (256-thread CTAs, 4 per SM: a 16 384-point launch is one wave); 32 for small ones, where the
 // launch is a fraction of a wave and only its latency counts (3 instead of 11 unknowns per thread in the two passes).
-template <int CTRL_LANES>
-__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1) k_control(const CArgs c) {
+// The control step of CTRL_PTS points: thread (pt, lane) = lane `lane` of CTRL_LANES of point `pt`; every thread of the CTA
+// must call it (CTA-wide barriers).  Two callers:
+//   k_control (FUSED = false): CTA = CTRL_PTS consecutive points, the solver's results come from global memory
+//     (DX, QK rows; RMAX, DVMAX, BAD), every point of the batch is visited, idle ones included;
+//   k_lu<.., true> (FUSED = true): CTA = one group of list entries straight after their solve, the update vector and the
+//     charges are still in the group's shared memory (sv = vals + pt: dx of unknown i at sv[(nnz + cts[i]) * LU_PTS], charge
+//     of row i at sv[(nnz + N + i) * LU_PTS]); idle points are visited through the idle list, which this step also builds.
+// act = role of the point in THIS round (ACT_*), inb = the thread has a point.  s_red: two rows of CTRL_PTS slots, zeroed
+// by the caller behind a barrier (Newton norm and LTE estimate: non-negative doubles, reduced over the lanes by atomicMax
+// on their bit patterns).
+template <int CTRL_LANES, bool FUSED>
+__device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c, const long long inst, const bool inb, const int act,
+                                               const int pt, const int lane, unsigned long long (*s_red)[CTRL_PTS],
+                                               const double* DXg, const double* QKg, const double rmax_in, const double dvmax_in,
+                                               const int bad_in, const double* sv, const u16* cts, const int nnz) {
     static_assert(CTRL_PTS == 32, "lane 0 of the points of a CTA must be exactly one warp (list compaction by ballot)");
-    __shared__ double s_err[CTRL_LANES][CTRL_PTS];
-    __shared__ double s_nrm[CTRL_LANES][CTRL_PTS];
-    const NArgs& a = c.n;
     const long long B = a.B;
-    const int pt = threadIdx.x % CTRL_PTS, lane = threadIdx.x / CTRL_PTS;
-    const long long inst = (long long)blockIdx.x * CTRL_PTS + pt;
-    const bool inb = inst < B;
-    const int act = inb ? a.active[inst] : ACT_DONE;
     const bool live = act == ACT_ANY || act == ACT_FULL;   // took part in this round
     const bool pv = act == ACT_ANY;                         // ... with a value-only iteration
-    int phase = live ? a.ist[(size_t)IS_PHASE * B + inst] : PH_DONE;
     const int N = a.N, NV = a.NV;
     const Opts& o = a.o;
     const long long ii = inb ? inst : 0;   // dead threads keep in-bounds addresses, never dereferenced
+    int phase = live ? a.ist[(size_t)IS_PHASE * B + ii] : PH_DONE;
     double* __restrict__ X = a.X + ii;   double* __restrict__ XN = a.XN + ii; double* __restrict__ X1 = a.X1 + ii;
     double* __restrict__ X2 = a.X2 + ii; double* __restrict__ XP = a.XP + ii; double* __restrict__ QN = a.QN + ii;
     double* __restrict__ Q1 = a.Q1 + ii; double* __restrict__ QD = a.QD + ii; double* __restrict__ BETA = a.BETA + ii;
-    const double* __restrict__ DX = c.DX + ii; const double* __restrict__ QK = c.QK + ii;
+    const double* __restrict__ DX = FUSED ? nullptr : DXg + ii; const double* __restrict__ QK = FUSED ? nullptr : QKg + ii;
     const unsigned char* __restrict__ mask = a.lte_mask;
 #define IST(k) a.ist[(size_t)(k) * B + ii]
 #define DST(k) a.dst[(size_t)(k) * B + ii]
 #define V(arr, i) arr[(size_t)(i) * B]
+#define DXV(i) (FUSED ? sv[(size_t)(nnz + cts[i]) * LU_PTS] : V(DX, i))
+#define QKV(i) (FUSED ? sv[(size_t)(nnz + N + (i)) * LU_PTS] : V(QK, i))
     int it = 0, stage = 0, nh = 0, bpi = 0, kstep = 0, status = 0, hit_bp = 0, method = 0, np = 0, sidx = 0, nnewton = 0,
         nacc = 0, nrej = 0, retry = 0;
     double t = 0, tnew = 0, h = 0, h1 = 0, h2 = 0, hprop = 0, gshunt = 0, lim = 0, alpha = 0, rmax = 0, dvmax = 0, nrm_prev = 0, kappa = 0;
@@ -246,7 +275,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
         sidx = IST(IS_SIDX); nnewton = IST(IS_NNEWTON); nacc = IST(IS_NACC); nrej = IST(IS_NREJ); retry = IST(IS_RETRY);
         t = DST(DS_T); tnew = DST(DS_TNEW); h = DST(DS_H); h1 = DST(DS_H1); h2 = DST(DS_H2);
         hprop = DST(DS_HPROP); gshunt = DST(DS_GSHUNT); lim = DST(DS_LIM); nrm_prev = DST(DS_NRM); kappa = DST(DS_KAPPA);
-        alpha = a.alpha[ii]; rmax = c.RMAX[ii]; dvmax = c.DVMAX[ii]; badpt = c.BAD[ii];
+        alpha = a.alpha[ii]; rmax = rmax_in; dvmax = dvmax_in; badpt = bad_in;
     }
     const double alpha_old = alpha;
     bool finish = false, begin = false, newton_ok = false, newton_fail = false;
@@ -278,7 +307,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
         if (solving) {
 #pragma unroll 4
             for (int i = lane; i < N; i += CTRL_LANES) {
-                const double dx = sc * V(DX, i);
+                const double dx = sc * DXV(i);
                 const double xo = V(X, i), xn = xo + dx;
                 const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
                 nrm = fmax(nrm, fabs(dx) / (o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol));
@@ -289,13 +318,11 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
                 }
             }
         }
-        s_nrm[lane][pt] = nrm;
-        s_err[lane][pt] = err;
+        if (nrm > 0.0) atomicMax(&s_red[0][pt], (unsigned long long)__double_as_longlong(nrm));
+        if (err > 0.0) atomicMax(&s_red[1][pt], (unsigned long long)__double_as_longlong(err));
     }
     __syncthreads();   // reductions; also publishes the updated X rows to the other lanes of the point
-    double nrm = 0.0, err = 0.0;
-#pragma unroll
-    for (int l = 0; l < CTRL_LANES; l++) { nrm = fmax(nrm, s_nrm[l][pt]); err = fmax(err, s_err[l][pt]); }
+    const double nrm = __longlong_as_double((long long)s_red[0][pt]), err = __longlong_as_double((long long)s_red[1][pt]);
     const int phase_in = phase;
 
     // ---- scalar control, replicated across the lanes of a point ------------------------------------
@@ -499,7 +526,7 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
         for (int i = lane; i < N; i += CTRL_LANES) {
             double x = V(X, i), xn = V(XN, i), x1 = V(X1, i), x2 = V(X2, i), qn = V(QN, i), q1 = V(Q1, i), qd = V(QD, i);
             if (do_accept) {
-                const double qk = V(QK, i);
+                const double qk = QKV(i);
                 qd = alpha_old * qk + V(BETA, i);
                 x2 = x1; x1 = xn; xn = x;
                 q1 = qn; qn = qk;
@@ -507,8 +534,8 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
             } else if (copy_mode == 1) { x = 0.0; xn = 0.0; V(X, i) = x; V(XN, i) = xn; }
             else if (copy_mode == 2) { xn = x; V(XN, i) = xn; }
             else if (copy_mode == 3) { x = xn; V(X, i) = x; }
-            else if (copy_mode == 4) { qn = V(QK, i); qd = 0.0; V(QN, i) = qn; V(QD, i) = qd; }
-            else if (copy_mode == 5) { xn = x; qn = V(QK, i); qd = 0.0; V(XN, i) = xn; V(QN, i) = qn; V(QD, i) = qd; }
+            else if (copy_mode == 4) { qn = QKV(i); qd = 0.0; V(QN, i) = qn; V(QD, i) = qd; }
+            else if (copy_mode == 5) { xn = x; qn = QKV(i); qd = 0.0; V(XN, i) = xn; V(QN, i) = qn; V(QD, i) = qd; }
             if (reinit_begin) V(BETA, i) = a1 * qn;
             if (begin) {
                 double beta = a1 * qn;
@@ -566,21 +593,47 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
         }
         if (inb && (live || act == ACT_IDLE)) a.active[inst] = role;
         const unsigned bf = __ballot_sync(0xffffffffu, role == ACT_FULL), ba = __ballot_sync(0xffffffffu, role == ACT_ANY);
-        int basef = 0, basea = 0;
+        const unsigned bi = FUSED ? __ballot_sync(0xffffffffu, role == ACT_IDLE) : 0u;
+        int basef = 0, basea = 0, basei = 0;
         if (pt == 0) {
             if (bf) basef = atomicAdd(c.next_cnt + 0, __popc(bf));
             if (ba) basea = atomicAdd(c.next_cnt + 1, __popc(ba));
+            if (bi) basei = atomicAdd(c.next_cnt + 2, __popc(bi));
         }
         basef = __shfl_sync(0xffffffffu, basef, 0);
         basea = __shfl_sync(0xffffffffu, basea, 0);
+        if (FUSED) basei = __shfl_sync(0xffffffffu, basei, 0);
         const unsigned below = (1u << pt) - 1u;
         if (role == ACT_FULL) c.next_full[basef + __popc(bf & below)] = (int)inst;
         if (role == ACT_ANY) c.next_any[basea + __popc(ba & below)] = (int)inst;
+        if (FUSED && role == ACT_IDLE) c.next_idle[basei + __popc(bi & below)] = (int)inst;
     }
 #undef IST
 #undef DST
 #undef V
+#undef DXV
+#undef QKV
 }
+
+#ifndef CTRL_MINB
+#define CTRL_MINB 4   // resident CTAs per SM of the 8-lane variant (64 registers per thread)
+#endif
+template <int CTRL_LANES>
+__global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? CTRL_MINB : 1) k_control(const CArgs c) {
+    __shared__ unsigned long long s_red[2][CTRL_PTS];
+    const int pt = threadIdx.x % CTRL_PTS, lane = threadIdx.x / CTRL_PTS;
+    const long long inst = (long long)blockIdx.x * CTRL_PTS + pt;
+    const bool inb = inst < c.n.B;
+    const int act = inb ? c.n.active[inst] : ACT_DONE;
+    if (lane == 0) { s_red[0][pt] = 0ull; s_red[1][pt] = 0ull; }
+    const long long ii = inb ? inst : 0;
+    const bool live = act == ACT_ANY || act == ACT_FULL;
+    const double rmax = live ? c.RMAX[ii] : 0.0, dvmax = live ? c.DVMAX[ii] : 0.0;
+    const int bad = live ? c.BAD[ii] : 0;
+    __syncthreads();
+    control_points<CTRL_LANES, false>(c.n, c.k, inst, inb, act, pt, lane, s_red, c.DX, c.QK, rmax, dvmax, bad, nullptr, nullptr, 0);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // k_lu: assembly + batched static-pivot sparse LU + triangular solves, factors staged in shared memory.
@@ -602,21 +655,6 @@ __global__ void __launch_bounds__(CTRL_PTS * CTRL_LANES, CTRL_LANES <= 8 ? 4 : 1
 // The op lists are warp-uniform int4 streams read through L1; the code is a handful of small loops, so it
 // stays in the instruction cache (the generated straight-line k_solve it replaces was 13.6k SASS
 // instructions and ran at the cold instruction-fetch rate, ~29 cycles per instruction).
-#ifndef LU_PTS
-#define LU_PTS 32     // points per group (lane = point); 16: two entry-workers per warp, half the shared memory per CTA
-#endif
-#ifndef LU_W
-#define LU_W 16       // entry-workers per CTA
-#endif
-#ifndef LU_MINB
-#define LU_MINB 1
-#endif
-#ifndef CB_LU_LIN_UNROLL
-#define CB_LU_LIN_UNROLL 1
-#endif
-#ifndef LU_GU
-#define LU_GU 8      // independent HBM loads in flight per worker in the gather phases
-#endif
 // Index tables of k_lu: every small table (level schedules, pivot / row lists, the U pattern, the linear-part maps) is
 // packed as 16-bit entries into ONE blob (ops as four 16-bit positions = 8 bytes).  When the blob fits behind the matrices
 // of the group (DFF: 207 KB of matrices + ~12 KB of tables of the 227 KB a CTA may have) every CTA copies it into shared
@@ -631,7 +669,6 @@ struct LuTabs {
     int mtab;                 // the distinct multipliers of the gather items (doubles)
     int bytes;                // size of the blob (multiple of 16)
 };
-typedef unsigned short u16;
 
 struct LArgs {
     NArgs n;
@@ -655,11 +692,12 @@ struct LArgs {
     double *DX, *QK, *RMAX, *DVMAX;
     int* BAD;
     double growth_max;        // pivot-growth bound: an elimination multiplier above it flags the point (BAD bit 1)
+    CtlArgs k;                // the control step, when it is fused into this kernel (k_lu<.., true>)
 };
 
 // One group of LU_PTS points (lane = point) of one kind: SOLVE = value-only iteration with the stored factors.
 // tb = base of the table blob (shared or global memory).
-template <bool SOLVE>
+template <bool SOLVE, bool FUSED>
 __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const unsigned char* __restrict__ tb,
                                          unsigned long long (*s_red)[LU_PTS], int* s_bad,
                                          const long long inst, const bool on, const int lane, const int w) {
@@ -859,44 +897,52 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
         }
         __syncthreads();
     }
-    if (on)
+    if (on && !FUSED)
         for (int i = w; i < N; i += LU_W) c.QK[(size_t)i * B + inst] = Qv[(size_t)i * LU_PTS];
     // ---- 4. update vector and norms ---------------------------------------------------------------------
     double dvm = 0.0;
     for (int i = w; i < N; i += LU_W) {
         const double dx = VL(nnz + col_to_step[i]);
-        if (on) c.DX[(size_t)i * B + inst] = dx;
+        if (on && !FUSED) c.DX[(size_t)i * B + inst] = dx;
         if (i < NV) dvm = fmax(dvm, fabs(dx));
         bad |= !isfinite(dx);
     }
     atomicMax(&s_red[1][lane], (unsigned long long)__double_as_longlong(dvm));
     if (bad) atomicOr(&s_bad[lane], bad);
     __syncthreads();
-    if (w == 0 && on) {
-        c.RMAX[inst] = __longlong_as_double((long long)s_red[0][lane]);
-        c.DVMAX[inst] = __longlong_as_double((long long)s_red[1][lane]);
-        c.BAD[inst] = s_bad[lane];
+    if (!FUSED) {
+        if (w == 0 && on) {
+            c.RMAX[inst] = __longlong_as_double((long long)s_red[0][lane]);
+            c.DVMAX[inst] = __longlong_as_double((long long)s_red[1][lane]);
+            c.BAD[inst] = s_bad[lane];
+        }
+        __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
     }
-    __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
 #undef VL
 #undef T16
 }
 
 // A CTA works through groups g = blockIdx.x, blockIdx.x + gridDim.x, ... of this round's lists: first the groups of
 // full-iteration points (assembly + LU + solves, factors stored), then the groups of value-only points (solves with the
-// stored factors).  The lists are dense (device-wide compaction by k_control), so every group but the last of each kind
-// is full whatever fraction of the sweep points takes part in the round.
+// stored factors).  The lists are dense (device-wide compaction by the control step), so every group but the last of each
+// kind is full whatever fraction of the sweep points takes part in the round.
 // STAGED: the table blob is copied behind the matrices in shared memory (launch with lu_smem + t.bytes dynamic bytes).
-template <bool STAGED>
+// FUSED: the control step of the group's points (control_points: Newton update, convergence, step control, output
+//   sampling, next round's lists) runs as the tail of their solve, with the update vector and the charges still in
+//   shared memory -- no k_control launch, no DX / QK / RMAX / DVMAX / BAD round trip through HBM.  Idle points of the
+//   lock-step schedule are visited through a third list.  The counters zeroed here are those of the round after next
+//   (three rotating list buffers), because this kernel itself fills the next round's.
+template <bool STAGED, bool FUSED>
 __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
     extern __shared__ __align__(16) double vals_[];
     __shared__ unsigned long long s_red[2][LU_PTS];
+    __shared__ unsigned long long s_ctl[2][LU_PTS];
     __shared__ int s_bad[LU_PTS];
     const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
-    if (blockIdx.x == 0 && threadIdx.x < 2) c.zero_cnt[threadIdx.x] = 0;
-    const int nf = c.cur.cnt[0], na = c.cur.cnt[1];
-    const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS;
-    if ((int)blockIdx.x >= gf + ga) return;
+    if (blockIdx.x == 0 && threadIdx.x < 3) c.zero_cnt[threadIdx.x] = 0;
+    const int nf = c.cur.cnt[0], na = c.cur.cnt[1], ni = FUSED ? c.cur.cnt[2] : 0;
+    const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS, gi = (ni + LU_PTS - 1) / LU_PTS;
+    if ((int)blockIdx.x >= gf + ga + gi) return;
     const unsigned char* tb = c.tab;
     if (STAGED) {
         unsigned char* st = (unsigned char*)(vals_ + (size_t)(c.n.nnz_lu + 2 * c.n.N) * LU_PTS);
@@ -905,14 +951,25 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
         tb = st;
         __syncthreads();
     }
-    for (int g = blockIdx.x; g < gf + ga; g += gridDim.x) {
-        const bool solve = g >= gf;
-        const int g0 = (solve ? g - gf : g) * LU_PTS, n = solve ? na : nf;
-        const int* __restrict__ list = solve ? c.cur.any : c.cur.full;
+    for (int g = blockIdx.x; g < gf + ga + gi; g += gridDim.x) {
+        const int kind = g < gf ? 0 : (g < gf + ga ? 1 : 2);
+        const int g0 = (kind == 0 ? g : (kind == 1 ? g - gf : g - gf - ga)) * LU_PTS, n = kind == 0 ? nf : (kind == 1 ? na : ni);
+        const int* __restrict__ list = kind == 0 ? c.cur.full : (kind == 1 ? c.cur.any : c.cur.idle);
         const bool on = g0 + lane < n;
         const long long inst = list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
-        if (solve) lu_group<true>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
-        else lu_group<false>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
+        if (FUSED && w == 0) { s_ctl[0][lane] = 0ull; s_ctl[1][lane] = 0ull; }
+        if (kind == 1) lu_group<true, FUSED>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
+        else if (kind == 0) lu_group<false, FUSED>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
+        else if (FUSED) __syncthreads();   // publishes the zeroed reduction slots
+        if (FUSED) {
+            const double rmax = kind < 2 ? __longlong_as_double((long long)s_red[0][lane]) : 0.0;
+            const double dvmax = kind < 2 ? __longlong_as_double((long long)s_red[1][lane]) : 0.0;
+            const int bad = kind < 2 ? s_bad[lane] : 0;
+            const int act = on ? (kind == 0 ? ACT_FULL : (kind == 1 ? ACT_ANY : ACT_IDLE)) : ACT_DONE;
+            control_points<LU_W, true>(c.n, c.k, inst, on, act, lane, w, s_ctl, nullptr, nullptr, rmax, dvmax, bad, vals_ + lane,
+                                       (const u16*)(tb + c.t.col_to_step), c.n.nnz_lu);
+            __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
+        }
     }
 }
 

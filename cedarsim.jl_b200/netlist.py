@@ -676,8 +676,14 @@ class _Flattener:
             shape = build_host(cm).shape()
         else:
             shape = shape_of(cm)
-        if len(nodes) > cm.nports:
-            raise NetlistError(f"{name}: {len(nodes)} nodes for Verilog-A module {cm.module} with {cm.nports} ports")
+        # a module that reads $abstime has a hidden last port for the circuit's time net (va/compiler.py _lower_abstime)
+        timed = cm.nports > 0 and cm.terminals[cm.nports - 1] == _TIME_NET
+        if len(nodes) > cm.nports - (1 if timed else 0):
+            raise NetlistError(f"{name}: {len(nodes)} nodes for Verilog-A module {cm.module} with {cm.nports - (1 if timed else 0)} ports")
+        if timed:
+            if len(nodes) < cm.nports - 1:
+                raise NetlistError(f"{name}: a module that reads $abstime needs all of its {cm.nports - 1} ports connected")
+            nodes = list(nodes) + [self._time_net()]
         lut = {p.lower(): p for p in cm.params}
         over = self.overrides(name + ".", list(lut))
         vals: Dict[str, Num] = {}

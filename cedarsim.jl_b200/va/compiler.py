@@ -2193,8 +2193,55 @@ class _Compiler:
         return "\n".join(L) + "\n"
 
 
+TIME_PORT = "time__"   # hidden port of a module that reads $abstime / $realtime (see _lower_abstime)
+
+
+def _lower_abstime(mod: Module) -> Module:
+    """`$abstime` / `$realtime` inside a module: the device code takes no time argument, so simulation time enters the way
+    it does for behavioural sources (netlist._behavioural) -- as the voltage of a net driven by V(t) = t.  A module that
+    reads the time gets one extra, hidden port TIME_PORT behind its own ports and every `$abstime` becomes the probe
+    V(time__); the netlist flattener connects the port to the circuit's time net (0 V in the DC solve, like `$abstime`
+    there).  Returns `mod` itself when it does not read the time."""
+    import copy
+    hit = [False]
+
+    def walk(x):
+        if isinstance(x, tuple):
+            if len(x) >= 2 and x[0] == "call" and x[1] in ("$abstime", "$realtime"):
+                hit[0] = True
+                return ("probe", "V", [TIME_PORT])
+            return tuple(walk(y) for y in x)
+        if isinstance(x, list):
+            return [walk(y) for y in x]
+        return x
+
+    analog = walk(mod.analog)
+    if not hit[0]:
+        return mod
+    for f in mod.functions.values():
+        probe = [False]
+
+        def has(x):
+            if isinstance(x, tuple) and len(x) >= 2 and x[0] == "call" and x[1] in ("$abstime", "$realtime"):
+                probe[0] = True
+            if isinstance(x, (tuple, list)):
+                for y in x:
+                    has(y)
+        has(f.body)
+        if probe[0]:
+            raise VACompileError(f"$abstime inside analog function {f.name} is not supported")
+    if TIME_PORT in mod.nets:
+        raise VACompileError(f"net name {TIME_PORT} is reserved")
+    m2 = copy.copy(mod)
+    m2.analog = analog
+    m2.ports = list(mod.ports) + [TIME_PORT]
+    m2.nets = list(m2.ports) + [n for n in mod.nets if n not in mod.ports]
+    return m2
+
+
 def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None,
                    probe_branches=()) -> CompiledModel:
+    mod = _lower_abstime(mod)
     full = _Compiler(mod, name or mod.name, const_params, runtime_params, probe_branches=probe_branches)
     cm = full.compile()
     try:

@@ -169,3 +169,21 @@ def test_multimode_source_reinitialised_at_t0_on_gpu():
     assert np.all(np.abs(sols.y - yo) <= 1e-6 * np.abs(yo) + 1e-9)
     sols = tran_(cs, (0.0, 1e-3), saveat=ts, t0_reinit=0, **kw)
     assert np.abs(sols.array("in")[:, 0] - 5.0).max() < 1e-12
+
+
+def test_abstime_inside_verilog_a_module_sweep():
+    """`$abstime` read inside Verilog-A modules (hidden time port, va/compiler.py _lower_abstime) through the sweep API:
+    amplitude sweep of a module sine source and a conductance growing with time, closed forms at every point."""
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = ('* abstime\n.hdl "abstime_src.va"\nxs in 0 va_sine ampl=2 freq=1meg\nr1 in 0 1k\n'
+            'v2 b 0 1\nr2 b c 1k\nxg c 0 va_ramp_g g0=1m tau=1u\n')
+    amp = np.linspace(0.5, 3.0, 48)
+    ts = np.linspace(0.0, 2e-6, 401)
+    cs = CircuitSweep(deck, Sweep("xs.ampl", amp), outputs=["in", "c"], include_dirs=[inc])
+    sols = tran_(cs, (0.0, 2e-6), saveat=ts, reltol=1e-6, dt_max=2e-9)
+    assert sols.status.max() == 0
+    vin = sols.array(cs.sys.node_in)
+    assert np.abs(vin - amp[:, None] * np.sin(2e6 * np.pi * ts)[None, :]).max() < 2e-4
+    g = 1e-3 * (1.0 + ts / 1e-6)
+    assert np.abs(sols.array(cs.sys.node_c) - (1.0 / (1.0 + 1e3 * g))[None, :]).max() < 1e-9

@@ -421,3 +421,23 @@ def test_multimode_source_is_reinitialised_at_t0():   # test/basic.jl:534-552: v
     y, st, _ = orc.tran(fl.fc, 0.0, 0.01, np.array([0.0, 0.01]))
     assert st.max() == 0
     assert abs(y[0, 0, 0] - 10.0) < 1e-9 and abs(y[1, 0, 0] - 5.0) < 1e-6     # algebraic node jumps, capacitor voltage is held
+
+
+def test_abstime_inside_verilog_a_modules():
+    """`$abstime` inside a Verilog-A module (the reference passes the simulation time to every device,
+    src/vasim.jl `$abstime` -> sim time): a module source V = A sin(2 pi f $abstime) and a conductance that grows with
+    time, against their closed forms; 0 at the DC operating point."""
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = ('* abstime\n.hdl "abstime_src.va"\nxs in 0 va_sine ampl=2 freq=1meg\nr1 in 0 1k\n'
+            'v2 b 0 1\nr2 b c 1k\nxg c 0 va_ramp_g g0=1m tau=1u\n')
+    fl = netlist.flatten(netlist.parse_netlist(deck, include_dirs=[inc]), host=True)
+    fc = fl.fc
+    _, xf, st, _ = orc.dc(fc, None)
+    assert st.max() == 0 and abs(xf[fc.unknown("in"), 0]) < 1e-15 and abs(xf[fc.unknown("c"), 0] - 0.5) < 1e-12
+    ts = np.linspace(0.0, 2e-6, 401)
+    y, st, _ = orc.tran(fc, 0.0, 2e-6, ts, opts=orc.default_options(reltol=1e-6, dt_max=2e-9))
+    assert st.max() == 0
+    assert np.abs(y[fc.unknown("in"), :, 0] - 2.0 * np.sin(2e6 * np.pi * ts)).max() < 1e-4
+    g = 1e-3 * (1.0 + ts / 1e-6)
+    assert np.abs(y[fc.unknown("c"), :, 0] - 1.0 / (1.0 + 1e3 * g)).max() < 1e-9      # divider 1k against 1 / g(t): algebraic, exact
