@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 #include <nvrtc.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX: ranges around the phases of a call (tracing)
 #include <unistd.h>
 
 #include <algorithm>
@@ -26,6 +27,11 @@
 #include <vector>
 
 #include "kernels.cuh"
+// RAII NVTX range: the phases of every entry point show up by name in Nsight Systems / Nsight Compute (--nvtx)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 #define CB_NBUF 3   // rotating buffers of the per-round point lists (solve())
 #include "symbolic.hpp"
 #include "va_prelude.h"
@@ -687,6 +693,7 @@ static int nvrtc_compile(cb_circuit* c, const char* cache_dir) {
 }
 
 extern "C" int cb_circuit_compile(cb_circuit* c, const char* cache_dir, double* compile_seconds) {
+    NvtxRange nvtx_("cb:circuit_compile (symbolic analysis, NVRTC)");
     if (!c) return fail(CB_ERR_INVALID, "null circuit");
     auto t0 = std::chrono::steady_clock::now();
     c->lin_contrib.clear();
@@ -1417,6 +1424,7 @@ static inline void launch_lu(cb_plan* p, unsigned grid, cudaStream_t st, const L
 }
 
 static int run_setup(cb_plan* p, const cb_options* opt) {
+    NvtxRange nvtx_("cb:setup (linear stamps, device-model caches)");
     const cb_circuit* c = p->c;
     if (p->setup_valid && std::memcmp(&p->last_temp, &opt->temp, sizeof(cb_pref)) == 0 &&
         std::memcmp(&p->last_gmin, &opt->gmin, sizeof(cb_pref)) == 0)
@@ -1447,6 +1455,7 @@ static int run_setup(cb_plan* p, const cb_options* opt) {
 
 // value-only variants: their own bias-independent cache, filled on first use after a parameter change
 static int run_setupv(cb_plan* p, const cb_options* opt) {
+    NvtxRange nvtx_("cb:setup value-only caches");
     const cb_circuit* c = p->c;
     if (p->setupv_valid) return CB_OK;
     for (size_t m = 0; m < c->models.size(); m++) {
@@ -1491,6 +1500,7 @@ static int collect_breakpoints(const cb_circuit* c, double t0, double t1, std::v
 
 static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, double t1, const double* saveat,
                  int64_t nsave, cb_stats* stats) {
+    NvtxRange nvtx_(dc_only ? "cb:solve dc" : "cb:solve tran");
     cb_circuit* c = p->c;
     if (!p->params_set && c->P > 0) return fail(CB_ERR_STATE, "cb_plan_set_params was not called");
     CUDA_TRY(cudaSetDevice(p->device));
@@ -1661,7 +1671,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     // `next_v`: lock-step schedule of the next round; ev: optional timing events {start, after eval, after evalv, end}
     auto launch_round = [&](int par, bool full_kernels, bool value_kernels, int next_v, cudaEvent_t* ev) -> int {
         if (ev) cudaEventRecord(ev[0], p->stream);
-        const bool fork = p->fork_models && (n_live_models > 1 || (full_kernels && value_kernels)) && !ev;
+        const bool fork = (p->fork_models && (n_live_models > 1 || (full_kernels && value_kernels)) && !ev);
         if (fork) CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
         int slot = 0;
         for (int kind = 0; kind < 2; kind++) {          // 0: full evaluation of the full list, 1: value-only of the other
@@ -1708,6 +1718,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     // lock-step schedule: kind of round r (0-based round index since the transient phase began)
     auto is_vround = [&](int64_t since_tran) { return use_v && !mixed && since_tran % (v_rounds + 1) != 0; };
 
+    NvtxRange nvtx_rounds_("cb:rounds (eval / k_lu / control)");
     const bool use_graph = !timing && !(std::getenv("CB_NOGRAPH") && std::atoi(std::getenv("CB_NOGRAPH")) != 0);
     int window = std::getenv("CB_POLL") ? std::max(2, std::atoi(std::getenv("CB_POLL"))) : 24;
     window = ((window + CB_NBUF * (v_rounds + 1) - 1) / (CB_NBUF * (v_rounds + 1))) * (CB_NBUF * (v_rounds + 1));   // whole cycles of the schedule and of the list buffers
@@ -1860,6 +1871,7 @@ static cudaError_t rows_to_host(void* dst, const void* src, size_t rows, long lo
 }
 
 static int dc1(cb_plan* p, const cb_options* opt, double* x_out, double* x_full, int32_t* status, cb_stats* stats, long long pitch) {
+    NvtxRange nvtx_("cb:dc");
     if (!p || !opt) return fail(CB_ERR_INVALID, "null argument");
     int rc = solve(p, opt, true, 0.0, 1.0, nullptr, 0, stats);
     if (rc != CB_OK) return rc;
@@ -1993,6 +2005,7 @@ static int tran1(cb_plan* p, double t0, double t1, const double* saveat, int64_t
                  double* y_out, int32_t* status, cb_stats* stats, long long pitch) {
     int rc = tran_device1(p, t0, t1, saveat, n_save, opt, nullptr, nullptr, stats);
     if (rc != CB_OK) return rc;
+    NvtxRange nvtx_("cb:tran results to host");
     const double t = now_s();
     const long long B = p->B;
     if (y_out && n_save > 0 && p->na.O > 0)
@@ -2089,6 +2102,7 @@ static int ac_tables(cb_plan* p, bool noise) {
 
 static int small_signal(cb_plan* p, bool noise, const double* freqs, int64_t F, const cb_options* opt, double* out,
                         int32_t* status, cb_stats* stats, long long pitch) {
+    NvtxRange nvtx_(noise ? "cb:noise" : "cb:ac");
     if (!p || !opt || !freqs || F <= 0 || !out) return fail(CB_ERR_INVALID, "null argument");
     for (int64_t k = 0; k < F; k++)
         if (!(freqs[k] > 0.0) || !std::isfinite(freqs[k])) return fail(CB_ERR_INVALID, "frequencies must be positive");

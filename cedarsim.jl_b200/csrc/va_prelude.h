@@ -289,6 +289,14 @@ VA_FN size_t va_cache_index(const long long B, const int dev, const int ncp, con
 #ifndef VA_STAGES
 #define VA_STAGES 4
 #endif
+// ring geometry of the value-only variant (no spills to keep L1 for, little arithmetic per cache row: a deeper ring
+// hides more of the row latency; ncu: 90 % of its shared-memory-read stalls wait for the row copies)
+#ifndef VA_AHEAD_V
+#define VA_AHEAD_V VA_AHEAD
+#endif
+#ifndef VA_STAGES_V
+#define VA_STAGES_V VA_STAGES
+#endif
 
 // VA_CACHE_HINT=1: the cache rows are read once per launch and never again before ~1 GB of other rows has passed: mark
 // them evict-first in L2 so that they do not push out the lines that ARE re-used (register spills of the eval kernels,
@@ -310,8 +318,8 @@ VA_FN void va_cp16(unsigned dst, const double* src) {
 }
 // Ring geometry in shared memory.  8-byte copies: [stage][row][thread] (a thread's slots are NTHR doubles apart,
 // conflict-free).  16-byte copies: [stage][row pair][thread][2].
-#define VA_RING_IDX(s) (VA_LAYOUT >= 2 ? (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * (VA_CHUNK_ROWS / 2) + ((s) % VA_CHUNK_ROWS) / 2) * (2 * VA_EVAL_THREADS) + ((s) & 1)) \
-                                       : (((((s) / VA_CHUNK_ROWS) % VA_STAGES) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS))
+#define VA_RING_IDX(s) (VA_LAYOUT >= 2 ? (((((s) / VA_CHUNK_ROWS) % va_stages_) * (VA_CHUNK_ROWS / 2) + ((s) % VA_CHUNK_ROWS) / 2) * (2 * VA_EVAL_THREADS) + ((s) & 1)) \
+                                       : (((((s) / VA_CHUNK_ROWS) % va_stages_) * VA_CHUNK_ROWS + (s) % VA_CHUNK_ROWS) * VA_EVAL_THREADS))
 #define VA_RING_TID(t) (VA_LAYOUT >= 2 ? 2 * (t) : (t))
 template <int L, int ROWS, int STAGES, int NTHR>
 VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, const double* cache) {
@@ -336,10 +344,10 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 #define VA_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define VA_CHUNK(k)                                                                              \
     {                                                                                            \
-        if ((k) + VA_AHEAD < VA_NCHUNK)                                                          \
-            va_issue<VA_LAYOUT, VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>((k) + VA_AHEAD, NCACHE_P, sbase_, cache_); \
+        if ((k) + va_ahead_ < VA_NCHUNK)                                                         \
+            va_issue<VA_LAYOUT, VA_CHUNK_ROWS, va_stages_, VA_EVAL_THREADS>((k) + va_ahead_, NCACHE_P, sbase_, cache_); \
         VA_COMMIT();                                                                             \
-        asm volatile("cp.async.wait_group %0;" ::"n"(VA_AHEAD) : "memory");                      \
+        asm volatile("cp.async.wait_group %0;" ::"n"(va_ahead_) : "memory");                      \
     }
 #define CACHE_LD(s) ring_[VA_RING_IDX(s)]
 #define CACHE_LDG(s) __ldg(cache_ + VA_SLOT_OFF(s))
@@ -352,21 +360,22 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
 // rows [source] and [NNOISE + source] of its own output block; its own cache; used by cb_noise only)
 #define VA_SETUPN_BEGIN(NAME) VA_SETUP_BEGIN_(k_setupn_##NAME)
 #define VA_SETUPN_END(NAME) }
-#define VA_EVALN_BEGIN(NAME) VA_EVAL_BEGIN_(k_evaln_##NAME, va_metan_##NAME, 1)
+#define VA_EVALN_BEGIN(NAME) VA_EVAL_BEGIN_(k_evaln_##NAME, va_metan_##NAME, 1, VA_AHEAD, VA_STAGES)
 #define VA_EVALN_END(NAME) VA_EVAL_END(NAME)
 #define OUT_N(k, v) out_[(size_t)(k) * a.B] = (v)
 #define OUT_NE(k, v) out_[(size_t)(NNOISE + (k)) * a.B] = (v)
-#define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS)
-#define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS)
+#define VA_EVAL_BEGIN(NAME) VA_EVAL_BEGIN_(k_eval_##NAME, va_meta_##NAME, VA_EVAL_MINBLOCKS, VA_AHEAD, VA_STAGES)
+#define VA_EVALV_BEGIN(NAME) VA_EVAL_BEGIN_(k_evalv_##NAME, va_metav_##NAME, VA_EVALV_MINBLOCKS, VA_AHEAD_V, VA_STAGES_V)
 #define VA_EVALV_END(NAME) VA_EVAL_END(NAME)
 // Thread mapping: thread k of the launch takes the k-th entry of the point list of this kind of iteration (full /
 // value-only), which k_control compacted device-wide; threads beyond the count exit before any work.  The lists ascend
 // inside runs of up to 32 points, so a warp reads a few contiguous row segments; with every point live the launch is as
 // coalesced as the identity mapping.
-#define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS)                                                  \
-    extern "C" __device__ int META[6] = {VA_EVAL_THREADS, VA_STAGES * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS, NUNI, 0}; \
+#define VA_EVAL_BEGIN_(KERNEL, META, MINBLOCKS, AHEAD, STAGES)                                   \
+    extern "C" __device__ int META[6] = {VA_EVAL_THREADS, (STAGES) * VA_CHUNK_ROWS * VA_EVAL_THREADS * 8, NCACHE, MINBLOCKS, NUNI, 0}; \
     extern "C" __global__ void __launch_bounds__(VA_EVAL_THREADS, MINBLOCKS) KERNEL(VaArgs a) {  \
-        static_assert((VA_STAGES - VA_AHEAD - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
+        constexpr int va_ahead_ = (AHEAD), va_stages_ = (STAGES);   /* ring geometry of this kernel (VA_CHUNK, CACHE_LD) */ \
+        static_assert((va_stages_ - va_ahead_ - 1) * VA_CHUNK_ROWS >= VA_WINDOW - 1, "cache ring too shallow"); \
         extern __shared__ __align__(16) double va_ring_[];                                       \
         if (blockDim.x != VA_EVAL_THREADS) __trap();                                             \
         long long inst;                                                                          \
@@ -381,8 +390,8 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
         (void)uni_;                                                                              \
         const double* ring_ = va_ring_ + VA_RING_TID(threadIdx.x);                               \
         const unsigned sbase_ = (unsigned)__cvta_generic_to_shared(va_ring_ + VA_RING_TID(threadIdx.x)); \
-        _Pragma("unroll") for (int c_ = 0; c_ < VA_AHEAD; c_++) {                                \
-            if (c_ < VA_NCHUNK) va_issue<VA_LAYOUT, VA_CHUNK_ROWS, VA_STAGES, VA_EVAL_THREADS>(c_, NCACHE_P, sbase_, cache_); \
+        _Pragma("unroll") for (int c_ = 0; c_ < va_ahead_; c_++) {                               \
+            if (c_ < VA_NCHUNK) va_issue<VA_LAYOUT, VA_CHUNK_ROWS, va_stages_, VA_EVAL_THREADS>(c_, NCACHE_P, sbase_, cache_); \
             VA_COMMIT();                                                                         \
         }                                                                                        \
         const double alpha_ = a.alpha[inst];                                                     \
