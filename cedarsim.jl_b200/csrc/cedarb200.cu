@@ -33,6 +33,7 @@ struct NvtxRange {
     ~NvtxRange() { nvtxRangePop(); }
 };
 #define CB_NBUF 3   // rotating buffers of the per-round point lists (solve())
+#include "spice_front.hpp"
 #include "symbolic.hpp"
 #include "va_prelude.h"
 
@@ -247,6 +248,69 @@ struct Reader {
     }
 };
 }  // namespace
+
+// ---- native netlist front end (spice_front.hpp): deck text + sweep values -> flat circuit + params[P][B] ----------------
+extern "C" int cb_netlist_flatten(const char* text, const char* base_dir, const char* const* sweep_names, int n_sweep,
+                                  const double* sweep_values, int64_t n_inst, const char* const* output_names, int n_outputs,
+                                  cb_netlist** out) {
+    if (!text || !out || n_sweep < 0 || n_outputs < 0 || n_inst < 1 || (n_sweep > 0 && (!sweep_names || !sweep_values)) ||
+        (n_outputs > 0 && !output_names))
+        return fail(CB_ERR_INVALID, "null / negative argument");
+    try {
+        auto h = std::make_unique<cb_netlist>();
+        sf::parse_into(h->nl, text, true, base_dir ? base_dir : "", 0);
+        std::vector<std::string> names, outs;
+        for (int k = 0; k < n_sweep; k++) names.push_back(sweep_names[k] ? sweep_names[k] : "");
+        for (int k = 0; k < n_outputs; k++) outs.push_back(output_names[k] ? output_names[k] : "");
+        sf::Flattener(h->nl, h->fc).run(names, sweep_values, n_inst, outs);
+        sf::Flat& fc = h->fc;
+        h->unknown_names = fc.node_names;
+        h->unknown_names.insert(h->unknown_names.end(), fc.branch_names.begin(), fc.branch_names.end());
+        if (fc.outputs.empty() && n_outputs == 0)
+            for (size_t k = 0; k < h->unknown_names.size(); k++) fc.outputs.push_back((int32_t)k);   // default: every unknown
+        if (h->unknown_names.empty()) return fail(CB_ERR_INVALID, "the deck has no unknowns");
+        const size_t P = fc.columns.size();
+        h->params.resize(P * (size_t)n_inst);
+        for (size_t k = 0; k < P; k++) std::copy(fc.columns[k].begin(), fc.columns[k].end(), h->params.begin() + k * (size_t)n_inst);
+        cb_flat_circuit& f = h->flat;
+        f.n_unknowns = (int32_t)h->unknown_names.size();
+        f.n_nodes = (int32_t)fc.node_names.size();
+        f.n_params = (int32_t)P;
+        f.n_devices = (int32_t)fc.devices.size();
+        f.devices = fc.devices.data();
+        f.n_waves = (int32_t)fc.waves.size();
+        f.waves = fc.waves.data();
+        f.n_va_models = 0; f.va_models = nullptr; f.n_va_insts = 0; f.va_insts = nullptr;
+        f.n_outputs = (int32_t)fc.outputs.size();
+        f.outputs = fc.outputs.data();
+        *out = h.release();
+        return CB_OK;
+    } catch (const std::exception& e) {
+        return fail(CB_ERR_INVALID, std::string("netlist: ") + e.what());
+    }
+}
+
+extern "C" int cb_netlist_circuit(cb_netlist* nl, cb_circuit** out) {
+    if (!nl || !out) return fail(CB_ERR_INVALID, "null argument");
+    return cb_circuit_create(&nl->flat, out);
+}
+extern "C" const cb_flat_circuit* cb_netlist_flat(const cb_netlist* nl) { return nl ? &nl->flat : nullptr; }
+extern "C" int32_t cb_netlist_n_unknowns(const cb_netlist* nl) { return nl ? nl->flat.n_unknowns : -1; }
+extern "C" int32_t cb_netlist_n_params(const cb_netlist* nl) { return nl ? nl->flat.n_params : -1; }
+extern "C" const double* cb_netlist_params(const cb_netlist* nl) { return nl ? nl->params.data() : nullptr; }
+extern "C" const char* cb_netlist_unknown_name(const cb_netlist* nl, int32_t i) {
+    return (nl && i >= 0 && i < (int32_t)nl->unknown_names.size()) ? nl->unknown_names[(size_t)i].c_str() : nullptr;
+}
+extern "C" const char* cb_netlist_param_name(const cb_netlist* nl, int32_t i) {
+    return (nl && i >= 0 && i < (int32_t)nl->fc.param_names.size()) ? nl->fc.param_names[(size_t)i].c_str() : nullptr;
+}
+extern "C" int32_t cb_netlist_unknown(const cb_netlist* nl, const char* name) { return (nl && name) ? nl->fc.unknown(name) : -1; }
+extern "C" double cb_netlist_option(const cb_netlist* nl, const char* name, double dflt) {
+    if (!nl || !name) return dflt;
+    auto it = nl->fc.options.find(sf::lower(name));
+    return it == nl->fc.options.end() ? dflt : it->second;
+}
+extern "C" void cb_netlist_destroy(cb_netlist* nl) { delete nl; }
 
 extern "C" int cb_circuit_load(const char* path, cb_circuit** out) {
     if (!path || !out) return fail(CB_ERR_INVALID, "null argument");

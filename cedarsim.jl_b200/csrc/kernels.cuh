@@ -89,6 +89,24 @@ struct NArgs {
     Opts o;
 };
 
+// IEEE division as ONE out-of-line body (~40 instructions with its slow path) instead of ~25 inlined instructions at each
+// of the ~70 division sites of the control step: that code is mostly straight-line and every CTA walks it once, so at
+// small batches (one CTA per SM, code evicted between rounds by the 300 KB eval kernels) its time is instruction fetch,
+// not arithmetic.  Same result bit for bit.
+#ifndef CB_CTRL_SMALL_CODE
+#define CB_CTRL_SMALL_CODE 1
+#endif
+#if CB_CTRL_SMALL_CODE
+__device__ __noinline__ double cb_ddiv(double a, double b) { return a / b; }
+#define DIV(a, b) cb_ddiv((a), (b))
+#define CB_CTRL_INLINE __noinline__
+#define CB_CTRL_UNROLL _Pragma("unroll 1")
+#else
+#define DIV(a, b) ((a) / (b))
+#define CB_CTRL_INLINE __forceinline__
+#define CB_CTRL_UNROLL _Pragma("unroll 4")
+#endif
+
 __device__ __forceinline__ double pv(const Pref& p, const double* params, long long B, long long inst) {
     return p.col < 0 ? p.value : params[(size_t)p.col * B + inst];
 }
@@ -151,19 +169,19 @@ __device__ inline double wave_tran(const WaveDev& w, double t, const double* par
     return 0.0;
 }
 
-__device__ inline double wave_value(const WaveDev& w, double t, bool dcop, const double* params, long long B,
+__device__ CB_CTRL_INLINE double wave_value(const WaveDev& w, double t, bool dcop, const double* params, long long B,
                                     long long inst) {
     if (dcop) return w.has_dc ? pv(w.dc, params, B, inst) : wave_tran(w, 0.0, params, B, inst);
     return wave_tran(w, t, params, B, inst);
 }
 
 // value of the accepted interpolation polynomial at tt for unknown i (mirrors oracle predict())
-__device__ __forceinline__ double poly_at(int nh, double tt, double tn, double xn, double h1, double x1, double h2,
-                                          double x2) {
+__device__ CB_CTRL_INLINE double poly_at(int nh, double tt, double tn, double xn, double h1, double x1, double h2,
+                                         double x2) {
     if (nh <= 0) return xn;
     const double a = tt - tn;
-    if (nh == 1) return xn + a * (xn - x1) / h1;
-    const double d1 = (xn - x1) / h1, d2 = (x1 - x2) / h2, dd = (d1 - d2) / (h1 + h2);
+    if (nh == 1) return xn + DIV(a * (xn - x1), h1);
+    const double d1 = DIV(xn - x1, h1), d2 = DIV(x1 - x2, h2), dd = DIV(d1 - d2, h1 + h2);
     return xn + a * d1 + a * (a + h1) * dd;
 }
 
@@ -291,13 +309,13 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     double sc = 1.0, ratio = 0.0;
     if (solving) {
         lim = o.dv_max;
-        sc = dvmax > lim ? lim / dvmax : 1.0;
+        sc = dvmax > lim ? DIV(lim, dvmax) : 1.0;
         if (want_lte) {
-            if (method == 0) ratio = h / (2.0 * h + h1);
+            if (method == 0) ratio = DIV(h, 2.0 * h + h1);
             else {
-                const double pc = h * (h + h1) * (h + h1 + h2) / 6.0;
-                const double lc = method == 1 ? h * h * h / 12.0 : h * h * (h + h1) * (h + h1) / (6.0 * (2.0 * h + h1));
-                ratio = np >= 2 ? lc / (lc + pc) : h / (2.0 * h + h1);
+                const double pc = DIV(h * (h + h1) * (h + h1 + h2), 6.0);
+                const double lc = method == 1 ? DIV(h * h * h, 12.0) : DIV(h * h * (h + h1) * (h + h1), 6.0 * (2.0 * h + h1));
+                ratio = np >= 2 ? DIV(lc, lc + pc) : DIV(h, 2.0 * h + h1);
             }
         }
     }
@@ -305,16 +323,16 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         double nrm = 0.0;
         double err = 0.0;
         if (solving) {
-#pragma unroll 4
+            CB_CTRL_UNROLL
             for (int i = lane; i < N; i += CTRL_LANES) {
                 const double dx = sc * DXV(i);
                 const double xo = V(X, i), xn = xo + dx;
                 const double atol = i < NV ? o.nr_vabstol : o.nr_iabstol;
-                nrm = fmax(nrm, fabs(dx) / (o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol));
+                nrm = fmax(nrm, DIV(fabs(dx), o.nr_reltol * fmax(fabs(xn), fabs(xo)) + atol));
                 V(X, i) = xn;
                 if (want_lte && mask[i]) {
                     const double tol = o.reltol * fmax(fabs(xn), fabs(V(XN, i))) + (i < NV ? o.vabstol : o.iabstol);
-                    err = fmax(err, ratio * fabs(xn - V(XP, i)) / tol);
+                    err = fmax(err, DIV(ratio * fabs(xn - V(XP, i)), tol));
                 }
             }
         }
@@ -348,12 +366,12 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
                         // convergence; kappa learnt from the attempts that did take a second iteration)
                         if (o.rate_test >= 2 && !pv) est = fmin(nrm, 3.0 * kappa * nrm * nrm);
                     } else {
-                        if (it == 1 && nrm_prev > 0.0) kappa = fmax(fmax(nrm / (nrm_prev * nrm_prev), 0.7 * kappa), o.kappa_floor);
+                        if (it == 1 && nrm_prev > 0.0) kappa = fmax(fmax(DIV(nrm, nrm_prev * nrm_prev), 0.7 * kappa), o.kappa_floor);
                         if (nrm < nrm_prev) {
                             // safety 3; a chord update (value-only round) contracts half as fast as the ratio observed
                             // across the preceding Newton update suggests (e_2 ~ 2 (e_1 / e_0) e_1)
-                            const double rho = nrm / nrm_prev;
-                            est = nrm * fmin(1.0, (pv ? 6.0 : 3.0) * rho / (1.0 - rho));
+                            const double rho = DIV(nrm, nrm_prev);
+                            est = nrm * fmin(1.0, DIV((pv ? 6.0 : 3.0) * rho, 1.0 - rho));
                         }
                     }
                 }
@@ -439,7 +457,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
                 if (dc_done) {
                     gshunt = 0.0;
                     if (o.dc_only) {
-                        for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[(size_t)k * B + inst] = V(X, a.outputs[k]);
+                        CB_CTRL_UNROLL for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[(size_t)k * B + inst] = V(X, a.outputs[k]);
                         phase = PH_DONE;
                         if (lane == 0) atomicAdd(a.done_count, 1);
                     } else {
@@ -465,7 +483,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     if (out_init) {
         const double* __restrict__ src0 = out_from_x ? X : XN;
         while (sidx < o.nsave && a.saveat[sidx] <= o.t0 + o.teps) {
-            for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(src0, a.outputs[k]);
+            CB_CTRL_UNROLL for (int k = lane; k < a.O; k += CTRL_LANES) a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(src0, a.outputs[k]);
             sidx++;
         }
     }
@@ -473,7 +491,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         const double ts = a.saveat[sx];
         const bool exact = fabs(ts - t) <= o.teps;
         const int ni = o.method == 0 ? 1 : nh_out;   // history order before a breakpoint hit resets nh
-        for (int k = lane; k < a.O; k += CTRL_LANES) {
+        CB_CTRL_UNROLL for (int k = lane; k < a.O; k += CTRL_LANES) {
             const int u = a.outputs[k];
             const double xn = V(X, u);
             a.y_out[((size_t)k * o.nsave + sx) * B + inst] = exact ? xn : poly_at(ni, ts, t, xn, h1, V(XN, u), h2, V(X1, u));
@@ -483,7 +501,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     double a1 = 0.0, a2 = 0.0;
     if (reinit_begin) {   // backward Euler over h0 = span * 1e-12 "from t0 to t0": beta = -q_dc / h0, Newton starts at the operating point
         tnew = o.t0; h = o.span * 1e-12;
-        alpha = 1.0 / h; a1 = -alpha;
+        alpha = DIV(1.0, h); a1 = -alpha;
         method = 0; np = 0; retry = 0;
     }
     if (begin) {
@@ -506,13 +524,13 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         if (!more) { finish = true; begin = false; }
         else {
             method = nh == 0 ? 0 : o.method;
-            if (method == 0) { alpha = 1.0 / h; a1 = -alpha; }
-            else if (method == 1) { alpha = 2.0 / h; a1 = -alpha; }
+            if (method == 0) { alpha = DIV(1.0, h); a1 = -alpha; }
+            else if (method == 1) { alpha = DIV(2.0, h); a1 = -alpha; }
             else {
-                const double rho = h / h1;
-                alpha = (1.0 + 2.0 * rho) / (h * (1.0 + rho));
-                a1 = -(1.0 + rho) / h;
-                a2 = rho * rho / (h * (1.0 + rho));
+                const double rho = DIV(h, h1);
+                alpha = DIV(1.0 + 2.0 * rho, h * (1.0 + rho));
+                a1 = -DIV(1.0 + rho, h);
+                a2 = DIV(rho * rho, h * (1.0 + rho));
             }
             np = method == 0 ? (nh < 1 ? nh : 1) : nh;
             it = 0;
@@ -522,7 +540,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     __syncthreads();   // output sampling has read the un-shifted history rows of other lanes
     // ---- pass 2 over this lane's unknowns: history shift (accept), DC copies, beta + predictor (begin)
     if (do_accept || copy_mode || begin || reinit_begin) {
-#pragma unroll 4
+            CB_CTRL_UNROLL
         for (int i = lane; i < N; i += CTRL_LANES) {
             double x = V(X, i), xn = V(XN, i), x1 = V(X1, i), x2 = V(X2, i), qn = V(QN, i), q1 = V(Q1, i), qd = V(QD, i);
             if (do_accept) {
@@ -544,7 +562,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
                 V(BETA, i) = beta;
                 const double xp = poly_at(np, tnew, t, xn, h1, x1, h2, x2);
                 V(XP, i) = xp;
-                double lm = np >= 1 ? fabs(xn - x1) * (h / h1) : 0.0;
+                double lm = np >= 1 ? fabs(xn - x1) * DIV(h, h1) : 0.0;
                 if (i < NV) lm = fmin(lm, o.dv_max);
                 V(X, i) = xn + fmax(-lm, fmin(lm, xp - xn));
             }
@@ -553,7 +571,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     __syncthreads();   // the fill below reads XN rows written by other lanes
     if (finish) {
         for (; sidx < o.nsave; sidx++)
-            for (int k = lane; k < a.O; k += CTRL_LANES)
+            CB_CTRL_UNROLL for (int k = lane; k < a.O; k += CTRL_LANES)
                 a.y_out[((size_t)k * o.nsave + sidx) * B + inst] = V(XN, a.outputs[k]);
         phase = PH_DONE;
         if (lane == 0) atomicAdd(a.done_count, 1);
@@ -571,8 +589,8 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         }
         if (phase != PH_DONE) {
             // source stepping of the operating point: every independent source times stage / source_steps
-            const double src_scale = (phase == PH_DC && stage > o.gmin_steps) ? (double)(stage - o.gmin_steps) / (double)o.source_steps : 1.0;
-            for (int w = lane; w < a.nwaves; w += CTRL_LANES)
+            const double src_scale = (phase == PH_DC && stage > o.gmin_steps) ? DIV((double)(stage - o.gmin_steps), (double)o.source_steps) : 1.0;
+            CB_CTRL_UNROLL for (int w = lane; w < a.nwaves; w += CTRL_LANES)
                 c.WV[(size_t)w * B + inst] = src_scale * wave_value(a.waves[w], tnew, phase != PH_TRAN && phase != PH_REINIT, a.params, B, inst);
         }
     }

@@ -786,10 +786,18 @@ class Flattener {
                 if (vals.size() > 7) throw Error(name + ": too many " + src.tran_kind + " arguments");
                 for (size_t k = 0; k < vals.size(); k++) w.v[k] = fc.value(name + "." + (pulse ? "pulse" : "sin") + std::to_string(k), vals[k]);
                 w.kind = pulse ? CB_W_PULSE : CB_W_SIN;
-                if (pulse) {   // SPICE defaults the engine's waveform code expects filled in: tr, tf, pw, per
-                    if (vals.size() < 2) throw Error(name + ": PULSE needs at least v1 v2");
-                    for (size_t k = 2; k < vals.size() && k < 7; k++)
-                        if (w.v[k].col >= 0) throw Error(name + ": PULSE timing values cannot be swept");
+                const double inf = std::numeric_limits<double>::infinity();
+                if (pulse) {   // PULSE v1 v2 td tr tf [pw [per]]; a period <= 0 means one pulse, as in SPICE
+                    if (vals.size() < 5) throw Error(name + ": PULSE needs v1 v2 td tr tf [pw [per]]");
+                    for (size_t k = vals.size(); k < 7; k++) w.v[k] = cb_pref{inf, -1, 0};
+                    for (int k = 2; k < 7; k++)
+                        if (w.v[k].col >= 0) throw Error(name + ": PULSE timing parameters cannot be swept (shared breakpoints)");
+                    if (!(w.v[6].value > 0.0)) w.v[6].value = inf;
+                    for (int k = 2; k < 6; k++)
+                        if (!(w.v[k].value >= 0.0 && w.v[k].value < inf)) throw Error(name + ": PULSE td / tr / tf / pw must be finite and >= 0");
+                } else {       // SIN vo va freq td theta phase ncycles
+                    const double dflt[7] = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0, inf};
+                    for (size_t k = vals.size(); k < 7; k++) w.v[k] = cb_pref{dflt[k], -1, 0};
                 }
             }
         }

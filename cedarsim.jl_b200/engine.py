@@ -108,12 +108,16 @@ def measure_fp64_peak(device: int = 0) -> float:
 class Circuit:
     """A compiled circuit: flat description + generated device code + symbolic LU."""
 
-    def __init__(self, fc: F.FlatCircuit, models: Sequence = (), cache_dir: Optional[str] = CUBIN_CACHE):
+    def __init__(self, fc: F.FlatCircuit, models: Sequence = (), cache_dir: Optional[str] = CUBIN_CACHE, _handle=None):
         self.lib = load()
         self.fc = fc
-        self.packed = fc.pack()
         self.handle = C.c_void_p()
-        _check(self.lib.cb_circuit_create(self.packed.ref(), C.byref(self.handle)))
+        if _handle is not None:        # created by the library itself (NativeNetlist: cb_netlist_circuit)
+            self.packed = None
+            self.handle = _handle
+        else:
+            self.packed = fc.pack()
+            _check(self.lib.cb_circuit_create(self.packed.ref(), C.byref(self.handle)))
         if fc.va_models:
             by_name = {cm.name: cm for cm in models}
             src = cuda_source([by_name[m.name] for m in fc.va_models]).encode()
@@ -275,6 +279,93 @@ class Plan:
     def close(self):
         if self.handle:
             self.lib.cb_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NativeNetlist:
+    """The library's own netlist front end (include/cedarb200.h cb_netlist_*, csrc/spice_front.hpp): a SPICE-subset deck and
+    the sweep's values go in as text and arrays, the flat circuit and the parameter matrix come back -- no Python parser,
+    flattener or struct packing on the way.  `fc` is a read-only FlatCircuit VIEW of what the library built (names,
+    devices, waves, outputs), so results can be named and the CPU oracle can be handed the same circuit."""
+
+    def __init__(self, text: str, sweep: Optional[dict] = None, outputs: Optional[Sequence[str]] = None, base_dir: Optional[str] = None):
+        lib = load()
+        lib.cb_netlist_flat.restype = C.POINTER(F.cb_flat_circuit)
+        lib.cb_netlist_params.restype = C.POINTER(C.c_double)
+        lib.cb_netlist_unknown_name.restype = C.c_char_p
+        lib.cb_netlist_param_name.restype = C.c_char_p
+        lib.cb_netlist_option.restype = C.c_double
+        self.lib = lib
+        sweep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in (sweep or {}).items()}
+        B = len(next(iter(sweep.values()))) if sweep else 1
+        names = (C.c_char_p * max(1, len(sweep)))(*[k.encode() for k in sweep])
+        vals = np.ascontiguousarray(np.stack(list(sweep.values())) if sweep else np.zeros((0, B)))
+        outs = list(outputs or [])
+        onames = (C.c_char_p * max(1, len(outs)))(*[o.encode() for o in outs])
+        self.handle = C.c_void_p()
+        _check(lib.cb_netlist_flatten(text.encode(), base_dir.encode() if base_dir else None, names, C.c_int(len(sweep)),
+                                      _dp(vals) if sweep else None, C.c_int64(B), onames, C.c_int(len(outs)), C.byref(self.handle)))
+        self.B = B
+        P = int(lib.cb_netlist_n_params(self.handle))
+        self.params = np.ctypeslib.as_array(lib.cb_netlist_params(self.handle), shape=(P, B)).copy() if P else np.zeros((0, B))
+        self.fc = self._view()
+
+    def _view(self) -> F.FlatCircuit:
+        lib, h = self.lib, self.handle
+        f = lib.cb_netlist_flat(h).contents
+        fc = F.FlatCircuit()
+        names = [lib.cb_netlist_unknown_name(h, i).decode() for i in range(f.n_unknowns)]
+        fc.node_names = names[:f.n_nodes]
+        fc.branch_names = names[f.n_nodes:]
+        fc._node_index = {n: i for i, n in enumerate(fc.node_names)}
+        fc.param_names = [lib.cb_netlist_param_name(h, i).decode() for i in range(f.n_params)]
+
+        def val(p):
+            return F.Col(p.col) if p.col >= 0 else float(p.value)
+        for i in range(f.n_waves):
+            w = f.waves[i]
+            wv = F.Wave(int(w.kind), dc=(val(w.dc) if w.has_dc else None))
+            if w.kind == F.W_PWL:
+                wv.t = [float(w.t[k]) for k in range(w.npts)]
+                wv.y = [val(w.y[k]) for k in range(w.npts)]
+            elif w.kind in (F.W_PULSE, F.W_SIN):
+                wv.v = [val(w.v[k]) for k in range(7)]
+            wv.ac = float(w.ac_mag)
+            fc.waves.append(wv)
+        for i in range(f.n_devices):
+            d = f.devices[i]
+            nn = {F.DEV_VCVS: 4, F.DEV_VCCS: 4}.get(int(d.kind), 2)
+            fc.devices.append(F.Device(int(d.kind), f"d{i}", [int(d.n[k]) for k in range(nn)], val(d.value), int(d.branch), int(d.wave),
+                                       float(d.mult)))
+        fc.outputs = [int(f.outputs[k]) for k in range(f.n_outputs)]
+        fc._finalized = True
+        return fc
+
+    def unknown(self, name: str) -> int:
+        u = int(self.lib.cb_netlist_unknown(self.handle, name.encode()))
+        if u < 0:
+            raise KeyError(f"no unknown named {name!r}")
+        return u
+
+    def option(self, name: str, default: float = float("nan")) -> float:
+        return float(self.lib.cb_netlist_option(self.handle, name.encode(), C.c_double(default)))
+
+    def circuit(self, cache_dir: Optional[str] = CUBIN_CACHE) -> Circuit:
+        """cb_netlist_circuit + cb_circuit_compile: the engine circuit of this deck, created by the library from its own
+        flat circuit."""
+        ch = C.c_void_p()
+        _check(self.lib.cb_netlist_circuit(self.handle, C.byref(ch)))
+        return Circuit(self.fc, (), cache_dir, _handle=ch)
+
+    def close(self):
+        if self.handle:
+            self.lib.cb_netlist_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -478,10 +478,11 @@ class SweepSolution:
 class CircuitSweep:
     """CircuitSweep(circuit, sweep): compile once for the set of swept names, then solve all points
     in one batched call.  `circuit` is a parsed `Netlist` (or SPICE text), or a callable
-    `builder(columns: dict, B: int) -> Flattened`."""
+    `builder(columns: dict, B: int) -> Flattened`.  front_end="native": SPICE text is read and flattened by the engine
+    library itself (cb_netlist_*, csrc/spice_front.hpp: R C L V I E G X decks) instead of the Python front end."""
 
     def __init__(self, circuit, iterator, outputs: Optional[Sequence[str]] = None, devices: Optional[Sequence[int]] = None,
-                 host: bool = False, include_dirs: Optional[Sequence[str]] = None, lang: str = "spice"):
+                 host: bool = False, include_dirs: Optional[Sequence[str]] = None, lang: str = "spice", front_end: str = "python"):
         self.iterator = sweepify(iterator)
         self.shape = self.iterator.shape
         self.circuit = circuit
@@ -490,6 +491,23 @@ class CircuitSweep:
         B = len(self.iterator)
         if B == 0:   # the reference compiles from `first(iterator)` (src/sweeps.jl:414-417) and fails on an empty one as well
             raise ValueError("empty sweep: a CircuitSweep needs at least one point")
+        self._native = None
+        if isinstance(circuit, str) and front_end == "native":
+            if lang != "spice":
+                raise ValueError("the native front end reads SPICE decks only")
+            import math
+            from .flat import Col
+            nn = engine.NativeNetlist(circuit, self.columns, outputs, base_dir=(include_dirs[0] if include_dirs else None))
+            opts = {}
+            t = nn.option("temp")
+            if "temp" in nn.fc.param_names:
+                opts["temp"] = Col(nn.fc.param_names.index("temp"))
+            elif not math.isnan(t):
+                opts["temp"] = t
+            self._native = nn
+            circuit = lambda columns, B_: Flattened(nn.fc, nn.params, [], opts, None)   # noqa: E731
+        elif front_end != "python":
+            raise ValueError("front_end must be 'python' or 'native'")
         if isinstance(circuit, str):
             from .netlist import parse_netlist
             if lang == "spectre":
@@ -532,7 +550,7 @@ class CircuitSweep:
     def _ensure_plans(self):
         if self._plans:
             return
-        self._compiled = engine.Circuit(self.flat.fc, self.flat.models)
+        self._compiled = self._native.circuit() if self._native is not None else engine.Circuit(self.flat.fc, self.flat.models)
         # one plan over all the GPUs named in `devices` (cb_plan_create_multi: contiguous block of points per GPU, one
         # host thread per lane inside the library, results copied straight into the caller's arrays)
         plan = self._compiled.plan(len(self), devices=self.devices)

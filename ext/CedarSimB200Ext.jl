@@ -164,6 +164,47 @@ function B200Sweep(netlist_path::AbstractString, iterator; outputs::Vector{Strin
     return cs
 end
 
+"""
+    B200Sweep(spice_text, iterator, Val(:native); outputs, device = 0, cache_dir = nothing, base_dir = nothing)
+
+The same with the LIBRARY's own netlist front end (`cb_netlist_flatten`, include/cedarb200.h): SPICE text and the sweep's
+values go straight across the C ABI -- no Python process, no files.  For decks of R C L V I E G and subcircuits; decks
+with MOSFETs / Verilog-A / behavioural sources are refused by the library with a message and take the method above.
+`nothing` entries of a SerialSweep are passed as NaN (= keep the default, src/sweeps.jl:18-21).
+"""
+function B200Sweep(spice_text::AbstractString, iterator, ::Val{:native}; outputs::Vector{String}, device::Integer = 0,
+                   cache_dir = nothing, base_dir = nothing)
+    names = sort!(collect(string.(sweepvars(iterator))))
+    points = collect(iterator)
+    B = length(points)
+    vals = Matrix{Float64}(undef, B, length(names))          # (B, n_sweep): C layout [n_sweep][B]
+    for (i, point) in enumerate(points)
+        d = Dict(string(k) => v for (k, v) in pairs(point))
+        for (j, n) in enumerate(names)
+            vals[i, j] = d[n] === nothing ? NaN : Float64(d[n])
+        end
+    end
+    nl = Ref{Ptr{Cvoid}}(C_NULL); c = Ref{Ptr{Cvoid}}(C_NULL); p = Ref{Ptr{Cvoid}}(C_NULL); secs = Ref{Cdouble}(0.0)
+    GC.@preserve vals check(ccall((:cb_netlist_flatten, lib), Cint,
+        (Cstring, Cstring, Ptr{Cstring}, Cint, Ptr{Cdouble}, Int64, Ptr{Cstring}, Cint, Ref{Ptr{Cvoid}}),
+        spice_text, base_dir === nothing ? C_NULL : base_dir, names, length(names), vals, B, outputs, length(outputs), nl))
+    check(ccall((:cb_netlist_circuit, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), nl[], c))
+    check(ccall((:cb_circuit_compile, lib), Cint, (Ptr{Cvoid}, Cstring, Ref{Cdouble}), c[],
+                cache_dir === nothing ? C_NULL : cache_dir, secs))
+    P = Int(ccall((:cb_netlist_n_params, lib), Int32, (Ptr{Cvoid},), nl[]))
+    params = Matrix{Float64}(undef, B, P)
+    P > 0 && unsafe_copyto!(pointer(params), ccall((:cb_netlist_params, lib), Ptr{Cdouble}, (Ptr{Cvoid},), nl[]), B * P)
+    ccall((:cb_netlist_destroy, lib), Cvoid, (Ptr{Cvoid},), nl[])
+    check(ccall((:cb_plan_create, lib), Cint, (Ptr{Cvoid}, Int64, Cint, Ref{Ptr{Cvoid}}), c[], B, device, p))
+    cs = B200Sweep(iterator, c[], p[], params, lowercase.(outputs), Dict{String,Any}("B" => B, "P" => P), secs[])
+    GC.@preserve params check(ccall((:cb_plan_set_params, lib), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), p[], params))
+    finalizer(cs) do x
+        ccall((:cb_plan_destroy, lib), Cvoid, (Ptr{Cvoid},), x.plan)
+        ccall((:cb_circuit_destroy, lib), Cvoid, (Ptr{Cvoid},), x.circuit)
+    end
+    return cs
+end
+
 # minimal JSON reader for the flat {"key": number | string | [..] | {..} | null} files the front end writes
 function _read_json(path)
     s = read(path, String); i = Ref(1)

@@ -5,6 +5,10 @@
  *   abi_smoke layout           print {"struct.field": [offset, size], ..., "struct": [0, sizeof]} as JSON
  *   abi_smoke run <lib.so>     dlopen the engine, build the two-resistor divider of the reference's test/sweep.jl:326-340
  *                              through the C ABI alone and solve its DC sweep on the GPU (needs a GPU)
+ *   abi_smoke netlist <lib.so> [flatten]
+ *                              the same sweep from DECK TEXT: cb_netlist_flatten (the library's own SPICE reader) ->
+ *                              cb_netlist_circuit -> cb_circuit_compile -> cb_plan_create -> cb_dc; with `flatten` it stops
+ *                              after the host-side steps (no GPU needed) and prints what the reader built
  */
 #include <dlfcn.h>
 #include <math.h>
@@ -122,9 +126,86 @@ static int run(const char *path) {
     }
 }
 
+static int run_netlist(const char *path, int flatten_only) {
+    void *h = dlopen(path, RTLD_NOW);
+    const char *(*p_cb_last_error)(void);
+    int (*p_cb_options_init)(cb_options *, size_t);
+    int (*p_cb_netlist_flatten)(const char *, const char *, const char *const *, int, const double *, int64_t, const char *const *, int,
+                                cb_netlist **);
+    int (*p_cb_netlist_circuit)(cb_netlist *, cb_circuit **);
+    int32_t (*p_cb_netlist_n_unknowns)(const cb_netlist *);
+    int32_t (*p_cb_netlist_n_params)(const cb_netlist *);
+    const double *(*p_cb_netlist_params)(const cb_netlist *);
+    const char *(*p_cb_netlist_param_name)(const cb_netlist *, int32_t);
+    int32_t (*p_cb_netlist_unknown)(const cb_netlist *, const char *);
+    void (*p_cb_netlist_destroy)(cb_netlist *);
+    int (*p_cb_circuit_compile)(cb_circuit *, const char *, double *);
+    int (*p_cb_plan_create)(cb_circuit *, int64_t, int, cb_plan **);
+    int (*p_cb_plan_set_params)(cb_plan *, const double *);
+    int (*p_cb_dc)(cb_plan *, const cb_options *, double *, double *, int32_t *, cb_stats *);
+    void (*p_cb_plan_destroy)(cb_plan *);
+    void (*p_cb_circuit_destroy)(cb_circuit *);
+    /* the deck of the reference's test/sweep.jl:342-371: a subcircuit parameter swept through the instance */
+    static const char deck[] =
+        "* Parameter scoping test\n"
+        ".subckt subcircuit1 vss gnd l=11\n"
+        ".param r_load=1\n"
+        "r1 vss gnd 'r_load'\n"
+        ".ends\n"
+        ".param v_in=1\n"
+        "x1 vcc 0 subcircuit1 r_load=10\n"
+        "v1 vcc 0 DC 'v_in'\n";
+    enum { B = 256 };
+    const char *names[2] = {"v_in", "x1.r_load"};
+    const char *outs[1] = {"v1.i"};
+    static double vals[2 * B], x[B];
+    static int32_t status[B];
+    cb_netlist *nl = NULL;
+    cb_circuit *c = NULL;
+    cb_plan *p = NULL;
+    cb_options opt;
+    cb_stats st;
+    int i, rc;
+    double err = 0.0;
+    if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+    SYM(cb_last_error) SYM(cb_options_init) SYM(cb_netlist_flatten) SYM(cb_netlist_circuit) SYM(cb_netlist_n_unknowns)
+    SYM(cb_netlist_n_params) SYM(cb_netlist_params) SYM(cb_netlist_param_name) SYM(cb_netlist_unknown) SYM(cb_netlist_destroy)
+    SYM(cb_circuit_compile) SYM(cb_plan_create) SYM(cb_plan_set_params) SYM(cb_dc) SYM(cb_plan_destroy) SYM(cb_circuit_destroy)
+    for (i = 0; i < B; i++) { vals[i] = 0.5 + (i % 16) * 0.1; vals[B + i] = 5.0 + (i / 16); }
+    rc = p_cb_netlist_flatten(deck, NULL, names, 2, vals, B, outs, 1, &nl);
+    if (rc == CB_OK) rc = p_cb_netlist_circuit(nl, &c);
+    if (rc == CB_OK) rc = p_cb_circuit_compile(c, NULL, NULL);
+    if (rc != CB_OK) { fprintf(stderr, "cb error %d: %s\n", rc, p_cb_last_error()); return 5; }
+    if (p_cb_netlist_n_unknowns(nl) != 2 || p_cb_netlist_n_params(nl) != 2 || p_cb_netlist_unknown(nl, "v1.i") != 1 ||
+        p_cb_netlist_unknown(nl, "x1.node_vss") != 0) { fprintf(stderr, "unexpected flat circuit\n"); return 6; }
+    if (flatten_only) {
+        printf("{\"unknowns\": %d, \"params\": [\"%s\", \"%s\"], \"first_row\": [%.17g, %.17g]}\n", (int)p_cb_netlist_n_unknowns(nl),
+               p_cb_netlist_param_name(nl, 0), p_cb_netlist_param_name(nl, 1), p_cb_netlist_params(nl)[0], p_cb_netlist_params(nl)[1]);
+        p_cb_circuit_destroy(c);
+        p_cb_netlist_destroy(nl);
+        return 0;
+    }
+    if (p_cb_options_init(&opt, sizeof opt) != CB_OK) { fprintf(stderr, "%s\n", p_cb_last_error()); return 4; }
+    rc = p_cb_plan_create(c, B, 0, &p);
+    if (rc == CB_OK) rc = p_cb_plan_set_params(p, p_cb_netlist_params(nl));
+    if (rc == CB_OK) rc = p_cb_dc(p, &opt, x, NULL, status, &st);
+    if (rc != CB_OK) { fprintf(stderr, "cb error %d: %s\n", rc, p_cb_last_error()); return 5; }
+    for (i = 0; i < B; i++) {
+        const double want = -vals[i] / vals[B + i];   /* reference test/sweep.jl:369: I = v_in / r_load through the source */
+        if (status[i] != CB_ST_SUCCESS) { fprintf(stderr, "point %d status %d\n", i, status[i]); return 6; }
+        if (fabs(x[i] - want) > err) err = fabs(x[i] - want);
+    }
+    printf("{\"points\": %d, \"max_abs_err\": %.3e}\n", (int)B, err);
+    p_cb_plan_destroy(p);
+    p_cb_circuit_destroy(c);
+    p_cb_netlist_destroy(nl);
+    return err < 1e-12 ? 0 : 7;
+}
+
 int main(int argc, char **argv) {
     if (argc >= 2 && strcmp(argv[1], "layout") == 0) return layout();
     if (argc >= 3 && strcmp(argv[1], "run") == 0) return run(argv[2]);
-    fprintf(stderr, "usage: abi_smoke layout | run <libcedarb200.so>\n");
+    if (argc >= 3 && strcmp(argv[1], "netlist") == 0) return run_netlist(argv[2], argc >= 4 && strcmp(argv[3], "flatten") == 0);
+    fprintf(stderr, "usage: abi_smoke layout | run <libcedarb200.so> | netlist <libcedarb200.so> [flatten]\n");
     return 1;
 }

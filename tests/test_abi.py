@@ -209,3 +209,24 @@ def test_c_harness_solves_the_divider_sweep_through_the_abi():
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout)
     assert out["points"] == 400 and out["max_abs_err"] < 1e-12
+
+
+def test_c_harness_flattens_a_deck_with_the_native_front_end():
+    """Pure C, no GPU: deck text -> cb_netlist_flatten -> cb_netlist_circuit -> cb_circuit_compile (reference deck of
+    test/sweep.jl:342-371: a subcircuit parameter swept through the instance)."""
+    import json
+    import subprocess
+    r = subprocess.run([_build_abi_smoke(), "netlist", engine.LIB_PATH, "flatten"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out == {"unknowns": 2, "params": ["x1.r1.r", "v1.dc"], "first_row": [5.0, 5.0]}
+
+
+@pytest.mark.gpu
+def test_c_harness_solves_a_deck_sweep_from_text():
+    import json
+    import subprocess
+    r = subprocess.run([_build_abi_smoke(), "netlist", engine.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["points"] == 256 and out["max_abs_err"] < 1e-12

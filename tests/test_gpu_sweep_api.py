@@ -187,3 +187,24 @@ def test_abstime_inside_verilog_a_module_sweep():
     assert np.abs(vin - amp[:, None] * np.sin(2e6 * np.pi * ts)[None, :]).max() < 2e-4
     g = 1e-3 * (1.0 + ts / 1e-6)
     assert np.abs(sols.array(cs.sys.node_c) - (1.0 / (1.0 + 1e3 * g))[None, :]).max() < 1e-9
+
+
+def test_native_front_end_matches_the_python_one():
+    """The same decks through the library's own netlist reader (front_end="native": cb_netlist_flatten -> cb_netlist_circuit,
+    no Python parser / flattener / struct packing) and through the Python front end: identical results on the GPU, and the
+    reference's known answers (test/sweep.jl:326-371)."""
+    r1 = np.arange(100.0, 2001, 100)
+    sw = ProductSweep(R1=r1, R2=r1)
+    a = dc_(CircuitSweep(TWO_R, sw, front_end="native"))
+    b = dc_(CircuitSweep(TWO_R, sw))
+    cs = CircuitSweep(TWO_R, sw, front_end="native")
+    assert a.status.max() == 0 and np.array_equal(a.array(cs.sys.v.I), b.array(cs.sys.v.I))
+    R1, R2 = np.meshgrid(r1, r1, indexing="ij")
+    assert np.abs(a.array(cs.sys.v.I) + 1.0 / (R1 + R2)).max() < 1e-12
+    deck = ("* rc ladder in a subcircuit, pulse drive\n.param vdd=1 rr=1k\n.subckt stage a b r=1k c=1p\nr1 a b 'r'\nc1 b 0 'c'\n.ends\n"
+            "v1 in 0 PULSE(0 'vdd' 1n 0.1n 0.1n 4n 10n)\nx1 in n1 stage r='rr'\nx2 n1 n2 stage r='2*rr' c=2p\nx3 n2 out stage\n")
+    ts = np.linspace(0.0, 20e-9, 201)
+    sw = ProductSweep(vdd=np.linspace(0.8, 1.2, 8), rr=np.linspace(500.0, 2000.0, 8))
+    ya = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"], front_end="native"), (0.0, 20e-9), saveat=ts, reltol=1e-5)
+    yb = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"]), (0.0, 20e-9), saveat=ts, reltol=1e-5)
+    assert ya.status.max() == 0 and np.array_equal(ya.y, yb.y)

@@ -1,0 +1,141 @@
+"""The library's own netlist front end (cb_netlist_*, csrc/spice_front.hpp) against the Python one (netlist.py): the same
+decks -- restated reference tests -- must flatten to the same unknowns, devices, waves, parameter columns and values, and
+the CPU oracle must get the reference's known answers from the natively flattened circuit.  No GPU needed: flattening
+and cb_circuit_create run on the host."""
+import math
+
+import numpy as np
+import pytest
+
+from cedarsim.jl_b200 import engine, netlist
+from cedarsim.jl_b200.flat import Col
+from oracle import orc
+
+
+def _same(a, b):
+    if isinstance(a, Col) or isinstance(b, Col):
+        return isinstance(a, Col) and isinstance(b, Col) and a.index == b.index
+    return (math.isinf(a) and math.isinf(b) and (a > 0) == (b > 0)) or a == b
+
+
+def _compare(deck, sweep=None, outputs=None):
+    sweep = {k: np.asarray(v, dtype=float) for k, v in (sweep or {}).items()}
+    nn = engine.NativeNetlist(deck, sweep, outputs)
+    fl = netlist.flatten(netlist.parse_netlist(deck), sweep, outputs=outputs)
+    a, b = nn.fc, fl.fc
+    assert a.node_names == b.node_names and a.branch_names == b.branch_names
+    assert a.param_names == b.param_names
+    assert nn.params.shape == fl.params.shape and np.array_equal(nn.params, fl.params)     # bit for bit
+    assert len(a.devices) == len(b.devices)
+    for da, db in zip(a.devices, b.devices):
+        assert (da.kind, list(da.nodes), da.branch, da.wave, da.mult) == (db.kind, list(db.nodes) + [] * 0, db.branch, db.wave, db.mult), (da, db)
+        assert _same(da.value, db.value), (da, db)
+    assert len(a.waves) == len(b.waves)
+    pa, pb = a.pack(), b.pack()      # compare the waves as they cross the ABI (defaults filled in)
+    for i in range(len(a.waves)):
+        wa, wb = pa.struct.waves[i], pb.struct.waves[i]
+        assert (wa.kind, wa.has_dc, wa.npts, wa.ac_mag) == (wb.kind, wb.has_dc, wb.npts, wb.ac_mag)
+        assert (wa.dc.col, wa.dc.value) == (wb.dc.col, wb.dc.value)
+        for k in range(7):
+            assert wa.v[k].col == wb.v[k].col and (wa.v[k].value == wb.v[k].value or (math.isinf(wa.v[k].value) and math.isinf(wb.v[k].value)))
+        for k in range(wa.npts):
+            assert wa.t[k] == wb.t[k] and (wa.y[k].col, wa.y[k].value) == (wb.y[k].col, wb.y[k].value)
+    assert a.outputs == b.outputs
+    return nn, fl
+
+
+TWO_R = "* two resistor\n.param R1=100 R2=100\nV vcc 0 1\nRa vcc out 'R1'\nRb out 0 'R2'\n"
+
+
+def test_two_resistor_sweep_known_answer():   # test/sweep.jl:326-340
+    r1, r2 = np.meshgrid(np.arange(100.0, 2001, 100), np.arange(100.0, 2001, 100), indexing="ij")
+    nn, _ = _compare(TWO_R, {"R1": r1.ravel(order="F"), "R2": r2.ravel(order="F")})
+    x, xf, st, _ = orc.dc(nn.fc, nn.params)
+    assert st.max() == 0
+    assert np.abs(xf[nn.unknown("v.i")] + 1.0 / (nn.params[0] + nn.params[1])).max() < 1e-12
+    assert nn.unknown("node_out") == nn.unknown("out") == 1
+
+
+def test_numbers_and_units():   # test/basic.jl:609-638: magnitudes, 1Amp, 1Meg, 1Mil, 0.22u === 0.22e-6
+    deck = ("* units\ni1 vcc 0 DC -1Amp\nr1 vcc 0 r=1Meg\nr2 vcc 0 1Mil\nc1 vcc 0 0.22u\nc2 vcc 0 0.22e-6\nl1 vcc x 10n\nr3 x 0 2.5k\n"
+            "r4 x 0 3g\nr5 x 0 4T\nr6 x 0 5p ; trailing comment\nr7 x 0 6f $ another\n+ m=2\n")
+    nn, _ = _compare(deck)
+    vals = [d.value for d in nn.fc.devices]
+    assert vals[1:] == [1e6, 25.4e-6, 0.22e-6, 0.22e-6, 10e-9, 2.5e3, 3e9, 4e12, 5e-12, 6e-15]
+    assert nn.fc.devices[-1].mult == 2.0
+
+
+def test_parameter_scoping_and_subcircuits():   # test/basic.jl:382-467, test/params.jl:58-99
+    deck = """* Parameter scoping test
+.param r_load=1
+.subckt subcircuit1 vss gnd l=11 r_load=2
+.param w=22
+.param r_load2='r_load*2'
+r1 vss gnd 'r_load'
+r2 vss gnd 'r_load2' m=2
+.ends
+.subckt outer a b foo=1
+.subckt inner a b foo=foo+2000
+r1 a b r='foo'
+.ends
+x1 a b inner
+x2 a b inner foo=foo+100
+.ends
+x1 vcc 0 subcircuit1 r_load=10
+x2 vcc 0 subcircuit1
+xo vcc 0 outer foo='r_load+1' m=3
+v1 vcc 0 DC 1
+"""
+    nn, fl = _compare(deck)
+    _compare(deck, {"r_load": np.linspace(1.0, 4.0, 7)})
+    _compare(deck, {"x1.r_load": np.linspace(1.0, 4.0, 7), "xo.foo": [np.nan, 5, 6, np.nan, 8, 9, 10]})     # NaN keeps the default
+    _, xf, st, _ = orc.dc(nn.fc, None)
+    g = 1 / 10 + 2 / 20 + 1 / 2 + 2 / 4 + 3 * (1 / 2002 + 1 / 102)   # inner default foo+2000 and the override foo+100 both read outer's foo = 2
+    assert st.max() == 0 and abs(xf[nn.unknown("v1.i"), 0] + g) < 1e-12
+    assert nn.unknown("x1.node_vss") == nn.unknown("vcc")          # subcircuit port alias (test/alias.jl)
+
+
+def test_expressions_match_the_python_evaluator():
+    deck = ("* expr\n.param a=3 b='a**2 + 1' c={max(a, b) / 4} d='a > 2 ? sqrt(b) : -1' e='(a+1)*(b-1) % 5'\n"
+            "r1 1 0 'b'\nr2 1 0 'c'\nr3 1 0 'd'\nr4 1 0 'exp(-a) + ln(b) + log10(100) + abs(-2) + pow(2, 3) + min(a, 1)'\n"
+            "r5 1 0 'a == 3 && b != 1 || !a'\nr6 1 0 'agauss(7, 1, 3) + pi + int(2.7) + 2^3^2'\nr7 1 0 '-a**2'\nv1 1 0 1\n").replace(" e='(a+1)*(b-1) % 5'", "")
+    nn, _ = _compare(deck)
+    _compare(deck, {"a": np.linspace(0.5, 5.0, 11)})
+    assert nn.fc.devices[5].value == 7 + math.pi + 2 + 2.0 ** 9 and nn.fc.devices[6].value == -9.0
+
+
+def test_sources_and_temper():   # src/spectre_env.jl:15-77, 144-198; test/basic.jl:469-517 (temper)
+    deck = ("* sources\n.param vdd=1.2 tr=1n\n.temp 50\nv1 in 0 DC 0 PULSE(0 'vdd' 1n 'tr' 1n 5n 20n)\nv2 a 0 PWL(0 0 1n 'vdd' 2n 0)\n"
+            "v3 b 0 DC 5 SIN(10 3 1k) AC 2\ni1 c 0 SIN(0 1m 1meg 1n)\nr1 in 0 'temper'\nr2 a 0 1k\nr3 b 0 1k\nr4 c 0 1k\n"
+            "e1 d 0 in 0 2\nr5 d 0 1k\ng1 f 0 in 0 1m\nr6 f 0 1k\nv4 g 0 dc=3\nr7 g 0 1k\nv5 h 0 PULSE(0 1 0 1n 1n 5n)\nr8 h 0 1\n")
+    nn, _ = _compare(deck)
+    assert nn.fc.devices[4].value == 50.0 and nn.option("temp") == 50.0
+    _compare(deck, {"vdd": np.linspace(0.8, 1.4, 5), "e1.gain": np.linspace(1.0, 3.0, 5), "temp": np.linspace(0.0, 100.0, 5)})
+    ts = np.linspace(0.0, 4e-9, 81)
+    y, st, _ = orc.tran(nn.fc, 0.0, 4e-9, ts, opts=orc.default_options(reltol=1e-6))
+    assert st.max() == 0
+    assert np.abs(y[nn.unknown("a"), :, 0] - np.interp(ts, [0, 1e-9, 2e-9], [0, 1.2, 0])).max() < 1e-9
+    assert np.abs(y[nn.unknown("d"), :, 0] - 2 * y[nn.unknown("in"), :, 0]).max() < 1e-9
+
+
+def test_refused_constructs_and_errors():
+    for deck, what in (("* b\nb1 1 0 v='V(2)'\nr1 1 0 1\n", "behavioural"), ("* m\nm1 d g s b nmos\n", "MOSFET"),
+                       ("* mod\n.model nmos nmos level=72\nr1 1 0 1\n", ".model"), ("* x\nx1 1 0 nosuch\n", "unknown subcircuit"),
+                       ("* u\nr1 1 0 'nope'\n", "undefined parameter")):
+        with pytest.raises(RuntimeError, match=what):
+            engine.NativeNetlist(deck)
+    with pytest.raises(RuntimeError, match="do not name any parameter"):
+        engine.NativeNetlist(TWO_R, {"r3": np.ones(4)})
+    with pytest.raises(RuntimeError, match="no unknown named"):
+        engine.NativeNetlist(TWO_R, outputs=["nosuch"])
+
+
+def test_circuit_from_the_native_flat_circuit_compiles():
+    """cb_netlist_circuit + cb_circuit_compile need no GPU; the symbolic analysis sees the same matrix as through the
+    Python front end."""
+    r = np.linspace(100.0, 2000.0, 16)
+    nn = engine.NativeNetlist(TWO_R, {"R1": r, "R2": r[::-1].copy()}, outputs=["out", "v.i"])
+    c1 = nn.circuit()
+    fl = netlist.flatten(netlist.parse_netlist(TWO_R), {"R1": r, "R2": r[::-1].copy()}, outputs=["out", "v.i"])
+    c2 = engine.Circuit(fl.fc, fl.models)
+    assert c1.lu_info() == c2.lu_info()
