@@ -1696,7 +1696,8 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     auto vargs = [&](int par, size_t m) { return (void*)vargs_store[par][m].b; };
     auto vargs_v = [&](int par, size_t m) { return (void*)vargs_v_store[par][m].b; };
     // The control step as the tail of k_lu (kernels.cuh, k_lu<.., true>) instead of a k_control launch per round
-    // (off by default: measured 2.7x SLOWER, profiles/probe_r2o.log -- see DESIGN.md section 4; CB_FUSE=1 selects it)
+    // (off by default: measured 2.7x SLOWER because the lists lose their runs of consecutive points, profiles/probe_r2o.log,
+    // ncu_lu_fused_r2v.json -- see DESIGN.md section 4; CB_FUSE=1 selects it)
     bool fused = false;
     if (const char* e = std::getenv("CB_FUSE")) fused = p->lu && std::atoi(e) != 0;
     // Round r reads list buffer r % 3 and fills buffer (r + 1) % 3; its k_lu zeroes the counters of the buffer that is

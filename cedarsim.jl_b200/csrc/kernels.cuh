@@ -90,9 +90,9 @@ struct NArgs {
 };
 
 // IEEE division as ONE out-of-line body (~40 instructions with its slow path) instead of ~25 inlined instructions at each
-// of the ~70 division sites of the control step: that code is mostly straight-line and every CTA walks it once, so at
-// small batches (one CTA per SM, code evicted between rounds by the 300 KB eval kernels) its time is instruction fetch,
-// not arithmetic.  Same result bit for bit.
+// of the ~70 division sites of the control step, no unrolling of its loops, out-of-line waveform / interpolation helpers:
+// k_control shrinks from 7.8 k to 4.6 k SASS instructions.  Same results bit for bit; measured flat in time at 2 048 and
+// 16 384 points (profiles/probe_r2u.log) -- kept for the smaller footprint, -DCB_CTRL_SMALL_CODE=0 restores the inlined form.
 #ifndef CB_CTRL_SMALL_CODE
 #define CB_CTRL_SMALL_CODE 1
 #endif
@@ -950,6 +950,12 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
 //   shared memory -- no k_control launch, no DX / QK / RMAX / DVMAX / BAD round trip through HBM.  Idle points of the
 //   lock-step schedule are visited through a third list.  The counters zeroed here are those of the round after next
 //   (three rotating list buffers), because this kernel itself fills the next round's.
+//   Parity-green and 2.7x SLOWER (profiles/probe_r2o.log; ncu profiles/ncu_lu_fused_r2v.json): the groups then append
+//   their points to the next lists in GROUP order, and after a few rounds of points moving between the full / value-only /
+//   idle lists a group's 32 entries come from many different 32-point blocks -- every row access of k_lu and of the eval
+//   kernels (base + inst * 8 bytes per lane) touches 17 sectors per request instead of 4.4.  The stand-alone k_control
+//   walks the points in instance order every round and so re-establishes runs of consecutive points; that ordered
+//   compaction is what fusion gives up.  Off by default (CB_FUSE=1).
 template <bool STAGED, bool FUSED>
 __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
     extern __shared__ __align__(16) double vals_[];
