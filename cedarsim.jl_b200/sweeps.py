@@ -588,18 +588,66 @@ class CircuitSweep:
         return results
 
 
-def dc_(cs: CircuitSweep, **kw) -> SweepSolution:
-    """dc!(cs): DC operating point of every sweep point."""
+# Host retry policy for the points a batched solve leaves unconverged (the reference's CedarDCOp
+# restarts a failed initialisation up to ten times with a more robust algorithm, src/dcop.jl:53-94): the failed points
+# alone are solved again as a small batch of their own, with progressively more patient options -- longer gmin / source
+# stepping ladders and a tighter Newton step limit for the operating point, plain full Newton (no rate test, no chord
+# iterations) and more iterations per step for the transient, finally backward Euler.  Points that converge on a rung
+# replace their entries; the others keep their status code.  `retry=False` switches it off, `retry=[dict, ...]` gives
+# another ladder.
+RETRY_LADDER = (
+    dict(gmin_steps=20, source_steps=40, max_newton_dc=400, dv_max=0.25, nr_rate_test=0, value_rounds=0, max_newton_tran=50),
+    dict(gmin_steps=20, source_steps=100, max_newton_dc=1000, dv_max=0.1, nr_rate_test=0, value_rounds=0, max_newton_tran=100,
+         method=0),
+)
+
+
+def _retry_failed(cs: CircuitSweep, kw: dict, retry, solve, y: np.ndarray, status: np.ndarray, stats: dict, point_axis: int):
+    """solve(plan, opts) -> (y_sub with the points on `point_axis`, status_sub).  Mutates y / status / stats in place."""
+    ladder = RETRY_LADDER if retry is True else tuple(retry or ())
+    stats["retried_points"] = stats["recovered_points"] = 0
+    for rung in ladder:
+        failed = np.flatnonzero(status != 0)
+        if failed.size == 0:
+            break
+        stats["retried_points"] = max(stats["retried_points"], int(failed.size))
+        opts = cs._options(dict(kw, **rung))
+        plan = cs._compiled.plan(int(failed.size), devices=[cs.devices[0]])
+        try:
+            P = cs.flat.params
+            plan.set_params(np.ascontiguousarray(P[:, failed]) if P.size else None)
+            plan.set_x0(cs.x0 if cs.x0 is None or cs.x0.ndim == 1 else np.ascontiguousarray(cs.x0[:, failed]))
+            y_sub, st_sub = solve(plan, opts)
+        finally:
+            plan.close()
+        ok = st_sub == 0
+        if ok.any():
+            idx = [slice(None)] * y.ndim
+            idx[point_axis] = failed[ok]
+            sub = [slice(None)] * y.ndim
+            sub[point_axis] = np.flatnonzero(ok)
+            y[tuple(idx)] = y_sub[tuple(sub)]
+            status[failed[ok]] = 0
+            stats["recovered_points"] += int(ok.sum())
+
+
+def dc_(cs: CircuitSweep, retry=True, **kw) -> SweepSolution:
+    """dc!(cs): DC operating point of every sweep point.  retry: see RETRY_LADDER."""
     opts = cs._options(kw)
     res = cs._run(lambda plan: plan.dc(opts, want_full=False))
     y = np.concatenate([r[0] for r in res], axis=1)
     status = np.concatenate([r[2] for r in res])
     stats = _merge_stats([r[3] for r in res])
+    if retry and status.any():
+        def solve(plan, o):
+            r = plan.dc(o, want_full=False)
+            return r[0], r[2]
+        _retry_failed(cs, kw, retry, solve, y, status, stats, point_axis=1)
     return SweepSolution(cs, y, status, stats, None)
 
 
-def tran_(cs: CircuitSweep, tspan: Optional[Tuple[float, float]] = None, saveat=None, **kw) -> SweepSolution:
-    """tran!(cs, tspan): transient of every sweep point from its DC operating point."""
+def tran_(cs: CircuitSweep, tspan: Optional[Tuple[float, float]] = None, saveat=None, retry=True, **kw) -> SweepSolution:
+    """tran!(cs, tspan): transient of every sweep point from its DC operating point.  retry: see RETRY_LADDER."""
     if tspan is None:
         if cs.flat.tran is None:
             raise ValueError("no tspan given and the netlist has no .tran card")
@@ -615,7 +663,13 @@ def tran_(cs: CircuitSweep, tspan: Optional[Tuple[float, float]] = None, saveat=
     res = cs._run(lambda plan: plan.tran(t0, t1, saveat, opts))
     y = np.concatenate([r[0] for r in res], axis=2)
     status = np.concatenate([r[1] for r in res])
-    return SweepSolution(cs, y, status, _merge_stats([r[2] for r in res]), saveat)
+    stats = _merge_stats([r[2] for r in res])
+    if retry and status.any():
+        def solve(plan, o):
+            r = plan.tran(t0, t1, saveat, o)
+            return r[0], r[1]
+        _retry_failed(cs, kw, retry, solve, y, status, stats, point_axis=2)
+    return SweepSolution(cs, y, status, stats, saveat)
 
 
 class FreqSolution:

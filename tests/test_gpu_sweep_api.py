@@ -208,3 +208,24 @@ def test_native_front_end_matches_the_python_one():
     ya = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"], front_end="native"), (0.0, 20e-9), saveat=ts, reltol=1e-5)
     yb = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"]), (0.0, 20e-9), saveat=ts, reltol=1e-5)
     assert ya.status.max() == 0 and np.array_equal(ya.y, yb.y)
+
+
+def test_failed_points_are_retried_by_the_host_ladder(tmp_path):
+    """Host retry policy (sweeps.RETRY_LADDER; the reference restarts a failed CedarDCOp initialisation, src/dcop.jl:53-94):
+    with three Newton iterations and no gmin / source stepping most operating points of a diode behind a resistor fail;
+    the failed points alone are solved again with the patient options and end on the implicit solution."""
+    (tmp_path / "dio.va").write_text('`include "disciplines.vams"\nmodule dio(p, n);\n    inout p, n;\n    electrical p, n;\n'
+                                     '    parameter real is = 1e-14;\n    analog begin\n        I(p, n) <+ is * (limexp(V(p, n) / 0.025852) - 1.0);\n'
+                                     '    end\nendmodule\n')
+    text = f"* diode\n.hdl \"{tmp_path / 'dio.va'}\"\n.param vin=1\nV1 in 0 'vin'\nR1 in d 1k\nX1 d 0 dio\n"
+    vin = np.linspace(0.2, 5.0, 64)
+    hard = dict(max_newton_dc=3, gmin_steps=0, source_steps=0)
+    raw = dc_(CircuitSweep(text, Sweep("vin", vin), outputs=["d"]), retry=False, **hard)
+    assert (raw.status != 0).sum() > 16                       # the first pass alone leaves failures
+    cs = CircuitSweep(text, Sweep("vin", vin), outputs=["d"])
+    sols = dc_(cs, **hard)
+    assert sols.status.max() == 0 and sols.stats["recovered_points"] == (raw.status != 0).sum()
+    vd = sols.array(cs.sys.node_d)
+    assert np.abs((vin - vd) / 1e3 - 1e-14 * (np.exp(vd / 0.025852) - 1.0)).max() < 1e-9      # KCL at the diode node
+    ok = raw.status == 0
+    assert np.array_equal(vd[ok], raw.array(cs.sys.node_d)[ok])                                 # converged points are untouched
