@@ -19,9 +19,11 @@
 //     device values, `temp`; every value that differs between sweep points becomes one column of params[P][B]
 //     (what ParamSim makes a runtime parameter, src/circuitodesystem.jl:66-97), a NaN entry keeps the default
 //     (`nothing` in a SerialSweep, src/sweeps.jl:18-21).
+//   * `.if` / `.elseif` / `.else` / `.endif` on constant top-level parameters, `.lib` sections (`.lib name` ... `.endl`,
+//     `.lib "file" name`, also from the file itself, test/basic.jl:312-336), `.model` cards of resistors
+//     (r = rsh (l - short) / (w - narrow), src/simpledevices.jl:62-70).
 // Not here (the decks that need them go through the Python host, which also owns the Verilog-A compiler): behavioural
-// sources, MOSFET / Verilog-A instances, `.model` cards, `.lib` sections, `.if` blocks, Spectre syntax.  They are refused
-// with a message, never skipped.
+// sources, MOSFET / Verilog-A instances (`.hdl`), Spectre syntax.  They are refused with a message, never skipped.
 //
 // Host-only code; depends on include/cedarb200.h alone.
 #pragma once
@@ -500,6 +502,8 @@ struct Subckt {
 struct Netlist {
     Subckt top;
     KV options;
+    std::map<std::string, std::map<std::string, double>> models;   // .model cards: name -> numeric parameters (lower-case keys)
+    std::map<std::string, std::string> model_master;               // name -> master (r, c, nmos, ...)
 };
 
 static Source parse_source(const std::vector<std::string>& toks, size_t from) {
@@ -547,9 +551,10 @@ static Card parse_card(const std::vector<std::string>& toks) {
         if (pos.size() > 2) {
             const std::string& v = pos[2];
             if ((std::isalpha((unsigned char)v[0]) || v[0] == '_')) {
-                // `R2 vcc 0 res`: a bare identifier is a parameter here (test/basic.jl:725-737); model cards are not read natively
-                c.has_value = true; c.value = v;
-                if (pos.size() > 3) throw unsupported("model-card resistors / capacitors");
+                // a bare identifier: a model name (`R1 a b rmod l=2u w=1u`), or a parameter (`R2 vcc 0 res`, test/basic.jl:725-737)
+                // -- decided when the circuit is flattened; an optional value may follow the model name
+                c.model = lower(v);
+                if (pos.size() > 3) { c.has_value = true; c.value = pos[3]; }
             } else { c.has_value = true; c.value = v; }
         }
         return c;
@@ -587,14 +592,61 @@ static Card parse_card(const std::vector<std::string>& toks) {
     throw Error("unsupported device card '" + toks[0] + "'");
 }
 
-static void parse_into(Netlist& nl, const std::string& text, bool first_is_title, const std::string& base_dir, int depth) {
+// values of the top-level parameters that are constants (for `.if` conditions, evaluated while reading like the reference)
+static Val const_env_eval(Netlist& nl, const std::string& text) {
+    Scope sc;
+    for (auto& p : nl.top.params) {
+        try {
+            Scope one;
+            one.values = sc.values;
+            sc.values[p.first] = one.eval(p.second);
+        } catch (const Error&) {}
+    }
+    return sc.eval(text);
+}
+
+// lib_section: empty = an ordinary file; else only the `.lib <name>` ... `.endl` section of that name is read
+static void parse_into(Netlist& nl, const std::string& text, bool first_is_title, const std::string& base_dir, int depth,
+                       const std::string& lib_section = std::string()) {
     if (depth > 16) throw Error(".include nesting too deep");
     std::vector<Subckt*> stack{&nl.top};
+    std::vector<char> cond_stack, cond_taken;   // .if nesting: is the current branch live / has any branch been live
+    std::string in_lib;                         // name of the `.lib` section being defined here, if any
+    bool in_lib_def = false;
     for (const std::string& line : logical_lines(text, first_is_title)) {
         const std::vector<std::string> toks = tokens(line);
         if (toks.empty()) continue;
         const std::string head = lower(toks[0]);
         Subckt* cur = stack.back();
+        auto unquote = [](std::string f) {
+            if (f.size() >= 2 && std::strchr("'\"", f.front())) f = f.substr(1, f.size() - 2);
+            return f;
+        };
+        if (head == ".lib" && toks.size() == 2) { in_lib = lower(unquote(toks[1])); in_lib_def = true; continue; }   // section definition
+        if (head == ".endl") { in_lib_def = false; in_lib.clear(); continue; }
+        // a section is inert where it is defined and is read only through `.lib "file" name` (also from the file itself)
+        if (lib_section.empty() ? in_lib_def : (!in_lib_def || in_lib != lib_section)) continue;
+        if (head == ".if" || head == ".elseif" || head == ".else" || head == ".endif") {
+            std::string cond;   // from the raw line: the card tokenizer splits `==`
+            {
+                size_t k = 0;
+                while (k < line.size() && std::isspace((unsigned char)line[k])) k++;
+                while (k < line.size() && !std::isspace((unsigned char)line[k]) && line[k] != '(') k++;
+                cond = line.substr(k);
+            }
+            auto truth = [&]() { const Val v = const_env_eval(nl, cond); return v.v[0] != 0.0; };
+            if (head == ".if") { cond_stack.push_back(truth()); cond_taken.push_back(cond_stack.back()); }
+            else if (cond_stack.empty()) throw Error(head + " without .if");
+            else if (head == ".else") { cond_stack.back() = !cond_taken.back(); cond_taken.back() = 1; }
+            else if (head == ".elseif") { cond_stack.back() = !cond_taken.back() && truth(); cond_taken.back() = cond_taken.back() || cond_stack.back(); }
+            else { cond_stack.pop_back(); cond_taken.pop_back(); }
+            continue;
+        }
+        {
+            bool live = true;
+            for (char c : cond_stack) live = live && c;
+            if (!live) continue;
+        }
         if (head[0] == '.') {
             if (head == ".param" || head == ".parameter" || head == ".parameters") {
                 std::vector<std::string> pos;
@@ -621,10 +673,10 @@ static void parse_into(Netlist& nl, const std::string& text, bool first_is_title
                 stack.push_back(sub.get());
             } else if (head == ".ends") {
                 if (stack.size() > 1) stack.pop_back();
-            } else if (head == ".include" || head == ".inc") {
-                if (toks.size() < 2) throw Error(".include without a file name");
-                std::string fname = toks[1];
-                if (fname.size() >= 2 && std::strchr("'\"", fname.front())) fname = fname.substr(1, fname.size() - 2);
+            } else if (head == ".include" || head == ".inc" || head == ".lib") {
+                if (toks.size() < 2) throw Error(head + " without a file name");
+                std::string fname = unquote(toks[1]);
+                const std::string section = (head == ".lib" && toks.size() > 2) ? lower(unquote(toks[2])) : std::string();
                 if (lower(fname).compare(0, 8, "jlpkg://") == 0) throw Error("package include " + fname + " is handled by the Python front end");
                 const std::string path = (!fname.empty() && fname[0] == '/') ? fname : (base_dir.empty() ? fname : base_dir + "/" + fname);
                 std::ifstream f(path);
@@ -632,7 +684,7 @@ static void parse_into(Netlist& nl, const std::string& text, bool first_is_title
                 std::stringstream ss;
                 ss << f.rdbuf();
                 const size_t slash = path.find_last_of('/');
-                parse_into(nl, ss.str(), false, slash == std::string::npos ? std::string() : path.substr(0, slash), depth + 1);
+                parse_into(nl, ss.str(), false, slash == std::string::npos ? std::string() : path.substr(0, slash), depth + 1, section);
             } else if (head == ".option" || head == ".options") {
                 std::vector<std::string> pos;
                 split_params(toks, 1, pos, nl.options);
@@ -642,8 +694,25 @@ static void parse_into(Netlist& nl, const std::string& text, bool first_is_title
                     for (auto& q : nl.options) if (q.first == "temp") { q.second = toks[1]; found = true; }
                     if (!found) nl.options.push_back({"temp", toks[1]});
                 }
-            } else if (head == ".model" || head == ".hdl" || head == ".lib" || head == ".endl" || head == ".if" || head == ".elseif" ||
-                       head == ".else" || head == ".endif") {
+            } else if (head == ".model") {
+                // `.model name master (k=v ...)`: numeric parameters are kept (resistor geometry cards); device models that
+                // need generated code are refused where an instance uses them
+                std::vector<std::string> flat, pos;
+                for (size_t q = 1; q < toks.size(); q++) if (toks[q] != "(" && toks[q] != ")" && toks[q] != ",") flat.push_back(toks[q]);
+                KV kv;
+                split_params(flat, 0, pos, kv);
+                if (pos.size() < 2) throw Error(".model needs a name and a master");
+                const std::string name = lower(pos[0]);
+                nl.model_master[name] = lower(pos[1]);
+                std::map<std::string, double>& mp = nl.models[name];
+                for (auto& q : kv) {
+                    try {
+                        Scope empty;
+                        const Val v = empty.eval(q.second);
+                        mp[q.first] = v.v[0];
+                    } catch (const Error&) {}   // not a constant: left to the (absent) parameter scope, like the Python reader's card.exprs
+                }
+            } else if (head == ".hdl") {
                 throw Error(head + " cards are handled by the Python front end (netlist.py), not by the native reader");
             }
             // every other dot-card is ignored, as the reference warns and continues (src/spectre.jl:1520-1522)
@@ -835,7 +904,7 @@ class Flattener {
             const std::string name = prefix + card.name;
             std::vector<std::string> onames;
             for (auto& p : card.params) onames.push_back(p.first);
-            for (const char* s : {"r", "c", "l", "dc", "gain", "m"}) onames.push_back(s);
+            for (const char* s : {"r", "c", "l", "dc", "gain", "w", "nfin", "m"}) onames.push_back(s);
             const std::map<std::string, Val> over = overrides(name + ".", onames);
             auto par = [&](const std::string& key, Val& out) -> bool {
                 auto it = over.find(key);
@@ -857,9 +926,31 @@ class Flattener {
                 if (over.count(key)) { v = over.at(key); have = true; }
                 else if (card.has_value) { v = scope.eval(card.value); have = true; }
                 else have = par(key, v);
+                if (!have && !card.model.empty() && !nl.models.count(card.model)) {
+                    v = scope.eval(card.model);   // `R2 vcc 0 res`: a bare identifier that is a parameter, not a model
+                    have = true;
+                }
+                if (!have && k == 'r' && !card.model.empty()) {
+                    // model card / geometry: r = rsh (l - short) / (w - narrow)  (src/simpledevices.jl:62-70)
+                    const std::map<std::string, double>& mp = nl.models.at(card.model);
+                    auto g = [&](const char* key2, double d) -> Val {
+                        Val x;
+                        if (par(key2, x)) return x;
+                        auto it = mp.find(key2);
+                        return Val(it == mp.end() ? d : it->second);
+                    };
+                    if (mp.count("r")) v = Val(mp.at("r"));
+                    else {
+                        const Val num = map2(g("rsh", 50.0), map2(g("l", 1e-6), g("short", 0.0), [](double a, double b) { return a - b; }),
+                                             [](double a, double b) { return a * b; });
+                        v = map2(num, map2(g("w", 1e-6), g("narrow", 0.0), [](double a, double b) { return a - b; }),
+                                 [](double a, double b) { return a / b; });
+                    }
+                    have = true;
+                }
                 if (!have) {
                     if (k == 'c') v = Val(1.0);
-                    else throw Error(name + ": no value (model-card geometry is handled by the Python front end)");
+                    else throw Error(name + ": no value");
                 }
                 add_dev(k == 'r' ? CB_DEV_R : k == 'c' ? CB_DEV_C : CB_DEV_L, name, nodes, fc.value(name + "." + key, v), -1, mult, k == 'l');
             } else if (k == 'v' || k == 'i') {
