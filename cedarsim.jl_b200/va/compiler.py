@@ -2239,9 +2239,109 @@ def _lower_abstime(mod: Module) -> Module:
     return m2
 
 
+def _lower_switch_branches(mod: Module) -> Module:
+    """A branch that receives BOTH `V(a,b) <+` and `I(a,b) <+` contributions (a switch branch): the kind of the LAST
+    contribution executed decides what the branch is, and a contribution of the other kind discards what was
+    accumulated before (the reference resets its accumulator when the kind changes, src/vasim.jl:149-154, 172-177).
+    Lowered here, before code generation, to constructs the generator already has: per switch branch an integer mode
+    (0 none, 1 voltage, 2 current) and two real accumulators are ordinary module variables, every contribution becomes
+
+        if (mode != KIND) begin acc_KIND = 0; mode = KIND; end   acc_KIND = acc_KIND + (expr);
+
+    and one contribution at the end of the analog block closes the branch through its own current unknown:
+
+        I(a,b) <+ I(a,b) - ((mode == 1) ? V(a,b) - acc_v : I(a,b) - acc_i);
+
+    i.e. the row of the branch current reads  V(a,b) - acc_v = 0  in voltage mode and  I(a,b) - acc_i = 0  otherwise
+    (I = 0 when no contribution ran, the LRM's unassigned branch).  The mode may depend on run-time parameters -- one
+    sweep can hold points of both kinds.  ddt() inside a contribution to a switch branch is not supported."""
+    import copy
+
+    def nodes_of(nodes):
+        nodes = list(nodes)
+        if len(nodes) == 1 and nodes[0] in mod.branches:
+            nodes = list(mod.branches[nodes[0]])
+        g = lambda n: "0" if n in ("0", "gnd") else n
+        return (g(nodes[0]), g(nodes[1]) if len(nodes) > 1 else "0")
+
+    kinds: Dict[Tuple[str, str], Set[str]] = {}
+
+    def scan(x):
+        if isinstance(x, tuple):
+            if len(x) >= 4 and x[0] == "contrib" and x[1] in ("V", "potential", "I", "flow"):
+                a, b = nodes_of(x[2])
+                key = (a, b) if (a, b) in kinds or (b, a) not in kinds else (b, a)
+                kinds.setdefault(key, set()).add("V" if x[1] in ("V", "potential") else "I")
+            for y in x:
+                scan(y)
+        elif isinstance(x, list):
+            for y in x:
+                scan(y)
+        elif isinstance(x, dict):
+            for y in x.values():
+                scan(y)
+
+    scan(list(mod.analog))
+    switches = {k: i for i, k in enumerate(sorted(k for k, v in kinds.items() if len(v) == 2))}
+    if not switches:
+        return mod
+
+    def has_ddt(e) -> bool:
+        if isinstance(e, tuple):
+            if len(e) >= 2 and e[0] == "call" and e[1] in ("ddt", "idt"):
+                return True
+            return any(has_ddt(y) for y in e)
+        if isinstance(e, list):
+            return any(has_ddt(y) for y in e)
+        return False
+
+    num = lambda v: ("num", v, isinstance(v, int))
+
+    def rewrite(x):
+        if isinstance(x, tuple):
+            if len(x) >= 4 and x[0] == "contrib" and x[1] in ("V", "potential", "I", "flow"):
+                a, b = nodes_of(x[2])
+                key, sign = ((a, b), 1.0) if (a, b) in switches else (((b, a), -1.0) if (b, a) in switches else (None, 1.0))
+                if key is not None:
+                    if has_ddt(x[3]):
+                        raise VACompileError(f"ddt() in a contribution to the switch branch ({a}, {b}) is not supported")
+                    k = switches[key]
+                    is_v = x[1] in ("V", "potential")
+                    mode, acc = f"sw{k}__m", f"sw{k}__{'v' if is_v else 'i'}"
+                    e = x[3] if sign > 0 else ("un", "-", x[3])
+                    kind = 1 if is_v else 2
+                    return ("block", None, [
+                        ("if", ("bin", "!=", ("var", mode), num(kind)),
+                         ("block", None, [("assign", acc, num(0.0)), ("assign", mode, num(kind))], {}), None),
+                        ("assign", acc, ("bin", "+", ("var", acc), e))], {})
+            return tuple(rewrite(y) for y in x)
+        if isinstance(x, list):
+            return [rewrite(y) for y in x]
+        if isinstance(x, dict):
+            return {kk: rewrite(v) for kk, v in x.items()}
+        return x
+
+    m2 = copy.copy(mod)
+    m2.var_types = dict(mod.var_types)
+    head, tail = [], []
+    for (a, b), k in switches.items():
+        for nm, ty in ((f"sw{k}__m", "integer"), (f"sw{k}__v", "real"), (f"sw{k}__i", "real")):
+            if nm in m2.var_types:
+                raise VACompileError(f"variable name {nm} is reserved")
+            m2.var_types[nm] = ty
+        head += [("assign", f"sw{k}__m", num(0)), ("assign", f"sw{k}__v", num(0.0)), ("assign", f"sw{k}__i", num(0.0))]
+        nodes = [a] if b == "0" else [a, b]
+        ibr, vbr = ("probe", "I", list(nodes)), ("probe", "V", list(nodes))
+        row = ("cond", ("bin", "==", ("var", f"sw{k}__m"), num(1)), ("bin", "-", vbr, ("var", f"sw{k}__v")),
+               ("bin", "-", ibr, ("var", f"sw{k}__i")))
+        tail.append(("contrib", "I", list(nodes), ("bin", "-", ibr, row)))
+    m2.analog = head + rewrite(list(mod.analog)) + tail
+    return m2
+
+
 def compile_module(mod: Module, name: Optional[str] = None, const_params=None, runtime_params=None,
                    probe_branches=()) -> CompiledModel:
-    mod = _lower_abstime(mod)
+    mod = _lower_switch_branches(_lower_abstime(mod))
     full = _Compiler(mod, name or mod.name, const_params, runtime_params, probe_branches=probe_branches)
     cm = full.compile()
     try:

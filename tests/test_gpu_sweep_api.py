@@ -229,3 +229,19 @@ def test_failed_points_are_retried_by_the_host_ladder(tmp_path):
     assert np.abs((vin - vd) / 1e3 - 1e-14 * (np.exp(vd / 0.025852) - 1.0)).max() < 1e-9      # KCL at the diode node
     ok = raw.status == 0
     assert np.array_equal(vd[ok], raw.array(cs.sys.node_d)[ok])                                 # converged points are untouched
+
+
+def test_switch_branch_sweep_holds_both_kinds():
+    """Switch branch (va/compiler.py _lower_switch_branches) on the GPU: the same device is a voltage source at some sweep
+    points and a conductance at others; DC and a transient with a capacitor across it."""
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = '* switch\n.hdl "switch_branch.va"\nv1 in 0 2\nr1 in out 1k\nc1 out 0 1n\nxs out 0 va_switch mode=0 v0=0.5 r=3k\n'
+    cs = CircuitSweep(deck, ProductSweep(**{"xs.mode": [0.0, 1.0], "xs.v0": np.linspace(0.2, 1.8, 16)}), outputs=["out"], include_dirs=[inc])
+    sols = dc_(cs)
+    assert sols.status.max() == 0
+    out = sols.array(cs.sys.node_out)                           # (2, 16)
+    assert np.abs(out[0] - 1.5).max() < 1e-12 and np.abs(out[1] - np.linspace(0.2, 1.8, 16)).max() < 1e-12
+    ts = np.linspace(0.0, 5e-6, 51)
+    tr = tran_(cs, (0.0, 5e-6), saveat=ts, reltol=1e-6)
+    assert tr.status.max() == 0 and np.abs(tr.array(cs.sys.node_out) - out[:, :, None]).max() < 1e-9     # starts and stays at the operating point

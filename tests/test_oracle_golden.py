@@ -441,3 +441,20 @@ def test_abstime_inside_verilog_a_modules():
     assert np.abs(y[fc.unknown("in"), :, 0] - 2.0 * np.sin(2e6 * np.pi * ts)).max() < 1e-4
     g = 1e-3 * (1.0 + ts / 1e-6)
     assert np.abs(y[fc.unknown("c"), :, 0] - 1.0 / (1.0 + 1e3 * g)).max() < 1e-9      # divider 1k against 1 / g(t): algebraic, exact
+
+
+def test_switch_branch_voltage_or_current_by_parameter():
+    """A branch that receives both `V() <+` and `I() <+` contributions (switch branch; the reference resets its accumulator
+    when the kind changes, src/vasim.jl:149-154): the last kind executed decides, earlier contributions of the other kind
+    are discarded, contributions of one kind accumulate.  The mode is a run-time parameter: one sweep holds both kinds."""
+    import os
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "va")
+    deck = '* switch\n.hdl "switch_branch.va"\nv1 in 0 2\nr1 in out 1k\nxs out 0 va_switch mode=0 v0=0.5 r=3k\n'
+    mode = np.array([0.0, 1.0, 0.0, 1.0])
+    v0 = np.array([0.5, 0.5, 1.5, 1.5])
+    fl = netlist.flatten(netlist.parse_netlist(deck, include_dirs=[inc]), {"xs.mode": mode, "xs.v0": v0}, host=True)
+    _, xf, st, _ = orc.dc(fl.fc, fl.params)
+    assert st.max() == 0
+    assert np.abs(xf[fl.fc.unknown("out")] - np.where(mode > 0.5, v0, 2.0 * 3e3 / 4e3)).max() < 1e-12
+    i_br = xf[fl.fc.unknown("xs.i(p,n)")]                       # the branch current is an unknown of the device in both modes
+    assert np.abs(i_br - (2.0 - xf[fl.fc.unknown("out")]) / 1e3).max() < 1e-12
