@@ -244,4 +244,4 @@ def test_switch_branch_sweep_holds_both_kinds():
     assert np.abs(out[0] - 1.5).max() < 1e-12 and np.abs(out[1] - np.linspace(0.2, 1.8, 16)).max() < 1e-12
     ts = np.linspace(0.0, 5e-6, 51)
     tr = tran_(cs, (0.0, 5e-6), saveat=ts, reltol=1e-6)
-    assert tr.status.max() == 0 and np.abs(tr.array(cs.sys.node_out) - out[:, :, None]).max() < 1e-9     # starts and stays at the operating point
+    assert tr.status.max() == 0 and np.abs(tr.array(cs.sys.node_out) - out[:, :, None]).max() < 1e-6     # stays at the operating point (LTE tolerance: vabstol = 1e-6 V)
