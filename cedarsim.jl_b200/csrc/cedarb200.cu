@@ -250,15 +250,16 @@ struct Reader {
 }  // namespace
 
 // ---- native netlist front end (spice_front.hpp): deck text + sweep values -> flat circuit + params[P][B] ----------------
-extern "C" int cb_netlist_flatten(const char* text, const char* base_dir, const char* const* sweep_names, int n_sweep,
-                                  const double* sweep_values, int64_t n_inst, const char* const* output_names, int n_outputs,
-                                  cb_netlist** out) {
+static int netlist_flatten(bool spectre, const char* text, const char* base_dir, const char* const* sweep_names, int n_sweep,
+                           const double* sweep_values, int64_t n_inst, const char* const* output_names, int n_outputs,
+                           cb_netlist** out) {
     if (!text || !out || n_sweep < 0 || n_outputs < 0 || n_inst < 1 || (n_sweep > 0 && (!sweep_names || !sweep_values)) ||
         (n_outputs > 0 && !output_names))
         return fail(CB_ERR_INVALID, "null / negative argument");
     try {
         auto h = std::make_unique<cb_netlist>();
-        sf::parse_into(h->nl, text, true, base_dir ? base_dir : "", 0);
+        if (spectre) sf::parse_spectre_into(h->nl, text, base_dir ? base_dir : "", 0);
+        else sf::parse_into(h->nl, text, true, base_dir ? base_dir : "", 0);
         std::vector<std::string> names, outs;
         for (int k = 0; k < n_sweep; k++) names.push_back(sweep_names[k] ? sweep_names[k] : "");
         for (int k = 0; k < n_outputs; k++) outs.push_back(output_names[k] ? output_names[k] : "");
@@ -288,6 +289,17 @@ extern "C" int cb_netlist_flatten(const char* text, const char* base_dir, const 
     } catch (const std::exception& e) {
         return fail(CB_ERR_INVALID, std::string("netlist: ") + e.what());
     }
+}
+
+extern "C" int cb_netlist_flatten(const char* text, const char* base_dir, const char* const* sweep_names, int n_sweep,
+                                  const double* sweep_values, int64_t n_inst, const char* const* output_names, int n_outputs,
+                                  cb_netlist** out) {
+    return netlist_flatten(false, text, base_dir, sweep_names, n_sweep, sweep_values, n_inst, output_names, n_outputs, out);
+}
+extern "C" int cb_netlist_flatten_spectre(const char* text, const char* base_dir, const char* const* sweep_names, int n_sweep,
+                                          const double* sweep_values, int64_t n_inst, const char* const* output_names,
+                                          int n_outputs, cb_netlist** out) {
+    return netlist_flatten(true, text, base_dir, sweep_names, n_sweep, sweep_values, n_inst, output_names, n_outputs, out);
 }
 
 extern "C" int cb_netlist_circuit(cb_netlist* nl, cb_circuit** out) {

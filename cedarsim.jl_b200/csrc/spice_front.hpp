@@ -1,4 +1,4 @@
-// spice_front.hpp -- native netlist front end of the engine: a SPICE-subset reader and
+// spice_front.hpp -- native netlist front end of the engine: a SPICE- / Spectre-subset reader and
 // flattener in C++ behind the C ABI (cb_netlist_*, include/cedarb200.h), so that a binding without a front end of its
 // own goes from deck text + sweep values to a compiled circuit and its parameter matrix without the Python host.
 //
@@ -22,8 +22,9 @@
 //   * `.if` / `.elseif` / `.else` / `.endif` on constant top-level parameters, `.lib` sections (`.lib name` ... `.endl`,
 //     `.lib "file" name`, also from the file itself, test/basic.jl:312-336), `.model` cards of resistors
 //     (r = rsh (l - short) / (w - narrow), src/simpledevices.jl:62-70).
+//   * the Spectre-language subset of spectre.py (parse_spectre_into below; cb_netlist_flatten_spectre).
 // Not here (the decks that need them go through the Python host, which also owns the Verilog-A compiler): behavioural
-// sources, MOSFET / Verilog-A instances (`.hdl`), Spectre syntax.  They are refused with a message, never skipped.
+// sources, MOSFET / Verilog-A instances (`.hdl`, `ahdl_include`).  They are refused with a message, never skipped.
 //
 // Host-only code; depends on include/cedarb200.h alone.
 #pragma once
@@ -719,6 +720,266 @@ static void parse_into(Netlist& nl, const std::string& text, bool first_is_title
             continue;
         }
         cur->cards.push_back(parse_card(toks));
+    }
+}
+
+// ---- Spectre-language subset (the same rules as spectre.py; reference's Spectre-syntax tests test/basic.jl:168-205,
+//      :265-278): instances `name (n1 n2 ...) master k=v ...` of resistor capacitor inductor vsource isource vcvs vccs and of
+//      subcircuits, `subckt ... ends` with `parameters`, `model` cards of resistors, `include`, `type=pwl wave=[...]` /
+//      `type=sine` / `type=pulse` sources, `\` continuations, `//` and `*` comments.  bsource / ahdl_include are refused.
+static std::vector<std::string> spectre_lines(const std::string& text) {
+    std::vector<std::string> out;
+    std::string cur, raw;
+    auto flush_raw = [&]() {
+        std::string line;   // strip `// ...` outside quotes
+        {
+            char quote = 0;
+            size_t k = 0;
+            for (; k < raw.size(); k++) {
+                const char ch = raw[k];
+                if (quote) { if (ch == quote) quote = 0; }
+                else if (ch == '"' || ch == '\'') quote = ch;
+                else if (ch == '/' && k + 1 < raw.size() && raw[k + 1] == '/') break;
+            }
+            line = raw.substr(0, k);
+        }
+        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
+        size_t b = 0;
+        while (b < line.size() && std::isspace((unsigned char)line[b])) b++;
+        if (cur.empty() && b < line.size() && line[b] == '*') return;
+        if (!line.empty() && line.back() == '\\') { cur += line.substr(0, line.size() - 1) + " "; return; }
+        cur += line;
+        long open = 0;
+        for (char ch : cur) open += (ch == '[') - (ch == ']');
+        if (open > 0) { cur += " "; return; }   // a vector that runs over the line end
+        size_t c0 = 0, c1 = cur.size();
+        while (c0 < c1 && std::isspace((unsigned char)cur[c0])) c0++;
+        while (c1 > c0 && std::isspace((unsigned char)cur[c1 - 1])) c1--;
+        if (c1 > c0) out.push_back(cur.substr(c0, c1 - c0));
+        cur.clear();
+    };
+    for (char c : text) {
+        if (c == '\n') { flush_raw(); raw.clear(); }
+        else if (c != '\r') raw += c;
+    }
+    flush_raw();
+    {
+        size_t c0 = 0, c1 = cur.size();
+        while (c0 < c1 && std::isspace((unsigned char)cur[c0])) c0++;
+        while (c1 > c0 && std::isspace((unsigned char)cur[c1 - 1])) c1--;
+        if (c1 > c0) out.push_back(cur.substr(c0, c1 - c0));
+    }
+    return out;
+}
+
+// [...] | "..." | '...' | ( | ) | = | run of other characters
+static std::vector<std::string> spectre_tokens(const std::string& line) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    const size_t n = line.size();
+    while (i < n) {
+        const char c = line[i];
+        if (std::isspace((unsigned char)c)) { i++; continue; }
+        if (c == '[' || c == '"' || c == '\'') {
+            const char close = c == '[' ? ']' : c;
+            size_t j = line.find(close, i + 1);
+            if (j == std::string::npos) throw Error("unterminated bracket / quote in '" + line + "'");
+            out.push_back(line.substr(i, j - i + 1));
+            i = j + 1;
+            continue;
+        }
+        if (c == '(' || c == ')' || c == '=') { out.push_back(std::string(1, c)); i++; continue; }
+        size_t j = i;
+        while (j < n && !std::isspace((unsigned char)line[j]) && !std::strchr("()=[]", line[j])) j++;
+        out.push_back(line.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+
+// `a=1 b = x*2 c = p ? 1 : 2` -> (a, '1'), (b, 'x*2'), (c, 'p ? 1 : 2'): a value runs up to the next `name =`
+static KV spectre_assignments(const std::string& text) {
+    struct Hit { size_t name0, name1, eq1; };
+    std::vector<Hit> hits;
+    const size_t n = text.size();
+    for (size_t i = 0; i < n; i++) {
+        if (!(std::isalpha((unsigned char)text[i]) || text[i] == '_')) continue;
+        if (i > 0 && (std::isalnum((unsigned char)text[i - 1]) || text[i - 1] == '_' || text[i - 1] == '.' || text[i - 1] == '$')) continue;
+        size_t j = i;
+        while (j < n && (std::isalnum((unsigned char)text[j]) || text[j] == '_')) j++;
+        size_t k = j;
+        while (k < n && std::isspace((unsigned char)text[k])) k++;
+        if (k < n && text[k] == '=' && !(k + 1 < n && text[k + 1] == '=')) hits.push_back({i, j, k + 1});   // not `==` (and `!=` `<=` `>=` never follow a name directly... they follow an operator character)
+        i = j > i ? j - 1 : i;
+    }
+    KV out;
+    for (size_t h = 0; h < hits.size(); h++) {
+        const size_t end = h + 1 < hits.size() ? hits[h + 1].name0 : n;
+        std::string val = text.substr(hits[h].eq1, end - hits[h].eq1);
+        size_t b = 0, e = val.size();
+        while (b < e && std::isspace((unsigned char)val[b])) b++;
+        while (e > b && std::isspace((unsigned char)val[e - 1])) e--;
+        const std::string key = lower(text.substr(hits[h].name0, hits[h].name1 - hits[h].name0));
+        bool found = false;
+        for (auto& p : out) if (p.first == key) { p.second = val.substr(b, e - b); found = true; }
+        if (!found) out.push_back({key, val.substr(b, e - b)});
+    }
+    return out;
+}
+
+static std::string strip_quotes(std::string f) {
+    while (!f.empty() && std::strchr("\"'", f.front())) f.erase(f.begin());
+    while (!f.empty() && std::strchr("\"'", f.back())) f.pop_back();
+    return f;
+}
+
+static Source spectre_source(const KV& kv, const std::string& name) {
+    Source s;
+    auto get = [&](const char* k, const char* d) { const std::string* v = kv_get(kv, k); return v ? *v : std::string(d); };
+    if (const std::string* v = kv_get(kv, "dc")) { s.has_dc = true; s.dc = *v; }
+    if (const std::string* v = kv_get(kv, "mag")) { s.has_ac = true; s.ac = *v; }
+    const std::string typ = lower(strip_quotes(get("type", "dc")));
+    if (typ == "pwl") {
+        std::string w = get("wave", "[]");
+        std::string flat;
+        for (char c : w) flat += (c == '[' || c == ']' || c == ',') ? ' ' : c;
+        std::stringstream ss(flat);
+        std::string t;
+        s.tran_kind = "pwl";
+        while (ss >> t) s.tran_args.push_back(t);
+    } else if (typ == "sine" || typ == "sin") {   // SIN(vo va freq td theta phase), src/spectre_env.jl:169-176
+        s.tran_kind = "sin";
+        s.tran_args = {kv_get(kv, "sinedc") ? get("sinedc", "0") : get("dc", "0"), get("ampl", "0"), get("freq", "0"), get("delay", "0"),
+                       get("damp", "0"), get("sinephase", "0")};
+    } else if (typ == "pulse") {                  // PULSE(v1 v2 td tr tf pw per), src/spectre_env.jl:153-166
+        s.tran_kind = "pulse";
+        s.tran_args = {get("val0", "0"), get("val1", "0"), get("delay", "0"), get("rise", "0"), get("fall", "0"), get("width", "0"),
+                       get("period", "0")};
+    } else if (typ != "dc") throw Error(name + ": source type '" + typ + "' is outside the Spectre subset");
+    return s;
+}
+
+static void parse_spectre_into(Netlist& nl, const std::string& text, const std::string& base_dir, int depth) {
+    if (depth > 16) throw Error("include nesting too deep");
+    static const std::map<std::string, char> prims = {{"resistor", 'r'}, {"capacitor", 'c'}, {"inductor", 'l'}, {"vsource", 'v'},
+                                                      {"isource", 'i'}, {"vcvs", 'e'}, {"vccs", 'g'}};
+    std::vector<Subckt*> stack{&nl.top};
+    for (const std::string& line : spectre_lines(text)) {
+        const std::vector<std::string> toks = spectre_tokens(line);
+        if (toks.empty()) continue;
+        const std::string head = lower(toks[0]);
+        Subckt* cur = stack.back();
+        if (head == "simulator") {
+            if (lower(line).find("spice") != std::string::npos)
+                throw Error("`simulator lang=spice` sections are outside the Spectre subset; use the SPICE reader");
+            continue;
+        }
+        if (head == "parameters") {
+            KV& dst = cur == &nl.top ? cur->params : cur->local_params;
+            for (auto& p : spectre_assignments(line.substr(toks[0].size()))) {
+                bool found = false;
+                for (auto& q : dst) if (q.first == p.first) { q.second = p.second; found = true; }
+                if (!found) dst.push_back(p);
+            }
+            continue;
+        }
+        if (head == "subckt" || head == "inline") {
+            std::vector<std::string> t;
+            for (size_t k = 1; k < toks.size(); k++) if (toks[k] != "(" && toks[k] != ")" && lower(toks[k]) != "subckt") t.push_back(lower(toks[k]));
+            if (t.empty()) throw Error("subckt without a name");
+            auto sub = std::make_shared<Subckt>();
+            sub->name = t[0];
+            sub->ports.assign(t.begin() + 1, t.end());
+            cur->subckts[sub->name] = sub;
+            stack.push_back(sub.get());
+            continue;
+        }
+        if (head == "ends") { if (stack.size() > 1) stack.pop_back(); continue; }
+        if (head == "model") {
+            if (toks.size() < 3) throw Error("model needs a name and a master");
+            const std::string name = lower(toks[1]);
+            nl.model_master[name] = lower(toks[2]);
+            std::map<std::string, double>& mp = nl.models[name];
+            for (auto& q : spectre_assignments(line)) {
+                try { Scope empty; mp[q.first] = empty.eval(q.second).v[0]; } catch (const Error&) {}
+            }
+            continue;
+        }
+        if (head == "ahdl_include") throw Error("ahdl_include (Verilog-A) is handled by the Python front end");
+        if (head == "include") {
+            if (toks.size() < 2) throw Error("include without a file name");
+            const std::string fname = strip_quotes(toks[1]);
+            if (lower(fname).compare(0, 8, "jlpkg://") == 0 || (fname.size() > 3 && lower(fname).substr(fname.size() - 3) == ".va"))
+                throw Error("include " + fname + " is handled by the Python front end");
+            const std::string path = (!fname.empty() && fname[0] == '/') ? fname : (base_dir.empty() ? fname : base_dir + "/" + fname);
+            std::ifstream f(path);
+            if (!f) throw Error("cannot open include file '" + path + "'");
+            std::stringstream ss;
+            ss << f.rdbuf();
+            const size_t slash = path.find_last_of('/');
+            const std::string dir = slash == std::string::npos ? std::string() : path.substr(0, slash);
+            const std::string low = lower(ss.str());
+            const bool is_spectre = low.find("simulator lang=spectre") != std::string::npos || (path.size() > 4 && lower(path).substr(path.size() - 4) == ".scs");
+            if (is_spectre) parse_spectre_into(nl, ss.str(), dir, depth + 1);
+            else parse_into(nl, ss.str(), false, dir, depth + 1, std::string());
+            continue;
+        }
+        if (head == "global" || head == "save" || head == "ic" || head == "nodeset" || head == "options") continue;
+        if (toks.size() > 1) {
+            const std::string t1 = lower(toks[1]);
+            if (t1 == "options" || t1 == "tran" || t1 == "dc" || t1 == "ac" || t1 == "noise" || t1 == "info") continue;   // analyses and controls
+        }
+        // ---- instance: name (nodes) master k=v ...   (parentheses optional)
+        Card c;
+        c.name = head;
+        std::vector<std::string> nodes, pos;
+        KV kv;
+        std::string master;
+        size_t from = 1;
+        if (toks.size() > 1 && toks[1] == "(") {
+            size_t close = 2;
+            while (close < toks.size() && toks[close] != ")") nodes.push_back(toks[close++]);
+            from = close + 1;
+            split_params(toks, from, pos, kv);
+            master = pos.empty() ? "" : pos[0];
+        } else {
+            split_params(toks, 1, pos, kv);
+            if (!pos.empty()) { master = pos.back(); nodes.assign(pos.begin(), pos.end() - 1); }
+        }
+        if (master.empty()) throw Error(c.name + ": no master / subcircuit name");
+        {   // values may be whole expressions (`r=(p1+p2)/p3`): re-read the assignments from the raw text behind the master
+            const size_t at = line.find(master, toks[0].size());
+            if (at != std::string::npos) {
+                const KV kv2 = spectre_assignments(line.substr(at + master.size()));
+                if (!kv2.empty()) kv = kv2;
+            }
+        }
+        for (auto& nd : nodes) nd = lower(nd);
+        const std::string m = lower(master);
+        auto pit = prims.find(m);
+        if (pit != prims.end()) {
+            c.kind = pit->second;
+            const size_t want = (c.kind == 'e' || c.kind == 'g') ? 4 : 2;
+            if (nodes.size() < want) throw Error(c.name + ": " + std::to_string(want) + " nodes expected");
+            c.nodes.assign(nodes.begin(), nodes.begin() + want);
+            if (c.kind == 'v' || c.kind == 'i') c.src = spectre_source(kv, c.name);
+            else if (c.kind == 'e' || c.kind == 'g') {
+                const std::string* g = c.kind == 'e' ? kv_get(kv, "gain") : (kv_get(kv, "gm") ? kv_get(kv, "gm") : kv_get(kv, "gain"));
+                if (g) { c.has_value = true; c.value = *g; }
+                c.params = kv;
+            } else c.params = kv;
+        } else if (m == "bsource") {
+            throw Error(c.name + ": behavioural sources are handled by the Python front end (netlist.py), not by the native reader");
+        } else if (nl.models.count(m)) {
+            const std::string& master2 = nl.model_master[m];
+            if (master2 == "resistor" || master2 == "r" || master2 == "res") {
+                if (nodes.size() < 2) throw Error(c.name + ": two nodes expected");
+                c.kind = 'r'; c.nodes.assign(nodes.begin(), nodes.begin() + 2); c.model = m; c.params = kv;
+            } else throw Error(c.name + ": instances of model '" + m + "' (" + master2 + ") need generated device code: handled by the Python front end");
+        } else {
+            c.kind = 'x'; c.nodes = nodes; c.model = m; c.params = kv;   // subcircuit instance, resolved by the flattener
+        }
+        cur->cards.push_back(c);
     }
 }
 

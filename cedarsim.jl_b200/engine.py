@@ -294,7 +294,8 @@ class NativeNetlist:
     flattener or struct packing on the way.  `fc` is a read-only FlatCircuit VIEW of what the library built (names,
     devices, waves, outputs), so results can be named and the CPU oracle can be handed the same circuit."""
 
-    def __init__(self, text: str, sweep: Optional[dict] = None, outputs: Optional[Sequence[str]] = None, base_dir: Optional[str] = None):
+    def __init__(self, text: str, sweep: Optional[dict] = None, outputs: Optional[Sequence[str]] = None, base_dir: Optional[str] = None,
+                 lang: str = "spice"):
         lib = load()
         lib.cb_netlist_flat.restype = C.POINTER(F.cb_flat_circuit)
         lib.cb_netlist_params.restype = C.POINTER(C.c_double)
@@ -309,7 +310,8 @@ class NativeNetlist:
         outs = list(outputs or [])
         onames = (C.c_char_p * max(1, len(outs)))(*[o.encode() for o in outs])
         self.handle = C.c_void_p()
-        _check(lib.cb_netlist_flatten(text.encode(), base_dir.encode() if base_dir else None, names, C.c_int(len(sweep)),
+        flatten = lib.cb_netlist_flatten_spectre if lang == "spectre" else lib.cb_netlist_flatten
+        _check(flatten(text.encode(), base_dir.encode() if base_dir else None, names, C.c_int(len(sweep)),
                                       _dp(vals) if sweep else None, C.c_int64(B), onames, C.c_int(len(outs)), C.byref(self.handle)))
         self.B = B
         P = int(lib.cb_netlist_n_params(self.handle))

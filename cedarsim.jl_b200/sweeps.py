@@ -493,11 +493,9 @@ class CircuitSweep:
             raise ValueError("empty sweep: a CircuitSweep needs at least one point")
         self._native = None
         if isinstance(circuit, str) and front_end == "native":
-            if lang != "spice":
-                raise ValueError("the native front end reads SPICE decks only")
             import math
             from .flat import Col
-            nn = engine.NativeNetlist(circuit, self.columns, outputs, base_dir=(include_dirs[0] if include_dirs else None))
+            nn = engine.NativeNetlist(circuit, self.columns, outputs, base_dir=(include_dirs[0] if include_dirs else None), lang=lang)
             opts = {}
             t = nn.option("temp")
             if "temp" in nn.fc.param_names:

@@ -208,6 +208,12 @@ def test_native_front_end_matches_the_python_one():
     ya = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"], front_end="native"), (0.0, 20e-9), saveat=ts, reltol=1e-5)
     yb = tran_(CircuitSweep(deck, sw, outputs=["out", "x2.b", "v1.i"]), (0.0, 20e-9), saveat=ts, reltol=1e-5)
     assert ya.status.max() == 0 and np.array_equal(ya.y, yb.y)
+    # and a Spectre-language deck (test/basic.jl:265-278) through cb_netlist_flatten_spectre
+    sub = "\nsubckt myres vcc gnd\n    parameters r=1k\n    r1 (vcc gnd) resistor r=r\nends myres\n\nx1 (vcc 0) myres r=2k\nv1  (vcc 0) vsource dc=1\n"
+    rr = np.array([1e3, 2e3, 4e3])
+    cs = CircuitSweep(sub, Sweep("x1.r", rr), lang="spectre", front_end="native")
+    sp = dc_(cs)
+    assert sp.status.max() == 0 and np.allclose(-sp.array(cs.sys.v1.I), 1.0 / rr, rtol=1e-14, atol=0)     # sys.x1.r1.I == 0.5e-3 at r = 2k
 
 
 def test_failed_points_are_retried_by_the_host_ladder(tmp_path):

@@ -160,3 +160,52 @@ def test_if_chain_lib_sections_and_resistor_model_cards(tmp_path):
     assert nn.fc.node_names == fl.fc.node_names and [d.value for d in nn.fc.devices] == [d.value for d in fl.fc.devices] == [0.0, 1337.0]
     _, xf, st, _ = orc.dc(nn.fc, None)
     assert abs(-xf[nn.unknown("v1.i"), 0] - 1 / 1337) < 1e-15
+
+
+def _compare_spectre(deck, sweep=None, outputs=None, base_dir=None):
+    from cedarsim.jl_b200 import spectre
+    sweep = {k: np.asarray(v, dtype=float) for k, v in (sweep or {}).items()}
+    nn = engine.NativeNetlist(deck, sweep, outputs, base_dir=base_dir, lang="spectre")
+    fl = netlist.flatten(spectre.parse_spectre(deck, include_dirs=[base_dir] if base_dir else None), sweep, outputs=outputs)
+    a, b = nn.fc, fl.fc
+    assert a.node_names == b.node_names and a.branch_names == b.branch_names and a.param_names == b.param_names
+    assert np.array_equal(nn.params, fl.params)
+    assert [(d.kind, list(d.nodes), d.branch, d.wave, d.mult) for d in a.devices] == [(d.kind, list(d.nodes), d.branch, d.wave, d.mult) for d in b.devices]
+    assert all(_same(x.value, y.value) for x, y in zip(a.devices, b.devices))
+    pa, pb = a.pack(), b.pack()
+    for i in range(len(a.waves)):
+        wa, wb = pa.struct.waves[i], pb.struct.waves[i]
+        assert (wa.kind, wa.has_dc, wa.npts, wa.dc.col, wa.dc.value) == (wb.kind, wb.has_dc, wb.npts, wb.dc.col, wb.dc.value)
+        assert all(wa.t[k] == wb.t[k] and wa.y[k].value == wb.y[k].value for k in range(wa.npts))
+        assert all(wa.v[k].col == wb.v[k].col and (wa.v[k].value == wb.v[k].value or wa.v[k].value != wa.v[k].value or
+                                                  (math.isinf(wa.v[k].value) and math.isinf(wb.v[k].value))) for k in range(7))
+    return nn
+
+
+def test_spectre_language_decks_natively():
+    """The reference's Spectre-syntax decks (test/basic.jl:168-205 sources, :265-278 subcircuit) through the library's own
+    Spectre-subset reader (cb_netlist_flatten_spectre) and through spectre.py: same flat circuit, reference answers."""
+    sources = ("\nI1 (0 1) isource dc=2.2u\nR1 (1 0) resistor r=1000\n\nI2 (0 2) isource type=pwl wave=[0 1m .5 2m 1 1.75m]\n"
+               "R2 (2 0) resistor r=2k\n\nV3 (0 3) vsource dc=1.5\nR3 (3 0) resistor r=1k\n\n"
+               "V4 (0 4) vsource type=pwl wave=[ 0 1 .5 2 \\\n        1 5]\nR4 (4 0) resistor r=4k   // a comment\n"
+               "V5 (5 0) vsource type=sine sinedc=1 ampl=2 freq=3 delay=0.1\nR5 (5 0) resistor r=1k\n"
+               "V6 (6 0) vsource type=pulse val0=0 val1=1 delay=0.1 rise=0.1 fall=0.1 width=0.2 period=1\nR6 (6 0) resistor r=1k\n"
+               "E1 (7 0 3 0) vcvs gain=2\nR7 (7 0) resistor r=1k\nG1 (8 0 3 0) vccs gm=1m\nR8 (8 0) resistor r=1k\n")
+    nn = _compare_spectre(sources)
+    ts = np.linspace(0.0, 1.0, 11)
+    y, st, _ = orc.tran(nn.fc, 0.0, 1.0, ts, opts=orc.default_options())
+    v = lambda n: y[nn.unknown(n), :, 0]
+    assert st.max() == 0 and np.allclose(v("1"), 2.2e-3) and np.allclose(v("3"), -1.5)
+    assert np.isclose(v("2")[-1], 3.5) and np.isclose(v("4")[-1], -5.0) and np.allclose(v("7"), -3.0) and np.allclose(v("8"), 1.5)
+    sub = ("\nparameters rtop=2k\nsubckt myres vcc gnd\n    parameters r=1k\n    r1 (vcc gnd) resistor r=r\nends myres\n\n"
+           "x1 (vcc 0) myres r=rtop\nx2 (vcc 0) myres r=(rtop+1k)/3\nv1  (vcc 0) vsource dc=1\n")
+    nn = _compare_spectre(sub)
+    _, xf, st, _ = orc.dc(nn.fc, None)
+    assert st.max() == 0 and abs(-xf[nn.unknown("v1.i"), 0] - (0.5e-3 + 1e-3)) < 1e-15          # sys.x1.r1.I == 0.5e-3 (+ x2)
+    nn = _compare_spectre(sub, {"x1.r": np.array([1e3, 2e3, 4e3]), "rtop": np.array([2e3, 5e3, 8e3])})
+    _, xf, st, _ = orc.dc(nn.fc, nn.params)
+    assert np.allclose(-xf[nn.unknown("v1.i")], 1 / np.array([1e3, 2e3, 4e3]) + 3 / np.array([3e3, 6e3, 9e3]), rtol=1e-14, atol=0)
+    with pytest.raises(RuntimeError, match="behavioural"):
+        engine.NativeNetlist("B5 (0 5) bsource v=$time*V(3)\nR5 (5 0) resistor r=1k\n", lang="spectre")
+    with pytest.raises(RuntimeError, match="ahdl_include"):
+        engine.NativeNetlist('ahdl_include "x.va"\nR5 (5 0) resistor r=1k\n', lang="spectre")
