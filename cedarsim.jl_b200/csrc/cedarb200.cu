@@ -136,7 +136,7 @@ static int check_options(const cb_options* o) {
 extern "C" void cb_options_default(cb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->struct_size = (uint32_t)sizeof(cb_options); o->abi_version = CB_ABI_VERSION;
-    o->mixed_rounds = 0; o->source_steps = 10; o->t0_reinit = 1; o->pivot_growth_max = 1e14;
+    o->mixed_rounds = 0; o->source_steps = 10; o->t0_reinit = 1; o->pivot_repair = 0; o->pivot_growth_max = 1e14;
     o->temp.value = 27.0; o->temp.col = -1;
     o->gmin.value = 1e-12; o->gmin.col = -1;
     o->reltol = 1e-3; o->vabstol = 1e-6; o->iabstol = 1e-12;
@@ -851,6 +851,7 @@ struct cb_plan {
     bool lu = false;         // solve kernel = hand-written shared-memory batched LU (k_lu), else the generated k_solve
     LArgs la{};
     size_t lu_smem = 0;
+    double* d_pp_scratch = nullptr;          // [SMs][N (N + 1)]: dense systems of the points k_lu re-solves with partial pivoting
     bool lu_staged = false;                  // k_lu's table blob lives in shared memory behind the matrices
     std::vector<unsigned char> lu_blob;
     int* d_dc_count = nullptr;
@@ -1304,6 +1305,18 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             t.rl_ptr = add16(c->rl_ptr); t.rl_lin = add16(c->rl_lin); t.rl_col = add16(c->rl_col);
             t.rs_ptr = add16(c->rs_ptr); t.rs_wave = add16(c->rs_wave);
             t.row_to_step = add16(S.row_to_step); t.col_to_step = add16(S.col_to_step);
+            {   // elimination step of the row / column of every LU entry (repair pass: scatter into the dense system)
+                std::vector<int> er(S.nnz_lu, 0), ec(S.nnz_lu, 0);
+                for (int k = 0; k < N; k++) {
+                    er[S.diag_pos[k]] = k; ec[S.diag_pos[k]] = k;
+                    for (int li = S.l_ptr[k]; li < S.l_ptr[k + 1]; li++) { er[S.l_pos[li]] = S.l_row[li]; ec[S.l_pos[li]] = k; }
+                    for (int uj = S.u_ptr[k]; uj < S.u_ptr[k + 1]; uj++) { er[S.u_pos[uj]] = k; ec[S.u_pos[uj]] = S.u_col[uj]; }
+                }
+                std::vector<unsigned short> er16(er.begin(), er.end()), ec16(ec.begin(), ec.end());
+                unsigned short* d16;
+                TRY(p->upload(&d16, er16)); la.e_row = d16;
+                TRY(p->upload(&d16, ec16)); la.e_col = d16;
+            }
             if (std::getenv("CB_DEBUG"))
                 std::fprintf(stderr, "k_lu schedule: N=%d nnz=%d levels=%d back-levels=%d ops=%zu fwd-levels=%d fwd-ops=%zu smem=%zu\n", N,
                              S.nnz_lu, sch.nlev, sch.nblev, sch.ops.size(), nslev, sops.size(), p->lu_smem);
@@ -1381,11 +1394,13 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
                 if (p->lu_staged) p->lu_smem += blob.size();
                 if (std::getenv("CB_DEBUG")) std::fprintf(stderr, "k_lu tables: %zu bytes, staged=%d\n", blob.size(), (int)p->lu_staged);
                 if (p->lu_staged) {
-                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
                 } else {
-                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
-                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(k_lu<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lu_smem));
                 }
             }
             la.LUF = nullptr;
@@ -1403,6 +1418,10 @@ static int plan_create1(cb_circuit* c, int64_t n_inst, int device_id, cb_plan** 
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
             p->num_sms = std::max(1, prop.multiProcessorCount);
+        }
+        if (p->lu) {   // one dense system per k_lu CTA (the grid never exceeds the SM count), no more than the batch has groups
+            const long long ctas = std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
+            TRY(p->alloc(&p->d_pp_scratch, (size_t)ctas * N * (N + 1)));
         }
         a.scratch = nullptr;
         a.sm_stride = 0;
@@ -1489,13 +1508,17 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     a->uni_per_inst = (opt->temp.col >= 0 || opt->gmin.col >= 0) ? 1 : 0; a->pad_ = 0;
 }
 
+// (the repairable variant, k_lu<., ., true>, when the arguments carry a repair scratch: cb_options.pivot_repair)
 static inline void launch_lu(cb_plan* p, unsigned grid, cudaStream_t st, const LArgs& la, bool fused = false) {
+    const bool rep = la.pp_scratch != nullptr && !fused;
     if (p->lu_staged) {
-        if (fused) k_lu<true, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
-        else k_lu<true, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        if (fused) k_lu<true, true, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else if (rep) k_lu<true, false, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else k_lu<true, false, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
     } else {
-        if (fused) k_lu<false, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
-        else k_lu<false, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        if (fused) k_lu<false, true, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else if (rep) k_lu<false, false, true><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
+        else k_lu<false, false, false><<<grid, LU_PTS * LU_W, p->lu_smem, st>>>(la);
     }
 }
 
@@ -1735,6 +1758,7 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         largs[par].zero_cnt = p->d_cnt + (fused ? nxt2 : nxt) * 4;
         largs[par].k = cargs[par].k;
         largs[par].growth_max = opt->pivot_growth_max > 0.0 ? opt->pivot_growth_max : 1e300;
+        largs[par].pp_scratch = (opt->pivot_repair && !fused) ? p->d_pp_scratch : nullptr;
     }
     int n_live_models = 0;
     for (size_t m = 0; m < c->models.size(); m++) n_live_models += !c->model_insts[m].empty();
@@ -2007,6 +2031,7 @@ static int sens_dc1(cb_plan* p, const cb_options* opt, int64_t n_dir, const doub
     la.cur = Lists{p->d_lists, p->d_lists + B, p->d_lists + 2 * B, p->d_cnt};
     la.zero_cnt = p->d_cnt + 4;
     la.growth_max = 1e300;
+    la.pp_scratch = nullptr;
     a.o.rate_test = 0;
     const unsigned lu_grid = (unsigned)std::min<long long>((B + LU_PTS - 1) / LU_PTS + 1, (long long)p->num_sms);
     // 1. factors of J(x*): one full iteration of every point at the solution (alpha = 0: the DC Jacobian)

@@ -304,7 +304,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
     bool out_from_x = false, reinit_begin = false;
 
     // ---- pass 1: Newton update of this lane's unknowns, convergence and LTE partials ------------
-    const bool solving = live && phase != PH_TRAN_INIT && !badpt;
+    const bool solving = live && phase != PH_TRAN_INIT && (!badpt || (badpt & 4));   // (bit 2: re-solved by k_lu's repair pass)
     const bool want_lte = solving && phase == PH_TRAN && !o.fixed_step && np >= 1;
     double sc = 1.0, ratio = 0.0;
     if (solving) {
@@ -353,10 +353,12 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         } else {
             nnewton++;
             if (!pv && lane == 0) a.ist[(size_t)IS_NFULL * B + ii]++;
-            if (badpt) {
+            if ((badpt & 2) && lane == 0) a.ist[(size_t)IS_NGROWTH * B + ii]++;   // pivot-growth monitor of k_lu
+            if (badpt & 4) retry = 1;   // re-solved with partial pivoting by k_lu's repair pass: the iteration stands, but the
+                                        // stored factors are the ones that failed -> full iterations for the rest of the attempt
+            if (badpt && !(badpt & 4)) {
                 newton_fail = true;
                 status = 4;
-                if ((badpt & 2) && lane == 0) a.ist[(size_t)IS_NGROWTH * B + ii]++;   // pivot-growth monitor of k_lu
             } else {
                 const double restol = phase == PH_DC ? o.dc_abstol : 1e300;
                 double est = nrm;   // estimate of the weighted error left after this update
@@ -711,19 +713,88 @@ struct LArgs {
     int* BAD;
     double growth_max;        // pivot-growth bound: an elimination multiplier above it flags the point (BAD bit 1)
     CtlArgs k;                // the control step, when it is fused into this kernel (k_lu<.., true>)
+    double* pp_scratch;       // [gridDim.x][N (N + 1)] dense system of the point being re-solved with partial pivoting, or null
+    const u16 *e_row, *e_col; // per LU entry: elimination step of its row / of its column (repair pass only; global memory)
 };
 
+// The slow path behind the pivot-growth monitor (hard part 3): ONE point's N x N system, dense in
+// global scratch as A[N][N + 1] (last column = right-hand side, everything in elimination-step coordinates), solved by the
+// whole CTA with PARTIAL pivoting -- row search, swap, rank-1 update per column with three barriers each, then a
+// column-oriented backward substitution.  ~2 N barriers and N^3 / 3 multiply-adds: ~0.1 ms for the DFF's 85 unknowns,
+// paid only by points whose static pivot order failed numerically.  Returns 0, or 1 when a column has no usable pivot.
+// The solution is left in the last column.
+__device__ __noinline__ int lu_dense_pp(double* __restrict__ A, const int N, int* s_i, double* s_v) {
+    const int T = LU_PTS * LU_W, tid = threadIdx.x, ld = N + 1;
+    for (int k = 0; k < N; k++) {
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + tid; i < N; i += T) {
+            const double v = fabs(A[(size_t)i * ld + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_v[tid >> 5] = best; s_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < LU_W; q++) if (s_v[q] > s_v[0]) { s_v[0] = s_v[q]; s_i[0] = s_i[q]; }
+        }
+        __syncthreads();
+        const int p = s_i[0];
+        const double pv = s_v[0];
+        __syncthreads();   // s_v / s_i are rewritten by the next column's search
+        if (!(pv > 0.0) || !isfinite(pv)) return 1;
+        if (p != k) {
+            for (int j = tid; j <= N; j += T) {
+                const double t = A[(size_t)k * ld + j];
+                A[(size_t)k * ld + j] = A[(size_t)p * ld + j];
+                A[(size_t)p * ld + j] = t;
+            }
+            __syncthreads();
+        }
+        const double inv = 1.0 / A[(size_t)k * ld + k];
+        const int nr = N - k - 1, nc = N - k;   // rows k + 1 .. N - 1, columns k + 1 .. N
+        for (int idx = tid; idx < nr * nc; idx += T) {
+            const int i = k + 1 + idx / nc, j = k + 1 + idx % nc;
+            A[(size_t)i * ld + j] -= (A[(size_t)i * ld + k] * inv) * A[(size_t)k * ld + j];
+        }
+        __syncthreads();
+    }
+    for (int k = N - 1; k >= 0; k--) {
+        if (tid == 0) A[(size_t)k * ld + N] /= A[(size_t)k * ld + k];
+        __syncthreads();
+        const double xk = A[(size_t)k * ld + N];
+        for (int i = tid; i < k; i += T) A[(size_t)i * ld + N] -= A[(size_t)i * ld + k] * xk;
+        __syncthreads();
+    }
+    return 0;
+}
+
 // One group of LU_PTS points (lane = point) of one kind: SOLVE = value-only iteration with the stored factors.
+// Full groups may take a second pass ("repair", when LArgs.pp_scratch is set): the points that the first pass flagged
+// (zero / non-finite pivot, elimination multiplier above growth_max, non-finite update) are assembled again and solved
+// one by one with lu_dense_pp; their BAD word becomes 4 | 2 ("solved by the slow path": the control step carries on
+// with the iteration instead of rejecting it, and keeps the point on full iterations for the rest of the attempt,
+// because its stored factors are the ones that failed).
 // tb = base of the table blob (shared or global memory).
-template <bool SOLVE, bool FUSED>
-__device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const unsigned char* __restrict__ tb,
+template <bool SOLVE, bool FUSED, bool REPAIR, bool CANREPAIR>
+__device__ __forceinline__ int lu_group(const LArgs& c, double* vals_, const unsigned char* __restrict__ tb,
                                          unsigned long long (*s_red)[LU_PTS], int* s_bad,
-                                         const long long inst, const bool on, const int lane, const int w) {
+                                         const long long inst, const bool on, const int lane, const int w,
+                                         int* s_redo, int* s_pi, double* s_pv) {
 #define T16(name) ((const u16*)(tb + c.t.name))
+    const NArgs& a = c.n;
+    // REPAIR: the second pass over a full group (see above), compiled as a function of its own (lu_repair) so that the
+    // code of the normal pass is what it would be without it
+    const bool redo = REPAIR && s_redo[lane] != 0;   // this lane's point is being re-solved
+    const bool st = on && (!REPAIR || redo);         // this thread stores results of its lane's point
+    if (REPAIR) __syncthreads();                     // s_redo is read by everybody before anything rewrites shared memory
     // per-point reductions over the workers: max |r|, max |dv| (non-negative, never NaN: fmax drops NaNs -> the bit
     // patterns order like the values) and the singular / non-finite / growth flags, by shared-memory atomics
     if (w == 0) { s_red[0][lane] = 0ull; s_red[1][lane] = 0ull; s_bad[lane] = 0; }
-    const NArgs& a = c.n;
     const long long B = a.B;
     const int N = a.N, NV = a.NV, nnz = a.nnz_lu;
     double* __restrict__ vals = vals_ + lane;
@@ -820,6 +891,24 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
     atomicMax(&s_red[0][lane], (unsigned long long)__double_as_longlong(rmax));
     int bad = 0;
     __syncthreads();
+    if (REPAIR) {
+        // ---- 2'. repair pass: the flagged points one by one, dense with partial pivoting (lu_dense_pp)
+        double* __restrict__ A = c.pp_scratch + (size_t)blockIdx.x * N * (N + 1);
+        const u16* __restrict__ e_row = c.e_row;
+        const u16* __restrict__ e_col = c.e_col;
+        for (int l = 0; l < LU_PTS; l++) {
+            if (!s_redo[l]) continue;   // block-uniform
+            for (int k = threadIdx.x; k < N * (N + 1); k += LU_PTS * LU_W) A[k] = 0.0;
+            __syncthreads();
+            for (int e = threadIdx.x; e < nnz; e += LU_PTS * LU_W) A[(size_t)e_row[e] * (N + 1) + e_col[e]] = vals_[(size_t)e * LU_PTS + l];
+            for (int r = threadIdx.x; r < N; r += LU_PTS * LU_W) A[(size_t)r * (N + 1) + N] = vals_[(size_t)(nnz + r) * LU_PTS + l];
+            __syncthreads();
+            const int sing = lu_dense_pp(A, N, s_pi, s_pv);
+            for (int r = threadIdx.x; r < N; r += LU_PTS * LU_W) vals_[(size_t)(nnz + r) * LU_PTS + l] = sing ? 0.0 : A[(size_t)r * (N + 1) + N];
+            if (threadIdx.x == 0) s_bad[l] = sing ? 3 : 6;   // 6 = growth seen (2) + solved by the slow path (4)
+            __syncthreads();
+        }
+    } else {
     // ---- 2. elimination by levels (fused forward substitution) ------------------------------------------
     {
         const int nlev = SOLVE ? c.nslev : c.nlev;
@@ -874,6 +963,7 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
             __syncthreads();
         }
     }
+    }   // !REPAIR
     // ---- 3b. charges of the updated iterate to first order: q(x + dx) ~ q(x) + C dx (linear capacitors exactly).
     //          The accepted step keeps these charges, so they must belong to the iterate that is accepted, not to
     //          the point of the last device evaluation (which lies |dx| away).  In value-only rounds dQ/dV is that
@@ -915,13 +1005,13 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
         }
         __syncthreads();
     }
-    if (on && !FUSED)
+    if (st && !FUSED)
         for (int i = w; i < N; i += LU_W) c.QK[(size_t)i * B + inst] = Qv[(size_t)i * LU_PTS];
     // ---- 4. update vector and norms ---------------------------------------------------------------------
     double dvm = 0.0;
     for (int i = w; i < N; i += LU_W) {
         const double dx = VL(nnz + col_to_step[i]);
-        if (on && !FUSED) c.DX[(size_t)i * B + inst] = dx;
+        if (st && !FUSED) c.DX[(size_t)i * B + inst] = dx;
         if (i < NV) dvm = fmax(dvm, fabs(dx));
         bad |= !isfinite(dx);
     }
@@ -929,15 +1019,30 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
     if (bad) atomicOr(&s_bad[lane], bad);
     __syncthreads();
     if (!FUSED) {
-        if (w == 0 && on) {
+        if (w == 0 && st) {
             c.RMAX[inst] = __longlong_as_double((long long)s_red[0][lane]);
             c.DVMAX[inst] = __longlong_as_double((long long)s_red[1][lane]);
             c.BAD[inst] = s_bad[lane];
         }
+        if (CANREPAIR && !SOLVE && !REPAIR) {
+            // a second pass for the points this pass flagged?  (block-uniform answer; the barrier is also the one after
+            // which the next group may reuse the shared-memory matrix and the reduction slots)
+            const int flagged = on ? s_bad[lane] : 0;
+            if (w == 0) s_redo[lane] = flagged != 0;
+            return __syncthreads_or(flagged != 0);
+        }
         __syncthreads();   // the next group reuses the shared-memory matrix and the reduction slots
     }
+    return 0;
 #undef VL
 #undef T16
+}
+
+// The repair pass as a function of its own (see lu_group<.., REPAIR = true>)
+__device__ __noinline__ void lu_repair(const LArgs& c, double* vals_, const unsigned char* tb, unsigned long long (*s_red)[LU_PTS],
+                                       int* s_bad, const long long inst, const bool on, const int lane, const int w, int* s_redo,
+                                       int* s_pi, double* s_pv) {
+    lu_group<false, false, true, true>(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
 }
 
 // A CTA works through groups g = blockIdx.x, blockIdx.x + gridDim.x, ... of this round's lists: first the groups of
@@ -956,12 +1061,18 @@ __device__ __forceinline__ void lu_group(const LArgs& c, double* vals_, const un
 //   kernels (base + inst * 8 bytes per lane) touches 17 sectors per request instead of 4.4.  The stand-alone k_control
 //   walks the points in instance order every round and so re-establishes runs of consecutive points; that ordered
 //   compaction is what fusion gives up.  Off by default (CB_FUSE=1).
-template <bool STAGED, bool FUSED>
-__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
+// REPAIRABLE: full groups may call the repair pass (cb_options.pivot_repair); the kernel without it is exactly the
+// kernel there was before the repair pass existed (same-box A/B: the repairable one is 1 % / 2 % slower at 16 384 / 2 048
+// points, profiles/probe_r2ag.log, although the pass itself never runs on the bench workload).
+template <bool STAGED, bool FUSED, bool REPAIRABLE>
+__global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const __grid_constant__ LArgs c) {
     extern __shared__ __align__(16) double vals_[];
     __shared__ unsigned long long s_red[2][LU_PTS];
     __shared__ unsigned long long s_ctl[2][LU_PTS];
     __shared__ int s_bad[LU_PTS];
+    __shared__ int s_redo[LU_PTS];   // repair pass of lu_group: lanes to re-solve, pivot search scratch
+    __shared__ int s_pi[LU_W];
+    __shared__ double s_pv[LU_W];
     const int lane = threadIdx.x % LU_PTS, w = threadIdx.x / LU_PTS;
     if (blockIdx.x == 0 && threadIdx.x < 3) c.zero_cnt[threadIdx.x] = 0;
     const int nf = c.cur.cnt[0], na = c.cur.cnt[1], ni = FUSED ? c.cur.cnt[2] : 0;
@@ -982,8 +1093,11 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const LArgs c) {
         const bool on = g0 + lane < n;
         const long long inst = list[on ? g0 + lane : g0];   // idle lanes shadow the group's first point, never store
         if (FUSED && w == 0) { s_ctl[0][lane] = 0ull; s_ctl[1][lane] = 0ull; }
-        if (kind == 1) lu_group<true, FUSED>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
-        else if (kind == 0) lu_group<false, FUSED>(c, vals_, tb, s_red, s_bad, inst, on, lane, w);
+        if (kind == 1) lu_group<true, FUSED, false, false>(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
+        else if (kind == 0) {
+            const int flagged = lu_group<false, FUSED, false, REPAIRABLE && !FUSED>(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
+            if (REPAIRABLE && !FUSED && flagged && c.pp_scratch) lu_repair(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
+        }
         else if (FUSED) __syncthreads();   // publishes the zeroed reduction slots
         if (FUSED) {
             const double rmax = kind < 2 ? __longlong_as_double((long long)s_red[0][lane]) : 0.0;

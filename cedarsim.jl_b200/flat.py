@@ -131,7 +131,7 @@ class cb_options(C.Structure):
         ("mixed_rounds", C.c_int32),
         ("source_steps", C.c_int32),
         ("t0_reinit", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("pivot_repair", C.c_int32),
         ("pivot_growth_max", C.c_double),
     ]
 

@@ -590,13 +590,15 @@ class CircuitSweep:
 # restarts a failed initialisation up to ten times with a more robust algorithm, src/dcop.jl:53-94): the failed points
 # alone are solved again as a small batch of their own, with progressively more patient options -- longer gmin / source
 # stepping ladders and a tighter Newton step limit for the operating point, plain full Newton (no rate test, no chord
-# iterations) and more iterations per step for the transient, finally backward Euler.  Points that converge on a rung
+# iterations) and more iterations per step for the transient, finally backward Euler; every rung also switches on the
+# partial-pivoting repair pass of k_lu for iterations the pivot-growth monitor flags (cb_options.pivot_repair).  Points that converge on a rung
 # replace their entries; the others keep their status code.  `retry=False` switches it off, `retry=[dict, ...]` gives
 # another ladder.
 RETRY_LADDER = (
-    dict(gmin_steps=20, source_steps=40, max_newton_dc=400, dv_max=0.25, nr_rate_test=0, value_rounds=0, max_newton_tran=50),
+    dict(gmin_steps=20, source_steps=40, max_newton_dc=400, dv_max=0.25, nr_rate_test=0, value_rounds=0, max_newton_tran=50,
+         pivot_repair=1),
     dict(gmin_steps=20, source_steps=100, max_newton_dc=1000, dv_max=0.1, nr_rate_test=0, value_rounds=0, max_newton_tran=100,
-         method=0),
+         method=0, pivot_repair=1),
 )
 
 

@@ -61,7 +61,7 @@ mutable struct cb_options
     mixed_rounds::Int32
     source_steps::Int32
     t0_reinit::Int32
-    reserved_::Int32
+    pivot_repair::Int32
     pivot_growth_max::Cdouble
     cb_options() = new()
 end

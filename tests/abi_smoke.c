@@ -44,7 +44,7 @@ static int layout(void) {
     F(cb_options, max_newton_tran); F(cb_options, method); F(cb_options, fixed_step); F(cb_options, dt); F(cb_options, dt_min);
     F(cb_options, dt_max); F(cb_options, gmin_steps); F(cb_options, skip_dc); F(cb_options, nr_rate_test);
     F(cb_options, value_rounds); F(cb_options, mixed_rounds); F(cb_options, source_steps); F(cb_options, t0_reinit);
-    F(cb_options, reserved_); F(cb_options, pivot_growth_max);
+    F(cb_options, pivot_repair); F(cb_options, pivot_growth_max);
     S_(cb_stats); F(cb_stats, newton_iters); F(cb_stats, lu_factors); F(cb_stats, steps_accepted); F(cb_stats, steps_rejected);
     F(cb_stats, rounds); F(cb_stats, kernel_launches); F(cb_stats, solve_seconds); F(cb_stats, h2d_seconds); F(cb_stats, d2h_seconds);
     F(cb_stats, eval_seconds); F(cb_stats, newton_seconds); F(cb_stats, value_rounds); F(cb_stats, full_iters);

@@ -243,7 +243,40 @@ def test_pivot_growth_monitor_flags_instead_of_losing_accuracy(host_bsimcmg):
     plan.set_params(P)
     x, xf, st, stats = plan.dc(engine.default_options())
     assert st.max() == 0 and stats["pivot_fallbacks"] == 0
-    # an absurdly small bound: every factorisation is flagged, no point may be reported as converged
+    # an absurdly small bound: every factorisation is flagged; without the repair pass no point may be reported as converged
     x, xf, st, stats = plan.dc(engine.default_options(pivot_growth_max=1e-6, gmin_steps=2, source_steps=2, max_newton_dc=10))
     assert st.min() != 0 and stats["pivot_fallbacks"] > 0
     plan.close()
+
+
+def test_flagged_points_are_resolved_with_partial_pivoting(host_bsimcmg):
+    """The slow path behind the pivot-growth monitor (cb_options.pivot_repair, k_lu's repair pass + lu_dense_pp): with an
+    absurdly small growth bound EVERY full iteration of EVERY point is flagged and re-solved, dense, with partial
+    pivoting.  Operating points and a fixed-step transient of the 30-FET DFF (85 unknowns) must come out as from the
+    static-pivot factorisation (same Newton iterates up to rounding: 1e-9 V) and as from the CPU oracle."""
+    from cedarsim.jl_b200 import engine
+    from oracle import orc
+    import bench
+    fc, ms = circuits.dff(host=host_bsimcmg)
+    B = 40                                  # two groups, the second one partly filled
+    P = np.ascontiguousarray(circuits.dff_mc_params(fc, 64)[:, :B])
+    x0 = x0_from(fc, bench.DFF_NODESET)
+    ts = np.linspace(0.0, 4e-9, 41)
+    kw = dict(fixed_step=1, dt=25e-12)
+    plan = engine.Circuit(fc, ms).plan(B)
+    plan.set_params(P)
+    plan.set_x0(x0)
+    xa, xfa, sa, _ = plan.dc(engine.default_options())
+    xb, xfb, sb, stb = plan.dc(engine.default_options(pivot_growth_max=1e-6, pivot_repair=1))
+    assert sa.max() == 0 and sb.max() == 0 and stb["pivot_fallbacks"] >= B
+    assert np.abs(xfa[:fc.n_nodes] - xfb[:fc.n_nodes]).max() < 1e-9
+    ya, sta, _ = plan.tran(0.0, 4e-9, ts, engine.default_options(**kw))
+    yb, stb_, stats = plan.tran(0.0, 4e-9, ts, engine.default_options(pivot_growth_max=1e-6, pivot_repair=1, value_rounds=2, **kw))   # chord iterations asked for:
+    plan.close()                                                                                               # rescued points must stay on full ones
+    assert sta.max() == 0 and stb_.max() == 0
+    assert np.all(np.abs(ya - yb) <= 1e-6 * np.abs(ya) + 1e-9), np.abs(ya - yb).max()
+    assert stats["pivot_fallbacks"] > 0 and stats["full_iters"] == stats["newton_iters"]
+    orc.set_x0(x0)
+    yo, so, _ = orc.tran(fc, 0.0, 4e-9, ts, params=P, opts=orc.default_options(**kw), nthreads=8)
+    orc.set_x0(None)
+    assert so.max() == 0 and np.all(np.abs(yb - yo) <= 1e-6 * np.abs(yo) + 1e-9)
