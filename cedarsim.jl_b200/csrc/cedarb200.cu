@@ -1488,7 +1488,7 @@ struct VaArgsH {
     long long B; const double* x; const double* alpha; const int* list; const double* cache; double* out;
     const int* term; const double* params; const double* par_val; const int* par_col; const uint8_t* given;
     double temp_val; double gmin_val; int temp_col; int gmin_col; const int* count;
-    double* uni; int uni_per_inst; int pad_;
+    double* uni; int uni_per_inst; int want; const int* active;
 };
 
 // which point list a device-evaluation launch runs over: this round's full-iteration or value-only points
@@ -1505,7 +1505,8 @@ static void fill_va_args(cb_plan* p, size_t m, const cb_options* opt, void* out_
     a->temp_val = opt->temp.value; a->gmin_val = opt->gmin.value;
     a->temp_col = opt->temp.col; a->gmin_col = opt->gmin.col;
     a->uni = p->d_uni[value_only ? 1 : 0][m];
-    a->uni_per_inst = (opt->temp.col >= 0 || opt->gmin.col >= 0) ? 1 : 0; a->pad_ = 0;
+    a->uni_per_inst = (opt->temp.col >= 0 || opt->gmin.col >= 0) ? 1 : 0;
+    a->want = 0; a->active = nullptr;   // list mode (solve() switches its launches to blocked mode for small batches)
 }
 
 // (the repairable variant, k_lu<., ., true>, when the arguments carry a repair scratch: cb_options.pivot_repair)
@@ -1735,6 +1736,12 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
     // ncu_lu_fused_r2v.json -- see DESIGN.md section 4; CB_FUSE=1 selects it)
     bool fused = false;
     if (const char* e = std::getenv("CB_FUSE")) fused = p->lu && std::atoi(e) != 0;
+    // Blocked mode of the fused kernel for SMALL batches (kernels.cuh, k_lu): no point lists, group = 32 consecutive points,
+    // control step as the tail of the solve.  While the whole GPU runs at most 4 096 points every k_lu launch is under one
+    // wave of CTAs whatever the participation, and the k_control launch it saves is a fifth of a latency-bound round.
+    bool blocked = p->lu && std::max(B, p->device_points) <= 4096 && !timing && !opt->pivot_repair;   // (the repair pass lives in the list-based kernel)
+    if (const char* e = std::getenv("CB_BLOCKED")) blocked = p->lu && std::atoi(e) != 0 && !opt->pivot_repair;
+    if (blocked) fused = true;
     // Round r reads list buffer r % 3 and fills buffer (r + 1) % 3; its k_lu zeroes the counters of the buffer that is
     // filled next: (r + 1) % 3 when k_control fills it after k_lu, (r + 2) % 3 when k_lu fills (r + 1) % 3 itself.
     CArgs cargs[CB_NBUF];
@@ -1743,6 +1750,11 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
         for (size_t m = 0; m < c->models.size(); m++) {
             fill_va_args(p, m, opt, vargs(par, m), false, par);
             if (use_v) fill_va_args(p, m, opt, vargs_v(par, m), true, par);
+            if (blocked) {
+                VaArgsH* va = (VaArgsH*)vargs(par, m);
+                va->list = nullptr; va->active = a.active; va->want = ACT_FULL;
+                if (use_v) { va = (VaArgsH*)vargs_v(par, m); va->list = nullptr; va->active = a.active; va->want = ACT_ANY; }
+            }
         }
         const int nxt = (par + 1) % CB_NBUF, nxt2 = (par + 2) % CB_NBUF;
         int* lists_next = p->d_lists + (size_t)nxt * 3 * B;
@@ -1757,6 +1769,8 @@ static int solve(cb_plan* p, const cb_options* opt, bool dc_only, double t0, dou
                                p->d_cnt + par * 4};
         largs[par].zero_cnt = p->d_cnt + (fused ? nxt2 : nxt) * 4;
         largs[par].k = cargs[par].k;
+        largs[par].blocked = blocked ? 1 : 0;
+        if (blocked) largs[par].k.next_cnt = nullptr;   // no lists: a.active[] carries the roles
         largs[par].growth_max = opt->pivot_growth_max > 0.0 ? opt->pivot_growth_max : 1e300;
         largs[par].pp_scratch = (opt->pivot_repair && !fused) ? p->d_pp_scratch : nullptr;
     }

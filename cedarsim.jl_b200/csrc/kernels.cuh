@@ -615,6 +615,7 @@ __device__ __forceinline__ void control_points(const NArgs& a, const CtlArgs& c,
         const unsigned bf = __ballot_sync(0xffffffffu, role == ACT_FULL), ba = __ballot_sync(0xffffffffu, role == ACT_ANY);
         const unsigned bi = FUSED ? __ballot_sync(0xffffffffu, role == ACT_IDLE) : 0u;
         int basef = 0, basea = 0, basei = 0;
+        if (FUSED && !c.next_cnt) return;   // blocked mode: a.active[] is all the next round needs
         if (pt == 0) {
             if (bf) basef = atomicAdd(c.next_cnt + 0, __popc(bf));
             if (ba) basea = atomicAdd(c.next_cnt + 1, __popc(ba));
@@ -714,6 +715,7 @@ struct LArgs {
     double growth_max;        // pivot-growth bound: an elimination multiplier above it flags the point (BAD bit 1)
     CtlArgs k;                // the control step, when it is fused into this kernel (k_lu<.., true>)
     double* pp_scratch;       // [gridDim.x][N (N + 1)] dense system of the point being re-solved with partial pivoting, or null
+    int blocked, pad3_;       // fused kernel only: 1 = no point lists at all, group g = sweep points [32 g, 32 g + 32), see k_lu
     const u16 *e_row, *e_col; // per LU entry: elimination step of its row / of its column (repair pass only; global memory)
 };
 
@@ -1077,7 +1079,7 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const __grid_cons
     if (blockIdx.x == 0 && threadIdx.x < 3) c.zero_cnt[threadIdx.x] = 0;
     const int nf = c.cur.cnt[0], na = c.cur.cnt[1], ni = FUSED ? c.cur.cnt[2] : 0;
     const int gf = (nf + LU_PTS - 1) / LU_PTS, ga = (na + LU_PTS - 1) / LU_PTS, gi = (ni + LU_PTS - 1) / LU_PTS;
-    if ((int)blockIdx.x >= gf + ga + gi) return;
+    if (!(FUSED && c.blocked) && (int)blockIdx.x >= gf + ga + gi) return;
     const unsigned char* tb = c.tab;
     if (STAGED) {
         unsigned char* st = (unsigned char*)(vals_ + (size_t)(c.n.nnz_lu + 2 * c.n.N) * LU_PTS);
@@ -1085,6 +1087,42 @@ __global__ void __launch_bounds__(LU_PTS * LU_W, LU_MINB) k_lu(const __grid_cons
         for (int k = threadIdx.x; k < c.t.bytes / 16; k += LU_PTS * LU_W) ((int4*)st)[k] = __ldg(src + k);
         tb = st;
         __syncthreads();
+    }
+    if (FUSED && c.blocked) {
+        // Blocked mode (small batches, where a round is latency-bound and the launch of a separate control kernel is a
+        // fifth of it): no point lists.  Group g IS the block of sweep points [32 g, 32 g + 32): every access is a run of
+        // consecutive points whatever the participation (which is what the list-based fused mode loses), lanes whose
+        // point takes no part in this kind of iteration shadow along without storing, and the control step of the block
+        // runs as the tail of its solve.  Costs a value-only round the groups it could have skipped -- nothing while the
+        // whole batch is under one wave of CTAs.
+        const long long Bn = c.n.B;
+        const int nblk = (int)((Bn + LU_PTS - 1) / LU_PTS);
+        for (int g = blockIdx.x; g < nblk; g += gridDim.x) {
+            const long long k = (long long)g * LU_PTS + lane;
+            const bool inb = k < Bn;
+            const long long inst = inb ? k : Bn - 1;
+            const int act = inb ? c.n.active[inst] : ACT_DONE;
+            const int any_f = __syncthreads_or(act == ACT_FULL), any_a = __syncthreads_or(act == ACT_ANY);
+            const int any_i = __syncthreads_or(act == ACT_IDLE);
+            if (!(any_f | any_a | any_i)) continue;
+            for (int kind = 0; kind < 3; kind++) {
+                if (kind == 0 ? !any_f : (kind == 1 ? !any_a : (any_f | any_a) != 0)) continue;   // kind 2: a block of idle points only
+                const bool last = kind == 2 || (kind == 1) || !any_a;
+                const bool on = kind < 2 && act == (kind == 0 ? ACT_FULL : ACT_ANY);
+                if (w == 0) { s_ctl[0][lane] = 0ull; s_ctl[1][lane] = 0ull; }
+                if (kind == 0) lu_group<false, true, false, false>(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
+                else if (kind == 1) lu_group<true, true, false, false>(c, vals_, tb, s_red, s_bad, inst, on, lane, w, s_redo, s_pi, s_pv);
+                else __syncthreads();
+                const int act_eff = on ? act : ((last && act == ACT_IDLE) ? ACT_IDLE : ACT_DONE);
+                const double rmax = on ? __longlong_as_double((long long)s_red[0][lane]) : 0.0;
+                const double dvmax = on ? __longlong_as_double((long long)s_red[1][lane]) : 0.0;
+                const int bad = on ? s_bad[lane] : 0;
+                control_points<LU_W, true>(c.n, c.k, inst, act_eff != ACT_DONE, act_eff, lane, w, s_ctl, nullptr, nullptr, rmax, dvmax, bad,
+                                           vals_ + lane, (const u16*)(tb + c.t.col_to_step), c.n.nnz_lu);
+                __syncthreads();
+            }
+        }
+        return;
     }
     for (int g = blockIdx.x; g < gf + ga + gi; g += gridDim.x) {
         const int kind = g < gf ? 0 : (g < gf + ga ? 1 : 2);

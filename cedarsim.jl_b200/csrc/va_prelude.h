@@ -30,7 +30,9 @@ struct VaArgs {
                                  // CTAs beyond the count exit at once)
     double* uni;                 // [NUNI] cached values that are the same for every device of the model (they depend on the
                                  // model card, temperature and gmin only), or [B][NUNI] when temperature / gmin are swept
-    int uni_per_inst; int pad_;
+    int uni_per_inst;
+    int want;                    // blocked mode (list == nullptr): thread k is sweep point k and takes part iff active[k] == want
+    const int* active;
 };
 
 // Branch-free reciprocal, square root, exp, log and pow for the eval stream.  Two reasons: (1) the compiler's own
@@ -381,8 +383,13 @@ VA_FN void va_issue(const int chunk, const int ncache, const unsigned sbase, con
         long long inst;                                                                          \
         {                                                                                        \
             const long long k_ = (long long)blockIdx.x * VA_EVAL_THREADS + threadIdx.x;          \
-            if (k_ >= (long long)*a.count) return;                                               \
-            inst = a.list[k_];                                                                   \
+            if (a.list) {                                                                        \
+                if (k_ >= (long long)*a.count) return;                                           \
+                inst = a.list[k_];                                                               \
+            } else {   /* blocked mode: no lists, the point's role decides */                    \
+                if (k_ >= a.B || a.active[k_] != a.want) return;                                 \
+                inst = k_;                                                                       \
+            }                                                                                    \
         }                                                                                        \
         const int dev = blockIdx.y;                                                              \
         const double* __restrict__ cache_ = a.cache + va_cache_index<VA_LAYOUT>(a.B, dev, NCACHE_P, inst);    \
