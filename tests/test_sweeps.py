@@ -148,3 +148,59 @@ def test_empty_sweep_is_refused():   # src/sweeps.jl:414-417: the circuit is com
     from cedarsim.jl_b200.sweeps import CircuitSweep
     with pytest.raises(ValueError, match="empty sweep"):
         CircuitSweep("* r\nv1 a 0 1\nr1 a 0 1k\n", Sweep("r1.r", np.array([])))
+
+
+def test_retry_ladder_host_logic_with_a_fake_engine():
+    """sweeps._retry_failed (host retry policy) without a GPU: the unconverged points alone are handed
+    to a new small plan with the ladder's options, points that converge there replace their entries, the others keep
+    their status, converged points are never touched; the sub-batch gets the failed points' parameter columns / nodeset."""
+    from cedarsim.jl_b200 import sweeps as S
+
+    calls = []
+
+    class FakePlan:
+        def __init__(self, n):
+            self.n = n
+        def set_params(self, P):
+            self.P = P
+        def set_x0(self, x0):
+            self.x0 = x0
+        def close(self):
+            calls[-1]["closed"] = True
+
+    class FakeCompiled:
+        def plan(self, n, devices=None):
+            calls.append({"n": n, "devices": devices})
+            p = FakePlan(n)
+            calls[-1]["plan"] = p
+            return p
+
+    class FakeFlat:
+        params = np.arange(2 * 8, dtype=float).reshape(2, 8)
+
+    class FakeCS:
+        flat, devices, x0, _compiled = FakeFlat(), [3], np.arange(5 * 8, dtype=float).reshape(5, 8), FakeCompiled()
+        def _options(self, kw):
+            return dict(kw)
+
+    y = np.zeros((2, 8))
+    status = np.array([0, 1, 0, 2, 0, 0, 4, 0], dtype=np.int32)
+    stats = {}
+
+    def solve(plan, opts):      # rung 1 rescues the first failed point only, rung 2 the last one
+        rung = 1 if opts["source_steps"] == 40 else 2
+        st = np.ones(plan.n, dtype=np.int32)
+        st[0 if rung == 1 else -1] = 0
+        return np.full((2, plan.n), 10.0 * rung) + plan.P[:1], st
+
+    S._retry_failed(FakeCS(), dict(reltol=1e-3), True, solve, y, status, stats, point_axis=1)
+    assert [c["n"] for c in calls] == [3, 2] and all(c["devices"] == [3] and c["closed"] for c in calls)
+    assert np.array_equal(calls[0]["plan"].P, FakeFlat.params[:, [1, 3, 6]]) and np.array_equal(calls[0]["plan"].x0, FakeCS.x0[:, [1, 3, 6]])
+    assert np.array_equal(calls[1]["plan"].P, FakeFlat.params[:, [3, 6]])
+    assert status.tolist() == [0, 0, 0, 2, 0, 0, 0, 0]                       # point 3 stays InitialFailure
+    assert y[0].tolist() == [0, 10.0 + 1, 0, 0, 0, 0, 20.0 + 6, 0]          # rescued entries only
+    assert stats == {"retried_points": 3, "recovered_points": 2}
+    # retry=False-like: an empty ladder does nothing
+    calls.clear()
+    S._retry_failed(FakeCS(), {}, (), solve, y, status, stats, point_axis=1)
+    assert not calls
